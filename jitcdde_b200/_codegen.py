@@ -1,0 +1,337 @@
+"""
+Code generation: SymPy expressions of a DDE's right-hand side → one block of
+C statements in a small macro vocabulary.
+
+This replaces the reference's `compile_C` code path
+(/root/reference/jitcdde/_jitcdde.py:420-575), which prints one
+`set_dy(i, …)` statement per component through SymEngine's C printer into `f.c`
+/ `helpers.c` and binds them to the C core with the macros at
+/root/reference/jitcdde/jitced_template.c:382-391.
+
+Here the *same token stream* is consumed by three back-ends, each of which only
+defines the macros differently:
+
+  * the CUDA engine (`csrc/jdde_engine.cuh`) — the product,
+  * the plain-C restatement in `oracle/dde_oracle.c`              — test oracle,
+  * the reference's own `jitced_template.c`, compiled unmodified
+    by `oracle/build_ref.py` into `oracle/_ref/`                  — test oracle.
+
+Feeding all three from one printer keeps the association order of every
+floating-point expression identical, which is what makes bit-for-bit comparison
+of step sequences possible (SURVEY.md §7 "hard parts" 1).
+
+Vocabulary (all macros):
+  JDDE_Y(i)                 current state component            (reference: current_y)
+  JDDE_PAR(k)               k-th control parameter             (reference: self->parameter_<name>)
+  JDDE_SEG                  type of an anchor-pair handle      (reference: anchor *)
+  JDDE_ANCHORS(k, time)     bracket search at lookup site k    (reference: anchors → get_past_anchors)
+  JDDE_PAST_Y(time, i, s)   cubic Hermite value                (reference: past_y  → get_past_value)
+  JDDE_PAST_DY(time, i, s)  cubic Hermite derivative           (reference: past_dy → get_past_diff)
+  JDDE_SET_DY(i, value)     store derivative component         (reference: set_dy)
+  JDDE_IPOW(x, e)           x**e for a literal integer e as a fixed multiplication chain
+
+Lookup sites: the reference gives every textual `anchors(…)` call its own
+search cursor (`anchor_mem`, jitced_template.c:44-45, 193-217;
+`past_calls`, _jitcdde.py:508-517). Two call sites with the same argument
+expression see the same sequence of times from the same initial cursor, so
+their cursors and results are always identical; merging them (which common
+subexpression elimination does here) changes no result.
+"""
+
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass, field
+
+import sympy
+from sympy.printing.c import C99CodePrinter
+
+from ._symbols import anchors, current_y, past_dy, past_y, t
+
+_MAX_IPOW = 64
+
+
+class _MacroPrinter(C99CodePrinter):
+	"""Prints SymPy expressions in the JDDE_* macro vocabulary."""
+
+	def __init__(self, par_index, seg_symbols, literal_pow=False):
+		super().__init__({"allow_unknown_functions": True})
+		self.par_index = par_index
+		self.seg_symbols = seg_symbols
+		self.literal_pow = literal_pow
+		self.n_sites = 0
+
+	def _print_Symbol(self, expr):
+		if expr in self.par_index:
+			return f"JDDE_PAR({self.par_index[expr]})"
+		return super()._print_Symbol(expr)
+
+	def _print_AppliedUndef(self, expr):
+		# SymPy's dispatcher skips the concrete class of undefined functions
+		handler = getattr(self, "_print_" + type(expr).__name__, None)
+		if handler is None:
+			return self._print_Function(expr)
+		return handler(expr)
+
+	def _print_current_y(self, expr):
+		return f"JDDE_Y({self._print(expr.args[0])})"
+
+	def _print_past_y(self, expr):
+		tm, i, seg = expr.args
+		return f"JDDE_PAST_Y({self._print(tm)}, {self._print(i)}, {self._print(seg)})"
+
+	def _print_past_dy(self, expr):
+		tm, i, seg = expr.args
+		return f"JDDE_PAST_DY({self._print(tm)}, {self._print(i)}, {self._print(seg)})"
+
+	def _print_anchors(self, expr):
+		site = self.n_sites
+		self.n_sites += 1
+		return f"JDDE_ANCHORS({site}, {self._print(expr.args[0])})"
+
+	def _print_Pow(self, expr):
+		base, exp = expr.args
+		if not self.literal_pow and exp.is_Integer and 0 < abs(int(exp)) <= _MAX_IPOW and int(exp) != 1:
+			e = int(exp)
+			core = f"JDDE_IPOW({self._print(base)}, {abs(e)})"
+			return core if e > 0 else f"(1.0/{core})"
+		return super()._print_Pow(expr)
+
+
+@dataclass
+class RHSProgram:
+	"""Result of code generation for one DDE."""
+	n: int
+	param_names: list
+	n_sites: int
+	body: str                      # statements in the JDDE_* vocabulary
+	uses_past_dy: bool
+	literal_f: list = field(default_factory=list)   # one reference-style `set_dy(i, …)` per component, no CSE, libm pow
+	literal_sites: int = 0
+
+	@property
+	def n_params(self):
+		return len(self.param_names)
+
+	@property
+	def key(self):
+		h = hashlib.sha256()
+		h.update(repr((self.n, self.param_names, self.n_sites)).encode())
+		h.update(self.body.encode())
+		return h.hexdigest()[:16]
+
+
+def _substitute_helpers(exprs, helpers):
+	"""Inline helpers (symbol, expression) into the expressions. Helpers may
+	depend on earlier helpers; substitute until no helper symbol is left
+	(the reference sorts them topologically, _jitcdde.py:207)."""
+	if not helpers:
+		return exprs
+	subs = {sympy.sympify(s): sympy.sympify(e) for s, e in helpers}
+	symbols = set(subs)
+	out = []
+	for expr in exprs:
+		for _ in range(len(subs)+1):
+			if not (expr.free_symbols & symbols):
+				break
+			expr = expr.xreplace(subs)
+		else:
+			raise ValueError("Helpers depend on each other cyclically.")
+		out.append(expr)
+	return out
+
+
+def _to_plain_functions(expr):
+	"""Map symbols that came from another package's flavour (e.g. a user's own
+	`sympy.Function("current_y")`) onto ours by name."""
+	ours = {f.__name__: f for f in (current_y, past_y, past_dy, anchors)}
+	repl = {}
+	for f in expr.atoms(sympy.Function):
+		name = type(f).__name__
+		if name in ours and type(f) is not ours[name]:
+			repl[f] = ours[name](*f.args)
+	for s in expr.free_symbols:
+		if s.name == "t" and s != t:
+			repl[s] = t
+	return expr.xreplace(repl) if repl else expr
+
+
+def generate(f_sym, helpers=(), control_pars=(), simplify=False, do_cse=True):
+	"""
+	f_sym: list of expressions (component i = dy_i/dt), helpers: list of
+	(symbol, expression) incl. anchor helpers, control_pars: list of symbols.
+	"""
+	control_pars = [sympy.sympify(p) for p in control_pars]
+	exprs = [_to_plain_functions(sympy.sympify(e)) for e in f_sym]
+	helpers = [(sympy.sympify(s), _to_plain_functions(sympy.sympify(e))) for s, e in helpers]
+	exprs = _substitute_helpers(exprs, helpers)
+	if simplify:
+		exprs = [sympy.simplify(e, ratio=1.0) for e in exprs]
+	n = len(exprs)
+
+	allowed = {t, *control_pars}
+	for i, e in enumerate(exprs):
+		bad = e.free_symbols - allowed
+		if bad:
+			raise ValueError(f"Invalid symbol ({sorted(s.name for s in bad)}) in equation {i}.")
+
+	par_index = {p: k for k, p in enumerate(control_pars)}
+
+	# literal flavour: what the reference would emit (no CSE, libm pow)
+	lit = _LiteralPrinter(par_index)
+	literal_f = [f"set_dy({i}, {lit.doprint(e)});" for i, e in enumerate(exprs)]
+
+	if do_cse:
+		replacements, reduced = sympy.cse(exprs, symbols=sympy.numbered_symbols("x"), order="none")
+	else:
+		replacements, reduced = [], list(exprs)
+	# every distinct anchors(...) must become a named temporary so that it is
+	# evaluated exactly once per RHS evaluation
+	replacements, reduced = _hoist_anchors(replacements, reduced)
+
+	seg_symbols = {s for s, e in replacements if e.func == anchors}
+	printer = _MacroPrinter(par_index, seg_symbols)
+	lines = []
+	for s, e in replacements:
+		if e.func == anchors:
+			lines.append(f"JDDE_SEG {s.name} = {printer.doprint(e)};")
+		else:
+			lines.append(f"const double {s.name} = {printer.doprint(e)};")
+	for i, e in enumerate(reduced):
+		lines.append(f"JDDE_SET_DY({i}, {printer.doprint(e)});")
+	body = "\n".join(lines) + "\n"
+
+	uses_past_dy = any(e.has(past_dy) for e in exprs)
+	return RHSProgram(
+		n=n,
+		param_names=[p.name for p in control_pars],
+		n_sites=printer.n_sites,
+		body=body,
+		uses_past_dy=uses_past_dy,
+		literal_f=literal_f,
+		literal_sites=lit.n_sites,
+	)
+
+
+def _hoist_anchors(replacements, reduced):
+	"""Make every anchors(arg) call a statement of its own (`y0 = anchors(arg)`),
+	placed right before its first use, and merge calls with identical argument."""
+	out = []
+	seg_of = {}          # anchors(arg) expression -> symbol
+	counter = [0]
+
+	def hoist(expr):
+		calls = sorted(expr.atoms(anchors), key=sympy.default_sort_key)
+		# inner-most first (nested delays)
+		changed = True
+		while changed:
+			changed = False
+			for call in sorted(expr.atoms(anchors), key=lambda c: c.count_ops()):
+				arg = call.args[0]
+				if arg.has(anchors):
+					continue
+				if call not in seg_of:
+					sym = sympy.Symbol(f"s{counter[0]}")
+					counter[0] += 1
+					seg_of[call] = sym
+					out.append((sym, call))
+				expr = expr.xreplace({call: seg_of[call]})
+				changed = True
+				break
+		del calls
+		return expr
+
+	for s, e in replacements:
+		if e.func == anchors and not e.args[0].has(anchors):
+			if e in seg_of:
+				# same lookup already hoisted under another name: alias it
+				out.append((s, seg_of[e]))
+			else:
+				seg_of[e] = s
+				out.append((s, e))
+			continue
+		out.append((s, hoist(e)))
+	new_reduced = [hoist(e) for e in reduced]
+	# aliases `s = other_symbol` are removed by substitution
+	alias = {s: e for s, e in out if isinstance(e, sympy.Symbol)}
+	if alias:
+		out = [(s, e.xreplace(alias)) for s, e in out if s not in alias]
+		new_reduced = [e.xreplace(alias) for e in new_reduced]
+	return out, new_reduced
+
+
+class _LiteralPrinter(C99CodePrinter):
+	"""Reference vocabulary (jitced_template.c:382-391), no CSE, `pow` for all powers."""
+
+	def __init__(self, par_index):
+		super().__init__({"allow_unknown_functions": True})
+		self.par_names = {p: f"self->parameter_{p.name}" for p in par_index}
+		self.n_sites = 0
+
+	def _print_Symbol(self, expr):
+		if expr in self.par_names:
+			return self.par_names[expr]
+		return super()._print_Symbol(expr)
+
+	def _print_AppliedUndef(self, expr):
+		if type(expr).__name__ == "anchors":
+			return self._print_anchors(expr)
+		return self._print_Function(expr)
+
+	def _print_anchors(self, expr):
+		self.n_sites += 1
+		return f"anchors({self._print(expr.args[0])})"
+
+
+# ---------------------------------------------------------------------------
+# Tangent-vector system for Lyapunov exponents
+# ---------------------------------------------------------------------------
+
+def get_delays(exprs, helpers=()):
+	"""[0, *delays] with delay = t − argument of every anchors(...) call
+	(/root/reference/jitcdde/_jitcdde.py:60-67)."""
+	terms = set()
+	for e in list(exprs) + [h[1] for h in helpers]:
+		e = _to_plain_functions(sympy.sympify(e))
+		terms.update(call.args[0] for call in e.atoms(anchors))
+	delays = [sympy.simplify(t - term) for term in sorted(terms, key=sympy.default_sort_key)]
+	return [0, *delays]
+
+
+def tangent_vector_f(f_basic, helpers, n, n_lyap, delays, simplify=True):
+	"""
+	Extended system (main dynamics + n_lyap tangent vectors), following
+	/root/reference/jitcdde/_jitcdde.py:1046-1089: for exponent i and component
+	c the derivative is Σ_delays Σ_k ∂f_c/∂y_k(t−δ) · y_{k+(i+1)n}(t−δ).
+	"""
+	from ._symbols import y
+	f_basic = [_to_plain_functions(sympy.sympify(e)) for e in f_basic]
+	helpers = [(sympy.sympify(s), _to_plain_functions(sympy.sympify(e))) for s, e in helpers]
+	f_basic = _substitute_helpers(f_basic, helpers)
+
+	jacs = []   # jacs[d][c][k]
+	for delay in delays:
+		rows = []
+		for entry in f_basic:
+			row = []
+			for k in range(n):
+				var = y(k, t - delay)
+				dummy = sympy.Dummy()
+				d = entry.xreplace({var: dummy}).diff(dummy).xreplace({dummy: var})
+				if simplify:
+					d = sympy.simplify(d)
+				row.append(d)
+			rows.append(row)
+		jacs.append(rows)
+
+	out = list(f_basic)
+	for i in range(n_lyap):
+		for c in range(n):
+			expression = sympy.Integer(0)
+			for delay, jac in zip(delays, jacs, strict=True):
+				for k, entry in enumerate(jac[c]):
+					expression += entry * y(k + (i+1)*n, t - delay)
+			if simplify:
+				expression = sympy.simplify(expression, ratio=1.0)
+			out.append(expression)
+	return out

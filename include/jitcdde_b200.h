@@ -1,0 +1,185 @@
+/*
+ * jitcdde_b200.h — C ABI of the B200 DDE integration engine (libjitcdde_b200.so).
+ *
+ * Boundary. The reference (neurophysik/jitcdde) crosses from Python into native
+ * code through a generated CPython extension type `dde_integrator`
+ * (/root/reference/jitcdde/jitced_template.c:1183-1232), 5–7 calls per integration
+ * step (/root/reference/jitcdde/_jitcdde.py:830-861). Those calls cannot cross a
+ * PCIe boundary per step, so the boundary sits one level higher: every entry point
+ * below is a whole-ensemble operation with the meaning of one method of the
+ * reference's Python class `jitcdde` / `jitcdde_lyap`
+ * (/root/reference/jitcdde/_jitcdde.py); the per-step methods of `dde_integrator`
+ * it absorbs are listed with each function.
+ *
+ * Conventions
+ *   - plain C, no CUDA or torch types; all buffers are caller-owned HOST memory,
+ *     C-contiguous, float64 / int32 / int64. The handle owns device memory and
+ *     the stream.
+ *   - an ensemble has n_members independent trajectories ("members") of the same
+ *     n-dimensional DDE; arrays with a member axis are [n_members][...].
+ *     `per_member = 0` broadcasts one value to all members.
+ *   - every function returns 0 on success or a JDDE_E_* code; jdde_last_error()
+ *     gives the text. Integration problems of single members are not errors of
+ *     the call: they are reported in `status[member]` (JDDE_STATUS_*), the
+ *     ensemble counterpart of the reference raising UnsuccessfulIntegration
+ *     (_jitcdde.py:135-139, 745-765).
+ *   - output pointers may be NULL: the result then stays in device memory and the
+ *     call returns without synchronising (see jdde_synchronize).
+ *   - a handle is not thread-safe. There is no CPU fallback: without a CUDA
+ *     device jdde_create fails with JDDE_E_CUDA.
+ */
+#ifndef JITCDDE_B200_H
+#define JITCDDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JDDE_ABI_VERSION 1
+
+/* return codes */
+#define JDDE_OK            0
+#define JDDE_E_INVALID     1   /* bad argument / wrong call order */
+#define JDDE_E_CUDA        2   /* CUDA runtime error (text in jdde_last_error) */
+#define JDDE_E_IMAGE       3   /* kernel image does not match the descriptor */
+#define JDDE_E_NOMEM       4
+
+/* per-member status */
+#define JDDE_STATUS_OK         0
+#define JDDE_STATUS_MIN_STEP   1   /* dt < min_step: the reference raises UnsuccessfulIntegration (_jitcdde.py:745-765) */
+#define JDDE_STATUS_OVERFLOW   2   /* anchor ring full; call jdde_grow_ring and repeat the call */
+#define JDDE_STATUS_NONFINITE  3   /* state became NaN/inf */
+#define JDDE_STATUS_BACKWARDS  4   /* integrate_blindly with target < t (reference: ValueError, _jitcdde.py:897) */
+#define JDDE_STATUS_BUDGET     5   /* more attempted steps in one call than jdde_set_attempt_budget allows (kernel watchdog) */
+
+typedef struct jdde_handle jdde_handle;
+
+/* What the generated kernel image was compiled for (cf. the Jinja2 variables the
+ * reference renders its template with, _jitcdde.py:562-573). */
+typedef struct jdde_desc
+{
+	int32_t n;              /* dimension incl. tangent vectors                         */
+	int32_t n_basic;        /* dimension of the DDE proper (n_basic == n: no Lyapunov)  */
+	int32_t n_sites;        /* distinct anchors(...) lookup sites (anchor_mem_length)   */
+	int32_t n_params;       /* control parameters (control_pars)                        */
+	int32_t ring_capacity;  /* anchors kept per member, power of two >= 4               */
+	int32_t device;         /* CUDA device ordinal                                      */
+	int64_t n_members;      /* ensemble size on this device                             */
+} jdde_desc;
+
+/* set_integration_parameters, _jitcdde.py:621-638 (same names, same defaults on the Python side).
+ * pws_fuzzy_increase (RNG-driven step-size increase) is not supported; the deterministic
+ * credit rule (_jitcdde.py:733-741) is always used. */
+typedef struct jdde_int_params
+{
+	double atol, rtol, first_step, min_step, max_step;
+	double decrease_threshold, increase_threshold, safety_factor, max_factor, min_factor;
+	double pws_factor, pws_atol, pws_rtol, pws_base_increase_chance;
+	int32_t pws_max_iterations;
+	int32_t reserved;
+} jdde_int_params;
+
+/* ---- life cycle ------------------------------------------------------------------- */
+
+/* Replaces dde_integrator_init (jitced_template.c:608-652) minus the past, which is set separately. */
+int jdde_create(const jdde_desc * desc, jdde_handle ** out);
+int jdde_destroy(jdde_handle * h);                        /* dde_integrator_dealloc, :563-573 */
+const char * jdde_last_error(const jdde_handle * h);      /* h may be NULL: error of the last failed jdde_create */
+
+/* Load the kernels generated for this DDE (a cubin for sm_100a produced by
+ * jitcdde_b200/_build.py from csrc/jdde_kernels.cuh + the generated right-hand side).
+ * Replaces _compile_and_load / module import (_jitcdde.py:575, 585-588). */
+int jdde_load_rhs(jdde_handle * h, const void * image, size_t len);
+
+/* Use a caller-provided CUDA stream (a cudaStream_t passed as void*), e.g. torch's
+ * current stream, so that callers can bracket calls with their own events. */
+int jdde_set_stream(jdde_handle * h, void * cuda_stream);
+int jdde_synchronize(jdde_handle * h);
+
+/* ---- definition of the problem ----------------------------------------------------- */
+
+/* Initial past as anchors (time, state[n], diff[n]), n_anchors >= 2; resets integration progress.
+ * times[n_anchors], states[n_anchors][n], diffs[n_anchors][n]; with per_member each has a leading
+ * member axis. Replaces initiate_past_from_list (jitced_template.c:575-606) as driven by
+ * add_past_point(s) / constant_past (_jitcdde.py:282-324). */
+int jdde_set_past(jdde_handle * h, int32_t n_anchors, const double * times, const double * states, const double * diffs, int32_t per_member);
+
+/* params[n_params] or [n_members][n_params]. set_parameters, jitced_template.c:167-185, _jitcdde.py:594-614. */
+int jdde_set_parameters(jdde_handle * h, const double * params, int32_t per_member);
+
+/* Also resets the step size to first_step and the past-within-step memory, as the reference does
+ * (_jitcdde.py:710-728). max_delay is the `forget` horizon (_jitcdde.py:835). */
+int jdde_set_integration_parameters(jdde_handle * h, const jdde_int_params * p, double max_delay);
+
+/* ---- integration -------------------------------------------------------------------- */
+
+/* jitcdde.integrate (_jitcdde.py:807-836): adaptive steps until t >= target, state at target by
+ * Hermite interpolation of the last step, then forget(max_delay). Absorbs get_t, get_next_step,
+ * past_within_step, get_p, check_new_y_diff, accept_step, get_recent_state, forget
+ * (jitced_template.c:187, 421, 474, 502, 526, 287, 534) and try_single_step / _adjust_step_size
+ * (_jitcdde.py:775-861). target: 1 value or [n_members]; out_state [n_members][n]; status [n_members]. */
+int jdde_integrate(jdde_handle * h, const double * target, int32_t per_member, double * out_state, int32_t * status);
+
+/* step_on_discontinuities (_jitcdde.py:985-997): for each of the n_steps sorted step lengths,
+ * adaptive steps capped so that one lands on t + step; steps [n_steps] or [n_members][n_steps]
+ * (the host side computes them with _propagate_delays, :75-86). */
+int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double * steps, int32_t per_member, double * out_state, int32_t * status);
+
+/* integrate_blindly (_jitcdde.py:880-933): fixed steps, no error control; step <= 0 means max_step.
+ * target == t performs adjust_diff() as the reference does. out_state = state of the last anchor. */
+int jdde_integrate_blindly(jdde_handle * h, const double * target, int32_t per_member, double step, double * out_state, int32_t * status);
+
+/* jump (_jitcdde.py:1002-1044) → apply_jump, truncate_past, extrema (jitced_template.c:1122-1174,
+ * 1089-1108, 253-285). amplitude [n] or [n_members][n]; time 1 value or [n_members];
+ * minima/maxima [n_members][n]. */
+int jdde_jump(jdde_handle * h, const double * amplitude, int32_t amplitude_per_member, const double * time, int32_t time_per_member, double width, int32_t forward, double * minima, double * maxima);
+
+/* adjust_diff (_jitcdde.py:863-878): zero-amplitude backward jump of width shift_ratio·(t_last − t_prev). */
+int jdde_adjust_diff(jdde_handle * h, double shift_ratio, double * minima, double * maxima);
+
+/* ---- Lyapunov exponents (n_basic < n) ------------------------------------------------- */
+
+/* orthonormalise (jitced_template.c:846-878 with :657-844): norms [n_members][n_lyap]. */
+int jdde_orthonormalise(jdde_handle * h, int32_t n_lyap, double delay, double * norms);
+
+/* jitcdde_lyap.integrate (_jitcdde.py:1141-1172): out_state [n_members][n_basic],
+ * lyaps [n_members][n_lyap] = log(norms)/delta_t (0 where delta_t == 0), delta_t [n_members]. */
+int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t per_member, double * out_state, double * lyaps, double * delta_t, int32_t * status);
+
+/* ---- inspection ----------------------------------------------------------------------- */
+
+int jdde_get_t(jdde_handle * h, double * t);                              /* get_t, jitced_template.c:187-190 */
+int jdde_get_dt(jdde_handle * h, double * dt);                            /* attribute jitcdde.dt */
+int jdde_get_current_state(jdde_handle * h, double * state);              /* get_current_state, :330-334; [n_members][n] */
+int jdde_get_status(jdde_handle * h, int32_t * status);
+/* accepted steps, rejected attempts, right-hand-side evaluations per member (the reference has no counters) */
+int jdde_get_counters(jdde_handle * h, int64_t * accepted, int64_t * rejected, int64_t * rhs_evals);
+/* Sum over members, computed on the device (for the throughput metric). */
+int jdde_sum_counters(jdde_handle * h, int64_t * accepted, int64_t * rejected, int64_t * rhs_evals);
+
+/* get_state (_jitcdde.py:357-371): forget(max_delay) for all members, then all anchors of one member.
+ * times[max_anchors], states/diffs[max_anchors][n]; *n_anchors receives the number written
+ * (or needed, if larger than max_anchors). get_full_state, jitced_template.c:336-352. */
+int jdde_get_state(jdde_handle * h, int64_t member, int32_t max_anchors, int32_t * n_anchors, double * times, double * states, double * diffs);
+
+/* Double (or more) the ring of every member, keeping all anchors, and clear JDDE_STATUS_OVERFLOW.
+ * The reference's list is unbounded (malloc per anchor, jitced_template.c:434). */
+int jdde_grow_ring(jdde_handle * h, int32_t new_capacity);
+
+/* Reset every member whose status equals `code` to JDDE_STATUS_OK (e.g. JDDE_STATUS_BUDGET to continue). */
+int jdde_clear_status(jdde_handle * h, int32_t code);
+/* Upper bound of attempted steps per member and call (default 1<<24); guards against kernels that never end. */
+int jdde_set_attempt_budget(jdde_handle * h, int64_t attempts);
+
+/* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
+int64_t jdde_launch_count(const jdde_handle * h);
+/* Device pointer of the last integration result [n_members][n] as an integer address (for zero-copy interop). */
+uint64_t jdde_device_result(const jdde_handle * h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,103 @@
+"""
+Building the native parts for sm_100a: the runtime library (C ABI,
+include/jitcdde_b200.h) and one kernel image (cubin) per right-hand side.
+
+Counterpart of the reference's `_compile_and_load` via jitcxde_common/setuptools
+(/root/reference/jitcdde/_jitcdde.py:560-575) and of `save_compiled` /
+`module_location` (:178-179): images are cached in-tree under
+jitcdde_b200/_cache/, keyed by a hash of the generated code, the engine sources
+and the compiler flags, so a parameter sweep compiles once.
+
+nvcc cross-compiles without a GPU. Everything is built for sm_100a only.
+"""
+
+import hashlib
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_PKG, "csrc")
+INCLUDE = os.path.join(os.path.dirname(_PKG), "include")
+CACHE = os.path.join(_PKG, "_cache")
+RUNTIME_LIB = os.path.join(_PKG, "libjitcdde_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+#: verification build: no FMA contraction → bit-identical with the CPU oracle (hard part 1)
+VERIFY = "verify"
+#: production build: FMA contraction allowed (nvcc default)
+FAST = "fast"
+
+
+def nvcc():
+	path = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+	if not os.path.exists(path):
+		raise RuntimeError("nvcc not found; the engine has no CPU fallback and cannot be built without the CUDA toolkit")
+	return path
+
+
+def _newer(target, sources):
+	if not os.path.exists(target):
+		return True
+	t = os.path.getmtime(target)
+	return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_runtime(force=False, verbose=False):
+	"""nvcc -shared … csrc/jdde_runtime.cu → jitcdde_b200/libjitcdde_b200.so"""
+	sources = [os.path.join(CSRC, "jdde_runtime.cu"), os.path.join(CSRC, "jdde_abi.h"), os.path.join(INCLUDE, "jitcdde_b200.h")]
+	if force or _newer(RUNTIME_LIB, sources):
+		cmd = [nvcc(), "-shared", "-Xcompiler", "-fPIC", "-O2", "-std=c++17", *ARCH, "-lineinfo",
+			sources[0], "-o", RUNTIME_LIB]
+		if verbose:
+			print(" ".join(cmd))
+		subprocess.run(cmd, check=True)
+	return RUNTIME_LIB
+
+
+def _engine_hash():
+	h = hashlib.sha256()
+	for name in ("jdde_engine.cuh", "jdde_kernels.cu", "jdde_math.h", "jdde_abi.h"):
+		with open(os.path.join(CSRC, name), "rb") as f:
+			h.update(f.read())
+	with open(os.path.join(INCLUDE, "jitcdde_b200.h"), "rb") as f:
+		h.update(f.read())
+	return h.hexdigest()[:12]
+
+
+def image_path(program, n_basic, mode, block, extra_flags=()):
+	tag = hashlib.sha256(repr((program.key, n_basic, mode, block, tuple(extra_flags), _engine_hash())).encode()).hexdigest()[:20]
+	return os.path.join(CACHE, f"jdde_{tag}.cubin")
+
+
+def build_image(program, n_basic=None, mode=FAST, block=128, extra_flags=(), force=False, verbose=False):
+	"""
+	Compile the kernel image for one generated right-hand side
+	(`program` = _codegen.RHSProgram). Returns the path of the cubin.
+	"""
+	n_basic = n_basic or program.n
+	os.makedirs(CACHE, exist_ok=True)
+	path = image_path(program, n_basic, mode, block, extra_flags)
+	if os.path.exists(path) and not force:
+		return path
+	rhs = os.path.join(CACHE, f"rhs_{program.key}.inc")
+	with open(rhs, "w") as f:
+		f.write(program.body)
+	flags = ["-O3", "-std=c++17", "-lineinfo", *ARCH]
+	if mode == VERIFY:
+		flags.append("-fmad=false")
+	elif mode != FAST:
+		raise ValueError(mode)
+	cmd = [nvcc(), "-cubin", *flags,
+		f"-DJD_N={program.n}", f"-DJD_NBASIC={n_basic}", f"-DJD_NSITES={program.n_sites}",
+		f"-DJD_NPARAMS={program.n_params}", f'-DJD_RHS_FILE="{rhs}"', f"-DJD_BLOCK={block}",
+		*extra_flags,
+		os.path.join(CSRC, "jdde_kernels.cu"), "-o", path + ".tmp"]
+	if verbose:
+		print(" ".join(cmd))
+	result = subprocess.run(cmd, capture_output=True, text=True)
+	if result.returncode:
+		raise RuntimeError(f"nvcc failed:\n{result.stderr}\ncommand: {' '.join(cmd)}")
+	os.replace(path + ".tmp", path)
+	return path

@@ -1,0 +1,290 @@
+"""
+ctypes binding of the C ABI (include/jitcdde_b200.h) — the thin layer between the
+Python drop-in classes (`_jitcdde.py`) and libjitcdde_b200.so.
+
+In the reference this place is taken by the generated CPython extension type
+`dde_integrator` (/root/reference/jitcdde/jitced_template.c:1183-1232).
+There is no fallback: if the library is missing or no CUDA device is present,
+an exception is raised.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import _build
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int32_p = ctypes.POINTER(ctypes.c_int32)
+c_int64_p = ctypes.POINTER(ctypes.c_int64)
+
+STATUS_OK, STATUS_MIN_STEP, STATUS_OVERFLOW, STATUS_NONFINITE, STATUS_BACKWARDS, STATUS_BUDGET = range(6)
+
+
+class Desc(ctypes.Structure):
+	_fields_ = [
+		("n", ctypes.c_int32), ("n_basic", ctypes.c_int32), ("n_sites", ctypes.c_int32), ("n_params", ctypes.c_int32),
+		("ring_capacity", ctypes.c_int32), ("device", ctypes.c_int32), ("n_members", ctypes.c_int64),
+	]
+
+
+class IntParams(ctypes.Structure):
+	_fields_ = [
+		("atol", ctypes.c_double), ("rtol", ctypes.c_double), ("first_step", ctypes.c_double),
+		("min_step", ctypes.c_double), ("max_step", ctypes.c_double),
+		("decrease_threshold", ctypes.c_double), ("increase_threshold", ctypes.c_double),
+		("safety_factor", ctypes.c_double), ("max_factor", ctypes.c_double), ("min_factor", ctypes.c_double),
+		("pws_factor", ctypes.c_double), ("pws_atol", ctypes.c_double), ("pws_rtol", ctypes.c_double),
+		("pws_base_increase_chance", ctypes.c_double),
+		("pws_max_iterations", ctypes.c_int32), ("reserved", ctypes.c_int32),
+	]
+
+
+#: every symbol include/jitcdde_b200.h declares, with (restype, argtypes)
+_H = ctypes.c_void_p
+SIGNATURES = {
+	"jdde_create": (ctypes.c_int, [ctypes.POINTER(Desc), ctypes.POINTER(_H)]),
+	"jdde_destroy": (ctypes.c_int, [_H]),
+	"jdde_last_error": (ctypes.c_char_p, [_H]),
+	"jdde_load_rhs": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_size_t]),
+	"jdde_set_stream": (ctypes.c_int, [_H, ctypes.c_void_p]),
+	"jdde_synchronize": (ctypes.c_int, [_H]),
+	"jdde_set_past": (ctypes.c_int, [_H, ctypes.c_int32, c_double_p, c_double_p, c_double_p, ctypes.c_int32]),
+	"jdde_set_parameters": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32]),
+	"jdde_set_integration_parameters": (ctypes.c_int, [_H, ctypes.POINTER(IntParams), ctypes.c_double]),
+	"jdde_integrate": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, c_int32_p]),
+	"jdde_step_on_discontinuities": (ctypes.c_int, [_H, ctypes.c_int32, c_double_p, ctypes.c_int32, c_double_p, c_int32_p]),
+	"jdde_integrate_blindly": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_int32_p]),
+	"jdde_jump": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, ctypes.c_int32, ctypes.c_double, ctypes.c_int32, c_double_p, c_double_p]),
+	"jdde_adjust_diff": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_double_p]),
+	"jdde_orthonormalise": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_double, c_double_p]),
+	"jdde_integrate_lyap": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, c_double_p, c_double_p, c_int32_p]),
+	"jdde_get_t": (ctypes.c_int, [_H, c_double_p]),
+	"jdde_get_dt": (ctypes.c_int, [_H, c_double_p]),
+	"jdde_get_current_state": (ctypes.c_int, [_H, c_double_p]),
+	"jdde_get_status": (ctypes.c_int, [_H, c_int32_p]),
+	"jdde_get_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
+	"jdde_sum_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
+	"jdde_get_state": (ctypes.c_int, [_H, ctypes.c_int64, ctypes.c_int32, c_int32_p, c_double_p, c_double_p, c_double_p]),
+	"jdde_grow_ring": (ctypes.c_int, [_H, ctypes.c_int32]),
+	"jdde_clear_status": (ctypes.c_int, [_H, ctypes.c_int32]),
+	"jdde_set_attempt_budget": (ctypes.c_int, [_H, ctypes.c_int64]),
+	"jdde_launch_count": (ctypes.c_int64, [_H]),
+	"jdde_device_result": (ctypes.c_uint64, [_H]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+	"""Load libjitcdde_b200.so (building it with nvcc if it is not there yet)."""
+	global _lib
+	if _lib is not None and path is None:
+		return _lib
+	path = path or _build.RUNTIME_LIB
+	if not os.path.exists(path):
+		_build.build_runtime()
+	lib = ctypes.CDLL(path)
+	for name, (restype, argtypes) in SIGNATURES.items():
+		fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol
+		fn.restype = restype
+		fn.argtypes = argtypes
+	_lib = lib
+	return lib
+
+
+class EngineError(RuntimeError):
+	pass
+
+
+def _f64(a):
+	return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dp(a):
+	return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+class Engine:
+	"""One ensemble on one GPU: owns a jdde_handle."""
+
+	def __init__(self, n, n_basic, n_sites, n_params, n_members, ring_capacity=64, device=0):
+		self.lib = load_library()
+		self.n, self.n_basic, self.n_sites, self.n_params = n, n_basic, n_sites, n_params
+		self.N = int(n_members)
+		self.ring_capacity = ring_capacity
+		self.device = device
+		desc = Desc(n=n, n_basic=n_basic, n_sites=n_sites, n_params=n_params,
+			ring_capacity=ring_capacity, device=device, n_members=self.N)
+		self._h = _H()
+		rc = self.lib.jdde_create(ctypes.byref(desc), ctypes.byref(self._h))
+		if rc:
+			message = self.lib.jdde_last_error(None).decode()
+			self._h = None
+			raise EngineError(f"jdde_create failed ({rc}): {message}")
+
+	def close(self):
+		if getattr(self, "_h", None):
+			self.lib.jdde_destroy(self._h)
+			self._h = None
+
+	__del__ = close
+
+	def _check(self, rc):
+		if rc:
+			raise EngineError(f"error {rc}: {self.lib.jdde_last_error(self._h).decode()}")
+
+	def load_image(self, path):
+		with open(path, "rb") as f:
+			image = f.read()
+		self._image = image   # keep alive
+		self._check(self.lib.jdde_load_rhs(self._h, image, len(image)))
+
+	def set_stream(self, stream_ptr):
+		self._check(self.lib.jdde_set_stream(self._h, ctypes.c_void_p(stream_ptr)))
+
+	def synchronize(self):
+		self._check(self.lib.jdde_synchronize(self._h))
+
+	def set_past(self, times, states, diffs):
+		times, states, diffs = _f64(times), _f64(states), _f64(diffs)
+		per_member = times.ndim == 2
+		k = times.shape[-1]
+		expected = (self.N, k, self.n) if per_member else (k, self.n)
+		if states.shape != expected or diffs.shape != expected or (per_member and times.shape[0] != self.N):
+			raise ValueError(f"past has wrong shape: times {times.shape}, states {states.shape}, expected states {expected}")
+		self._check(self.lib.jdde_set_past(self._h, k, _dp(times), _dp(states), _dp(diffs), int(per_member)))
+
+	def set_parameters(self, params):
+		params = _f64(params)
+		per_member = params.ndim == 2
+		if params.shape != ((self.N, self.n_params) if per_member else (self.n_params,)):
+			raise ValueError(f"parameters have wrong shape {params.shape}")
+		self._check(self.lib.jdde_set_parameters(self._h, _dp(params), int(per_member)))
+
+	def set_integration_parameters(self, max_delay, **kwargs):
+		p = IntParams(**kwargs)
+		self._check(self.lib.jdde_set_integration_parameters(self._h, ctypes.byref(p), float(max_delay)))
+
+	def _targets(self, target):
+		target = _f64(target)
+		if target.ndim == 0:
+			return target.reshape(1), 0
+		if target.shape != (self.N,):
+			raise ValueError(f"target times must be a scalar or have shape ({self.N},)")
+		return target, 1
+
+	def integrate(self, target, out=None, status=None, fetch=True):
+		target, pm = self._targets(target)
+		if fetch and out is None:
+			out = np.empty((self.N, self.n))
+		if fetch and status is None:
+			status = np.empty(self.N, dtype=np.int32)
+		self._check(self.lib.jdde_integrate(self._h, _dp(target), pm, _dp(out) if fetch else None,
+			status.ctypes.data_as(c_int32_p) if fetch else None))
+		return out, status
+
+	def step_on_discontinuities(self, steps, out=None, status=None):
+		steps = _f64(steps)
+		pm = int(steps.ndim == 2)
+		if pm and steps.shape[0] != self.N:
+			raise ValueError("steps have wrong shape")
+		out = np.empty((self.N, self.n)) if out is None else out
+		status = np.empty(self.N, dtype=np.int32) if status is None else status
+		self._check(self.lib.jdde_step_on_discontinuities(self._h, steps.shape[-1], _dp(steps), pm, _dp(out), status.ctypes.data_as(c_int32_p)))
+		return out, status
+
+	def integrate_blindly(self, target, step):
+		target, pm = self._targets(target)
+		out = np.empty((self.N, self.n))
+		status = np.empty(self.N, dtype=np.int32)
+		self._check(self.lib.jdde_integrate_blindly(self._h, _dp(target), pm, float(step or 0.0), _dp(out), status.ctypes.data_as(c_int32_p)))
+		return out, status
+
+	def jump(self, amplitude, time, width, forward):
+		amplitude = _f64(amplitude)
+		amp_pm = int(amplitude.ndim == 2)
+		time = _f64(time)
+		time_pm = int(time.ndim == 1)
+		if not time_pm:
+			time = time.reshape(1)
+		mi, ma = np.empty((self.N, self.n)), np.empty((self.N, self.n))
+		self._check(self.lib.jdde_jump(self._h, _dp(amplitude), amp_pm, _dp(time), time_pm, float(width), int(forward), _dp(mi), _dp(ma)))
+		return mi, ma
+
+	def adjust_diff(self, shift_ratio):
+		mi, ma = np.empty((self.N, self.n)), np.empty((self.N, self.n))
+		self._check(self.lib.jdde_adjust_diff(self._h, float(shift_ratio), _dp(mi), _dp(ma)))
+		return mi, ma
+
+	def orthonormalise(self, n_lyap, delay):
+		norms = np.empty((self.N, n_lyap))
+		self._check(self.lib.jdde_orthonormalise(self._h, n_lyap, float(delay), _dp(norms)))
+		return norms
+
+	def integrate_lyap(self, target):
+		target, pm = self._targets(target)
+		n_lyap = self.n//self.n_basic-1
+		state = np.empty((self.N, self.n_basic))
+		lyaps = np.empty((self.N, n_lyap))
+		delta_t = np.empty(self.N)
+		status = np.empty(self.N, dtype=np.int32)
+		self._check(self.lib.jdde_integrate_lyap(self._h, _dp(target), pm, _dp(state), _dp(lyaps), _dp(delta_t), status.ctypes.data_as(c_int32_p)))
+		return state, lyaps, delta_t, status
+
+	def get_t(self):
+		t = np.empty(self.N)
+		self._check(self.lib.jdde_get_t(self._h, _dp(t)))
+		return t
+
+	def get_dt(self):
+		dt = np.empty(self.N)
+		self._check(self.lib.jdde_get_dt(self._h, _dp(dt)))
+		return dt
+
+	def get_current_state(self):
+		out = np.empty((self.N, self.n))
+		self._check(self.lib.jdde_get_current_state(self._h, _dp(out)))
+		return out
+
+	def get_status(self):
+		status = np.empty(self.N, dtype=np.int32)
+		self._check(self.lib.jdde_get_status(self._h, status.ctypes.data_as(c_int32_p)))
+		return status
+
+	def get_counters(self):
+		a, r, f = (np.empty(self.N, dtype=np.int64) for _ in range(3))
+		self._check(self.lib.jdde_get_counters(self._h, a.ctypes.data_as(c_int64_p), r.ctypes.data_as(c_int64_p), f.ctypes.data_as(c_int64_p)))
+		return a, r, f
+
+	def sum_counters(self):
+		a, r, f = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+		self._check(self.lib.jdde_sum_counters(self._h, ctypes.byref(a), ctypes.byref(r), ctypes.byref(f)))
+		return a.value, r.value, f.value
+
+	def get_state(self, member=0):
+		count = ctypes.c_int32()
+		self._check(self.lib.jdde_get_state(self._h, member, 0, ctypes.byref(count), None, None, None))
+		k = count.value
+		times, states, diffs = np.empty(k), np.empty((k, self.n)), np.empty((k, self.n))
+		self._check(self.lib.jdde_get_state(self._h, member, k, ctypes.byref(count), _dp(times), _dp(states), _dp(diffs)))
+		return times, states, diffs
+
+	def grow_ring(self, new_capacity):
+		self._check(self.lib.jdde_grow_ring(self._h, int(new_capacity)))
+		self.ring_capacity = int(new_capacity)
+
+	def clear_status(self, code):
+		self._check(self.lib.jdde_clear_status(self._h, int(code)))
+
+	def set_attempt_budget(self, attempts):
+		self._check(self.lib.jdde_set_attempt_budget(self._h, int(attempts)))
+
+	@property
+	def launch_count(self):
+		return self.lib.jdde_launch_count(self._h)
+
+	@property
+	def device_result(self):
+		return self.lib.jdde_device_result(self._h)

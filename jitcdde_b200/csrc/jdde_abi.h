@@ -1,0 +1,65 @@
+/*
+ * jdde_abi.h — layout shared by the runtime library (jdde_runtime.cu) and the per-DDE
+ * kernel image (jdde_kernels.cu). Internal; the public boundary is include/jitcdde_b200.h.
+ *
+ * Data layout in HBM for an ensemble of n_members trajectories ("members"):
+ *
+ *   ring   [n_members][cap][A] doubles. One member's anchors are contiguous (member-major):
+ *          a trajectory reads and writes its history sequentially in time, so consecutive steps
+ *          of a thread hit the same or the next 128-byte line. An anchor is
+ *          { time, state[n], diff[n], padding } with A = 1+2n rounded up to a multiple of 4
+ *          doubles (32 bytes), so an anchor never straddles a 32-byte sector (n = 1: exactly one
+ *          sector). Slot of logical anchor index i = i & (cap-1); first/last/current are logical
+ *          indices that only grow (the reference: malloc'd doubly-linked list,
+ *          /root/reference/jitcdde/jitced_template.c:25-54).
+ *   par    [n_params][n_members]           control parameters (structure of arrays: coalesced)
+ *   dt, last_pws, credit, last_start, first, last, current, count, status, cursor[n_sites],
+ *   accepted, rejected, attempts, extra_rhs: [n_members] each (structure of arrays), the
+ *          per-trajectory controller state that the reference keeps as attributes of its Python
+ *          object (/root/reference/jitcdde/_jitcdde.py:710-741) and of dde_integrator
+ *          (jitced_template.c:37-54).
+ */
+#ifndef JDDE_ABI_H
+#define JDDE_ABI_H
+
+#include "../../include/jitcdde_b200.h"
+
+#define JDDE_IMAGE_MAGIC 0x4a444445   /* "JDDE" */
+
+typedef struct jdde_problem
+{
+	double * ring;
+	double * par;
+	double * dt;
+	double * last_pws;
+	double * credit;
+	double * last_start;
+	int * first;
+	int * last;
+	int * current;
+	int * count;
+	int * status;
+	int * cursor;
+	long long * accepted;
+	long long * rejected;
+	long long * attempts;
+	long long * extra_rhs;
+	long long n_members;
+	int cap;
+	int anchor_stride;
+	double max_delay;
+	jdde_int_params P;
+} jdde_problem;
+
+/* `jdde_image_desc` global in every kernel image */
+typedef struct jdde_image_desc_t
+{
+	int magic, abi, n, n_basic, n_sites, n_params, anchor_stride, block;
+} jdde_image_desc_t;
+
+static inline int jdde_anchor_stride(int n)
+{
+	return ((1+2*n) + 3) & ~3;
+}
+
+#endif

@@ -1,0 +1,957 @@
+/*
+ * jdde_engine.cuh — the DDE integration engine: one trajectory ("member") per thread.
+ *
+ * Hand-written FP64 device code for the Shampine–Thompson method as implemented by
+ * neurophysik/jitcdde: Bogacki–Shampine 3(2) stages with FSAL, cubic-Hermite history,
+ * embedded error estimate, GSL-style step-size control, past-within-step iteration,
+ * discontinuity stepping, jumps, dense output, forget, and Gram–Schmidt
+ * orthonormalisation of separation functions for Lyapunov exponents.
+ *
+ * Reference behaviour reproduced here (file:line under /root/reference/jitcdde/):
+ *   history + lookup      jitced_template.c:25-54, 56-114, 193-251
+ *   step                  jitced_template.c:398-472
+ *   error norm / accept   jitced_template.c:474-532
+ *   forget / output       jitced_template.c:287-320, 534-561
+ *   jumps                 jitced_template.c:253-285, 1089-1174
+ *   Lyapunov              jitced_template.c:657-878
+ *   controller            _jitcdde.py:621-1000 (runs INSIDE the kernel here; the reference
+ *                         crosses Python↔C 5–7 times per step for it)
+ *
+ * Design for B200:
+ *   - whole `integrate(target)` for an ensemble is ONE kernel launch; every thread runs its own
+ *     adaptive loop (own step size, own accept/reject, no lockstep between trajectories);
+ *   - the working set of a step — current anchor, tentative anchor, controller state, search
+ *     cursors — lives in registers for the whole launch; HBM sees one anchor store per attempt
+ *     and the anchor loads of the delayed lookups;
+ *   - the history is a power-of-two ring per member in HBM (jdde_abi.h), addressed by logical
+ *     indices; the bracket search keeps one cursor per lookup site and reproduces the reference's
+ *     walk including its tie-breaks;
+ *   - arithmetic keeps the reference's association order; with -fmad=false the results are
+ *     bit-identical to the CPU oracle (tests/), with FMA contraction they agree to rounding.
+ *
+ * The functions are __host__ __device__ so that tests/ can compile the same engine with g++ and
+ * compare it with the oracle without a GPU; the product only ever runs the CUDA build.
+ */
+#ifndef JDDE_ENGINE_CUH
+#define JDDE_ENGINE_CUH
+
+#include <math.h>
+#include "jdde_math.h"
+#include "jdde_abi.h"
+
+#if !defined(JD_N) || !defined(JD_NSITES) || !defined(JD_NPARAMS) || !defined(JD_RHS_FILE)
+#error "JD_N, JD_NSITES, JD_NPARAMS and JD_RHS_FILE must be defined by the generated translation unit"
+#endif
+#ifndef JD_NBASIC
+#define JD_NBASIC JD_N
+#endif
+
+#define JD_A ((((1+2*JD_N))+3)&~3)
+#define JD_NORM_THRESHOLD (1e-30)     /* jitced_template.c:15 */
+
+#if defined(__CUDACC__)
+#  define JD_FN __host__ __device__ __forceinline__
+#  define JD_UNROLL _Pragma("unroll")
+#else
+#  define JD_FN inline
+#  define JD_UNROLL
+#endif
+
+namespace jdde {
+
+/* pair of anchors bracketing a time (what `anchors(t)` returns in the reference: anchor *) */
+struct Seg
+{
+	const double * v;
+	const double * w;
+	double tv;
+	double tw;
+};
+
+/* everything one trajectory needs while a kernel runs; lives in registers / local memory */
+struct Member
+{
+	double * ring;
+	int mask;
+	int cap;
+	int first, last, current;
+	int cursor[JD_NSITES > 0 ? JD_NSITES : 1];
+	double par[JD_NPARAMS > 0 ? JD_NPARAMS : 1];
+
+	double cur_t, cur_y[JD_N], cur_d[JD_N];     /* last accepted anchor (`current`) */
+	double new_t, new_y[JD_N], new_d[JD_N];     /* tentative anchor (`last_anchor` while last != current) */
+	double old_y[JD_N];                         /* state of the replaced tentative anchor (`old_last`) */
+	bool has_old;
+	double err[JD_N];
+	double pws;                                 /* past_within_step */
+	double last_start;                          /* last_actual_step_start */
+
+	double dt, last_pws, credit;
+	int count;
+
+	long long accepted, rejected, attempts, extra_rhs;
+	int status;
+
+	JD_FN double * slot(int const index) const { return ring + (size_t)(index & mask)*JD_A; }
+};
+
+/* ------------------------------------------------------------------ load / store */
+
+JD_FN void load_member(jdde_problem const & P, long long const m, Member & M)
+{
+	M.cap = P.cap;
+	M.mask = P.cap-1;
+	M.ring = P.ring + (size_t)m*P.cap*JD_A;
+	M.first = P.first[m];
+	M.last = P.last[m];
+	M.current = P.current[m];
+	JD_UNROLL
+	for (int s = 0; s < JD_NSITES; s++)
+		M.cursor[s] = P.cursor[(size_t)s*P.n_members+m];
+	JD_UNROLL
+	for (int k = 0; k < JD_NPARAMS; k++)
+		M.par[k] = P.par[(size_t)k*P.n_members+m];
+	double const * const c = M.slot(M.current);
+	M.cur_t = c[0];
+	JD_UNROLL
+	for (int i = 0; i < JD_N; i++)
+	{
+		M.cur_y[i] = c[1+i];
+		M.cur_d[i] = c[1+JD_N+i];
+	}
+	M.has_old = false;
+	M.pws = 0.0;
+	M.last_start = P.last_start[m];
+	M.dt = P.dt[m];
+	M.last_pws = P.last_pws[m];
+	M.credit = P.credit[m];
+	M.count = P.count[m];
+	M.accepted = P.accepted[m];
+	M.rejected = P.rejected[m];
+	M.attempts = P.attempts[m];
+	M.extra_rhs = P.extra_rhs[m];
+	M.status = P.status[m];
+}
+
+JD_FN void store_member(jdde_problem const & P, long long const m, Member const & M)
+{
+	P.first[m] = M.first;
+	P.last[m] = M.last;
+	P.current[m] = M.current;
+	JD_UNROLL
+	for (int s = 0; s < JD_NSITES; s++)
+		P.cursor[(size_t)s*P.n_members+m] = M.cursor[s];
+	P.last_start[m] = M.last_start;
+	P.dt[m] = M.dt;
+	P.last_pws[m] = M.last_pws;
+	P.credit[m] = M.credit;
+	P.count[m] = M.count;
+	P.accepted[m] = M.accepted;
+	P.rejected[m] = M.rejected;
+	P.attempts[m] = M.attempts;
+	P.extra_rhs[m] = M.extra_rhs;
+	P.status[m] = M.status;
+}
+
+/* ------------------------------------------------------------------ history lookup */
+
+/* get_past_anchors, jitced_template.c:193-217. One cursor per lookup site; the walk's stopping
+ * rules decide which segment is taken when t equals an anchor time. */
+JD_FN Seg anchors(Member & M, int const site, double const t)
+{
+	int ca = M.cursor[site];
+	double const * pa = M.slot(ca);
+	double ta = pa[0];
+	while (ta > t && ca > M.first)
+	{
+		--ca;
+		pa = M.slot(ca);
+		ta = pa[0];
+	}
+	double const * pn = M.slot(ca+1);
+	double tn = pn[0];
+	while (tn < t && ca+2 <= M.last)
+	{
+		++ca;
+		pa = pn;
+		ta = tn;
+		pn = M.slot(ca+1);
+		tn = pn[0];
+	}
+	if (t > M.cur_t)
+		M.pws = fmax(M.pws, t-M.cur_t);
+	M.cursor[site] = ca;
+	Seg s;
+	s.v = pa; s.w = pn; s.tv = ta; s.tw = tn;
+	return s;
+}
+
+/* get_past_value, jitced_template.c:221-235 */
+JD_FN double past_y(double const t, int const index, Seg const & s)
+{
+	double const q = s.tw-s.tv;
+	double const x = (t - s.tv)/q;
+	double const a = s.v[1+index];
+	double const b = s.v[1+JD_N+index] * q;
+	double const c = s.w[1+index];
+	double const d = s.w[1+JD_N+index] * q;
+	return (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
+}
+
+/* get_past_diff, jitced_template.c:237-251 */
+JD_FN double past_dy(double const t, int const index, Seg const & s)
+{
+	double const q = s.tw-s.tv;
+	double const x = (t - s.tv)/q;
+	double const a = s.v[1+index];
+	double const b = s.v[1+JD_N+index] * q;
+	double const c = s.w[1+index];
+	double const d = s.w[1+JD_N+index] * q;
+	return ( (1-x)*(b-x*3*(2*(a-c)+b+d)) + d*x ) /q;
+}
+
+JD_FN Seg segment_at(Member const & M, int const vi)
+{
+	Seg s;
+	s.v = M.slot(vi);
+	s.w = M.slot(vi+1);
+	s.tv = s.v[0];
+	s.tw = s.w[0];
+	return s;
+}
+
+/* ------------------------------------------------------------------ right-hand side */
+
+/* macro vocabulary of the generated statements (jitced_template.c:382-391) */
+#define JDDE_Y(i) (y[i])
+#define JDDE_PAR(k) (M.par[k])
+#define JDDE_SEG ::jdde::Seg const
+#define JDDE_ANCHORS(k, tm) ::jdde::anchors(M, k, tm)
+#define JDDE_PAST_Y(tm, i, s) ::jdde::past_y(tm, i, s)
+#define JDDE_PAST_DY(tm, i, s) ::jdde::past_dy(tm, i, s)
+#define JDDE_SET_DY(i, value) (dY[i] = (value))
+#define JDDE_IPOW(x, e) jdde_ipow(x, e)
+
+/* eval_f, jitced_template.c:398-419 */
+JD_FN void eval_f(Member & M, double const t, double const * const y, double * const dY)
+{
+	#include JD_RHS_FILE
+}
+
+/* ------------------------------------------------------------------ one attempted step */
+
+/* get_next_step, jitced_template.c:421-472 */
+JD_FN void get_next_step(Member & M, double const delta_t)
+{
+	M.last_start = M.cur_t;
+	M.pws = 0.0;
+	M.attempts++;
+
+	double argument[JD_N];
+	double k_2[JD_N];
+	JD_UNROLL
+	for (int i = 0; i < JD_N; i++)
+		argument[i] = M.cur_y[i] + 0.5*delta_t*M.cur_d[i];
+	eval_f(M, M.cur_t+0.5*delta_t, argument, k_2);
+
+	double k_3[JD_N];
+	JD_UNROLL
+	for (int i = 0; i < JD_N; i++)
+		argument[i] = M.cur_y[i] + 0.75*delta_t*k_2[i];
+	eval_f(M, M.cur_t+0.75*delta_t, argument, k_3);
+
+	double ny[JD_N], nd[JD_N];
+	JD_UNROLL
+	for (int i = 0; i < JD_N; i++)
+		ny[i] = M.cur_y[i] + (delta_t/9.) * (2*M.cur_d[i]+3*k_2[i]+4*k_3[i]);
+
+	double const nt = M.cur_t + delta_t;
+	eval_f(M, nt, ny, nd);
+
+	JD_UNROLL
+	for (int i = 0; i < JD_N; i++)
+		M.err[i] = (5*M.cur_d[i]-6*k_2[i]-8*k_3[i]+9*nd[i]) * (delta_t/72.);
+
+	if (M.last == M.current)
+		M.last++;                      /* append_anchor, :56-73 */
+	else
+	{
+		/* replace_last_anchor, :106-114: keep the replaced state for check_new_y_diff */
+		JD_UNROLL
+		for (int i = 0; i < JD_N; i++)
+			M.old_y[i] = M.new_y[i];
+		M.has_old = true;
+	}
+	M.new_t = nt;
+	double * const dst = M.slot(M.last);
+	dst[0] = nt;
+	JD_UNROLL
+	for (int i = 0; i < JD_N; i++)
+	{
+		M.new_y[i] = ny[i];
+		M.new_d[i] = nd[i];
+		dst[1+i] = ny[i];
+		dst[1+JD_N+i] = nd[i];
+	}
+}
+
+/* get_p, jitced_template.c:474-498 */
+JD_FN double get_p(Member const & M, double const atol, double const rtol)
+{
+	double p = 0.0;
+	JD_UNROLL
+	for (int i = 0; i < JD_N; i++)
+	{
+		double const error = fabs(M.err[i]);
+		double const tolerance = atol+rtol*fabs(M.new_y[i]);
+		if (error != 0.0 || tolerance != 0.0)
+		{
+			double const x = error/tolerance;
+			if (x > p)
+				p = x;
+		}
+	}
+	return p;
+}
+
+/* check_new_y_diff, jitced_template.c:502-524 */
+JD_FN bool check_new_y_diff(Member const & M, double const atol, double const rtol)
+{
+	if (!M.has_old)
+		return false;
+	bool result = true;
+	JD_UNROLL
+	for (int i = 0; i < JD_N; i++)
+	{
+		double const difference = fabs(M.new_y[i] - M.old_y[i]);
+		double const tolerance = atol + fabs(rtol*M.new_y[i]);
+		result &= (tolerance >= difference);
+	}
+	return result;
+}
+
+/* accept_step, jitced_template.c:526-532 */
+JD_FN void accept_step(Member & M)
+{
+	M.current = M.last;
+	M.has_old = false;
+	M.cur_t = M.new_t;
+	JD_UNROLL
+	for (int i = 0; i < JD_N; i++)
+	{
+		M.cur_y[i] = M.new_y[i];
+		M.cur_d[i] = M.new_d[i];
+	}
+}
+
+/* forget, jitced_template.c:534-561 */
+JD_FN void forget(Member & M, double const delay)
+{
+	double const threshold = fmin(M.cur_t - delay, M.last_start);
+	while (M.first+1 < M.last && M.slot(M.first+1)[0] < threshold)
+		M.first++;
+	JD_UNROLL
+	for (int s = 0; s < JD_NSITES; s++)
+		if (M.cursor[s] < M.first)
+			M.cursor[s] = M.first;
+}
+
+/* get_recent_state, jitced_template.c:287-320 */
+JD_FN void get_recent_state(Member const & M, double const t, double * const out, int const n_out)
+{
+	double const * const w = M.slot(M.last);
+	double const * const v = M.slot(M.last-1);
+	double const q = w[0]-v[0];
+	double const x = (t - v[0])/q;
+	JD_UNROLL
+	for (int index = 0; index < JD_N; index++)
+	{
+		double const a = v[1+index];
+		double const b = v[1+JD_N+index] * q;
+		double const c = w[1+index];
+		double const d = w[1+JD_N+index] * q;
+		if (index < n_out)
+			out[index] = (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
+	}
+}
+
+/* ------------------------------------------------------------------ controller (_jitcdde.py) */
+
+/* _jitcdde.py:21 */
+JD_FN double sigmoid(double const x) { return (tanh(x)+1)/2; }
+
+/* _jitcdde.py:745-765: UnsuccessfulIntegration becomes a per-member status */
+JD_FN void control_for_min_step(Member & M, jdde_int_params const & P)
+{
+	if (M.dt < P.min_step)
+		M.status = JDDE_STATUS_MIN_STEP;
+}
+
+/* _jitcdde.py:767-773 */
+JD_FN double increase_chance(Member const & M, jdde_int_params const & P, double const new_dt)
+{
+	double const q = new_dt/M.last_pws;
+	double const is_explicit = sigmoid(1-q);
+	double const far_from_explicit = sigmoid(q-P.pws_factor);
+	double const few_iterations = sigmoid(1-M.count/P.pws_factor);
+	double const profile = is_explicit+far_from_explicit*few_iterations;
+	return profile + P.pws_base_increase_chance*(1-profile);
+}
+
+/* _jitcdde.py:733-741 */
+JD_FN bool do_increase(Member & M, double const p)
+{
+	M.credit += p;
+	if (M.credit >= 0.9)
+	{
+		M.credit = 0.0;
+		return true;
+	}
+	return false;
+}
+
+/* _adjust_step_size, _jitcdde.py:775-794 with q = 3 (:726). The two fractional powers use the
+ * libm-free roots of jdde_math.h so that CPU oracle and GPU take bit-identical step sizes. */
+JD_FN bool adjust_step_size(Member & M, jdde_int_params const & P)
+{
+	double const p = get_p(M, P.atol, P.rtol);
+	if (p > P.decrease_threshold)
+	{
+		M.dt *= fmax(P.safety_factor*jdde_inv_root3(p), P.min_factor);
+		control_for_min_step(M, P);
+		return false;
+	}
+	if (p <= P.increase_threshold)
+	{
+		double const factor = (p != 0.0) ? P.safety_factor*jdde_inv_root4(p) : P.max_factor;
+		double const new_dt = fmin(M.dt*fmin(factor, P.max_factor), P.max_step);
+		if (M.last_pws == 0.0 || do_increase(M, increase_chance(M, P, new_dt)))
+		{
+			M.dt = new_dt;
+			M.count = 0;
+			M.last_pws = 0.0;
+		}
+	}
+	return true;
+}
+
+/* try_single_step, _jitcdde.py:838-861 */
+JD_FN bool try_single_step(Member & M, jdde_int_params const & P, double const length)
+{
+	get_next_step(M, length);
+
+	if (M.pws != 0.0)
+	{
+		M.last_pws = M.pws;
+
+		/* if possible, shrink the step to make the integration explicit */
+		if (M.dt > P.pws_factor*M.pws)
+		{
+			M.dt /= P.pws_factor;
+			control_for_min_step(M, P);
+			return false;
+		}
+
+		bool converged = false;
+		for (int count = 1; count <= P.pws_max_iterations; count++)
+		{
+			M.count = count;
+			get_next_step(M, M.dt);
+			if (check_new_y_diff(M, P.pws_atol, P.pws_rtol))
+			{
+				converged = true;
+				break;
+			}
+		}
+		if (!converged)
+		{
+			M.dt /= P.pws_factor;
+			control_for_min_step(M, P);
+			return false;
+		}
+	}
+	return adjust_step_size(M, P);
+}
+
+/* Room for one more anchor? The reference's list is unbounded; the ring is not. forget() first
+ * (it never removes an anchor a valid lookup can reach), then report overflow. */
+JD_FN bool ensure_room(Member & M, double const max_delay)
+{
+	if (M.last+2-M.first <= M.cap)
+		return true;
+	forget(M, max_delay);
+	if (M.last+2-M.first <= M.cap)
+		return true;
+	M.status = JDDE_STATUS_OVERFLOW;
+	return false;
+}
+
+/* the `while t < target` loops of integrate (_jitcdde.py:830-832) and of
+ * step_on_discontinuities (:988-993, steps capped at the target) */
+template <bool CAPPED>
+JD_FN void step_until(Member & M, jdde_problem const & P, double const target, long long & budget)
+{
+	while (M.cur_t < target && M.status == JDDE_STATUS_OK)
+	{
+		if (!ensure_room(M, P.max_delay))
+			break;
+		if (!(M.dt > 0.0))
+		{
+			/* a step size of zero/NaN would never reach the target: the reference would spin forever */
+			M.status = JDDE_STATUS_NONFINITE;
+			break;
+		}
+		if (budget-- <= 0)
+		{
+			/* watchdog: a kernel must end; the caller clears the status and calls again to go on */
+			M.status = JDDE_STATUS_BUDGET;
+			break;
+		}
+		double const length = CAPPED ? fmin(M.dt, target-M.cur_t) : M.dt;
+		if (try_single_step(M, P.P, length))
+		{
+			accept_step(M);
+			M.accepted++;
+		}
+		else
+			M.rejected++;
+	}
+}
+
+/* ------------------------------------------------------------------ jumps */
+
+/* remove_last_anchor, jitced_template.c:88-104 */
+JD_FN void remove_last_anchor(Member & M)
+{
+	M.has_old = false;
+	M.last--;
+	JD_UNROLL
+	for (int s = 0; s < JD_NSITES; s++)
+		if (M.cursor[s] == M.last)
+			M.cursor[s] = M.last-1;
+}
+
+JD_FN void reload_current(Member & M)
+{
+	double const * const c = M.slot(M.current);
+	M.cur_t = c[0];
+	M.new_t = c[0];
+	for (int i = 0; i < JD_N; i++)
+	{
+		M.cur_y[i] = M.new_y[i] = c[1+i];
+		M.cur_d[i] = M.new_d[i] = c[1+JD_N+i];
+	}
+}
+
+/* truncate_past, jitced_template.c:1089-1108 */
+JD_FN void truncate_past(Member & M, double const time)
+{
+	while (M.last-1 > M.first && M.slot(M.last-1)[0] >= time)
+		remove_last_anchor(M);
+
+	Seg const left = segment_at(M, M.last-1);
+	double ny[JD_N], nd[JD_N];
+	for (int i = 0; i < JD_N; i++)
+	{
+		ny[i] = past_y (time, i, left);
+		nd[i] = past_dy(time, i, left);
+	}
+	double * const dst = M.slot(M.last);
+	dst[0] = time;
+	for (int i = 0; i < JD_N; i++)
+	{
+		dst[1+i] = ny[i];
+		dst[1+JD_N+i] = nd[i];
+	}
+	M.current = M.last;
+	M.has_old = false;
+	reload_current(M);
+}
+
+/* extrema, jitced_template.c:253-285 */
+JD_FN void extrema(Seg const & s, int const index, double & minimum, double & maximum)
+{
+	double const q = s.tw-s.tv;
+	double const a = s.v[1+index];
+	double const b = s.v[1+JD_N+index] * q;
+	double const c = s.w[1+index];
+	double const d = s.w[1+JD_N+index] * q;
+
+	minimum = fmin(a,c);
+	maximum = fmax(a,c);
+
+	double const radicant = b*b + b*d + d*d + 3*(a-c)*(3*(a-c) + 2*(b+d));
+	if (radicant >= 0)
+	{
+		double const A = 1/(2*a + b - 2*c + d);
+		double const B = a + 2*b/3 - c + d/3;
+		for (int sign = -1; sign <= 1; sign += 2)
+		{
+			double const x = (B+sign*sqrt(radicant)/3) * A;
+			if (0 < x && x < 1)
+			{
+				double const value = (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
+				minimum = fmin(minimum,value);
+				maximum = fmax(maximum,value);
+			}
+		}
+	}
+}
+
+/* apply_jump, jitced_template.c:1122-1174 */
+JD_FN void apply_jump(Member & M, jdde_problem const & P, double const * const change, double const time, double const width, double * const minima, double * const maxima)
+{
+	double const nt = time+width;
+
+	int left = M.last-1;
+	while (left > M.first && M.slot(left)[0] >= nt)
+		left--;
+	Seg const ls = segment_at(M, left);
+
+	double ny[JD_N], nd[JD_N];
+	for (int i = 0; i < JD_N; i++)
+		ny[i] = past_y(nt, i, ls) + change[i];
+	eval_f(M, nt, ny, nd);
+	M.extra_rhs++;
+
+	truncate_past(M, time);
+	if (!ensure_room(M, P.max_delay))
+		return;
+	M.last++;
+	double * const dst = M.slot(M.last);
+	dst[0] = nt;
+	for (int i = 0; i < JD_N; i++)
+	{
+		dst[1+i] = ny[i];
+		dst[1+JD_N+i] = nd[i];
+	}
+	M.current = M.last;
+	M.has_old = false;
+	reload_current(M);
+
+	Seg const js = segment_at(M, M.last-1);
+	for (int i = 0; i < JD_N; i++)
+		extrema(js, i, minima[i], maxima[i]);
+}
+
+/* adjust_diff, _jitcdde.py:863-878 (get_state forgets first, :367-371) */
+JD_FN void adjust_diff(Member & M, jdde_problem const & P, double const shift_ratio, double * const minima, double * const maxima)
+{
+	forget(M, P.max_delay);
+	double const t_last = M.slot(M.last)[0];
+	double const width = shift_ratio*(t_last-M.slot(M.last-1)[0]);
+	double zero[JD_N];
+	for (int i = 0; i < JD_N; i++)
+		zero[i] = 0.0;
+	apply_jump(M, P, zero, t_last-width, width, minima, maxima);
+}
+
+/* integrate_blindly, _jitcdde.py:880-933 */
+JD_FN void integrate_blindly(Member & M, jdde_problem const & P, double const target, double step, double * const out)
+{
+	if (!(step > 0))
+		step = P.P.max_step;
+	double const total = target-M.cur_t;
+	if (total > 0)
+	{
+		if (total < step)
+			step = total;
+		long long const number = (long long) rint(total/step);   /* Python round(): ties to even */
+		double const dt = total/number;
+		for (long long k = 0; k < number && M.status == JDDE_STATUS_OK; k++)
+		{
+			if (!ensure_room(M, P.max_delay))
+				break;
+			get_next_step(M, dt);
+			accept_step(M);
+			M.accepted++;
+			forget(M, P.max_delay);
+		}
+	}
+	else if (total == 0)
+	{
+		double mi[JD_N], ma[JD_N];
+		adjust_diff(M, P, 1e-4, mi, ma);
+	}
+	else
+		M.status = JDDE_STATUS_BACKWARDS;
+	/* get_current_state, jitced_template.c:330-334: state of the last anchor */
+	double const * const w = M.slot(M.last);
+	for (int i = 0; i < JD_N; i++)
+		out[i] = w[1+i];
+}
+
+/* ------------------------------------------------------------------ Lyapunov exponents */
+#if JD_NBASIC != JD_N
+
+/* calculate_sp_matrix, jitced_template.c:657-674 */
+JD_FN void sp_matrix(double const q, double m[4][4])
+{
+	double const cq = q/420.;
+	double const cqq = cq*q;
+	double const cqqq = cqq*q;
+	m[0][0] = 156*cq;  m[0][1] = 22*cqq;  m[0][2] = 54*cq;   m[0][3] = -13*cqq;
+	m[1][0] = 22*cqq;  m[1][1] = 4*cqqq;  m[1][2] = 13*cqq;  m[1][3] = -3*cqqq;
+	m[2][0] = 54*cq;   m[2][1] = 13*cqq;  m[2][2] = 156*cq;  m[2][3] = -22*cqq;
+	m[3][0] = -13*cqq; m[3][1] = -3*cqqq; m[3][2] = -22*cqq; m[3][3] = 4*cqqq;
+}
+
+/* calculate_partial_sp_matrix, jitced_template.c:676-709 */
+JD_FN void partial_sp_matrix(double const q, double const z, double m[4][4])
+{
+	double const cq = q/420.;
+	double const cqq = cq*q;
+	double const cqqq = cqq*q;
+
+	double const z3 = z*z*z;
+	double const z4 = z*z3;
+	double const z5 = z*z4;
+
+	double const h_1 = (- 120*z*z - 350*z - 252) * z5 * cqq ;
+	double const h_2 = (-  60*z*z - 140*z -  84) * z5 * cqqq;
+	double const h_3 = (- 120*z*z - 420*z - 378) * z5 * cq  ;
+	double const h_4 = (-  70*z*z - 168*z - 105) * z4 * cqqq;
+	double const h_6 = (          - 105*z - 140) * z3 * cqq ;
+	double const h_7 = (          - 210*z - 420) * z3 * cq  ;
+	double const h_5 = (2*h_2 + 3*h_4)/q;
+	double const h_8 = - h_5 + h_7*q - h_6 - 0.5*(z*q)*(z*q);
+
+	m[0][0] = 2*h_3;     m[0][1] = h_1;     m[0][2] = h_7-2*h_3;       m[0][3] = h_5;
+	m[1][0] = h_1;       m[1][1] = h_2;     m[1][2] = h_6-h_1;         m[1][3] = h_2+h_4;
+	m[2][0] = h_7-2*h_3; m[2][1] = h_6-h_1; m[2][2] = 2*h_3-2*h_7-z*q; m[2][3] = h_8;
+	m[3][0] = h_5;       m[3][1] = h_2+h_4; m[3][2] = h_8;             m[3][3] = h_2+(h_5+h_6-h_1)*q;
+}
+
+/* scalar_product, jitced_template.c:773-817 (norm_sq, :740-771, is the case begin_1 == begin_2).
+ * Segment matrices (calculate_sp_matrices, :711-733) are recomputed from the anchor times
+ * instead of being stored with every anchor: zero before threshold = current.time − delay,
+ * partial for the segment containing it, full afterwards. */
+JD_FN double scalar_product(Member const & M, double const threshold, int const begin_1, int const begin_2)
+{
+	double sum = 0;
+	bool partial_done = false;
+	for (int vi = M.first; vi < M.last; vi++)
+	{
+		double const * const v = M.slot(vi);
+		double const * const w = M.slot(vi+1);
+		double const q = w[0] - v[0];
+		double m[4][4];
+		if (!partial_done)
+		{
+			if (w[0] < threshold)
+				continue;
+			partial_sp_matrix(q, (threshold - w[0]) / q, m);
+			partial_done = true;
+		}
+		else
+			sp_matrix(q, m);
+		double const * const vector_1[4] = { v+1+begin_1, v+1+JD_N+begin_1, w+1+begin_1, w+1+JD_N+begin_1 };
+		double const * const vector_2[4] = { v+1+begin_2, v+1+JD_N+begin_2, w+1+begin_2, w+1+JD_N+begin_2 };
+		double part = 0;
+		for (int i = 0; i < 4; i++)
+			for (int j = 0; j < 4; j++)
+				for (int index = 0; index < JD_NBASIC; index++)
+					part += m[i][j] * vector_1[i][index] * vector_2[j][index];
+		sum += part;
+	}
+	return sum;
+}
+
+/* orthonormalise, jitced_template.c:846-878 incl. subtract_from_past (:832-844), scale_past (:819-830) */
+JD_FN void orthonormalise(Member & M, int const n_lyap, double const delay, double * const norms)
+{
+	double const threshold = M.slot(M.current)[0] - delay;
+	for (int i = 0; i < n_lyap; i++)
+	{
+		int const bi = (i+1)*JD_NBASIC;
+		for (int j = 0; j < i; j++)
+		{
+			int const bj = (j+1)*JD_NBASIC;
+			double const sp = scalar_product(M, threshold, bi, bj);
+			for (int k = M.first; k <= M.last; k++)
+			{
+				double * const a = M.slot(k);
+				for (int c = 0; c < JD_NBASIC; c++)
+				{
+					a[1+bi+c]      -= sp*a[1+bj+c];
+					a[1+JD_N+bi+c] -= sp*a[1+JD_N+bj+c];
+				}
+			}
+		}
+		double const norm = sqrt(scalar_product(M, threshold, bi, bi));
+		if (norm > JD_NORM_THRESHOLD)
+		{
+			double const factor = 1./norm;
+			for (int k = M.first; k <= M.last; k++)
+			{
+				double * const a = M.slot(k);
+				for (int c = 0; c < JD_NBASIC; c++)
+				{
+					a[1+bi+c]      *= factor;
+					a[1+JD_N+bi+c] *= factor;
+				}
+			}
+		}
+		norms[i] = norm;
+	}
+}
+#endif
+
+/* ------------------------------------------------------------------ per-member entry points
+ * (one call = what one kernel thread does; the host twin in tests/ loops over members) */
+
+/* initial past, dde_integrator_init + initiate_past_from_list, jitced_template.c:575-652 */
+JD_FN void member_set_past(jdde_problem const & P, long long const m, int const n_anchors, double const * times, double const * states, double const * diffs, int const per_member)
+{
+	if (per_member)
+	{
+		times += (size_t)m*n_anchors;
+		states += (size_t)m*n_anchors*JD_N;
+		diffs += (size_t)m*n_anchors*JD_N;
+	}
+	double * const ring = P.ring + (size_t)m*P.cap*JD_A;
+	for (int k = 0; k < n_anchors; k++)
+	{
+		double * const a = ring + (size_t)k*JD_A;
+		a[0] = times[k];
+		for (int i = 0; i < JD_N; i++)
+		{
+			a[1+i] = states[(size_t)k*JD_N+i];
+			a[1+JD_N+i] = diffs[(size_t)k*JD_N+i];
+		}
+	}
+	P.first[m] = 0;
+	P.last[m] = n_anchors-1;
+	P.current[m] = n_anchors-1;
+	for (int s = 0; s < JD_NSITES; s++)
+		P.cursor[(size_t)s*P.n_members+m] = n_anchors-2;
+	P.last_start[m] = times[0];
+	P.status[m] = JDDE_STATUS_OK;
+	P.accepted[m] = P.rejected[m] = P.attempts[m] = P.extra_rhs[m] = 0;
+}
+
+/* controller reset of set_integration_parameters, _jitcdde.py:710-728 */
+JD_FN void member_reset_controller(jdde_problem const & P, long long const m)
+{
+	P.dt[m] = P.P.first_step;
+	P.last_pws[m] = 0.0;
+	P.count[m] = 0;
+	P.credit[m] = 0.0;
+}
+
+/* integrate (n_steps == 0: `targets` are absolute times) or step_on_discontinuities
+ * (n_steps > 0: `targets` are step lengths, applied cumulatively, _jitcdde.py:986-987) */
+JD_FN void member_integrate(jdde_problem const & P, long long const m, double const * const targets, int const per_member, int const n_steps, double * const out, int const n_out, long long budget)
+{
+	Member M;
+	load_member(P, m, M);
+	if (M.status != JDDE_STATUS_OK)
+		return;
+	double target;
+	if (n_steps == 0)
+	{
+		target = per_member ? targets[m] : targets[0];
+		step_until<false>(M, P, target, budget);
+	}
+	else
+	{
+		target = M.cur_t;
+		double const * const steps = per_member ? targets+(size_t)m*n_steps : targets;
+		for (int s = 0; s < n_steps && M.status == JDDE_STATUS_OK; s++)
+		{
+			target = M.cur_t + steps[s];
+			step_until<true>(M, P, target, budget);
+		}
+	}
+	if (M.status == JDDE_STATUS_OK)
+	{
+		if (out)
+			get_recent_state(M, target, out+(size_t)m*n_out, n_out);
+		forget(M, P.max_delay);
+	}
+	store_member(P, m, M);
+}
+
+JD_FN void member_integrate_blindly(jdde_problem const & P, long long const m, double const * const targets, int const per_member, double const step, double * const out)
+{
+	Member M;
+	load_member(P, m, M);
+	if (M.status != JDDE_STATUS_OK)
+		return;
+	double res[JD_N];
+	integrate_blindly(M, P, per_member ? targets[m] : targets[0], step, res);
+	if (out)
+		for (int i = 0; i < JD_N; i++)
+			out[(size_t)m*JD_N+i] = res[i];
+	store_member(P, m, M);
+}
+
+/* mode 0: jump(amplitude, time, width, forward); mode 1: adjust_diff(shift_ratio = width) */
+JD_FN void member_jump(jdde_problem const & P, long long const m, int const mode, double const * const amplitude, int const amp_pm, double const * const time, int const time_pm, double const width, int const forward, double * const minima, double * const maxima)
+{
+	Member M;
+	load_member(P, m, M);
+	if (M.status != JDDE_STATUS_OK)
+		return;
+	double mi[JD_N], ma[JD_N];
+	if (mode == 1)
+		adjust_diff(M, P, width, mi, ma);
+	else
+	{
+		double change[JD_N];
+		for (int i = 0; i < JD_N; i++)
+			change[i] = amp_pm ? amplitude[(size_t)m*JD_N+i] : amplitude[i];
+		double const tm = time_pm ? time[m] : time[0];
+		apply_jump(M, P, change, forward ? tm : tm-width, width, mi, ma);
+	}
+	for (int i = 0; i < JD_N; i++)
+	{
+		if (minima) minima[(size_t)m*JD_N+i] = mi[i];
+		if (maxima) maxima[(size_t)m*JD_N+i] = ma[i];
+	}
+	store_member(P, m, M);
+}
+
+JD_FN void member_forget(jdde_problem const & P, long long const m)
+{
+	Member M;
+	load_member(P, m, M);
+	forget(M, P.max_delay);
+	store_member(P, m, M);
+}
+
+#if JD_NBASIC != JD_N
+/* orthonormalise and, if old_t is given, the tail of jitcdde_lyap.integrate (_jitcdde.py:1162-1172) */
+JD_FN void member_orthonormalise(jdde_problem const & P, long long const m, int const n_lyap, double const delay, double * const norms, double const * const old_t, double * const lyaps, double * const delta_t)
+{
+	Member M;
+	load_member(P, m, M);
+	if (M.status != JDDE_STATUS_OK)
+		return;
+	double nrm[JD_N/JD_NBASIC];
+	if (old_t)
+	{
+		double const dt = M.cur_t-old_t[m];
+		delta_t[m] = dt;
+		if (dt != 0)
+		{
+			orthonormalise(M, n_lyap, delay, nrm);
+			for (int i = 0; i < n_lyap; i++)
+				lyaps[(size_t)m*n_lyap+i] = log(nrm[i]) / dt;
+		}
+		else
+			for (int i = 0; i < n_lyap; i++)
+				lyaps[(size_t)m*n_lyap+i] = 0.0;
+	}
+	else
+	{
+		orthonormalise(M, n_lyap, delay, nrm);
+		for (int i = 0; i < n_lyap; i++)
+			norms[(size_t)m*n_lyap+i] = nrm[i];
+	}
+}
+#endif
+
+} // namespace jdde
+
+#endif

@@ -1,0 +1,164 @@
+/*
+ * jdde_kernels.cu — the per-DDE kernel image. Compiled once per right-hand side by
+ * jitcdde_b200/_build.py:
+ *
+ *   nvcc -cubin -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 [-fmad=false]
+ *        -DJD_N=… -DJD_NBASIC=… -DJD_NSITES=… -DJD_NPARAMS=… -DJD_RHS_FILE="rhs_<key>.inc"
+ *
+ * and loaded by the runtime library with cudaLibraryLoadData (jdde_load_rhs). This is the
+ * counterpart of the reference rendering jitced_template.c and building a CPython extension per
+ * DDE (/root/reference/jitcdde/_jitcdde.py:560-575).
+ *
+ * Every kernel maps one thread to one trajectory of the ensemble; the grid covers all members.
+ * Block size JD_BLOCK (default 128): blocks are the scheduling granule that evens out the
+ * different amounts of work of different members, 148 SMs × several resident blocks each.
+ */
+#include "jdde_engine.cuh"
+
+#ifndef JD_BLOCK
+#define JD_BLOCK 128
+#endif
+#ifndef JD_MIN_BLOCKS
+#define JD_MIN_BLOCKS 1
+#endif
+
+extern "C" __device__ const jdde_image_desc_t jdde_image_desc = {
+	JDDE_IMAGE_MAGIC, JDDE_ABI_VERSION, JD_N, JD_NBASIC, JD_NSITES, JD_NPARAMS, JD_A, JD_BLOCK
+};
+
+#define JD_MEMBER_INDEX() ((long long)blockIdx.x*blockDim.x+threadIdx.x)
+
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_set_past(jdde_problem const P, int const n_anchors, double const * const times, double const * const states, double const * const diffs, int const per_member)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members)
+		jdde::member_set_past(P, m, n_anchors, times, states, diffs, per_member);
+}
+
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_reset_controller(jdde_problem const P)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members)
+		jdde::member_reset_controller(P, m);
+}
+
+/* THE hot kernel: integrate / step_on_discontinuities for the whole ensemble */
+extern "C" __global__ void __launch_bounds__(JD_BLOCK, JD_MIN_BLOCKS)
+jdde_k_integrate(jdde_problem const P, double const * const targets, int const per_member, int const n_steps, double * const out, int const n_out, long long const budget)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members)
+		jdde::member_integrate(P, m, targets, per_member, n_steps, out, n_out, budget);
+}
+
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_integrate_blindly(jdde_problem const P, double const * const targets, int const per_member, double const step, double * const out)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members)
+		jdde::member_integrate_blindly(P, m, targets, per_member, step, out);
+}
+
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_jump(jdde_problem const P, int const mode, double const * const amplitude, int const amp_pm, double const * const time, int const time_pm, double const width, int const forward, double * const minima, double * const maxima)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members)
+		jdde::member_jump(P, m, mode, amplitude, amp_pm, time, time_pm, width, forward, minima, maxima);
+}
+
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_forget(jdde_problem const P)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members)
+		jdde::member_forget(P, m);
+}
+
+/* what = 0: t (get_t), 1: state of the last anchor (get_current_state), 2: dt */
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_get(jdde_problem const P, int const what, double * const out)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m >= P.n_members)
+		return;
+	double const * const ring = P.ring + (size_t)m*P.cap*JD_A;
+	if (what == 0)
+		out[m] = ring[(size_t)(P.current[m] & (P.cap-1))*JD_A];
+	else if (what == 1)
+	{
+		double const * const a = ring + (size_t)(P.last[m] & (P.cap-1))*JD_A;
+		for (int i = 0; i < JD_N; i++)
+			out[(size_t)m*JD_N+i] = a[1+i];
+	}
+	else
+		out[m] = P.dt[m];
+}
+
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_clear_status(jdde_problem const P, int const code)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members && P.status[m] == code)
+		P.status[m] = JDDE_STATUS_OK;
+}
+
+/* sums of accepted / rejected / right-hand-side evaluations over the ensemble: warp shuffle
+ * reduction, one atomic per warp */
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_sum_counters(jdde_problem const P, unsigned long long * const out)
+{
+	long long const m = JD_MEMBER_INDEX();
+	unsigned long long a = 0, r = 0, f = 0;
+	if (m < P.n_members)
+	{
+		a = (unsigned long long)P.accepted[m];
+		r = (unsigned long long)P.rejected[m];
+		f = (unsigned long long)(3*P.attempts[m] + P.extra_rhs[m]);
+	}
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		a += __shfl_down_sync(0xffffffffu, a, o);
+		r += __shfl_down_sync(0xffffffffu, r, o);
+		f += __shfl_down_sync(0xffffffffu, f, o);
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		atomicAdd(out+0, a);
+		atomicAdd(out+1, r);
+		atomicAdd(out+2, f);
+	}
+}
+
+/* copy every member's live anchors into a ring of another capacity (jdde_grow_ring) */
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_regrow(jdde_problem const P, double * const new_ring, int const new_cap)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m >= P.n_members)
+		return;
+	double const * const src = P.ring + (size_t)m*P.cap*JD_A;
+	double * const dst = new_ring + (size_t)m*new_cap*JD_A;
+	int const first = P.first[m], last = P.last[m];
+	for (int k = first; k <= last; k++)
+	{
+		double const * const a = src + (size_t)(k & (P.cap-1))*JD_A;
+		double * const b = dst + (size_t)(k & (new_cap-1))*JD_A;
+		for (int i = 0; i < JD_A; i++)
+			b[i] = a[i];
+	}
+	if (P.status[m] == JDDE_STATUS_OVERFLOW)
+		P.status[m] = JDDE_STATUS_OK;
+}
+
+#if JD_NBASIC != JD_N
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_orthonormalise(jdde_problem const P, int const n_lyap, double const delay, double * const norms, double const * const old_t, double * const lyaps, double * const delta_t)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members)
+		jdde::member_orthonormalise(P, m, n_lyap, delay, norms, old_t, lyaps, delta_t);
+}
+#endif

@@ -1,0 +1,678 @@
+/*
+ * jdde_runtime.cu — libjitcdde_b200.so: the C ABI of include/jitcdde_b200.h.
+ *
+ * Host-side runtime of the engine: owns the device memory of one ensemble (layout: jdde_abi.h),
+ * loads the per-DDE kernel image (jdde_kernels.cu compiled for sm_100a) with
+ * cudaLibraryLoadData and launches its kernels on one CUDA stream. It contains no device code
+ * and no numerical code of its own: all arithmetic of the hot path is in jdde_engine.cuh.
+ *
+ * It replaces the CPython glue of the reference's generated module
+ * (/root/reference/jitcdde/jitced_template.c:1178-1268) and the module build/load plumbing of
+ * jitcxde_common used at /root/reference/jitcdde/_jitcdde.py:560-588.
+ *
+ * There is deliberately no CPU fallback: every entry point needs a CUDA device.
+ */
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "jdde_abi.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Kernels
+{
+	cudaKernel_t set_past = nullptr, reset_controller = nullptr, integrate = nullptr, integrate_blindly = nullptr,
+		jump = nullptr, forget = nullptr, get = nullptr, clear_status = nullptr, sum_counters = nullptr,
+		regrow = nullptr, orthonormalise = nullptr;
+};
+
+} // namespace
+
+struct jdde_handle
+{
+	jdde_desc desc{};
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	cudaLibrary_t lib = nullptr;
+	Kernels k;
+	int block = 128;
+	jdde_problem P{};
+	bool have_past = false, have_params = false, have_int_params = false;
+	long long budget = 1ll << 24;
+	int64_t launches = 0;
+	std::string err;
+
+	/* device scratch */
+	double * d_in = nullptr;  size_t in_bytes = 0;      /* staged inputs */
+	double * d_out = nullptr;                            /* [N][n] result of the last integration */
+	double * d_out2 = nullptr;                           /* [N][n] second result (maxima, lyaps) */
+	double * d_aux = nullptr;                            /* [N] (old t, delta t) */
+	double * d_aux2 = nullptr;                           /* [N] */
+	unsigned long long * d_sums = nullptr;               /* [3] */
+	std::vector<void *> allocations;
+};
+
+namespace {
+
+int fail(jdde_handle * h, int code, const std::string & msg)
+{
+	if (h)
+		h->err = msg;
+	else
+		g_create_error = msg;
+	return code;
+}
+
+#define JD_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return fail(h, JDDE_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+template <class T>
+int dev_alloc(jdde_handle * h, T ** p, size_t count)
+{
+	void * q = nullptr;
+	cudaError_t e = cudaMalloc(&q, count*sizeof(T) ? count*sizeof(T) : 1);
+	if (e != cudaSuccess)
+		return fail(h, e == cudaErrorMemoryAllocation ? JDDE_E_NOMEM : JDDE_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+	h->allocations.push_back(q);
+	*p = static_cast<T *>(q);
+	return JDDE_OK;
+}
+
+int ensure_stage(jdde_handle * h, size_t doubles)
+{
+	size_t const need = doubles*sizeof(double);
+	if (need <= h->in_bytes)
+		return JDDE_OK;
+	if (h->d_in)
+	{
+		JD_CUDA(h, cudaStreamSynchronize(h->stream));
+		JD_CUDA(h, cudaFree(h->d_in));
+		h->d_in = nullptr;
+		h->in_bytes = 0;
+	}
+	JD_CUDA(h, cudaMalloc((void **)&h->d_in, need*2));
+	h->in_bytes = need*2;
+	return JDDE_OK;
+}
+
+/* host → device copy of an input into the staging buffer (same stream as the kernels: ordered) */
+int stage_in(jdde_handle * h, const double * host, size_t count, double ** dev, size_t offset_doubles = 0)
+{
+	int rc = ensure_stage(h, offset_doubles+count);
+	if (rc) return rc;
+	*dev = h->d_in+offset_doubles;
+	JD_CUDA(h, cudaMemcpyAsync(*dev, host, count*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	return JDDE_OK;
+}
+
+int launch(jdde_handle * h, cudaKernel_t kernel, void ** args)
+{
+	if (!kernel)
+		return fail(h, JDDE_E_INVALID, "kernel image not loaded (jdde_load_rhs) or kernel missing from the image");
+	long long const N = h->desc.n_members;
+	unsigned const grid = (unsigned)((N + h->block - 1)/h->block);
+	JD_CUDA(h, cudaLaunchKernel((const void *)kernel, dim3(grid), dim3(h->block), args, 0, h->stream));
+	h->launches++;
+	return JDDE_OK;
+}
+
+int ready(jdde_handle * h)
+{
+	if (!h)
+		return JDDE_E_INVALID;
+	if (cudaSetDevice(h->desc.device) != cudaSuccess)
+		return fail(h, JDDE_E_CUDA, "cudaSetDevice failed");
+	return JDDE_OK;
+}
+
+int ready_to_integrate(jdde_handle * h)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!h->lib) return fail(h, JDDE_E_INVALID, "no kernel image loaded (jdde_load_rhs)");
+	if (!h->have_past) return fail(h, JDDE_E_INVALID, "no past set (jdde_set_past)");
+	if (!h->have_int_params) return fail(h, JDDE_E_INVALID, "integration parameters not set (jdde_set_integration_parameters)");
+	if (h->desc.n_params && !h->have_params) return fail(h, JDDE_E_INVALID, "control parameters not set (jdde_set_parameters)");
+	return JDDE_OK;
+}
+
+/* copy results to the caller and synchronise, if the caller wants anything */
+int finish(jdde_handle * h, double * out, const double * d_src, size_t count, int32_t * status)
+{
+	bool sync = false;
+	if (out)
+	{
+		JD_CUDA(h, cudaMemcpyAsync(out, d_src, count*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+		sync = true;
+	}
+	if (status)
+	{
+		JD_CUDA(h, cudaMemcpyAsync(status, h->P.status, (size_t)h->desc.n_members*sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+		sync = true;
+	}
+	if (sync)
+		JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	return JDDE_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int jdde_create(const jdde_desc * desc, jdde_handle ** out)
+{
+	if (!desc || !out)
+		return fail(nullptr, JDDE_E_INVALID, "null argument");
+	*out = nullptr;
+	if (desc->n < 1 || desc->n_basic < 1 || desc->n % desc->n_basic || desc->n_sites < 0 || desc->n_params < 0 || desc->n_members < 1)
+		return fail(nullptr, JDDE_E_INVALID, "invalid descriptor");
+	if (desc->ring_capacity < 4 || (desc->ring_capacity & (desc->ring_capacity-1)))
+		return fail(nullptr, JDDE_E_INVALID, "ring_capacity must be a power of two >= 4");
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count < 1)
+		return fail(nullptr, JDDE_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this engine has no CPU fallback)");
+	if (desc->device < 0 || desc->device >= count)
+		return fail(nullptr, JDDE_E_INVALID, "device ordinal out of range");
+
+	jdde_handle * h = new (std::nothrow) jdde_handle;
+	if (!h)
+		return fail(nullptr, JDDE_E_NOMEM, "out of host memory");
+	h->desc = *desc;
+	auto bail = [&](int rc) { g_create_error = h->err; jdde_destroy(h); return rc; };
+	if (cudaSetDevice(desc->device) != cudaSuccess)
+		return bail(fail(h, JDDE_E_CUDA, "cudaSetDevice failed"));
+	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+		return bail(fail(h, JDDE_E_CUDA, "cudaStreamCreate failed"));
+	h->own_stream = true;
+
+	size_t const N = (size_t)desc->n_members;
+	int const A = jdde_anchor_stride(desc->n);
+	jdde_problem & P = h->P;
+	P.n_members = desc->n_members;
+	P.cap = desc->ring_capacity;
+	P.anchor_stride = A;
+	int rc;
+	if ((rc = dev_alloc(h, &P.ring, N*(size_t)P.cap*A))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.par, N*(size_t)(desc->n_params ? desc->n_params : 1)))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.dt, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.last_pws, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.credit, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.last_start, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.first, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.last, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.current, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.count, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.status, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.cursor, N*(size_t)(desc->n_sites ? desc->n_sites : 1)))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.accepted, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.rejected, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.attempts, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.extra_rhs, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &h->d_out, N*(size_t)desc->n))) return bail(rc);
+	if ((rc = dev_alloc(h, &h->d_out2, N*(size_t)desc->n))) return bail(rc);
+	if ((rc = dev_alloc(h, &h->d_aux, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &h->d_aux2, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &h->d_sums, 3))) return bail(rc);
+	if (cudaMemsetAsync(P.status, 0, N*sizeof(int), h->stream) != cudaSuccess)
+		return bail(fail(h, JDDE_E_CUDA, "cudaMemset failed"));
+	*out = h;
+	return JDDE_OK;
+}
+
+int jdde_destroy(jdde_handle * h)
+{
+	if (!h)
+		return JDDE_OK;
+	cudaSetDevice(h->desc.device);
+	if (h->stream)
+		cudaStreamSynchronize(h->stream);
+	for (void * p : h->allocations)
+		cudaFree(p);
+	if (h->d_in)
+		cudaFree(h->d_in);
+	if (h->lib)
+		cudaLibraryUnload(h->lib);
+	if (h->own_stream && h->stream)
+		cudaStreamDestroy(h->stream);
+	delete h;
+	return JDDE_OK;
+}
+
+const char * jdde_last_error(const jdde_handle * h)
+{
+	return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!image || !len)
+		return fail(h, JDDE_E_INVALID, "empty image");
+	if (h->lib)
+	{
+		cudaLibraryUnload(h->lib);
+		h->lib = nullptr;
+		h->k = Kernels();
+	}
+	JD_CUDA(h, cudaLibraryLoadData(&h->lib, image, nullptr, nullptr, 0, nullptr, nullptr, 0));
+
+	void * dptr = nullptr;
+	size_t bytes = 0;
+	if (cudaLibraryGetGlobal(&dptr, &bytes, h->lib, "jdde_image_desc") != cudaSuccess || bytes != sizeof(jdde_image_desc_t))
+		return fail(h, JDDE_E_IMAGE, "image has no jdde_image_desc");
+	jdde_image_desc_t d;
+	JD_CUDA(h, cudaMemcpy(&d, dptr, sizeof(d), cudaMemcpyDeviceToHost));
+	if (d.magic != JDDE_IMAGE_MAGIC || d.abi != JDDE_ABI_VERSION)
+		return fail(h, JDDE_E_IMAGE, "image built for another ABI version");
+	if (d.n != h->desc.n || d.n_basic != h->desc.n_basic || d.n_sites != h->desc.n_sites || d.n_params != h->desc.n_params || d.anchor_stride != h->P.anchor_stride)
+	{
+		char buf[256];
+		snprintf(buf, sizeof buf, "image (n=%d, n_basic=%d, sites=%d, params=%d) does not match descriptor (n=%d, n_basic=%d, sites=%d, params=%d)",
+			d.n, d.n_basic, d.n_sites, d.n_params, h->desc.n, h->desc.n_basic, h->desc.n_sites, h->desc.n_params);
+		return fail(h, JDDE_E_IMAGE, buf);
+	}
+	h->block = d.block;
+
+	struct { const char * name; cudaKernel_t * slot; bool required; } const table[] = {
+		{"jdde_k_set_past", &h->k.set_past, true},
+		{"jdde_k_reset_controller", &h->k.reset_controller, true},
+		{"jdde_k_integrate", &h->k.integrate, true},
+		{"jdde_k_integrate_blindly", &h->k.integrate_blindly, true},
+		{"jdde_k_jump", &h->k.jump, true},
+		{"jdde_k_forget", &h->k.forget, true},
+		{"jdde_k_get", &h->k.get, true},
+		{"jdde_k_clear_status", &h->k.clear_status, true},
+		{"jdde_k_sum_counters", &h->k.sum_counters, true},
+		{"jdde_k_regrow", &h->k.regrow, true},
+		{"jdde_k_orthonormalise", &h->k.orthonormalise, false},
+	};
+	for (auto const & entry : table)
+	{
+		cudaError_t e = cudaLibraryGetKernel(entry.slot, h->lib, entry.name);
+		if (e != cudaSuccess)
+		{
+			*entry.slot = nullptr;
+			(void)cudaGetLastError();
+			if (entry.required)
+				return fail(h, JDDE_E_IMAGE, std::string("image lacks kernel ") + entry.name);
+		}
+	}
+	return JDDE_OK;
+}
+
+int jdde_set_stream(jdde_handle * h, void * cuda_stream)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	if (h->own_stream)
+	{
+		cudaStreamDestroy(h->stream);
+		h->own_stream = false;
+	}
+	h->stream = static_cast<cudaStream_t>(cuda_stream);
+	return JDDE_OK;
+}
+
+int jdde_synchronize(jdde_handle * h)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	return JDDE_OK;
+}
+
+int jdde_set_past(jdde_handle * h, int32_t n_anchors, const double * times, const double * states, const double * diffs, int32_t per_member)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!h->lib) return fail(h, JDDE_E_INVALID, "no kernel image loaded (jdde_load_rhs)");
+	if (n_anchors < 2)
+		return fail(h, JDDE_E_INVALID, "need at least two anchors (reference: _jitcdde.py:582)");
+	if (n_anchors+1 > h->P.cap)
+		return fail(h, JDDE_E_INVALID, "initial past does not fit into the ring; increase ring_capacity");
+	if (!times || !states || !diffs)
+		return fail(h, JDDE_E_INVALID, "null argument");
+	size_t const members = per_member ? (size_t)h->desc.n_members : 1;
+	size_t const nt = members*(size_t)n_anchors, ns = nt*(size_t)h->desc.n;
+	/* one staging buffer: [times | states | diffs] */
+	if ((rc = ensure_stage(h, nt+2*ns))) return rc;
+	double * d_times, * d_states, * d_diffs;
+	if ((rc = stage_in(h, times, nt, &d_times, 0))) return rc;
+	if ((rc = stage_in(h, states, ns, &d_states, nt))) return rc;
+	if ((rc = stage_in(h, diffs, ns, &d_diffs, nt+ns))) return rc;
+	int pm = per_member ? 1 : 0;
+	int na = n_anchors;
+	void * args[] = { &h->P, &na, &d_times, &d_states, &d_diffs, &pm };
+	if ((rc = launch(h, h->k.set_past, args))) return rc;
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	h->have_past = true;
+	return JDDE_OK;
+}
+
+int jdde_set_parameters(jdde_handle * h, const double * params, int32_t per_member)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	int const np = h->desc.n_params;
+	if (np == 0)
+		return JDDE_OK;
+	if (!params)
+		return fail(h, JDDE_E_INVALID, "null argument");
+	size_t const N = (size_t)h->desc.n_members;
+	/* transpose to [n_params][n_members] on the host: coalesced loads on the device */
+	std::vector<double> soa((size_t)np*N);
+	for (size_t m = 0; m < N; m++)
+		for (int k = 0; k < np; k++)
+			soa[(size_t)k*N+m] = per_member ? params[m*np+k] : params[k];
+	JD_CUDA(h, cudaMemcpyAsync(h->P.par, soa.data(), soa.size()*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	h->have_params = true;
+	return JDDE_OK;
+}
+
+int jdde_set_integration_parameters(jdde_handle * h, const jdde_int_params * p, double max_delay)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!h->lib) return fail(h, JDDE_E_INVALID, "no kernel image loaded (jdde_load_rhs)");
+	if (!p)
+		return fail(h, JDDE_E_INVALID, "null argument");
+	/* the assertions of the reference, _jitcdde.py:695-708 */
+	if (!(p->decrease_threshold >= 1.0) || !(p->increase_threshold <= 1.0) || !(p->max_factor >= 1.0) || !(p->min_factor <= 1.0)
+		|| !(p->safety_factor <= 1.0) || !(p->atol >= 0.0) || !(p->rtol >= 0.0) || !(p->pws_atol >= 0.0) || !(p->pws_rtol >= 0.0)
+		|| !(p->pws_max_iterations > 0) || !(p->pws_factor >= 2) || !(p->pws_base_increase_chance >= 0) || !(max_delay >= 0.0))
+		return fail(h, JDDE_E_INVALID, "integration parameter out of range (see _jitcdde.py:695-708)");
+	h->P.P = *p;
+	/* clipping of first_step / min_step, _jitcdde.py:688-693 */
+	if (h->P.P.first_step > h->P.P.max_step)
+		h->P.P.first_step = h->P.P.max_step;
+	if (h->P.P.min_step > h->P.P.first_step)
+		h->P.P.min_step = h->P.P.first_step;
+	h->P.max_delay = max_delay;
+	void * args[] = { &h->P };
+	if ((rc = launch(h, h->k.reset_controller, args))) return rc;
+	h->have_int_params = true;
+	return JDDE_OK;
+}
+
+static int run_integrate(jdde_handle * h, const double * targets, size_t count, int per_member, int n_steps, double * out_state, int n_out, int32_t * status)
+{
+	int rc;
+	double * d_targets;
+	if (!targets)
+		return fail(h, JDDE_E_INVALID, "null argument");
+	if ((rc = stage_in(h, targets, count, &d_targets))) return rc;
+	int pm = per_member ? 1 : 0;
+	long long budget = h->budget;
+	void * args[] = { &h->P, &d_targets, &pm, &n_steps, &h->d_out, &n_out, &budget };
+	if ((rc = launch(h, h->k.integrate, args))) return rc;
+	return finish(h, out_state, h->d_out, (size_t)h->desc.n_members*n_out, status);
+}
+
+int jdde_integrate(jdde_handle * h, const double * target, int32_t per_member, double * out_state, int32_t * status)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	return run_integrate(h, target, per_member ? (size_t)h->desc.n_members : 1, per_member, 0, out_state, h->desc.n, status);
+}
+
+int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double * steps, int32_t per_member, double * out_state, int32_t * status)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (n_steps < 1)
+		return fail(h, JDDE_E_INVALID, "n_steps must be positive (for an ODE the reference calls adjust_diff instead, _jitcdde.py:998-1000)");
+	return run_integrate(h, steps, (per_member ? (size_t)h->desc.n_members : 1)*(size_t)n_steps, per_member, n_steps, out_state, h->desc.n, status);
+}
+
+int jdde_integrate_blindly(jdde_handle * h, const double * target, int32_t per_member, double step, double * out_state, int32_t * status)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (!target)
+		return fail(h, JDDE_E_INVALID, "null argument");
+	double * d_targets;
+	if ((rc = stage_in(h, target, per_member ? (size_t)h->desc.n_members : 1, &d_targets))) return rc;
+	int pm = per_member ? 1 : 0;
+	void * args[] = { &h->P, &d_targets, &pm, &step, &h->d_out };
+	if ((rc = launch(h, h->k.integrate_blindly, args))) return rc;
+	return finish(h, out_state, h->d_out, (size_t)h->desc.n_members*h->desc.n, status);
+}
+
+static int run_jump(jdde_handle * h, int mode, const double * amplitude, int amp_pm, const double * time, int time_pm, double width, int forward, double * minima, double * maxima)
+{
+	int rc;
+	size_t const N = (size_t)h->desc.n_members;
+	int const n = h->desc.n;
+	double * d_amp = nullptr, * d_time = nullptr;
+	if (mode == 0)
+	{
+		if (!amplitude || !time)
+			return fail(h, JDDE_E_INVALID, "null argument");
+		size_t const na = (amp_pm ? N : 1)*(size_t)n, nt = time_pm ? N : 1;
+		std::vector<double> buf(na+nt);
+		memcpy(buf.data(), amplitude, na*sizeof(double));
+		memcpy(buf.data()+na, time, nt*sizeof(double));
+		if ((rc = stage_in(h, buf.data(), na+nt, &d_amp))) return rc;
+		JD_CUDA(h, cudaStreamSynchronize(h->stream));   /* buf is a temporary */
+		d_time = d_amp+na;
+	}
+	void * args[] = { &h->P, &mode, &d_amp, &amp_pm, &d_time, &time_pm, &width, &forward, &h->d_out, &h->d_out2 };
+	if ((rc = launch(h, h->k.jump, args))) return rc;
+	if (minima)
+		JD_CUDA(h, cudaMemcpyAsync(minima, h->d_out, N*n*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	if (maxima)
+		JD_CUDA(h, cudaMemcpyAsync(maxima, h->d_out2, N*n*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	if (minima || maxima)
+		JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	return JDDE_OK;
+}
+
+int jdde_jump(jdde_handle * h, const double * amplitude, int32_t amplitude_per_member, const double * time, int32_t time_per_member, double width, int32_t forward, double * minima, double * maxima)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (!(width >= 0))
+		return fail(h, JDDE_E_INVALID, "width must be non-negative (_jitcdde.py:1035)");
+	return run_jump(h, 0, amplitude, amplitude_per_member ? 1 : 0, time, time_per_member ? 1 : 0, width, forward ? 1 : 0, minima, maxima);
+}
+
+int jdde_adjust_diff(jdde_handle * h, double shift_ratio, double * minima, double * maxima)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	return run_jump(h, 1, nullptr, 0, nullptr, 0, shift_ratio, 0, minima, maxima);
+}
+
+int jdde_orthonormalise(jdde_handle * h, int32_t n_lyap, double delay, double * norms)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (h->desc.n == h->desc.n_basic || n_lyap < 0 || (n_lyap+1)*h->desc.n_basic > h->desc.n)
+		return fail(h, JDDE_E_INVALID, "orthonormalise needs n_basic < n and (n_lyap+1)·n_basic <= n");
+	const double * null_d = nullptr;
+	double * null_o = nullptr;
+	void * args[] = { &h->P, &n_lyap, &delay, &h->d_out2, &null_d, &null_o, &null_o };
+	if ((rc = launch(h, h->k.orthonormalise, args))) return rc;
+	return finish(h, norms, h->d_out2, (size_t)h->desc.n_members*n_lyap, nullptr);
+}
+
+int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t per_member, double * out_state, double * lyaps, double * delta_t, int32_t * status)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	int const nb = h->desc.n_basic;
+	if (h->desc.n == nb)
+		return fail(h, JDDE_E_INVALID, "integrate_lyap needs n_basic < n");
+	int n_lyap = h->desc.n/nb-1;
+	size_t const N = (size_t)h->desc.n_members;
+	/* old_t = get_t() (_jitcdde.py:1162) */
+	int what = 0;
+	void * gargs[] = { &h->P, &what, &h->d_aux };
+	if ((rc = launch(h, h->k.get, gargs))) return rc;
+	if ((rc = run_integrate(h, target, per_member ? N : 1, per_member, 0, nullptr, nb, nullptr))) return rc;
+	double delay = h->P.max_delay;
+	const double * old_t = h->d_aux;
+	void * args[] = { &h->P, &n_lyap, &delay, &h->d_out2, &old_t, &h->d_out2, &h->d_aux2 };
+	if ((rc = launch(h, h->k.orthonormalise, args))) return rc;
+	if (lyaps)
+		JD_CUDA(h, cudaMemcpyAsync(lyaps, h->d_out2, N*n_lyap*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	if (delta_t)
+		JD_CUDA(h, cudaMemcpyAsync(delta_t, h->d_aux2, N*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	return finish(h, out_state, h->d_out, N*nb, status);
+}
+
+static int run_get(jdde_handle * h, int what, double * out, size_t per_member_count)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!h->have_past) return fail(h, JDDE_E_INVALID, "no past set (jdde_set_past)");
+	if (!out) return fail(h, JDDE_E_INVALID, "null argument");
+	void * args[] = { &h->P, &what, &h->d_out2 };
+	if ((rc = launch(h, h->k.get, args))) return rc;
+	return finish(h, out, h->d_out2, (size_t)h->desc.n_members*per_member_count, nullptr);
+}
+
+int jdde_get_t(jdde_handle * h, double * t) { return run_get(h, 0, t, 1); }
+int jdde_get_current_state(jdde_handle * h, double * state) { return run_get(h, 1, state, h ? h->desc.n : 0); }
+int jdde_get_dt(jdde_handle * h, double * dt) { return run_get(h, 2, dt, 1); }
+
+int jdde_get_status(jdde_handle * h, int32_t * status)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!status) return fail(h, JDDE_E_INVALID, "null argument");
+	return finish(h, nullptr, nullptr, 0, status);
+}
+
+int jdde_get_counters(jdde_handle * h, int64_t * accepted, int64_t * rejected, int64_t * rhs_evals)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	size_t const N = (size_t)h->desc.n_members;
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	if (accepted)
+		JD_CUDA(h, cudaMemcpy(accepted, h->P.accepted, N*sizeof(int64_t), cudaMemcpyDeviceToHost));
+	if (rejected)
+		JD_CUDA(h, cudaMemcpy(rejected, h->P.rejected, N*sizeof(int64_t), cudaMemcpyDeviceToHost));
+	if (rhs_evals)
+	{
+		std::vector<long long> attempts(N), extra(N);
+		JD_CUDA(h, cudaMemcpy(attempts.data(), h->P.attempts, N*sizeof(long long), cudaMemcpyDeviceToHost));
+		JD_CUDA(h, cudaMemcpy(extra.data(), h->P.extra_rhs, N*sizeof(long long), cudaMemcpyDeviceToHost));
+		for (size_t m = 0; m < N; m++)
+			rhs_evals[m] = 3*attempts[m]+extra[m];
+	}
+	return JDDE_OK;
+}
+
+int jdde_sum_counters(jdde_handle * h, int64_t * accepted, int64_t * rejected, int64_t * rhs_evals)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!h->have_past) return fail(h, JDDE_E_INVALID, "no past set (jdde_set_past)");
+	JD_CUDA(h, cudaMemsetAsync(h->d_sums, 0, 3*sizeof(unsigned long long), h->stream));
+	void * args[] = { &h->P, &h->d_sums };
+	if ((rc = launch(h, h->k.sum_counters, args))) return rc;
+	unsigned long long sums[3];
+	JD_CUDA(h, cudaMemcpyAsync(sums, h->d_sums, sizeof sums, cudaMemcpyDeviceToHost, h->stream));
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	if (accepted) *accepted = (int64_t)sums[0];
+	if (rejected) *rejected = (int64_t)sums[1];
+	if (rhs_evals) *rhs_evals = (int64_t)sums[2];
+	return JDDE_OK;
+}
+
+int jdde_get_state(jdde_handle * h, int64_t member, int32_t max_anchors, int32_t * n_anchors, double * times, double * states, double * diffs)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!h->have_past) return fail(h, JDDE_E_INVALID, "no past set (jdde_set_past)");
+	if (member < 0 || member >= h->desc.n_members || !n_anchors)
+		return fail(h, JDDE_E_INVALID, "member out of range or null argument");
+	/* get_state() forgets first (_jitcdde.py:368) */
+	if (h->have_int_params)
+	{
+		void * args[] = { &h->P };
+		if ((rc = launch(h, h->k.forget, args))) return rc;
+	}
+	int first, last;
+	JD_CUDA(h, cudaMemcpyAsync(&first, h->P.first+member, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	JD_CUDA(h, cudaMemcpyAsync(&last, h->P.last+member, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	int const count = last-first+1;
+	*n_anchors = count;
+	if (count > max_anchors || !times || !states || !diffs)
+		return JDDE_OK;
+	int const A = h->P.anchor_stride, cap = h->P.cap, n = h->desc.n;
+	std::vector<double> ring((size_t)cap*A);
+	JD_CUDA(h, cudaMemcpy(ring.data(), h->P.ring+(size_t)member*cap*A, ring.size()*sizeof(double), cudaMemcpyDeviceToHost));
+	for (int k = 0; k < count; k++)
+	{
+		const double * a = ring.data()+(size_t)((first+k) & (cap-1))*A;
+		times[k] = a[0];
+		memcpy(states+(size_t)k*n, a+1, n*sizeof(double));
+		memcpy(diffs+(size_t)k*n, a+1+n, n*sizeof(double));
+	}
+	return JDDE_OK;
+}
+
+int jdde_grow_ring(jdde_handle * h, int32_t new_capacity)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!h->lib) return fail(h, JDDE_E_INVALID, "no kernel image loaded (jdde_load_rhs)");
+	if (new_capacity <= h->P.cap || (new_capacity & (new_capacity-1)))
+		return fail(h, JDDE_E_INVALID, "new capacity must be a larger power of two");
+	size_t const N = (size_t)h->desc.n_members;
+	double * new_ring = nullptr;
+	cudaError_t e = cudaMalloc((void **)&new_ring, N*(size_t)new_capacity*h->P.anchor_stride*sizeof(double));
+	if (e != cudaSuccess)
+		return fail(h, JDDE_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+	if (h->have_past)
+	{
+		int nc = new_capacity;
+		void * args[] = { &h->P, &new_ring, &nc };
+		if ((rc = launch(h, h->k.regrow, args))) { cudaFree(new_ring); return rc; }
+	}
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	for (auto & p : h->allocations)
+		if (p == h->P.ring)
+			p = new_ring;
+	cudaFree(h->P.ring);
+	h->P.ring = new_ring;
+	h->P.cap = new_capacity;
+	h->desc.ring_capacity = new_capacity;
+	return JDDE_OK;
+}
+
+int jdde_clear_status(jdde_handle * h, int32_t code)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	int c = code;
+	void * args[] = { &h->P, &c };
+	return launch(h, h->k.clear_status, args);
+}
+
+int jdde_set_attempt_budget(jdde_handle * h, int64_t attempts)
+{
+	if (!h || attempts < 1)
+		return fail(h, JDDE_E_INVALID, "budget must be positive");
+	h->budget = attempts;
+	return JDDE_OK;
+}
+
+int64_t jdde_launch_count(const jdde_handle * h) { return h ? h->launches : 0; }
+uint64_t jdde_device_result(const jdde_handle * h) { return h ? (uint64_t)(uintptr_t)h->d_out : 0; }
+
+} // extern "C"

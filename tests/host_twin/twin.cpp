@@ -1,0 +1,302 @@
+/*
+ * twin.cpp — TEST SCAFFOLDING, never part of the product.
+ *
+ * Compiles the engine header (jitcdde_b200/csrc/jdde_engine.cuh, whose functions are
+ * __host__ __device__) with g++ and implements the C ABI of include/jitcdde_b200.h on host
+ * memory by looping over the members. This lets the CPU test-suite (`-m "not gpu"`) drive the
+ * very same step/controller/lookup code through the very same Python classes and compare it
+ * bit for bit with the oracle — without a GPU. The product library (jdde_runtime.cu) has no
+ * such path: it fails without a CUDA device. Tests select this twin explicitly by
+ * monkeypatching jitcdde_b200._capi.load_library (tests/conftest.py).
+ */
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "jdde_engine.cuh"
+
+struct jdde_handle
+{
+	jdde_desc desc{};
+	jdde_problem P{};
+	std::vector<double> ring, par, dt, last_pws, credit, last_start, out, out2, aux, aux2;
+	std::vector<int> first, last, current, count, status, cursor;
+	std::vector<long long> accepted, rejected, attempts, extra_rhs;
+	bool have_past = false, have_params = false, have_int = false;
+	long long budget = 1ll << 24;
+	long long launches = 0;
+	std::string err;
+};
+
+static std::string g_err;
+static int fail(jdde_handle * h, int code, const char * msg) { (h ? h->err : g_err) = msg; return code; }
+
+static void bind(jdde_handle * h)
+{
+	jdde_problem & P = h->P;
+	P.ring = h->ring.data(); P.par = h->par.data(); P.dt = h->dt.data(); P.last_pws = h->last_pws.data();
+	P.credit = h->credit.data(); P.last_start = h->last_start.data(); P.first = h->first.data(); P.last = h->last.data();
+	P.current = h->current.data(); P.count = h->count.data(); P.status = h->status.data(); P.cursor = h->cursor.data();
+	P.accepted = h->accepted.data(); P.rejected = h->rejected.data(); P.attempts = h->attempts.data(); P.extra_rhs = h->extra_rhs.data();
+}
+
+extern "C" {
+
+int jdde_create(const jdde_desc * d, jdde_handle ** out)
+{
+	if (!d || !out) return fail(nullptr, JDDE_E_INVALID, "null argument");
+	if (d->n != JD_N || d->n_basic != JD_NBASIC || d->n_sites != JD_NSITES || d->n_params != JD_NPARAMS)
+		return fail(nullptr, JDDE_E_IMAGE, "twin compiled for another system");
+	if (d->ring_capacity < 4 || (d->ring_capacity & (d->ring_capacity-1)))
+		return fail(nullptr, JDDE_E_INVALID, "ring_capacity must be a power of two >= 4");
+	jdde_handle * h = new jdde_handle;
+	h->desc = *d;
+	size_t const N = (size_t)d->n_members;
+	h->ring.assign(N*d->ring_capacity*JD_A, 0.0);
+	h->par.assign(N*(JD_NPARAMS ? JD_NPARAMS : 1), 0.0);
+	for (auto v : { &h->dt, &h->last_pws, &h->credit, &h->last_start, &h->aux, &h->aux2 }) v->assign(N, 0.0);
+	h->out.assign(N*JD_N, 0.0); h->out2.assign(N*JD_N, 0.0);
+	for (auto v : { &h->first, &h->last, &h->current, &h->count, &h->status }) v->assign(N, 0);
+	h->cursor.assign(N*(JD_NSITES ? JD_NSITES : 1), 0);
+	for (auto v : { &h->accepted, &h->rejected, &h->attempts, &h->extra_rhs }) v->assign(N, 0);
+	h->P.n_members = d->n_members; h->P.cap = d->ring_capacity; h->P.anchor_stride = JD_A;
+	bind(h);
+	*out = h;
+	return JDDE_OK;
+}
+
+int jdde_destroy(jdde_handle * h) { delete h; return JDDE_OK; }
+const char * jdde_last_error(const jdde_handle * h) { return h ? h->err.c_str() : g_err.c_str(); }
+int jdde_load_rhs(jdde_handle *, const void *, size_t) { return JDDE_OK; }
+int jdde_set_stream(jdde_handle *, void *) { return JDDE_OK; }
+int jdde_synchronize(jdde_handle *) { return JDDE_OK; }
+
+int jdde_set_past(jdde_handle * h, int32_t k, const double * times, const double * states, const double * diffs, int32_t pm)
+{
+	if (k < 2) return fail(h, JDDE_E_INVALID, "need at least two anchors");
+	if (k+1 > h->P.cap) return fail(h, JDDE_E_INVALID, "initial past does not fit into the ring; increase ring_capacity");
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_set_past(h->P, m, k, times, states, diffs, pm);
+	h->have_past = true; h->launches++;
+	return JDDE_OK;
+}
+
+int jdde_set_parameters(jdde_handle * h, const double * params, int32_t pm)
+{
+	size_t const N = (size_t)h->P.n_members;
+	for (size_t m = 0; m < N; m++)
+		for (int k = 0; k < JD_NPARAMS; k++)
+			h->par[(size_t)k*N+m] = pm ? params[m*JD_NPARAMS+k] : params[k];
+	h->have_params = true;
+	return JDDE_OK;
+}
+
+int jdde_set_integration_parameters(jdde_handle * h, const jdde_int_params * p, double max_delay)
+{
+	if (!(p->decrease_threshold >= 1.0) || !(p->increase_threshold <= 1.0) || !(p->max_factor >= 1.0) || !(p->min_factor <= 1.0)
+		|| !(p->safety_factor <= 1.0) || !(p->atol >= 0.0) || !(p->rtol >= 0.0) || !(p->pws_atol >= 0.0) || !(p->pws_rtol >= 0.0)
+		|| !(p->pws_max_iterations > 0) || !(p->pws_factor >= 2) || !(p->pws_base_increase_chance >= 0) || !(max_delay >= 0.0))
+		return fail(h, JDDE_E_INVALID, "integration parameter out of range (see _jitcdde.py:695-708)");
+	h->P.P = *p;
+	if (h->P.P.first_step > h->P.P.max_step) h->P.P.first_step = h->P.P.max_step;
+	if (h->P.P.min_step > h->P.P.first_step) h->P.P.min_step = h->P.P.first_step;
+	h->P.max_delay = max_delay;
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_reset_controller(h->P, m);
+	h->have_int = true; h->launches++;
+	return JDDE_OK;
+}
+
+static int ready(jdde_handle * h)
+{
+	if (!h->have_past) return fail(h, JDDE_E_INVALID, "no past set (jdde_set_past)");
+	if (!h->have_int) return fail(h, JDDE_E_INVALID, "integration parameters not set (jdde_set_integration_parameters)");
+	if (JD_NPARAMS && !h->have_params) return fail(h, JDDE_E_INVALID, "control parameters not set (jdde_set_parameters)");
+	return 0;
+}
+
+static void give(jdde_handle * h, double * out, const std::vector<double> & src, size_t count, int32_t * status)
+{
+	if (out) memcpy(out, src.data(), count*sizeof(double));
+	if (status) memcpy(status, h->status.data(), (size_t)h->P.n_members*sizeof(int32_t));
+}
+
+int jdde_integrate(jdde_handle * h, const double * target, int32_t pm, double * out, int32_t * status)
+{
+	if (int rc = ready(h)) return rc;
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_integrate(h->P, m, target, pm, 0, h->out.data(), JD_N, h->budget);
+	h->launches++;
+	give(h, out, h->out, (size_t)h->P.n_members*JD_N, status);
+	return JDDE_OK;
+}
+
+int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double * steps, int32_t pm, double * out, int32_t * status)
+{
+	if (int rc = ready(h)) return rc;
+	if (n_steps < 1) return fail(h, JDDE_E_INVALID, "n_steps must be positive");
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_integrate(h->P, m, steps, pm, n_steps, h->out.data(), JD_N, h->budget);
+	h->launches++;
+	give(h, out, h->out, (size_t)h->P.n_members*JD_N, status);
+	return JDDE_OK;
+}
+
+int jdde_integrate_blindly(jdde_handle * h, const double * target, int32_t pm, double step, double * out, int32_t * status)
+{
+	if (int rc = ready(h)) return rc;
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_integrate_blindly(h->P, m, target, pm, step, h->out.data());
+	h->launches++;
+	give(h, out, h->out, (size_t)h->P.n_members*JD_N, status);
+	return JDDE_OK;
+}
+
+int jdde_jump(jdde_handle * h, const double * amplitude, int32_t apm, const double * time, int32_t tpm, double width, int32_t forward, double * minima, double * maxima)
+{
+	if (int rc = ready(h)) return rc;
+	if (!(width >= 0)) return fail(h, JDDE_E_INVALID, "width must be non-negative (_jitcdde.py:1035)");
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_jump(h->P, m, 0, amplitude, apm, time, tpm, width, forward, h->out.data(), h->out2.data());
+	h->launches++;
+	give(h, minima, h->out, (size_t)h->P.n_members*JD_N, nullptr);
+	give(h, maxima, h->out2, (size_t)h->P.n_members*JD_N, nullptr);
+	return JDDE_OK;
+}
+
+int jdde_adjust_diff(jdde_handle * h, double shift_ratio, double * minima, double * maxima)
+{
+	if (int rc = ready(h)) return rc;
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_jump(h->P, m, 1, nullptr, 0, nullptr, 0, shift_ratio, 0, h->out.data(), h->out2.data());
+	h->launches++;
+	give(h, minima, h->out, (size_t)h->P.n_members*JD_N, nullptr);
+	give(h, maxima, h->out2, (size_t)h->P.n_members*JD_N, nullptr);
+	return JDDE_OK;
+}
+
+int jdde_orthonormalise(jdde_handle * h, int32_t n_lyap, double delay, double * norms)
+{
+#if JD_NBASIC != JD_N
+	if (int rc = ready(h)) return rc;
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_orthonormalise(h->P, m, n_lyap, delay, h->out2.data(), nullptr, nullptr, nullptr);
+	h->launches++;
+	give(h, norms, h->out2, (size_t)h->P.n_members*n_lyap, nullptr);
+	return JDDE_OK;
+#else
+	(void)n_lyap; (void)delay; (void)norms;
+	return fail(h, JDDE_E_INVALID, "orthonormalise needs n_basic < n and (n_lyap+1)·n_basic <= n");
+#endif
+}
+
+int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t pm, double * out_state, double * lyaps, double * delta_t, int32_t * status)
+{
+#if JD_NBASIC != JD_N
+	if (int rc = ready(h)) return rc;
+	int const n_lyap = JD_N/JD_NBASIC-1;
+	for (long long m = 0; m < h->P.n_members; m++)
+		h->aux[m] = h->ring[((size_t)m*h->P.cap + (h->current[m] & (h->P.cap-1)))*JD_A];
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_integrate(h->P, m, target, pm, 0, h->out.data(), JD_NBASIC, h->budget);
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_orthonormalise(h->P, m, n_lyap, h->P.max_delay, h->out2.data(), h->aux.data(), h->out2.data(), h->aux2.data());
+	h->launches += 3;
+	give(h, lyaps, h->out2, (size_t)h->P.n_members*n_lyap, nullptr);
+	give(h, delta_t, h->aux2, (size_t)h->P.n_members, nullptr);
+	give(h, out_state, h->out, (size_t)h->P.n_members*JD_NBASIC, status);
+	return JDDE_OK;
+#else
+	(void)target; (void)pm; (void)out_state; (void)lyaps; (void)delta_t; (void)status;
+	return fail(h, JDDE_E_INVALID, "integrate_lyap needs n_basic < n");
+#endif
+}
+
+int jdde_get_t(jdde_handle * h, double * t)
+{
+	for (long long m = 0; m < h->P.n_members; m++)
+		t[m] = h->ring[((size_t)m*h->P.cap + (h->current[m] & (h->P.cap-1)))*JD_A];
+	return JDDE_OK;
+}
+int jdde_get_dt(jdde_handle * h, double * dt) { memcpy(dt, h->dt.data(), h->dt.size()*sizeof(double)); return JDDE_OK; }
+int jdde_get_current_state(jdde_handle * h, double * s)
+{
+	for (long long m = 0; m < h->P.n_members; m++)
+		memcpy(s+(size_t)m*JD_N, &h->ring[((size_t)m*h->P.cap + (h->last[m] & (h->P.cap-1)))*JD_A+1], JD_N*sizeof(double));
+	return JDDE_OK;
+}
+int jdde_get_status(jdde_handle * h, int32_t * status) { give(h, nullptr, h->out, 0, status); return JDDE_OK; }
+
+int jdde_get_counters(jdde_handle * h, int64_t * a, int64_t * r, int64_t * f)
+{
+	for (long long m = 0; m < h->P.n_members; m++)
+	{
+		if (a) a[m] = h->accepted[m];
+		if (r) r[m] = h->rejected[m];
+		if (f) f[m] = 3*h->attempts[m]+h->extra_rhs[m];
+	}
+	return JDDE_OK;
+}
+
+int jdde_sum_counters(jdde_handle * h, int64_t * a, int64_t * r, int64_t * f)
+{
+	int64_t sa = 0, sr = 0, sf = 0;
+	for (long long m = 0; m < h->P.n_members; m++)
+	{
+		sa += h->accepted[m]; sr += h->rejected[m]; sf += 3*h->attempts[m]+h->extra_rhs[m];
+	}
+	if (a) *a = sa;
+	if (r) *r = sr;
+	if (f) *f = sf;
+	return JDDE_OK;
+}
+
+int jdde_get_state(jdde_handle * h, int64_t member, int32_t max_anchors, int32_t * n_anchors, double * times, double * states, double * diffs)
+{
+	if (!h->have_past) return fail(h, JDDE_E_INVALID, "no past set (jdde_set_past)");
+	if (member < 0 || member >= h->P.n_members || !n_anchors) return fail(h, JDDE_E_INVALID, "member out of range or null argument");
+	if (h->have_int)
+		for (long long m = 0; m < h->P.n_members; m++)
+			jdde::member_forget(h->P, m);
+	int const first = h->first[member], count = h->last[member]-first+1;
+	*n_anchors = count;
+	if (count > max_anchors || !times) return JDDE_OK;
+	for (int k = 0; k < count; k++)
+	{
+		const double * a = &h->ring[((size_t)member*h->P.cap + ((first+k) & (h->P.cap-1)))*JD_A];
+		times[k] = a[0];
+		memcpy(states+(size_t)k*JD_N, a+1, JD_N*sizeof(double));
+		memcpy(diffs+(size_t)k*JD_N, a+1+JD_N, JD_N*sizeof(double));
+	}
+	return JDDE_OK;
+}
+
+int jdde_grow_ring(jdde_handle * h, int32_t new_cap)
+{
+	if (new_cap <= h->P.cap || (new_cap & (new_cap-1))) return fail(h, JDDE_E_INVALID, "new capacity must be a larger power of two");
+	size_t const N = (size_t)h->P.n_members;
+	std::vector<double> nr(N*new_cap*JD_A, 0.0);
+	if (h->have_past)
+		for (size_t m = 0; m < N; m++)
+		{
+			for (int k = h->first[m]; k <= h->last[m]; k++)
+				memcpy(&nr[(m*new_cap + (k & (new_cap-1)))*JD_A], &h->ring[(m*h->P.cap + (k & (h->P.cap-1)))*JD_A], JD_A*sizeof(double));
+			if (h->status[m] == JDDE_STATUS_OVERFLOW) h->status[m] = JDDE_STATUS_OK;
+		}
+	h->ring.swap(nr);
+	h->P.cap = new_cap; h->desc.ring_capacity = new_cap;
+	bind(h);
+	return JDDE_OK;
+}
+
+int jdde_clear_status(jdde_handle * h, int32_t code)
+{
+	for (auto & s : h->status) if (s == code) s = JDDE_STATUS_OK;
+	return JDDE_OK;
+}
+int jdde_set_attempt_budget(jdde_handle * h, int64_t attempts) { if (attempts < 1) return fail(h, JDDE_E_INVALID, "budget must be positive"); h->budget = attempts; return JDDE_OK; }
+int64_t jdde_launch_count(const jdde_handle * h) { return h->launches; }
+uint64_t jdde_device_result(const jdde_handle *) { return 0; }
+
+} // extern "C"

@@ -1,0 +1,54 @@
+"""
+Builds and loads the host twin of the engine (tests/host_twin/twin.cpp) — TEST SCAFFOLDING.
+
+The twin is the engine header compiled with g++ behind the same C ABI, so that the CPU
+test-suite can run the product's Python classes and step logic without a GPU and compare
+them with the oracle. It is selected only by the `use_twin` context manager below, which
+patches jitcdde_b200._capi.load_library for the duration of a test.
+"""
+
+import contextlib
+import ctypes
+import os
+import subprocess
+
+from jitcdde_b200 import _build, _capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_OUT = os.path.join(_HERE, "host_twin", "_build")
+
+
+def build_twin(program, n_basic=None):
+	n_basic = n_basic or program.n
+	os.makedirs(_OUT, exist_ok=True)
+	rhs = os.path.join(_OUT, f"rhs_{program.key}.inc")
+	with open(rhs, "w") as f:
+		f.write(program.body)
+	so = os.path.join(_OUT, f"twin_{program.key}_{n_basic}.so")
+	src = os.path.join(_HERE, "host_twin", "twin.cpp")
+	deps = [src] + [os.path.join(_build.CSRC, x) for x in ("jdde_engine.cuh", "jdde_math.h", "jdde_abi.h")]
+	if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+		subprocess.run([
+			"g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+			f"-DJD_N={program.n}", f"-DJD_NBASIC={n_basic}", f"-DJD_NSITES={program.n_sites}",
+			f"-DJD_NPARAMS={program.n_params}", f'-DJD_RHS_FILE="{rhs}"',
+			f"-I{_build.CSRC}", src, "-o", so, "-lm",
+		], check=True)
+	lib = ctypes.CDLL(so)
+	for name, (restype, argtypes) in _capi.SIGNATURES.items():
+		fn = getattr(lib, name)
+		fn.restype = restype
+		fn.argtypes = argtypes
+	return lib
+
+
+@contextlib.contextmanager
+def use_twin(program, n_basic=None):
+	"""Within this context jitcdde_b200 talks to the host twin instead of libjitcdde_b200.so."""
+	lib = build_twin(program, n_basic)
+	saved = _capi.load_library
+	_capi.load_library = lambda path=None: lib
+	try:
+		yield lib
+	finally:
+		_capi.load_library = saved

@@ -114,6 +114,9 @@ int jdde_set_parameters(jdde_handle * h, const double * params, int32_t per_memb
  * (_jitcdde.py:710-728). max_delay is the `forget` horizon (_jitcdde.py:835). */
 int jdde_set_integration_parameters(jdde_handle * h, const jdde_int_params * p, double max_delay);
 
+/* Change only the `forget` horizon (attribute jitcdde.max_delay), keeping step size and counters. */
+int jdde_set_max_delay(jdde_handle * h, double max_delay);
+
 /* ---- integration -------------------------------------------------------------------- */
 
 /* jitcdde.integrate (_jitcdde.py:807-836): adaptive steps until t >= target, state at target by
@@ -127,6 +130,12 @@ int jdde_integrate(jdde_handle * h, const double * target, int32_t per_member, d
  * adaptive steps capped so that one lands on t + step; steps [n_steps] or [n_members][n_steps]
  * (the host side computes them with _propagate_delays, :75-86). */
 int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double * steps, int32_t per_member, double * out_state, int32_t * status);
+
+/* Repeat the last jdde_integrate / jdde_step_on_discontinuities / jdde_integrate_lyap call after
+ * members stopped with JDDE_STATUS_OVERFLOW (then call jdde_grow_ring first) or JDDE_STATUS_BUDGET
+ * (jdde_clear_status): stopped members continue where they were, finished members are not stepped
+ * again. Outputs as for the original call (lyaps/delta_t may be NULL unless it was integrate_lyap). */
+int jdde_resume(jdde_handle * h, double * out_state, double * lyaps, double * delta_t, int32_t * status);
 
 /* integrate_blindly (_jitcdde.py:880-933): fixed steps, no error control; step <= 0 means max_step.
  * target == t performs adjust_diff() as the reference does. out_state = state of the last anchor. */
@@ -148,6 +157,10 @@ int jdde_orthonormalise(jdde_handle * h, int32_t n_lyap, double delay, double * 
 /* jitcdde_lyap.integrate (_jitcdde.py:1141-1172): out_state [n_members][n_basic],
  * lyaps [n_members][n_lyap] = log(norms)/delta_t (0 where delta_t == 0), delta_t [n_members]. */
 int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t per_member, double * out_state, double * lyaps, double * delta_t, int32_t * status);
+
+/* jitcdde_lyap.integrate_blindly (_jitcdde.py:1191-1209): fixed steps, orthonormalising after every
+ * step; lyaps = average over the steps of log(norms)/dt; total_time [n_members]. */
+int jdde_integrate_blindly_lyap(jdde_handle * h, const double * target, int32_t per_member, double step, double * out_state, double * lyaps, double * total_time, int32_t * status);
 
 /* ---- inspection ----------------------------------------------------------------------- */
 

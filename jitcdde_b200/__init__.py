@@ -1,0 +1,43 @@
+"""
+jitcdde_b200 — B200-native integration engine for delay differential equations with
+the user-facing API of neurophysik/jitcdde (reference export list:
+/root/reference/jitcdde/__init__.py:1).
+
+    from jitcdde_b200 import jitcdde, y, t
+    DDE = jitcdde([0.25*y(0,t-15)/(1+y(0,t-15)**10) - 0.1*y(0)])
+    DDE.constant_past([1.0]); DDE.step_on_discontinuities(); DDE.integrate(100.)
+
+The integrator runs as CUDA kernels for sm_100a behind a C ABI
+(include/jitcdde_b200.h); there is no CPU fallback. Ensembles of trajectories
+(`n_members=N`) are the data-parallel axis. Scope and design: DESIGN.md.
+"""
+
+from ._symbols import anchors, current_y, dy, past_dy, past_y, quadrature, t, y
+from ._jitcdde import UnsuccessfulIntegration, jitcdde, jitcdde_lyap, _find_max_delay, _propagate_delays
+from ._codegen import get_delays as _get_delays
+
+
+def shard(n_members, rank, world_size):
+	"""Contiguous block of members [start, stop) that process `rank` of `world_size` integrates.
+	Ensemble members are independent, so multi-GPU runs (one process per GPU) need no
+	communication until results are gathered."""
+	base, extra = divmod(n_members, world_size)
+	start = rank*base + min(rank, extra)
+	return start, start + base + (1 if rank < extra else 0)
+
+
+def _out_of_scope(name):
+	def stub(*args, **kwargs):
+		raise NotImplementedError(f"{name} is outside the accelerated path of this package (see DESIGN.md, scope).")
+	stub.__name__ = name
+	return stub
+
+jitcdde_input = _out_of_scope("jitcdde_input")
+jitcdde_restricted_lyap = _out_of_scope("jitcdde_restricted_lyap")
+jitcdde_transversal_lyap = _out_of_scope("jitcdde_transversal_lyap")
+input = _out_of_scope("input")  # noqa: A001
+
+__all__ = [
+	"UnsuccessfulIntegration", "anchors", "current_y", "dy", "jitcdde", "jitcdde_lyap",
+	"past_dy", "past_y", "quadrature", "t", "y", "shard",
+]

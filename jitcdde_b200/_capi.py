@@ -55,7 +55,10 @@ SIGNATURES = {
 	"jdde_set_integration_parameters": (ctypes.c_int, [_H, ctypes.POINTER(IntParams), ctypes.c_double]),
 	"jdde_integrate": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, c_int32_p]),
 	"jdde_step_on_discontinuities": (ctypes.c_int, [_H, ctypes.c_int32, c_double_p, ctypes.c_int32, c_double_p, c_int32_p]),
+	"jdde_resume": (ctypes.c_int, [_H, c_double_p, c_double_p, c_double_p, c_int32_p]),
 	"jdde_integrate_blindly": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_int32_p]),
+	"jdde_integrate_blindly_lyap": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_double_p, c_double_p, c_int32_p]),
+	"jdde_set_max_delay": (ctypes.c_int, [_H, ctypes.c_double]),
 	"jdde_jump": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, ctypes.c_int32, ctypes.c_double, ctypes.c_int32, c_double_p, c_double_p]),
 	"jdde_adjust_diff": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_double_p]),
 	"jdde_orthonormalise": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_double, c_double_p]),
@@ -195,12 +198,37 @@ class Engine:
 		self._check(self.lib.jdde_step_on_discontinuities(self._h, steps.shape[-1], _dp(steps), pm, _dp(out), status.ctypes.data_as(c_int32_p)))
 		return out, status
 
+	def resume(self, lyap=False):
+		"""repeat the last integrate / step_on_discontinuities / integrate_lyap call for members that stopped"""
+		status = np.empty(self.N, dtype=np.int32)
+		if lyap:
+			n_lyap = self.n//self.n_basic-1
+			state, lyaps, delta_t = np.empty((self.N, self.n_basic)), np.empty((self.N, n_lyap)), np.empty(self.N)
+			self._check(self.lib.jdde_resume(self._h, _dp(state), _dp(lyaps), _dp(delta_t), status.ctypes.data_as(c_int32_p)))
+			return state, lyaps, delta_t, status
+		out = np.empty((self.N, self.n))
+		self._check(self.lib.jdde_resume(self._h, _dp(out), None, None, status.ctypes.data_as(c_int32_p)))
+		return out, status
+
 	def integrate_blindly(self, target, step):
 		target, pm = self._targets(target)
 		out = np.empty((self.N, self.n))
 		status = np.empty(self.N, dtype=np.int32)
 		self._check(self.lib.jdde_integrate_blindly(self._h, _dp(target), pm, float(step or 0.0), _dp(out), status.ctypes.data_as(c_int32_p)))
 		return out, status
+
+	def integrate_blindly_lyap(self, target, step):
+		target, pm = self._targets(target)
+		n_lyap = self.n//self.n_basic-1
+		state = np.empty((self.N, self.n_basic))
+		lyaps = np.empty((self.N, n_lyap))
+		total = np.empty(self.N)
+		status = np.empty(self.N, dtype=np.int32)
+		self._check(self.lib.jdde_integrate_blindly_lyap(self._h, _dp(target), pm, float(step or 0.0), _dp(state), _dp(lyaps), _dp(total), status.ctypes.data_as(c_int32_p)))
+		return state, lyaps, total, status
+
+	def set_max_delay(self, max_delay):
+		self._check(self.lib.jdde_set_max_delay(self._h, float(max_delay)))
 
 	def jump(self, amplitude, time, width, forward):
 		amplitude = _f64(amplitude)

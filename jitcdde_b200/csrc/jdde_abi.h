@@ -44,6 +44,8 @@ typedef struct jdde_problem
 	long long * rejected;
 	long long * attempts;
 	long long * extra_rhs;
+	int * resume_index;      /* step_on_discontinuities: index of the step a member stopped in (n_steps: done) */
+	double * resume_target;  /* ... and the target time of that step */
 	long long n_members;
 	int cap;
 	int anchor_stride;

@@ -646,41 +646,6 @@ JD_FN void adjust_diff(Member & M, jdde_problem const & P, double const shift_ra
 	apply_jump(M, P, zero, t_last-width, width, minima, maxima);
 }
 
-/* integrate_blindly, _jitcdde.py:880-933 */
-JD_FN void integrate_blindly(Member & M, jdde_problem const & P, double const target, double step, double * const out)
-{
-	if (!(step > 0))
-		step = P.P.max_step;
-	double const total = target-M.cur_t;
-	if (total > 0)
-	{
-		if (total < step)
-			step = total;
-		long long const number = (long long) rint(total/step);   /* Python round(): ties to even */
-		double const dt = total/number;
-		for (long long k = 0; k < number && M.status == JDDE_STATUS_OK; k++)
-		{
-			if (!ensure_room(M, P.max_delay))
-				break;
-			get_next_step(M, dt);
-			accept_step(M);
-			M.accepted++;
-			forget(M, P.max_delay);
-		}
-	}
-	else if (total == 0)
-	{
-		double mi[JD_N], ma[JD_N];
-		adjust_diff(M, P, 1e-4, mi, ma);
-	}
-	else
-		M.status = JDDE_STATUS_BACKWARDS;
-	/* get_current_state, jitced_template.c:330-334: state of the last anchor */
-	double const * const w = M.slot(M.last);
-	for (int i = 0; i < JD_N; i++)
-		out[i] = w[1+i];
-}
-
 /* ------------------------------------------------------------------ Lyapunov exponents */
 #if JD_NBASIC != JD_N
 
@@ -797,6 +762,70 @@ JD_FN void orthonormalise(Member & M, int const n_lyap, double const delay, doub
 }
 #endif
 
+/* integrate_blindly, _jitcdde.py:880-933; with `lyaps` the variant of jitcdde_lyap (:1191-1209):
+ * orthonormalise after every step and average log(norms)/dt */
+JD_FN void integrate_blindly(Member & M, jdde_problem const & P, double const target, double step, double * const out, int const n_out, double * const lyaps, double * const total_time)
+{
+	if (!(step > 0))
+		step = P.P.max_step;
+	double const total = target-M.cur_t;
+	if (total_time)
+		*total_time = total;
+#if JD_NBASIC != JD_N
+	int const n_lyap = JD_N/JD_NBASIC-1;
+	double lyap_sum[JD_N/JD_NBASIC];
+	for (int i = 0; i < n_lyap; i++)
+		lyap_sum[i] = 0.0;
+#endif
+	if (total > 0)
+	{
+		if (total < step)
+			step = total;
+		long long const number = (long long) rint(total/step);   /* Python round(): ties to even */
+		double const dt = total/number;
+		for (long long k = 0; k < number && M.status == JDDE_STATUS_OK; k++)
+		{
+			if (!ensure_room(M, P.max_delay))
+				break;
+			get_next_step(M, dt);
+			accept_step(M);
+			M.accepted++;
+			forget(M, P.max_delay);
+#if JD_NBASIC != JD_N
+			if (lyaps)
+			{
+				double norms[JD_N/JD_NBASIC];
+				orthonormalise(M, n_lyap, P.max_delay, norms);
+				reload_current(M);
+				for (int i = 0; i < n_lyap; i++)
+					lyap_sum[i] += log(norms[i])/dt;
+			}
+#endif
+		}
+#if JD_NBASIC != JD_N
+		if (lyaps)
+			for (int i = 0; i < n_lyap; i++)
+				lyaps[i] = lyap_sum[i]/number;
+#endif
+	}
+	else if (total == 0)
+	{
+		double mi[JD_N], ma[JD_N];
+		adjust_diff(M, P, 1e-4, mi, ma);
+#if JD_NBASIC != JD_N
+		if (lyaps)
+			for (int i = 0; i < n_lyap; i++)
+				lyaps[i] = 0.0;
+#endif
+	}
+	else
+		M.status = JDDE_STATUS_BACKWARDS;
+	/* get_current_state, jitced_template.c:330-334: state of the last anchor */
+	double const * const w = M.slot(M.last);
+	for (int i = 0; i < n_out; i++)
+		out[i] = w[1+i];
+}
+
 /* ------------------------------------------------------------------ per-member entry points
  * (one call = what one kernel thread does; the host twin in tests/ loops over members) */
 
@@ -840,8 +869,10 @@ JD_FN void member_reset_controller(jdde_problem const & P, long long const m)
 }
 
 /* integrate (n_steps == 0: `targets` are absolute times) or step_on_discontinuities
- * (n_steps > 0: `targets` are step lengths, applied cumulatively, _jitcdde.py:986-987) */
-JD_FN void member_integrate(jdde_problem const & P, long long const m, double const * const targets, int const per_member, int const n_steps, double * const out, int const n_out, long long budget)
+ * (n_steps > 0: `targets` are step lengths, applied cumulatively, _jitcdde.py:986-987).
+ * `resume`: the call repeats an earlier one that stopped for some members (ring overflow, attempt
+ * budget); members continue in the step and towards the target they had reached. */
+JD_FN void member_integrate(jdde_problem const & P, long long const m, double const * const targets, int const per_member, int const n_steps, int const resume, double * const out, int const n_out, long long budget)
 {
 	Member M;
 	load_member(P, m, M);
@@ -855,13 +886,19 @@ JD_FN void member_integrate(jdde_problem const & P, long long const m, double co
 	}
 	else
 	{
-		target = M.cur_t;
+		target = resume ? P.resume_target[m] : M.cur_t;
 		double const * const steps = per_member ? targets+(size_t)m*n_steps : targets;
-		for (int s = 0; s < n_steps && M.status == JDDE_STATUS_OK; s++)
+		int s = resume ? P.resume_index[m] : 0;
+		for (; s < n_steps; s++)
 		{
-			target = M.cur_t + steps[s];
+			if (!(resume && s == P.resume_index[m]))
+				target = M.cur_t + steps[s];
 			step_until<true>(M, P, target, budget);
+			if (M.status != JDDE_STATUS_OK)
+				break;
 		}
+		P.resume_index[m] = s;
+		P.resume_target[m] = target;
 	}
 	if (M.status == JDDE_STATUS_OK)
 	{
@@ -872,17 +909,24 @@ JD_FN void member_integrate(jdde_problem const & P, long long const m, double co
 	store_member(P, m, M);
 }
 
-JD_FN void member_integrate_blindly(jdde_problem const & P, long long const m, double const * const targets, int const per_member, double const step, double * const out)
+JD_FN void member_integrate_blindly(jdde_problem const & P, long long const m, double const * const targets, int const per_member, double const step, double * const out, int const n_out, double * const lyaps, double * const total_time)
 {
 	Member M;
 	load_member(P, m, M);
 	if (M.status != JDDE_STATUS_OK)
 		return;
 	double res[JD_N];
-	integrate_blindly(M, P, per_member ? targets[m] : targets[0], step, res);
+	double ly[JD_N/JD_NBASIC];
+	double total;
+	integrate_blindly(M, P, per_member ? targets[m] : targets[0], step, res, n_out, lyaps ? ly : nullptr, &total);
 	if (out)
-		for (int i = 0; i < JD_N; i++)
-			out[(size_t)m*JD_N+i] = res[i];
+		for (int i = 0; i < n_out; i++)
+			out[(size_t)m*n_out+i] = res[i];
+	if (lyaps)
+		for (int i = 0; i < JD_N/JD_NBASIC-1; i++)
+			lyaps[(size_t)m*(JD_N/JD_NBASIC-1)+i] = ly[i];
+	if (total_time)
+		total_time[m] = total;
 	store_member(P, m, M);
 }
 

@@ -46,19 +46,19 @@ jdde_k_reset_controller(jdde_problem const P)
 
 /* THE hot kernel: integrate / step_on_discontinuities for the whole ensemble */
 extern "C" __global__ void __launch_bounds__(JD_BLOCK, JD_MIN_BLOCKS)
-jdde_k_integrate(jdde_problem const P, double const * const targets, int const per_member, int const n_steps, double * const out, int const n_out, long long const budget)
+jdde_k_integrate(jdde_problem const P, double const * const targets, int const per_member, int const n_steps, int const resume, double * const out, int const n_out, long long const budget)
 {
 	long long const m = JD_MEMBER_INDEX();
 	if (m < P.n_members)
-		jdde::member_integrate(P, m, targets, per_member, n_steps, out, n_out, budget);
+		jdde::member_integrate(P, m, targets, per_member, n_steps, resume, out, n_out, budget);
 }
 
 extern "C" __global__ void __launch_bounds__(JD_BLOCK)
-jdde_k_integrate_blindly(jdde_problem const P, double const * const targets, int const per_member, double const step, double * const out)
+jdde_k_integrate_blindly(jdde_problem const P, double const * const targets, int const per_member, double const step, double * const out, int const n_out, double * const lyaps, double * const total_time)
 {
 	long long const m = JD_MEMBER_INDEX();
 	if (m < P.n_members)
-		jdde::member_integrate_blindly(P, m, targets, per_member, step, out);
+		jdde::member_integrate_blindly(P, m, targets, per_member, step, out, n_out, lyaps, total_time);
 }
 
 extern "C" __global__ void __launch_bounds__(JD_BLOCK)

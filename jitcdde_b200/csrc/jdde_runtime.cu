@@ -55,6 +55,10 @@ struct jdde_handle
 	double * d_aux = nullptr;                            /* [N] (old t, delta t) */
 	double * d_aux2 = nullptr;                           /* [N] */
 	unsigned long long * d_sums = nullptr;               /* [3] */
+	/* last integration call, for jdde_resume */
+	int last_kind = 0;                                   /* 0 none, 1 integrate, 2 step_on_discontinuities, 3 integrate_lyap */
+	int last_per_member = 0, last_n_steps = 0;
+	std::vector<double> last_targets;
 	std::vector<void *> allocations;
 };
 
@@ -215,6 +219,8 @@ int jdde_create(const jdde_desc * desc, jdde_handle ** out)
 	if ((rc = dev_alloc(h, &P.rejected, N))) return bail(rc);
 	if ((rc = dev_alloc(h, &P.attempts, N))) return bail(rc);
 	if ((rc = dev_alloc(h, &P.extra_rhs, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.resume_index, N))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.resume_target, N))) return bail(rc);
 	if ((rc = dev_alloc(h, &h->d_out, N*(size_t)desc->n))) return bail(rc);
 	if ((rc = dev_alloc(h, &h->d_out2, N*(size_t)desc->n))) return bail(rc);
 	if ((rc = dev_alloc(h, &h->d_aux, N))) return bail(rc);
@@ -404,16 +410,22 @@ int jdde_set_integration_parameters(jdde_handle * h, const jdde_int_params * p, 
 	return JDDE_OK;
 }
 
-static int run_integrate(jdde_handle * h, const double * targets, size_t count, int per_member, int n_steps, double * out_state, int n_out, int32_t * status)
+static int run_integrate(jdde_handle * h, const double * targets, size_t count, int per_member, int n_steps, int resume, double * out_state, int n_out, int32_t * status)
 {
 	int rc;
 	double * d_targets;
 	if (!targets)
 		return fail(h, JDDE_E_INVALID, "null argument");
+	if (!resume)
+	{
+		h->last_targets.assign(targets, targets+count);
+		h->last_per_member = per_member;
+		h->last_n_steps = n_steps;
+	}
 	if ((rc = stage_in(h, targets, count, &d_targets))) return rc;
 	int pm = per_member ? 1 : 0;
 	long long budget = h->budget;
-	void * args[] = { &h->P, &d_targets, &pm, &n_steps, &h->d_out, &n_out, &budget };
+	void * args[] = { &h->P, &d_targets, &pm, &n_steps, &resume, &h->d_out, &n_out, &budget };
 	if ((rc = launch(h, h->k.integrate, args))) return rc;
 	return finish(h, out_state, h->d_out, (size_t)h->desc.n_members*n_out, status);
 }
@@ -422,7 +434,8 @@ int jdde_integrate(jdde_handle * h, const double * target, int32_t per_member, d
 {
 	int rc = ready_to_integrate(h);
 	if (rc) return rc;
-	return run_integrate(h, target, per_member ? (size_t)h->desc.n_members : 1, per_member, 0, out_state, h->desc.n, status);
+	h->last_kind = 1;
+	return run_integrate(h, target, per_member ? (size_t)h->desc.n_members : 1, per_member, 0, 0, out_state, h->desc.n, status);
 }
 
 int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double * steps, int32_t per_member, double * out_state, int32_t * status)
@@ -431,21 +444,52 @@ int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double 
 	if (rc) return rc;
 	if (n_steps < 1)
 		return fail(h, JDDE_E_INVALID, "n_steps must be positive (for an ODE the reference calls adjust_diff instead, _jitcdde.py:998-1000)");
-	return run_integrate(h, steps, (per_member ? (size_t)h->desc.n_members : 1)*(size_t)n_steps, per_member, n_steps, out_state, h->desc.n, status);
+	h->last_kind = 2;
+	return run_integrate(h, steps, (per_member ? (size_t)h->desc.n_members : 1)*(size_t)n_steps, per_member, n_steps, 0, out_state, h->desc.n, status);
+}
+
+static int run_blind(jdde_handle * h, const double * target, int per_member, double step, int n_out, bool lyap, double * out_state, double * lyaps, double * total_time, int32_t * status)
+{
+	int rc;
+	if (!target)
+		return fail(h, JDDE_E_INVALID, "null argument");
+	size_t const N = (size_t)h->desc.n_members;
+	double * d_targets;
+	if ((rc = stage_in(h, target, per_member ? N : 1, &d_targets))) return rc;
+	int pm = per_member ? 1 : 0;
+	double * d_lyaps = lyap ? h->d_out2 : nullptr;
+	double * d_total = lyap ? h->d_aux2 : nullptr;
+	void * args[] = { &h->P, &d_targets, &pm, &step, &h->d_out, &n_out, &d_lyaps, &d_total };
+	if ((rc = launch(h, h->k.integrate_blindly, args))) return rc;
+	if (lyap && lyaps)
+		JD_CUDA(h, cudaMemcpyAsync(lyaps, h->d_out2, N*(size_t)(h->desc.n/h->desc.n_basic-1)*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	if (lyap && total_time)
+		JD_CUDA(h, cudaMemcpyAsync(total_time, h->d_aux2, N*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	return finish(h, out_state, h->d_out, N*n_out, status);
 }
 
 int jdde_integrate_blindly(jdde_handle * h, const double * target, int32_t per_member, double step, double * out_state, int32_t * status)
 {
 	int rc = ready_to_integrate(h);
 	if (rc) return rc;
-	if (!target)
-		return fail(h, JDDE_E_INVALID, "null argument");
-	double * d_targets;
-	if ((rc = stage_in(h, target, per_member ? (size_t)h->desc.n_members : 1, &d_targets))) return rc;
-	int pm = per_member ? 1 : 0;
-	void * args[] = { &h->P, &d_targets, &pm, &step, &h->d_out };
-	if ((rc = launch(h, h->k.integrate_blindly, args))) return rc;
-	return finish(h, out_state, h->d_out, (size_t)h->desc.n_members*h->desc.n, status);
+	return run_blind(h, target, per_member, step, h->desc.n, false, out_state, nullptr, nullptr, status);
+}
+
+int jdde_integrate_blindly_lyap(jdde_handle * h, const double * target, int32_t per_member, double step, double * out_state, double * lyaps, double * total_time, int32_t * status)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (h->desc.n == h->desc.n_basic)
+		return fail(h, JDDE_E_INVALID, "integrate_blindly_lyap needs n_basic < n");
+	return run_blind(h, target, per_member, step, h->desc.n_basic, true, out_state, lyaps, total_time, status);
+}
+
+int jdde_set_max_delay(jdde_handle * h, double max_delay)
+{
+	if (!h || !(max_delay >= 0.0))
+		return fail(h, JDDE_E_INVALID, "max_delay must be non-negative");
+	h->P.max_delay = max_delay;
+	return JDDE_OK;
 }
 
 static int run_jump(jdde_handle * h, int mode, const double * amplitude, int amp_pm, const double * time, int time_pm, double width, int forward, double * minima, double * maxima)
@@ -506,20 +550,20 @@ int jdde_orthonormalise(jdde_handle * h, int32_t n_lyap, double delay, double * 
 	return finish(h, norms, h->d_out2, (size_t)h->desc.n_members*n_lyap, nullptr);
 }
 
-int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t per_member, double * out_state, double * lyaps, double * delta_t, int32_t * status)
+static int run_lyap(jdde_handle * h, const double * target, size_t count, int per_member, int resume, double * out_state, double * lyaps, double * delta_t, int32_t * status)
 {
-	int rc = ready_to_integrate(h);
-	if (rc) return rc;
+	int rc;
 	int const nb = h->desc.n_basic;
-	if (h->desc.n == nb)
-		return fail(h, JDDE_E_INVALID, "integrate_lyap needs n_basic < n");
 	int n_lyap = h->desc.n/nb-1;
 	size_t const N = (size_t)h->desc.n_members;
-	/* old_t = get_t() (_jitcdde.py:1162) */
-	int what = 0;
-	void * gargs[] = { &h->P, &what, &h->d_aux };
-	if ((rc = launch(h, h->k.get, gargs))) return rc;
-	if ((rc = run_integrate(h, target, per_member ? N : 1, per_member, 0, nullptr, nb, nullptr))) return rc;
+	if (!resume)
+	{
+		/* old_t = get_t() (_jitcdde.py:1162); a resumed call keeps the one of the original call */
+		int what = 0;
+		void * gargs[] = { &h->P, &what, &h->d_aux };
+		if ((rc = launch(h, h->k.get, gargs))) return rc;
+	}
+	if ((rc = run_integrate(h, target, count, per_member, 0, resume, nullptr, nb, nullptr))) return rc;
 	double delay = h->P.max_delay;
 	const double * old_t = h->d_aux;
 	void * args[] = { &h->P, &n_lyap, &delay, &h->d_out2, &old_t, &h->d_out2, &h->d_aux2 };
@@ -529,6 +573,33 @@ int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t per_memb
 	if (delta_t)
 		JD_CUDA(h, cudaMemcpyAsync(delta_t, h->d_aux2, N*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
 	return finish(h, out_state, h->d_out, N*nb, status);
+}
+
+int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t per_member, double * out_state, double * lyaps, double * delta_t, int32_t * status)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (h->desc.n == h->desc.n_basic)
+		return fail(h, JDDE_E_INVALID, "integrate_lyap needs n_basic < n");
+	h->last_kind = 3;
+	return run_lyap(h, target, per_member ? (size_t)h->desc.n_members : 1, per_member, 0, out_state, lyaps, delta_t, status);
+}
+
+int jdde_resume(jdde_handle * h, double * out_state, double * lyaps, double * delta_t, int32_t * status)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	std::vector<double> const targets = h->last_targets;
+	switch (h->last_kind)
+	{
+		case 1:
+		case 2:
+			return run_integrate(h, targets.data(), targets.size(), h->last_per_member, h->last_n_steps, 1, out_state, h->desc.n, status);
+		case 3:
+			return run_lyap(h, targets.data(), targets.size(), h->last_per_member, 1, out_state, lyaps, delta_t, status);
+		default:
+			return fail(h, JDDE_E_INVALID, "nothing to resume");
+	}
 }
 
 static int run_get(jdde_handle * h, int what, double * out, size_t per_member_count)

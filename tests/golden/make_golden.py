@@ -1,0 +1,235 @@
+"""
+Generates the golden vectors in this directory from the REFERENCE'S OWN C core.
+
+Run in the build container (where /root/reference exists):   python tests/golden/make_golden.py
+
+For every system below, /root/reference/jitcdde/jitced_template.c is rendered and compiled
+unmodified (oracle/build_ref.py) and driven by the restated Python controller
+(oracle/controller.py), i.e. the outputs recorded here are outputs of the reference
+implementation, not of this repository's engine or oracle. The fixtures also carry the inputs
+(past, parameters, sample times), so that the tests need nothing from /root/reference.
+
+Flavour: "chain" right-hand side + libm-free controller roots (root_mode=1) — the configuration
+the CUDA verification build reproduces bit for bit. For the Mackey–Glass ensemble the
+"literal" flavour (what the reference itself would print: nested anchors() calls, libm pow,
+libm roots) is recorded as well, to pin how little the flavours differ.
+
+Also copied here (data, not code): the reference's own golden vector for the two coupled
+Rösslers, tests/two_Roessler_past.dat + tests/two_Roessler_y10.dat.
+"""
+
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from jitcdde_b200._past import Past  # noqa: E402
+from oracle import build_ref, controller, oracle  # noqa: E402
+from tests import systems  # noqa: E402
+
+REF_TESTS = "/root/reference/tests"
+
+
+def roots_from(lib):
+	lib.jo_inv_root.restype = ctypes.c_double
+	lib.jo_inv_root.argtypes = [ctypes.c_double, ctypes.c_int]
+	return lambda p, order: lib.jo_inv_root(p, int(order))
+
+
+def make_core(prog, name, past, n_basic=None, flavour="chain", parameters=None):
+	build_ref.build_ref(prog, name, n_basic=n_basic, flavour=flavour, force=True)
+	module = build_ref.load_ref(name)
+	core = module.dde_integrator([(float(a[0]), np.array(a[1], dtype=float), np.array(a[2], dtype=float)) for a in past])
+	if parameters is not None:
+		core.set_parameters(*[float(x) for x in parameters])
+	return core
+
+
+def past_arrays(past):
+	return dict(
+		past_times=np.array([a[0] for a in past], dtype=float),
+		past_states=np.array([a[1] for a in past], dtype=float),
+		past_diffs=np.array([a[2] for a in past], dtype=float),
+	)
+
+
+def save(name, **arrays):
+	path = os.path.join(HERE, name + ".npz")
+	np.savez_compressed(path, **arrays)
+	print("wrote", path, {k: np.shape(v) for k, v in arrays.items()})
+
+
+def golden_roessler():
+	system = systems.two_roessler()
+	prog = systems.program(system)
+	roots = roots_from(oracle.build(prog))
+	data = np.loadtxt(os.path.join(REF_TESTS, "two_Roessler_past.dat"))
+	y10 = np.loadtxt(os.path.join(REF_TESTS, "two_Roessler_y10.dat"))
+	past = [(r[0], r[1:7], r[7:13]) for r in data]
+	times = np.linspace(0, 10, 10, endpoint=True)
+
+	core = make_core(prog, "ref_roessler", past)
+	C = controller.Controller(core, system["delay"], root_mode=1, roots=roots, **systems.ROESSLER_TEST_PARAMETERS)
+	samples = np.array([C.integrate(T) for T in times])
+	result = dict(samples=samples, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
+
+	# jump in the middle (tests/test_jitcdde.py:110-118) + adjust_diff at the start (:98-102)
+	core = make_core(prog, "ref_roessler", past)
+	C = controller.Controller(core, system["delay"], root_mode=1, roots=roots, **systems.ROESSLER_TEST_PARAMETERS)
+	ad_min, ad_max = C.adjust_diff()
+	mid = C.integrate(5.0)
+	change = np.random.default_rng(42).normal(0, 0.1, 6)
+	j_min, j_max = C.jump(change, 5.0)
+	after_jump = C.integrate(7.0)
+	state_anchors = C.get_state()
+	save("roessler", **past_arrays(past), y10_reference=y10, times=times, **result,
+		adjust_diff_min=ad_min, adjust_diff_max=ad_max, mid=mid, change=change, jump_min=j_min, jump_max=j_max,
+		after_jump=after_jump, n_anchors_after=len(state_anchors), jump_accepted=C.accepted, jump_rejected=C.rejected)
+
+
+def golden_mg_ensemble():
+	system = systems.mackey_glass()
+	prog = systems.program(system)
+	roots = roots_from(oracle.build(prog))
+	N = 24
+	pars = systems.mg_grid(N)
+	past = [(-1.0, [1.0], [0.0]), (0.0, [1.0], [0.0])]
+	offsets = np.arange(0, 300, 10.0)
+	out = {}
+	for flavour, root_mode in (("chain", 1), ("literal", 0)):
+		samples = np.empty((len(offsets), N, 1))
+		counts = np.empty((N, 2), dtype=np.int64)
+		final_t = np.empty(N)
+		disc = np.empty((N, 1))
+		n_anchors = np.empty(N, dtype=np.int64)
+		for m in range(N):
+			core = make_core(prog, f"ref_mg_{flavour}", past, flavour=flavour, parameters=pars[m])
+			C = controller.Controller(core, 25.0, root_mode=root_mode, roots=roots)
+			disc[m] = C.step_on_discontinuities(controller.discontinuity_steps([pars[m, 1]]))
+			t0 = C.t
+			for s, off in enumerate(offsets):
+				samples[s, m] = C.integrate(t0+off)
+			counts[m] = C.accepted, C.rejected
+			final_t[m] = C.t
+			n_anchors[m] = len(C.get_state())
+		out[flavour] = dict(samples=samples, counts=counts, final_t=final_t, disc=disc, n_anchors=n_anchors)
+	save("mg_ensemble", parameters=pars, offsets=offsets, **past_arrays(past),
+		**{f"{k}_{fl}": v for fl, d in out.items() for k, v in d.items()})
+
+
+def golden_neutral():
+	system = systems.neutral()
+	prog = systems.program(system)
+	roots = roots_from(oracle.build(prog))
+	past = [(-1.0, system["initial"], np.zeros(6)), (0.0, system["initial"], np.zeros(6))]
+	core = make_core(prog, "ref_neutral", past)
+	C = controller.Controller(core, system["delay"], root_mode=1, roots=roots, rtol=1e-5)
+	mi, ma = C.adjust_diff()
+	times = np.linspace(0.5, 5, 10)
+	samples = np.array([C.integrate(T) for T in times])
+	save("neutral", **past_arrays(past), adjust_diff_min=mi, adjust_diff_max=ma, times=times, samples=samples,
+		control=np.array(system["control"]), accepted=C.accepted, rejected=C.rejected)
+
+
+def golden_state_dependent():
+	system = systems.state_dependent()
+	prog = systems.program(system)
+	roots = roots_from(oracle.build(prog))
+	past = system["past"]
+	core = make_core(prog, "ref_state_dependent", past)
+	C = controller.Controller(core, system["max_delay"], root_mode=1, roots=roots)
+	blind = C.integrate_blindly(0.01)
+	times = np.linspace(0.9, 2, 30)
+	samples = np.array([C.integrate(T) for T in times])
+	save("state_dependent", **past_arrays(past), blind=blind, times=times, samples=samples,
+		accepted=C.accepted, rejected=C.rejected, n_anchors=len(C.get_state()))
+
+
+def golden_ode():
+	system = systems.fitzhugh_nagumo_ode()
+	prog = systems.program(system)
+	roots = roots_from(oracle.build(prog))
+	past = [(-1.0, system["y0"], system["f_of_y0"]), (0.0, system["y0"], system["f_of_y0"])]
+	core = make_core(prog, "ref_ode", past)
+	C = controller.Controller(core, 0.0, root_mode=1, roots=roots)
+	adaptive = C.integrate(1.0)
+	core = make_core(prog, "ref_ode", past)
+	C2 = controller.Controller(core, 0.0, root_mode=1, roots=roots)
+	blind = C2.integrate_blindly(0.98, 0.01)
+	after_blind = C2.integrate(1.0)
+	save("ode", **past_arrays(past), adaptive=adaptive, blind=blind, after_blind=after_blind, y1=system["y1"],
+		accepted=C.accepted, rejected=C.rejected)
+
+
+def golden_kuramoto():
+	system = systems.kuramoto()
+	prog = systems.program(system)
+	roots = roots_from(oracle.build(prog))
+	n = prog.n
+	past = [(-1.0, system["initial"], np.zeros(n)), (0.0, system["initial"], np.zeros(n))]
+	core = make_core(prog, "ref_kuramoto", past)
+	C = controller.Controller(core, system["max_delay"], root_mode=1, roots=roots, rtol=0, atol=1e-5)
+	blind = C.integrate_blindly(system["max_delay"], 0.1)
+	t0 = C.t
+	offsets = np.arange(0, 4, 0.2)
+	samples = np.array([C.integrate(t0+o) for o in offsets])
+	save("kuramoto", **past_arrays(past), blind=blind, offsets=offsets, samples=samples, accepted=C.accepted, rejected=C.rejected)
+
+
+def golden_lyap():
+	# Mackey–Glass with 3 exponents (limit cycle: deterministic, non-chaotic), cf. examples/mackey_glass_lyap.py
+	system = systems.mackey_glass(control=False)
+	n_lyap = 3
+	prog, n_basic = systems.lyap_program(system, n_lyap)
+	roots = roots_from(oracle.build(prog, n_basic=n_basic))
+	P = Past(n=prog.n, n_basic=n_basic, rng=np.random.default_rng(7))
+	P.constant([1.0])
+	past = [(a.time, a.state, a.diff) for a in P]
+	core = make_core(prog, "ref_mg_lyap", past, n_basic=n_basic)
+	C = controller.Controller(core, 15.0, root_mode=1, roots=roots)
+	C.step_on_discontinuities(controller.discontinuity_steps([15.0]))
+	t0 = C.t
+	offsets = np.arange(10, 310, 10.0)
+	states, lyaps, weights = [], [], []
+	for o in offsets:
+		s, l, w = C.integrate_lyap(t0+o, n_basic, n_lyap)
+		states.append(s); lyaps.append(l); weights.append(w)
+	save("mg_lyap", **past_arrays(past), n_lyap=n_lyap, offsets=offsets, states=np.array(states), lyaps=np.array(lyaps), weights=np.array(weights),
+		accepted=C.accepted, rejected=C.rejected)
+
+	# two Rösslers with 4 exponents (tests/test_lyaps.py:16-56), short horizon for the bitwise check
+	system = systems.two_roessler()
+	prog, n_basic = systems.lyap_program(system, 4)
+	roots = roots_from(oracle.build(prog, n_basic=n_basic))
+	rng = np.random.default_rng(seed=42)
+	P = Past(n=prog.n, n_basic=n_basic, rng=np.random.default_rng(11))
+	P.add((-system["delay"], rng.random(6), rng.random(6)))
+	P.add((0.0, rng.random(6), rng.random(6)))
+	past = [(a.time, a.state, a.diff) for a in P]
+	core = make_core(prog, "ref_roessler_lyap", past, n_basic=n_basic)
+	C = controller.Controller(core, system["delay"], root_mode=1, roots=roots, **systems.LYAP_TEST_PARAMETERS)
+	C.step_on_discontinuities(controller.discontinuity_steps([system["delay"]]))
+	t0 = C.t
+	offsets = np.arange(10, 60, 10.0)
+	states, lyaps, weights = [], [], []
+	for o in offsets:
+		s, l, w = C.integrate_lyap(t0+o, n_basic, 4)
+		states.append(s); lyaps.append(l); weights.append(w)
+	save("roessler_lyap", **past_arrays(past), offsets=offsets, states=np.array(states), lyaps=np.array(lyaps), weights=np.array(weights),
+		accepted=C.accepted, rejected=C.rejected, lyap_controls=np.array([0.0806, 0, -0.0368, -0.1184]))
+
+
+if __name__ == "__main__":
+	assert build_ref.reference_available(), "run this where /root/reference exists"
+	golden_roessler()
+	golden_mg_ensemble()
+	golden_neutral()
+	golden_state_dependent()
+	golden_ode()
+	golden_kuramoto()
+	golden_lyap()

@@ -21,7 +21,9 @@ struct jdde_handle
 	jdde_desc desc{};
 	jdde_problem P{};
 	std::vector<double> ring, par, dt, last_pws, credit, last_start, out, out2, aux, aux2;
-	std::vector<int> first, last, current, count, status, cursor;
+	std::vector<int> first, last, current, count, status, cursor, resume_index;
+	std::vector<double> resume_target, last_targets;
+	int last_kind = 0, last_pm = 0, last_n_steps = 0;
 	std::vector<long long> accepted, rejected, attempts, extra_rhs;
 	bool have_past = false, have_params = false, have_int = false;
 	long long budget = 1ll << 24;
@@ -38,6 +40,7 @@ static void bind(jdde_handle * h)
 	P.ring = h->ring.data(); P.par = h->par.data(); P.dt = h->dt.data(); P.last_pws = h->last_pws.data();
 	P.credit = h->credit.data(); P.last_start = h->last_start.data(); P.first = h->first.data(); P.last = h->last.data();
 	P.current = h->current.data(); P.count = h->count.data(); P.status = h->status.data(); P.cursor = h->cursor.data();
+	P.resume_index = h->resume_index.data(); P.resume_target = h->resume_target.data();
 	P.accepted = h->accepted.data(); P.rejected = h->rejected.data(); P.attempts = h->attempts.data(); P.extra_rhs = h->extra_rhs.data();
 }
 
@@ -59,6 +62,7 @@ int jdde_create(const jdde_desc * d, jdde_handle ** out)
 	h->out.assign(N*JD_N, 0.0); h->out2.assign(N*JD_N, 0.0);
 	for (auto v : { &h->first, &h->last, &h->current, &h->count, &h->status }) v->assign(N, 0);
 	h->cursor.assign(N*(JD_NSITES ? JD_NSITES : 1), 0);
+	h->resume_index.assign(N, 0); h->resume_target.assign(N, 0.0);
 	for (auto v : { &h->accepted, &h->rejected, &h->attempts, &h->extra_rhs }) v->assign(N, 0);
 	h->P.n_members = d->n_members; h->P.cap = d->ring_capacity; h->P.anchor_stride = JD_A;
 	bind(h);
@@ -122,12 +126,24 @@ static void give(jdde_handle * h, double * out, const std::vector<double> & src,
 	if (status) memcpy(status, h->status.data(), (size_t)h->P.n_members*sizeof(int32_t));
 }
 
+static void remember(jdde_handle * h, int kind, const double * targets, size_t count, int pm, int n_steps)
+{
+	h->last_kind = kind; h->last_pm = pm; h->last_n_steps = n_steps;
+	h->last_targets.assign(targets, targets+count);
+}
+
+static void run_integrate(jdde_handle * h, const double * targets, int pm, int n_steps, int resume, int n_out)
+{
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_integrate(h->P, m, targets, pm, n_steps, resume, h->out.data(), n_out, h->budget);
+	h->launches++;
+}
+
 int jdde_integrate(jdde_handle * h, const double * target, int32_t pm, double * out, int32_t * status)
 {
 	if (int rc = ready(h)) return rc;
-	for (long long m = 0; m < h->P.n_members; m++)
-		jdde::member_integrate(h->P, m, target, pm, 0, h->out.data(), JD_N, h->budget);
-	h->launches++;
+	remember(h, 1, target, pm ? (size_t)h->P.n_members : 1, pm, 0);
+	run_integrate(h, target, pm, 0, 0, JD_N);
 	give(h, out, h->out, (size_t)h->P.n_members*JD_N, status);
 	return JDDE_OK;
 }
@@ -136,9 +152,8 @@ int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double 
 {
 	if (int rc = ready(h)) return rc;
 	if (n_steps < 1) return fail(h, JDDE_E_INVALID, "n_steps must be positive");
-	for (long long m = 0; m < h->P.n_members; m++)
-		jdde::member_integrate(h->P, m, steps, pm, n_steps, h->out.data(), JD_N, h->budget);
-	h->launches++;
+	remember(h, 2, steps, (pm ? (size_t)h->P.n_members : 1)*(size_t)n_steps, pm, n_steps);
+	run_integrate(h, steps, pm, n_steps, 0, JD_N);
 	give(h, out, h->out, (size_t)h->P.n_members*JD_N, status);
 	return JDDE_OK;
 }
@@ -147,11 +162,26 @@ int jdde_integrate_blindly(jdde_handle * h, const double * target, int32_t pm, d
 {
 	if (int rc = ready(h)) return rc;
 	for (long long m = 0; m < h->P.n_members; m++)
-		jdde::member_integrate_blindly(h->P, m, target, pm, step, h->out.data());
+		jdde::member_integrate_blindly(h->P, m, target, pm, step, h->out.data(), JD_N, nullptr, nullptr);
 	h->launches++;
 	give(h, out, h->out, (size_t)h->P.n_members*JD_N, status);
 	return JDDE_OK;
 }
+
+int jdde_integrate_blindly_lyap(jdde_handle * h, const double * target, int32_t pm, double step, double * out, double * lyaps, double * total_time, int32_t * status)
+{
+	if (int rc = ready(h)) return rc;
+	if (JD_N == JD_NBASIC) return fail(h, JDDE_E_INVALID, "integrate_blindly_lyap needs n_basic < n");
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_integrate_blindly(h->P, m, target, pm, step, h->out.data(), JD_NBASIC, h->out2.data(), h->aux2.data());
+	h->launches++;
+	give(h, lyaps, h->out2, (size_t)h->P.n_members*(JD_N/JD_NBASIC-1), nullptr);
+	give(h, total_time, h->aux2, (size_t)h->P.n_members, nullptr);
+	give(h, out, h->out, (size_t)h->P.n_members*JD_NBASIC, status);
+	return JDDE_OK;
+}
+
+int jdde_set_max_delay(jdde_handle * h, double max_delay) { if (!(max_delay >= 0.0)) return fail(h, JDDE_E_INVALID, "max_delay must be non-negative"); h->P.max_delay = max_delay; return JDDE_OK; }
 
 int jdde_jump(jdde_handle * h, const double * amplitude, int32_t apm, const double * time, int32_t tpm, double width, int32_t forward, double * minima, double * maxima)
 {
@@ -191,26 +221,47 @@ int jdde_orthonormalise(jdde_handle * h, int32_t n_lyap, double delay, double * 
 #endif
 }
 
-int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t pm, double * out_state, double * lyaps, double * delta_t, int32_t * status)
+static int run_lyap(jdde_handle * h, const double * target, int pm, int resume, double * out_state, double * lyaps, double * delta_t, int32_t * status)
 {
 #if JD_NBASIC != JD_N
-	if (int rc = ready(h)) return rc;
 	int const n_lyap = JD_N/JD_NBASIC-1;
-	for (long long m = 0; m < h->P.n_members; m++)
-		h->aux[m] = h->ring[((size_t)m*h->P.cap + (h->current[m] & (h->P.cap-1)))*JD_A];
-	for (long long m = 0; m < h->P.n_members; m++)
-		jdde::member_integrate(h->P, m, target, pm, 0, h->out.data(), JD_NBASIC, h->budget);
+	if (!resume)
+		for (long long m = 0; m < h->P.n_members; m++)
+			h->aux[m] = h->ring[((size_t)m*h->P.cap + (h->current[m] & (h->P.cap-1)))*JD_A];
+	run_integrate(h, target, pm, 0, resume, JD_NBASIC);
 	for (long long m = 0; m < h->P.n_members; m++)
 		jdde::member_orthonormalise(h->P, m, n_lyap, h->P.max_delay, h->out2.data(), h->aux.data(), h->out2.data(), h->aux2.data());
-	h->launches += 3;
+	h->launches += 2;
 	give(h, lyaps, h->out2, (size_t)h->P.n_members*n_lyap, nullptr);
 	give(h, delta_t, h->aux2, (size_t)h->P.n_members, nullptr);
 	give(h, out_state, h->out, (size_t)h->P.n_members*JD_NBASIC, status);
 	return JDDE_OK;
 #else
-	(void)target; (void)pm; (void)out_state; (void)lyaps; (void)delta_t; (void)status;
+	(void)target; (void)pm; (void)resume; (void)out_state; (void)lyaps; (void)delta_t; (void)status;
 	return fail(h, JDDE_E_INVALID, "integrate_lyap needs n_basic < n");
 #endif
+}
+
+int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t pm, double * out_state, double * lyaps, double * delta_t, int32_t * status)
+{
+	if (int rc = ready(h)) return rc;
+	remember(h, 3, target, pm ? (size_t)h->P.n_members : 1, pm, 0);
+	return run_lyap(h, target, pm, 0, out_state, lyaps, delta_t, status);
+}
+
+int jdde_resume(jdde_handle * h, double * out_state, double * lyaps, double * delta_t, int32_t * status)
+{
+	if (int rc = ready(h)) return rc;
+	std::vector<double> const targets = h->last_targets;
+	if (h->last_kind == 1 || h->last_kind == 2)
+	{
+		run_integrate(h, targets.data(), h->last_pm, h->last_n_steps, 1, JD_N);
+		give(h, out_state, h->out, (size_t)h->P.n_members*JD_N, status);
+		return JDDE_OK;
+	}
+	if (h->last_kind == 3)
+		return run_lyap(h, targets.data(), h->last_pm, 1, out_state, lyaps, delta_t, status);
+	return fail(h, JDDE_E_INVALID, "nothing to resume");
 }
 
 int jdde_get_t(jdde_handle * h, double * t)

@@ -1,0 +1,164 @@
+"""
+Scenarios shared by the CPU tests (engine host twin) and the GPU tests (CUDA engine): each one
+drives the product's public Python API exactly as a user of the reference would, on the inputs
+stored in a golden fixture (tests/golden/*.npz, outputs of the reference's own C core), and
+returns what the fixture recorded.
+"""
+
+import os
+
+import numpy as np
+
+from jitcdde_b200 import jitcdde, jitcdde_lyap
+from tests import systems
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+	return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def past_of(g):
+	return [(g["past_times"][k], g["past_states"][k], g["past_diffs"][k]) for k in range(len(g["past_times"]))]
+
+
+def make(system, cls=jitcdde, **kwargs):
+	options = dict(verbose=False)
+	for key in ("helpers", "control_pars", "max_delay", "delays"):
+		if key in system and system[key] is not None and len(np.shape(system[key])) >= 0:
+			if key == "control_pars" and not system[key]:
+				continue
+			options[key] = system[key]
+	options.update(kwargs)
+	return cls(system["f"], **options)
+
+
+def roessler(g, **kw):
+	DDE = make(systems.two_roessler(), **kw)
+	DDE.set_integration_parameters(**systems.ROESSLER_TEST_PARAMETERS)
+	DDE.add_past_points(past_of(g))
+	DDE.initial_discontinuities_handled = True
+	samples = np.array([DDE.integrate(T) for T in g["times"]])
+	accepted, rejected, _ = DDE.counters()
+	return dict(samples=samples, accepted=accepted[0], rejected=rejected[0], final_t=DDE.t)
+
+
+def roessler_jump(g, **kw):
+	DDE = make(systems.two_roessler(), **kw)
+	DDE.set_integration_parameters(**systems.ROESSLER_TEST_PARAMETERS)
+	DDE.add_past_points(past_of(g))
+	ad_min, ad_max = DDE.adjust_diff()
+	mid = DDE.integrate(5.0)
+	j_min, j_max = DDE.jump(g["change"], 5.0)
+	after = DDE.integrate(7.0)
+	n_anchors = len(DDE.get_state())
+	accepted, rejected, _ = DDE.counters()
+	return dict(adjust_diff_min=ad_min, adjust_diff_max=ad_max, mid=mid, jump_min=j_min, jump_max=j_max, after_jump=after,
+		n_anchors_after=n_anchors, jump_accepted=accepted[0], jump_rejected=rejected[0])
+
+
+def mg_ensemble(g, **kw):
+	pars = g["parameters"]
+	N = len(pars)
+	DDE = make(systems.mackey_glass(), max_delay=25.0, n_members=N, **kw)
+	DDE.constant_past([1.0])
+	DDE.set_parameters(pars)
+	DDE.delays = pars[:, 1:2]            # one numeric delay per member (τ is a control parameter)
+	DDE.max_delay = 25.0
+	disc = DDE.step_on_discontinuities()
+	t0 = DDE.t
+	samples = np.array([DDE.integrate(t0+off) for off in g["offsets"]])
+	accepted, rejected, _ = DDE.counters()
+	n_anchors = np.array([len(DDE.get_state(m)) for m in range(N)])
+	return dict(samples=samples, counts=np.stack([accepted, rejected], axis=1), final_t=DDE.t, disc=disc, n_anchors=n_anchors)
+
+
+def neutral(g, **kw):
+	system = systems.neutral()
+	DDE = make(system, **kw)
+	DDE.set_integration_parameters(rtol=1e-5)
+	DDE.constant_past(system["initial"])
+	mi, ma = DDE.adjust_diff()
+	samples = np.array([DDE.integrate(T) for T in g["times"]])
+	accepted, rejected, _ = DDE.counters()
+	return dict(adjust_diff_min=mi, adjust_diff_max=ma, samples=samples, accepted=accepted[0], rejected=rejected[0])
+
+
+def state_dependent(g, **kw):
+	system = systems.state_dependent()
+	DDE = make(system, **kw)
+	for anchor in system["past"]:
+		DDE.add_past_point(*anchor)
+	blind = DDE.integrate_blindly(0.01)
+	samples = np.array([DDE.integrate(T) for T in g["times"]])
+	accepted, rejected, _ = DDE.counters()
+	return dict(blind=blind, samples=samples, accepted=accepted[0], rejected=rejected[0], n_anchors=len(DDE.get_state()))
+
+
+def ode(g, **kw):
+	system = systems.fitzhugh_nagumo_ode()
+	DDE = make(system, **kw)
+	DDE.add_past_point(-1.0, system["y0"], system["f_of_y0"])
+	DDE.add_past_point(0.0, system["y0"], system["f_of_y0"])
+	adaptive = DDE.integrate(1.0)
+	accepted, rejected, _ = DDE.counters()
+	DDE2 = make(system, **kw)
+	DDE2.add_past_point(-1.0, system["y0"], system["f_of_y0"])
+	DDE2.add_past_point(0.0, system["y0"], system["f_of_y0"])
+	blind = DDE2.integrate_blindly(0.98, 0.01)
+	after_blind = DDE2.integrate(1.0)
+	return dict(adaptive=adaptive, blind=blind, after_blind=after_blind, accepted=accepted[0], rejected=rejected[0])
+
+
+def kuramoto(g, **kw):
+	system = systems.kuramoto()
+	DDE = make(system, **kw)
+	DDE.set_integration_parameters(rtol=0, atol=1e-5)
+	DDE.constant_past(system["initial"], time=0.0)
+	blind = DDE.integrate_blindly(system["max_delay"], 0.1)
+	t0 = DDE.t
+	samples = np.array([DDE.integrate(t0+o) for o in g["offsets"]])
+	accepted, rejected, _ = DDE.counters()
+	return dict(blind=blind, samples=samples, accepted=accepted[0], rejected=rejected[0])
+
+
+def _lyap_run(DDE, g):
+	t0 = DDE.t
+	states, lyaps, weights = [], [], []
+	for o in g["offsets"]:
+		s, l, w = DDE.integrate(t0+o)
+		states.append(s); lyaps.append(l); weights.append(w)
+	accepted, rejected, _ = DDE.counters()
+	return dict(states=np.array(states), lyaps=np.array(lyaps), weights=np.array(weights), accepted=accepted[0], rejected=rejected[0])
+
+
+def mg_lyap(g, **kw):
+	DDE = make(systems.mackey_glass(control=False), cls=jitcdde_lyap, n_lyap=int(g["n_lyap"]), **kw)
+	DDE.add_past_points(past_of(g))      # full anchors incl. the tangent vectors the fixture was made with
+	DDE.step_on_discontinuities()
+	return _lyap_run(DDE, g)
+
+
+def roessler_lyap(g, **kw):
+	DDE = make(systems.two_roessler(), cls=jitcdde_lyap, n_lyap=4, **kw)
+	DDE.add_past_points(past_of(g))
+	DDE.set_integration_parameters(**systems.LYAP_TEST_PARAMETERS)
+	DDE.step_on_discontinuities()
+	return _lyap_run(DDE, g)
+
+
+ALL = dict(roessler=roessler, roessler_jump=roessler_jump, mg_ensemble=mg_ensemble, neutral=neutral,
+	state_dependent=state_dependent, ode=ode, kuramoto=kuramoto, mg_lyap=mg_lyap, roessler_lyap=roessler_lyap)
+FIXTURE = dict(roessler_jump="roessler")
+
+
+def compare(result, g, exact, rtol=1e-10, suffix=""):
+	"""exact: bit for bit; otherwise counts identical and values within rtol (relative)."""
+	for key, value in result.items():
+		expected = g[key+suffix] if key+suffix in g else g[key]
+		value = np.asarray(value)
+		if exact or value.dtype.kind in "iu":
+			assert np.array_equal(value, np.asarray(expected).reshape(value.shape)), f"{key}: not identical (max abs diff {np.max(np.abs(value-np.asarray(expected).reshape(value.shape)))})"
+		else:
+			np.testing.assert_allclose(value, np.asarray(expected).reshape(value.shape), rtol=rtol, atol=1e-300, err_msg=key)

@@ -1,0 +1,25 @@
+"""
+CPU tests of the product's Python classes and engine logic (no GPU): the engine header compiled
+for the host (tests/host_twin) behind the real C ABI and the real `jitcdde` / `jitcdde_lyap`
+classes must reproduce, bit for bit, what the reference's own C core produced
+(tests/golden/*.npz). The CUDA build of the same code is checked in test_gpu_parity.py.
+"""
+
+import numpy as np
+import pytest
+
+from tests import scenarios
+
+
+@pytest.mark.parametrize("name", sorted(scenarios.ALL))
+def test_bitwise_against_reference_core(twin, name):
+	g = scenarios.golden(scenarios.FIXTURE.get(name, name))
+	result = scenarios.ALL[name](g)
+	scenarios.compare(result, g, exact=True, suffix="_chain" if name == "mg_ensemble" else "")
+
+
+def test_reference_golden_vector(twin):
+	"""tests/test_jitcdde.py:88-97: state at T=10 within the reference's own tolerance"""
+	g = scenarios.golden("roessler")
+	result = scenarios.roessler(g)
+	np.testing.assert_allclose(result["samples"][-1], g["y10_reference"], rtol=1e-3, atol=1e-6)

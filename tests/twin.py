@@ -43,12 +43,23 @@ def build_twin(program, n_basic=None):
 
 
 @contextlib.contextmanager
-def use_twin(program, n_basic=None):
-	"""Within this context jitcdde_b200 talks to the host twin instead of libjitcdde_b200.so."""
-	lib = build_twin(program, n_basic)
-	saved = _capi.load_library
-	_capi.load_library = lambda path=None: lib
+def use_twin():
+	"""
+	Within this context jitcdde_b200 talks to the host twin instead of libjitcdde_b200.so:
+	`_build.build_image` compiles the twin for the generated program with g++ (instead of a
+	cubin with nvcc), `_capi.load_library` returns it and `Engine.load_image` is a no-op.
+	"""
+	state = {}
+
+	def fake_build_image(program, n_basic=None, **kwargs):
+		state["lib"] = build_twin(program, n_basic)
+		return "<host twin>"
+
+	saved = _build.build_image, _capi.load_library, _capi.Engine.load_image
+	_build.build_image = fake_build_image
+	_capi.load_library = lambda path=None: state["lib"]
+	_capi.Engine.load_image = lambda self, path: None
 	try:
-		yield lib
+		yield state
 	finally:
-		_capi.load_library = saved
+		_build.build_image, _capi.load_library, _capi.Engine.load_image = saved

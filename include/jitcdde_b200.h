@@ -187,6 +187,11 @@ int jdde_clear_status(jdde_handle * h, int32_t code);
 /* Upper bound of attempted steps per member and call (default 1<<24); guards against kernels that never end. */
 int jdde_set_attempt_budget(jdde_handle * h, int64_t attempts);
 
+/* Page-locked host memory for callers that want asynchronous, full-bandwidth copies of their
+ * input/output buffers (bench.py's end-to-end leg); plain malloc'd buffers work everywhere, too. */
+int jdde_host_alloc(size_t bytes, void ** out);
+int jdde_host_free(void * p);
+
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t jdde_launch_count(const jdde_handle * h);
 /* Device pointer of the last integration result [n_members][n] as an integer address (for zero-copy interop). */

@@ -15,6 +15,7 @@ The integrator runs as CUDA kernels for sm_100a behind a C ABI
 from ._symbols import anchors, current_y, dy, past_dy, past_y, quadrature, t, y
 from ._jitcdde import UnsuccessfulIntegration, jitcdde, jitcdde_lyap, _find_max_delay, _propagate_delays
 from ._codegen import get_delays as _get_delays
+from ._capi import pinned_empty
 
 
 def shard(n_members, rank, world_size):
@@ -39,5 +40,5 @@ input = _out_of_scope("input")  # noqa: A001
 
 __all__ = [
 	"UnsuccessfulIntegration", "anchors", "current_y", "dy", "jitcdde", "jitcdde_lyap",
-	"past_dy", "past_y", "quadrature", "t", "y", "shard",
+	"past_dy", "past_y", "quadrature", "t", "y", "shard", "pinned_empty",
 ]

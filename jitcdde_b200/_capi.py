@@ -73,6 +73,8 @@ SIGNATURES = {
 	"jdde_grow_ring": (ctypes.c_int, [_H, ctypes.c_int32]),
 	"jdde_clear_status": (ctypes.c_int, [_H, ctypes.c_int32]),
 	"jdde_set_attempt_budget": (ctypes.c_int, [_H, ctypes.c_int64]),
+	"jdde_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+	"jdde_host_free": (ctypes.c_int, [ctypes.c_void_p]),
 	"jdde_launch_count": (ctypes.c_int64, [_H]),
 	"jdde_device_result": (ctypes.c_uint64, [_H]),
 }
@@ -99,6 +101,36 @@ def load_library(path=None):
 
 class EngineError(RuntimeError):
 	pass
+
+
+class _PinnedBuffer:
+	def __init__(self, lib, nbytes):
+		self.lib = lib
+		self.ptr = ctypes.c_void_p()
+		if lib.jdde_host_alloc(nbytes, ctypes.byref(self.ptr)):
+			raise EngineError("jdde_host_alloc failed: " + lib.jdde_last_error(None).decode())
+		self.nbytes = nbytes
+
+	def __del__(self):
+		if self.ptr:
+			self.lib.jdde_host_free(self.ptr)
+			self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.float64):
+	"""NumPy array in page-locked host memory (jdde_host_alloc); freed with the array."""
+	dtype = np.dtype(dtype)
+	count = int(np.prod(shape))
+	buffer = _PinnedBuffer(load_library(), max(1, count*dtype.itemsize))
+	raw = (ctypes.c_char*buffer.nbytes).from_address(buffer.ptr.value)
+	array = np.frombuffer(raw, dtype=dtype, count=count).reshape(shape)
+	_keep_alive[id(raw)] = buffer
+	import weakref
+	weakref.finalize(raw, _keep_alive.pop, id(raw), None)
+	return array
+
+
+_keep_alive = {}
 
 
 def _f64(a):

@@ -449,15 +449,23 @@ class jitcdde:
 		self._initiate()
 		return self._shape_scalar(self._engine.get_t())
 
-	def integrate(self, target_time):
+	def integrate(self, target_time, out=None):
+		"""
+		As the reference's `integrate` (_jitcdde.py:807-836). Ensemble extension: `target_time`
+		may be an array of shape (n_members,), and `out` a preallocated (n_members, n) float64
+		array (e.g. from `jitcdde_b200.pinned_empty`) that receives and is returned as the result.
+		"""
 		self._initiate()
 		if self.n_members == 1 and self._engine.get_t()[0] > target_time:
 			warn("The target time is smaller than the current time. No integration step will happen. The returned state will be extrapolated from the interpolating Hermite polynomial for the last integration step. You may see this because you try to integrate backwards in time, in which case you did something wrong. You may see this just because your sampling step is small, in which case there is no need to worry (though you should think about increasing your sampling time).", stacklevel=2)
 		if not self.initial_discontinuities_handled:
 			warn("You did not explicitly handle initial discontinuities. Proceed only if you know what you are doing. This is only fine if you somehow chose your initial past such that the derivative of the last anchor complies with the DDE. In this case, you can set the attribute `initial_discontinuities_handled` to `True` to suppress this warning. See https://jitcdde.rtfd.io/#discontinuities for details.", stacklevel=2)
-		result, status = self._engine.integrate(target_time)
+		result, status = self._engine.integrate(target_time, out=out)
 		while self._check_status(status, retry=True):
 			result, status = self._engine.resume()
+			if out is not None:
+				out[...] = result
+				result = out
 		return self._shape_state(result)
 
 	def adjust_diff(self, shift_ratio=1e-4):

@@ -743,6 +743,22 @@ int jdde_set_attempt_budget(jdde_handle * h, int64_t attempts)
 	return JDDE_OK;
 }
 
+int jdde_host_alloc(size_t bytes, void ** out)
+{
+	if (!out)
+		return JDDE_E_INVALID;
+	*out = nullptr;
+	cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+	if (e != cudaSuccess)
+		return fail(nullptr, JDDE_E_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+	return JDDE_OK;
+}
+
+int jdde_host_free(void * p)
+{
+	return cudaFreeHost(p) == cudaSuccess ? JDDE_OK : JDDE_E_CUDA;
+}
+
 int64_t jdde_launch_count(const jdde_handle * h) { return h ? h->launches : 0; }
 uint64_t jdde_device_result(const jdde_handle * h) { return h ? (uint64_t)(uintptr_t)h->d_out : 0; }
 

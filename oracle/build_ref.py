@@ -35,7 +35,7 @@ TEMPLATE = "/root/reference/jitcdde/jitced_template.c"
 _CSRC = os.path.join(os.path.dirname(_HERE), "jitcdde_b200", "csrc")
 
 VERIFY_FLAGS = ["-O2", "-ffp-contract=off", "-g", "-UNDEBUG"]
-FAST_FLAGS = ["-O3", "-march=native", "-DNDEBUG"]
+FAST_FLAGS = ["-Ofast", "-DNDEBUG"]   # reference-like default flags (jitcxde_common: -Ofast), without -march=native: must run on the GPU box, too
 
 
 def reference_available():

@@ -11,6 +11,7 @@ reference's Python API (/root/reference/jitcdde/_jitcdde.py).
 """
 
 import ctypes
+import hashlib
 import os
 import subprocess
 
@@ -23,7 +24,7 @@ _CSRC = os.path.join(os.path.dirname(_HERE), "jitcdde_b200", "csrc")
 #: verification flags: no fast-math, no FMA contraction (hard part 1)
 VERIFY_FLAGS = ["-O2", "-ffp-contract=off"]
 #: timing flags for the CPU-baseline leg
-FAST_FLAGS = ["-O3", "-march=native"]
+FAST_FLAGS = ["-O3"]   # no -march=native: the prebuilt .so must also run on the GPU box's host CPU
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 
@@ -73,7 +74,7 @@ def build(program, n_basic=None, flags=VERIFY_FLAGS, openmp=False, tag=""):
 	"""Compile the oracle for `program`; returns the loaded ctypes library."""
 	os.makedirs(_BUILD, exist_ok=True)
 	n_basic = n_basic or program.n
-	name = f"oracle_{program.key}_{n_basic}{tag}_{'omp' if openmp else 'st'}_{abs(hash(tuple(flags))) % 10**8}"
+	name = f"oracle_{program.key}_{n_basic}{tag}_{'omp' if openmp else 'st'}_{hashlib.sha256(repr(tuple(flags)).encode()).hexdigest()[:8]}"
 	rhs = os.path.join(_BUILD, f"rhs_{program.key}.inc")
 	so = os.path.join(_BUILD, name + ".so")
 	src = os.path.join(_HERE, "dde_oracle.c")

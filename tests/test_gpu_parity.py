@@ -1,0 +1,169 @@
+"""
+GPU parity tests (run with -m gpu on a B200): the CUDA engine, called through the C ABI by the
+product's Python classes, against
+  - golden vectors produced by the reference's own C core (tests/golden/*.npz),
+  - the CPU oracle (oracle/dde_oracle.c) on seeded ensembles the oracle finishes in seconds,
+  - size-independent properties at the full per-GPU ensemble size of BASELINE.json configs[1].
+
+Bars: verification build (nvcc -fmad=false): bit for bit — identical accepted/rejected step counts
+and identical states. Production build (FMA contraction): identical step counts and states within
+1e-9 relative for the non-chaotic systems (north_star asks 1e-10 of the verification build, which is
+exact), 1e-6 for the chaotic Rössler systems over their short horizons.
+"""
+
+import numpy as np
+import pytest
+
+from jitcdde_b200 import UnsuccessfulIntegration, _build, _capi, jitcdde
+from oracle import oracle
+from tests import scenarios, systems
+
+pytestmark = pytest.mark.gpu
+
+CHAOTIC = {"roessler", "roessler_jump", "roessler_lyap"}
+
+
+@pytest.mark.parametrize("name", sorted(scenarios.ALL))
+def test_verification_build_is_bitwise_identical_to_reference_core(name):
+	g = scenarios.golden(scenarios.FIXTURE.get(name, name))
+	result = scenarios.ALL[name](g, verification=True)
+	scenarios.compare(result, g, exact=True, suffix="_chain" if name == "mg_ensemble" else "")
+
+
+@pytest.mark.parametrize("name", sorted(scenarios.ALL))
+def test_production_build_matches_reference_core(name):
+	g = scenarios.golden(scenarios.FIXTURE.get(name, name))
+	result = scenarios.ALL[name](g, verification=False)
+	rtol = 1e-6 if name in CHAOTIC else 1e-9
+	if name.endswith("lyap"):
+		# local exponents near zero: compare absolutely as well
+		for key in ("lyaps",):
+			np.testing.assert_allclose(result.pop(key), g[key], rtol=rtol, atol=1e-9)
+	scenarios.compare(result, g, exact=False, rtol=rtol, suffix="_chain" if name == "mg_ensemble" else "")
+
+
+def test_reference_golden_vector():
+	"""tests/test_jitcdde.py:88-97 with the reference's own tolerance, production build"""
+	g = scenarios.golden("roessler")
+	result = scenarios.roessler(g)
+	np.testing.assert_allclose(result["samples"][-1], g["y10_reference"], rtol=1e-3, atol=1e-6)
+
+
+def _mg_engine(N, mode, cap=128):
+	prog = systems.program(systems.mackey_glass())
+	pars = systems.mg_grid(N)
+	E = _capi.Engine(1, 1, prog.n_sites, 2, N, ring_capacity=cap)
+	E.load_image(_build.build_image(prog, mode=mode))
+	E.set_past(np.array([-1.0, 0.0]), np.ones((2, 1)), np.zeros((2, 1)))
+	E.set_parameters(pars)
+	E.set_integration_parameters(25.0, **oracle.DEFAULTS)
+	return prog, pars, E
+
+
+@pytest.mark.parametrize("mode", [_build.VERIFY, _build.FAST])
+def test_ensemble_against_oracle(mode):
+	"""4096 members of the (β, τ) grid over 300 time units: every member's step counts and samples"""
+	N = 4096
+	prog, pars, E = _mg_engine(N, mode)
+	offsets = np.arange(0, 300, 10.0)
+	disc, status = E.step_on_discontinuities(pars[:, 1:2].copy())
+	t0 = E.get_t()
+	samples = np.array([E.integrate(t0+o)[0] for o in offsets])
+	accepted, rejected, rhs = E.get_counters()
+	assert not E.get_status().any()
+
+	lib = oracle.build(prog, flags=oracle.FAST_FLAGS if False else oracle.VERIFY_FLAGS)
+	ref = oracle.run_ensemble(lib, (np.array([-1.0, 0.0]), np.ones((2, 1)), np.zeros((2, 1))), pars, 25.0, 1, pars[:, 1:2].copy(), offsets)
+	assert np.array_equal(accepted, ref["counters"][:, 0])
+	assert np.array_equal(rejected, ref["counters"][:, 1])
+	assert np.array_equal(rhs, ref["counters"][:, 2])
+	if mode == _build.VERIFY:
+		assert np.array_equal(samples, ref["out"])
+		assert np.array_equal(E.get_t(), ref["t"])
+	else:
+		np.testing.assert_allclose(samples, ref["out"], rtol=1e-9)
+	E.close()
+
+
+def test_full_size_properties():
+	"""Per-GPU share of the 10^7-member ensemble (2^20 members): determinism, sampling-grid
+	independence, and a random subsample checked bit for bit against the oracle."""
+	N = 1 << 20
+	horizon = 100.0
+	results = []
+	for n_calls in (1, 10):
+		prog, pars, E = _mg_engine(N, _build.VERIFY)
+		E.step_on_discontinuities(pars[:, 1:2].copy())
+		t0 = E.get_t()
+		for k in range(1, n_calls+1):
+			out, status = E.integrate(t0+horizon*k/n_calls)
+		assert not status.any()
+		results.append((out.copy(), E.get_t(), *E.get_counters()))
+		E.close()
+	# sampling grid does not change the steps (the integrator overshoots and interpolates, _jitcdde.py:830-834)
+	for a, b in zip(results[0][1:], results[1][1:]):
+		assert np.array_equal(a, b)
+	np.testing.assert_array_equal(results[0][0], results[1][0])
+
+	out, t_end, accepted, rejected, rhs = results[0]
+	assert accepted.min() > 50 and (accepted+rejected).max() < 5000
+	assert np.array_equal(rhs, 3*(accepted+rejected))       # FSAL: 3 evaluations per attempt, no pws iterations here
+
+	rng = np.random.default_rng(1)
+	pick = np.sort(rng.choice(N, 512, replace=False))
+	lib = oracle.build(prog)
+	ref = oracle.run_ensemble(lib, (np.array([-1.0, 0.0]), np.ones((2, 1)), np.zeros((2, 1))), pars[pick], 25.0, 1, pars[pick, 1:2].copy(), [horizon])
+	assert np.array_equal(out[pick], ref["out"][0])
+	assert np.array_equal(accepted[pick], ref["counters"][:, 0])
+	assert np.array_equal(t_end[pick], ref["t"])
+
+
+def test_ring_growth_and_resume():
+	"""A ring that is too small overflows, grows and the call resumes: same result as a large ring."""
+	g = scenarios.golden("mg_ensemble")
+	big = scenarios.mg_ensemble(g, verification=True, ring_capacity=256)
+	small = scenarios.mg_ensemble(g, verification=True, ring_capacity=8)
+	for key in big:
+		assert np.array_equal(big[key], small[key]), key
+
+
+def test_unsuccessful_integration():
+	"""tests/test_jitcdde.py:332-351"""
+	g = scenarios.golden("roessler")
+	for pars in (dict(min_step=1.0), dict(min_step=1e-3, rtol=1e-10, atol=0), dict(min_step=1e-3, rtol=0, atol=1e-10)):
+		DDE = scenarios.make(systems.two_roessler())
+		DDE.add_past_points(scenarios.past_of(g))
+		DDE.set_integration_parameters(**pars)
+		with pytest.raises(UnsuccessfulIntegration):
+			DDE.integrate(1000)
+
+
+def test_call_order_errors():
+	prog = systems.program(systems.mackey_glass())
+	E = _capi.Engine(1, 1, prog.n_sites, 2, 8)
+	with pytest.raises(_capi.EngineError, match="no kernel image"):
+		E.set_integration_parameters(25.0, **oracle.DEFAULTS)
+	E.load_image(_build.build_image(prog))
+	with pytest.raises(_capi.EngineError, match="no past set"):
+		E.integrate(1.0)
+	with pytest.raises(_capi.EngineError, match="two anchors"):
+		E.set_past(np.array([0.0]), np.ones((1, 1)), np.zeros((1, 1)))
+	E.set_past(np.array([-1.0, 0.0]), np.ones((2, 1)), np.zeros((2, 1)))
+	with pytest.raises(_capi.EngineError, match="integration parameters not set"):
+		E.integrate(1.0)
+	E.set_integration_parameters(25.0, **oracle.DEFAULTS)
+	with pytest.raises(_capi.EngineError, match="control parameters not set"):
+		E.integrate(1.0)
+	E.close()
+
+
+def test_watchdog_budget():
+	prog, pars, E = _mg_engine(64, _build.FAST)
+	E.set_attempt_budget(5)
+	out, status = E.integrate(100.0)
+	assert (status == _capi.STATUS_BUDGET).all()
+	E.set_attempt_budget(1 << 24)
+	E.clear_status(_capi.STATUS_BUDGET)
+	out, status = E.resume()
+	assert not status.any()
+	E.close()

@@ -11,12 +11,12 @@ Workload: dy/dt = β·y(t−τ)/(1+y(t−τ)^10) − 0.1·y, co
 deterministic grid β_i = 0.15+0.20·i/2499, τ_j = 10+15·j/3999 (10^7 members on 8 GPUs ⇒ 1.25·10^6
 members per GPU, weak scaling: contiguous member ranges per rank, no collective in the data path),
 past = constant 1, default integration parameters of the reference, per-member
-step_on_discontinuities (target τ_j), then the sampling loop `integrate(t0 + 10·k)`.
+step_on_discontinuities (target τ_j), then the sampling loop `integrate(30 + 10·k)`.
 One bench STEP = one `integrate` call advancing every member by 10 time units (≈ 23 accepted
 steps per member). `value` = accepted steps of all members and ranks ÷ device time (CUDA events on the
 launching stream, max over ranks) with all inputs resident in HBM; `e2e` = the same loop through the
-public Python API with host buffers: per step the per-member target times go host→device from
-pinned memory and states + status come back device→host.
+public Python API with host buffers: per step the target time goes host→device and the states and
+per-member status come back device→host into pinned memory.
 """
 
 import argparse
@@ -65,11 +65,13 @@ def measured_peaks():
 
 # --------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-	"""Samples SM clock and throttle reasons through NVML while the timed region runs."""
+	"""Samples SM clock and throttle reasons through NVML (≈0.2 ms per sample) in a background thread;
+	the summary covers the samples taken between mark_start() and mark_end(), i.e. DURING the timed region."""
 
 	def __init__(self, index):
-		self.samples, self.reasons = [], set()
+		self.samples = []          # (time, sm_mhz, reasons mask)
 		self.max_mhz = None
+		self.window = [None, None]
 		self._stop = threading.Event()
 		try:
 			import pynvml
@@ -77,46 +79,51 @@ class ClockSampler:
 			self.nv = pynvml
 			self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
 			self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+			self.thread = threading.Thread(target=self._run, daemon=True)
+			self.thread.start()
 		except Exception:
 			self.nv = None
-		self.thread = threading.Thread(target=self._run, daemon=True)
 
 	def _run(self):
 		nv = self.nv
-		names = {
-			"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
-			"hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
-			"sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
-			"sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
-		}
 		get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
 		while not self._stop.is_set():
 			try:
-				self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
-				mask = get_reasons(self.handle)
-				for name, bit in names.items():
-					if mask & bit:
-						self.reasons.add(name)
+				self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM), get_reasons(self.handle)))
 			except Exception:
 				pass
-			time.sleep(0.002)
+			time.sleep(0.0005)
 
-	def __enter__(self):
-		if self.nv:
-			self.thread.start()
-		return self
+	def mark_start(self):
+		self.window[0] = time.perf_counter()
 
-	def __exit__(self, *exc):
+	def mark_end(self):
+		self.window[1] = time.perf_counter()
+
+	def stop(self):
 		self._stop.set()
 		if self.nv:
 			self.thread.join()
 
 	def summary(self):
+		nv = self.nv
+		if not nv:
+			return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+		bits = {
+			"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+			"hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+			"sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+			"sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+		}
+		inside = [s for s in self.samples if self.window[0] <= s[0] <= self.window[1]]
+		mask = 0
+		for s in inside:
+			mask |= s[2]
 		return {
-			"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+			"sm_mhz": float(np.median([s[1] for s in inside])) if inside else None,
 			"sm_max_mhz": self.max_mhz,
-			"reasons": sorted(self.reasons),
-			"samples": len(self.samples),
+			"reasons": sorted(name for name, bit in bits.items() if mask & bit),
+			"samples": len(inside),
 		}
 
 
@@ -280,31 +287,33 @@ def gpu_arm(args):
 		return float(t.item())
 
 	# ---------------- device-resident loop: `value`
+	# After the discontinuity stepping member j stands at t = tau_j (10…25). All members are then sampled
+	# on the common time grid T_k = 30 + 10 k, as a user of the reference samples a trajectory
+	# (examples/mackey_glass.py:76-78). The only per-step input is the scalar T_k (8 bytes); the ensemble
+	# state (anchor rings, controller state) is resident in HBM.
 	DDE = fresh()
 	engine = DDE._engine
 	stream = torch.cuda.current_stream()
 	engine.set_stream(stream.cuda_stream)
-	t0_members = engine.get_t()
-	d_targets = pinned_empty((members,))
+	T0 = 30.0
 	k = 0
 	for _ in range(args.warmup):
 		k += 1
-		np.add(t0_members, ADVANCE*k, out=d_targets)
-		engine.integrate(d_targets, fetch=False)
+		engine.integrate(T0+ADVANCE*k, fetch=False)
 	accepted_before = engine.sum_counters()[0]
 	launches_before = engine.launch_count
-	# the per-member target times of all timed steps are staged up front: inputs are resident
-	# in HBM when the timed region starts
-	all_targets = [t0_members+ADVANCE*(k+1+j) for j in range(args.steps)]
 	ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-	with ClockSampler(local_rank) as clocks:
-		barrier()
-		ev0.record(stream)
-		for j in range(args.steps):
-			engine.integrate(all_targets[j], fetch=False)
-		ev1.record(stream)
-		barrier()
-	k += args.steps
+	clocks = ClockSampler(local_rank)
+	barrier()
+	clocks.mark_start()
+	ev0.record(stream)
+	for _ in range(args.steps):
+		k += 1
+		engine.integrate(T0+ADVANCE*k, fetch=False)
+	ev1.record(stream)
+	barrier()
+	clocks.mark_end()
+	clocks.stop()
 	ms = reduce_max(ev0.elapsed_time(ev1))
 	launches = engine.launch_count-launches_before
 	accepted = engine.sum_counters()[0]-accepted_before
@@ -315,26 +324,26 @@ def gpu_arm(args):
 	value = total_accepted/(ms*1e-3)
 
 	# ---------------- end to end through the public API with host buffers: `e2e`
+	# per step: the target time goes host→device, the kernel runs, states (N×8 B) and per-member status
+	# (N×4 B) come back device→host into pinned memory; all inside the timed region
 	out = pinned_empty((members, 1))
 	for _ in range(2):
 		k += 1
-		np.add(t0_members, ADVANCE*k, out=d_targets)
-		DDE.integrate(d_targets, out=out)
+		DDE.integrate(T0+ADVANCE*k, out=out)
 	accepted_before = engine.sum_counters()[0]
 	barrier()
 	w0 = time.perf_counter()
 	ev0.record(stream)
+	checksum = 0.0
 	for _ in range(args.steps):
 		k += 1
-		np.add(t0_members, ADVANCE*k, out=d_targets)     # this step's inputs, written into pinned host memory
-		result = DDE.integrate(d_targets, out=out)         # H2D targets, kernel, D2H states + status
-		checksum = float(result[0, 0])
+		result = DDE.integrate(T0+ADVANCE*k, out=out)     # H2D target, kernel, D2H states + status, status check
+		checksum += float(result[0, 0])
 	ev1.record(stream)
 	barrier()
 	e2e_ms = reduce_max(max(ev0.elapsed_time(ev1), 1e3*(time.perf_counter()-w0)))
 	e2e_accepted = reduce_sum(engine.sum_counters()[0]-accepted_before)
 	e2e_value = e2e_accepted/(e2e_ms*1e-3)
-	del checksum
 
 	peak, peak_source = measured_peaks()
 	# dominant kernel = jdde_k_integrate, one launch per step: algorithmic bytes of this rank's launches ÷ their duration
@@ -343,7 +352,7 @@ def gpu_arm(args):
 		"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
 		"ms_per_step": ms/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
 		"dtype": "f64", "data": "synthetic", "config": config(members, world),
-		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(members*8), "d2h_bytes_per_step": int(members*8+members*4),
+		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(members*8+members*4),
 			"ms_per_step": e2e_ms/args.steps},
 		"gpu_launches": int(launches),
 		"clocks": clocks.summary(),

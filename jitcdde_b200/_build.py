@@ -66,18 +66,53 @@ def _engine_hash():
 	return h.hexdigest()[:12]
 
 
+def use_window(program):
+	"""
+	Keep the anchors around each lookup cursor in registers (JD_WINDOW in csrc/jdde_engine.cuh)?
+	Measured on B200 for the Mackey–Glass ensemble (profiles/variants_r01.md): the window removes most
+	global loads, but its registers cost more resident warps than the loads cost latency — L1 serves the
+	sequential ring reads well. Off by default; JITCDDE_B200_WINDOW=1 turns it on (tests exercise both).
+	"""
+	override = os.environ.get("JITCDDE_B200_WINDOW")
+	if override is not None:
+		return bool(int(override)) and program.n_sites > 0
+	return False
+
+
+def launch_shape(program):
+	"""
+	(block size, resident blocks per SM) the kernels are compiled for. The integrate kernel is bound by
+	latency (dependent FP64 chains and scattered anchor loads), so for small systems it is compiled for
+	64 registers per thread — 32 resident warps per SM — and lets ptxas spill the cold controller state;
+	measured optimum on B200 (profiles/variants_r01.md). Larger systems keep all registers.
+	"""
+	override = os.environ.get("JITCDDE_B200_LAUNCH")
+	if override:
+		block, blocks = override.split("x")
+		return int(block), int(blocks)
+	if program.n <= 2:
+		return 64, 16
+	if program.n <= 8:
+		return 128, 4
+	return 128, 1
+
+
 def image_path(program, n_basic, mode, block, extra_flags=()):
-	tag = hashlib.sha256(repr((program.key, n_basic, mode, block, tuple(extra_flags), _engine_hash())).encode()).hexdigest()[:20]
+	tag = hashlib.sha256(repr((program.key, n_basic, mode, block, tuple(extra_flags), use_window(program), launch_shape(program), _engine_hash())).encode()).hexdigest()[:20]
 	return os.path.join(CACHE, f"jdde_{tag}.cubin")
 
 
-def build_image(program, n_basic=None, mode=FAST, block=128, extra_flags=(), force=False, verbose=False):
+def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), force=False, verbose=False):
 	"""
 	Compile the kernel image for one generated right-hand side
 	(`program` = _codegen.RHSProgram). Returns the path of the cubin.
 	"""
 	n_basic = n_basic or program.n
 	os.makedirs(CACHE, exist_ok=True)
+	default_block, default_blocks = launch_shape(program)
+	block = block or default_block
+	if not any(f.startswith("-DJD_MIN_BLOCKS") for f in extra_flags):
+		extra_flags = (*extra_flags, f"-DJD_MIN_BLOCKS={default_blocks}")
 	path = image_path(program, n_basic, mode, block, extra_flags)
 	if os.path.exists(path) and not force:
 		return path
@@ -92,6 +127,7 @@ def build_image(program, n_basic=None, mode=FAST, block=128, extra_flags=(), for
 	cmd = [nvcc(), "-cubin", *flags,
 		f"-DJD_N={program.n}", f"-DJD_NBASIC={n_basic}", f"-DJD_NSITES={program.n_sites}",
 		f"-DJD_NPARAMS={program.n_params}", f'-DJD_RHS_FILE="{rhs}"', f"-DJD_BLOCK={block}",
+		f"-DJD_WINDOW={int(use_window(program))}",
 		*extra_flags,
 		os.path.join(CSRC, "jdde_kernels.cu"), "-o", path + ".tmp"]
 	if verbose:

@@ -203,9 +203,9 @@ class Engine:
 		self._check(self.lib.jdde_set_integration_parameters(self._h, ctypes.byref(p), float(max_delay)))
 
 	def _targets(self, target):
+		if np.ndim(target) == 0:
+			return np.array([target], dtype=np.float64), 0
 		target = _f64(target)
-		if target.ndim == 0:
-			return target.reshape(1), 0
 		if target.shape != (self.N,):
 			raise ValueError(f"target times must be a scalar or have shape ({self.N},)")
 		return target, 1

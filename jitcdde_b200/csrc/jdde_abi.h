@@ -4,7 +4,7 @@
  *
  * Data layout in HBM for an ensemble of n_members trajectories ("members"):
  *
- *   ring   [n_members][cap][A] doubles. One member's anchors are contiguous (member-major):
+ *   ring   [n_members][cap][A] doubles (+ 16 doubles of skew per member, jdde_ring_stride). One member's anchors are contiguous (member-major):
  *          a trajectory reads and writes its history sequentially in time, so consecutive steps
  *          of a thread hit the same or the next 128-byte line. An anchor is
  *          { time, state[n], diff[n], padding } with A = 1+2n rounded up to a multiple of 4
@@ -49,6 +49,8 @@ typedef struct jdde_problem
 	long long n_members;
 	int cap;
 	int anchor_stride;
+	long long ring_stride;   /* doubles between the rings of consecutive members: cap·A plus a skew of one 128-byte
+	                            line, so that equal slots of neighbouring members do not fall into the same cache sets */
 	double max_delay;
 	jdde_int_params P;
 } jdde_problem;
@@ -59,9 +61,20 @@ typedef struct jdde_image_desc_t
 	int magic, abi, n, n_basic, n_sites, n_params, anchor_stride, block;
 } jdde_image_desc_t;
 
-static inline int jdde_anchor_stride(int n)
+#if defined(__CUDACC__)
+#  define JDDE_ABI_FN static __host__ __device__ inline
+#else
+#  define JDDE_ABI_FN static inline
+#endif
+
+JDDE_ABI_FN int jdde_anchor_stride(int n)
 {
 	return ((1+2*n) + 3) & ~3;
+}
+
+JDDE_ABI_FN long long jdde_ring_stride(int cap, int anchor_stride)
+{
+	return (long long)cap*anchor_stride + 16;
 }
 
 #endif

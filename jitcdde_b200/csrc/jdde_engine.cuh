@@ -26,6 +26,11 @@
  *   - the history is a power-of-two ring per member in HBM (jdde_abi.h), addressed by logical
  *     indices; the bracket search keeps one cursor per lookup site and reproduces the reference's
  *     walk including its tie-breaks;
+ *   - JD_WINDOW (small systems): per lookup site the anchor pair the cursor points at AND the
+ *     next anchor are kept in registers across stages, attempts and steps. A lookup that stays
+ *     in its segment touches no memory; one that moves on takes the prefetched anchor and issues
+ *     the load of the following one, whose latency is hidden behind the rest of the step. Only
+ *     accepted anchors (index <= current) are cached: they are immutable while the kernel runs;
  *   - arithmetic keeps the reference's association order; with -fmad=false the results are
  *     bit-identical to the CPU oracle (tests/), with FMA contraction they agree to rounding.
  *
@@ -47,6 +52,9 @@
 #endif
 
 #define JD_A ((((1+2*JD_N))+3)&~3)
+#ifndef JD_WINDOW
+#define JD_WINDOW 0
+#endif
 #define JD_NORM_THRESHOLD (1e-30)     /* jitced_template.c:15 */
 
 #if defined(__CUDACC__)
@@ -59,7 +67,57 @@
 
 namespace jdde {
 
-/* pair of anchors bracketing a time (what `anchors(t)` returns in the reference: anchor *) */
+/* 16-byte vector access to anchors (anchors are 32-byte aligned: LDG.128 / STG.128) */
+struct alignas(16) d2 { double x, y; };
+
+JD_FN void load_anchor(double const * const p, double (&a)[JD_A])
+{
+	JD_UNROLL
+	for (int k = 0; k < JD_A; k += 2)
+	{
+		d2 const v = *reinterpret_cast<d2 const *>(p+k);
+		a[k] = v.x;
+		a[k+1] = v.y;
+	}
+}
+
+JD_FN void store_anchor(double * const p, double const (&a)[JD_A])
+{
+	JD_UNROLL
+	for (int k = 0; k < JD_A; k += 2)
+	{
+		d2 v;
+		v.x = a[k];
+		v.y = a[k+1];
+		*reinterpret_cast<d2 *>(p+k) = v;
+	}
+}
+
+/* pair of anchors bracketing a time (what `anchors(t)` returns in the reference: anchor *);
+ * element 0 of an anchor is its time, 1..n the state, n+1..2n the derivative */
+#if JD_WINDOW
+struct Seg
+{
+	double v[JD_A];
+	double w[JD_A];
+};
+JD_FN double seg_tv(Seg const & s) { return s.v[0]; }
+JD_FN double seg_tw(Seg const & s) { return s.w[0]; }
+
+/* register-resident window of one lookup site: the anchor pair (cursor, cursor+1) plus the prefetched
+ * neighbours cursor-1 and cursor+2, so that the cursor can move one anchor in either direction (forward:
+ * time advances; backward: retry with a smaller step after a rejection) without waiting for memory */
+struct Window
+{
+	bool valid;
+	bool prev_ok;
+	bool next_ok;
+	double p[JD_A];
+	double v[JD_A];
+	double w[JD_A];
+	double n[JD_A];
+};
+#else
 struct Seg
 {
 	const double * v;
@@ -67,6 +125,9 @@ struct Seg
 	double tv;
 	double tw;
 };
+JD_FN double seg_tv(Seg const & s) { return s.tv; }
+JD_FN double seg_tw(Seg const & s) { return s.tw; }
+#endif
 
 /* everything one trajectory needs while a kernel runs; lives in registers / local memory */
 struct Member
@@ -76,6 +137,9 @@ struct Member
 	int cap;
 	int first, last, current;
 	int cursor[JD_NSITES > 0 ? JD_NSITES : 1];
+#if JD_WINDOW
+	Window win[JD_NSITES > 0 ? JD_NSITES : 1];
+#endif
 	double par[JD_NPARAMS > 0 ? JD_NPARAMS : 1];
 
 	double cur_t, cur_y[JD_N], cur_d[JD_N];     /* last accepted anchor (`current`) */
@@ -85,15 +149,30 @@ struct Member
 	double err[JD_N];
 	double pws;                                 /* past_within_step */
 	double last_start;                          /* last_actual_step_start */
+	double tfn;                                 /* time of anchor first+1 (prefetched for forget) */
+	bool tfn_valid;
 
 	double dt, last_pws, credit;
 	int count;
 
-	long long accepted, rejected, attempts, extra_rhs;
+	int accepted, rejected, attempts, extra_rhs;   /* since load_member; added to the 64-bit totals by store_member */
 	int status;
 
 	JD_FN double * slot(int const index) const { return ring + (size_t)(index & mask)*JD_A; }
+
+	JD_FN void invalidate_windows()
+	{
+#if JD_WINDOW
+		JD_UNROLL
+		for (int s = 0; s < JD_NSITES; s++)
+			win[s].valid = false;
+#endif
+	}
 };
+
+#if JD_WINDOW
+JD_FN void fill_window(Member & M, int const site);
+#endif
 
 /* ------------------------------------------------------------------ load / store */
 
@@ -101,7 +180,7 @@ JD_FN void load_member(jdde_problem const & P, long long const m, Member & M)
 {
 	M.cap = P.cap;
 	M.mask = P.cap-1;
-	M.ring = P.ring + (size_t)m*P.cap*JD_A;
+	M.ring = P.ring + (size_t)m*P.ring_stride;
 	M.first = P.first[m];
 	M.last = P.last[m];
 	M.current = P.current[m];
@@ -111,7 +190,8 @@ JD_FN void load_member(jdde_problem const & P, long long const m, Member & M)
 	JD_UNROLL
 	for (int k = 0; k < JD_NPARAMS; k++)
 		M.par[k] = P.par[(size_t)k*P.n_members+m];
-	double const * const c = M.slot(M.current);
+	double c[JD_A];
+	load_anchor(M.slot(M.current), c);
 	M.cur_t = c[0];
 	JD_UNROLL
 	for (int i = 0; i < JD_N; i++)
@@ -119,6 +199,12 @@ JD_FN void load_member(jdde_problem const & P, long long const m, Member & M)
 		M.cur_y[i] = c[1+i];
 		M.cur_d[i] = c[1+JD_N+i];
 	}
+#if JD_WINDOW
+	JD_UNROLL
+	for (int s = 0; s < JD_NSITES; s++)
+		fill_window(M, s);              /* issued now, needed at the first lookup */
+#endif
+	M.tfn_valid = false;
 	M.has_old = false;
 	M.pws = 0.0;
 	M.last_start = P.last_start[m];
@@ -126,10 +212,7 @@ JD_FN void load_member(jdde_problem const & P, long long const m, Member & M)
 	M.last_pws = P.last_pws[m];
 	M.credit = P.credit[m];
 	M.count = P.count[m];
-	M.accepted = P.accepted[m];
-	M.rejected = P.rejected[m];
-	M.attempts = P.attempts[m];
-	M.extra_rhs = P.extra_rhs[m];
+	M.accepted = M.rejected = M.attempts = M.extra_rhs = 0;
 	M.status = P.status[m];
 }
 
@@ -146,30 +229,31 @@ JD_FN void store_member(jdde_problem const & P, long long const m, Member const 
 	P.last_pws[m] = M.last_pws;
 	P.credit[m] = M.credit;
 	P.count[m] = M.count;
-	P.accepted[m] = M.accepted;
-	P.rejected[m] = M.rejected;
-	P.attempts[m] = M.attempts;
-	P.extra_rhs[m] = M.extra_rhs;
+	P.accepted[m] += M.accepted;
+	P.rejected[m] += M.rejected;
+	P.attempts[m] += M.attempts;
+	P.extra_rhs[m] += M.extra_rhs;
 	P.status[m] = M.status;
 }
 
 /* ------------------------------------------------------------------ history lookup */
 
 /* get_past_anchors, jitced_template.c:193-217. One cursor per lookup site; the walk's stopping
- * rules decide which segment is taken when t equals an anchor time. */
-JD_FN Seg anchors(Member & M, int const site, double const t)
+ * rules decide which segment is taken when t equals an anchor time.
+ * This is the walk through memory; returns the index of the left anchor. */
+JD_FN int walk(Member & M, int const site, double const t, double const * & pa, double const * & pn, double & ta, double & tn)
 {
 	int ca = M.cursor[site];
-	double const * pa = M.slot(ca);
-	double ta = pa[0];
+	pa = M.slot(ca);
+	ta = pa[0];
 	while (ta > t && ca > M.first)
 	{
 		--ca;
 		pa = M.slot(ca);
 		ta = pa[0];
 	}
-	double const * pn = M.slot(ca+1);
-	double tn = pn[0];
+	pn = M.slot(ca+1);
+	tn = pn[0];
 	while (tn < t && ca+2 <= M.last)
 	{
 		++ca;
@@ -181,16 +265,112 @@ JD_FN Seg anchors(Member & M, int const site, double const t)
 	if (t > M.cur_t)
 		M.pws = fmax(M.pws, t-M.cur_t);
 	M.cursor[site] = ca;
+	return ca;
+}
+
+#if JD_WINDOW
+/* (re)load the window of a site around its cursor; only accepted anchors (index <= current) are cached */
+JD_FN void fill_window(Member & M, int const site)
+{
+	Window & W = M.win[site];
+	int const ca = M.cursor[site];
+	W.valid = ca+1 <= M.current;
+	if (!W.valid)
+		return;
+	load_anchor(M.slot(ca), W.v);
+	load_anchor(M.slot(ca+1), W.w);
+	W.next_ok = ca+2 <= M.current;
+	if (W.next_ok)
+		load_anchor(M.slot(ca+2), W.n);
+	W.prev_ok = ca-1 >= M.first;
+	if (W.prev_ok)
+		load_anchor(M.slot(ca-1), W.p);
+}
+
+JD_FN Seg anchors(Member & M, int const site, double const t)
+{
+	Window & W = M.win[site];
 	Seg s;
-	s.v = pa; s.w = pn; s.tv = ta; s.tw = tn;
+	/* Fast path: the same comparisons as in walk(), on cached anchors. They are accepted anchors, hence
+	 * immutable while the kernel runs and not later than current.time. */
+	if (W.valid)
+	{
+		bool hit = true;
+		/* while (ca->time > t && ca->previous) ca = ca->previous; */
+		while (W.v[0] > t && M.cursor[site] > M.first)
+		{
+			if (!W.prev_ok)
+			{
+				hit = false;
+				break;
+			}
+			int const ca = --M.cursor[site];
+			JD_UNROLL
+			for (int k = 0; k < JD_A; k++)
+			{
+				W.n[k] = W.w[k];
+				W.w[k] = W.v[k];
+				W.v[k] = W.p[k];
+			}
+			W.next_ok = true;
+			W.prev_ok = ca-1 >= M.first;
+			if (W.prev_ok)
+				load_anchor(M.slot(ca-1), W.p);    /* prefetch */
+		}
+		/* while (ca->next->time < t && ca->next->next) ca = ca->next; */
+		while (hit && W.w[0] < t)
+		{
+			if (!W.next_ok)
+			{
+				hit = false;      /* next anchor is tentative or missing: let walk() decide */
+				break;
+			}
+			int const ca = ++M.cursor[site];
+			JD_UNROLL
+			for (int k = 0; k < JD_A; k++)
+			{
+				W.p[k] = W.v[k];
+				W.v[k] = W.w[k];
+				W.w[k] = W.n[k];
+			}
+			W.prev_ok = true;
+			W.next_ok = ca+2 <= M.current;
+			if (W.next_ok)
+				load_anchor(M.slot(ca+2), W.n);    /* prefetch: not needed before the cursor moves again */
+		}
+		if (hit)
+		{
+			/* t <= time of an accepted anchor <= current.time: no past-within-step contribution */
+			JD_UNROLL
+			for (int k = 0; k < JD_A; k++)
+			{
+				s.v[k] = W.v[k];
+				s.w[k] = W.w[k];
+			}
+			return s;
+		}
+	}
+	double const * pa; double const * pn; double ta, tn;
+	walk(M, site, t, pa, pn, ta, tn);
+	load_anchor(pa, s.v);
+	load_anchor(pn, s.w);
+	fill_window(M, site);
 	return s;
 }
+#else
+JD_FN Seg anchors(Member & M, int const site, double const t)
+{
+	Seg s;
+	walk(M, site, t, s.v, s.w, s.tv, s.tw);
+	return s;
+}
+#endif
 
 /* get_past_value, jitced_template.c:221-235 */
 JD_FN double past_y(double const t, int const index, Seg const & s)
 {
-	double const q = s.tw-s.tv;
-	double const x = (t - s.tv)/q;
+	double const q = seg_tw(s)-seg_tv(s);
+	double const x = (t - seg_tv(s))/q;
 	double const a = s.v[1+index];
 	double const b = s.v[1+JD_N+index] * q;
 	double const c = s.w[1+index];
@@ -201,8 +381,8 @@ JD_FN double past_y(double const t, int const index, Seg const & s)
 /* get_past_diff, jitced_template.c:237-251 */
 JD_FN double past_dy(double const t, int const index, Seg const & s)
 {
-	double const q = s.tw-s.tv;
-	double const x = (t - s.tv)/q;
+	double const q = seg_tw(s)-seg_tv(s);
+	double const x = (t - seg_tv(s))/q;
 	double const a = s.v[1+index];
 	double const b = s.v[1+JD_N+index] * q;
 	double const c = s.w[1+index];
@@ -213,10 +393,15 @@ JD_FN double past_dy(double const t, int const index, Seg const & s)
 JD_FN Seg segment_at(Member const & M, int const vi)
 {
 	Seg s;
+#if JD_WINDOW
+	load_anchor(M.slot(vi), s.v);
+	load_anchor(M.slot(vi+1), s.w);
+#else
 	s.v = M.slot(vi);
 	s.w = M.slot(vi+1);
 	s.tv = s.v[0];
 	s.tw = s.w[0];
+#endif
 	return s;
 }
 
@@ -283,16 +468,20 @@ JD_FN void get_next_step(Member & M, double const delta_t)
 		M.has_old = true;
 	}
 	M.new_t = nt;
-	double * const dst = M.slot(M.last);
-	dst[0] = nt;
+	double a[JD_A];
+	a[0] = nt;
 	JD_UNROLL
 	for (int i = 0; i < JD_N; i++)
 	{
 		M.new_y[i] = ny[i];
 		M.new_d[i] = nd[i];
-		dst[1+i] = ny[i];
-		dst[1+JD_N+i] = nd[i];
+		a[1+i] = ny[i];
+		a[1+JD_N+i] = nd[i];
 	}
+	JD_UNROLL
+	for (int k = 1+2*JD_N; k < JD_A; k++)
+		a[k] = 0.0;
+	store_anchor(M.slot(M.last), a);
 }
 
 /* get_p, jitced_template.c:474-498 */
@@ -344,16 +533,35 @@ JD_FN void accept_step(Member & M)
 	}
 }
 
-/* forget, jitced_template.c:534-561 */
+/* forget, jitced_template.c:534-561. The reference forgets once per integrate() call; the thresholds only
+ * grow, so forgetting after every accepted step and once more at the end of the call leaves the same first
+ * anchor. Done incrementally, each call inspects one anchor time that was requested a whole step earlier
+ * (tfn), instead of a serial chain of ~20 cold loads at the end of the kernel. */
 JD_FN void forget(Member & M, double const delay)
 {
 	double const threshold = fmin(M.cur_t - delay, M.last_start);
-	while (M.first+1 < M.last && M.slot(M.first+1)[0] < threshold)
+	if (!M.tfn_valid)
+	{
+		M.tfn = M.slot(M.first+1)[0];
+		M.tfn_valid = true;
+	}
+	bool moved = false;
+	while (M.first+1 < M.last && M.tfn < threshold)
+	{
 		M.first++;
-	JD_UNROLL
-	for (int s = 0; s < JD_NSITES; s++)
-		if (M.cursor[s] < M.first)
-			M.cursor[s] = M.first;
+		M.tfn = M.slot(M.first+1)[0];
+		moved = true;
+	}
+	if (moved)
+	{
+		JD_UNROLL
+		for (int s = 0; s < JD_NSITES; s++)
+			if (M.cursor[s] < M.first)
+			{
+				M.cursor[s] = M.first;
+				M.invalidate_windows();
+			}
+	}
 }
 
 /* get_recent_state, jitced_template.c:287-320 */
@@ -435,40 +643,40 @@ JD_FN bool adjust_step_size(Member & M, jdde_int_params const & P)
 	return true;
 }
 
-/* try_single_step, _jitcdde.py:838-861 */
+/* try_single_step, _jitcdde.py:838-861. Written as one loop so that the step code is instantiated once:
+ * pass 0 is the attempt with `length`; if a delayed lookup reached into the step (past within step),
+ * passes 1..pws_max_iterations repeat the step with self.dt (sic, :853) until two successive results agree. */
 JD_FN bool try_single_step(Member & M, jdde_int_params const & P, double const length)
 {
-	get_next_step(M, length);
-
-	if (M.pws != 0.0)
+	double step = length;
+	int count = 0;
+	for (;;)
 	{
-		M.last_pws = M.pws;
-
-		/* if possible, shrink the step to make the integration explicit */
-		if (M.dt > P.pws_factor*M.pws)
+		get_next_step(M, step);
+		if (count == 0)
 		{
-			M.dt /= P.pws_factor;
-			control_for_min_step(M, P);
-			return false;
-		}
-
-		bool converged = false;
-		for (int count = 1; count <= P.pws_max_iterations; count++)
-		{
-			M.count = count;
-			get_next_step(M, M.dt);
-			if (check_new_y_diff(M, P.pws_atol, P.pws_rtol))
-			{
-				converged = true;
+			if (M.pws == 0.0)
 				break;
+			M.last_pws = M.pws;
+			/* if possible, shrink the step to make the integration explicit */
+			if (M.dt > P.pws_factor*M.pws)
+			{
+				M.dt /= P.pws_factor;
+				control_for_min_step(M, P);
+				return false;
 			}
 		}
-		if (!converged)
+		else if (check_new_y_diff(M, P.pws_atol, P.pws_rtol))
+			break;
+		if (count == P.pws_max_iterations)
 		{
 			M.dt /= P.pws_factor;
 			control_for_min_step(M, P);
 			return false;
 		}
+		count++;
+		M.count = count;
+		step = M.dt;
 	}
 	return adjust_step_size(M, P);
 }
@@ -488,8 +696,7 @@ JD_FN bool ensure_room(Member & M, double const max_delay)
 
 /* the `while t < target` loops of integrate (_jitcdde.py:830-832) and of
  * step_on_discontinuities (:988-993, steps capped at the target) */
-template <bool CAPPED>
-JD_FN void step_until(Member & M, jdde_problem const & P, double const target, long long & budget)
+JD_FN void step_until(Member & M, jdde_problem const & P, double const target, bool const capped, long long & budget)
 {
 	while (M.cur_t < target && M.status == JDDE_STATUS_OK)
 	{
@@ -507,11 +714,12 @@ JD_FN void step_until(Member & M, jdde_problem const & P, double const target, l
 			M.status = JDDE_STATUS_BUDGET;
 			break;
 		}
-		double const length = CAPPED ? fmin(M.dt, target-M.cur_t) : M.dt;
+		double const length = capped ? fmin(M.dt, target-M.cur_t) : M.dt;
 		if (try_single_step(M, P.P, length))
 		{
 			accept_step(M);
 			M.accepted++;
+			forget(M, P.max_delay);
 		}
 		else
 			M.rejected++;
@@ -524,6 +732,7 @@ JD_FN void step_until(Member & M, jdde_problem const & P, double const target, l
 JD_FN void remove_last_anchor(Member & M)
 {
 	M.has_old = false;
+	M.invalidate_windows();
 	M.last--;
 	JD_UNROLL
 	for (int s = 0; s < JD_NSITES; s++)
@@ -549,6 +758,7 @@ JD_FN void truncate_past(Member & M, double const time)
 	while (M.last-1 > M.first && M.slot(M.last-1)[0] >= time)
 		remove_last_anchor(M);
 
+	M.invalidate_windows();
 	Seg const left = segment_at(M, M.last-1);
 	double ny[JD_N], nd[JD_N];
 	for (int i = 0; i < JD_N; i++)
@@ -571,7 +781,7 @@ JD_FN void truncate_past(Member & M, double const time)
 /* extrema, jitced_template.c:253-285 */
 JD_FN void extrema(Seg const & s, int const index, double & minimum, double & maximum)
 {
-	double const q = s.tw-s.tv;
+	double const q = seg_tw(s)-seg_tv(s);
 	double const a = s.v[1+index];
 	double const b = s.v[1+JD_N+index] * q;
 	double const c = s.w[1+index];
@@ -796,6 +1006,7 @@ JD_FN void integrate_blindly(Member & M, jdde_problem const & P, double const ta
 			{
 				double norms[JD_N/JD_NBASIC];
 				orthonormalise(M, n_lyap, P.max_delay, norms);
+				M.invalidate_windows();
 				reload_current(M);
 				for (int i = 0; i < n_lyap; i++)
 					lyap_sum[i] += log(norms[i])/dt;
@@ -838,7 +1049,7 @@ JD_FN void member_set_past(jdde_problem const & P, long long const m, int const 
 		states += (size_t)m*n_anchors*JD_N;
 		diffs += (size_t)m*n_anchors*JD_N;
 	}
-	double * const ring = P.ring + (size_t)m*P.cap*JD_A;
+	double * const ring = P.ring + (size_t)m*P.ring_stride;
 	for (int k = 0; k < n_anchors; k++)
 	{
 		double * const a = ring + (size_t)k*JD_A;
@@ -882,7 +1093,7 @@ JD_FN void member_integrate(jdde_problem const & P, long long const m, double co
 	if (n_steps == 0)
 	{
 		target = per_member ? targets[m] : targets[0];
-		step_until<false>(M, P, target, budget);
+		step_until(M, P, target, false, budget);
 	}
 	else
 	{
@@ -893,7 +1104,7 @@ JD_FN void member_integrate(jdde_problem const & P, long long const m, double co
 		{
 			if (!(resume && s == P.resume_index[m]))
 				target = M.cur_t + steps[s];
-			step_until<true>(M, P, target, budget);
+			step_until(M, P, target, true, budget);
 			if (M.status != JDDE_STATUS_OK)
 				break;
 		}

@@ -84,7 +84,7 @@ jdde_k_get(jdde_problem const P, int const what, double * const out)
 	long long const m = JD_MEMBER_INDEX();
 	if (m >= P.n_members)
 		return;
-	double const * const ring = P.ring + (size_t)m*P.cap*JD_A;
+	double const * const ring = P.ring + (size_t)m*P.ring_stride;
 	if (what == 0)
 		out[m] = ring[(size_t)(P.current[m] & (P.cap-1))*JD_A];
 	else if (what == 1)
@@ -139,8 +139,8 @@ jdde_k_regrow(jdde_problem const P, double * const new_ring, int const new_cap)
 	long long const m = JD_MEMBER_INDEX();
 	if (m >= P.n_members)
 		return;
-	double const * const src = P.ring + (size_t)m*P.cap*JD_A;
-	double * const dst = new_ring + (size_t)m*new_cap*JD_A;
+	double const * const src = P.ring + (size_t)m*P.ring_stride;
+	double * const dst = new_ring + (size_t)m*jdde_ring_stride(new_cap, JD_A);
 	int const first = P.first[m], last = P.last[m];
 	for (int k = first; k <= last; k++)
 	{

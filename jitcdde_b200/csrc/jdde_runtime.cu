@@ -202,8 +202,9 @@ int jdde_create(const jdde_desc * desc, jdde_handle ** out)
 	P.n_members = desc->n_members;
 	P.cap = desc->ring_capacity;
 	P.anchor_stride = A;
+	P.ring_stride = jdde_ring_stride(P.cap, A);
 	int rc;
-	if ((rc = dev_alloc(h, &P.ring, N*(size_t)P.cap*A))) return bail(rc);
+	if ((rc = dev_alloc(h, &P.ring, N*(size_t)P.ring_stride))) return bail(rc);
 	if ((rc = dev_alloc(h, &P.par, N*(size_t)(desc->n_params ? desc->n_params : 1)))) return bail(rc);
 	if ((rc = dev_alloc(h, &P.dt, N))) return bail(rc);
 	if ((rc = dev_alloc(h, &P.last_pws, N))) return bail(rc);
@@ -686,7 +687,7 @@ int jdde_get_state(jdde_handle * h, int64_t member, int32_t max_anchors, int32_t
 		return JDDE_OK;
 	int const A = h->P.anchor_stride, cap = h->P.cap, n = h->desc.n;
 	std::vector<double> ring((size_t)cap*A);
-	JD_CUDA(h, cudaMemcpy(ring.data(), h->P.ring+(size_t)member*cap*A, ring.size()*sizeof(double), cudaMemcpyDeviceToHost));
+	JD_CUDA(h, cudaMemcpy(ring.data(), h->P.ring+(size_t)member*h->P.ring_stride, ring.size()*sizeof(double), cudaMemcpyDeviceToHost));
 	for (int k = 0; k < count; k++)
 	{
 		const double * a = ring.data()+(size_t)((first+k) & (cap-1))*A;
@@ -706,7 +707,7 @@ int jdde_grow_ring(jdde_handle * h, int32_t new_capacity)
 		return fail(h, JDDE_E_INVALID, "new capacity must be a larger power of two");
 	size_t const N = (size_t)h->desc.n_members;
 	double * new_ring = nullptr;
-	cudaError_t e = cudaMalloc((void **)&new_ring, N*(size_t)new_capacity*h->P.anchor_stride*sizeof(double));
+	cudaError_t e = cudaMalloc((void **)&new_ring, N*(size_t)jdde_ring_stride(new_capacity, h->P.anchor_stride)*sizeof(double));
 	if (e != cudaSuccess)
 		return fail(h, JDDE_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
 	if (h->have_past)
@@ -722,6 +723,7 @@ int jdde_grow_ring(jdde_handle * h, int32_t new_capacity)
 	cudaFree(h->P.ring);
 	h->P.ring = new_ring;
 	h->P.cap = new_capacity;
+	h->P.ring_stride = jdde_ring_stride(new_capacity, h->P.anchor_stride);
 	h->desc.ring_capacity = new_capacity;
 	return JDDE_OK;
 }

@@ -1,0 +1,32 @@
+"""A/B timing of kernel build variants on the bench workload (device-resident loop). Usage: python scripts/gpu_variants.py "W=1,MB=4" "W=0,MB=5" ..."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from jitcdde_b200 import _build, _capi
+from oracle import oracle
+from tests import systems
+
+N = int(os.environ.get("MEMBERS", 1250000)); STEPS = int(os.environ.get("STEPS", 20)); WARM = int(os.environ.get("WARM", 13))
+prog = systems.program(systems.mackey_glass()); pars = systems.mg_grid(N)
+ref = None
+for spec in sys.argv[1:]:
+    opts = dict(kv.split("=") for kv in spec.split(","))
+    os.environ["JITCDDE_B200_WINDOW"] = opts.get("W", "1")
+    flags = [f"-DJD_MIN_BLOCKS={opts.get('MB','1')}"] + ([f"-maxrregcount={opts['R']}"] if "R" in opts else []) + [f"-D{d}" for d in opts.get("D","").split("+") if d]
+    block = int(opts.get("B", 128)); cap = int(opts.get("CAP", 128))
+    image = _build.build_image(prog, mode=opts.get("mode", "fast"), block=block, extra_flags=tuple(flags))
+    E = _capi.Engine(1, 1, prog.n_sites, 2, N, ring_capacity=cap); E.load_image(image)
+    E.set_past(np.array([-1.0, 0.0]), np.ones((2, 1)), np.zeros((2, 1))); E.set_parameters(pars)
+    E.set_integration_parameters(25.0, **oracle.DEFAULTS)
+    E.step_on_discontinuities(pars[:, 1:2].copy()); t0 = E.get_t()
+    T0 = 30.0
+    for k in range(1, WARM+1): E.integrate(T0+10.0*k, fetch=False)
+    a0 = E.sum_counters()[0]; E.synchronize(); w0 = time.perf_counter()
+    for k in range(WARM+1, WARM+STEPS+1): E.integrate(T0+10.0*k, fetch=False)
+    E.synchronize(); el = time.perf_counter()-w0
+    a1 = E.sum_counters()[0]
+    out, st = E.integrate(T0+10.0*(WARM+STEPS))
+    chk = float(out.sum())
+    if ref is None: ref = chk
+    print(f"{spec:28s} {1e3*el/STEPS:8.3f} ms/step  {(a1-a0)/el:.3e} steps/s  status={np.unique(st)} checksum_rel_dev={abs(chk-ref)/abs(ref):.2e}", flush=True)
+    E.close()

@@ -56,7 +56,7 @@ int jdde_create(const jdde_desc * d, jdde_handle ** out)
 	jdde_handle * h = new jdde_handle;
 	h->desc = *d;
 	size_t const N = (size_t)d->n_members;
-	h->ring.assign(N*d->ring_capacity*JD_A, 0.0);
+	h->ring.assign(N*(size_t)jdde_ring_stride(d->ring_capacity, JD_A), 0.0);
 	h->par.assign(N*(JD_NPARAMS ? JD_NPARAMS : 1), 0.0);
 	for (auto v : { &h->dt, &h->last_pws, &h->credit, &h->last_start, &h->aux, &h->aux2 }) v->assign(N, 0.0);
 	h->out.assign(N*JD_N, 0.0); h->out2.assign(N*JD_N, 0.0);
@@ -64,7 +64,7 @@ int jdde_create(const jdde_desc * d, jdde_handle ** out)
 	h->cursor.assign(N*(JD_NSITES ? JD_NSITES : 1), 0);
 	h->resume_index.assign(N, 0); h->resume_target.assign(N, 0.0);
 	for (auto v : { &h->accepted, &h->rejected, &h->attempts, &h->extra_rhs }) v->assign(N, 0);
-	h->P.n_members = d->n_members; h->P.cap = d->ring_capacity; h->P.anchor_stride = JD_A;
+	h->P.n_members = d->n_members; h->P.cap = d->ring_capacity; h->P.anchor_stride = JD_A; h->P.ring_stride = jdde_ring_stride(d->ring_capacity, JD_A);
 	bind(h);
 	*out = h;
 	return JDDE_OK;
@@ -227,7 +227,7 @@ static int run_lyap(jdde_handle * h, const double * target, int pm, int resume, 
 	int const n_lyap = JD_N/JD_NBASIC-1;
 	if (!resume)
 		for (long long m = 0; m < h->P.n_members; m++)
-			h->aux[m] = h->ring[((size_t)m*h->P.cap + (h->current[m] & (h->P.cap-1)))*JD_A];
+			h->aux[m] = h->ring[(size_t)m*h->P.ring_stride + (size_t)(h->current[m] & (h->P.cap-1))*JD_A];
 	run_integrate(h, target, pm, 0, resume, JD_NBASIC);
 	for (long long m = 0; m < h->P.n_members; m++)
 		jdde::member_orthonormalise(h->P, m, n_lyap, h->P.max_delay, h->out2.data(), h->aux.data(), h->out2.data(), h->aux2.data());
@@ -267,14 +267,14 @@ int jdde_resume(jdde_handle * h, double * out_state, double * lyaps, double * de
 int jdde_get_t(jdde_handle * h, double * t)
 {
 	for (long long m = 0; m < h->P.n_members; m++)
-		t[m] = h->ring[((size_t)m*h->P.cap + (h->current[m] & (h->P.cap-1)))*JD_A];
+		t[m] = h->ring[(size_t)m*h->P.ring_stride + (size_t)(h->current[m] & (h->P.cap-1))*JD_A];
 	return JDDE_OK;
 }
 int jdde_get_dt(jdde_handle * h, double * dt) { memcpy(dt, h->dt.data(), h->dt.size()*sizeof(double)); return JDDE_OK; }
 int jdde_get_current_state(jdde_handle * h, double * s)
 {
 	for (long long m = 0; m < h->P.n_members; m++)
-		memcpy(s+(size_t)m*JD_N, &h->ring[((size_t)m*h->P.cap + (h->last[m] & (h->P.cap-1)))*JD_A+1], JD_N*sizeof(double));
+		memcpy(s+(size_t)m*JD_N, &h->ring[(size_t)m*h->P.ring_stride + (size_t)(h->last[m] & (h->P.cap-1))*JD_A+1], JD_N*sizeof(double));
 	return JDDE_OK;
 }
 int jdde_get_status(jdde_handle * h, int32_t * status) { give(h, nullptr, h->out, 0, status); return JDDE_OK; }
@@ -315,7 +315,7 @@ int jdde_get_state(jdde_handle * h, int64_t member, int32_t max_anchors, int32_t
 	if (count > max_anchors || !times) return JDDE_OK;
 	for (int k = 0; k < count; k++)
 	{
-		const double * a = &h->ring[((size_t)member*h->P.cap + ((first+k) & (h->P.cap-1)))*JD_A];
+		const double * a = &h->ring[(size_t)member*h->P.ring_stride + (size_t)((first+k) & (h->P.cap-1))*JD_A];
 		times[k] = a[0];
 		memcpy(states+(size_t)k*JD_N, a+1, JD_N*sizeof(double));
 		memcpy(diffs+(size_t)k*JD_N, a+1+JD_N, JD_N*sizeof(double));
@@ -327,16 +327,17 @@ int jdde_grow_ring(jdde_handle * h, int32_t new_cap)
 {
 	if (new_cap <= h->P.cap || (new_cap & (new_cap-1))) return fail(h, JDDE_E_INVALID, "new capacity must be a larger power of two");
 	size_t const N = (size_t)h->P.n_members;
-	std::vector<double> nr(N*new_cap*JD_A, 0.0);
+	size_t const new_stride = (size_t)jdde_ring_stride(new_cap, JD_A);
+	std::vector<double> nr(N*new_stride, 0.0);
 	if (h->have_past)
 		for (size_t m = 0; m < N; m++)
 		{
 			for (int k = h->first[m]; k <= h->last[m]; k++)
-				memcpy(&nr[(m*new_cap + (k & (new_cap-1)))*JD_A], &h->ring[(m*h->P.cap + (k & (h->P.cap-1)))*JD_A], JD_A*sizeof(double));
+				memcpy(&nr[m*new_stride + (size_t)(k & (new_cap-1))*JD_A], &h->ring[m*h->P.ring_stride + (size_t)(k & (h->P.cap-1))*JD_A], JD_A*sizeof(double));
 			if (h->status[m] == JDDE_STATUS_OVERFLOW) h->status[m] = JDDE_STATUS_OK;
 		}
 	h->ring.swap(nr);
-	h->P.cap = new_cap; h->desc.ring_capacity = new_cap;
+	h->P.cap = new_cap; h->desc.ring_capacity = new_cap; h->P.ring_stride = (long long)new_stride;
 	bind(h);
 	return JDDE_OK;
 }

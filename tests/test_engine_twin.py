@@ -18,6 +18,17 @@ def test_bitwise_against_reference_core(twin, name):
 	scenarios.compare(result, g, exact=True, suffix="_chain" if name == "mg_ensemble" else "")
 
 
+@pytest.mark.parametrize("window", ["0", "1"])
+@pytest.mark.parametrize("name", ["mg_ensemble", "state_dependent", "kuramoto", "roessler", "roessler_jump", "neutral", "mg_lyap"])
+def test_register_window_does_not_change_results(twin, monkeypatch, name, window):
+	"""The register-resident anchor window (JD_WINDOW) is an access-path optimisation: forced on or off,
+	also for systems where the build policy would not choose it, results stay bit-identical."""
+	monkeypatch.setenv("JITCDDE_B200_WINDOW", window)
+	g = scenarios.golden(scenarios.FIXTURE.get(name, name))
+	result = scenarios.ALL[name](g)
+	scenarios.compare(result, g, exact=True, suffix="_chain" if name == "mg_ensemble" else "")
+
+
 def test_reference_golden_vector(twin):
 	"""tests/test_jitcdde.py:88-97: state at T=10 within the reference's own tolerance"""
 	g = scenarios.golden("roessler")

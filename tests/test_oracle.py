@@ -139,6 +139,26 @@ def test_neutral():
 	np.testing.assert_allclose(samples[-1], system["control"], rtol=1e-4)
 
 
+def test_neutral_is_ulp_sensitive():
+	"""Why GPU results for this system are compared at the reference's own tolerance (1e-4): changing one
+	initial value by one ulp changes the reference algorithm's accept/reject sequence and its result by ~1e-5."""
+	system = systems.neutral()
+	g = scenarios.golden("neutral")
+	lib = oracle.build(systems.program(system))
+	outcomes = []
+	for factor in (1.0, 1.0+2.3e-16):
+		past = [(a[0], a[1].copy(), a[2].copy()) for a in scenarios.past_of(g)]
+		for anchor in past:
+			anchor[1][0] *= factor
+		T = oracle.Trajectory(lib, past, max_delay=system["delay"], rtol=1e-5)
+		T.adjust_diff()
+		outcomes.append((np.array([T.integrate(t) for t in g["times"]]), T.counters))
+	(a, ca), (b, cb) = outcomes
+	deviation = np.max(np.abs(a-b)/np.abs(a))
+	assert 1e-9 < deviation < 1e-4
+	np.testing.assert_allclose(b[-1], system["control"], rtol=1e-4)
+
+
 def test_state_dependent_delay():
 	system = systems.state_dependent()
 	g = scenarios.golden("state_dependent")

@@ -20,18 +20,19 @@ _OUT = os.path.join(_HERE, "host_twin", "_build")
 
 def build_twin(program, n_basic=None):
 	n_basic = n_basic or program.n
+	window = int(_build.use_window(program))
 	os.makedirs(_OUT, exist_ok=True)
 	rhs = os.path.join(_OUT, f"rhs_{program.key}.inc")
 	with open(rhs, "w") as f:
 		f.write(program.body)
-	so = os.path.join(_OUT, f"twin_{program.key}_{n_basic}.so")
+	so = os.path.join(_OUT, f"twin_{program.key}_{n_basic}_w{window}.so")
 	src = os.path.join(_HERE, "host_twin", "twin.cpp")
 	deps = [src] + [os.path.join(_build.CSRC, x) for x in ("jdde_engine.cuh", "jdde_math.h", "jdde_abi.h")]
 	if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
 		subprocess.run([
 			"g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
 			f"-DJD_N={program.n}", f"-DJD_NBASIC={n_basic}", f"-DJD_NSITES={program.n_sites}",
-			f"-DJD_NPARAMS={program.n_params}", f'-DJD_RHS_FILE="{rhs}"',
+			f"-DJD_NPARAMS={program.n_params}", f'-DJD_RHS_FILE="{rhs}"', f"-DJD_WINDOW={window}",
 			f"-I{_build.CSRC}", src, "-o", so, "-lm",
 		], check=True)
 	lib = ctypes.CDLL(so)

@@ -215,10 +215,16 @@ class Engine:
 		if fetch and out is None:
 			out = np.empty((self.N, self.n))
 		if fetch and status is None:
-			status = np.empty(self.N, dtype=np.int32)
+			status = self._pinned_status()
 		self._check(self.lib.jdde_integrate(self._h, _dp(target), pm, _dp(out) if fetch else None,
 			status.ctypes.data_as(c_int32_p) if fetch else None))
 		return out, status
+
+	def _pinned_status(self):
+		"""per-member status lands in page-locked memory (full-bandwidth D2H); callers get a fresh copy only if they keep it"""
+		if getattr(self, "_status_buffer", None) is None:
+			self._status_buffer = pinned_empty((self.N,), np.int32)
+		return self._status_buffer
 
 	def step_on_discontinuities(self, steps, out=None, status=None):
 		steps = _f64(steps)

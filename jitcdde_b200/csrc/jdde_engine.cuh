@@ -55,6 +55,8 @@
 #ifndef JD_WINDOW
 #define JD_WINDOW 0
 #endif
+/* Lookups hand anchor pairs around by value (registers) when anchors are small, by pointer otherwise */
+#define JD_SEG_BY_VALUE (JD_WINDOW || JD_A <= 8)
 #define JD_NORM_THRESHOLD (1e-30)     /* jitced_template.c:15 */
 
 #if defined(__CUDACC__)
@@ -95,7 +97,7 @@ JD_FN void store_anchor(double * const p, double const (&a)[JD_A])
 
 /* pair of anchors bracketing a time (what `anchors(t)` returns in the reference: anchor *);
  * element 0 of an anchor is its time, 1..n the state, n+1..2n the derivative */
-#if JD_WINDOW
+#if JD_SEG_BY_VALUE
 struct Seg
 {
 	double v[JD_A];
@@ -103,7 +105,19 @@ struct Seg
 };
 JD_FN double seg_tv(Seg const & s) { return s.v[0]; }
 JD_FN double seg_tw(Seg const & s) { return s.w[0]; }
+#else
+struct Seg
+{
+	const double * v;
+	const double * w;
+	double tv;
+	double tw;
+};
+JD_FN double seg_tv(Seg const & s) { return s.tv; }
+JD_FN double seg_tw(Seg const & s) { return s.tw; }
+#endif
 
+#if JD_WINDOW
 /* register-resident window of one lookup site: the anchor pair (cursor, cursor+1) plus the prefetched
  * neighbours cursor-1 and cursor+2, so that the cursor can move one anchor in either direction (forward:
  * time advances; backward: retry with a smaller step after a rejection) without waiting for memory */
@@ -117,24 +131,13 @@ struct Window
 	double w[JD_A];
 	double n[JD_A];
 };
-#else
-struct Seg
-{
-	const double * v;
-	const double * w;
-	double tv;
-	double tw;
-};
-JD_FN double seg_tv(Seg const & s) { return s.tv; }
-JD_FN double seg_tw(Seg const & s) { return s.tw; }
 #endif
 
 /* everything one trajectory needs while a kernel runs; lives in registers / local memory */
 struct Member
 {
 	double * ring;
-	int mask;
-	int cap;
+	int mask;                                   /* ring capacity - 1 */
 	int first, last, current;
 	int cursor[JD_NSITES > 0 ? JD_NSITES : 1];
 #if JD_WINDOW
@@ -144,16 +147,16 @@ struct Member
 
 	double cur_t, cur_y[JD_N], cur_d[JD_N];     /* last accepted anchor (`current`) */
 	double new_t, new_y[JD_N], new_d[JD_N];     /* tentative anchor (`last_anchor` while last != current) */
-	double old_y[JD_N];                         /* state of the replaced tentative anchor (`old_last`) */
-	bool has_old;
 	double err[JD_N];
 	double pws;                                 /* past_within_step */
 	double last_start;                          /* last_actual_step_start */
-	double tfn;                                 /* time of anchor first+1 (prefetched for forget) */
-	bool tfn_valid;
 
-	double dt, last_pws, credit;
-	int count;
+	double dt;
+	/* Past-within-step memory of the controller (last_pws, count, increase_credit; _jitcdde.py:727-741) is only
+	 * touched when a delay is shorter than a step. It stays in the per-member arrays in global memory and is
+	 * accessed by the cold paths directly; the hot loop only carries this flag (last_pws != False). */
+	bool pws_pending;
+	long long index;                            /* this member's index in the per-member arrays */
 
 	int accepted, rejected, attempts, extra_rhs;   /* since load_member; added to the 64-bit totals by store_member */
 	int status;
@@ -178,8 +181,8 @@ JD_FN void fill_window(Member & M, int const site);
 
 JD_FN void load_member(jdde_problem const & P, long long const m, Member & M)
 {
-	M.cap = P.cap;
 	M.mask = P.cap-1;
+	M.index = m;
 	M.ring = P.ring + (size_t)m*P.ring_stride;
 	M.first = P.first[m];
 	M.last = P.last[m];
@@ -204,14 +207,10 @@ JD_FN void load_member(jdde_problem const & P, long long const m, Member & M)
 	for (int s = 0; s < JD_NSITES; s++)
 		fill_window(M, s);              /* issued now, needed at the first lookup */
 #endif
-	M.tfn_valid = false;
-	M.has_old = false;
 	M.pws = 0.0;
 	M.last_start = P.last_start[m];
 	M.dt = P.dt[m];
-	M.last_pws = P.last_pws[m];
-	M.credit = P.credit[m];
-	M.count = P.count[m];
+	M.pws_pending = P.last_pws[m] != 0.0;
 	M.accepted = M.rejected = M.attempts = M.extra_rhs = 0;
 	M.status = P.status[m];
 }
@@ -226,9 +225,6 @@ JD_FN void store_member(jdde_problem const & P, long long const m, Member const 
 		P.cursor[(size_t)s*P.n_members+m] = M.cursor[s];
 	P.last_start[m] = M.last_start;
 	P.dt[m] = M.dt;
-	P.last_pws[m] = M.last_pws;
-	P.credit[m] = M.credit;
-	P.count[m] = M.count;
 	P.accepted[m] += M.accepted;
 	P.rejected[m] += M.rejected;
 	P.attempts[m] += M.attempts;
@@ -357,6 +353,52 @@ JD_FN Seg anchors(Member & M, int const site, double const t)
 	fill_window(M, site);
 	return s;
 }
+#elif JD_SEG_BY_VALUE
+/* Small anchors: the three anchors the cursor can reach without a second memory round trip (cursor,
+ * cursor+1, cursor+2) are requested at once, as 16-byte vector loads, before the comparisons of the walk are
+ * made on them. In the common cases — the cursor stays or moves on by one anchor — a lookup thus costs one
+ * memory latency instead of three to four dependent ones; everything else continues with the generic walk. */
+JD_FN Seg anchors(Member & M, int const site, double const t)
+{
+	Seg s;
+	int ca = M.cursor[site];
+	bool const third = ca+2 <= M.last;
+	double a2[JD_A];
+	load_anchor(M.slot(ca), s.v);
+	load_anchor(M.slot(ca+1), s.w);
+	load_anchor(M.slot(third ? ca+2 : ca+1), a2);
+	if (s.v[0] > t && ca > M.first)
+	{
+		/* backwards (retry after a rejected step, state-dependent delays): generic walk */
+		double const * pa; double const * pn; double ta, tn;
+		walk(M, site, t, pa, pn, ta, tn);
+		load_anchor(pa, s.v);
+		load_anchor(pn, s.w);
+		return s;
+	}
+	if (s.w[0] < t && third)
+	{
+		++ca;
+		JD_UNROLL
+		for (int k = 0; k < JD_A; k++)
+		{
+			s.v[k] = s.w[k];
+			s.w[k] = a2[k];
+		}
+		while (s.w[0] < t && ca+2 <= M.last)
+		{
+			++ca;
+			JD_UNROLL
+			for (int k = 0; k < JD_A; k++)
+				s.v[k] = s.w[k];
+			load_anchor(M.slot(ca+1), s.w);
+		}
+	}
+	if (t > M.cur_t)
+		M.pws = fmax(M.pws, t-M.cur_t);
+	M.cursor[site] = ca;
+	return s;
+}
 #else
 JD_FN Seg anchors(Member & M, int const site, double const t)
 {
@@ -393,7 +435,7 @@ JD_FN double past_dy(double const t, int const index, Seg const & s)
 JD_FN Seg segment_at(Member const & M, int const vi)
 {
 	Seg s;
-#if JD_WINDOW
+#if JD_SEG_BY_VALUE
 	load_anchor(M.slot(vi), s.v);
 	load_anchor(M.slot(vi+1), s.w);
 #else
@@ -457,16 +499,10 @@ JD_FN void get_next_step(Member & M, double const delta_t)
 	for (int i = 0; i < JD_N; i++)
 		M.err[i] = (5*M.cur_d[i]-6*k_2[i]-8*k_3[i]+9*nd[i]) * (delta_t/72.);
 
+	/* append_anchor (:56-73) after an accepted step, replace_last_anchor (:106-114) on a retry. The state of
+	 * the replaced anchor (`old_last`) is only needed by the past-within-step iteration: see try_single_step. */
 	if (M.last == M.current)
-		M.last++;                      /* append_anchor, :56-73 */
-	else
-	{
-		/* replace_last_anchor, :106-114: keep the replaced state for check_new_y_diff */
-		JD_UNROLL
-		for (int i = 0; i < JD_N; i++)
-			M.old_y[i] = M.new_y[i];
-		M.has_old = true;
-	}
+		M.last++;
 	M.new_t = nt;
 	double a[JD_A];
 	a[0] = nt;
@@ -503,16 +539,15 @@ JD_FN double get_p(Member const & M, double const atol, double const rtol)
 	return p;
 }
 
-/* check_new_y_diff, jitced_template.c:502-524 */
-JD_FN bool check_new_y_diff(Member const & M, double const atol, double const rtol)
+/* check_new_y_diff, jitced_template.c:502-524. `old_y` = state of the tentative anchor that the last
+ * get_next_step replaced (old_last; it always exists where the controller calls this, _jitcdde.py:851-855). */
+JD_FN bool check_new_y_diff(Member const & M, double const * const old_y, double const atol, double const rtol)
 {
-	if (!M.has_old)
-		return false;
 	bool result = true;
 	JD_UNROLL
 	for (int i = 0; i < JD_N; i++)
 	{
-		double const difference = fabs(M.new_y[i] - M.old_y[i]);
+		double const difference = fabs(M.new_y[i] - old_y[i]);
 		double const tolerance = atol + fabs(rtol*M.new_y[i]);
 		result &= (tolerance >= difference);
 	}
@@ -523,7 +558,6 @@ JD_FN bool check_new_y_diff(Member const & M, double const atol, double const rt
 JD_FN void accept_step(Member & M)
 {
 	M.current = M.last;
-	M.has_old = false;
 	M.cur_t = M.new_t;
 	JD_UNROLL
 	for (int i = 0; i < JD_N; i++)
@@ -533,24 +567,34 @@ JD_FN void accept_step(Member & M)
 	}
 }
 
-/* forget, jitced_template.c:534-561. The reference forgets once per integrate() call; the thresholds only
- * grow, so forgetting after every accepted step and once more at the end of the call leaves the same first
- * anchor. Done incrementally, each call inspects one anchor time that was requested a whole step earlier
- * (tfn), instead of a serial chain of ~20 cold loads at the end of the kernel. */
+/* forget, jitced_template.c:534-561: drop anchors while the next one is still older than the threshold.
+ * The anchor times are inspected eight at a time (independent loads in flight together) instead of one
+ * after the other; which anchor becomes the first one is unchanged. */
 JD_FN void forget(Member & M, double const delay)
 {
 	double const threshold = fmin(M.cur_t - delay, M.last_start);
-	if (!M.tfn_valid)
-	{
-		M.tfn = M.slot(M.first+1)[0];
-		M.tfn_valid = true;
-	}
 	bool moved = false;
-	while (M.first+1 < M.last && M.tfn < threshold)
+	for (;;)
 	{
-		M.first++;
-		M.tfn = M.slot(M.first+1)[0];
-		moved = true;
+		double tm[8];
+		JD_UNROLL
+		for (int j = 0; j < 8; j++)
+			tm[j] = M.slot(M.first+1+j)[0];      /* slots beyond `last` hold stale or unset times; they are masked below */
+		int advance = 0;
+		bool stop = false;
+		JD_UNROLL
+		for (int j = 0; j < 8; j++)
+		{
+			/* while (first+1 < last && time[first+1] < threshold) first++ */
+			if (!stop && M.first+1+j < M.last && tm[j] < threshold)
+				advance++;
+			else
+				stop = true;
+		}
+		M.first += advance;
+		moved |= advance > 0;
+		if (advance < 8)
+			break;
 	}
 	if (moved)
 	{
@@ -595,33 +639,31 @@ JD_FN void control_for_min_step(Member & M, jdde_int_params const & P)
 		M.status = JDDE_STATUS_MIN_STEP;
 }
 
-/* _jitcdde.py:767-773 */
-JD_FN double increase_chance(Member const & M, jdde_int_params const & P, double const new_dt)
+/* _increase_chance (_jitcdde.py:767-773) and the deterministic do_increase (:733-741); cold: only after a
+ * past-within-step event. Operates on the controller memory in the per-member arrays. */
+JD_FN bool pws_allows_increase(Member const & M, jdde_problem const & P, double const new_dt)
 {
-	double const q = new_dt/M.last_pws;
+	jdde_int_params const & I = P.P;
+	double const q = new_dt/P.last_pws[M.index];
 	double const is_explicit = sigmoid(1-q);
-	double const far_from_explicit = sigmoid(q-P.pws_factor);
-	double const few_iterations = sigmoid(1-M.count/P.pws_factor);
+	double const far_from_explicit = sigmoid(q-I.pws_factor);
+	double const few_iterations = sigmoid(1-P.count[M.index]/I.pws_factor);
 	double const profile = is_explicit+far_from_explicit*few_iterations;
-	return profile + P.pws_base_increase_chance*(1-profile);
-}
+	double const chance = profile + I.pws_base_increase_chance*(1-profile);
 
-/* _jitcdde.py:733-741 */
-JD_FN bool do_increase(Member & M, double const p)
-{
-	M.credit += p;
-	if (M.credit >= 0.9)
-	{
-		M.credit = 0.0;
-		return true;
-	}
-	return false;
+	double credit = P.credit[M.index] + chance;
+	bool const increase = credit >= 0.9;
+	if (increase)
+		credit = 0.0;
+	P.credit[M.index] = credit;
+	return increase;
 }
 
 /* _adjust_step_size, _jitcdde.py:775-794 with q = 3 (:726). The two fractional powers use the
  * libm-free roots of jdde_math.h so that CPU oracle and GPU take bit-identical step sizes. */
-JD_FN bool adjust_step_size(Member & M, jdde_int_params const & P)
+JD_FN bool adjust_step_size(Member & M, jdde_problem const & PR)
 {
+	jdde_int_params const & P = PR.P;
 	double const p = get_p(M, P.atol, P.rtol);
 	if (p > P.decrease_threshold)
 	{
@@ -633,11 +675,15 @@ JD_FN bool adjust_step_size(Member & M, jdde_int_params const & P)
 	{
 		double const factor = (p != 0.0) ? P.safety_factor*jdde_inv_root4(p) : P.max_factor;
 		double const new_dt = fmin(M.dt*fmin(factor, P.max_factor), P.max_step);
-		if (M.last_pws == 0.0 || do_increase(M, increase_chance(M, P, new_dt)))
+		if (!M.pws_pending || pws_allows_increase(M, PR, new_dt))
 		{
 			M.dt = new_dt;
-			M.count = 0;
-			M.last_pws = 0.0;
+			if (M.pws_pending)
+			{
+				PR.count[M.index] = 0;
+				PR.last_pws[M.index] = 0.0;
+				M.pws_pending = false;
+			}
 		}
 	}
 	return true;
@@ -646,18 +692,27 @@ JD_FN bool adjust_step_size(Member & M, jdde_int_params const & P)
 /* try_single_step, _jitcdde.py:838-861. Written as one loop so that the step code is instantiated once:
  * pass 0 is the attempt with `length`; if a delayed lookup reached into the step (past within step),
  * passes 1..pws_max_iterations repeat the step with self.dt (sic, :853) until two successive results agree. */
-JD_FN bool try_single_step(Member & M, jdde_int_params const & P, double const length)
+JD_FN bool try_single_step(Member & M, jdde_problem const & PR, double const length)
 {
+	jdde_int_params const & P = PR.P;
 	double step = length;
 	int count = 0;
 	for (;;)
 	{
+		double old_y[JD_N];
+		if (count)
+		{
+			JD_UNROLL
+			for (int i = 0; i < JD_N; i++)
+				old_y[i] = M.new_y[i];
+		}
 		get_next_step(M, step);
 		if (count == 0)
 		{
 			if (M.pws == 0.0)
 				break;
-			M.last_pws = M.pws;
+			PR.last_pws[M.index] = M.pws;
+			M.pws_pending = true;
 			/* if possible, shrink the step to make the integration explicit */
 			if (M.dt > P.pws_factor*M.pws)
 			{
@@ -666,7 +721,7 @@ JD_FN bool try_single_step(Member & M, jdde_int_params const & P, double const l
 				return false;
 			}
 		}
-		else if (check_new_y_diff(M, P.pws_atol, P.pws_rtol))
+		else if (check_new_y_diff(M, old_y, P.pws_atol, P.pws_rtol))
 			break;
 		if (count == P.pws_max_iterations)
 		{
@@ -675,20 +730,20 @@ JD_FN bool try_single_step(Member & M, jdde_int_params const & P, double const l
 			return false;
 		}
 		count++;
-		M.count = count;
+		PR.count[M.index] = count;
 		step = M.dt;
 	}
-	return adjust_step_size(M, P);
+	return adjust_step_size(M, PR);
 }
 
 /* Room for one more anchor? The reference's list is unbounded; the ring is not. forget() first
  * (it never removes an anchor a valid lookup can reach), then report overflow. */
 JD_FN bool ensure_room(Member & M, double const max_delay)
 {
-	if (M.last+2-M.first <= M.cap)
+	if (M.last+1-M.first <= M.mask)
 		return true;
 	forget(M, max_delay);
-	if (M.last+2-M.first <= M.cap)
+	if (M.last+1-M.first <= M.mask)
 		return true;
 	M.status = JDDE_STATUS_OVERFLOW;
 	return false;
@@ -715,11 +770,10 @@ JD_FN void step_until(Member & M, jdde_problem const & P, double const target, b
 			break;
 		}
 		double const length = capped ? fmin(M.dt, target-M.cur_t) : M.dt;
-		if (try_single_step(M, P.P, length))
+		if (try_single_step(M, P, length))
 		{
 			accept_step(M);
 			M.accepted++;
-			forget(M, P.max_delay);
 		}
 		else
 			M.rejected++;
@@ -731,7 +785,6 @@ JD_FN void step_until(Member & M, jdde_problem const & P, double const target, b
 /* remove_last_anchor, jitced_template.c:88-104 */
 JD_FN void remove_last_anchor(Member & M)
 {
-	M.has_old = false;
 	M.invalidate_windows();
 	M.last--;
 	JD_UNROLL
@@ -774,7 +827,6 @@ JD_FN void truncate_past(Member & M, double const time)
 		dst[1+JD_N+i] = nd[i];
 	}
 	M.current = M.last;
-	M.has_old = false;
 	reload_current(M);
 }
 
@@ -836,7 +888,6 @@ JD_FN void apply_jump(Member & M, jdde_problem const & P, double const * const c
 		dst[1+JD_N+i] = nd[i];
 	}
 	M.current = M.last;
-	M.has_old = false;
 	reload_current(M);
 
 	Seg const js = segment_at(M, M.last-1);

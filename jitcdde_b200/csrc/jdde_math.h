@@ -2,8 +2,8 @@
  * jdde_math.h — the handful of scalar routines that must give the same bits on
  * the CPU (gcc, C11 or C++) and on the GPU (nvcc, -fmad=false verification build).
  *
- * Only +, -, *, /, sqrt (all correctly rounded under IEEE-754) and exact
- * exponent manipulation are used, so the results do not depend on a libm.
+ * Only +, -, * (correctly rounded under IEEE-754) and exact exponent
+ * manipulation are used, so the results do not depend on a libm.
  *
  *  jdde_ipow(x,e)    x**e for integer e>=1 as a fixed square-and-multiply chain.
  *                    The reference prints `pow(x, e)` (SymEngine C printer) and
@@ -48,28 +48,43 @@ JDDE_HD double jdde_ipow(double x, unsigned e)
 	return result;
 }
 
+/* p**(-1/r) for r = 3, 4 by Newton's iteration on y**(-r) = m,  y <- y + y·(1 − m·y^r)/r,  written with
+ * multiplications only (1/3 as a rounded constant, 1/4 exact): relative error e -> ((r+1)/2)·e², so five
+ * steps take the cubic starting polynomial (error < 8 %) below one ulp. p = m·2^e is split exactly with
+ * frexp/ldexp such that e is a multiple of r. */
 JDDE_HD double jdde_inv_root4(double p)
 {
-	return 1.0/sqrt(sqrt(p));
+	int e;
+	double m = frexp(p, &e);
+	int r = e % 4;
+	if (r < 0)
+		r += 4;
+	int const k = (e - r)/4;
+	m = ldexp(m, r);                 /* m in [0.5,8) */
+	double y = 1.217525705905916 + m*(-0.25141147967130534 + m*(0.03938573046995773 + m*-0.002237737611829044));
+	for (int i = 0; i < 5; i++)
+	{
+		double const y2 = y*y;
+		double const y4 = y2*y2;
+		y = y + y*(1.0 - m*y4)*0.25;
+	}
+	return ldexp(y, -k);
 }
 
 JDDE_HD double jdde_inv_root3(double p)
 {
-	/* p = m·2^e with m in [0.5,1); fold e mod 3 into m so that m in [0.5,4) */
 	int e;
 	double m = frexp(p, &e);
 	int r = e % 3;
 	if (r < 0)
 		r += 3;
 	int const k = (e - r)/3;
-	m = ldexp(m, r);
-	/* quadratic start for m**(-1/3) on [0.5,4), relative error < 6 % */
-	double y = 1.4774 + m*(-0.4930 + m*0.0706);
-	/* Newton on y**(-3) = m:  y <- y + y·(1 − m·y³)/3, error e -> 2e² */
-	for (int i = 0; i < 6; i++)
+	m = ldexp(m, r);                 /* m in [0.5,4) */
+	double y = 1.4841220496057164 + m*(-0.6341672442901666 + m*(0.1816221035823464 + m*-0.01927416318870279));
+	for (int i = 0; i < 5; i++)
 	{
 		double const y3 = y*y*y;
-		y = y + y*(1.0 - m*y3)/3.0;
+		y = y + y*(1.0 - m*y3)*0x1.5555555555555p-2;
 	}
 	return ldexp(y, -k);
 }

@@ -158,7 +158,11 @@ def compare(result, g, exact, rtol=1e-10, suffix=""):
 	for key, value in result.items():
 		expected = g[key+suffix] if key+suffix in g else g[key]
 		value = np.asarray(value)
-		if exact or value.dtype.kind in "iu":
+		if key == "lyaps" and exact:
+			# log(norms)/Δt: the reference takes the logarithm with NumPy (_jitcdde.py:1168), whose vectorised log
+			# differs from libm's by an ulp now and then; the norms themselves are compared through the states
+			np.testing.assert_allclose(value, expected, rtol=4e-16, atol=1e-17, err_msg=key)
+		elif exact or value.dtype.kind in "iu":
 			assert np.array_equal(value, np.asarray(expected).reshape(value.shape)), f"{key}: not identical (max abs diff {np.max(np.abs(value-np.asarray(expected).reshape(value.shape)))})"
 		else:
 			np.testing.assert_allclose(value, np.asarray(expected).reshape(value.shape), rtol=rtol, atol=1e-300, err_msg=key)

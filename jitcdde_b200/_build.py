@@ -82,16 +82,17 @@ def use_window(program):
 def launch_shape(program):
 	"""
 	(block size, resident blocks per SM) the kernels are compiled for. The integrate kernel is bound by
-	latency (dependent FP64 chains and scattered anchor loads), so for small systems it is compiled for
-	64 registers per thread — 32 resident warps per SM — and lets ptxas spill the cold controller state;
-	measured optimum on B200 (profiles/variants_r01.md). Larger systems keep all registers.
+	latency (dependent FP64 chains and scattered anchor loads), not by issue slots or bandwidth, so resident
+	warps matter more than spill-free code: for small systems it is compiled for one-warp blocks, 20 per SM
+	(<= 96 registers per thread; a finished warp frees its slot at once), the measured optimum on B200
+	(profiles/variants_r01.md). Larger systems keep all registers.
 	"""
 	override = os.environ.get("JITCDDE_B200_LAUNCH")
 	if override:
 		block, blocks = override.split("x")
 		return int(block), int(blocks)
 	if program.n <= 2:
-		return 64, 16
+		return 32, 20
 	if program.n <= 8:
 		return 128, 4
 	return 128, 1
@@ -122,7 +123,9 @@ def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), fo
 	flags = ["-O3", "-std=c++17", "-lineinfo", *ARCH]
 	if mode == VERIFY:
 		flags.append("-fmad=false")
-	elif mode != FAST:
+	elif mode == FAST:
+		flags.append("-DJD_FAST=1")
+	else:
 		raise ValueError(mode)
 	cmd = [nvcc(), "-cubin", *flags,
 		f"-DJD_N={program.n}", f"-DJD_NBASIC={n_basic}", f"-DJD_NSITES={program.n_sites}",

@@ -18,13 +18,7 @@ from ._codegen import get_delays as _get_delays
 from ._capi import pinned_empty
 
 
-def shard(n_members, rank, world_size):
-	"""Contiguous block of members [start, stop) that process `rank` of `world_size` integrates.
-	Ensemble members are independent, so multi-GPU runs (one process per GPU) need no
-	communication until results are gathered."""
-	base, extra = divmod(n_members, world_size)
-	start = rank*base + min(rank, extra)
-	return start, start + base + (1 if rank < extra else 0)
+from ._dist import gather_members, shard
 
 
 def _out_of_scope(name):
@@ -40,5 +34,5 @@ input = _out_of_scope("input")  # noqa: A001
 
 __all__ = [
 	"UnsuccessfulIntegration", "anchors", "current_y", "dy", "jitcdde", "jitcdde_lyap",
-	"past_dy", "past_y", "quadrature", "t", "y", "shard", "pinned_empty",
+	"past_dy", "past_y", "quadrature", "t", "y", "shard", "gather_members", "pinned_empty",
 ]

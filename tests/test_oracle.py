@@ -198,6 +198,30 @@ def test_lyapunov_bitwise(name):
 		np.testing.assert_allclose(lyaps, g["lyaps"][k], rtol=4e-16, atol=1e-17)
 
 
+def test_lyapunov_step_count_is_perturbation_sensitive():
+	"""Why Lyapunov runs of the production build (FMA contraction) are compared statistically: perturbing one
+	tangent component of the initial past by 1e-15 changes the reference algorithm's own accepted-step count
+	by several percent (the sub-leading separation functions are nearly dependent at first, Gram–Schmidt
+	amplifies rounding, and the error norm over all components feeds this back into the step size)."""
+	g = scenarios.golden("mg_lyap")
+	system = systems.mackey_glass(control=False)
+	system["delay"] = 15.0
+	prog, n_basic = systems.lyap_program(system, 3)
+	counts = []
+	for eps in (0.0, 1e-15):
+		past = [(a[0], a[1].copy(), a[2].copy()) for a in scenarios.past_of(g)]
+		past[1][1][2] *= 1+eps
+		lib = oracle.build(prog, n_basic=n_basic)
+		T = oracle.Trajectory(lib, past, max_delay=15.0)
+		T.step_on_discontinuities([15.0])
+		t0 = T.t
+		for o in g["offsets"]:
+			T.integrate_lyap(t0+o)
+		counts.append(T.counters["accepted"])
+	assert counts[0] == int(g["accepted"])
+	assert 0.01 < abs(counts[1]-counts[0])/counts[0] < 0.15
+
+
 def test_orthonormality_invariants():
 	"""tests/test_past.py:9-26: after orthonormalise the separation functions have norm 1 and vanishing scalar products"""
 	g = scenarios.golden("roessler_lyap")

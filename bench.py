@@ -46,6 +46,7 @@ def config(members_per_gpu, world):
 		"workload": "mackey_glass_beta_tau_sweep (BASELINE.json configs[1])",
 		"members_per_gpu": members_per_gpu,
 		"members_total": members_per_gpu*world,
+		"sharding": "members dealt round-robin to the ranks, no data-path collective",
 		"step": f"integrate(): advance every member by {ADVANCE:g} time units",
 		"integration_parameters": "reference defaults (atol 1e-10, rtol 1e-5)",
 		"discontinuities": "step_on_discontinuities, target tau_j per member",
@@ -237,7 +238,7 @@ def gpu_arm(args):
 	import torch
 	import torch.distributed as dist
 
-	from jitcdde_b200 import jitcdde, pinned_empty, shard
+	from jitcdde_b200 import jitcdde, pinned_empty
 	from tests import systems
 
 	rank = int(os.environ.get("RANK", 0))
@@ -252,8 +253,10 @@ def gpu_arm(args):
 		dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
 	members = args.members
-	start, stop = shard(members*world, rank, world)
-	pars = systems.mg_grid(members*world)[start:stop]
+	# Weak scaling: every rank integrates `members` members. Members are dealt to the ranks round-robin
+	# (rank r takes r, r+world, … of the global grid), so every GPU sees the same mix of (β, τ) and hence of
+	# step sizes; contiguous blocks would give the ranks with larger β systematically more steps.
+	pars = systems.mg_grid(members*world)[rank::world]
 	system = systems.mackey_glass()
 
 	def fresh():

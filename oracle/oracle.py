@@ -245,34 +245,52 @@ class Trajectory:
 		self.lib.jo_raw_truncate(self._h, ctypes.c_double(time))
 
 
-def run_ensemble(lib, past, parameters, max_delay, disc_mode, disc_steps, sample_offsets, root_mode=1, per_member_past=False, keep_output=True, **integration_parameters):
+def run_ensemble(lib, past, parameters, max_delay, disc_mode, disc_steps, sample_offsets, root_mode=1, per_member_past=False, keep_output=True, lyap=False, n_members=None, **integration_parameters):
 	"""
-	Run N independent members through past → discontinuity handling → sampling loop
-	(jo_run_ensemble). `past` = (times[k], states[k][n], diffs[k][n]) shared by all members,
-	or with a leading member axis if `per_member_past`.
-	Returns dict(out[n_samples][N][n], counters[N][3], status[N], t[N]).
+	Run N independent members through past → discontinuity handling → sampling loop (jo_run_ensemble).
+	`past` = (times[k], states[k][n], diffs[k][n]) shared by all members, or with a leading member axis if
+	`per_member_past`. disc_mode: 0 none, 1 step_on_discontinuities(disc_steps[m]), 2 adjust_diff,
+	3 integrate_blindly(t + disc_steps[m][0], step = disc_steps[m][1]). With `lyap`, samples are taken with
+	integrate_lyap. Returns dict(out, counters[N][3], status[N], t[N] [, lyaps, weights]).
 	"""
-	n = lib.jo_n()
-	parameters = _arr(parameters)
-	N = parameters.shape[0] if parameters.ndim == 2 else int(np.shape(disc_steps)[0])
+	n, n_basic = lib.jo_n(), lib.jo_n_basic()
 	times, states, diffs = (_arr(x) for x in past)
+	parameters = _arr(parameters) if parameters is not None else np.zeros((0, 0))
+	if n_members is not None:
+		N = int(n_members)
+	elif parameters.ndim == 2 and parameters.shape[0]:
+		N = parameters.shape[0]
+	elif per_member_past:
+		N = times.shape[0]
+	else:
+		N = int(np.shape(disc_steps)[0])
 	k = times.shape[-1]
 	P = make_params(root_mode, **integration_parameters)
-	disc = _arr(disc_steps if disc_steps is not None else np.zeros((N, 0)))
-	n_disc = disc.shape[1] if disc.ndim == 2 else 0
+	disc = _arr(disc_steps if disc_steps is not None else np.zeros((N, 1)))
+	if disc.ndim == 1:
+		disc = np.ascontiguousarray(np.broadcast_to(disc, (N, disc.shape[0])))
+	n_disc = disc.shape[1]
 	offs = _arr(sample_offsets)
-	out = np.empty((len(offs), N, n)) if keep_output else None
+	n_out = n_basic if lyap else n
+	n_lyap = n//n_basic-1
+	out = np.empty((len(offs), N, n_out)) if keep_output else None
+	lyaps = np.zeros((len(offs), N, n_lyap)) if lyap else None
+	weights = np.zeros((len(offs), N)) if lyap else None
 	counters = np.zeros((N, 3), dtype=np.int64)
 	status = np.zeros(N, dtype=np.int32)
 	final_t = np.empty(N)
 	lib.jo_run_ensemble(
 		ctypes.c_long(N), ctypes.c_int(k), _p(times), _p(states), _p(diffs), ctypes.c_int(int(per_member_past)),
-		_p(parameters), ctypes.byref(P), ctypes.c_double(max_delay),
+		_p(parameters) if parameters.size else None, ctypes.byref(P), ctypes.c_double(max_delay),
 		ctypes.c_int(disc_mode), ctypes.c_int(n_disc), _p(disc),
 		ctypes.c_int(len(offs)), _p(offs),
 		_p(out) if keep_output else None,
+		_p(lyaps) if lyap else None, _p(weights) if lyap else None,
 		counters.ctypes.data_as(ctypes.POINTER(ctypes.c_long)),
 		status.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
 		_p(final_t),
 	)
-	return dict(out=out, counters=counters, status=status, t=final_t)
+	result = dict(out=out, counters=counters, status=status, t=final_t)
+	if lyap:
+		result.update(lyaps=lyaps, weights=weights)
+	return result

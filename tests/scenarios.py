@@ -166,3 +166,104 @@ def compare(result, g, exact, rtol=1e-10, suffix=""):
 			assert np.array_equal(value, np.asarray(expected).reshape(value.shape)), f"{key}: not identical (max abs diff {np.max(np.abs(value-np.asarray(expected).reshape(value.shape)))})"
 		else:
 			np.testing.assert_allclose(value, np.asarray(expected).reshape(value.shape), rtol=rtol, atol=1e-300, err_msg=key)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Ensemble versions of the other BASELINE.json configurations (C3, C5a, C5b), run through the
+# product API (`product_*`) and through the oracle's ensemble driver (`oracle_*`) on the same inputs.
+
+def c3_inputs(N, seed=5):
+	"""two Rösslers + 4 exponents, coupling k_m = 0.5·m/(N−1) (tests/test_lyaps.py:16-45)"""
+	from jitcdde_b200._past import Past
+	rng = np.random.default_rng(seed)
+	P = Past(n=30, n_basic=6, rng=np.random.default_rng(seed+1))
+	P.add((-4.5, rng.random(6), rng.random(6)))
+	P.add((0.0, rng.random(6), rng.random(6)))
+	k = (0.5*np.arange(N)/max(N-1, 1)).reshape(N, 1)
+	return [(a.time, a.state, a.diff) for a in P], k, np.arange(10, 60, 10.0)
+
+
+def product_c3(N, **kw):
+	past, k, offsets = c3_inputs(N)
+	system = systems.two_roessler(control=True)
+	DDE = jitcdde_lyap(system["f"], n_lyap=4, control_pars=system["control_pars"], n_members=N, verbose=False, **kw)
+	DDE.add_past_points(past)
+	DDE.set_integration_parameters(**systems.LYAP_TEST_PARAMETERS)
+	DDE.set_parameters(k)
+	DDE.step_on_discontinuities()
+	t0 = DDE.t
+	states, lyaps, weights = [], [], []
+	for o in offsets:
+		s, l, w = DDE.integrate(t0+o)
+		states.append(np.atleast_2d(s)); lyaps.append(np.atleast_2d(l)); weights.append(np.atleast_1d(w))
+	accepted, rejected, _ = DDE.counters()
+	return dict(out=np.array(states), lyaps=np.array(lyaps), weights=np.array(weights), accepted=accepted, rejected=rejected)
+
+
+def oracle_c3(N):
+	from oracle import oracle
+	past, k, offsets = c3_inputs(N)
+	system = systems.two_roessler(control=True)
+	prog, n_basic = systems.lyap_program(system, 4)
+	lib = oracle.build(prog, n_basic=n_basic)
+	arrays = (np.array([a[0] for a in past]), np.array([a[1] for a in past]), np.array([a[2] for a in past]))
+	r = oracle.run_ensemble(lib, arrays, k, 4.5, 1, np.array([4.5]), offsets, lyap=True, **systems.LYAP_TEST_PARAMETERS)
+	return dict(out=r["out"], lyaps=r["lyaps"], weights=r["weights"], accepted=r["counters"][:, 0], rejected=r["counters"][:, 1])
+
+
+def c5a_inputs(N):
+	"""examples/state_dependent.py:14-29 with initial states shifted by 1e-3·m/N"""
+	shift = 1e-3*np.arange(N)/N
+	times = np.broadcast_to(np.array([-2.0, -1.1, -0.9, 0.0]), (N, 4)).copy()
+	states = (np.array([4.5, 4.5, -0.5, -0.5])[None, :]+shift[:, None]).reshape(N, 4, 1)
+	return times, states, np.zeros((N, 4, 1)), np.linspace(0.9, 2, 12)
+
+
+def product_c5a(N, **kw):
+	times, states, diffs, sample_times = c5a_inputs(N)
+	system = systems.state_dependent()
+	DDE = jitcdde(system["f"], max_delay=1e10, n_members=N, verbose=False, **kw)
+	for j in range(4):
+		DDE.add_past_point(times[:, j] if N > 1 else times[0, j], states[:, j] if N > 1 else states[0, j], diffs[:, j] if N > 1 else diffs[0, j])
+	DDE.integrate_blindly(0.01)
+	out = np.array([np.atleast_2d(DDE.integrate(T)) for T in sample_times])
+	accepted, rejected, _ = DDE.counters()
+	return dict(out=out, accepted=accepted, rejected=rejected)
+
+
+def oracle_c5a(N):
+	from oracle import oracle
+	times, states, diffs, sample_times = c5a_inputs(N)
+	lib = oracle.build(systems.program(systems.state_dependent()))
+	# integrate_blindly(0.01) from t = 0 with the default step (max_step = 10 → one step of 0.01), then absolute sample times
+	r = oracle.run_ensemble(lib, (times, states, diffs), None, 1e10, 3, np.array([0.01, 0.0]), sample_times-0.01, per_member_past=True, n_members=N)
+	return dict(out=r["out"], accepted=r["counters"][:, 0], rejected=r["counters"][:, 1])
+
+
+def c5b_inputs(N):
+	system = systems.neutral()
+	shift = 1e-3*np.arange(N)/N
+	return np.array(system["initial"])[None, :]+shift[:, None], np.linspace(1, 5, 5)
+
+
+def product_c5b(N, **kw):
+	initial, sample_times = c5b_inputs(N)
+	system = systems.neutral()
+	DDE = jitcdde(system["f"], helpers=system["helpers"], n_members=N, verbose=False, **kw)
+	DDE.set_integration_parameters(rtol=1e-5)
+	DDE.constant_past(initial if N > 1 else initial[0])
+	DDE.adjust_diff()
+	out = np.array([np.atleast_2d(DDE.integrate(T)) for T in sample_times])
+	accepted, rejected, _ = DDE.counters()
+	return dict(out=out, accepted=accepted, rejected=rejected)
+
+
+def oracle_c5b(N):
+	from oracle import oracle
+	initial, sample_times = c5b_inputs(N)
+	system = systems.neutral()
+	lib = oracle.build(systems.program(system))
+	times = np.broadcast_to(np.array([-1.0, 0.0]), (N, 2)).copy()
+	states = np.stack([initial, initial], axis=1)
+	r = oracle.run_ensemble(lib, (times, states, np.zeros_like(states)), None, system["delay"], 2, None, sample_times-0.0, per_member_past=True, n_members=N, rtol=1e-5)
+	return dict(out=r["out"], accepted=r["counters"][:, 0], rejected=r["counters"][:, 1], t=r["t"])

@@ -34,3 +34,15 @@ def test_reference_golden_vector(twin):
 	g = scenarios.golden("roessler")
 	result = scenarios.roessler(g)
 	np.testing.assert_allclose(result["samples"][-1], g["y10_reference"], rtol=1e-3, atol=1e-6)
+
+
+def test_ensembles_of_other_configurations(twin):
+	"""C3 (Lyapunov ensemble over the coupling), C5a (state-dependent delay, per-member pasts), C5b (neutral):
+	product API on the host twin against the oracle's ensemble driver, bit for bit (same libm on the host)."""
+	for product, reference, N in ((scenarios.product_c3, scenarios.oracle_c3, 6), (scenarios.product_c5a, scenarios.oracle_c5a, 9), (scenarios.product_c5b, scenarios.oracle_c5b, 5)):
+		ours, theirs = product(N), reference(N)
+		for key in ours:
+			if key == "lyaps":
+				np.testing.assert_allclose(ours[key], theirs[key], rtol=4e-16, atol=1e-17)
+			else:
+				assert np.array_equal(ours[key], theirs[key]), (product.__name__, key, np.max(np.abs(ours[key]-theirs[key])))

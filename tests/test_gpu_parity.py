@@ -200,3 +200,34 @@ def test_watchdog_budget():
 	out, status = E.resume()
 	assert not status.any()
 	E.close()
+
+
+def test_lyapunov_ensemble_c3():
+	"""BASELINE.json configs[2] shape at test size: two Rösslers + 4 exponents over a grid of couplings;
+	verification build against the oracle (bit for bit; exponents to an ulp of CUDA's log)."""
+	N = 256
+	ours, theirs = scenarios.product_c3(N, verification=True), scenarios.oracle_c3(N)
+	for key in ("out", "weights", "accepted", "rejected"):
+		assert np.array_equal(ours[key], theirs[key]), key
+	np.testing.assert_allclose(ours["lyaps"], theirs["lyaps"], rtol=1e-13, atol=1e-15)
+
+
+def test_state_dependent_ensemble_c5a():
+	"""BASELINE.json configs[4], state-dependent delay with per-member pasts (divergent lookups, backward
+	moves of the cursor, max_delay = 1e10 so nothing is ever forgotten and rings grow)."""
+	N = 4096
+	ours, theirs = scenarios.product_c5a(N, verification=True), scenarios.oracle_c5a(N)
+	for key in ours:
+		assert np.array_equal(ours[key], theirs[key]), key
+	fast = scenarios.product_c5a(N, verification=False)
+	assert np.array_equal(fast["accepted"], theirs["accepted"])
+	np.testing.assert_allclose(fast["out"], theirs["out"], rtol=1e-9)
+
+
+def test_neutral_ensemble_c5b():
+	"""BASELINE.json configs[4], neutral DDE (past_dy): libm functions in the right-hand side and ulp
+	sensitivity of the system itself → the reference's own tolerance (tests/test_neutral.py: rtol 1e-4)."""
+	N = 1024
+	ours, theirs = scenarios.product_c5b(N), scenarios.oracle_c5b(N)
+	np.testing.assert_allclose(ours["out"], theirs["out"], rtol=1e-4)
+	assert np.all(np.abs(ours["accepted"]-theirs["accepted"]) <= 0.05*theirs["accepted"]+2)

@@ -229,5 +229,6 @@ def test_neutral_ensemble_c5b():
 	sensitivity of the system itself → the reference's own tolerance (tests/test_neutral.py: rtol 1e-4)."""
 	N = 1024
 	ours, theirs = scenarios.product_c5b(N), scenarios.oracle_c5b(N)
-	np.testing.assert_allclose(ours["out"], theirs["out"], rtol=1e-4)
+	# components oscillate through zero: tolerance relative to the amplitude (~1) as well
+	np.testing.assert_allclose(ours["out"], theirs["out"], rtol=1e-4, atol=1e-4)
 	assert np.all(np.abs(ours["accepted"]-theirs["accepted"]) <= 0.05*theirs["accepted"]+2)

@@ -66,33 +66,44 @@ def _engine_hash():
 	return h.hexdigest()[:12]
 
 
+def _anchor_doubles(program):
+	return ((1+2*program.n)+3) & ~3
+
+
 def use_window(program):
 	"""
-	Keep the anchors around each lookup cursor in registers (JD_WINDOW in csrc/jdde_engine.cuh)?
-	Measured on B200 for the Mackey–Glass ensemble (profiles/variants_r01.md): the window removes most
-	global loads, but its registers cost more resident warps than the loads cost latency — L1 serves the
-	sequential ring reads well. Off by default; JITCDDE_B200_WINDOW=1 turns it on (tests exercise both).
+	How lookups reach the anchors around their cursor (JD_WINDOW in csrc/jdde_engine.cuh):
+	  0  speculative vector loads through L1/L2 at every lookup,
+	  1  a register-resident window (measured slower: its registers cost resident warps),
+	  2  a per-thread window in shared memory filled by cp.async one move ahead (fastest where it fits:
+	     1.29e10 → 1.77e10 steps/s for the Mackey–Glass ensemble, profiles/variants_r01.md).
+	Mode 2 needs 4 anchors × lookup sites × 8·A bytes of shared memory per thread; it is chosen when that is
+	at most 128 bytes (n = 1 with one distinct delay), so that 32 warps per SM stay resident.
+	JITCDDE_B200_WINDOW overrides (tests exercise all modes).
 	"""
 	override = os.environ.get("JITCDDE_B200_WINDOW")
 	if override is not None:
-		return bool(int(override)) and program.n_sites > 0
-	return False
+		return int(override) if program.n_sites > 0 else 0
+	if program.n_sites > 0 and program.n_sites*4*_anchor_doubles(program)*8 <= 128:
+		return 2
+	return 0
 
 
 def launch_shape(program):
 	"""
 	(block size, resident blocks per SM) the kernels are compiled for. The integrate kernel is bound by
 	latency (dependent FP64 chains and scattered anchor loads), not by issue slots or bandwidth, so resident
-	warps matter more than spill-free code: for small systems it is compiled for one-warp blocks, 20 per SM
-	(<= 96 registers per thread; a finished warp frees its slot at once), the measured optimum on B200
-	(profiles/variants_r01.md). Larger systems keep all registers.
+	warps matter more than spill-free code: small systems are compiled for one-warp blocks (a finished warp
+	frees its slot at once) — 32 per SM (64 registers per thread) with the shared-memory window, 20 per SM
+	(<= 96 registers) without — the measured optima on B200 (profiles/variants_r01.md). Larger systems keep
+	all registers.
 	"""
 	override = os.environ.get("JITCDDE_B200_LAUNCH")
 	if override:
 		block, blocks = override.split("x")
 		return int(block), int(blocks)
 	if program.n <= 2:
-		return 32, 20
+		return (32, 32) if use_window(program) == 2 else (32, 20)
 	if program.n <= 8:
 		return 128, 4
 	return 128, 1

@@ -87,9 +87,8 @@ def load_library(path=None):
 	global _lib
 	if _lib is not None and path is None:
 		return _lib
-	path = path or _build.RUNTIME_LIB
-	if not os.path.exists(path):
-		_build.build_runtime()
+	if path is None:
+		path = _build.build_runtime()      # no-op unless the sources are newer than the library
 	lib = ctypes.CDLL(path)
 	for name, (restype, argtypes) in SIGNATURES.items():
 		fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol

@@ -58,7 +58,7 @@ typedef struct jdde_problem
 /* `jdde_image_desc` global in every kernel image */
 typedef struct jdde_image_desc_t
 {
-	int magic, abi, n, n_basic, n_sites, n_params, anchor_stride, block;
+	int magic, abi, n, n_basic, n_sites, n_params, anchor_stride, block, smem_bytes;
 } jdde_image_desc_t;
 
 #if defined(__CUDACC__)

@@ -117,7 +117,24 @@ JD_FN double seg_tv(Seg const & s) { return s.tv; }
 JD_FN double seg_tw(Seg const & s) { return s.tw; }
 #endif
 
-#if JD_WINDOW
+#if JD_WINDOW == 2
+/* Shared-memory window (device only): per thread and lookup site a private 4-anchor circular buffer in shared
+ * memory holds the anchors cursor-1 … cursor+2 (slot = index & 3). Anchors are brought in with cp.async
+ * (global → shared without passing through registers) one move ahead of their use, so a lookup that stays in
+ * its segment or moves by one anchor in either direction reads shared memory only and never waits for L2 or
+ * HBM; registers hold just three flags per site. Only accepted anchors (index <= current) are staged: they are
+ * immutable while the kernel runs. This is the staging of `north_star`, without the register cost of JD_WINDOW=1. */
+struct Window
+{
+	bool valid;
+	bool prev_ok;
+	bool next_ok;
+};
+#ifndef JD_BLOCK
+#define JD_BLOCK 128
+#endif
+#define JD_WIN_SMEM_BYTES ((JD_NSITES > 0 ? JD_NSITES : 1)*4*JD_A*8*JD_BLOCK)
+#elif JD_WINDOW
 /* register-resident window of one lookup site: the anchor pair (cursor, cursor+1) plus the prefetched
  * neighbours cursor-1 and cursor+2, so that the cursor can move one anchor in either direction (forward:
  * time advances; backward: retry with a smaller step after a rejection) without waiting for memory */
@@ -265,7 +282,133 @@ JD_FN int walk(Member & M, int const site, double const t, double const * & pa, 
 	return ca;
 }
 
-#if JD_WINDOW
+#if JD_WINDOW == 2
+#if defined(__CUDA_ARCH__)
+extern __shared__ d2 jd_win_smem[];
+
+/* row r of this thread's column: rows are 16-byte elements, JD_BLOCK per row → conflict-free LDS.128 */
+__device__ __forceinline__ d2 * win_row(int const site, int const index, int const half)
+{
+	return jd_win_smem + (size_t)((site*4 + (index & 3))*(JD_A/2) + half)*JD_BLOCK + threadIdx.x;
+}
+
+__device__ __forceinline__ void win_fetch(int const site, int const index, double const * const anchor)
+{
+	JD_UNROLL
+	for (int h = 0; h < JD_A/2; h++)
+	{
+		unsigned const dst = (unsigned)__cvta_generic_to_shared(win_row(site, index, h));
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(anchor+2*h) : "memory");
+	}
+}
+
+__device__ __forceinline__ void win_wait()
+{
+	asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+__device__ __forceinline__ double win_time(int const site, int const index)
+{
+	return win_row(site, index, 0)->x;
+}
+
+__device__ __forceinline__ void win_read(int const site, int const index, double (&a)[JD_A])
+{
+	JD_UNROLL
+	for (int h = 0; h < JD_A/2; h++)
+	{
+		d2 const v = *win_row(site, index, h);
+		a[2*h] = v.x;
+		a[2*h+1] = v.y;
+	}
+}
+#else
+/* host pass of nvcc: never executed */
+inline void win_fetch(int, int, double const *) {}
+inline void win_wait() {}
+inline double win_time(int, int) { return 0.0; }
+inline void win_read(int, int, double (&)[JD_A]) {}
+#endif
+
+JD_FN void fill_window(Member & M, int const site)
+{
+	Window & W = M.win[site];
+	int const ca = M.cursor[site];
+	W.valid = ca+1 <= M.current;
+	if (!W.valid)
+		return;
+	win_fetch(site, ca, M.slot(ca));
+	win_fetch(site, ca+1, M.slot(ca+1));
+	W.next_ok = ca+2 <= M.current;
+	if (W.next_ok)
+		win_fetch(site, ca+2, M.slot(ca+2));
+	W.prev_ok = ca-1 >= M.first;
+	if (W.prev_ok)
+		win_fetch(site, ca-1, M.slot(ca-1));
+}
+
+JD_FN Seg anchors(Member & M, int const site, double const t)
+{
+	Window & W = M.win[site];
+	Seg s;
+	if (W.valid)
+	{
+		win_wait();
+		int ca = M.cursor[site];
+		double tv = win_time(site, ca);
+		double tw = win_time(site, ca+1);
+		bool hit = true;
+		/* while (ca->time > t && ca->previous) ca = ca->previous; */
+		while (tv > t && ca > M.first)
+		{
+			if (!W.prev_ok)
+			{
+				hit = false;
+				break;
+			}
+			--ca;
+			W.next_ok = true;
+			W.prev_ok = ca-1 >= M.first;
+			win_wait();
+			tw = tv;
+			tv = win_time(site, ca);
+			if (W.prev_ok)
+				win_fetch(site, ca-1, M.slot(ca-1));      /* overwrites the slot of the old cursor+2 */
+		}
+		/* while (ca->next->time < t && ca->next->next) ca = ca->next; */
+		while (hit && tw < t)
+		{
+			if (!W.next_ok)
+			{
+				hit = false;      /* next anchor is tentative or missing: let walk() decide */
+				break;
+			}
+			++ca;
+			W.prev_ok = true;
+			W.next_ok = ca+2 <= M.current;
+			win_wait();
+			tv = tw;
+			tw = win_time(site, ca+1);
+			if (W.next_ok)
+				win_fetch(site, ca+2, M.slot(ca+2));      /* overwrites the slot of the old cursor-1 */
+		}
+		M.cursor[site] = ca;
+		if (hit)
+		{
+			/* t <= time of an accepted anchor <= current.time: no past-within-step contribution */
+			win_read(site, ca, s.v);
+			win_read(site, ca+1, s.w);
+			return s;
+		}
+	}
+	double const * pa; double const * pn; double ta, tn;
+	walk(M, site, t, pa, pn, ta, tn);
+	load_anchor(pa, s.v);
+	load_anchor(pn, s.w);
+	fill_window(M, site);
+	return s;
+}
+#elif JD_WINDOW
 /* (re)load the window of a site around its cursor; only accepted anchors (index <= current) are cached */
 JD_FN void fill_window(Member & M, int const site)
 {

@@ -13,17 +13,19 @@
  * Block size JD_BLOCK (default 128): blocks are the scheduling granule that evens out the
  * different amounts of work of different members, 148 SMs × several resident blocks each.
  */
-#include "jdde_engine.cuh"
-
 #ifndef JD_BLOCK
 #define JD_BLOCK 128
+#endif
+#include "jdde_engine.cuh"
+#ifndef JD_WIN_SMEM_BYTES
+#define JD_WIN_SMEM_BYTES 0
 #endif
 #ifndef JD_MIN_BLOCKS
 #define JD_MIN_BLOCKS 1
 #endif
 
 extern "C" __device__ const jdde_image_desc_t jdde_image_desc = {
-	JDDE_IMAGE_MAGIC, JDDE_ABI_VERSION, JD_N, JD_NBASIC, JD_NSITES, JD_NPARAMS, JD_A, JD_BLOCK
+	JDDE_IMAGE_MAGIC, JDDE_ABI_VERSION, JD_N, JD_NBASIC, JD_NSITES, JD_NPARAMS, JD_A, JD_BLOCK, JD_WIN_SMEM_BYTES
 };
 
 #define JD_MEMBER_INDEX() ((long long)blockIdx.x*blockDim.x+threadIdx.x)

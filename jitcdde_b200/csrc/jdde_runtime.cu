@@ -42,6 +42,7 @@ struct jdde_handle
 	cudaLibrary_t lib = nullptr;
 	Kernels k;
 	int block = 128;
+	int smem_bytes = 0;      /* dynamic shared memory per block (anchor staging window of the image) */
 	jdde_problem P{};
 	bool have_past = false, have_params = false, have_int_params = false;
 	long long budget = 1ll << 24;
@@ -121,7 +122,7 @@ int launch(jdde_handle * h, cudaKernel_t kernel, void ** args)
 		return fail(h, JDDE_E_INVALID, "kernel image not loaded (jdde_load_rhs) or kernel missing from the image");
 	long long const N = h->desc.n_members;
 	unsigned const grid = (unsigned)((N + h->block - 1)/h->block);
-	JD_CUDA(h, cudaLaunchKernel((const void *)kernel, dim3(grid), dim3(h->block), args, 0, h->stream));
+	JD_CUDA(h, cudaLaunchKernel((const void *)kernel, dim3(grid), dim3(h->block), args, (size_t)h->smem_bytes, h->stream));
 	h->launches++;
 	return JDDE_OK;
 }
@@ -287,6 +288,7 @@ int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
 		return fail(h, JDDE_E_IMAGE, buf);
 	}
 	h->block = d.block;
+	h->smem_bytes = d.smem_bytes;
 
 	struct { const char * name; cudaKernel_t * slot; bool required; } const table[] = {
 		{"jdde_k_set_past", &h->k.set_past, true},

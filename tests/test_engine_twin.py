@@ -21,8 +21,9 @@ def test_bitwise_against_reference_core(twin, name):
 @pytest.mark.parametrize("window", ["0", "1"])
 @pytest.mark.parametrize("name", ["mg_ensemble", "state_dependent", "kuramoto", "roessler", "roessler_jump", "neutral", "mg_lyap"])
 def test_register_window_does_not_change_results(twin, monkeypatch, name, window):
-	"""The register-resident anchor window (JD_WINDOW) is an access-path optimisation: forced on or off,
-	also for systems where the build policy would not choose it, results stay bit-identical."""
+	"""The register-resident anchor window (JD_WINDOW=1) is an access-path optimisation: forced on or off,
+	also for systems where the build policy would not choose it, results stay bit-identical. (The
+	shared-memory window, JD_WINDOW=2, is device-only and is covered by the GPU tests.)"""
 	monkeypatch.setenv("JITCDDE_B200_WINDOW", window)
 	g = scenarios.golden(scenarios.FIXTURE.get(name, name))
 	result = scenarios.ALL[name](g)

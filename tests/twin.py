@@ -20,7 +20,7 @@ _OUT = os.path.join(_HERE, "host_twin", "_build")
 
 def build_twin(program, n_basic=None):
 	n_basic = n_basic or program.n
-	window = int(_build.use_window(program))
+	window = int(_build.use_window(program)) % 2      # mode 2 (cp.async into shared memory) exists on the device only
 	os.makedirs(_OUT, exist_ok=True)
 	rhs = os.path.join(_OUT, f"rhs_{program.key}.inc")
 	with open(rhs, "w") as f:

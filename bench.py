@@ -327,8 +327,9 @@ def gpu_arm(args):
 	value = total_accepted/(ms*1e-3)
 
 	# ---------------- end to end through the public API with host buffers: `e2e`
-	# per step: the target time goes host→device, the kernel runs, states (N×8 B) and per-member status
-	# (N×4 B) come back device→host into pinned memory; all inside the timed region
+	# per step: the target time goes host→device, the kernel runs, the states (N×8 B) come back device→host
+	# into pinned memory together with the number of failed members (8 B; the status array follows only if
+	# it is non-zero); all inside the timed region
 	out = pinned_empty((members, 1))
 	for _ in range(2):
 		k += 1
@@ -355,7 +356,7 @@ def gpu_arm(args):
 		"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
 		"ms_per_step": ms/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
 		"dtype": "f64", "data": "synthetic", "config": config(members, world),
-		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(members*8+members*4),
+		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(members*8+8),
 			"ms_per_step": e2e_ms/args.steps},
 		"gpu_launches": int(launches),
 		"clocks": clocks.summary(),

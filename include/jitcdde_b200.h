@@ -168,6 +168,8 @@ int jdde_get_t(jdde_handle * h, double * t);                              /* get
 int jdde_get_dt(jdde_handle * h, double * dt);                            /* attribute jitcdde.dt */
 int jdde_get_current_state(jdde_handle * h, double * state);              /* get_current_state, :330-334; [n_members][n] */
 int jdde_get_status(jdde_handle * h, int32_t * status);
+/* Number of members whose status is not JDDE_STATUS_OK, counted on the device (8 bytes back instead of the array). */
+int jdde_count_failed(jdde_handle * h, int64_t * count);
 /* accepted steps, rejected attempts, right-hand-side evaluations per member (the reference has no counters) */
 int jdde_get_counters(jdde_handle * h, int64_t * accepted, int64_t * rejected, int64_t * rhs_evals);
 /* Sum over members, computed on the device (for the throughput metric). */

@@ -67,6 +67,7 @@ SIGNATURES = {
 	"jdde_get_dt": (ctypes.c_int, [_H, c_double_p]),
 	"jdde_get_current_state": (ctypes.c_int, [_H, c_double_p]),
 	"jdde_get_status": (ctypes.c_int, [_H, c_int32_p]),
+	"jdde_count_failed": (ctypes.c_int, [_H, c_int64_p]),
 	"jdde_get_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
 	"jdde_sum_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
 	"jdde_get_state": (ctypes.c_int, [_H, ctypes.c_int64, ctypes.c_int32, c_int32_p, c_double_p, c_double_p, c_double_p]),
@@ -209,14 +210,18 @@ class Engine:
 			raise ValueError(f"target times must be a scalar or have shape ({self.N},)")
 		return target, 1
 
-	def integrate(self, target, out=None, status=None, fetch=True):
+	def integrate(self, target, out=None, status=None, fetch=True, fetch_status=True):
+		"""fetch=False: leave everything on the device, do not synchronise. fetch_status=False: copy the
+		states back but not the per-member status (use count_failed / get_status afterwards)."""
 		target, pm = self._targets(target)
 		if fetch and out is None:
 			out = np.empty((self.N, self.n))
-		if fetch and status is None:
+		if fetch and fetch_status and status is None:
 			status = self._pinned_status()
+		if not (fetch and fetch_status):
+			status = None
 		self._check(self.lib.jdde_integrate(self._h, _dp(target), pm, _dp(out) if fetch else None,
-			status.ctypes.data_as(c_int32_p) if fetch else None))
+			status.ctypes.data_as(c_int32_p) if status is not None else None))
 		return out, status
 
 	def _pinned_status(self):
@@ -317,6 +322,11 @@ class Engine:
 		status = np.empty(self.N, dtype=np.int32)
 		self._check(self.lib.jdde_get_status(self._h, status.ctypes.data_as(c_int32_p)))
 		return status
+
+	def count_failed(self):
+		n = ctypes.c_int64()
+		self._check(self.lib.jdde_count_failed(self._h, ctypes.byref(n)))
+		return n.value
 
 	def get_counters(self):
 		a, r, f = (np.empty(self.N, dtype=np.int64) for _ in range(3))

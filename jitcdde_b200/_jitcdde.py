@@ -460,7 +460,9 @@ class jitcdde:
 			warn("The target time is smaller than the current time. No integration step will happen. The returned state will be extrapolated from the interpolating Hermite polynomial for the last integration step. You may see this because you try to integrate backwards in time, in which case you did something wrong. You may see this just because your sampling step is small, in which case there is no need to worry (though you should think about increasing your sampling time).", stacklevel=2)
 		if not self.initial_discontinuities_handled:
 			warn("You did not explicitly handle initial discontinuities. Proceed only if you know what you are doing. This is only fine if you somehow chose your initial past such that the derivative of the last anchor complies with the DDE. In this case, you can set the attribute `initial_discontinuities_handled` to `True` to suppress this warning. See https://jitcdde.rtfd.io/#discontinuities for details.", stacklevel=2)
-		result, status = self._engine.integrate(target_time, out=out)
+		# the per-member status stays on the device unless a member failed (8 bytes back instead of 4·N)
+		result, status = self._engine.integrate(target_time, out=out, fetch_status=False)
+		status = self._engine.get_status() if self._engine.count_failed() else None
 		while self._check_status(status, retry=True):
 			result, status = self._engine.resume()
 			if out is not None:

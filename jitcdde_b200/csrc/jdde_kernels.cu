@@ -107,6 +107,17 @@ jdde_k_clear_status(jdde_problem const P, int const code)
 		P.status[m] = JDDE_STATUS_OK;
 }
 
+/* number of members whose status is not OK (so that callers need not copy the whole status array back) */
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_count_failed(jdde_problem const P, unsigned long long * const out)
+{
+	long long const m = JD_MEMBER_INDEX();
+	bool const failed = m < P.n_members && P.status[m] != JDDE_STATUS_OK;
+	unsigned const ballot = __ballot_sync(0xffffffffu, failed);
+	if ((threadIdx.x & 31) == 0 && ballot)
+		atomicAdd(out, (unsigned long long)__popc(ballot));
+}
+
 /* sums of accepted / rejected / right-hand-side evaluations over the ensemble: warp shuffle
  * reduction, one atomic per warp */
 extern "C" __global__ void __launch_bounds__(JD_BLOCK)

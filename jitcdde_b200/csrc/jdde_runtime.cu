@@ -28,7 +28,7 @@ thread_local std::string g_create_error;
 struct Kernels
 {
 	cudaKernel_t set_past = nullptr, reset_controller = nullptr, integrate = nullptr, integrate_blindly = nullptr,
-		jump = nullptr, forget = nullptr, get = nullptr, clear_status = nullptr, sum_counters = nullptr,
+		jump = nullptr, forget = nullptr, get = nullptr, clear_status = nullptr, sum_counters = nullptr, count_failed = nullptr,
 		regrow = nullptr, orthonormalise = nullptr;
 };
 
@@ -300,6 +300,7 @@ int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
 		{"jdde_k_get", &h->k.get, true},
 		{"jdde_k_clear_status", &h->k.clear_status, true},
 		{"jdde_k_sum_counters", &h->k.sum_counters, true},
+		{"jdde_k_count_failed", &h->k.count_failed, true},
 		{"jdde_k_regrow", &h->k.regrow, true},
 		{"jdde_k_orthonormalise", &h->k.orthonormalise, false},
 	};
@@ -626,6 +627,21 @@ int jdde_get_status(jdde_handle * h, int32_t * status)
 	if (rc) return rc;
 	if (!status) return fail(h, JDDE_E_INVALID, "null argument");
 	return finish(h, nullptr, nullptr, 0, status);
+}
+
+int jdde_count_failed(jdde_handle * h, int64_t * count)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!count) return fail(h, JDDE_E_INVALID, "null argument");
+	JD_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long), h->stream));
+	void * args[] = { &h->P, &h->d_sums };
+	if ((rc = launch(h, h->k.count_failed, args))) return rc;
+	unsigned long long n = 0;
+	JD_CUDA(h, cudaMemcpyAsync(&n, h->d_sums, sizeof n, cudaMemcpyDeviceToHost, h->stream));
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	*count = (int64_t)n;
+	return JDDE_OK;
 }
 
 int jdde_get_counters(jdde_handle * h, int64_t * accepted, int64_t * rejected, int64_t * rhs_evals)

@@ -279,6 +279,14 @@ int jdde_get_current_state(jdde_handle * h, double * s)
 }
 int jdde_get_status(jdde_handle * h, int32_t * status) { give(h, nullptr, h->out, 0, status); return JDDE_OK; }
 
+int jdde_count_failed(jdde_handle * h, int64_t * count)
+{
+	int64_t n = 0;
+	for (auto s : h->status) n += s != JDDE_STATUS_OK;
+	*count = n;
+	return JDDE_OK;
+}
+
 int jdde_get_counters(jdde_handle * h, int64_t * a, int64_t * r, int64_t * f)
 {
 	for (long long m = 0; m < h->P.n_members; m++)

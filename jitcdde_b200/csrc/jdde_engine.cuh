@@ -127,6 +127,7 @@ JD_FN double seg_tw(Seg const & s) { return s.tw; }
 struct Window
 {
 	bool valid;
+	bool fresh;        /* the copies of (cursor, cursor+1) have been requested but not yet awaited */
 	bool prev_ok;
 	bool next_ok;
 };
@@ -339,6 +340,7 @@ JD_FN void fill_window(Member & M, int const site)
 		return;
 	win_fetch(site, ca, M.slot(ca));
 	win_fetch(site, ca+1, M.slot(ca+1));
+	W.fresh = true;
 	W.next_ok = ca+2 <= M.current;
 	if (W.next_ok)
 		win_fetch(site, ca+2, M.slot(ca+2));
@@ -347,13 +349,20 @@ JD_FN void fill_window(Member & M, int const site)
 		win_fetch(site, ca-1, M.slot(ca-1));
 }
 
+/* Invariant: the copies of the slots of cursor and cursor+1 have landed (unless W.fresh); those of cursor-1 and
+ * cursor+2 may still be in flight — they are awaited only when the cursor moves onto them, so a prefetch has
+ * the time until the next move (about one integration step) to arrive. */
 JD_FN Seg anchors(Member & M, int const site, double const t)
 {
 	Window & W = M.win[site];
 	Seg s;
 	if (W.valid)
 	{
-		win_wait();
+		if (W.fresh)
+		{
+			win_wait();
+			W.fresh = false;
+		}
 		int ca = M.cursor[site];
 		double tv = win_time(site, ca);
 		double tw = win_time(site, ca+1);

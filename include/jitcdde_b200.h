@@ -199,6 +199,54 @@ int64_t jdde_launch_count(const jdde_handle * h);
 /* Device pointer of the last integration result [n_members][n] as an integer address (for zero-copy interop). */
 uint64_t jdde_device_result(const jdde_handle * h);
 
+/* ==== one large delay-coupled network, partitioned by node ============================================
+ *
+ *   dy_i/dt = local(y_i, t, node_par_i) + Σ_{edges e into i} weight_e · coupling(y_{src_e}(t − tau_e), y_i)
+ *
+ * The structured counterpart of the reference's per-node symbolic expressions
+ * (/root/reference/examples/kuramoto_network.py:50-62), which cannot be code-generated for 10^4…10^6 nodes.
+ * Same method and controller as above (jitced_template.c:421-498, _jitcdde.py:775-836, 880-933), one scalar state
+ * per node, every delay at least as long as a step. With several GPUs each rank owns the nodes [lo, hi), holds the
+ * whole history, and after every attempt the ranks all-gather the staged anchor slices and max-reduce the error
+ * norm (the caller does this between jdde_net_attempt and jdde_net_control, e.g. with NCCL on the buffers
+ * reported by jdde_net_exchange_pointers). */
+typedef struct jdde_net jdde_net;
+
+typedef struct jdde_net_desc
+{
+	int64_t n;               /* nodes of the whole system */
+	int64_t lo, hi;          /* nodes [lo, hi) are integrated by this handle */
+	int64_t n_edges;         /* edges into the owned nodes */
+	int32_t n_node_params;   /* per-node parameters of `local` */
+	int32_t ring_capacity;   /* anchors kept, power of two */
+	int32_t device;
+	int32_t reserved;
+} jdde_net_desc;
+
+int jdde_net_create(const jdde_net_desc * desc, jdde_net ** out);
+int jdde_net_destroy(jdde_net * h);
+const char * jdde_net_last_error(const jdde_net * h);
+int jdde_net_load_image(jdde_net * h, const void * image, size_t len);
+int jdde_net_set_stream(jdde_net * h, void * cuda_stream);
+/* CSR by destination over the owned nodes: row_ptr[hi-lo+1], src/tau/weight[n_edges]; tau > 0. */
+int jdde_net_set_graph(jdde_net * h, const int64_t * row_ptr, const int32_t * src, const double * tau, const double * weight);
+int jdde_net_set_node_parameters(jdde_net * h, const double * par);          /* [n_node_params][n] */
+int jdde_net_set_past(jdde_net * h, int32_t n_anchors, const double * times, const double * states, const double * diffs);   /* states/diffs [n_anchors][n] */
+int jdde_net_set_integration_parameters(jdde_net * h, const jdde_int_params * p, double max_delay);
+/* pieces of one attempted step, for callers that exchange anchors between ranks in between */
+int jdde_net_begin(jdde_net * h, int32_t mode, double target, double step, int64_t steps);   /* mode 0 adaptive, 1 blind */
+int jdde_net_attempt(jdde_net * h);
+int jdde_net_control(jdde_net * h);
+int jdde_net_poll(jdde_net * h, int32_t * done, double * t, int32_t * status);
+int jdde_net_exchange_pointers(jdde_net * h, uint64_t * stage_state, uint64_t * stage_diff, uint64_t * p_bits);
+/* whole calls on a single rank: integrate (_jitcdde.py:807-836), integrate_blindly (:880-933), state [n] */
+int jdde_net_integrate(jdde_net * h, double target, double * out_state, int32_t * status);
+int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double * out_state, int32_t * status);
+int jdde_net_recent_state(jdde_net * h, double t, int32_t current_only, double * out_state);
+int jdde_net_get_counters(jdde_net * h, int64_t * accepted, int64_t * rejected, int64_t * attempts);
+int jdde_net_get_dt(jdde_net * h, double * dt);
+int64_t jdde_net_launch_count(const jdde_net * h);
+
 #ifdef __cplusplus
 }
 #endif

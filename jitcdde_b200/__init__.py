@@ -19,6 +19,7 @@ from ._capi import pinned_empty
 
 
 from ._dist import gather_members, shard
+from ._network import jitcdde_network
 
 
 def _out_of_scope(name):
@@ -34,5 +35,5 @@ input = _out_of_scope("input")  # noqa: A001
 
 __all__ = [
 	"UnsuccessfulIntegration", "anchors", "current_y", "dy", "jitcdde", "jitcdde_lyap",
-	"past_dy", "past_y", "quadrature", "t", "y", "shard", "gather_members", "pinned_empty",
+	"past_dy", "past_y", "quadrature", "t", "y", "jitcdde_network", "shard", "gather_members", "pinned_empty",
 ]

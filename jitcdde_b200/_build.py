@@ -46,10 +46,11 @@ def _newer(target, sources):
 
 def build_runtime(force=False, verbose=False):
 	"""nvcc -shared … csrc/jdde_runtime.cu → jitcdde_b200/libjitcdde_b200.so"""
-	sources = [os.path.join(CSRC, "jdde_runtime.cu"), os.path.join(CSRC, "jdde_abi.h"), os.path.join(INCLUDE, "jitcdde_b200.h")]
+	sources = [os.path.join(CSRC, "jdde_runtime.cu"), os.path.join(CSRC, "jdn_runtime.cu"), os.path.join(CSRC, "jdde_abi.h"),
+		os.path.join(CSRC, "jdn_abi.h"), os.path.join(INCLUDE, "jitcdde_b200.h")]
 	if force or _newer(RUNTIME_LIB, sources):
 		cmd = [nvcc(), "-shared", "-Xcompiler", "-fPIC", "-O2", "-std=c++17", *ARCH, "-lineinfo",
-			sources[0], "-o", RUNTIME_LIB]
+			sources[0], sources[1], "-o", RUNTIME_LIB]
 		if verbose:
 			print(" ".join(cmd))
 		subprocess.run(cmd, check=True)
@@ -144,6 +145,31 @@ def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), fo
 		f"-DJD_WINDOW={int(use_window(program))}",
 		*extra_flags,
 		os.path.join(CSRC, "jdde_kernels.cu"), "-o", path + ".tmp"]
+	if verbose:
+		print(" ".join(cmd))
+	result = subprocess.run(cmd, capture_output=True, text=True)
+	if result.returncode:
+		raise RuntimeError(f"nvcc failed:\n{result.stderr}\ncommand: {' '.join(cmd)}")
+	os.replace(path + ".tmp", path)
+	return path
+
+
+def build_net_image(program, block=256, force=False, verbose=False):
+	"""Kernel image of the network engine for one (local, coupling) pair (`program` = _codegen.NetProgram)."""
+	os.makedirs(CACHE, exist_ok=True)
+	h = hashlib.sha256()
+	for name in ("jdn_engine.cuh", "jdn_kernels.cu", "jdn_abi.h", "jdde_abi.h", "jdde_math.h"):
+		with open(os.path.join(CSRC, name), "rb") as f:
+			h.update(f.read())
+	tag = hashlib.sha256(repr((program.key, block, h.hexdigest())).encode()).hexdigest()[:20]
+	path = os.path.join(CACHE, f"jdn_{tag}.cubin")
+	if os.path.exists(path) and not force:
+		return path
+	rhs = os.path.join(CACHE, f"net_{program.key}.inc")
+	with open(rhs, "w") as f:
+		f.write(program.body)
+	cmd = [nvcc(), "-cubin", "-O3", "-std=c++17", "-lineinfo", *ARCH, f'-DJDN_RHS_FILE="{rhs}"', f"-DJDN_BLOCK={block}",
+		os.path.join(CSRC, "jdn_kernels.cu"), "-o", path + ".tmp"]
 	if verbose:
 		print(" ".join(cmd))
 	result = subprocess.run(cmd, capture_output=True, text=True)

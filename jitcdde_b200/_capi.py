@@ -80,6 +80,37 @@ SIGNATURES = {
 	"jdde_device_result": (ctypes.c_uint64, [_H]),
 }
 
+class NetDesc(ctypes.Structure):
+	_fields_ = [
+		("n", ctypes.c_int64), ("lo", ctypes.c_int64), ("hi", ctypes.c_int64), ("n_edges", ctypes.c_int64),
+		("n_node_params", ctypes.c_int32), ("ring_capacity", ctypes.c_int32), ("device", ctypes.c_int32), ("reserved", ctypes.c_int32),
+	]
+
+
+c_uint64_p = ctypes.POINTER(ctypes.c_uint64)
+SIGNATURES.update({
+	"jdde_net_create": (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(_H)]),
+	"jdde_net_destroy": (ctypes.c_int, [_H]),
+	"jdde_net_last_error": (ctypes.c_char_p, [_H]),
+	"jdde_net_load_image": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_size_t]),
+	"jdde_net_set_stream": (ctypes.c_int, [_H, ctypes.c_void_p]),
+	"jdde_net_set_graph": (ctypes.c_int, [_H, c_int64_p, c_int32_p, c_double_p, c_double_p]),
+	"jdde_net_set_node_parameters": (ctypes.c_int, [_H, c_double_p]),
+	"jdde_net_set_past": (ctypes.c_int, [_H, ctypes.c_int32, c_double_p, c_double_p, c_double_p]),
+	"jdde_net_set_integration_parameters": (ctypes.c_int, [_H, ctypes.POINTER(IntParams), ctypes.c_double]),
+	"jdde_net_begin": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_int64]),
+	"jdde_net_attempt": (ctypes.c_int, [_H]),
+	"jdde_net_control": (ctypes.c_int, [_H]),
+	"jdde_net_poll": (ctypes.c_int, [_H, c_int32_p, c_double_p, c_int32_p]),
+	"jdde_net_exchange_pointers": (ctypes.c_int, [_H, c_uint64_p, c_uint64_p, c_uint64_p]),
+	"jdde_net_integrate": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_int32_p]),
+	"jdde_net_integrate_blindly": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_double, c_double_p, c_int32_p]),
+	"jdde_net_recent_state": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int32, c_double_p]),
+	"jdde_net_get_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
+	"jdde_net_get_dt": (ctypes.c_int, [_H, c_double_p]),
+	"jdde_net_launch_count": (ctypes.c_int64, [_H]),
+})
+
 _lib = None
 
 
@@ -363,3 +394,108 @@ class Engine:
 	@property
 	def device_result(self):
 		return self.lib.jdde_device_result(self._h)
+
+
+class NetEngine:
+	"""One node-partitioned network (or this rank's part of it) on one GPU: owns a jdde_net handle."""
+
+	def __init__(self, n, lo, hi, n_edges, n_node_params, ring_capacity=128, device=0):
+		self.lib = load_library()
+		self.n, self.lo, self.hi = int(n), int(lo), int(hi)
+		desc = NetDesc(n=n, lo=lo, hi=hi, n_edges=n_edges, n_node_params=n_node_params, ring_capacity=ring_capacity, device=device)
+		self._h = _H()
+		rc = self.lib.jdde_net_create(ctypes.byref(desc), ctypes.byref(self._h))
+		if rc:
+			message = self.lib.jdde_net_last_error(None).decode()
+			self._h = None
+			raise EngineError(f"jdde_net_create failed ({rc}): {message}")
+
+	def close(self):
+		if getattr(self, "_h", None):
+			self.lib.jdde_net_destroy(self._h)
+			self._h = None
+
+	__del__ = close
+
+	def _check(self, rc):
+		if rc:
+			raise EngineError(f"error {rc}: {self.lib.jdde_net_last_error(self._h).decode()}")
+
+	def load_image(self, path):
+		with open(path, "rb") as f:
+			image = f.read()
+		self._image = image
+		self._check(self.lib.jdde_net_load_image(self._h, image, len(image)))
+
+	def set_stream(self, stream_ptr):
+		self._check(self.lib.jdde_net_set_stream(self._h, ctypes.c_void_p(stream_ptr)))
+
+	def set_graph(self, row_ptr, src, tau, weight):
+		row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+		src = np.ascontiguousarray(src, dtype=np.int32)
+		tau, weight = _f64(tau), _f64(weight)
+		self._check(self.lib.jdde_net_set_graph(self._h, row_ptr.ctypes.data_as(c_int64_p), src.ctypes.data_as(c_int32_p), _dp(tau), _dp(weight)))
+
+	def set_node_parameters(self, par):
+		par = _f64(par)
+		self._check(self.lib.jdde_net_set_node_parameters(self._h, _dp(par)))
+
+	def set_past(self, times, states, diffs):
+		times, states, diffs = _f64(times), _f64(states), _f64(diffs)
+		if states.shape != (len(times), self.n) or diffs.shape != states.shape:
+			raise ValueError("past has wrong shape")
+		self._check(self.lib.jdde_net_set_past(self._h, len(times), _dp(times), _dp(states), _dp(diffs)))
+
+	def set_integration_parameters(self, max_delay, **kwargs):
+		p = IntParams(**kwargs)
+		self._check(self.lib.jdde_net_set_integration_parameters(self._h, ctypes.byref(p), float(max_delay)))
+
+	def begin(self, mode, target, step=0.0, steps=0):
+		self._check(self.lib.jdde_net_begin(self._h, int(mode), float(target), float(step), int(steps)))
+
+	def attempt(self):
+		self._check(self.lib.jdde_net_attempt(self._h))
+
+	def control(self):
+		self._check(self.lib.jdde_net_control(self._h))
+
+	def poll(self):
+		done, status, t = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_double()
+		self._check(self.lib.jdde_net_poll(self._h, ctypes.byref(done), ctypes.byref(t), ctypes.byref(status)))
+		return bool(done.value), t.value, status.value
+
+	def exchange_pointers(self):
+		a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+		self._check(self.lib.jdde_net_exchange_pointers(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+		return a.value, b.value, c.value
+
+	def integrate(self, target):
+		out = np.empty(self.n)
+		status = ctypes.c_int32()
+		self._check(self.lib.jdde_net_integrate(self._h, float(target), _dp(out), ctypes.byref(status)))
+		return out, status.value
+
+	def integrate_blindly(self, target, step):
+		out = np.empty(self.n)
+		status = ctypes.c_int32()
+		self._check(self.lib.jdde_net_integrate_blindly(self._h, float(target), float(step or 0.0), _dp(out), ctypes.byref(status)))
+		return out, status.value
+
+	def recent_state(self, t, current_only=False):
+		out = np.empty(self.n)
+		self._check(self.lib.jdde_net_recent_state(self._h, float(t), int(current_only), _dp(out)))
+		return out
+
+	def counters(self):
+		a, r, k = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+		self._check(self.lib.jdde_net_get_counters(self._h, ctypes.byref(a), ctypes.byref(r), ctypes.byref(k)))
+		return a.value, r.value, k.value
+
+	def get_dt(self):
+		dt = ctypes.c_double()
+		self._check(self.lib.jdde_net_get_dt(self._h, ctypes.byref(dt)))
+		return dt.value
+
+	@property
+	def launch_count(self):
+		return self.lib.jdde_net_launch_count(self._h)

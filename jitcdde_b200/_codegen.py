@@ -335,3 +335,42 @@ def tangent_vector_f(f_basic, helpers, n, n_lyap, delays, simplify=True):
 				expression = sympy.simplify(expression, ratio=1.0)
 			out.append(expression)
 	return out
+
+
+# ---------------------------------------------------------------------------
+# Network engine: local and coupling function of a delay-coupled network
+# ---------------------------------------------------------------------------
+
+@dataclass
+class NetProgram:
+	"""Generated macros JDN_NPARAMS / JDN_LOCAL / JDN_COUPLING for csrc/jdn_engine.cuh."""
+	n_node_params: int
+	body: str
+
+	@property
+	def key(self):
+		return hashlib.sha256(self.body.encode()).hexdigest()[:16]
+
+
+def generate_network(local, coupling, n_node_params=0):
+	"""
+	local(y, t, *node_parameters) and coupling(y_delayed, y) return SymPy expressions of their (symbolic)
+	arguments:  dy_i/dt = local(y_i, t, p_i…) + Σ_e weight_e · coupling(y_src(t − tau_e), y_i).
+	"""
+	y_sym, yd_sym, t_sym = sympy.Symbol("jdn_y"), sympy.Symbol("jdn_yd"), sympy.Symbol("jdn_t")
+	pars = [sympy.Symbol(f"jdn_p{k}") for k in range(n_node_params)]
+	local_expr = sympy.sympify(local(y_sym, t_sym, *pars))
+	coupling_expr = sympy.sympify(coupling(yd_sym, y_sym))
+	for name, expr, allowed in (("local", local_expr, {y_sym, t_sym, *pars}), ("coupling", coupling_expr, {yd_sym, y_sym})):
+		bad = expr.free_symbols - allowed
+		if bad:
+			raise ValueError(f"Invalid symbol ({sorted(s.name for s in bad)}) in the {name} function.")
+	printer = _MacroPrinter({}, set())
+	names = {y_sym: "(y)", yd_sym: "(yd)", t_sym: "(t)", **{p: f"(par[{k}])" for k, p in enumerate(pars)}}
+	printer._print_Symbol = lambda expr: names.get(expr, expr.name)
+	body = (
+		f"#define JDN_NPARAMS {n_node_params}\n"
+		f"#define JDN_LOCAL(y, t, par) ({printer.doprint(local_expr)})\n"
+		f"#define JDN_COUPLING(yd, y) ({printer.doprint(coupling_expr)})\n"
+	)
+	return NetProgram(n_node_params=n_node_params, body=body)

@@ -1,0 +1,273 @@
+/*
+ * jdn_engine.cuh — network engine: one large delay-coupled system, node-parallel.
+ *
+ * Same numerical method as jdde_engine.cuh (Bogacki–Shampine stages with FSAL, cubic-Hermite history, the
+ * reference's step-size controller; /root/reference/jitcdde/jitced_template.c:193-251, 421-498 and
+ * /root/reference/jitcdde/_jitcdde.py:775-836, 880-933), organised for ONE trajectory with 10^4–10^6 components:
+ *
+ *   - every delay is at least as long as a step (enforced: max_step <= smallest delay; a lookup into the step
+ *     under way sets a flag and stops the integration), so the three stages of a node depend on the other nodes
+ *     only through the HISTORY. All three stages, the new anchor and the error estimate of a node are therefore
+ *     computed by one thread in ONE kernel (net_attempt_node) without any inter-node synchronisation;
+ *   - per in-edge the delayed state is interpolated at the three stage times in one pass (the three lookups
+ *     fall on the same two history rows: one set of gathers instead of three); the values for stages 2 and 3
+ *     wait in a per-edge scratch;
+ *   - the error norm is a max-reduction over nodes (block reduction + one atomic per block, then — with several
+ *     GPUs — one all-reduce); accept/reject, the step-size controller, forget and the termination test run in a
+ *     one-thread kernel (net_control) on the device, so that the host only polls a flag every few attempts;
+ *   - each edge keeps its own search cursor, exactly like a call site of `anchors()` in the reference.
+ *
+ * Functions are __host__ __device__ (tests compile them with g++ as the host twin).
+ */
+#ifndef JDN_ENGINE_CUH
+#define JDN_ENGINE_CUH
+
+#include <math.h>
+#include "jdde_math.h"
+#include "jdn_abi.h"
+
+#ifndef JDN_RHS_FILE
+#error "JDN_RHS_FILE (generated JDN_LOCAL / JDN_COUPLING macros) must be defined"
+#endif
+#include JDN_RHS_FILE
+
+#if defined(__CUDACC__)
+#  define JDN_FN __host__ __device__ __forceinline__
+#else
+#  define JDN_FN inline
+#endif
+
+#define JDDE_IPOW(x, e) jdde_ipow(x, e)
+
+namespace jdn {
+
+struct View
+{
+	double const * times;
+	int mask;
+	int first, current;
+	double t_cur;
+};
+
+JDN_FN double anchor_time(View const & V, int const index) { return V.times[index & V.mask]; }
+
+/* get_past_anchors (jitced_template.c:193-217) for one edge; the tentative anchor is never reachable here */
+JDN_FN int walk(View const & V, int ca, double const t)
+{
+	while (anchor_time(V, ca) > t && ca > V.first)
+		--ca;
+	while (anchor_time(V, ca+1) < t && ca+2 <= V.current)
+		++ca;
+	return ca;
+}
+
+/* get_past_value (jitced_template.c:221-235) of node j on the segment starting at anchor ca */
+JDN_FN double past_value(jdn_problem const & P, View const & V, int const ca, long long const j, double const t)
+{
+	double const tv = anchor_time(V, ca);
+	double const q = anchor_time(V, ca+1)-tv;
+	double const x = (t - tv)/q;
+	size_t const rv = (size_t)(ca & V.mask)*P.n + j;
+	size_t const rw = (size_t)((ca+1) & V.mask)*P.n + j;
+	double const a = P.state[rv];
+	double const b = P.diff[rv] * q;
+	double const c = P.state[rw];
+	double const d = P.diff[rw] * q;
+	return (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
+}
+
+/*
+ * One attempted step (get_next_step, jitced_template.c:421-472) of node i: returns this node's contribution
+ * |err|/(atol+rtol|y_new|) to the error norm (get_p, :474-498; negative if the contribution is to be skipped),
+ * writes the node's part of the tentative anchor. `scratch` holds two doubles per edge.
+ */
+JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h, long long const i, double * const scratch, int & pws)
+{
+	long long const row = i-P.lo;
+	long long const e0 = P.row_ptr[row], e1 = P.row_ptr[row+1];
+	size_t const rc = (size_t)(V.current & V.mask)*P.n + i;
+	double const y = P.state[rc];
+	double const k_1 = P.diff[rc];
+	double par[JDN_NPARAMS > 0 ? JDN_NPARAMS : 1];
+	for (int k = 0; k < JDN_NPARAMS; k++)
+		par[k] = P.node_par[(size_t)k*P.n+i];
+
+	double const t1 = V.t_cur+0.5*h, t2 = V.t_cur+0.75*h, t3 = V.t_cur+h;
+
+	/* stage 2: k_2 = f(t + h/2, y + h/2 k_1); the delayed inputs of stages 3 and 4 are interpolated alongside */
+	double const y1 = y + 0.5*h*k_1;
+	double acc = JDN_LOCAL(y1, t1, par);
+	for (long long e = e0; e < e1; e++)
+	{
+		long long const j = P.src[e];
+		double const tau = P.tau[e];
+		double const d1 = t1-tau, d2 = t2-tau, d3 = t3-tau;
+		if (d3 > V.t_cur)
+			pws = 1;
+		int ca = walk(V, P.cursor[e], d1);
+		double const H1 = past_value(P, V, ca, j, d1);
+		ca = walk(V, ca, d2);
+		scratch[2*e] = past_value(P, V, ca, j, d2);
+		ca = walk(V, ca, d3);
+		scratch[2*e+1] = past_value(P, V, ca, j, d3);
+		P.cursor[e] = ca;
+		acc += P.weight[e]*JDN_COUPLING(H1, y1);
+	}
+	double const k_2 = acc;
+
+	double const y2 = y + 0.75*h*k_2;
+	acc = JDN_LOCAL(y2, t2, par);
+	for (long long e = e0; e < e1; e++)
+		acc += P.weight[e]*JDN_COUPLING(scratch[2*e], y2);
+	double const k_3 = acc;
+
+	double const y_new = y + (h/9.) * (2*k_1+3*k_2+4*k_3);
+	acc = JDN_LOCAL(y_new, t3, par);
+	for (long long e = e0; e < e1; e++)
+		acc += P.weight[e]*JDN_COUPLING(scratch[2*e+1], y_new);
+	double const k_4 = acc;
+
+	double const error = fabs((5*k_1-6*k_2-8*k_3+9*k_4) * (h/72.));
+	P.stage_state[i] = y_new;
+	P.stage_diff[i] = k_4;
+
+	double const tolerance = P.ctrl->P.atol + P.ctrl->P.rtol*fabs(y_new);
+	if (error != 0.0 || tolerance != 0.0)
+		return error/tolerance;
+	return -1.0;
+}
+
+JDN_FN View view_of(jdn_problem const & P)
+{
+	jdn_control const & C = *P.ctrl;
+	View V;
+	V.times = P.times;
+	V.mask = P.cap-1;
+	V.first = C.first;
+	V.current = C.current;
+	V.t_cur = C.t;
+	return V;
+}
+
+/* forget, jitced_template.c:534-561 */
+JDN_FN void forget(jdn_problem const & P, jdn_control & C)
+{
+	int const mask = P.cap-1;
+	double const threshold = fmin(C.t - C.max_delay, C.last_start);
+	while (C.first+1 < C.current && P.times[(C.first+1) & mask] < threshold)
+		C.first++;
+}
+
+/* what follows an attempt on the Python side of the reference: _adjust_step_size (_jitcdde.py:775-794), accept_step,
+ * the loop test of integrate (:830) or the step count of integrate_blindly (:928-931), forget, and the preparation
+ * of the next attempt. Run by ONE thread. */
+JDN_FN void control(jdn_problem const & P)
+{
+	jdn_control & C = *P.ctrl;
+	C.commit_slot = -1;
+	if (C.done)
+		return;
+	jdde_int_params const & I = C.P;
+	int const mask = P.cap-1;
+	union { unsigned long long u; double d; } bits;
+	bits.u = C.p_bits;
+	double const p = bits.d;
+	C.attempts++;
+
+	if (C.pws)
+	{
+		/* a delay shorter than the step: the single-kernel stage evaluation does not cover this */
+		C.status = JDDE_STATUS_NONFINITE;
+		C.done = 1;
+		return;
+	}
+
+	bool accept = true;
+	if (C.mode == JDN_MODE_ADAPTIVE)
+	{
+		if (p > I.decrease_threshold)
+		{
+			C.dt *= fmax(I.safety_factor*jdde_inv_root3(p), I.min_factor);
+			accept = false;
+			C.rejected++;
+			if (C.dt < I.min_step)
+			{
+				C.status = JDDE_STATUS_MIN_STEP;
+				C.done = 1;
+				return;
+			}
+		}
+		else if (p <= I.increase_threshold)
+		{
+			double const factor = (p != 0.0) ? I.safety_factor*jdde_inv_root4(p) : I.max_factor;
+			C.dt = fmin(C.dt*fmin(factor, I.max_factor), I.max_step);
+		}
+	}
+
+	if (accept)
+	{
+		/* the staged anchor becomes anchor current+1, the end of the step (t, t+h) */
+		C.last_start = C.t;
+		C.t = C.t + C.h;
+		C.current++;
+		P.times[C.current & mask] = C.t;
+		C.commit_slot = C.current & mask;
+		C.accepted++;
+		if (C.mode == JDN_MODE_BLIND)
+		{
+			forget(P, C);
+			if (--C.remaining <= 0)
+				C.done = 1;
+		}
+		else if (!(C.t < C.target))
+		{
+			forget(P, C);
+			C.done = 1;
+		}
+	}
+	else
+		C.last_start = C.t;
+
+	if (C.done)
+		return;
+	if (!(C.dt > 0.0))
+	{
+		C.status = JDDE_STATUS_NONFINITE;
+		C.done = 1;
+		return;
+	}
+	if (C.current+2-C.first > P.cap)
+	{
+		forget(P, C);
+		if (C.current+2-C.first > P.cap)
+		{
+			C.status = JDDE_STATUS_OVERFLOW;
+			C.done = 1;
+			return;
+		}
+	}
+	if (C.mode == JDN_MODE_ADAPTIVE)
+		C.h = C.dt;
+	C.p_bits = 0;
+}
+
+/* get_recent_state, jitced_template.c:287-320: Hermite interpolation on the last segment */
+JDN_FN double recent_state(jdn_problem const & P, double const t, long long const i)
+{
+	jdn_control const & C = *P.ctrl;
+	int const mask = P.cap-1;
+	size_t const rv = (size_t)((C.current-1) & mask)*P.n + i;
+	size_t const rw = (size_t)(C.current & mask)*P.n + i;
+	double const tv = P.times[(C.current-1) & mask];
+	double const q = P.times[C.current & mask]-tv;
+	double const x = (t - tv)/q;
+	double const a = P.state[rv];
+	double const b = P.diff[rv] * q;
+	double const c = P.state[rw];
+	double const d = P.diff[rw] * q;
+	return (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
+}
+
+} // namespace jdn
+
+#endif

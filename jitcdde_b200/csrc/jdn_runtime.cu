@@ -1,0 +1,387 @@
+/*
+ * jdn_runtime.cu — host side of the network engine (jdde_net_* in include/jitcdde_b200.h); part of
+ * libjitcdde_b200.so. Owns the device memory of one system (layout: jdn_abi.h), loads the kernel image and
+ * launches  attempt → [anchor exchange between ranks, done by the caller] → control → commit  per attempted
+ * step; the controller runs on the device, the host polls a flag every few attempts. No numerical code here.
+ */
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "jdn_abi.h"
+
+struct jdde_net
+{
+	jdde_net_desc desc{};
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	cudaLibrary_t lib = nullptr;
+	cudaKernel_t k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr;
+	int block = 256;
+	jdn_problem P{};
+	double * scratch = nullptr, * d_out = nullptr, * d_par = nullptr;
+	long long * d_row_ptr = nullptr; int * d_src = nullptr; double * d_tau = nullptr, * d_weight = nullptr;
+	jdn_control host_ctrl{};
+	bool have_graph = false, have_past = false, have_int = false;
+	int64_t launches = 0;
+	int poll_every = 8;
+	std::string err;
+	std::vector<void *> allocations;
+};
+
+namespace {
+thread_local std::string g_net_error;
+
+int nfail(jdde_net * h, int code, const std::string & msg) { (h ? h->err : g_net_error) = msg; return code; }
+
+#define JN_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return nfail(h, JDDE_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+template <class T> int nalloc(jdde_net * h, T ** p, size_t count)
+{
+	void * q = nullptr;
+	cudaError_t e = cudaMalloc(&q, count*sizeof(T) ? count*sizeof(T) : 1);
+	if (e != cudaSuccess)
+		return nfail(h, e == cudaErrorMemoryAllocation ? JDDE_E_NOMEM : JDDE_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+	h->allocations.push_back(q);
+	*p = static_cast<T *>(q);
+	return JDDE_OK;
+}
+
+int nready(jdde_net * h)
+{
+	if (!h) return JDDE_E_INVALID;
+	if (cudaSetDevice(h->desc.device) != cudaSuccess) return nfail(h, JDDE_E_CUDA, "cudaSetDevice failed");
+	return JDDE_OK;
+}
+
+int nlaunch(jdde_net * h, cudaKernel_t k, long long threads, int block, size_t smem, void ** args)
+{
+	if (!k) return nfail(h, JDDE_E_INVALID, "kernel image not loaded (jdde_net_load_image)");
+	unsigned const grid = (unsigned)((threads+block-1)/block);
+	JN_CUDA(h, cudaLaunchKernel((const void *)k, dim3(grid ? grid : 1), dim3(block), args, smem, h->stream));
+	h->launches++;
+	return JDDE_OK;
+}
+
+int nready_run(jdde_net * h)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	if (!h->lib) return nfail(h, JDDE_E_INVALID, "no kernel image loaded (jdde_net_load_image)");
+	if (!h->have_graph) return nfail(h, JDDE_E_INVALID, "no graph set (jdde_net_set_graph)");
+	if (!h->have_past) return nfail(h, JDDE_E_INVALID, "no past set (jdde_net_set_past)");
+	if (!h->have_int) return nfail(h, JDDE_E_INVALID, "integration parameters not set (jdde_net_set_integration_parameters)");
+	return JDDE_OK;
+}
+} // namespace
+
+extern "C" {
+
+int jdde_net_create(const jdde_net_desc * d, jdde_net ** out)
+{
+	if (!d || !out) return nfail(nullptr, JDDE_E_INVALID, "null argument");
+	*out = nullptr;
+	if (d->n < 1 || d->lo < 0 || d->hi > d->n || d->lo >= d->hi || d->n_edges < 0 || d->n_node_params < 0)
+		return nfail(nullptr, JDDE_E_INVALID, "invalid descriptor");
+	if (d->ring_capacity < 4 || (d->ring_capacity & (d->ring_capacity-1)))
+		return nfail(nullptr, JDDE_E_INVALID, "ring_capacity must be a power of two >= 4");
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count < 1)
+		return nfail(nullptr, JDDE_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this engine has no CPU fallback)");
+	if (d->device < 0 || d->device >= count) return nfail(nullptr, JDDE_E_INVALID, "device ordinal out of range");
+	jdde_net * h = new (std::nothrow) jdde_net;
+	if (!h) return nfail(nullptr, JDDE_E_NOMEM, "out of host memory");
+	h->desc = *d;
+	auto bail = [&](int rc) { g_net_error = h->err; jdde_net_destroy(h); return rc; };
+	if (cudaSetDevice(d->device) != cudaSuccess) return bail(nfail(h, JDDE_E_CUDA, "cudaSetDevice failed"));
+	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(nfail(h, JDDE_E_CUDA, "cudaStreamCreate failed"));
+	h->own_stream = true;
+	size_t const n = (size_t)d->n, cap = (size_t)d->ring_capacity, E = (size_t)d->n_edges, owned = (size_t)(d->hi-d->lo);
+	jdn_problem & P = h->P;
+	P.n = d->n; P.lo = d->lo; P.hi = d->hi; P.cap = d->ring_capacity; P.n_node_params = d->n_node_params;
+	int rc;
+	if ((rc = nalloc(h, &P.ctrl, 1))) return bail(rc);
+	if ((rc = nalloc(h, &P.times, cap))) return bail(rc);
+	if ((rc = nalloc(h, &P.state, cap*n))) return bail(rc);
+	if ((rc = nalloc(h, &P.diff, cap*n))) return bail(rc);
+	if ((rc = nalloc(h, &P.stage_state, n))) return bail(rc);
+	if ((rc = nalloc(h, &P.stage_diff, n))) return bail(rc);
+	if ((rc = nalloc(h, &h->d_par, n*(size_t)(d->n_node_params ? d->n_node_params : 1)))) return bail(rc);
+	if ((rc = nalloc(h, &h->d_row_ptr, owned+1))) return bail(rc);
+	if ((rc = nalloc(h, &h->d_src, E))) return bail(rc);
+	if ((rc = nalloc(h, &h->d_tau, E))) return bail(rc);
+	if ((rc = nalloc(h, &h->d_weight, E))) return bail(rc);
+	if ((rc = nalloc(h, &P.cursor, E))) return bail(rc);
+	if ((rc = nalloc(h, &h->scratch, 2*E))) return bail(rc);
+	if ((rc = nalloc(h, &h->d_out, n))) return bail(rc);
+	P.node_par = h->d_par; P.row_ptr = h->d_row_ptr; P.src = h->d_src; P.tau = h->d_tau; P.weight = h->d_weight;
+	if (cudaMemsetAsync(P.ctrl, 0, sizeof(jdn_control), h->stream) != cudaSuccess) return bail(nfail(h, JDDE_E_CUDA, "cudaMemset failed"));
+	*out = h;
+	return JDDE_OK;
+}
+
+int jdde_net_destroy(jdde_net * h)
+{
+	if (!h) return JDDE_OK;
+	cudaSetDevice(h->desc.device);
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	for (void * p : h->allocations) cudaFree(p);
+	if (h->lib) cudaLibraryUnload(h->lib);
+	if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+	return JDDE_OK;
+}
+
+const char * jdde_net_last_error(const jdde_net * h) { return h ? h->err.c_str() : g_net_error.c_str(); }
+
+int jdde_net_load_image(jdde_net * h, const void * image, size_t len)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	if (!image || !len) return nfail(h, JDDE_E_INVALID, "empty image");
+	if (h->lib) { cudaLibraryUnload(h->lib); h->lib = nullptr; }
+	JN_CUDA(h, cudaLibraryLoadData(&h->lib, image, nullptr, nullptr, 0, nullptr, nullptr, 0));
+	void * dptr = nullptr; size_t bytes = 0;
+	if (cudaLibraryGetGlobal(&dptr, &bytes, h->lib, "jdn_image_desc") != cudaSuccess || bytes != sizeof(jdn_image_desc_t))
+		return nfail(h, JDDE_E_IMAGE, "image has no jdn_image_desc");
+	jdn_image_desc_t d;
+	JN_CUDA(h, cudaMemcpy(&d, dptr, sizeof d, cudaMemcpyDeviceToHost));
+	if (d.magic != JDN_IMAGE_MAGIC || d.abi != JDDE_ABI_VERSION) return nfail(h, JDDE_E_IMAGE, "image built for another ABI version");
+	if (d.n_node_params != h->desc.n_node_params) return nfail(h, JDDE_E_IMAGE, "image does not match the descriptor (node parameters)");
+	h->block = d.block;
+	struct { const char * name; cudaKernel_t * slot; } const table[] = {
+		{"jdn_k_attempt", &h->k_attempt}, {"jdn_k_control", &h->k_control}, {"jdn_k_commit", &h->k_commit},
+		{"jdn_k_begin", &h->k_begin}, {"jdn_k_recent_state", &h->k_recent}, {"jdn_k_set_past", &h->k_set_past},
+	};
+	for (auto const & entry : table)
+		if (cudaLibraryGetKernel(entry.slot, h->lib, entry.name) != cudaSuccess)
+			return nfail(h, JDDE_E_IMAGE, std::string("image lacks kernel ") + entry.name);
+	return JDDE_OK;
+}
+
+int jdde_net_set_stream(jdde_net * h, void * s)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+	h->stream = static_cast<cudaStream_t>(s);
+	return JDDE_OK;
+}
+
+int jdde_net_set_graph(jdde_net * h, const int64_t * row_ptr, const int32_t * src, const double * tau, const double * weight)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	if (!row_ptr || (h->desc.n_edges && (!src || !tau || !weight))) return nfail(h, JDDE_E_INVALID, "null argument");
+	size_t const owned = (size_t)(h->desc.hi-h->desc.lo), E = (size_t)h->desc.n_edges;
+	if (row_ptr[0] != 0 || (size_t)row_ptr[owned] != E) return nfail(h, JDDE_E_INVALID, "row_ptr does not match n_edges");
+	for (size_t e = 0; e < E; e++)
+		if (src[e] < 0 || src[e] >= h->desc.n || !(tau[e] > 0.0))
+			return nfail(h, JDDE_E_INVALID, "edge with source out of range or non-positive delay");
+	JN_CUDA(h, cudaMemcpyAsync(h->d_row_ptr, row_ptr, (owned+1)*sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+	JN_CUDA(h, cudaMemcpyAsync(h->d_src, src, E*sizeof(int), cudaMemcpyHostToDevice, h->stream));
+	JN_CUDA(h, cudaMemcpyAsync(h->d_tau, tau, E*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	JN_CUDA(h, cudaMemcpyAsync(h->d_weight, weight, E*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	h->have_graph = true;
+	return JDDE_OK;
+}
+
+int jdde_net_set_node_parameters(jdde_net * h, const double * par)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	if (!h->desc.n_node_params) return JDDE_OK;
+	if (!par) return nfail(h, JDDE_E_INVALID, "null argument");
+	JN_CUDA(h, cudaMemcpyAsync(h->d_par, par, (size_t)h->desc.n*h->desc.n_node_params*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	return JDDE_OK;
+}
+
+int jdde_net_set_past(jdde_net * h, int32_t n_anchors, const double * times, const double * states, const double * diffs)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	if (!h->lib) return nfail(h, JDDE_E_INVALID, "no kernel image loaded (jdde_net_load_image)");
+	if (n_anchors < 2) return nfail(h, JDDE_E_INVALID, "need at least two anchors (reference: _jitcdde.py:582)");
+	if (n_anchors+1 > h->P.cap) return nfail(h, JDDE_E_INVALID, "initial past does not fit into the ring; increase ring_capacity");
+	if (!times || !states || !diffs) return nfail(h, JDDE_E_INVALID, "null argument");
+	size_t const n = (size_t)h->desc.n, k = (size_t)n_anchors;
+	double * d_t = nullptr, * d_s = nullptr, * d_d = nullptr;
+	JN_CUDA(h, cudaMalloc((void **)&d_t, k*sizeof(double)));
+	JN_CUDA(h, cudaMalloc((void **)&d_s, k*n*sizeof(double)));
+	JN_CUDA(h, cudaMalloc((void **)&d_d, k*n*sizeof(double)));
+	JN_CUDA(h, cudaMemcpyAsync(d_t, times, k*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	JN_CUDA(h, cudaMemcpyAsync(d_s, states, k*n*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	JN_CUDA(h, cudaMemcpyAsync(d_d, diffs, k*n*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	int na = n_anchors; long long E = h->desc.n_edges;
+	void * args[] = { &h->P, &na, &d_t, &d_s, &d_d, &E };
+	rc = nlaunch(h, h->k_set_past, (long long)n, h->block, 0, args);
+	cudaStreamSynchronize(h->stream);
+	cudaFree(d_t); cudaFree(d_s); cudaFree(d_d);
+	if (rc) return rc;
+	h->have_past = true;
+	return JDDE_OK;
+}
+
+int jdde_net_set_integration_parameters(jdde_net * h, const jdde_int_params * p, double max_delay)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	if (!p) return nfail(h, JDDE_E_INVALID, "null argument");
+	if (!(p->decrease_threshold >= 1.0) || !(p->increase_threshold <= 1.0) || !(p->max_factor >= 1.0) || !(p->min_factor <= 1.0)
+		|| !(p->safety_factor <= 1.0) || !(p->atol >= 0.0) || !(p->rtol >= 0.0) || !(max_delay >= 0.0))
+		return nfail(h, JDDE_E_INVALID, "integration parameter out of range (see _jitcdde.py:695-708)");
+	jdde_int_params q = *p;
+	if (q.first_step > q.max_step) q.first_step = q.max_step;
+	if (q.min_step > q.first_step) q.min_step = q.first_step;
+	/* controller fields are set in place: P, dt (= first_step, _jitcdde.py:712), max_delay */
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	jdn_control c;
+	JN_CUDA(h, cudaMemcpy(&c, h->P.ctrl, sizeof c, cudaMemcpyDeviceToHost));
+	c.P = q; c.dt = q.first_step; c.max_delay = max_delay; c.cap = h->P.cap;
+	JN_CUDA(h, cudaMemcpy(h->P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice));
+	h->have_int = true;
+	return JDDE_OK;
+}
+
+int jdde_net_begin(jdde_net * h, int32_t mode, double target, double step, int64_t steps)
+{
+	int rc = nready_run(h);
+	if (rc) return rc;
+	int m = mode; long long s = steps;
+	void * args[] = { &h->P, &m, &target, &step, &s };
+	return nlaunch(h, h->k_begin, 1, 1, 0, args);
+}
+
+int jdde_net_attempt(jdde_net * h)
+{
+	int rc = nready_run(h);
+	if (rc) return rc;
+	void * args[] = { &h->P, &h->scratch };
+	return nlaunch(h, h->k_attempt, h->desc.hi-h->desc.lo, h->block, (size_t)h->P.cap*sizeof(double), args);
+}
+
+int jdde_net_control(jdde_net * h)
+{
+	int rc = nready_run(h);
+	if (rc) return rc;
+	void * args[] = { &h->P };
+	if ((rc = nlaunch(h, h->k_control, 1, 1, 0, args))) return rc;
+	return nlaunch(h, h->k_commit, h->desc.n, h->block, 0, args);
+}
+
+int jdde_net_poll(jdde_net * h, int32_t * done, double * t, int32_t * status)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	JN_CUDA(h, cudaMemcpyAsync(&h->host_ctrl, h->P.ctrl, sizeof(jdn_control), cudaMemcpyDeviceToHost, h->stream));
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	if (done) *done = h->host_ctrl.done;
+	if (t) *t = h->host_ctrl.t;
+	if (status) *status = h->host_ctrl.status;
+	return JDDE_OK;
+}
+
+int jdde_net_recent_state(jdde_net * h, double t, int32_t current_only, double * out)
+{
+	int rc = nready_run(h);
+	if (rc) return rc;
+	int co = current_only;
+	void * args[] = { &h->P, &t, &co, &h->d_out };
+	if ((rc = nlaunch(h, h->k_recent, h->desc.n, h->block, 0, args))) return rc;
+	if (out)
+	{
+		JN_CUDA(h, cudaMemcpyAsync(out, h->d_out, (size_t)h->desc.n*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+		JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	}
+	return JDDE_OK;
+}
+
+static int run_until_done(jdde_net * h)
+{
+	for (;;)
+	{
+		int rc;
+		for (int k = 0; k < h->poll_every; k++)
+		{
+			if ((rc = jdde_net_attempt(h))) return rc;
+			if ((rc = jdde_net_control(h))) return rc;
+		}
+		int32_t done = 0;
+		if ((rc = jdde_net_poll(h, &done, nullptr, nullptr))) return rc;
+		if (done) return JDDE_OK;
+	}
+}
+
+/* single-rank convenience: the whole jitcdde.integrate (_jitcdde.py:807-836) */
+int jdde_net_integrate(jdde_net * h, double target, double * out_state, int32_t * status)
+{
+	int rc = jdde_net_begin(h, JDN_MODE_ADAPTIVE, target, 0.0, 0);
+	if (rc) return rc;
+	if ((rc = run_until_done(h))) return rc;
+	if (status) *status = h->host_ctrl.status;
+	if (h->host_ctrl.status == JDDE_STATUS_OK)
+		return jdde_net_recent_state(h, target, 0, out_state);
+	return JDDE_OK;
+}
+
+/* integrate_blindly (_jitcdde.py:880-933); step <= 0 means max_step */
+int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double * out_state, int32_t * status)
+{
+	int rc = nready_run(h);
+	if (rc) return rc;
+	if ((rc = jdde_net_poll(h, nullptr, nullptr, nullptr))) return rc;
+	if (!(step > 0)) step = h->host_ctrl.P.max_step;
+	double const total = target-h->host_ctrl.t;
+	if (total < 0) return nfail(h, JDDE_E_INVALID, "Can't integrate backwards in time.");
+	long long number = 0; double dt = 0;
+	if (total > 0)
+	{
+		if (total < step) step = total;
+		number = (long long) rint(total/step);
+		dt = total/number;
+	}
+	if ((rc = jdde_net_begin(h, JDN_MODE_BLIND, target, dt, number))) return rc;
+	if (number > 0 && (rc = run_until_done(h))) return rc;
+	if ((rc = jdde_net_poll(h, nullptr, nullptr, nullptr))) return rc;
+	if (status) *status = h->host_ctrl.status;
+	return jdde_net_recent_state(h, target, 1, out_state);
+}
+
+int jdde_net_get_counters(jdde_net * h, int64_t * accepted, int64_t * rejected, int64_t * attempts)
+{
+	int rc = jdde_net_poll(h, nullptr, nullptr, nullptr);
+	if (rc) return rc;
+	if (accepted) *accepted = h->host_ctrl.accepted;
+	if (rejected) *rejected = h->host_ctrl.rejected;
+	if (attempts) *attempts = h->host_ctrl.attempts;
+	return JDDE_OK;
+}
+
+int jdde_net_get_dt(jdde_net * h, double * dt)
+{
+	int rc = jdde_net_poll(h, nullptr, nullptr, nullptr);
+	if (rc) return rc;
+	if (dt) *dt = h->host_ctrl.dt;
+	return JDDE_OK;
+}
+
+int jdde_net_exchange_pointers(jdde_net * h, uint64_t * stage_state, uint64_t * stage_diff, uint64_t * p_bits)
+{
+	if (!h) return JDDE_E_INVALID;
+	if (stage_state) *stage_state = (uint64_t)(uintptr_t)h->P.stage_state;
+	if (stage_diff) *stage_diff = (uint64_t)(uintptr_t)h->P.stage_diff;
+	if (p_bits) *p_bits = (uint64_t)(uintptr_t)&h->P.ctrl->p_bits;
+	return JDDE_OK;
+}
+
+int64_t jdde_net_launch_count(const jdde_net * h) { return h ? h->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,124 @@
+"""
+The network engine (`jitcdde_network`: one large delay-coupled system, node-parallel, structured graph input)
+against the symbolic path (`jitcdde`, one expression per node as in the reference's
+examples/kuramoto_network.py:42-63) on a small Kuramoto network. Both run on the host twin here (CPU); the GPU
+version of the same comparison is in test_gpu_network.py. The symbolic path itself is pinned to the reference's C
+core (golden "kuramoto"). The two paths add the coupling terms in a different order (SymPy sorts sums), so they
+agree to rounding, not bit for bit: states within 1e-9, identical step counts.
+"""
+
+import numpy as np
+import pytest
+import sympy
+
+from tests import systems
+
+
+def kuramoto_graph(n, seed=3, q=0.3, c=1.5):
+	rng = np.random.default_rng(seed)
+	A = rng.choice([1, 0], size=(n, n), p=[q, 1-q])
+	np.fill_diagonal(A, 0)
+	tau = rng.uniform(np.pi/5, 2*np.pi, size=(n, n))
+	omega = rng.uniform(0.8, 1.2, n)
+	initial = rng.uniform(0, 2*np.pi, n)
+	src, dst = np.nonzero(A)           # A[j, i]: edge j → i
+	return dict(n=n, A=A, tau=tau, omega=omega, initial=initial, src=src, dst=dst, edge_tau=tau[dst, src], weight=c/(n-1))
+
+
+def run_network(g, sample_times, blind_to, **kw):
+	from jitcdde_b200 import jitcdde_network
+	net = jitcdde_network(g["n"], local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=g["weight"], node_parameters=[g["omega"]], verbose=False, **kw)
+	net.set_integration_parameters(rtol=0, atol=1e-6)
+	net.constant_past(g["initial"], time=0.0)
+	blind = net.integrate_blindly(blind_to, 0.1)
+	samples = np.array([net.integrate(T) for T in sample_times])
+	return blind, samples, net.counters(), net.t
+
+
+def run_symbolic(g, sample_times, blind_to, **kw):
+	from jitcdde_b200 import jitcdde, t, y
+	n, A, tau = g["n"], g["A"], g["tau"]
+	f = [g["omega"][i] + g["weight"]*sum(sympy.sin(y(j, t-tau[i, j])-y(i)) for j in range(n) if A[j, i]) for i in range(n)]
+	DDE = jitcdde(f, verbose=False, max_delay=float(np.max(g["edge_tau"])), ring_capacity=256, **kw)
+	DDE.set_integration_parameters(rtol=0, atol=1e-6, max_step=float(np.min(g["edge_tau"])))
+	DDE.constant_past(g["initial"], time=0.0)
+	blind = DDE.integrate_blindly(blind_to, 0.1)
+	samples = np.array([DDE.integrate(T) for T in sample_times])
+	accepted, rejected, _ = DDE.counters()
+	return blind, samples, (int(accepted[0]), int(rejected[0])), DDE.t
+
+
+def test_network_engine_matches_symbolic_path(twin):
+	g = kuramoto_graph(12)
+	blind_to = float(np.max(g["edge_tau"]))
+	times = blind_to + np.arange(0.5, 5.5, 0.5)
+	nb, ns, nc, nt = run_network(g, times, blind_to)
+	sb, ss, sc, st = run_symbolic(g, times, blind_to)
+	np.testing.assert_allclose(nb, sb, rtol=1e-10)
+	np.testing.assert_allclose(ns, ss, rtol=1e-9)
+	assert (nc[0], nc[1]) == sc
+	assert abs(nt-st) < 1e-9
+
+
+def test_node_partition_exchange_protocol(twin):
+	"""Two engine instances, each owning half of the nodes (what two ranks hold), driven through the per-attempt
+	protocol attempt → exchange staged slices + max of the error norm → control: same trajectory as one instance."""
+	from jitcdde_b200 import _build, _capi, _codegen
+	g = kuramoto_graph(10)
+	n = g["n"]
+	blind_to = float(np.max(g["edge_tau"]))
+	times = blind_to + np.arange(0.5, 3.5, 0.5)
+	_, reference, counters, _ = run_network(g, times, blind_to)
+
+	program = _codegen.generate_network(lambda y, t, w: w, lambda yd, y: sympy.sin(yd-y), 1)
+	_build.build_net_image(program)
+	order = np.argsort(g["dst"], kind="stable")
+	src, dst, tau = g["src"][order], g["dst"][order], g["edge_tau"][order]
+	from oracle import oracle
+	pars = dict(oracle.DEFAULTS, rtol=0, atol=1e-6, max_step=float(tau.min()), first_step=min(1.0, float(tau.min())))
+	engines = []
+	for lo, hi in ((0, n//2), (n//2, n)):
+		mask = (dst >= lo) & (dst < hi)
+		row_ptr = np.concatenate([[0], np.cumsum(np.bincount(dst[mask]-lo, minlength=hi-lo))])
+		E = _capi.NetEngine(n, lo, hi, int(mask.sum()), 1, ring_capacity=128)
+		E.set_graph(row_ptr, src[mask], tau[mask], np.full(int(mask.sum()), g["weight"]))
+		E.set_node_parameters(g["omega"][None, :])
+		E.set_past([-1.0, 0.0], np.stack([g["initial"]]*2), np.zeros((2, n)))
+		E.set_integration_parameters(float(tau.max()), **pars)
+		engines.append((E, lo, hi))
+
+	import ctypes
+	def exchange():
+		views = []
+		for E, lo, hi in engines:
+			s, d, p = E.exchange_pointers()
+			views.append((np.ctypeslib.as_array(ctypes.cast(s, ctypes.POINTER(ctypes.c_double)), (n,)),
+				np.ctypeslib.as_array(ctypes.cast(d, ctypes.POINTER(ctypes.c_double)), (n,)),
+				np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), (1,)), lo, hi))
+		for s, d, p, lo, hi in views:           # all-gather
+			for s2, d2, p2, lo2, hi2 in views:
+				s2[lo:hi], d2[lo:hi] = s[lo:hi], d[lo:hi]
+		pmax = max(v[2][0] for v in views)      # all-reduce(max)
+		for v in views:
+			v[2][0] = pmax
+
+	def run(begin):
+		for E, _, _ in engines:
+			begin(E)
+		while not engines[0][0].poll()[0]:
+			for E, _, _ in engines:
+				E.attempt()
+			exchange()
+			for E, _, _ in engines:
+				E.control()
+
+	number = round(blind_to/0.1)
+	run(lambda E: E.begin(1, blind_to, blind_to/number, number))
+	samples = []
+	for T in times:
+		run(lambda E: E.begin(0, T))
+		samples.append(engines[0][0].recent_state(T))
+		assert np.array_equal(samples[-1], engines[1][0].recent_state(T))
+	assert np.array_equal(np.array(samples), reference)
+	assert engines[0][0].counters() == counters

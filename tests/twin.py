@@ -35,12 +35,43 @@ def build_twin(program, n_basic=None):
 			f"-DJD_NPARAMS={program.n_params}", f'-DJD_RHS_FILE="{rhs}"', f"-DJD_WINDOW={window}",
 			f"-I{_build.CSRC}", src, "-o", so, "-lm",
 		], check=True)
+	return _load(so)
+
+
+def _load(so):
 	lib = ctypes.CDLL(so)
 	for name, (restype, argtypes) in _capi.SIGNATURES.items():
-		fn = getattr(lib, name)
-		fn.restype = restype
-		fn.argtypes = argtypes
+		if hasattr(lib, name):
+			fn = getattr(lib, name)
+			fn.restype = restype
+			fn.argtypes = argtypes
 	return lib
+
+
+def build_net_twin(program):
+	"""host twin of the network engine (tests/host_twin/net_twin.cpp) for one (local, coupling) pair"""
+	os.makedirs(_OUT, exist_ok=True)
+	rhs = os.path.join(_OUT, f"net_{program.key}.inc")
+	with open(rhs, "w") as f:
+		f.write(program.body)
+	so = os.path.join(_OUT, f"net_twin_{program.key}.so")
+	src = os.path.join(_HERE, "host_twin", "net_twin.cpp")
+	deps = [src] + [os.path.join(_build.CSRC, x) for x in ("jdn_engine.cuh", "jdn_abi.h", "jdde_math.h", "jdde_abi.h")]
+	if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+		subprocess.run([
+			"g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+			f'-DJDN_RHS_FILE="{rhs}"', f"-I{_build.CSRC}", src, "-o", so, "-lm",
+		], check=True)
+	return _load(so)
+
+
+class _Both:
+	"""routes jdde_net_* to the network twin and everything else to the ensemble twin"""
+	def __init__(self, state):
+		self._state = state
+
+	def __getattr__(self, name):
+		return getattr(self._state["net_lib" if name.startswith("jdde_net_") else "lib"], name)
 
 
 @contextlib.contextmanager
@@ -56,11 +87,18 @@ def use_twin():
 		state["lib"] = build_twin(program, n_basic)
 		return "<host twin>"
 
-	saved = _build.build_image, _capi.load_library, _capi.Engine.load_image
+	def fake_build_net_image(program, **kwargs):
+		state["net_lib"] = build_net_twin(program)
+		return "<host twin>"
+
+	saved = _build.build_image, _build.build_net_image, _capi.load_library, _capi.Engine.load_image, _capi.NetEngine.load_image
 	_build.build_image = fake_build_image
-	_capi.load_library = lambda path=None: state["lib"]
+	_build.build_net_image = fake_build_net_image
+	both = _Both(state)
+	_capi.load_library = lambda path=None: both
 	_capi.Engine.load_image = lambda self, path: None
+	_capi.NetEngine.load_image = lambda self, path: None
 	try:
 		yield state
 	finally:
-		_build.build_image, _capi.load_library, _capi.Engine.load_image = saved
+		_build.build_image, _build.build_net_image, _capi.load_library, _capi.Engine.load_image, _capi.NetEngine.load_image = saved

@@ -32,11 +32,12 @@ class _DeviceArray:
 
 
 class jitcdde_network:
-	def __init__(self, n, local, coupling, edges, node_parameters=(), weight=None, max_delay=None, device=0, ring_capacity=128, verbose=True, poll_every=8):
+	def __init__(self, n, local, coupling, edges, node_parameters=(), weight=None, max_delay=None, device=0, ring_capacity=512, verbose=True, poll_every=8):
 		"""
 		n: number of nodes. local(y, t, *p) and coupling(y_delayed, y): functions returning SymPy expressions.
 		edges: (src, dst, tau[, weight]) arrays, one entry per directed edge src → dst with delay tau > 0.
 		node_parameters: sequence of arrays of length n, passed to `local` in this order.
+		ring_capacity: anchors kept (power of two); must exceed max_delay / smallest step (2·8·n bytes each).
 		"""
 		self.n = int(n)
 		self.verbose = verbose

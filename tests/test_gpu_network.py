@@ -22,7 +22,7 @@ def large_graph(n, k=10, seed=42):
 
 
 def test_network_engine_matches_symbolic_path_on_gpu():
-	g = kuramoto_graph(40, q=0.2)
+	g = kuramoto_graph(12)      # same graph as the CPU test; its symbolic image is prebuilt by __graft_entry__.build()
 	blind_to = float(np.max(g["edge_tau"]))
 	times = blind_to + np.arange(0.5, 5.5, 0.5)
 	nb, ns, nc, nt = run_network(g, times, blind_to)

@@ -36,10 +36,23 @@ def run_network(g, sample_times, blind_to, **kw):
 	return blind, samples, net.counters(), net.t
 
 
-def run_symbolic(g, sample_times, blind_to, **kw):
-	from jitcdde_b200 import jitcdde, t, y
+def symbolic_f(g):
+	from jitcdde_b200 import t, y
 	n, A, tau = g["n"], g["A"], g["tau"]
-	f = [g["omega"][i] + g["weight"]*sum(sympy.sin(y(j, t-tau[i, j])-y(i)) for j in range(n) if A[j, i]) for i in range(n)]
+	return [g["omega"][i] + g["weight"]*sum(sympy.sin(y(j, t-tau[i, j])-y(i)) for j in range(n) if A[j, i]) for i in range(n)]
+
+
+def prebuild_images():
+	"""called by __graft_entry__.build(): compile, on the CPU box, the kernel images the GPU tests of the network
+	engine need (the symbolic path has one lookup site per edge; its image takes minutes to compile)"""
+	from jitcdde_b200 import _build, _codegen
+	_build.build_image(_codegen.generate(symbolic_f(kuramoto_graph(12))), mode=_build.VERIFY)
+	_build.build_net_image(_codegen.generate_network(lambda y, t, w: w, lambda yd, y: sympy.sin(yd-y), 1))
+
+
+def run_symbolic(g, sample_times, blind_to, **kw):
+	from jitcdde_b200 import jitcdde
+	f = symbolic_f(g)
 	DDE = jitcdde(f, verbose=False, max_delay=float(np.max(g["edge_tau"])), ring_capacity=256, **kw)
 	DDE.set_integration_parameters(rtol=0, atol=1e-6, max_step=float(np.min(g["edge_tau"])))
 	DDE.constant_past(g["initial"], time=0.0)

@@ -15,7 +15,7 @@ from jitcdde_b200 import jitcdde_network
 for n in [int(x) for x in (sys.argv[1:] or ["100000", "1000000"])]:
     g = large_graph(n)
     net = jitcdde_network(n, local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y), edges=(g["src"], g["dst"], g["edge_tau"]),
-        weight=g["weight"], node_parameters=[g["omega"]], verbose=False, device=local, ring_capacity=128)
+        weight=g["weight"], node_parameters=[g["omega"]], verbose=False, device=local, ring_capacity=512)
     net.set_integration_parameters(rtol=0, atol=1e-5)
     net.constant_past(g["initial"], time=0.0)
     t0 = time.perf_counter(); net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1); t1 = time.perf_counter()

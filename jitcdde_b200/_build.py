@@ -37,23 +37,39 @@ def nvcc():
 	return path
 
 
-def _newer(target, sources):
-	if not os.path.exists(target):
+def _sources_hash(sources, extra=""):
+	h = hashlib.sha256(extra.encode())
+	for path in sources:
+		with open(path, "rb") as f:
+			h.update(f.read())
+	return h.hexdigest()
+
+
+def _stale(target, stamp_value):
+	"""A built file is current if its stamp file holds the hash of the sources it was built from (content, not
+	mtimes: the tree is copied to other machines, and several ranks may import the package at once)."""
+	try:
+		with open(target + ".stamp") as f:
+			return not os.path.exists(target) or f.read().strip() != stamp_value
+	except OSError:
 		return True
-	t = os.path.getmtime(target)
-	return any(os.path.getmtime(s) > t for s in sources)
 
 
 def build_runtime(force=False, verbose=False):
-	"""nvcc -shared … csrc/jdde_runtime.cu → jitcdde_b200/libjitcdde_b200.so"""
+	"""nvcc -shared … csrc/jdde_runtime.cu csrc/jdn_runtime.cu → jitcdde_b200/libjitcdde_b200.so"""
 	sources = [os.path.join(CSRC, "jdde_runtime.cu"), os.path.join(CSRC, "jdn_runtime.cu"), os.path.join(CSRC, "jdde_abi.h"),
 		os.path.join(CSRC, "jdn_abi.h"), os.path.join(INCLUDE, "jitcdde_b200.h")]
-	if force or _newer(RUNTIME_LIB, sources):
+	stamp = _sources_hash(sources)
+	if force or _stale(RUNTIME_LIB, stamp):
+		tmp = f"{RUNTIME_LIB}.{os.getpid()}.tmp"
 		cmd = [nvcc(), "-shared", "-Xcompiler", "-fPIC", "-O2", "-std=c++17", *ARCH, "-lineinfo",
-			sources[0], sources[1], "-o", RUNTIME_LIB]
+			sources[0], sources[1], "-o", tmp]
 		if verbose:
 			print(" ".join(cmd))
 		subprocess.run(cmd, check=True)
+		os.replace(tmp, RUNTIME_LIB)
+		with open(RUNTIME_LIB + ".stamp", "w") as f:
+			f.write(stamp)
 	return RUNTIME_LIB
 
 

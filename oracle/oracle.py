@@ -82,16 +82,30 @@ def build(program, n_basic=None, flags=VERIFY_FLAGS, openmp=False, tag=""):
 		with open(rhs, "w") as f:
 			f.write(program.body)
 	deps = [src, os.path.join(_CSRC, "jdde_math.h")]
-	if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+	h = hashlib.sha256()
+	for d in deps:
+		with open(d, "rb") as f:
+			h.update(f.read())
+	stamp = h.hexdigest()
+	try:
+		with open(so + ".stamp") as f:
+			current = os.path.exists(so) and f.read().strip() == stamp
+	except OSError:
+		current = False
+	if not current:
+		tmp = f"{so}.{os.getpid()}.tmp"
 		cmd = [
-			"gcc", "-std=c11", *flags, "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-unused-variable",
+			"gcc", "-std=c11", *flags, "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unknown-pragmas",
 			f"-DJO_N={program.n}", f"-DJO_NBASIC={n_basic}", f"-DJO_NSITES={program.n_sites}",
 			f"-DJO_NPARAMS={program.n_params}", f'-DJO_RHS_FILE="{rhs}"',
-			f"-I{_CSRC}", src, "-o", so, "-lm",
+			f"-I{_CSRC}", src, "-o", tmp, "-lm",
 		]
 		if openmp:
 			cmd.insert(2, "-fopenmp")
 		subprocess.run(cmd, check=True)
+		os.replace(tmp, so)
+		with open(so + ".stamp", "w") as f:
+			f.write(stamp)
 	lib = ctypes.CDLL(so)
 	lib.jo_create.restype = ctypes.c_void_p
 	lib.jo_create.argtypes = [ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]

@@ -1,0 +1,229 @@
+"""
+The reference's own API tests, restated for this package (tests/test_jitcdde.py, tests/test_past_from_function.py of
+the reference): every way of defining the same two-Rössler system — list, generator function, dictionary, helpers,
+control parameters (tuple and list form), common-subexpression off, a tiny extra delay that forces the
+past-within-step iteration — must reproduce the reference's golden vector y(T=10) within the reference's tolerance
+(rtol 1e-3, atol 1e-6), through all the ways of getting there (samples, one big step, adjust_diff first, zero jump,
+annihilating jumps, many tiny samples). Runs on the host twin here and on the GPU with -m gpu.
+"""
+
+import numpy as np
+import pytest
+import sympy
+
+from jitcdde_b200 import UnsuccessfulIntegration, _find_max_delay, _get_delays, jitcdde, quadrature, t, y
+from tests import scenarios
+
+omega = np.array([0.88167179, 0.87768425])
+delay = 4.5
+T = 10
+test_parameters = dict(rtol=1e-4, atol=1e-7, pws_rtol=1e-3, pws_atol=1e-3, first_step=30, max_step=100, min_step=1e-16)
+tolerance = dict(rtol=1e-3, atol=1e-6)
+
+f = [
+	omega[0] * (-y(1) - y(2)),
+	omega[0] * (y(0) + 0.165 * y(1)),
+	omega[0] * (0.2 + y(2) * (y(0) - 10.0)),
+	omega[1] * (-y(4) - y(5)) + 0.25 * (y(0, t-delay) - y(3)),
+	omega[1] * (y(3) + 0.165 * y(4)),
+	omega[1] * (0.2 + y(5) * (y(3) - 10.0)),
+]
+
+
+def f_generator():
+	yield from f
+
+
+tiny_delay = 1e-30
+f_with_tiny_delay = [
+	omega[0] * (-y(1) - y(2)),
+	omega[0] * (y(0) + 0.165 * y(1, t-tiny_delay)),
+	omega[0] * (0.2 + y(2) * (y(0) - 10.0)),
+	omega[1] * (-y(4) - y(5)) + 0.25 * (y(0, t-delay) - y(3, t-tiny_delay)),
+	omega[1] * (y(3) + 0.165 * y(4)),
+	omega[1] * (0.2 + y(5) * (y(3) - 10.0)),
+]
+
+delayed_y, y3m10, coupling_term = sympy.symbols("delayed_y y3m10 coupling_term")
+f_alt_helpers = [(delayed_y, y(0, t-delay)), (coupling_term, 0.25 * (delayed_y - y(3))), (y3m10, y(3)-10)]
+f_alt = [
+	omega[0] * (-y(1) - y(2)),
+	omega[0] * (y(0) + 0.165 * y(1)),
+	omega[0] * (0.2 + y(2) * (y(0) - 10.0)),
+	omega[1] * (-y(4) - y(5)) + coupling_term,
+	omega[1] * (y3m10 + 10 + 0.165 * y(4)),
+	omega[1] * (0.2 + y(5) * y3m10),
+]
+
+a, b, c, k, tau = sympy.symbols("a b c k tau")
+parameters = [0.165, 0.2, 10.0, 0.25, 4.5]
+f_params = [
+	omega[0] * (-y(1) - y(2)),
+	omega[0] * (y(0) + a * y(1)),
+	omega[0] * (b + y(2) * (y(0) - c)),
+	omega[1] * (-y(4) - y(5)) + k * (y(0, t-tau) - y(3)),
+	omega[1] * (y(3) + a * y(4)),
+	omega[1] * (b + y(5) * (y(3) - c)),
+]
+
+VARIANTS = {
+	"list": lambda: jitcdde(f, verbose=False),
+	"generator": lambda: jitcdde(f_generator, verbose=False),
+	"dictionary": lambda: jitcdde({y(i): entry for i, entry in enumerate(f)}, verbose=False),
+	"helpers": lambda: jitcdde(f_alt, helpers=f_alt_helpers, verbose=False),
+	"automatic_anchor_helpers": lambda: jitcdde(f, automatic_anchor_helpers=True, verbose=False),
+	"no_cse": lambda: jitcdde(f, verbose=False),
+	"parameters": lambda: jitcdde(f_params, control_pars=[a, b, c, k, tau], max_delay=parameters[-1], verbose=False),
+	"parameters_list": lambda: jitcdde(f_params, control_pars=[a, b, c, k, tau], max_delay=parameters[-1], verbose=False),
+	"past_within_step": lambda: jitcdde(f_with_tiny_delay, verbose=False),
+}
+NO_JUMPS = {"past_within_step"}      # "Because the minimum delay must be larger than the jump width" (tests/test_jitcdde.py:171-174)
+
+
+GPU_VARIANTS = ["list", "helpers", "parameters", "past_within_step"]
+
+
+def prebuild_images():
+	"""called by __graft_entry__.build(): compile the kernel images of the GPU variants on the CPU box"""
+	for name in GPU_VARIANTS:
+		VARIANTS[name]().compile_C()
+
+
+def prepared(name):
+	g = scenarios.golden("roessler")
+	DDE = VARIANTS[name]()
+	DDE.set_integration_parameters(**test_parameters)
+	DDE.add_past_points(scenarios.past_of(g))
+	DDE.check()
+	if name == "no_cse":
+		DDE.compile_C(do_cse=False)
+	if name == "parameters":
+		DDE.set_parameters(*parameters)
+	if name == "parameters_list":
+		DDE.set_parameters(parameters)
+	DDE.initial_discontinuities_handled = True
+	return DDE, g["y10_reference"]
+
+
+def run_variant(name):
+	results = {}
+	DDE, y10 = prepared(name)
+	for time in np.linspace(0, T, 10, endpoint=True):
+		value = DDE.integrate(time)
+	results["samples"] = value
+	DDE, _ = prepared(name)
+	results["one_big_step"] = DDE.integrate(T)
+	DDE, _ = prepared(name)
+	for time in np.linspace(0.0, T, 1000, endpoint=True):
+		value = DDE.integrate(time)
+	results["tiny_steps"] = value
+	if name not in NO_JUMPS:
+		DDE, _ = prepared(name)
+		DDE.adjust_diff()
+		results["adjust_diff"] = DDE.integrate(T)
+		DDE, _ = prepared(name)
+		DDE.integrate(T/2)
+		DDE.jump(np.zeros(6), T/2)
+		results["zero_jump"] = DDE.integrate(T)
+		DDE, _ = prepared(name)
+		rng = np.random.default_rng(seed=42)
+		DDE.integrate(T/2)
+		change = rng.normal(0, 10, 6)
+		DDE.jump(change, T/2)
+		DDE.jump(-change, T/2)
+		results["annihilating_jumps"] = DDE.integrate(T)
+	return results, y10
+
+
+def check_variant(name):
+	results, y10 = run_variant(name)
+	for how, value in results.items():
+		np.testing.assert_allclose(value, y10, err_msg=f"{name}/{how}", **tolerance)
+	# sampling grid does not influence the integration
+	assert np.array_equal(results["samples"], results["one_big_step"])
+	assert np.array_equal(results["samples"], results["tiny_steps"])
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_input_variants_reproduce_golden_vector(twin, name):
+	check_variant(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GPU_VARIANTS)
+def test_input_variants_reproduce_golden_vector_gpu(name):
+	check_variant(name)
+
+
+def test_jump_places_two_anchors(twin):
+	"""tests/test_jitcdde.py:353-371"""
+	g = scenarios.golden("roessler")
+	DDE = jitcdde(f, verbose=False)
+	DDE.set_integration_parameters(**test_parameters)
+	DDE.add_past_points(scenarios.past_of(g))
+	width, change = 1e-5, np.random.default_rng(1).normal(0, 5, 6)
+	before = DDE.integrate(T)
+	past = DDE.get_state()
+	DDE.jump(change, T, width)
+	past = DDE.get_state()
+	assert past[-1].time == T+width
+	assert past[-2].time == T
+	np.testing.assert_allclose(past[-1].state, before+change, rtol=1e-3)
+	np.testing.assert_allclose(past[-2].state, before, rtol=1e-3)
+
+
+def test_unsuccessful_integration(twin):
+	"""tests/test_jitcdde.py:332-351"""
+	g = scenarios.golden("roessler")
+	for pars in (dict(min_step=1.0), dict(min_step=1e-3, rtol=1e-10, atol=0), dict(min_step=1e-3, rtol=0, atol=1e-10)):
+		DDE = jitcdde(f, verbose=False)
+		DDE.add_past_points(scenarios.past_of(g))
+		DDE.set_integration_parameters(**pars)
+		with pytest.raises(UnsuccessfulIntegration):
+			DDE.integrate(1000)
+
+
+def test_find_max_delay_and_delays():
+	"""tests/test_jitcdde.py:373-385"""
+	assert _find_max_delay([0, 1, 4.5, 2]) == 4.5
+	assert sorted(float(d) for d in _get_delays(f)) == [0.0, 4.5]
+	with pytest.raises(ValueError):
+		_find_max_delay([0, sympy.Symbol("tau")])
+
+
+def test_check_rejects_bad_input():
+	"""tests/test_jitcdde.py:387-410"""
+	for bad in ([y(1)], [y(0, t-1)+y(2)], [sympy.Symbol("z")*y(0)], []):
+		with pytest.raises(ValueError):
+			jitcdde(bad, verbose=False).check()
+
+
+def test_quadrature():
+	"""tests/test_jitcdde.py:412-425: ∫_0^1 x² dx with both rules"""
+	x = sympy.Symbol("x")
+	for method, places in (("midpoint", 3), ("gauss", 10)):
+		value = float(quadrature(x**2, x, 0, 1, nsteps=20, method=method))
+		assert abs(value-1/3) < 10**-places
+
+
+def test_past_from_function(twin):
+	"""tests/test_past_from_function.py: a past given as callable, as symbolic expressions, or as explicit anchors
+	leads to the same trajectory (double Mackey–Glass; atol 0.01 as in the reference)"""
+	tau1, tau2 = 15, 10
+	f_mg = [0.25*y(0, t-tau1)/(1.0+y(0, t-tau1)**10) - 0.1*y(0) + 0.05*y(0, t-tau2)]
+	expressions = [sympy.cos(t)*0.1+0.9]
+	function = lambda time: [np.cos(time)*0.1+0.9]
+	results = []
+	for how in ("callable", "symbolic", "anchors"):
+		DDE = jitcdde(f_mg, verbose=False, ring_capacity=256)
+		if how == "callable":
+			DDE.past_from_function(function)
+		elif how == "symbolic":
+			DDE.past_from_function(expressions)
+		else:
+			for time in np.linspace(-15, 0, 200):
+				DDE.add_past_point(time, function(time), [-np.sin(time)*0.1])
+		DDE.step_on_discontinuities()
+		results.append(np.array([DDE.integrate(DDE.t+s) for s in (10, 50, 100)]))
+	np.testing.assert_allclose(results[0], results[1], atol=0.01)
+	np.testing.assert_allclose(results[0], results[2], atol=0.01)

@@ -238,7 +238,9 @@ int jdde_net_begin(jdde_net * h, int32_t mode, double target, double step, int64
 int jdde_net_attempt(jdde_net * h);
 int jdde_net_control(jdde_net * h);
 int jdde_net_poll(jdde_net * h, int32_t * done, double * t, int32_t * status);
-int jdde_net_exchange_pointers(jdde_net * h, uint64_t * stage_state, uint64_t * stage_diff, uint64_t * p_bits);
+/* device addresses of the staged anchor ([n][2] doubles: state, diff per node) and of the error norm (IEEE bits of a
+ * non-negative double) of the attempt under way */
+int jdde_net_exchange_pointers(jdde_net * h, uint64_t * stage, uint64_t * p_bits);
 /* whole calls on a single rank: integrate (_jitcdde.py:807-836), integrate_blindly (:880-933), state [n] */
 int jdde_net_integrate(jdde_net * h, double target, double * out_state, int32_t * status);
 int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double * out_state, int32_t * status);

@@ -102,7 +102,7 @@ SIGNATURES.update({
 	"jdde_net_attempt": (ctypes.c_int, [_H]),
 	"jdde_net_control": (ctypes.c_int, [_H]),
 	"jdde_net_poll": (ctypes.c_int, [_H, c_int32_p, c_double_p, c_int32_p]),
-	"jdde_net_exchange_pointers": (ctypes.c_int, [_H, c_uint64_p, c_uint64_p, c_uint64_p]),
+	"jdde_net_exchange_pointers": (ctypes.c_int, [_H, c_uint64_p, c_uint64_p]),
 	"jdde_net_integrate": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_int32_p]),
 	"jdde_net_integrate_blindly": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_double, c_double_p, c_int32_p]),
 	"jdde_net_recent_state": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int32, c_double_p]),
@@ -465,9 +465,9 @@ class NetEngine:
 		return bool(done.value), t.value, status.value
 
 	def exchange_pointers(self):
-		a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
-		self._check(self.lib.jdde_net_exchange_pointers(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
-		return a.value, b.value, c.value
+		a, b = ctypes.c_uint64(), ctypes.c_uint64()
+		self._check(self.lib.jdde_net_exchange_pointers(self._h, ctypes.byref(a), ctypes.byref(b)))
+		return a.value, b.value
 
 	def integrate(self, target):
 		out = np.empty(self.n)

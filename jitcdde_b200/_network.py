@@ -136,18 +136,17 @@ class jitcdde_network:
 	# ------------------------------------------------------------------ multi-GPU anchor exchange
 	def _setup_exchange(self):
 		import torch
-		state_ptr, diff_ptr, p_ptr = self._engine.exchange_pointers()
+		stage_ptr, p_ptr = self._engine.exchange_pointers()
 		as_tensor = lambda ptr, count: torch.as_tensor(_DeviceArray(ptr, (count,), "<f8"), device=torch.device("cuda", self.device))
-		self._exchange = (as_tensor(state_ptr, self.n), as_tensor(diff_ptr, self.n), as_tensor(p_ptr, 1))
+		self._exchange = (as_tensor(stage_ptr, 2*self.n), as_tensor(p_ptr, 1))
 		self._engine.set_stream(torch.cuda.current_stream().cuda_stream)
 
 	def _exchange_anchors(self):
 		"""all-gather of the staged [state, diff] slices over NVLink + max-reduction of the error norm (the IEEE bits of a
 		non-negative double are monotone in its value, so MAX on the float64 view is the max of the norms)"""
 		import torch.distributed as dist
-		state, diff, p = self._exchange
-		dist.all_gather_into_tensor(state, state[self.lo:self.hi])
-		dist.all_gather_into_tensor(diff, diff[self.lo:self.hi])
+		stage, p = self._exchange
+		dist.all_gather_into_tensor(stage, stage[2*self.lo:2*self.hi])      # in place: every rank's slice sits at its offset
 		dist.all_reduce(p, op=dist.ReduceOp.MAX)
 
 	def _run(self):

@@ -11,11 +11,12 @@
  *
  * HBM layout:
  *   times  [cap]          anchor times (shared by all nodes)
- *   state  [cap][n]       slot-major: the n values of one anchor are contiguous → the node-parallel reads and
- *   diff   [cap][n]       writes of a step are coalesced; delayed lookups gather within two neighbouring rows
+ *   hist   [cap][n][2]    slot-major, (state, diff) of a node interleaved: the n pairs of one anchor are contiguous →
+ *                         the node-parallel reads and writes of a step are coalesced, and a delayed lookup gathers ONE
+ *                         16-byte pair per history row (two rows per lookup) instead of four scattered doubles
  *   edges  CSR by destination node: row_ptr[n_owned+1], src[E], tau[E], weight[E], cursor[E]
  *          (cursor = the reference's per-call-site search cursor, jitced_template.c:44-45: one lookup site per edge)
- *   stage_state, stage_diff [n]   the tentative anchor of the attempt under way. It has a FIXED address, so with several
+ *   stage  [n][2]         the tentative anchor of the attempt under way. It has a FIXED address, so with several
  *          GPUs the slices computed by the ranks are all-gathered in place without the host knowing the ring index;
  *          a copy kernel commits it to the ring after the controller accepted the step.
  *   ctrl   one jdn_control in device memory: time, step size, indices, error norm, counters — the controller
@@ -57,10 +58,9 @@ typedef struct jdn_problem
 {
 	jdn_control * ctrl;
 	double * times;
-	double * state;
-	double * diff;
-	double * stage_state;     /* [n] tentative anchor of the attempt under way: written by the attempt kernel (owned nodes), */
-	double * stage_diff;      /* [n] completed by the all-gather between ranks, copied into the ring when the step is accepted */
+	double * hist;            /* [cap][n][2]: (state, diff) pairs */
+	double * stage;           /* [n][2] tentative anchor of the attempt under way: written by the attempt kernel (owned nodes),
+	                             completed by the all-gather between ranks, copied into the ring when the step is accepted */
 	double const * node_par;  /* [n_node_params][n] */
 	long long const * row_ptr;/* [n_owned+1], offsets into the edge arrays */
 	int const * src;

@@ -41,6 +41,8 @@
 
 namespace jdn {
 
+struct alignas(16) pair { double state, diff; };
+
 struct View
 {
 	double const * times;
@@ -67,12 +69,13 @@ JDN_FN double past_value(jdn_problem const & P, View const & V, int const ca, lo
 	double const tv = anchor_time(V, ca);
 	double const q = anchor_time(V, ca+1)-tv;
 	double const x = (t - tv)/q;
-	size_t const rv = (size_t)(ca & V.mask)*P.n + j;
-	size_t const rw = (size_t)((ca+1) & V.mask)*P.n + j;
-	double const a = P.state[rv];
-	double const b = P.diff[rv] * q;
-	double const c = P.state[rw];
-	double const d = P.diff[rw] * q;
+	pair const * const H = reinterpret_cast<pair const *>(P.hist);
+	pair const v = H[(size_t)(ca & V.mask)*P.n + j];
+	pair const w = H[(size_t)((ca+1) & V.mask)*P.n + j];
+	double const a = v.state;
+	double const b = v.diff * q;
+	double const c = w.state;
+	double const d = w.diff * q;
 	return (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
 }
 
@@ -85,9 +88,9 @@ JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h
 {
 	long long const row = i-P.lo;
 	long long const e0 = P.row_ptr[row], e1 = P.row_ptr[row+1];
-	size_t const rc = (size_t)(V.current & V.mask)*P.n + i;
-	double const y = P.state[rc];
-	double const k_1 = P.diff[rc];
+	pair const cur = reinterpret_cast<pair const *>(P.hist)[(size_t)(V.current & V.mask)*P.n + i];
+	double const y = cur.state;
+	double const k_1 = cur.diff;
 	double par[JDN_NPARAMS > 0 ? JDN_NPARAMS : 1];
 	for (int k = 0; k < JDN_NPARAMS; k++)
 		par[k] = P.node_par[(size_t)k*P.n+i];
@@ -128,8 +131,10 @@ JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h
 	double const k_4 = acc;
 
 	double const error = fabs((5*k_1-6*k_2-8*k_3+9*k_4) * (h/72.));
-	P.stage_state[i] = y_new;
-	P.stage_diff[i] = k_4;
+	pair staged;
+	staged.state = y_new;
+	staged.diff = k_4;
+	reinterpret_cast<pair *>(P.stage)[i] = staged;
 
 	double const tolerance = P.ctrl->P.atol + P.ctrl->P.rtol*fabs(y_new);
 	if (error != 0.0 || tolerance != 0.0)
@@ -256,15 +261,16 @@ JDN_FN double recent_state(jdn_problem const & P, double const t, long long cons
 {
 	jdn_control const & C = *P.ctrl;
 	int const mask = P.cap-1;
-	size_t const rv = (size_t)((C.current-1) & mask)*P.n + i;
-	size_t const rw = (size_t)(C.current & mask)*P.n + i;
+	pair const * const H = reinterpret_cast<pair const *>(P.hist);
+	pair const v = H[(size_t)((C.current-1) & mask)*P.n + i];
+	pair const w = H[(size_t)(C.current & mask)*P.n + i];
 	double const tv = P.times[(C.current-1) & mask];
 	double const q = P.times[C.current & mask]-tv;
 	double const x = (t - tv)/q;
-	double const a = P.state[rv];
-	double const b = P.diff[rv] * q;
-	double const c = P.state[rw];
-	double const d = P.diff[rw] * q;
+	double const a = v.state;
+	double const b = v.diff * q;
+	double const c = w.state;
+	double const d = w.diff * q;
 	return (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
 }
 

@@ -70,10 +70,7 @@ jdn_k_commit(jdn_problem const P)
 		return;
 	long long const i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
 	if (i < P.n)
-	{
-		P.state[(size_t)slot*P.n+i] = P.stage_state[i];
-		P.diff[(size_t)slot*P.n+i] = P.stage_diff[i];
-	}
+		reinterpret_cast<jdn::pair *>(P.hist)[(size_t)slot*P.n+i] = reinterpret_cast<jdn::pair const *>(P.stage)[i];
 }
 
 /* prepare a call: mode, target, step; blind: h and the number of steps are given by the host (_jitcdde.py:880-900) */
@@ -115,7 +112,7 @@ jdn_k_recent_state(jdn_problem const P, double const t, int const current_only, 
 	if (i >= P.n)
 		return;
 	if (current_only)
-		out[i] = P.state[(size_t)(P.ctrl->current & (P.cap-1))*P.n + i];      /* get_current_state */
+		out[i] = P.hist[2*((size_t)(P.ctrl->current & (P.cap-1))*P.n + i)];      /* get_current_state */
 	else
 		out[i] = jdn::recent_state(P, t, i);
 }
@@ -128,8 +125,8 @@ jdn_k_set_past(jdn_problem const P, int const n_anchors, double const * const ti
 	if (i < P.n)
 		for (int k = 0; k < n_anchors; k++)
 		{
-			P.state[(size_t)k*P.n+i] = states[(size_t)k*P.n+i];
-			P.diff[(size_t)k*P.n+i] = diffs[(size_t)k*P.n+i];
+			P.hist[2*((size_t)k*P.n+i)] = states[(size_t)k*P.n+i];
+			P.hist[2*((size_t)k*P.n+i)+1] = diffs[(size_t)k*P.n+i];
 		}
 	for (long long e = i; e < n_edges; e += (long long)gridDim.x*blockDim.x)
 		P.cursor[e] = n_anchors-2;      /* all cursors start at last_anchor->previous (:647-648) */

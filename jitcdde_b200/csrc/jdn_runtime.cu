@@ -107,10 +107,8 @@ int jdde_net_create(const jdde_net_desc * d, jdde_net ** out)
 	int rc;
 	if ((rc = nalloc(h, &P.ctrl, 1))) return bail(rc);
 	if ((rc = nalloc(h, &P.times, cap))) return bail(rc);
-	if ((rc = nalloc(h, &P.state, cap*n))) return bail(rc);
-	if ((rc = nalloc(h, &P.diff, cap*n))) return bail(rc);
-	if ((rc = nalloc(h, &P.stage_state, n))) return bail(rc);
-	if ((rc = nalloc(h, &P.stage_diff, n))) return bail(rc);
+	if ((rc = nalloc(h, &P.hist, 2*cap*n))) return bail(rc);
+	if ((rc = nalloc(h, &P.stage, 2*n))) return bail(rc);
 	if ((rc = nalloc(h, &h->d_par, n*(size_t)(d->n_node_params ? d->n_node_params : 1)))) return bail(rc);
 	if ((rc = nalloc(h, &h->d_row_ptr, owned+1))) return bail(rc);
 	if ((rc = nalloc(h, &h->d_src, E))) return bail(rc);
@@ -373,11 +371,10 @@ int jdde_net_get_dt(jdde_net * h, double * dt)
 	return JDDE_OK;
 }
 
-int jdde_net_exchange_pointers(jdde_net * h, uint64_t * stage_state, uint64_t * stage_diff, uint64_t * p_bits)
+int jdde_net_exchange_pointers(jdde_net * h, uint64_t * stage, uint64_t * p_bits)
 {
 	if (!h) return JDDE_E_INVALID;
-	if (stage_state) *stage_state = (uint64_t)(uintptr_t)h->P.stage_state;
-	if (stage_diff) *stage_diff = (uint64_t)(uintptr_t)h->P.stage_diff;
+	if (stage) *stage = (uint64_t)(uintptr_t)h->P.stage;
 	if (p_bits) *p_bits = (uint64_t)(uintptr_t)&h->P.ctrl->p_bits;
 	return JDDE_OK;
 }

@@ -15,7 +15,7 @@ struct jdde_net
 	jdde_net_desc desc{};
 	jdn_problem P{};
 	jdn_control ctrl{};
-	std::vector<double> times, state, diff, stage_state, stage_diff, par, tau, weight, scratch;
+	std::vector<double> times, hist, stage, par, tau, weight, scratch;
 	std::vector<long long> row_ptr;
 	std::vector<int> src, cursor;
 	bool have_graph = false, have_past = false, have_int = false;
@@ -35,14 +35,14 @@ int jdde_net_create(const jdde_net_desc * d, jdde_net ** out)
 	jdde_net * h = new jdde_net;
 	h->desc = *d;
 	size_t const n = (size_t)d->n, cap = (size_t)d->ring_capacity, E = (size_t)d->n_edges;
-	h->times.assign(cap, 0.0); h->state.assign(cap*n, 0.0); h->diff.assign(cap*n, 0.0);
-	h->stage_state.assign(n, 0.0); h->stage_diff.assign(n, 0.0);
+	h->times.assign(cap, 0.0); h->hist.assign(2*cap*n, 0.0);
+	h->stage.assign(2*n, 0.0);
 	h->par.assign(n*(JDN_NPARAMS ? JDN_NPARAMS : 1), 0.0);
 	h->row_ptr.assign((size_t)(d->hi-d->lo)+1, 0); h->src.assign(E, 0); h->tau.assign(E, 0.0); h->weight.assign(E, 0.0);
 	h->cursor.assign(E, 0); h->scratch.assign(2*E, 0.0);
 	jdn_problem & P = h->P;
-	P.ctrl = &h->ctrl; P.times = h->times.data(); P.state = h->state.data(); P.diff = h->diff.data();
-	P.stage_state = h->stage_state.data(); P.stage_diff = h->stage_diff.data(); P.node_par = h->par.data();
+	P.ctrl = &h->ctrl; P.times = h->times.data(); P.hist = h->hist.data();
+	P.stage = h->stage.data(); P.node_par = h->par.data();
 	P.row_ptr = h->row_ptr.data(); P.src = h->src.data(); P.tau = h->tau.data(); P.weight = h->weight.data(); P.cursor = h->cursor.data();
 	P.n = d->n; P.lo = d->lo; P.hi = d->hi; P.cap = d->ring_capacity; P.n_node_params = d->n_node_params;
 	*out = h;
@@ -74,8 +74,11 @@ int jdde_net_set_past(jdde_net * h, int32_t k, const double * times, const doubl
 	if (k+1 > h->P.cap) return fail(h, JDDE_E_INVALID, "initial past does not fit into the ring; increase ring_capacity");
 	size_t const n = (size_t)h->desc.n;
 	memcpy(h->times.data(), times, k*sizeof(double));
-	memcpy(h->state.data(), states, k*n*sizeof(double));
-	memcpy(h->diff.data(), diffs, k*n*sizeof(double));
+	for (size_t r = 0; r < (size_t)k*n; r++)
+	{
+		h->hist[2*r] = states[r];
+		h->hist[2*r+1] = diffs[r];
+	}
 	std::fill(h->cursor.begin(), h->cursor.end(), k-2);
 	jdn_control & C = h->ctrl;
 	C.first = 0; C.current = k-1; C.t = times[k-1]; C.last_start = times[0]; C.status = JDDE_STATUS_OK; C.done = 1; C.commit_slot = -1;
@@ -146,8 +149,7 @@ int jdde_net_control(jdde_net * h)
 	if (slot >= 0)
 	{
 		size_t const n = (size_t)h->desc.n;
-		memcpy(&h->state[slot*n], h->stage_state.data(), n*sizeof(double));
-		memcpy(&h->diff[slot*n], h->stage_diff.data(), n*sizeof(double));
+		memcpy(&h->hist[2*slot*n], h->stage.data(), 2*n*sizeof(double));
 	}
 	h->launches += 2;
 	return JDDE_OK;
@@ -161,10 +163,9 @@ int jdde_net_poll(jdde_net * h, int32_t * done, double * t, int32_t * status)
 	return JDDE_OK;
 }
 
-int jdde_net_exchange_pointers(jdde_net * h, uint64_t * a, uint64_t * b, uint64_t * c)
+int jdde_net_exchange_pointers(jdde_net * h, uint64_t * a, uint64_t * c)
 {
-	if (a) *a = (uint64_t)(uintptr_t)h->stage_state.data();
-	if (b) *b = (uint64_t)(uintptr_t)h->stage_diff.data();
+	if (a) *a = (uint64_t)(uintptr_t)h->stage.data();
 	if (c) *c = (uint64_t)(uintptr_t)&h->ctrl.p_bits;
 	return JDDE_OK;
 }
@@ -173,7 +174,7 @@ int jdde_net_recent_state(jdde_net * h, double t, int32_t current_only, double *
 {
 	size_t const n = (size_t)h->desc.n;
 	for (size_t i = 0; i < n; i++)
-		out[i] = current_only ? h->state[(size_t)(h->ctrl.current & (h->P.cap-1))*n+i] : jdn::recent_state(h->P, t, (long long)i);
+		out[i] = current_only ? h->hist[2*((size_t)(h->ctrl.current & (h->P.cap-1))*n+i)] : jdn::recent_state(h->P, t, (long long)i);
 	return JDDE_OK;
 }
 

@@ -105,16 +105,15 @@ def test_node_partition_exchange_protocol(twin):
 	def exchange():
 		views = []
 		for E, lo, hi in engines:
-			s, d, p = E.exchange_pointers()
-			views.append((np.ctypeslib.as_array(ctypes.cast(s, ctypes.POINTER(ctypes.c_double)), (n,)),
-				np.ctypeslib.as_array(ctypes.cast(d, ctypes.POINTER(ctypes.c_double)), (n,)),
+			s, p = E.exchange_pointers()
+			views.append((np.ctypeslib.as_array(ctypes.cast(s, ctypes.POINTER(ctypes.c_double)), (2*n,)),
 				np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), (1,)), lo, hi))
-		for s, d, p, lo, hi in views:           # all-gather
-			for s2, d2, p2, lo2, hi2 in views:
-				s2[lo:hi], d2[lo:hi] = s[lo:hi], d[lo:hi]
-		pmax = max(v[2][0] for v in views)      # all-reduce(max)
+		for s, p, lo, hi in views:           # all-gather of the staged (state, diff) pairs
+			for s2, p2, lo2, hi2 in views:
+				s2[2*lo:2*hi] = s[2*lo:2*hi]
+		pmax = max(v[1][0] for v in views)      # all-reduce(max)
 		for v in views:
-			v[2][0] = pmax
+			v[1][0] = pmax
 
 	def run(begin):
 		for E, _, _ in engines:

@@ -7,11 +7,10 @@
  *
  *   - every delay is at least as long as a step (enforced: max_step <= smallest delay; a lookup into the step
  *     under way sets a flag and stops the integration), so the three stages of a node depend on the other nodes
- *     only through the HISTORY. All three stages, the new anchor and the error estimate of a node are therefore
- *     computed by one thread in ONE kernel (net_attempt_node) without any inter-node synchronisation;
- *   - per in-edge the delayed state is interpolated at the three stage times in one pass (the three lookups
- *     fall on the same two history rows: one set of gathers instead of three); the values for stages 2 and 3
- *     wait in a per-edge scratch;
+ *     only through the HISTORY. An attempted step is therefore two kernels without any inter-node synchronisation
+ *     inside: an EDGE-parallel lookup kernel (one thread per in-edge interpolates the delayed source state at the
+ *     three stage times in one pass — the three lookups share their two history rows — into a per-edge scratch),
+ *     then a NODE-parallel step kernel (stages, new anchor, error contribution from the scratch values);
  *   - the error norm is a max-reduction over nodes (block reduction + one atomic per block, then — with several
  *     GPUs — one all-reduce); accept/reject, the step-size controller, forget and the termination test run in a
  *     one-thread kernel (net_control) on the device, so that the host only polls a flag every few attempts;
@@ -80,11 +79,34 @@ JDN_FN double past_value(jdn_problem const & P, View const & V, int const ca, lo
 }
 
 /*
- * One attempted step (get_next_step, jitced_template.c:421-472) of node i: returns this node's contribution
- * |err|/(atol+rtol|y_new|) to the error norm (get_p, :474-498; negative if the contribution is to be skipped),
- * writes the node's part of the tentative anchor. `scratch` holds two doubles per edge.
+ * Lookup phase of one attempted step, ONE EDGE: the delayed state of the source node at the three stage times
+ * t + h/2, t + 3h/4, t + h (get_past_anchors + get_past_value, jitced_template.c:193-235, three times for this
+ * edge's call site, in the order the reference evaluates them). The three lookups fall on the same or neighbouring
+ * history rows, so they share their gathers. Results go to scratch[3e…3e+2]; the edge's cursor is updated.
+ * Edge-parallel: 10^7 independent threads for a 10^6-node network of in-degree 10.
  */
-JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h, long long const i, double * const scratch, int & pws)
+JDN_FN void lookup_edge(jdn_problem const & P, View const & V, double const h, long long const e, double * const scratch, int & pws)
+{
+	long long const j = P.src[e];
+	double const tau = P.tau[e];
+	double const d1 = (V.t_cur+0.5*h)-tau, d2 = (V.t_cur+0.75*h)-tau, d3 = (V.t_cur+h)-tau;
+	if (d3 > V.t_cur)
+		pws = 1;
+	int ca = walk(V, P.cursor[e], d1);
+	scratch[3*e] = past_value(P, V, ca, j, d1);
+	ca = walk(V, ca, d2);
+	scratch[3*e+1] = past_value(P, V, ca, j, d2);
+	ca = walk(V, ca, d3);
+	scratch[3*e+2] = past_value(P, V, ca, j, d3);
+	P.cursor[e] = ca;
+}
+
+/*
+ * Step phase, ONE NODE (get_next_step, jitced_template.c:421-472): the three stages with the delayed inputs from
+ * `scratch`, the node's part of the tentative anchor, and its contribution |err|/(atol+rtol|y_new|) to the error
+ * norm (get_p, :474-498; negative if it is to be skipped). Couplings are summed in the order of the edge list.
+ */
+JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h, long long const i, double const * const scratch)
 {
 	long long const row = i-P.lo;
 	long long const e0 = P.row_ptr[row], e1 = P.row_ptr[row+1];
@@ -97,37 +119,22 @@ JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h
 
 	double const t1 = V.t_cur+0.5*h, t2 = V.t_cur+0.75*h, t3 = V.t_cur+h;
 
-	/* stage 2: k_2 = f(t + h/2, y + h/2 k_1); the delayed inputs of stages 3 and 4 are interpolated alongside */
 	double const y1 = y + 0.5*h*k_1;
 	double acc = JDN_LOCAL(y1, t1, par);
 	for (long long e = e0; e < e1; e++)
-	{
-		long long const j = P.src[e];
-		double const tau = P.tau[e];
-		double const d1 = t1-tau, d2 = t2-tau, d3 = t3-tau;
-		if (d3 > V.t_cur)
-			pws = 1;
-		int ca = walk(V, P.cursor[e], d1);
-		double const H1 = past_value(P, V, ca, j, d1);
-		ca = walk(V, ca, d2);
-		scratch[2*e] = past_value(P, V, ca, j, d2);
-		ca = walk(V, ca, d3);
-		scratch[2*e+1] = past_value(P, V, ca, j, d3);
-		P.cursor[e] = ca;
-		acc += P.weight[e]*JDN_COUPLING(H1, y1);
-	}
+		acc += P.weight[e]*JDN_COUPLING(scratch[3*e], y1);
 	double const k_2 = acc;
 
 	double const y2 = y + 0.75*h*k_2;
 	acc = JDN_LOCAL(y2, t2, par);
 	for (long long e = e0; e < e1; e++)
-		acc += P.weight[e]*JDN_COUPLING(scratch[2*e], y2);
+		acc += P.weight[e]*JDN_COUPLING(scratch[3*e+1], y2);
 	double const k_3 = acc;
 
 	double const y_new = y + (h/9.) * (2*k_1+3*k_2+4*k_3);
 	acc = JDN_LOCAL(y_new, t3, par);
 	for (long long e = e0; e < e1; e++)
-		acc += P.weight[e]*JDN_COUPLING(scratch[2*e+1], y_new);
+		acc += P.weight[e]*JDN_COUPLING(scratch[3*e+2], y_new);
 	double const k_4 = acc;
 
 	double const error = fabs((5*k_1-6*k_2-8*k_3+9*k_4) * (h/72.));

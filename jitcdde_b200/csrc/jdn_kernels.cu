@@ -2,10 +2,10 @@
  * jdn_kernels.cu — kernel image of the network engine, compiled per (local, coupling) function pair by
  * jitcdde_b200/_build.py with -DJDN_NPARAMS=… -DJDN_RHS_FILE="net_<key>.inc" for sm_100a.
  *
- * jdn_k_attempt: one thread per owned node, grid = ceil(n_owned / JDN_BLOCK) (10^6 nodes → 3907 blocks of 256:
- * 26 blocks per SM, several waves); the anchor times live in shared memory for the bracket search of every edge;
- * the per-node error contributions are max-reduced per block (warp shuffles, then shared memory) and merged with
- * one atomicMax per block.
+ * jdn_k_lookup: one thread per in-edge (10^7 threads for 10^6 nodes of in-degree 10); the anchor times live in
+ * shared memory for the bracket search. jdn_k_attempt: one thread per owned node (3907 blocks of 256 for 10^6
+ * nodes: 26 blocks per SM, several waves); the per-node error contributions are max-reduced per block (warp
+ * shuffles, then shared memory) and merged with one atomicMax per block.
  */
 #include "jdn_engine.cuh"
 
@@ -15,31 +15,46 @@
 
 extern "C" __device__ const jdn_image_desc_t jdn_image_desc = { JDN_IMAGE_MAGIC, JDDE_ABI_VERSION, JDN_NPARAMS, JDN_BLOCK };
 
+/* lookup phase: one thread per edge of the owned nodes */
 extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
-jdn_k_attempt(jdn_problem const P, double * const scratch)
+jdn_k_lookup(jdn_problem const P, double * const scratch, long long const n_edges)
 {
 	extern __shared__ double s_times[];      /* cap doubles */
-	__shared__ double s_max[JDN_BLOCK/32];
 	jdn_control const & C = *P.ctrl;
 	if (C.done)
 		return;
 	for (int k = threadIdx.x; k < P.cap; k += blockDim.x)
 		s_times[k] = P.times[k];
 	__syncthreads();
-
 	jdn::View V = jdn::view_of(P);
 	V.times = s_times;
+	long long const e = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if (e < n_edges)
+	{
+		int pws = 0;
+		jdn::lookup_edge(P, V, C.h, e, scratch, pws);
+		if (pws)
+			P.ctrl->pws = 1;
+	}
+}
+
+/* step phase: one thread per owned node */
+extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
+jdn_k_attempt(jdn_problem const P, double const * const scratch)
+{
+	__shared__ double s_max[JDN_BLOCK/32];
+	jdn_control const & C = *P.ctrl;
+	if (C.done)
+		return;
+	jdn::View const V = jdn::view_of(P);
 	long long const i = P.lo + (long long)blockIdx.x*blockDim.x + threadIdx.x;
 	double contribution = -1.0;
-	int pws = 0;
 	if (i < P.hi)
 	{
-		contribution = jdn::attempt_node(P, V, C.h, i, scratch, pws);
+		contribution = jdn::attempt_node(P, V, C.h, i, scratch);
 		if (!(contribution >= 0.0))      /* skipped (0/0) or NaN: ignored by the reference's `x > p` test */
 			contribution = -1.0;
 	}
-	if (pws)
-		P.ctrl->pws = 1;
 	for (int o = 16; o > 0; o >>= 1)
 		contribution = fmax(contribution, __shfl_down_sync(0xffffffffu, contribution, o));
 	if ((threadIdx.x & 31) == 0)

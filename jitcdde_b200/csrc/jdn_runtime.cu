@@ -19,7 +19,7 @@ struct jdde_net
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	cudaLibrary_t lib = nullptr;
-	cudaKernel_t k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr;
+	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr;
 	int block = 256;
 	jdn_problem P{};
 	double * scratch = nullptr, * d_out = nullptr, * d_par = nullptr;
@@ -115,7 +115,7 @@ int jdde_net_create(const jdde_net_desc * d, jdde_net ** out)
 	if ((rc = nalloc(h, &h->d_tau, E))) return bail(rc);
 	if ((rc = nalloc(h, &h->d_weight, E))) return bail(rc);
 	if ((rc = nalloc(h, &P.cursor, E))) return bail(rc);
-	if ((rc = nalloc(h, &h->scratch, 2*E))) return bail(rc);
+	if ((rc = nalloc(h, &h->scratch, 3*E))) return bail(rc);
 	if ((rc = nalloc(h, &h->d_out, n))) return bail(rc);
 	P.node_par = h->d_par; P.row_ptr = h->d_row_ptr; P.src = h->d_src; P.tau = h->d_tau; P.weight = h->d_weight;
 	if (cudaMemsetAsync(P.ctrl, 0, sizeof(jdn_control), h->stream) != cudaSuccess) return bail(nfail(h, JDDE_E_CUDA, "cudaMemset failed"));
@@ -153,7 +153,7 @@ int jdde_net_load_image(jdde_net * h, const void * image, size_t len)
 	if (d.n_node_params != h->desc.n_node_params) return nfail(h, JDDE_E_IMAGE, "image does not match the descriptor (node parameters)");
 	h->block = d.block;
 	struct { const char * name; cudaKernel_t * slot; } const table[] = {
-		{"jdn_k_attempt", &h->k_attempt}, {"jdn_k_control", &h->k_control}, {"jdn_k_commit", &h->k_commit},
+		{"jdn_k_lookup", &h->k_lookup}, {"jdn_k_attempt", &h->k_attempt}, {"jdn_k_control", &h->k_control}, {"jdn_k_commit", &h->k_commit},
 		{"jdn_k_begin", &h->k_begin}, {"jdn_k_recent_state", &h->k_recent}, {"jdn_k_set_past", &h->k_set_past},
 	};
 	for (auto const & entry : table)
@@ -262,8 +262,11 @@ int jdde_net_attempt(jdde_net * h)
 {
 	int rc = nready_run(h);
 	if (rc) return rc;
+	long long E = h->desc.n_edges;
+	void * largs[] = { &h->P, &h->scratch, &E };
+	if (E && (rc = nlaunch(h, h->k_lookup, E, h->block, (size_t)h->P.cap*sizeof(double), largs))) return rc;
 	void * args[] = { &h->P, &h->scratch };
-	return nlaunch(h, h->k_attempt, h->desc.hi-h->desc.lo, h->block, (size_t)h->P.cap*sizeof(double), args);
+	return nlaunch(h, h->k_attempt, h->desc.hi-h->desc.lo, h->block, 0, args);
 }
 
 int jdde_net_control(jdde_net * h)

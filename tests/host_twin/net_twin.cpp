@@ -39,7 +39,7 @@ int jdde_net_create(const jdde_net_desc * d, jdde_net ** out)
 	h->stage.assign(2*n, 0.0);
 	h->par.assign(n*(JDN_NPARAMS ? JDN_NPARAMS : 1), 0.0);
 	h->row_ptr.assign((size_t)(d->hi-d->lo)+1, 0); h->src.assign(E, 0); h->tau.assign(E, 0.0); h->weight.assign(E, 0.0);
-	h->cursor.assign(E, 0); h->scratch.assign(2*E, 0.0);
+	h->cursor.assign(E, 0); h->scratch.assign(3*E, 0.0);
 	jdn_problem & P = h->P;
 	P.ctrl = &h->ctrl; P.times = h->times.data(); P.hist = h->hist.data();
 	P.stage = h->stage.data(); P.node_par = h->par.data();
@@ -125,12 +125,16 @@ int jdde_net_attempt(jdde_net * h)
 	h->launches++;
 	if (C.done) return JDDE_OK;
 	jdn::View V = jdn::view_of(h->P);
+	for (long long e = 0; e < h->desc.n_edges; e++)
+	{
+		int pws = 0;
+		jdn::lookup_edge(h->P, V, C.h, e, h->scratch.data(), pws);
+		if (pws) C.pws = 1;
+	}
 	double m = -1.0;
 	for (long long i = h->P.lo; i < h->P.hi; i++)
 	{
-		int pws = 0;
-		double c = jdn::attempt_node(h->P, V, C.h, i, h->scratch.data(), pws);
-		if (pws) C.pws = 1;
+		double c = jdn::attempt_node(h->P, V, C.h, i, h->scratch.data());
 		if (c >= 0.0 && c > m) m = c;
 	}
 	if (m > 0.0)

@@ -350,6 +350,8 @@ def gpu_arm(args):
 	e2e_value = e2e_accepted/(e2e_ms*1e-3)
 
 	peak, peak_source = measured_peaks()
+	from jitcdde_b200._capi import measure_fp64_peak
+	fp64_peak = measure_fp64_peak(local_rank)      # FLOP/s, DFMA microbenchmark on this GPU (not in MEASURED_PEAKS.json)
 	# dominant kernel = jdde_k_integrate, one launch per step: algorithmic bytes of this rank's launches ÷ their duration
 	achieved = (total_accepted/world*BYTES_PER_STEP)/(ms*1e-3)/1e9
 	line = {
@@ -362,7 +364,8 @@ def gpu_arm(args):
 		"clocks": clocks.summary(),
 		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": TRAFFIC_PER_LAUNCH,
 			"kernel": "jdde_k_integrate", "algorithmic_bytes_per_accepted_step": BYTES_PER_STEP, "peak_source": peak_source,
-			"fp64_tflops_algorithmic": value/world*FLOPS_PER_STEP/1e12},
+			"fp64_tflops_algorithmic": value/world*FLOPS_PER_STEP/1e12, "fp64_peak_tflops_measured": fp64_peak/1e12,
+			"fp64_frac": value/world*FLOPS_PER_STEP/fp64_peak},
 		"accepted_steps_per_member_per_step": total_accepted/(members*world*args.steps),
 	}
 	if rank == 0 and world == 1 and not args.no_cpu:

@@ -194,6 +194,10 @@ int jdde_set_attempt_budget(jdde_handle * h, int64_t attempts);
 int jdde_host_alloc(size_t bytes, void ** out);
 int jdde_host_free(void * p);
 
+/* FP64 FMA throughput of the device in FLOP/s, measured with the microbenchmark image `image` (csrc/jdde_peak.cu):
+ * the denominator for the FP64 fraction that bench.py reports beside the bandwidth roofline. */
+int jdde_measure_fp64_peak(int32_t device, const void * image, size_t len, double * flops);
+
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t jdde_launch_count(const jdde_handle * h);
 /* Device pointer of the last integration result [n_members][n] as an integer address (for zero-copy interop). */

@@ -193,3 +193,14 @@ def build_net_image(program, block=256, force=False, verbose=False):
 		raise RuntimeError(f"nvcc failed:\n{result.stderr}\ncommand: {' '.join(cmd)}")
 	os.replace(path + ".tmp", path)
 	return path
+
+
+def build_peak_image(force=False):
+	"""cubin of the FP64 throughput microbenchmark (csrc/jdde_peak.cu)"""
+	os.makedirs(CACHE, exist_ok=True)
+	src = os.path.join(CSRC, "jdde_peak.cu")
+	path = os.path.join(CACHE, f"jdde_peak_{_sources_hash([src])[:16]}.cubin")
+	if not os.path.exists(path) or force:
+		subprocess.run([nvcc(), "-cubin", "-O3", "-lineinfo", *ARCH, src, "-o", path + ".tmp"], check=True)
+		os.replace(path + ".tmp", path)
+	return path

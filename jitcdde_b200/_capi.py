@@ -76,6 +76,7 @@ SIGNATURES = {
 	"jdde_set_attempt_budget": (ctypes.c_int, [_H, ctypes.c_int64]),
 	"jdde_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
 	"jdde_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+	"jdde_measure_fp64_peak": (ctypes.c_int, [ctypes.c_int32, ctypes.c_void_p, ctypes.c_size_t, c_double_p]),
 	"jdde_launch_count": (ctypes.c_int64, [_H]),
 	"jdde_device_result": (ctypes.c_uint64, [_H]),
 }
@@ -132,6 +133,18 @@ def load_library(path=None):
 
 class EngineError(RuntimeError):
 	pass
+
+
+def measure_fp64_peak(device=0):
+	"""FP64 FMA throughput of the device in FLOP/s (microbenchmark csrc/jdde_peak.cu)"""
+	lib = load_library()
+	with open(_build.build_peak_image(), "rb") as f:
+		image = f.read()
+	flops = ctypes.c_double()
+	rc = lib.jdde_measure_fp64_peak(device, image, len(image), ctypes.byref(flops))
+	if rc:
+		raise EngineError(f"jdde_measure_fp64_peak failed ({rc}): {lib.jdde_last_error(None).decode()}")
+	return flops.value
 
 
 class _PinnedBuffer:

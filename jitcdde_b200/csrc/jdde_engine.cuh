@@ -1158,43 +1158,114 @@ JD_FN double scalar_product(Member const & M, double const threshold, int const 
 	return sum;
 }
 
-/* orthonormalise, jitced_template.c:846-878 incl. subtract_from_past (:832-844), scale_past (:819-830) */
+/*
+ * One streaming pass over all anchors for orthonormalise: optionally  v[sub_i] -= sub_factor·v[sub_j]
+ * (subtract_from_past, jitced_template.c:832-844) and/or  v[scale_i] *= scale_factor  (scale_past, :819-830) on every
+ * anchor, and — on the values after these updates — the scalar product <v[acc_1], v[acc_2]> (:773-817). An anchor is
+ * updated when the stream reaches it; the segment ending there then has both its anchors up to date, so every product
+ * and every sum is formed from the same operands in the same order as by the reference's separate loops.
+ * Fusing turns the 2+3+4+… full passes per call into about a third of them (the kernel is bound by this traffic).
+ */
+JD_FN double orthonormalise_pass(Member & M, double const threshold, int const sub_i, int const sub_j, double const sub_factor,
+	int const scale_i, double const scale_factor, int const acc_1, int const acc_2)
+{
+	double sum = 0;
+	bool partial_done = false;
+	for (int k = M.first; k <= M.last; k++)
+	{
+		double * const w = M.slot(k);
+		if (sub_i >= 0)
+			for (int c = 0; c < JD_NBASIC; c++)
+			{
+				w[1+sub_i+c]      -= sub_factor*w[1+sub_j+c];
+				w[1+JD_N+sub_i+c] -= sub_factor*w[1+JD_N+sub_j+c];
+			}
+		if (scale_i >= 0)
+			for (int c = 0; c < JD_NBASIC; c++)
+			{
+				w[1+scale_i+c]      *= scale_factor;
+				w[1+JD_N+scale_i+c] *= scale_factor;
+			}
+		if (acc_1 < 0 || k == M.first)
+			continue;
+		double const * const v = M.slot(k-1);
+		double const q = w[0] - v[0];
+		double m[4][4];
+		if (!partial_done)
+		{
+			if (w[0] < threshold)
+				continue;
+			partial_sp_matrix(q, (threshold - w[0]) / q, m);
+			partial_done = true;
+		}
+		else
+			sp_matrix(q, m);
+		double const * const vector_1[4] = { v+1+acc_1, v+1+JD_N+acc_1, w+1+acc_1, w+1+JD_N+acc_1 };
+		double const * const vector_2[4] = { v+1+acc_2, v+1+JD_N+acc_2, w+1+acc_2, w+1+JD_N+acc_2 };
+		double part = 0;
+#if defined(JD_FAST)
+		/* production build: Σ_ij m_ij (Σ_index v1_i·v2_j) — 16 independent short chains instead of one chain of
+		 * 96 dependent additions. Another summation order than the reference's, i.e. other rounding: Lyapunov
+		 * results are compared statistically for this build; the verification build keeps the order. */
+		double row[4] = { 0.0, 0.0, 0.0, 0.0 };
+		JD_UNROLL
+		for (int i = 0; i < 4; i++)
+		{
+			JD_UNROLL
+			for (int j = 0; j < 4; j++)
+			{
+				double dot = 0;
+				JD_UNROLL
+				for (int index = 0; index < JD_NBASIC; index++)
+					dot += vector_1[i][index] * vector_2[j][index];
+				row[i] += m[i][j]*dot;
+			}
+		}
+		part = (row[0]+row[1])+(row[2]+row[3]);
+#else
+		for (int i = 0; i < 4; i++)
+			for (int j = 0; j < 4; j++)
+				for (int index = 0; index < JD_NBASIC; index++)
+					part += m[i][j] * vector_1[i][index] * vector_2[j][index];
+#endif
+		sum += part;
+	}
+	return sum;
+}
+
+/* orthonormalise, jitced_template.c:846-878: modified Gram–Schmidt on the separation functions, in place over all
+ * anchors; norms[i] = norm of vector i after orthogonalisation, before normalisation. The sequence of operations is
+ * the reference's; consecutive loops over the anchors are fused (orthonormalise_pass). */
 JD_FN void orthonormalise(Member & M, int const n_lyap, double const delay, double * const norms)
 {
 	double const threshold = M.slot(M.current)[0] - delay;
+	int pending_scale = -1;           /* vector whose normalisation still has to be applied to the anchors */
+	double pending_factor = 1.0;
 	for (int i = 0; i < n_lyap; i++)
 	{
 		int const bi = (i+1)*JD_NBASIC;
+		int sub_j = -1;
+		double sub_factor = 0.0;
 		for (int j = 0; j < i; j++)
 		{
 			int const bj = (j+1)*JD_NBASIC;
-			double const sp = scalar_product(M, threshold, bi, bj);
-			for (int k = M.first; k <= M.last; k++)
-			{
-				double * const a = M.slot(k);
-				for (int c = 0; c < JD_NBASIC; c++)
-				{
-					a[1+bi+c]      -= sp*a[1+bj+c];
-					a[1+JD_N+bi+c] -= sp*a[1+JD_N+bj+c];
-				}
-			}
+			/* sp = <v_i, v_j> after the previous subtraction; the scaling of v_{i-1} rides on the first pass */
+			double const sp = orthonormalise_pass(M, threshold, sub_j >= 0 ? bi : -1, sub_j, sub_factor, pending_scale, pending_factor, bi, bj);
+			pending_scale = -1;
+			sub_j = bj;
+			sub_factor = sp;
 		}
-		double const norm = sqrt(scalar_product(M, threshold, bi, bi));
+		double const norm = sqrt(orthonormalise_pass(M, threshold, sub_j >= 0 ? bi : -1, sub_j, sub_factor, pending_scale, pending_factor, bi, bi));
+		pending_scale = -1;
 		if (norm > JD_NORM_THRESHOLD)
 		{
-			double const factor = 1./norm;
-			for (int k = M.first; k <= M.last; k++)
-			{
-				double * const a = M.slot(k);
-				for (int c = 0; c < JD_NBASIC; c++)
-				{
-					a[1+bi+c]      *= factor;
-					a[1+JD_N+bi+c] *= factor;
-				}
-			}
+			pending_scale = bi;
+			pending_factor = 1./norm;
 		}
 		norms[i] = norm;
 	}
+	if (pending_scale >= 0)
+		orthonormalise_pass(M, threshold, -1, -1, 0.0, pending_scale, pending_factor, -1, -1);
 }
 #endif
 

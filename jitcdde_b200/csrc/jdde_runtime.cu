@@ -779,6 +779,42 @@ int jdde_host_free(void * p)
 	return cudaFreeHost(p) == cudaSuccess ? JDDE_OK : JDDE_E_CUDA;
 }
 
+int jdde_measure_fp64_peak(int32_t device, const void * image, size_t len, double * flops)
+{
+	if (!image || !len || !flops)
+		return fail(nullptr, JDDE_E_INVALID, "null argument");
+	JD_CUDA(nullptr, cudaSetDevice(device));
+	cudaLibrary_t lib;
+	JD_CUDA(nullptr, cudaLibraryLoadData(&lib, image, nullptr, nullptr, 0, nullptr, nullptr, 0));
+	cudaKernel_t kernel;
+	JD_CUDA(nullptr, cudaLibraryGetKernel(&kernel, lib, "jdde_k_fp64_peak"));
+	cudaDeviceProp prop;
+	JD_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+	int const block = 256, grid = prop.multiProcessorCount*16, iterations = 4096;
+	double * out = nullptr;
+	JD_CUDA(nullptr, cudaMalloc((void **)&out, (size_t)grid*block*sizeof(double)));
+	cudaEvent_t e0, e1;
+	JD_CUDA(nullptr, cudaEventCreate(&e0));
+	JD_CUDA(nullptr, cudaEventCreate(&e1));
+	int it = iterations; double a = 1.0000001, b = 1e-9;
+	void * args[] = { &out, &it, &a, &b };
+	float best = 1e30f;
+	for (int r = 0; r < 6; r++)
+	{
+		JD_CUDA(nullptr, cudaEventRecord(e0, 0));
+		JD_CUDA(nullptr, cudaLaunchKernel((const void *)kernel, dim3(grid), dim3(block), args, 0, 0));
+		JD_CUDA(nullptr, cudaEventRecord(e1, 0));
+		JD_CUDA(nullptr, cudaEventSynchronize(e1));
+		float ms = 0;
+		JD_CUDA(nullptr, cudaEventElapsedTime(&ms, e0, e1));
+		if (r > 0 && ms < best)
+			best = ms;
+	}
+	*flops = 2.0*8.0*iterations*(double)grid*block/(best*1e-3);
+	cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out); cudaLibraryUnload(lib);
+	return JDDE_OK;
+}
+
 int64_t jdde_launch_count(const jdde_handle * h) { return h ? h->launches : 0; }
 uint64_t jdde_device_result(const jdde_handle * h) { return h ? (uint64_t)(uintptr_t)h->d_out : 0; }
 

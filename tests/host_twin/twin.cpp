@@ -358,6 +358,7 @@ int jdde_clear_status(jdde_handle * h, int32_t code)
 int jdde_set_attempt_budget(jdde_handle * h, int64_t attempts) { if (attempts < 1) return fail(h, JDDE_E_INVALID, "budget must be positive"); h->budget = attempts; return JDDE_OK; }
 int jdde_host_alloc(size_t bytes, void ** out) { *out = malloc(bytes ? bytes : 1); return *out ? JDDE_OK : JDDE_E_NOMEM; }
 int jdde_host_free(void * p) { free(p); return JDDE_OK; }
+int jdde_measure_fp64_peak(int32_t, const void *, size_t, double * flops) { if (flops) *flops = 0.0; return JDDE_E_CUDA; }
 int64_t jdde_launch_count(const jdde_handle * h) { return h->launches; }
 uint64_t jdde_device_result(const jdde_handle *) { return 0; }
 

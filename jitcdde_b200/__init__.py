@@ -12,8 +12,8 @@ The integrator runs as CUDA kernels for sm_100a behind a C ABI
 (`n_members=N`) are the data-parallel axis. Scope and design: DESIGN.md.
 """
 
-from ._symbols import anchors, current_y, dy, past_dy, past_y, quadrature, t, y
-from ._jitcdde import UnsuccessfulIntegration, jitcdde, jitcdde_lyap, _find_max_delay, _propagate_delays
+from ._symbols import anchors, current_y, dy, input, past_dy, past_y, quadrature, t, y  # noqa: A004
+from ._jitcdde import UnsuccessfulIntegration, jitcdde, jitcdde_input, jitcdde_lyap, _find_max_delay, _propagate_delays
 from ._codegen import get_delays as _get_delays
 from ._capi import pinned_empty
 
@@ -28,12 +28,10 @@ def _out_of_scope(name):
 	stub.__name__ = name
 	return stub
 
-jitcdde_input = _out_of_scope("jitcdde_input")
 jitcdde_restricted_lyap = _out_of_scope("jitcdde_restricted_lyap")
 jitcdde_transversal_lyap = _out_of_scope("jitcdde_transversal_lyap")
-input = _out_of_scope("input")  # noqa: A001
 
 __all__ = [
-	"UnsuccessfulIntegration", "anchors", "current_y", "dy", "jitcdde", "jitcdde_lyap",
+	"UnsuccessfulIntegration", "anchors", "current_y", "dy", "input", "jitcdde", "jitcdde_input", "jitcdde_lyap",
 	"past_dy", "past_y", "quadrature", "t", "y", "jitcdde_network", "shard", "gather_members", "pinned_empty",
 ]

@@ -18,8 +18,8 @@ import numpy as np
 import sympy
 
 from . import _build, _capi, _codegen
-from ._past import Past
-from ._symbols import anchors, current_y, t
+from ._past import Anchor, Past, join
+from ._symbols import anchors, current_y, input_base_n, input_shift, t
 
 _default_min_step = 1e-10
 
@@ -621,3 +621,128 @@ class jitcdde_lyap(jitcdde):
 		if self.n_members == 1:
 			return state[0].copy(), lyaps[0].copy(), float(total[0])
 		return state, lyaps, total
+
+
+class jitcdde_input(jitcdde):
+	"""
+	Integrate the DDE (or ODE) with an external input (reference: _jitcdde.py:1519-1659). The input — a sequence of
+	anchors (time, state, diff) describing a cubic Hermite spline, e.g. what `get_state()` returns — is stored in the
+	past of dummy dynamical variables, which on the GPU are ordinary components of the anchors: `input(i)` in the
+	equations becomes a delayed lookup of component n+i. The integration must start at t = 0.
+	"""
+
+	def __init__(self, f_sym=(), input=None, **kwargs):  # noqa: A002
+		if input is None:
+			raise ValueError("You must define an input; otherwise just use plain jitcdde.")
+		input = [Anchor(float(a[0]), np.array(a[1], dtype=float), np.array(a[2], dtype=float)) for a in input]  # noqa: A001
+		if input[0].time > 0:
+			warn(f"Your input past does not begin at t=0 but at t={input[0].time}. Values before the beginning of the past will be extrapolated. You very likely do not want this.", stacklevel=2)
+		n_input = len(input[0].state)
+
+		basic = jitcdde._handle_input(self, f_sym, kwargs.pop("n", None))()
+		self.input_base_n = len(basic)
+		self.input_duration = input[-1].time
+		substitutions = {input_base_n: self.input_base_n, input_shift: self.input_duration}
+
+		self.regular_past = Past(n=self.input_base_n)
+		self.input_past = Past(n=n_input)
+		for anchor in input:
+			self.input_past.add((anchor.time-self.input_duration, anchor.state, anchor.diff))
+
+		# dummy dynamical variables with the constant derivative of the last input point (:1561-1562)
+		f_full = [sympy.sympify(e).subs(substitutions) for e in basic] + [sympy.Float(d) for d in input[-1].diff]
+
+		if kwargs.setdefault("delays", None) is not None:
+			kwargs["delays"] = [*kwargs["delays"], self.input_duration]
+		self._joined = None
+		super().__init__(f_full, n=len(f_full), **kwargs)
+
+	@property
+	def max_delay(self):
+		return jitcdde.max_delay.fget(self)
+
+	@max_delay.setter
+	def max_delay(self, new_max_delay):
+		if new_max_delay is not None:
+			assert new_max_delay >= 0.0, "Negative maximum delay."
+			new_max_delay = max(new_max_delay, self.input_duration)
+		self._max_delay = new_max_delay
+
+	def initiate_past(self):
+		pass
+
+	@property
+	def past(self):
+		if self._joined is None:
+			assert len(self.regular_past) > 1, "You need to add at least two past points first. Usually this means that you did not set an initial past at all."
+			if self.regular_past[-1].time != 0:
+				raise ValueError("For jitcdde_input, the initial past must end at t=0.")
+			self._joined = join(self.regular_past, self.input_past)
+		return self._joined
+
+	@past.setter
+	def past(self, value):
+		raise AssertionError("For jitcdde_input, the past attribute should not be directly set.")
+
+	def add_past_point(self, time, state, derivative):
+		self._joined = None
+		self.reset_integrator(idc_unhandled=True)
+		self.regular_past.add((time, state, derivative))
+
+	def add_past_points(self, anchors):
+		self._joined = None
+		self.reset_integrator(idc_unhandled=True)
+		for anchor in anchors:
+			self.regular_past.add(anchor)
+
+	def constant_past(self, state, time=0):
+		self._joined = None
+		self.reset_integrator(idc_unhandled=True)
+		self.regular_past.constant(state, time)
+
+	def past_from_function(self, function, times_of_interest=None, max_anchors=100, tol=5):
+		self._joined = None
+		self.reset_integrator(idc_unhandled=True)
+		if times_of_interest is None:
+			times_of_interest = np.linspace(-self.max_delay, 0, 10)
+		else:
+			times_of_interest = sorted(times_of_interest)
+		self.regular_past.from_function(function, times_of_interest, max_anchors, tol)
+
+	def get_state(self, member=0):
+		self._initiate()
+		times, states, diffs = self._engine.get_state(member)
+		self._joined = None
+		self.regular_past.clear()
+		for k in range(len(times)):
+			list.append(self.regular_past, Anchor(times[k], states[k][:self.input_base_n].copy(), diffs[k][:self.input_base_n].copy()))
+		return self.regular_past
+
+	def purge_past(self):
+		self._joined = None
+		self.regular_past.clear()
+		self.reset_integrator(idc_unhandled=True)
+
+	def integrate(self, target_time, out=None):
+		if np.any(np.asarray(target_time) > self.input_duration):
+			warn("Integrating beyond duration of input. From now on, the input will be extrapolated. You very likely do not want this. Instead define a longer input or stop integrating.", stacklevel=2)
+		return super().integrate(target_time)[..., :self.input_base_n]
+
+	def integrate_blindly(self, *args, **kwargs):
+		return super().integrate_blindly(*args, **kwargs)[..., :self.input_base_n]
+
+	def step_on_discontinuities(self, *args, **kwargs):
+		raise NotImplementedError("Stepping on discontinuities is not implemented for input yet. Use integrate_blindly or adjust_diff instead.")
+
+	def adjust_diff(self, shift_ratio=1e-4):
+		minima, maxima = super().adjust_diff(shift_ratio)
+		return minima[..., :self.input_base_n], maxima[..., :self.input_base_n]
+
+	def jump(self, amplitude, *args, **kwargs):
+		if np.ndim(amplitude) == 0:
+			amplitude = np.full(self.input_base_n, amplitude, dtype=float)
+		amplitude = np.asarray(amplitude, dtype=float)
+		assert amplitude.shape == (self.input_base_n,)
+		extended_amplitude = np.hstack((amplitude, np.zeros(self.input_past.n)))
+		minima, maxima = super().jump(extended_amplitude, *args, **kwargs)
+		return minima[..., :self.input_base_n], maxima[..., :self.input_base_n]

@@ -171,3 +171,27 @@ class Past(list):
 			states[:, j, :] = a.state
 			diffs[:, j, :] = a.diff
 		return times, states, diffs
+
+
+def _evaluate(spline, time):
+	"""(state, diff) of a single-trajectory spline at `time`; outside its range the first/last segment is extrapolated"""
+	times = np.array([a.time for a in spline], dtype=float)
+	hit = np.nonzero(times == time)[0]
+	if len(hit):
+		return spline[hit[0]].state, spline[hit[0]].diff
+	i = int(np.clip(np.searchsorted(times, time, side="right")-1, 0, len(spline)-2))
+	return _hermite(time, spline[i], spline[i+1])
+
+
+def join(*splines):
+	"""
+	Glue splines along the component axis (chspy.join, used by the reference at _jitcdde.py:1598): the result has
+	anchors at the union of all anchor times; a spline without an anchor at one of these times contributes its
+	interpolated (outside its range: extrapolated) value and derivative.
+	"""
+	times = sorted({float(anchor.time) for spline in splines for anchor in spline})
+	joined = Past(n=sum(spline.n for spline in splines))
+	for time in times:
+		parts = [_evaluate(spline, time) for spline in splines]
+		list.append(joined, Anchor(time, np.hstack([p[0] for p in parts]), np.hstack([p[1] for p in parts])))
+	return joined

@@ -65,3 +65,17 @@ def quadrature(integrand, variable, lower, upper, nsteps=20, method="gauss"):
 			)
 	else:
 		raise NotImplementedError(f"I know no integration method named {method}.")
+
+
+#: placeholders resolved by `jitcdde_input` (reference: _jitcdde.py:1509-1510)
+input_shift = sympy.Symbol("external_input", real=True, negative=False)
+input_base_n = sympy.Symbol("input_base_n", integer=True, negative=False)
+
+
+def input(index, time=t):  # noqa: A001
+	"""External input for `jitcdde_input` (/root/reference/jitcdde/_jitcdde.py:1511-1517): component `index` of the
+	input at `time` (default: now). Expands to a delayed lookup of a dummy dynamical variable."""
+	if time != t:
+		from warnings import warn
+		warn("Do not use delayed inputs unless you also have undelayed inputs (otherwise you can just shift your time frame). If you use delayed and undelayed inputs, you have to rely on automatic delay detection or explicitly add `input[-1].time+delay` to the delays (and consider it as a max_delay) for each delayed input.", stacklevel=2)
+	return y(index+input_base_n, time-input_shift)

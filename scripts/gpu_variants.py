@@ -3,8 +3,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from jitcdde_b200 import _build, _capi
-from oracle import oracle
+
 from tests import systems
+DEFAULTS = dict(atol=1e-10, rtol=1e-5, first_step=1.0, min_step=1e-10, max_step=10.0, decrease_threshold=1.1, increase_threshold=0.5, safety_factor=0.9, max_factor=5.0, min_factor=0.2, pws_factor=3, pws_atol=0.0, pws_rtol=1e-5, pws_max_iterations=10, pws_base_increase_chance=0.1)
 
 N = int(os.environ.get("MEMBERS", 1250000)); STEPS = int(os.environ.get("STEPS", 20)); WARM = int(os.environ.get("WARM", 13))
 prog = systems.program(systems.mackey_glass()); pars = systems.mg_grid(N)
@@ -17,7 +18,7 @@ for spec in sys.argv[1:]:
     image = _build.build_image(prog, mode=opts.get("mode", "fast"), block=block, extra_flags=tuple(flags))
     E = _capi.Engine(1, 1, prog.n_sites, 2, N, ring_capacity=cap); E.load_image(image)
     E.set_past(np.array([-1.0, 0.0]), np.ones((2, 1)), np.zeros((2, 1))); E.set_parameters(pars)
-    E.set_integration_parameters(25.0, **oracle.DEFAULTS)
+    E.set_integration_parameters(25.0, **DEFAULTS)
     E.step_on_discontinuities(pars[:, 1:2].copy()); t0 = E.get_t()
     T0 = 30.0
     for k in range(1, WARM+1): E.integrate(T0+10.0*k, fetch=False)

@@ -181,6 +181,19 @@ def golden_kuramoto():
 	save("kuramoto", **past_arrays(past), blind=blind, offsets=offsets, samples=samples, accepted=C.accepted, rejected=C.rejected)
 
 
+def golden_data_input():
+	"""the extended system and joined past that jitcdde_input hands to the core (reference: _jitcdde.py:1519-1659)"""
+	prog, past, max_delay = systems.data_input_program()
+	roots = roots_from(oracle.build(prog))
+	core = make_core(prog, "ref_data_input", past)
+	C = controller.Controller(core, max_delay, root_mode=1, roots=roots)
+	mi, ma = C.adjust_diff()
+	times = np.linspace(0, 70, 36)[1:]
+	samples = np.array([C.integrate(T)[:2] for T in times])
+	save("data_input", **past_arrays(past), adjust_diff_min=mi[:2], adjust_diff_max=ma[:2], times=times, samples=samples,
+		accepted=C.accepted, rejected=C.rejected, max_delay=max_delay)
+
+
 def golden_lyap():
 	# Mackey–Glass with 3 exponents (limit cycle: deterministic, non-chaotic), cf. examples/mackey_glass_lyap.py
 	system = systems.mackey_glass(control=False)
@@ -226,10 +239,7 @@ def golden_lyap():
 
 if __name__ == "__main__":
 	assert build_ref.reference_available(), "run this where /root/reference exists"
-	golden_roessler()
-	golden_mg_ensemble()
-	golden_neutral()
-	golden_state_dependent()
-	golden_ode()
-	golden_kuramoto()
-	golden_lyap()
+	makers = dict(roessler=golden_roessler, mg_ensemble=golden_mg_ensemble, neutral=golden_neutral, state_dependent=golden_state_dependent,
+		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input)
+	for name in sys.argv[1:] or makers:      # optional arguments: only these fixtures
+		makers[name]()

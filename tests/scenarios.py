@@ -148,8 +148,20 @@ def roessler_lyap(g, **kw):
 	return _lyap_run(DDE, g)
 
 
+def data_input(g, **kw):
+	"""jitcdde_input (examples/data_input.py): the input spline lives in dummy components of the anchors"""
+	from jitcdde_b200 import jitcdde_input
+	system = systems.data_input()
+	DDE = jitcdde_input(system["f"], system["input"], verbose=False, **kw)
+	DDE.constant_past(system["initial"])
+	mi, ma = DDE.adjust_diff()
+	samples = np.array([DDE.integrate(T) for T in g["times"]])
+	accepted, rejected, _ = DDE.counters()
+	return dict(adjust_diff_min=mi, adjust_diff_max=ma, samples=samples, accepted=accepted[0], rejected=rejected[0], max_delay=DDE.max_delay)
+
+
 ALL = dict(roessler=roessler, roessler_jump=roessler_jump, mg_ensemble=mg_ensemble, neutral=neutral,
-	state_dependent=state_dependent, ode=ode, kuramoto=kuramoto, mg_lyap=mg_lyap, roessler_lyap=roessler_lyap)
+	state_dependent=state_dependent, ode=ode, kuramoto=kuramoto, mg_lyap=mg_lyap, roessler_lyap=roessler_lyap, data_input=data_input)
 FIXTURE = dict(roessler_jump="roessler")
 
 

@@ -8,7 +8,7 @@ import numpy as np
 import sympy
 from sympy import Symbol, exp, sin, sqrt, tanh
 
-from jitcdde_b200 import anchors, current_y, past_dy, past_y, t, y
+from jitcdde_b200 import anchors, current_y, input, past_dy, past_y, t, y  # noqa: A004
 from jitcdde_b200 import _codegen
 
 
@@ -113,6 +113,28 @@ def kuramoto(n=6, seed=42):
 	τ = rng.uniform(np.pi/5, 2*np.pi, size=(n, n))
 	f = [ω + c/(n-1)*sum(sin(y(j, t-τ[i, j])-y(i)) for j in range(n) if A[j, i]) for i in range(n)]
 	return dict(f=f, control_pars=[], delays=τ.flatten(), max_delay=float(np.max(τ)), initial=rng.uniform(0, 2*np.pi, n))
+
+
+def data_input(seed=42):
+	"""examples/data_input.py:19-50 of the reference: two delay-coupled relaxators driven by irregularly sampled data"""
+	rng = np.random.default_rng(seed)
+	times = np.sort(rng.uniform(0, 70, 40))
+	times[0], times[-1] = 0.0, 70.0
+	data = np.stack([np.sin(0.3*times)+0.1*rng.normal(size=40), np.cos(0.2*times)+0.1*rng.normal(size=40)], axis=1)
+	slopes = np.gradient(data, times, axis=0)
+	tau = 10.0
+	f = [-y(0) + y(1, t-tau) + input(0), -y(1) + y(0, t-tau) + input(1)]
+	return dict(f=f, input=[(times[k], data[k], slopes[k]) for k in range(40)], tau=tau, initial=np.zeros(2))
+
+
+def data_input_program(system=None):
+	"""(program, joined past, max_delay) of the extended system jitcdde_input hands to the core"""
+	from jitcdde_b200 import jitcdde_input
+	system = system or data_input()
+	DDE = jitcdde_input(system["f"], system["input"], verbose=False)
+	DDE.constant_past(system["initial"])
+	program = _codegen.generate(list(DDE.f_sym()), helpers=DDE.helpers, control_pars=DDE.control_pars)
+	return program, [(a.time, a.state, a.diff) for a in DDE.past], DDE.max_delay
 
 
 def as_list(f):

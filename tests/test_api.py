@@ -227,3 +227,70 @@ def test_past_from_function(twin):
 		results.append(np.array([DDE.integrate(DDE.t+s) for s in (10, 50, 100)]))
 	np.testing.assert_allclose(results[0], results[1], atol=0.01)
 	np.testing.assert_allclose(results[0], results[2], atol=0.01)
+
+
+def test_input(twin):
+	"""tests/test_jitcdde.py:427-452 (as intended there: a subset of the components is replaced by the recorded
+	trajectory given as external input; the remaining ones must still reach the golden vector) and
+	examples/data_input.py (constant past + adjust_diff with input)."""
+	from itertools import combinations
+	from jitcdde_b200 import input, jitcdde_input  # noqa: A004
+	g = scenarios.golden("roessler")
+	DDE = jitcdde(f, verbose=False, max_delay=2*T)  # nothing is forgotten: the recording has to begin at t = 0
+	DDE.set_integration_parameters(**test_parameters)
+	DDE.add_past_points(scenarios.past_of(g))
+	DDE.integrate(T)
+	recorded = [(a.time, a.state.copy(), a.diff.copy()) for a in DDE.get_state()]
+	assert recorded[0][0] <= 0 and recorded[-1][0] >= T
+
+	rng = np.random.default_rng(seed=42)
+	combos = [combo for k in range(1, 6) for combo in combinations(range(6), k)]
+	for index in rng.choice(len(combos), 3, replace=False):
+		combo = combos[index]
+		substitutions = {y(i): input(i) for i in combo}
+		f_input = [expression.subs(substitutions) for expression in f]
+		DDE = jitcdde_input(f_input, recorded, verbose=False)
+		DDE.set_integration_parameters(**test_parameters)
+		DDE.add_past_points(scenarios.past_of(g))
+		DDE.initial_discontinuities_handled = True
+		value = DDE.integrate(T)
+		assert value.shape == (6,)
+		free = [i for i in range(6) if i not in combo]
+		np.testing.assert_allclose(value[free], g["y10_reference"][free], **tolerance)
+
+	# examples/data_input.py:19-50
+	times = np.linspace(0, 70, 20)
+	data = np.random.default_rng(42).normal(size=(20, 2))
+	slopes = np.gradient(data, times, axis=0)
+	spline = [(times[k], data[k], slopes[k]) for k in range(20)]
+	tau_in = 10
+	f_in = [-y(0) + y(1, t-tau_in) + input(0), -y(1) + y(0, t-tau_in) + input(1)]
+	DDE = jitcdde_input(f_in, spline, verbose=False)
+	DDE.constant_past(np.zeros(2))
+	DDE.adjust_diff()
+	result = np.vstack([DDE.integrate(time) for time in np.linspace(DDE.t, 70, 30)])
+	assert result.shape == (30, 2) and np.all(np.isfinite(result))
+	assert DDE.max_delay == 70
+
+
+def test_get_state_round_trip(twin):
+	"""get_state() → add_past_points() on a fresh integrator continues the same trajectory (_jitcdde.py:357-371, 318-331):
+	the anchors carry everything the integration depends on except the controller's step size."""
+	g = scenarios.golden("roessler")
+	DDE = jitcdde(f, verbose=False)
+	DDE.set_integration_parameters(**test_parameters)
+	DDE.add_past_points(scenarios.past_of(g))
+	DDE.initial_discontinuities_handled = True
+	DDE.integrate(T/2)
+	state = [(a.time, a.state.copy(), a.diff.copy()) for a in DDE.get_state()]
+	assert state[0][0] <= DDE.t-delay <= state[1][0] and state[-1][0] == DDE.t
+	dt = DDE.dt
+	expected = DDE.integrate(T)
+
+	DDE2 = jitcdde(f, verbose=False)
+	DDE2.set_integration_parameters(**{**test_parameters, "first_step": float(dt)})
+	DDE2.add_past_points(state)
+	DDE2.initial_discontinuities_handled = True
+	assert DDE2.t == state[-1][0]
+	np.testing.assert_allclose(DDE2.integrate(T), expected, rtol=1e-6)
+	np.testing.assert_allclose(expected, g["y10_reference"], **tolerance)

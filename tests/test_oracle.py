@@ -179,6 +179,19 @@ def test_many_lookup_sites():
 	assert np.array_equal(samples, g["samples"])
 
 
+def test_external_input():
+	"""jitcdde_input (examples/data_input.py): extended system + joined past, against the reference core"""
+	prog, past, max_delay = systems.data_input_program()
+	g = scenarios.golden("data_input")
+	assert np.array_equal(np.array([a[1] for a in past]), g["past_states"]) and np.array_equal(np.array([a[0] for a in past]), g["past_times"])
+	T = oracle.Trajectory(oracle.build(prog), past, max_delay=max_delay)
+	mi, ma = T.adjust_diff()
+	assert np.array_equal(mi[:2], g["adjust_diff_min"]) and np.array_equal(ma[:2], g["adjust_diff_max"])
+	samples = np.array([T.integrate(t)[:2] for t in g["times"]])
+	assert np.array_equal(samples, g["samples"])
+	assert (T.counters["accepted"], T.counters["rejected"]) == (int(g["accepted"]), int(g["rejected"]))
+
+
 @pytest.mark.parametrize("name", ["mg_lyap", "roessler_lyap"])
 def test_lyapunov_bitwise(name):
 	g = scenarios.golden(name)

@@ -75,7 +75,7 @@ def build_runtime(force=False, verbose=False):
 
 def _engine_hash():
 	h = hashlib.sha256()
-	for name in ("jdde_engine.cuh", "jdde_kernels.cu", "jdde_math.h", "jdde_abi.h"):
+	for name in ("jdde_engine.cuh", "jdde_team.cuh", "jdde_kernels.cu", "jdde_math.h", "jdde_abi.h"):
 		with open(os.path.join(CSRC, name), "rb") as f:
 			h.update(f.read())
 	with open(os.path.join(INCLUDE, "jitcdde_b200.h"), "rb") as f:

@@ -54,6 +54,8 @@ SIGNATURES = {
 	"jdde_set_parameters": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32]),
 	"jdde_set_integration_parameters": (ctypes.c_int, [_H, ctypes.POINTER(IntParams), ctypes.c_double]),
 	"jdde_integrate": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, c_int32_p]),
+	"jdde_integrate_async": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p]),
+	"jdde_wait_result": (ctypes.c_int, [_H, ctypes.c_int32]),
 	"jdde_step_on_discontinuities": (ctypes.c_int, [_H, ctypes.c_int32, c_double_p, ctypes.c_int32, c_double_p, c_int32_p]),
 	"jdde_resume": (ctypes.c_int, [_H, c_double_p, c_double_p, c_double_p, c_int32_p]),
 	"jdde_integrate_blindly": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_int32_p]),
@@ -267,6 +269,17 @@ class Engine:
 		self._check(self.lib.jdde_integrate(self._h, _dp(target), pm, _dp(out) if fetch else None,
 			status.ctypes.data_as(c_int32_p) if status is not None else None))
 		return out, status
+
+	def integrate_async(self, target, out):
+		"""queue an integrate() whose result lands in `out` (page-locked, (N, n) float64) by the next synchronize()"""
+		target, pm = self._targets(target)
+		if out.shape != (self.N, self.n) or out.dtype != np.float64 or not out.flags.c_contiguous:
+			raise ValueError("out must be a C-contiguous float64 array of shape (n_members, n)")
+		self._check(self.lib.jdde_integrate_async(self._h, _dp(target), pm, _dp(out)))
+		return out
+
+	def wait_result(self, age=0):
+		self._check(self.lib.jdde_wait_result(self._h, int(age)))
 
 	def _pinned_status(self):
 		"""per-member status lands in page-locked memory (full-bandwidth D2H); callers get a fresh copy only if they keep it"""

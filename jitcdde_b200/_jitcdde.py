@@ -449,17 +449,30 @@ class jitcdde:
 		self._initiate()
 		return self._shape_scalar(self._engine.get_t())
 
-	def integrate(self, target_time, out=None):
+	def integrate(self, target_time, out=None, wait=True):
 		"""
 		As the reference's `integrate` (_jitcdde.py:807-836). Ensemble extension: `target_time`
 		may be an array of shape (n_members,), and `out` a preallocated (n_members, n) float64
 		array (e.g. from `jitcdde_b200.pinned_empty`) that receives and is returned as the result.
+
+		Pipelined sampling: with `wait=False` (needs `out`, page-locked) the call only queues the work and
+		returns `out` at once; its content is valid after `synchronize()`. The copy of one sample to the host
+		then overlaps the integration up to the next one. Alternate between (at least) two `out` buffers.
+		Failures of members are raised by `synchronize()`; a full ring cannot be resumed in this mode (choose
+		`ring_capacity` large enough or sample synchronously).
 		"""
 		self._initiate()
-		if self.n_members == 1 and self._engine.get_t()[0] > target_time:
+		if self.n_members == 1 and wait and self._engine.get_t()[0] > target_time:
 			warn("The target time is smaller than the current time. No integration step will happen. The returned state will be extrapolated from the interpolating Hermite polynomial for the last integration step. You may see this because you try to integrate backwards in time, in which case you did something wrong. You may see this just because your sampling step is small, in which case there is no need to worry (though you should think about increasing your sampling time).", stacklevel=2)
 		if not self.initial_discontinuities_handled:
 			warn("You did not explicitly handle initial discontinuities. Proceed only if you know what you are doing. This is only fine if you somehow chose your initial past such that the derivative of the last anchor complies with the DDE. In this case, you can set the attribute `initial_discontinuities_handled` to `True` to suppress this warning. See https://jitcdde.rtfd.io/#discontinuities for details.", stacklevel=2)
+		if not wait:
+			if out is None:
+				raise ValueError("wait=False needs a preallocated `out` (jitcdde_b200.pinned_empty)")
+			self._queued = True
+			return self._engine.integrate_async(target_time, out)
+		if getattr(self, "_queued", False):
+			self.synchronize()
 		# the per-member status stays on the device unless a member failed (8 bytes back instead of 4·N)
 		result, status = self._engine.integrate(target_time, out=out, fetch_status=False)
 		status = self._engine.get_status() if self._engine.count_failed() else None
@@ -469,6 +482,22 @@ class jitcdde:
 				out[...] = result
 				result = out
 		return self._shape_state(result)
+
+	def wait_result(self, age=0):
+		"""wait for the `out` of the `integrate(..., wait=False)` call `age` calls ago (0: the latest, 1: the one before)
+		without waiting for younger work; member failures are only reported by `synchronize()`"""
+		self._engine.wait_result(age)
+
+	def synchronize(self):
+		"""wait for the results of `integrate(..., wait=False)` calls; raises if a member failed meanwhile"""
+		self._initiate()
+		self._engine.synchronize()
+		self._queued = False
+		if self._engine.count_failed():
+			status = self._engine.get_status()
+			if np.any(status == _capi.STATUS_OVERFLOW):
+				raise RuntimeError("the anchor ring of a member ran full during pipelined sampling: pass a larger ring_capacity or sample with wait=True")
+			self._check_status(status)
 
 	def adjust_diff(self, shift_ratio=1e-4):
 		self._initiate()

@@ -1507,4 +1507,6 @@ JD_FN void member_orthonormalise(jdde_problem const & P, long long const m, int 
 
 } // namespace jdde
 
+#include "jdde_team.cuh"
+
 #endif

@@ -174,4 +174,17 @@ jdde_k_orthonormalise(jdde_problem const P, int const n_lyap, double const delay
 	if (m < P.n_members)
 		jdde::member_orthonormalise(P, m, n_lyap, delay, norms, old_t, lyaps, delta_t);
 }
+
+/* one thread block per member (jdde_team.cuh); dynamic shared memory: blockDim.x + (capacity|1)·(1 + 2·n_basic·n_lyap) doubles */
+extern "C" __global__ void __launch_bounds__(JD_TEAM_BLOCK)
+jdde_k_orthonormalise_team(jdde_problem const P, int const n_lyap, double const delay, double * const norms, double const * const old_t, double * const lyaps, double * const delta_t, int const capacity)
+{
+	extern __shared__ double jd_team_smem[];
+	jdde::Team const T = { (int)threadIdx.x, (int)blockDim.x, jd_team_smem };
+	for (long long m = blockIdx.x; m < P.n_members; m += gridDim.x)
+	{
+		jdde::team_member_orthonormalise(T, P, m, n_lyap, delay, norms, old_t, lyaps, delta_t, jd_team_smem+blockDim.x, capacity);
+		__syncthreads();
+	}
+}
 #endif

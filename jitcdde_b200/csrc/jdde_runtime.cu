@@ -29,7 +29,7 @@ struct Kernels
 {
 	cudaKernel_t set_past = nullptr, reset_controller = nullptr, integrate = nullptr, integrate_blindly = nullptr,
 		jump = nullptr, forget = nullptr, get = nullptr, clear_status = nullptr, sum_counters = nullptr, count_failed = nullptr,
-		regrow = nullptr, orthonormalise = nullptr;
+		regrow = nullptr, orthonormalise = nullptr, orthonormalise_team = nullptr;
 };
 
 } // namespace
@@ -43,6 +43,15 @@ struct jdde_handle
 	Kernels k;
 	int block = 128;
 	int smem_bytes = 0;      /* dynamic shared memory per block (anchor staging window of the image) */
+	/* pipelined sampling (jdde_integrate_async): second result buffer, copy stream, events per buffer */
+	cudaStream_t copy_stream = nullptr;
+	double * d_out_alt = nullptr;
+	cudaEvent_t kernel_done[2] = { nullptr, nullptr }, copy_done[2] = { nullptr, nullptr };
+	bool copy_pending[2] = { false, false };
+	int out_slot = 0;
+	bool queueing = false;    /* inside jdde_integrate_async: the only entry point that does not wait for pending copies */
+	int team_smem_max = 0;   /* dynamic shared memory the team kernel may use (0: not yet asked) */
+	int sm_count = 0;
 	jdde_problem P{};
 	bool have_past = false, have_params = false, have_int_params = false;
 	long long budget = 1ll << 24;
@@ -127,12 +136,75 @@ int launch(jdde_handle * h, cudaKernel_t kernel, void ** args)
 	return JDDE_OK;
 }
 
+/*
+ * Gram–Schmidt over the history with one thread block per member (csrc/jdde_team.cuh). The tangent part of a member's
+ * anchors is staged in shared memory when its live anchors fit: up to the ring capacity if that fits into the opt-in
+ * maximum of the device (227 KB on sm_100), else as many as fit (longer histories run on global memory).
+ * JITCDDE_B200_TEAM=0 selects the one-thread-per-member kernel.
+ */
+int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * norms, const double * old_t, double * lyaps, double * delta_t)
+{
+	const char * const choice = getenv("JITCDDE_B200_TEAM");
+	if (!h->k.orthonormalise_team || (choice && choice[0] == '0'))
+	{
+		void * args[] = { &h->P, &n_lyap, &delay, &norms, &old_t, &lyaps, &delta_t };
+		return launch(h, h->k.orthonormalise, args);
+	}
+	int const per_anchor = 1 + 2*h->desc.n_basic*n_lyap;
+	int const cap = h->P.cap;
+	int block = ((cap/2 + 31)/32)*32;
+	block = block < 64 ? 64 : block > 512 ? 512 : block;
+	if (h->team_smem_max == 0)
+	{
+		int optin = 0;
+		if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->desc.device) != cudaSuccess || optin < 48*1024)
+			optin = 48*1024;
+		if (optin > 48*1024 && cudaFuncSetAttribute((const void *)h->k.orthonormalise_team, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess)
+		{
+			(void)cudaGetLastError();
+			optin = 48*1024;
+		}
+		h->team_smem_max = optin;
+		if (cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->desc.device) != cudaSuccess)
+			h->sm_count = 148;
+	}
+	long long const room = h->team_smem_max/(long long)sizeof(double) - block;     /* doubles left for the staged anchors */
+	int capacity = cap;
+	if ((long long)(capacity | 1)*per_anchor > room)
+		capacity = (int)(room/per_anchor) - 1;
+	if (capacity < 2)
+		capacity = 0;
+	size_t const smem = sizeof(double)*((size_t)block + (capacity ? (size_t)(capacity | 1)*per_anchor : 0));
+	long long const N = h->desc.n_members;
+	long long const most = (long long)h->sm_count*32;
+	unsigned const grid = (unsigned)(N < most ? N : most);
+	void * args[] = { &h->P, &n_lyap, &delay, &norms, &old_t, &lyaps, &delta_t, &capacity };
+	if (getenv("JITCDDE_B200_DEBUG"))
+	{
+		cudaFuncAttributes fa{};
+		cudaError_t const e = cudaFuncGetAttributes(&fa, (const void *)h->k.orthonormalise_team);
+		fprintf(stderr, "[jdde] orthonormalise_team: grid %u block %d smem %zu capacity %d (ring %d) smem_max %d | attributes: %s maxThreads %d regs %d local %zu maxDynamic %d static %zu\n",
+			grid, block, smem, capacity, cap, h->team_smem_max, cudaGetErrorString(e), fa.maxThreadsPerBlock, fa.numRegs, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes);
+		(void)cudaGetLastError();
+	}
+	JD_CUDA(h, cudaLaunchKernel((const void *)h->k.orthonormalise_team, dim3(grid), dim3(block), args, smem, h->stream));
+	h->launches++;
+	return JDDE_OK;
+}
+
 int ready(jdde_handle * h)
 {
 	if (!h)
 		return JDDE_E_INVALID;
 	if (cudaSetDevice(h->desc.device) != cudaSuccess)
 		return fail(h, JDDE_E_CUDA, "cudaSetDevice failed");
+	if (!h->queueing && (h->copy_pending[0] || h->copy_pending[1]))
+	{
+		/* results of jdde_integrate_async still on their way: every other call waits for them first, so that it
+		 * may reuse the result buffers */
+		JD_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+		h->copy_pending[0] = h->copy_pending[1] = false;
+	}
 	return JDDE_OK;
 }
 
@@ -241,6 +313,16 @@ int jdde_destroy(jdde_handle * h)
 	cudaSetDevice(h->desc.device);
 	if (h->stream)
 		cudaStreamSynchronize(h->stream);
+	if (h->copy_stream)
+	{
+		cudaStreamSynchronize(h->copy_stream);
+		for (int s = 0; s < 2; s++)
+		{
+			if (h->kernel_done[s]) cudaEventDestroy(h->kernel_done[s]);
+			if (h->copy_done[s]) cudaEventDestroy(h->copy_done[s]);
+		}
+		cudaStreamDestroy(h->copy_stream);
+	}
 	for (void * p : h->allocations)
 		cudaFree(p);
 	if (h->d_in)
@@ -289,6 +371,7 @@ int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
 	}
 	h->block = d.block;
 	h->smem_bytes = d.smem_bytes;
+	h->team_smem_max = 0;
 
 	struct { const char * name; cudaKernel_t * slot; bool required; } const table[] = {
 		{"jdde_k_set_past", &h->k.set_past, true},
@@ -303,6 +386,7 @@ int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
 		{"jdde_k_count_failed", &h->k.count_failed, true},
 		{"jdde_k_regrow", &h->k.regrow, true},
 		{"jdde_k_orthonormalise", &h->k.orthonormalise, false},
+		{"jdde_k_orthonormalise_team", &h->k.orthonormalise_team, false},
 	};
 	for (auto const & entry : table)
 	{
@@ -337,6 +421,11 @@ int jdde_synchronize(jdde_handle * h)
 	int rc = ready(h);
 	if (rc) return rc;
 	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	if (h->copy_stream)
+	{
+		JD_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+		h->copy_pending[0] = h->copy_pending[1] = false;
+	}
 	return JDDE_OK;
 }
 
@@ -414,12 +503,45 @@ int jdde_set_integration_parameters(jdde_handle * h, const jdde_int_params * p, 
 	return JDDE_OK;
 }
 
-static int run_integrate(jdde_handle * h, const double * targets, size_t count, int per_member, int n_steps, int resume, double * out_state, int n_out, int32_t * status)
+static int run_integrate(jdde_handle * h, const double * targets, size_t count, int per_member, int n_steps, int resume, double * out_state, int n_out, int32_t * status, bool pipelined = false)
 {
 	int rc;
 	double * d_targets;
 	if (!targets)
 		return fail(h, JDDE_E_INVALID, "null argument");
+	if (pipelined)
+	{
+		if (!out_state)
+			return fail(h, JDDE_E_INVALID, "null argument");
+		if (!h->copy_stream)
+		{
+			JD_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+			for (int s = 0; s < 2; s++)
+			{
+				JD_CUDA(h, cudaEventCreateWithFlags(&h->kernel_done[s], cudaEventDisableTiming));
+				JD_CUDA(h, cudaEventCreateWithFlags(&h->copy_done[s], cudaEventDisableTiming));
+			}
+			if ((rc = dev_alloc(h, &h->d_out_alt, (size_t)h->desc.n_members*h->desc.n))) return rc;
+		}
+		int const slot = h->out_slot ^= 1;
+		double * d_result = slot ? h->d_out_alt : h->d_out;
+		if (h->copy_pending[slot])       /* the copy that still reads this buffer (two calls ago) */
+			JD_CUDA(h, cudaStreamWaitEvent(h->stream, h->copy_done[slot], 0));
+		h->last_targets.assign(targets, targets+count);
+		h->last_per_member = per_member;
+		h->last_n_steps = n_steps;
+		if ((rc = stage_in(h, targets, count, &d_targets))) return rc;
+		int pm = per_member ? 1 : 0;
+		long long budget = h->budget;
+		void * args[] = { &h->P, &d_targets, &pm, &n_steps, &resume, &d_result, &n_out, &budget };
+		if ((rc = launch(h, h->k.integrate, args))) return rc;
+		JD_CUDA(h, cudaEventRecord(h->kernel_done[slot], h->stream));
+		JD_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->kernel_done[slot], 0));
+		JD_CUDA(h, cudaMemcpyAsync(out_state, d_result, (size_t)h->desc.n_members*n_out*sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+		JD_CUDA(h, cudaEventRecord(h->copy_done[slot], h->copy_stream));
+		h->copy_pending[slot] = true;
+		return JDDE_OK;
+	}
 	if (!resume)
 	{
 		h->last_targets.assign(targets, targets+count);
@@ -440,6 +562,30 @@ int jdde_integrate(jdde_handle * h, const double * target, int32_t per_member, d
 	if (rc) return rc;
 	h->last_kind = 1;
 	return run_integrate(h, target, per_member ? (size_t)h->desc.n_members : 1, per_member, 0, 0, out_state, h->desc.n, status);
+}
+
+int jdde_integrate_async(jdde_handle * h, const double * target, int32_t per_member, double * out_state)
+{
+	if (!h)
+		return JDDE_E_INVALID;
+	h->queueing = true;
+	int rc = ready_to_integrate(h);
+	h->queueing = false;
+	if (rc) return rc;
+	h->last_kind = 0;      /* nothing to resume */
+	return run_integrate(h, target, per_member ? (size_t)h->desc.n_members : 1, per_member, 0, 0, out_state, h->desc.n, nullptr, true);
+}
+
+int jdde_wait_result(jdde_handle * h, int32_t age)
+{
+	if (!h)
+		return JDDE_E_INVALID;
+	if (age < 0 || age > 1)
+		return fail(h, JDDE_E_INVALID, "age must be 0 or 1 (two results can be in flight)");
+	int const slot = h->out_slot ^ age;
+	if (h->copy_stream && h->copy_pending[slot])
+		JD_CUDA(h, cudaEventSynchronize(h->copy_done[slot]));
+	return JDDE_OK;
 }
 
 int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double * steps, int32_t per_member, double * out_state, int32_t * status)
@@ -547,10 +693,7 @@ int jdde_orthonormalise(jdde_handle * h, int32_t n_lyap, double delay, double * 
 	if (rc) return rc;
 	if (h->desc.n == h->desc.n_basic || n_lyap < 0 || (n_lyap+1)*h->desc.n_basic > h->desc.n)
 		return fail(h, JDDE_E_INVALID, "orthonormalise needs n_basic < n and (n_lyap+1)·n_basic <= n");
-	const double * null_d = nullptr;
-	double * null_o = nullptr;
-	void * args[] = { &h->P, &n_lyap, &delay, &h->d_out2, &null_d, &null_o, &null_o };
-	if ((rc = launch(h, h->k.orthonormalise, args))) return rc;
+	if ((rc = launch_orthonormalise(h, n_lyap, delay, h->d_out2, nullptr, nullptr, nullptr))) return rc;
 	return finish(h, norms, h->d_out2, (size_t)h->desc.n_members*n_lyap, nullptr);
 }
 
@@ -568,10 +711,7 @@ static int run_lyap(jdde_handle * h, const double * target, size_t count, int pe
 		if ((rc = launch(h, h->k.get, gargs))) return rc;
 	}
 	if ((rc = run_integrate(h, target, count, per_member, 0, resume, nullptr, nb, nullptr))) return rc;
-	double delay = h->P.max_delay;
-	const double * old_t = h->d_aux;
-	void * args[] = { &h->P, &n_lyap, &delay, &h->d_out2, &old_t, &h->d_out2, &h->d_aux2 };
-	if ((rc = launch(h, h->k.orthonormalise, args))) return rc;
+	if ((rc = launch_orthonormalise(h, n_lyap, h->P.max_delay, h->d_out2, h->d_aux, h->d_out2, h->d_aux2))) return rc;
 	if (lyaps)
 		JD_CUDA(h, cudaMemcpyAsync(lyaps, h->d_out2, N*n_lyap*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
 	if (delta_t)

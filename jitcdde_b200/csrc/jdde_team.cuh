@@ -1,0 +1,356 @@
+/*
+ * jdde_team.cuh — orthonormalisation of the separation functions by a TEAM of threads per member
+ * (kernel jdde_k_orthonormalise_team: one thread block per member) instead of one thread per member.
+ *
+ * Why: modified Gram–Schmidt over the history (/root/reference/jitcdde/jitced_template.c:846-878) is 1+2+…+n_lyap
+ * scalar-product passes over ALL anchors of a member (hundreds, 8·JD_A bytes each). One thread streaming its own ring
+ * has one cache line in flight per load and every pass goes to DRAM again (profiles/ncu_full_r01_c3_jdde_k_orthonormalise.csv:
+ * 2.7 MB of traffic per member, issue slots 1.8 % busy). Here the tangent part of a member's anchors
+ * (2·n_basic·n_lyap doubles + the time per anchor) is read ONCE into shared memory, component-major so that threads
+ * working on neighbouring anchors hit different banks, all passes run on chip, and the result is written back once.
+ * Members whose live anchors do not fit (`capacity`) run the same code on global memory (L1/L2).
+ *
+ * Arithmetic: every anchor update and every per-segment product is formed by ONE thread from the same operands in
+ * the same order as by the reference's loops. What a team changes is the order in which the per-segment parts are
+ * added up: the verification build (no JD_FAST) adds them in the reference's order (one thread, ascending segments:
+ * bit-identical results), the production build reduces them as a tree.
+ *
+ * The code is written against the small `Team` interface below; the host twin (tests/host_twin) runs it with a
+ * one-thread team, which checks indexing and arithmetic on the CPU.
+ */
+#ifndef JDDE_TEAM_CUH
+#define JDDE_TEAM_CUH
+
+#if JD_NBASIC != JD_N
+
+namespace jdde {
+
+#ifndef JD_TEAM_BLOCK
+#define JD_TEAM_BLOCK 512
+#endif
+
+struct Team
+{
+	int rank, size;
+	double * scratch;       /* shared by the team: at least `size` doubles */
+
+	/* body(e) for all e < count, then a barrier */
+	template <class F>
+	JD_FN void for_each(int const count, F && body) const
+	{
+#if defined(__CUDA_ARCH__)
+		for (int e = rank; e < count; e += size)
+			body(e);
+		__syncthreads();
+#else
+		for (int e = 0; e < count; e++)
+			body(e);
+#endif
+	}
+
+	/* Σ_{e<count} body(e), known to every thread afterwards */
+	template <class F>
+	JD_FN double sum(int const count, F && body) const
+	{
+#if defined(__CUDA_ARCH__)
+		double total = 0;
+#if defined(JD_FAST)
+		for (int e = rank; e < count; e += size)
+			total += body(e);
+		for (int offset = 16; offset > 0; offset >>= 1)
+			total += __shfl_down_sync(0xffffffffu, total, offset);
+		if ((rank & 31) == 0)
+			scratch[rank >> 5] = total;
+		__syncthreads();
+		if (rank == 0)
+		{
+			for (int w = 1; w < (size+31)/32; w++)
+				total += scratch[w];
+			scratch[0] = total;
+		}
+#else
+		/* the reference's order: ascending e, one accumulator */
+		for (int base = 0; base < count; base += size)
+		{
+			if (base+rank < count)
+				scratch[rank] = body(base+rank);
+			__syncthreads();
+			if (rank == 0)
+			{
+				int const n = count-base < size ? count-base : size;
+				for (int r = 0; r < n; r++)
+					total += scratch[r];
+			}
+			__syncthreads();
+		}
+		if (rank == 0)
+			scratch[0] = total;
+#endif
+		__syncthreads();
+		total = scratch[0];
+		__syncthreads();
+		return total;
+#else
+		double total = 0;
+		for (int e = 0; e < count; e++)
+			total += body(e);
+		return total;
+#endif
+	}
+};
+
+/* a member's anchors [first, first+count) as seen by the Gram–Schmidt passes: times and the tangent rows
+ * row = vector·2·n_basic + (0: state | n_basic: diff) + component */
+template <bool resident>      /* staged in shared memory | in the ring in global memory */
+struct Tangents
+{
+	double * ring;
+	int mask, first, count;
+	double * rows;          /* [2·n_basic·n_lyap + 1][ks]; the last row holds the anchor times */
+	double * times;         /* = rows + 2·n_basic·n_lyap·ks */
+	int ks;                 /* odd: rows of neighbouring index start in different banks */
+
+	static constexpr int R = 2*JD_NBASIC;
+
+	JD_FN double * slot(int const a) const { return ring + (size_t)((first+a) & mask)*JD_A; }
+
+	JD_FN static int offset(int const row)
+	{
+		int const vector = row/R, r = row-vector*R;
+		return r < JD_NBASIC ? 1+(vector+1)*JD_NBASIC+r : 1+JD_N+(vector+1)*JD_NBASIC+(r-JD_NBASIC);
+	}
+
+	JD_FN double time(int const a) const { return resident ? times[a] : slot(a)[0]; }
+	JD_FN double get(int const a, int const row) const { return resident ? rows[row*ks+a] : slot(a)[offset(row)]; }
+	JD_FN void set(int const a, int const row, double const x) const
+	{
+		if (resident)
+			rows[row*ks+a] = x;
+		else
+			slot(a)[offset(row)] = x;
+	}
+
+	/* body(a, r) for all anchors a and the R rows r of one vector. On chip, threads run along the anchors (consecutive
+	 * banks); in global memory along the components (consecutive addresses). */
+	template <class F>
+	JD_FN void sweep(Team const & T, F && body) const
+	{
+		if (resident)
+		{
+#if defined(__CUDA_ARCH__)
+			for (int r = 0; r < R; r++)
+				for (int a = T.rank; a < count; a += T.size)
+					body(a, r);
+			__syncthreads();
+#else
+			for (int r = 0; r < R; r++)
+				for (int a = 0; a < count; a++)
+					body(a, r);
+#endif
+		}
+		else
+			T.for_each(count*R, [&](int const e) { body(e/R, e%R); });
+	}
+};
+
+/* counterpart of orthonormalise_pass (jdde_engine.cuh) for a team; vectors are numbered from 0 */
+template <bool resident>
+JD_FN double team_pass(Team const & T, Tangents<resident> const & H, double const threshold, int const sub_i, int const sub_j, double const sub_factor,
+	int const scale_i, double const scale_factor, int const acc_1, int const acc_2)
+{
+	constexpr int R = Tangents<resident>::R;
+	if (sub_i >= 0)
+		H.sweep(T, [&](int const a, int const r) { H.set(a, sub_i*R+r, H.get(a, sub_i*R+r) - sub_factor*H.get(a, sub_j*R+r)); });
+	if (scale_i >= 0)
+		H.sweep(T, [&](int const a, int const r) { H.set(a, scale_i*R+r, H.get(a, scale_i*R+r)*scale_factor); });
+	if (acc_1 < 0)
+		return 0.0;
+
+	return T.sum(H.count-1, [&](int const segment) -> double
+	{
+		int const a = segment+1;
+		double const tw = H.time(a);
+		if (tw < threshold)
+			return 0.0;
+		double const tv = H.time(a-1);
+		double const q = tw - tv;
+		double m[4][4];
+		if (a == 1 || tv < threshold)      /* the first segment that reaches into the window */
+			partial_sp_matrix(q, (threshold - tw) / q, m);
+		else
+			sp_matrix(q, m);
+		int const b1 = acc_1*R, b2 = acc_2*R;
+		/* vector_x[i]: i = 0 v.state, 1 v.diff, 2 w.state, 3 w.diff → (anchor a-1+(i>>1), row base + (i&1)·n_basic) */
+		double part = 0;
+#if defined(JD_FAST)
+		double row[4] = { 0.0, 0.0, 0.0, 0.0 };
+		JD_UNROLL
+		for (int i = 0; i < 4; i++)
+		{
+			JD_UNROLL
+			for (int j = 0; j < 4; j++)
+			{
+				double dot = 0;
+				JD_UNROLL
+				for (int index = 0; index < JD_NBASIC; index++)
+					dot += H.get(a-1+(i>>1), b1+(i&1)*JD_NBASIC+index) * H.get(a-1+(j>>1), b2+(j&1)*JD_NBASIC+index);
+				row[i] += m[i][j]*dot;
+			}
+		}
+		part = (row[0]+row[1])+(row[2]+row[3]);
+#else
+		for (int i = 0; i < 4; i++)
+			for (int j = 0; j < 4; j++)
+				for (int index = 0; index < JD_NBASIC; index++)
+					part += m[i][j] * H.get(a-1+(i>>1), b1+(i&1)*JD_NBASIC+index) * H.get(a-1+(j>>1), b2+(j&1)*JD_NBASIC+index);
+#endif
+		return part;
+	});
+}
+
+/*
+ * Ring → shared memory (in = true: the tangent part of every anchor and its time) and back (in = false: the tangent
+ * part). One warp per anchor, lanes along the anchor's doubles: global accesses are contiguous runs (the state part,
+ * then the diff part of the separation functions). The way in uses cp.async: the copies of all anchors are in flight
+ * at once and do not occupy registers.
+ */
+JD_FN void stage(Team const & T, Tangents<true> const & H, int const n_lyap, bool const in)
+{
+	constexpr int R = 2*JD_NBASIC;
+	int const half = JD_NBASIC*n_lyap, per_anchor = 2*half;
+#if defined(__CUDA_ARCH__)
+	int const lane = T.rank & 31, warp = T.rank >> 5, n_warps = T.size >> 5;
+	for (int c = lane; c < per_anchor+(in ? 1 : 0); c += 32)
+#else
+	int const warp = 0, n_warps = 1;
+	for (int c = 0; c < per_anchor+(in ? 1 : 0); c++)
+#endif
+	{
+		int row = per_anchor, source = 0;                       /* the time */
+		if (c < per_anchor)
+		{
+			int const part = c/half, rem = c-part*half, vector = rem/JD_NBASIC, component = rem-vector*JD_NBASIC;
+			row = vector*R+part*JD_NBASIC+component;
+			source = 1+part*JD_N+JD_NBASIC+rem;
+		}
+		double * const on_chip = H.rows + row*H.ks;
+		for (int a = warp; a < H.count; a += n_warps)
+		{
+			if (!in)
+				H.slot(a)[source] = on_chip[a];
+			else
+			{
+#if defined(__CUDA_ARCH__)
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(on_chip+a)), "l"(H.slot(a)+source) : "memory");
+#else
+				on_chip[a] = H.slot(a)[source];
+#endif
+			}
+		}
+	}
+#if defined(__CUDA_ARCH__)
+	if (in)
+		asm volatile("cp.async.wait_all;" ::: "memory");
+	__syncthreads();
+#endif
+}
+
+/* orthonormalise (jdde_engine.cuh) with team passes; norms are known to every thread */
+template <bool resident>
+JD_FN void team_gram_schmidt(Team const & T, Tangents<resident> const & H, double const threshold, int const n_lyap, double * const norms)
+{
+	int pending_scale = -1;
+	double pending_factor = 1.0;
+	for (int i = 0; i < n_lyap; i++)
+	{
+		int sub_j = -1;
+		double sub_factor = 0.0;
+		for (int j = 0; j < i; j++)
+		{
+			double const sp = team_pass(T, H, threshold, sub_j >= 0 ? i : -1, sub_j, sub_factor, pending_scale, pending_factor, i, j);
+			pending_scale = -1;
+			sub_j = j;
+			sub_factor = sp;
+		}
+		double const norm = sqrt(team_pass(T, H, threshold, sub_j >= 0 ? i : -1, sub_j, sub_factor, pending_scale, pending_factor, i, i));
+		pending_scale = -1;
+		if (norm > JD_NORM_THRESHOLD)
+		{
+			pending_scale = i;
+			pending_factor = 1./norm;
+		}
+		norms[i] = norm;
+	}
+	if (pending_scale >= 0)
+		team_pass(T, H, threshold, -1, -1, 0.0, pending_scale, pending_factor, -1, -1);
+}
+
+/*
+ * member_orthonormalise (jdde_engine.cuh) for a team. `shared` = rows[2·n_basic·n_lyap + 1][ks] (the team's scratch lies elsewhere)
+ * with ks = capacity | 1; capacity = 0: no staging.
+ */
+JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, long long const m, int const n_lyap, double const delay,
+	double * const norms, double const * const old_t, double * const lyaps, double * const delta_t, double * const shared, int const capacity)
+{
+	if (P.status[m] != JDDE_STATUS_OK)
+		return;
+	constexpr int R = 2*JD_NBASIC;
+	double * const ring = P.ring + (size_t)m*P.ring_stride;
+	int const mask = P.cap-1, first = P.first[m], count = P.last[m]-first+1;
+	double const cur_t = ring[(size_t)(P.current[m] & mask)*JD_A];
+
+	double dt = 0;
+	if (old_t)
+	{
+		dt = cur_t-old_t[m];
+		if (dt == 0)
+		{
+			T.for_each(n_lyap+1, [&](int const i)
+			{
+				if (i < n_lyap)
+					lyaps[(size_t)m*n_lyap+i] = 0.0;
+				else
+					delta_t[m] = dt;
+			});
+			return;
+		}
+	}
+
+	double nrm[JD_N/JD_NBASIC];
+	if (capacity > 0 && count <= capacity)
+	{
+		Tangents<true> H;
+		H.ring = ring; H.mask = mask; H.first = first; H.count = count;
+		H.ks = capacity | 1;
+		H.rows = shared;
+		H.times = shared + R*n_lyap*H.ks;
+		stage(T, H, n_lyap, true);
+		team_gram_schmidt(T, H, cur_t-delay, n_lyap, nrm);
+		stage(T, H, n_lyap, false);
+	}
+	else
+	{
+		Tangents<false> H;
+		H.ring = ring; H.mask = mask; H.first = first; H.count = count;
+		H.ks = 0; H.rows = nullptr; H.times = nullptr;
+		team_gram_schmidt(T, H, cur_t-delay, n_lyap, nrm);
+	}
+
+	T.for_each(n_lyap+1, [&](int const i)
+	{
+		if (i < n_lyap)
+		{
+			if (old_t)
+				lyaps[(size_t)m*n_lyap+i] = log(nrm[i]) / dt;
+			else
+				norms[(size_t)m*n_lyap+i] = nrm[i];
+		}
+		else if (old_t)
+			delta_t[m] = dt;
+	});
+}
+
+} // namespace jdde
+
+#endif
+#endif

@@ -148,6 +148,21 @@ int jdde_integrate(jdde_handle * h, const double * target, int32_t pm, double * 
 	return JDDE_OK;
 }
 
+int jdde_integrate_async(jdde_handle * h, const double * target, int32_t pm, double * out)
+{
+	if (!out) return fail(h, JDDE_E_INVALID, "null argument");
+	int const rc = jdde_integrate(h, target, pm, out, nullptr);
+	h->last_kind = 0;
+	return rc;
+}
+
+int jdde_wait_result(jdde_handle * h, int32_t age)
+{
+	if (!h) return JDDE_E_INVALID;
+	if (age < 0 || age > 1) return fail(h, JDDE_E_INVALID, "age must be 0 or 1");
+	return JDDE_OK;
+}
+
 int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double * steps, int32_t pm, double * out, int32_t * status)
 {
 	if (int rc = ready(h)) return rc;
@@ -206,12 +221,31 @@ int jdde_adjust_diff(jdde_handle * h, double shift_ratio, double * minima, doubl
 	return JDDE_OK;
 }
 
+#if JD_NBASIC != JD_N
+/* JITCDDE_TWIN_TEAM = staging capacity in anchors (0: no staging) runs the team code of csrc/jdde_team.cuh with a
+ * one-thread team instead of member_orthonormalise */
+static void orthonormalise_all(jdde_handle * h, int n_lyap, double delay, double * norms, double const * old_t, double * lyaps, double * delta_t)
+{
+	const char * const team = getenv("JITCDDE_TWIN_TEAM");
+	if (!team)
+	{
+		for (long long m = 0; m < h->P.n_members; m++)
+			jdde::member_orthonormalise(h->P, m, n_lyap, delay, norms, old_t, lyaps, delta_t);
+		return;
+	}
+	int const capacity = atoi(team);
+	std::vector<double> shared(1 + (size_t)(capacity | 1)*(1 + 2*JD_NBASIC*n_lyap));
+	jdde::Team const T = { 0, 1, shared.data() };
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::team_member_orthonormalise(T, h->P, m, n_lyap, delay, norms, old_t, lyaps, delta_t, shared.data()+1, capacity);
+}
+#endif
+
 int jdde_orthonormalise(jdde_handle * h, int32_t n_lyap, double delay, double * norms)
 {
 #if JD_NBASIC != JD_N
 	if (int rc = ready(h)) return rc;
-	for (long long m = 0; m < h->P.n_members; m++)
-		jdde::member_orthonormalise(h->P, m, n_lyap, delay, h->out2.data(), nullptr, nullptr, nullptr);
+	orthonormalise_all(h, n_lyap, delay, h->out2.data(), nullptr, nullptr, nullptr);
 	h->launches++;
 	give(h, norms, h->out2, (size_t)h->P.n_members*n_lyap, nullptr);
 	return JDDE_OK;
@@ -229,8 +263,7 @@ static int run_lyap(jdde_handle * h, const double * target, int pm, int resume, 
 		for (long long m = 0; m < h->P.n_members; m++)
 			h->aux[m] = h->ring[(size_t)m*h->P.ring_stride + (size_t)(h->current[m] & (h->P.cap-1))*JD_A];
 	run_integrate(h, target, pm, 0, resume, JD_NBASIC);
-	for (long long m = 0; m < h->P.n_members; m++)
-		jdde::member_orthonormalise(h->P, m, n_lyap, h->P.max_delay, h->out2.data(), h->aux.data(), h->out2.data(), h->aux2.data());
+	orthonormalise_all(h, n_lyap, h->P.max_delay, h->out2.data(), h->aux.data(), h->out2.data(), h->aux2.data());
 	h->launches += 2;
 	give(h, lyaps, h->out2, (size_t)h->P.n_members*n_lyap, nullptr);
 	give(h, delta_t, h->aux2, (size_t)h->P.n_members, nullptr);

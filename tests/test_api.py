@@ -294,3 +294,46 @@ def test_get_state_round_trip(twin):
 	assert DDE2.t == state[-1][0]
 	np.testing.assert_allclose(DDE2.integrate(T), expected, rtol=1e-6)
 	np.testing.assert_allclose(expected, g["y10_reference"], **tolerance)
+
+
+def _pipelined_against_synchronous(N=6):
+	"""integrate(..., wait=False) / wait_result / synchronize deliver the same samples as synchronous calls"""
+	from jitcdde_b200 import pinned_empty
+	from tests import systems
+	pars = systems.mg_grid(N)
+	runs = []
+	for pipelined in (False, True):
+		DDE = scenarios.make(systems.mackey_glass(), max_delay=25.0, n_members=N, ring_capacity=256)   # pipelined calls cannot grow the ring
+		DDE.constant_past([1.0])
+		DDE.set_parameters(pars)
+		DDE.delays = pars[:, 1:2]
+		DDE.step_on_discontinuities()
+		times = 30+10.0*np.arange(1, 7)
+		if not pipelined:
+			runs.append(np.array([DDE.integrate(T) for T in times]))
+			continue
+		outs = [pinned_empty((N, 1)), pinned_empty((N, 1))]
+		samples = []
+		for i, T in enumerate(times):
+			assert DDE.integrate(T, out=outs[i & 1], wait=False) is outs[i & 1]
+			if i:
+				DDE.wait_result(1)
+				samples.append(outs[(i-1) & 1].copy())
+		DDE.synchronize()
+		samples.append(outs[(len(times)-1) & 1].copy())
+		runs.append(np.array(samples))
+		assert DDE.t.shape == (N,) and np.all(DDE.t >= times[-1])
+		# a synchronous call after queued ones drains them first
+		DDE.integrate(times[-1]+10, out=outs[0], wait=False)
+		after = DDE.integrate(times[-1]+20)
+		assert np.all(np.isfinite(after)) and np.all(np.isfinite(outs[0]))
+	assert np.array_equal(runs[0], runs[1])
+
+
+def test_pipelined_sampling(twin):
+	_pipelined_against_synchronous()
+
+
+@pytest.mark.gpu
+def test_pipelined_sampling_gpu():
+	_pipelined_against_synchronous(N=4096)

@@ -138,8 +138,8 @@ int launch(jdde_handle * h, cudaKernel_t kernel, void ** args)
 
 /*
  * Gram–Schmidt over the history with one thread block per member (csrc/jdde_team.cuh). The tangent part of a member's
- * anchors is staged in shared memory when its live anchors fit: up to the ring capacity if that fits into the opt-in
- * maximum of the device (227 KB on sm_100), else as many as fit (longer histories run on global memory).
+ * anchors is staged in shared memory: up to the ring capacity if that fits into the opt-in maximum of the device
+ * (227 KB on sm_100), else as many anchors as fit (longer histories are streamed through in tiles, pass by pass).
  * JITCDDE_B200_TEAM=0 selects the one-thread-per-member kernel.
  */
 int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * norms, const double * old_t, double * lyaps, double * delta_t)
@@ -172,14 +172,17 @@ int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * no
 	int capacity = cap;
 	if ((long long)(capacity | 1)*per_anchor > room)
 		capacity = (int)(room/per_anchor) - 1;
-	if (capacity < 2)
-		capacity = 0;
-	size_t const smem = sizeof(double)*((size_t)block + (capacity ? (size_t)(capacity | 1)*per_anchor : 0));
+	if (capacity < 4)       /* anchors too large for the staging area: one thread per member */
+	{
+		void * targs[] = { &h->P, &n_lyap, &delay, &norms, &old_t, &lyaps, &delta_t };
+		return launch(h, h->k.orthonormalise, targs);
+	}
+	size_t const smem = sizeof(double)*((size_t)block + (size_t)(capacity | 1)*per_anchor);
 	long long const N = h->desc.n_members;
 	long long const most = (long long)h->sm_count*32;
 	unsigned const grid = (unsigned)(N < most ? N : most);
 	void * args[] = { &h->P, &n_lyap, &delay, &norms, &old_t, &lyaps, &delta_t, &capacity };
-	if (getenv("JITCDDE_B200_DEBUG"))
+	if (getenv("JITCDDE_B200_DEBUG"))      /* launch shape and kernel attributes on stderr */
 	{
 		cudaFuncAttributes fa{};
 		cudaError_t const e = cudaFuncGetAttributes(&fa, (const void *)h->k.orthonormalise_team);

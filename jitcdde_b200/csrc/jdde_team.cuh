@@ -8,7 +8,8 @@
  * 2.7 MB of traffic per member, issue slots 1.8 % busy). Here the tangent part of a member's anchors
  * (2·n_basic·n_lyap doubles + the time per anchor) is read ONCE into shared memory, component-major so that threads
  * working on neighbouring anchors hit different banks, all passes run on chip, and the result is written back once.
- * Members whose live anchors do not fit (`capacity`) run the same code on global memory (L1/L2).
+ * A member whose live anchors do not fit (`capacity`) is streamed: every pass brings the anchors through shared memory
+ * tile by tile (each tile with the last anchor of the previous one, for the segment between them).
  *
  * Arithmetic: every anchor update and every per-segment product is formed by ONE thread from the same operands in
  * the same order as by the reference's loops. What a team changes is the order in which the per-segment parts are
@@ -48,9 +49,9 @@ struct Team
 #endif
 	}
 
-	/* Σ_{e<count} body(e), known to every thread afterwards */
+	/* initial + Σ_{e<count} body(e), known to every thread afterwards */
 	template <class F>
-	JD_FN double sum(int const count, F && body) const
+	JD_FN double sum(double const initial, int const count, F && body) const
 	{
 #if defined(__CUDA_ARCH__)
 		double total = 0;
@@ -66,10 +67,11 @@ struct Team
 		{
 			for (int w = 1; w < (size+31)/32; w++)
 				total += scratch[w];
-			scratch[0] = total;
+			scratch[0] = initial+total;
 		}
 #else
 		/* the reference's order: ascending e, one accumulator */
+		total = initial;
 		for (int base = 0; base < count; base += size)
 		{
 			if (base+rank < count)
@@ -91,7 +93,7 @@ struct Team
 		__syncthreads();
 		return total;
 #else
-		double total = 0;
+		double total = initial;
 		for (int e = 0; e < count; e++)
 			total += body(e);
 		return total;
@@ -99,9 +101,8 @@ struct Team
 	}
 };
 
-/* a member's anchors [first, first+count) as seen by the Gram–Schmidt passes: times and the tangent rows
+/* anchors [first, first+count) of a member, staged in shared memory: times and the tangent rows
  * row = vector·2·n_basic + (0: state | n_basic: diff) + component */
-template <bool resident>      /* staged in shared memory | in the ring in global memory */
 struct Tangents
 {
 	double * ring;
@@ -113,60 +114,93 @@ struct Tangents
 	static constexpr int R = 2*JD_NBASIC;
 
 	JD_FN double * slot(int const a) const { return ring + (size_t)((first+a) & mask)*JD_A; }
+	JD_FN double time(int const a) const { return times[a]; }
+	JD_FN double get(int const a, int const row) const { return rows[row*ks+a]; }
+	JD_FN void set(int const a, int const row, double const x) const { rows[row*ks+a] = x; }
 
-	JD_FN static int offset(int const row)
-	{
-		int const vector = row/R, r = row-vector*R;
-		return r < JD_NBASIC ? 1+(vector+1)*JD_NBASIC+r : 1+JD_N+(vector+1)*JD_NBASIC+(r-JD_NBASIC);
-	}
-
-	JD_FN double time(int const a) const { return resident ? times[a] : slot(a)[0]; }
-	JD_FN double get(int const a, int const row) const { return resident ? rows[row*ks+a] : slot(a)[offset(row)]; }
-	JD_FN void set(int const a, int const row, double const x) const
-	{
-		if (resident)
-			rows[row*ks+a] = x;
-		else
-			slot(a)[offset(row)] = x;
-	}
-
-	/* body(a, r) for all anchors a and the R rows r of one vector. On chip, threads run along the anchors (consecutive
-	 * banks); in global memory along the components (consecutive addresses). */
+	/* body(a, r) for the anchors a >= from and the R rows r of one vector; threads run along the anchors (consecutive banks) */
 	template <class F>
-	JD_FN void sweep(Team const & T, F && body) const
+	JD_FN void sweep(Team const & T, int const from, F && body) const
 	{
-		if (resident)
-		{
 #if defined(__CUDA_ARCH__)
-			for (int r = 0; r < R; r++)
-				for (int a = T.rank; a < count; a += T.size)
-					body(a, r);
-			__syncthreads();
+		for (int r = 0; r < R; r++)
+			for (int a = from+T.rank; a < count; a += T.size)
+				body(a, r);
+		__syncthreads();
 #else
-			for (int r = 0; r < R; r++)
-				for (int a = 0; a < count; a++)
-					body(a, r);
+		(void)T;
+		for (int r = 0; r < R; r++)
+			for (int a = from; a < count; a++)
+				body(a, r);
 #endif
-		}
-		else
-			T.for_each(count*R, [&](int const e) { body(e/R, e%R); });
 	}
 };
 
-/* counterpart of orthonormalise_pass (jdde_engine.cuh) for a team; vectors are numbered from 0 */
-template <bool resident>
-JD_FN double team_pass(Team const & T, Tangents<resident> const & H, double const threshold, int const sub_i, int const sub_j, double const sub_factor,
-	int const scale_i, double const scale_factor, int const acc_1, int const acc_2)
+/*
+ * Ring → shared memory (in = true: the tangent part of every anchor and its time) and back (in = false: the tangent
+ * part of the anchors a >= from). One warp per anchor, lanes along the anchor's doubles: global accesses are contiguous
+ * runs (the state part, then the diff part of the separation functions). The way in uses cp.async: the copies of all
+ * anchors are in flight at once and do not occupy registers.
+ */
+JD_FN void stage(Team const & T, Tangents const & H, int const n_lyap, bool const in, int const from)
 {
-	constexpr int R = Tangents<resident>::R;
-	if (sub_i >= 0)
-		H.sweep(T, [&](int const a, int const r) { H.set(a, sub_i*R+r, H.get(a, sub_i*R+r) - sub_factor*H.get(a, sub_j*R+r)); });
-	if (scale_i >= 0)
-		H.sweep(T, [&](int const a, int const r) { H.set(a, scale_i*R+r, H.get(a, scale_i*R+r)*scale_factor); });
-	if (acc_1 < 0)
-		return 0.0;
+	constexpr int R = 2*JD_NBASIC;
+	int const half = JD_NBASIC*n_lyap, per_anchor = 2*half;
+#if defined(__CUDA_ARCH__)
+	int const lane = T.rank & 31, warp = T.rank >> 5, n_warps = T.size >> 5;
+	for (int c = lane; c < per_anchor+(in ? 1 : 0); c += 32)
+#else
+	(void)T;
+	int const warp = 0, n_warps = 1;
+	for (int c = 0; c < per_anchor+(in ? 1 : 0); c++)
+#endif
+	{
+		int row = per_anchor, source = 0;                       /* the time */
+		if (c < per_anchor)
+		{
+			int const part = c/half, rem = c-part*half, vector = rem/JD_NBASIC, component = rem-vector*JD_NBASIC;
+			row = vector*R+part*JD_NBASIC+component;
+			source = 1+part*JD_N+JD_NBASIC+rem;
+		}
+		double * const on_chip = H.rows + row*H.ks;
+		for (int a = from+warp; a < H.count; a += n_warps)
+		{
+			if (!in)
+				H.slot(a)[source] = on_chip[a];
+			else
+			{
+#if defined(__CUDA_ARCH__)
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(on_chip+a)), "l"(H.slot(a)+source) : "memory");
+#else
+				on_chip[a] = H.slot(a)[source];
+#endif
+			}
+		}
+	}
+#if defined(__CUDA_ARCH__)
+	if (in)
+		asm volatile("cp.async.wait_all;" ::: "memory");
+	__syncthreads();
+#endif
+}
 
-	return T.sum(H.count-1, [&](int const segment) -> double
+/*
+ * Counterpart of orthonormalise_pass (jdde_engine.cuh) on the staged anchors; vectors are numbered from 0. Anchors
+ * a >= update_from are updated (a tile's first anchor may be the already updated last one of the previous tile);
+ * `leading` says that local anchor 0 is the member's first anchor; returns initial + the staged segments' parts.
+ */
+JD_FN double team_pass(Team const & T, Tangents const & H, double const threshold, int const sub_i, int const sub_j, double const sub_factor,
+	int const scale_i, double const scale_factor, int const acc_1, int const acc_2, int const update_from, bool const leading, double const initial)
+{
+	constexpr int R = Tangents::R;
+	if (sub_i >= 0)
+		H.sweep(T, update_from, [&](int const a, int const r) { H.set(a, sub_i*R+r, H.get(a, sub_i*R+r) - sub_factor*H.get(a, sub_j*R+r)); });
+	if (scale_i >= 0)
+		H.sweep(T, update_from, [&](int const a, int const r) { H.set(a, scale_i*R+r, H.get(a, scale_i*R+r)*scale_factor); });
+	if (acc_1 < 0)
+		return initial;
+
+	return T.sum(initial, H.count-1, [&](int const segment) -> double
 	{
 		int const a = segment+1;
 		double const tw = H.time(a);
@@ -175,7 +209,7 @@ JD_FN double team_pass(Team const & T, Tangents<resident> const & H, double cons
 		double const tv = H.time(a-1);
 		double const q = tw - tv;
 		double m[4][4];
-		if (a == 1 || tv < threshold)      /* the first segment that reaches into the window */
+		if ((leading && a == 1) || tv < threshold)      /* the first segment that reaches into the window */
 			partial_sp_matrix(q, (threshold - tw) / q, m);
 		else
 			sp_matrix(q, m);
@@ -208,56 +242,10 @@ JD_FN double team_pass(Team const & T, Tangents<resident> const & H, double cons
 	});
 }
 
-/*
- * Ring → shared memory (in = true: the tangent part of every anchor and its time) and back (in = false: the tangent
- * part). One warp per anchor, lanes along the anchor's doubles: global accesses are contiguous runs (the state part,
- * then the diff part of the separation functions). The way in uses cp.async: the copies of all anchors are in flight
- * at once and do not occupy registers.
- */
-JD_FN void stage(Team const & T, Tangents<true> const & H, int const n_lyap, bool const in)
-{
-	constexpr int R = 2*JD_NBASIC;
-	int const half = JD_NBASIC*n_lyap, per_anchor = 2*half;
-#if defined(__CUDA_ARCH__)
-	int const lane = T.rank & 31, warp = T.rank >> 5, n_warps = T.size >> 5;
-	for (int c = lane; c < per_anchor+(in ? 1 : 0); c += 32)
-#else
-	int const warp = 0, n_warps = 1;
-	for (int c = 0; c < per_anchor+(in ? 1 : 0); c++)
-#endif
-	{
-		int row = per_anchor, source = 0;                       /* the time */
-		if (c < per_anchor)
-		{
-			int const part = c/half, rem = c-part*half, vector = rem/JD_NBASIC, component = rem-vector*JD_NBASIC;
-			row = vector*R+part*JD_NBASIC+component;
-			source = 1+part*JD_N+JD_NBASIC+rem;
-		}
-		double * const on_chip = H.rows + row*H.ks;
-		for (int a = warp; a < H.count; a += n_warps)
-		{
-			if (!in)
-				H.slot(a)[source] = on_chip[a];
-			else
-			{
-#if defined(__CUDA_ARCH__)
-				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(on_chip+a)), "l"(H.slot(a)+source) : "memory");
-#else
-				on_chip[a] = H.slot(a)[source];
-#endif
-			}
-		}
-	}
-#if defined(__CUDA_ARCH__)
-	if (in)
-		asm volatile("cp.async.wait_all;" ::: "memory");
-	__syncthreads();
-#endif
-}
-
-/* orthonormalise (jdde_engine.cuh) with team passes; norms are known to every thread */
-template <bool resident>
-JD_FN void team_gram_schmidt(Team const & T, Tangents<resident> const & H, double const threshold, int const n_lyap, double * const norms)
+/* orthonormalise (jdde_engine.cuh): the sequence of passes, each carried out by pass(sub_i, sub_j, sub_factor, scale_i,
+ * scale_factor, acc_1, acc_2) → scalar product; norms are known to every thread */
+template <class Pass>
+JD_FN void team_gram_schmidt(Pass && pass, int const n_lyap, double * const norms)
 {
 	int pending_scale = -1;
 	double pending_factor = 1.0;
@@ -267,12 +255,12 @@ JD_FN void team_gram_schmidt(Team const & T, Tangents<resident> const & H, doubl
 		double sub_factor = 0.0;
 		for (int j = 0; j < i; j++)
 		{
-			double const sp = team_pass(T, H, threshold, sub_j >= 0 ? i : -1, sub_j, sub_factor, pending_scale, pending_factor, i, j);
+			double const sp = pass(sub_j >= 0 ? i : -1, sub_j, sub_factor, pending_scale, pending_factor, i, j);
 			pending_scale = -1;
 			sub_j = j;
 			sub_factor = sp;
 		}
-		double const norm = sqrt(team_pass(T, H, threshold, sub_j >= 0 ? i : -1, sub_j, sub_factor, pending_scale, pending_factor, i, i));
+		double const norm = sqrt(pass(sub_j >= 0 ? i : -1, sub_j, sub_factor, pending_scale, pending_factor, i, i));
 		pending_scale = -1;
 		if (norm > JD_NORM_THRESHOLD)
 		{
@@ -282,12 +270,12 @@ JD_FN void team_gram_schmidt(Team const & T, Tangents<resident> const & H, doubl
 		norms[i] = norm;
 	}
 	if (pending_scale >= 0)
-		team_pass(T, H, threshold, -1, -1, 0.0, pending_scale, pending_factor, -1, -1);
+		pass(-1, -1, 0.0, pending_scale, pending_factor, -1, -1);
 }
 
 /*
- * member_orthonormalise (jdde_engine.cuh) for a team. `shared` = rows[2·n_basic·n_lyap + 1][ks] (the team's scratch lies elsewhere)
- * with ks = capacity | 1; capacity = 0: no staging.
+ * member_orthonormalise (jdde_engine.cuh) for a team. `shared` = rows[2·n_basic·n_lyap + 1][ks] with ks = capacity | 1
+ * (the team's scratch lies elsewhere); capacity >= 4 anchors.
  */
 JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, long long const m, int const n_lyap, double const delay,
 	double * const norms, double const * const old_t, double * const lyaps, double * const delta_t, double * const shared, int const capacity)
@@ -295,9 +283,15 @@ JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, lo
 	if (P.status[m] != JDDE_STATUS_OK)
 		return;
 	constexpr int R = 2*JD_NBASIC;
-	double * const ring = P.ring + (size_t)m*P.ring_stride;
-	int const mask = P.cap-1, first = P.first[m], count = P.last[m]-first+1;
-	double const cur_t = ring[(size_t)(P.current[m] & mask)*JD_A];
+	Tangents H;
+	H.ring = P.ring + (size_t)m*P.ring_stride;
+	H.mask = P.cap-1;
+	H.ks = capacity | 1;
+	H.rows = shared;
+	H.times = shared + R*n_lyap*H.ks;
+	int const first = P.first[m], count = P.last[m]-first+1;
+	double const cur_t = H.ring[(size_t)(P.current[m] & H.mask)*JD_A];
+	double const threshold = cur_t-delay;
 
 	double dt = 0;
 	if (old_t)
@@ -317,23 +311,38 @@ JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, lo
 	}
 
 	double nrm[JD_N/JD_NBASIC];
-	if (capacity > 0 && count <= capacity)
+	if (count <= capacity)
 	{
-		Tangents<true> H;
-		H.ring = ring; H.mask = mask; H.first = first; H.count = count;
-		H.ks = capacity | 1;
-		H.rows = shared;
-		H.times = shared + R*n_lyap*H.ks;
-		stage(T, H, n_lyap, true);
-		team_gram_schmidt(T, H, cur_t-delay, n_lyap, nrm);
-		stage(T, H, n_lyap, false);
+		/* resident: one read, all passes on chip, one write */
+		H.first = first;
+		H.count = count;
+		stage(T, H, n_lyap, true, 0);
+		team_gram_schmidt([&](int const sub_i, int const sub_j, double const sub_factor, int const scale_i, double const scale_factor, int const acc_1, int const acc_2)
+		{
+			return team_pass(T, H, threshold, sub_i, sub_j, sub_factor, scale_i, scale_factor, acc_1, acc_2, 0, true, 0.0);
+		}, n_lyap, nrm);
+		stage(T, H, n_lyap, false, 0);
 	}
 	else
 	{
-		Tangents<false> H;
-		H.ring = ring; H.mask = mask; H.first = first; H.count = count;
-		H.ks = 0; H.rows = nullptr; H.times = nullptr;
-		team_gram_schmidt(T, H, cur_t-delay, n_lyap, nrm);
+		/* streamed: every pass goes through the anchors in tiles [lo, hi); a tile is staged together with anchor lo-1 */
+		team_gram_schmidt([&](int const sub_i, int const sub_j, double const sub_factor, int const scale_i, double const scale_factor, int const acc_1, int const acc_2)
+		{
+			double sum = 0.0;
+			for (int lo = 0; lo < count; )
+			{
+				int const halo = lo > 0 ? 1 : 0;
+				int const hi = count-lo <= capacity-halo ? count : lo+capacity-halo;
+				H.first = first+lo-halo;
+				H.count = hi-lo+halo;
+				stage(T, H, n_lyap, true, 0);
+				sum = team_pass(T, H, threshold, sub_i, sub_j, sub_factor, scale_i, scale_factor, acc_1, acc_2, halo, lo == 0, sum);
+				if (sub_i >= 0 || scale_i >= 0)
+					stage(T, H, n_lyap, false, halo);
+				lo = hi;
+			}
+			return sum;
+		}, n_lyap, nrm);
 	}
 
 	T.for_each(n_lyap+1, [&](int const i)

@@ -30,11 +30,11 @@ def test_register_window_does_not_change_results(twin, monkeypatch, name, window
 	scenarios.compare(result, g, exact=True, suffix="_chain" if name == "mg_ensemble" else "")
 
 
-@pytest.mark.parametrize("capacity", ["0", "40", "4096"])
+@pytest.mark.parametrize("capacity", ["4", "7", "40", "4096"])
 @pytest.mark.parametrize("name", ["mg_lyap", "roessler_lyap"])
 def test_team_orthonormalisation_is_bitwise_identical(twin, monkeypatch, name, capacity):
 	"""The block-per-member Gram–Schmidt of csrc/jdde_team.cuh (staged in shared memory when the live anchors fit the
-	capacity, on the ring otherwise; here with a one-thread team on the host) against the reference core's vectors."""
+	capacity, streamed through it in tiles otherwise; here with a one-thread team on the host) against the reference core's vectors."""
 	monkeypatch.setenv("JITCDDE_TWIN_TEAM", capacity)
 	g = scenarios.golden(name)
 	scenarios.compare(scenarios.ALL[name](g), g, exact=True)

@@ -95,6 +95,17 @@ class ClockSampler:
 				pass
 			time.sleep(0.0005)
 
+	def sample_now(self):
+		"""one sample taken by the calling thread (the background thread may be starved for a short timed region)"""
+		if not self.nv:
+			return
+		nv = self.nv
+		get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+		try:
+			self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM), get_reasons(self.handle)))
+		except Exception:
+			pass
+
 	def mark_start(self):
 		self.window[0] = time.perf_counter()
 
@@ -300,13 +311,13 @@ def gpu_arm(args):
 	engine.set_stream(stream.cuda_stream)
 	T0 = 30.0
 	k = 0
+	clocks = ClockSampler(local_rank)      # started before the warm-up: NVML's first queries are slow
 	for _ in range(args.warmup):
 		k += 1
 		engine.integrate(T0+ADVANCE*k, fetch=False)
 	accepted_before = engine.sum_counters()[0]
 	launches_before = engine.launch_count
 	ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-	clocks = ClockSampler(local_rank)
 	barrier()
 	clocks.mark_start()
 	ev0.record(stream)
@@ -314,6 +325,7 @@ def gpu_arm(args):
 		k += 1
 		engine.integrate(T0+ADVANCE*k, fetch=False)
 	ev1.record(stream)
+	clocks.sample_now()      # the host is ahead of the GPU here: the launches above are still running
 	barrier()
 	clocks.mark_end()
 	clocks.stop()

@@ -126,10 +126,10 @@ int jdde_set_max_delay(jdde_handle * h, double max_delay);
  * (_jitcdde.py:775-861). target: 1 value or [n_members]; out_state [n_members][n]; status [n_members]. */
 int jdde_integrate(jdde_handle * h, const double * target, int32_t per_member, double * out_state, int32_t * status);
 
-/* Pipelined sampling: as jdde_integrate, but returns as soon as the work is queued. The states are copied to
- * out_state (page-locked memory, e.g. from jdde_host_alloc, for the copy to be asynchronous) on a second stream
- * while the next call's kernel already runs; two device result buffers alternate, so up to two results are in
- * flight. out_state is valid and member failures can be asked for (jdde_count_failed) after jdde_synchronize.
+/* Pipelined sampling: as jdde_integrate, but returns as soon as the work is queued. If out_state is page-locked
+ * memory the GPU can address (jdde_host_alloc, cudaHostAlloc, registered memory), the kernel writes the states
+ * straight into it (also in jdde_integrate); otherwise they are copied on a second stream while the next call's
+ * kernel already runs, two device result buffers alternating. Up to two results are in flight. out_state is valid and member failures can be asked for (jdde_count_failed) after jdde_synchronize.
  * The sampling loop of the reference (examples/mackey_glass.py:76-79: one integrate() per sample) maps to a
  * sequence of these calls; members that stop with a full ring cannot be resumed in this mode. */
 int jdde_integrate_async(jdde_handle * h, const double * target, int32_t per_member, double * out_state);

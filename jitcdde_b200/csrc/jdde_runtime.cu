@@ -48,6 +48,7 @@ struct jdde_handle
 	double * d_out_alt = nullptr;
 	cudaEvent_t kernel_done[2] = { nullptr, nullptr }, copy_done[2] = { nullptr, nullptr };
 	bool copy_pending[2] = { false, false };
+	bool result_direct[2] = { false, false }, result_queued[2] = { false, false };
 	int out_slot = 0;
 	bool queueing = false;    /* inside jdde_integrate_async: the only entry point that does not wait for pending copies */
 	int team_smem_max = 0;   /* dynamic shared memory the team kernel may use (0: not yet asked) */
@@ -123,6 +124,29 @@ int stage_in(jdde_handle * h, const double * host, size_t count, double ** dev, 
 	*dev = h->d_in+offset_doubles;
 	JD_CUDA(h, cudaMemcpyAsync(*dev, host, count*sizeof(double), cudaMemcpyHostToDevice, h->stream));
 	return JDDE_OK;
+}
+
+/*
+ * Device-side alias of a caller's result buffer if it is page-locked host memory the GPU can address (cudaHostAlloc /
+ * jdde_host_alloc, registered memory): the kernel then writes its results straight into it over PCIe — posted
+ * writes spread over the kernel's run time, no device-side result buffer, no copy afterwards. nullptr otherwise.
+ */
+double * direct_alias(double * host)
+{
+	if (!host)
+		return nullptr;
+	cudaPointerAttributes attributes{};
+	if (cudaPointerGetAttributes(&attributes, host) != cudaSuccess)
+	{
+		(void)cudaGetLastError();
+		return nullptr;
+	}
+	const char * const choice = getenv("JITCDDE_B200_DIRECT");
+	if (choice && choice[0] == '0')
+		return nullptr;
+	if (attributes.type == cudaMemoryTypeHost && attributes.devicePointer)
+		return static_cast<double *>(attributes.devicePointer);
+	return nullptr;
 }
 
 int launch(jdde_handle * h, cudaKernel_t kernel, void ** args)
@@ -319,12 +343,12 @@ int jdde_destroy(jdde_handle * h)
 	if (h->copy_stream)
 	{
 		cudaStreamSynchronize(h->copy_stream);
-		for (int s = 0; s < 2; s++)
-		{
-			if (h->kernel_done[s]) cudaEventDestroy(h->kernel_done[s]);
-			if (h->copy_done[s]) cudaEventDestroy(h->copy_done[s]);
-		}
 		cudaStreamDestroy(h->copy_stream);
+	}
+	for (int s = 0; s < 2; s++)
+	{
+		if (h->kernel_done[s]) cudaEventDestroy(h->kernel_done[s]);
+		if (h->copy_done[s]) cudaEventDestroy(h->copy_done[s]);
 	}
 	for (void * p : h->allocations)
 		cudaFree(p);
@@ -512,23 +536,25 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 	double * d_targets;
 	if (!targets)
 		return fail(h, JDDE_E_INVALID, "null argument");
+	double * const direct = n_steps == 0 ? direct_alias(out_state) : nullptr;
 	if (pipelined)
 	{
 		if (!out_state)
 			return fail(h, JDDE_E_INVALID, "null argument");
-		if (!h->copy_stream)
-		{
-			JD_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+		if (!h->kernel_done[0])
 			for (int s = 0; s < 2; s++)
 			{
 				JD_CUDA(h, cudaEventCreateWithFlags(&h->kernel_done[s], cudaEventDisableTiming));
 				JD_CUDA(h, cudaEventCreateWithFlags(&h->copy_done[s], cudaEventDisableTiming));
 			}
+		if (!direct && !h->copy_stream)
+		{
+			JD_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 			if ((rc = dev_alloc(h, &h->d_out_alt, (size_t)h->desc.n_members*h->desc.n))) return rc;
 		}
 		int const slot = h->out_slot ^= 1;
-		double * d_result = slot ? h->d_out_alt : h->d_out;
-		if (h->copy_pending[slot])       /* the copy that still reads this buffer (two calls ago) */
+		double * d_result = direct ? direct : slot ? h->d_out_alt : h->d_out;
+		if (!direct && h->copy_pending[slot])       /* the copy that still reads this buffer (two calls ago) */
 			JD_CUDA(h, cudaStreamWaitEvent(h->stream, h->copy_done[slot], 0));
 		h->last_targets.assign(targets, targets+count);
 		h->last_per_member = per_member;
@@ -539,6 +565,10 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 		void * args[] = { &h->P, &d_targets, &pm, &n_steps, &resume, &d_result, &n_out, &budget };
 		if ((rc = launch(h, h->k.integrate, args))) return rc;
 		JD_CUDA(h, cudaEventRecord(h->kernel_done[slot], h->stream));
+		h->result_direct[slot] = direct != nullptr;
+		h->result_queued[slot] = true;
+		if (direct)
+			return JDDE_OK;
 		JD_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->kernel_done[slot], 0));
 		JD_CUDA(h, cudaMemcpyAsync(out_state, d_result, (size_t)h->desc.n_members*n_out*sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
 		JD_CUDA(h, cudaEventRecord(h->copy_done[slot], h->copy_stream));
@@ -554,8 +584,17 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 	if ((rc = stage_in(h, targets, count, &d_targets))) return rc;
 	int pm = per_member ? 1 : 0;
 	long long budget = h->budget;
-	void * args[] = { &h->P, &d_targets, &pm, &n_steps, &resume, &h->d_out, &n_out, &budget };
+	double * d_result = direct ? direct : h->d_out;
+	void * args[] = { &h->P, &d_targets, &pm, &n_steps, &resume, &d_result, &n_out, &budget };
 	if ((rc = launch(h, h->k.integrate, args))) return rc;
+	if (direct)
+	{
+		/* the states are already on their way into out_state; they have arrived when the kernel has ended */
+		if ((rc = finish(h, nullptr, nullptr, 0, status))) return rc;
+		if (!status)
+			JD_CUDA(h, cudaStreamSynchronize(h->stream));
+		return JDDE_OK;
+	}
 	return finish(h, out_state, h->d_out, (size_t)h->desc.n_members*n_out, status);
 }
 
@@ -586,7 +625,11 @@ int jdde_wait_result(jdde_handle * h, int32_t age)
 	if (age < 0 || age > 1)
 		return fail(h, JDDE_E_INVALID, "age must be 0 or 1 (two results can be in flight)");
 	int const slot = h->out_slot ^ age;
-	if (h->copy_stream && h->copy_pending[slot])
+	if (!h->result_queued[slot])
+		return JDDE_OK;
+	if (h->result_direct[slot])
+		JD_CUDA(h, cudaEventSynchronize(h->kernel_done[slot]));
+	else if (h->copy_pending[slot])
 		JD_CUDA(h, cudaEventSynchronize(h->copy_done[slot]));
 	return JDDE_OK;
 }

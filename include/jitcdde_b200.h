@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define JDDE_ABI_VERSION 1
+#define JDDE_ABI_VERSION 2
 
 /* return codes */
 #define JDDE_OK            0

@@ -75,7 +75,7 @@ def build_runtime(force=False, verbose=False):
 
 def _engine_hash():
 	h = hashlib.sha256()
-	for name in ("jdde_engine.cuh", "jdde_team.cuh", "jdde_kernels.cu", "jdde_math.h", "jdde_abi.h"):
+	for name in ("jdde_engine.cuh", "jdde_team.cuh", "jdde_group.cuh", "jdde_kernels.cu", "jdde_math.h", "jdde_abi.h"):
 		with open(os.path.join(CSRC, name), "rb") as f:
 			h.update(f.read())
 	with open(os.path.join(INCLUDE, "jitcdde_b200.h"), "rb") as f:
@@ -126,8 +126,47 @@ def launch_shape(program):
 	return 128, 1
 
 
+def use_group(program):
+	"""
+	Lanes per member of the adaptive stepper (JD_GROUP in csrc/jdde_group.cuh), 0 = one thread per member.
+	Blockwise Lyapunov programs (_codegen._generate_blocks) whose anchors are too large for registers anyway
+	(more than 8 doubles: the by-pointer access path) are integrated by 1 + n_lyap lanes per member: one thread
+	would need 16·n registers (local memory at n = 30), a lane needs 16·n_basic.
+	JITCDDE_B200_GROUP=0 switches back to one thread per member (tests compare both).
+	"""
+	if os.environ.get("JITCDDE_B200_GROUP", "1") == "0":
+		return 0
+	lanes = getattr(program, "group_lanes", 0)
+	if lanes and lanes <= 32 and _anchor_doubles(program) > 8 and use_window(program) == 0:
+		return lanes
+	return 0
+
+
+def group_shape(program):
+	"""(block size, resident blocks per SM) of jdde_k_integrate_group; JITCDDE_B200_GROUP_LAUNCH overrides"""
+	override = os.environ.get("JITCDDE_B200_GROUP_LAUNCH")
+	if override:
+		block, blocks = override.split("x")
+		return int(block), int(blocks)
+	return 64, 8
+
+
+def group_window(program):
+	"""
+	Shared-memory staging of the anchors a step can reach for the lane-group stepper (JD_GROUP_WINDOW in
+	csrc/jdde_group.cuh): 4 whole anchors per member and lookup site. Chosen when that is at most 4 KB per member
+	(two Rösslers + 4 exponents: 2 KB → 24 KB per block of 12 members); JITCDDE_B200_GROUP_WINDOW overrides.
+	"""
+	if not use_group(program):
+		return 0
+	override = os.environ.get("JITCDDE_B200_GROUP_WINDOW")
+	if override is not None:
+		return int(override) if program.n_sites > 0 else 0
+	return int(program.n_sites > 0 and program.n_sites*4*_anchor_doubles(program)*8 <= 4096)
+
+
 def image_path(program, n_basic, mode, block, extra_flags=()):
-	tag = hashlib.sha256(repr((program.key, n_basic, mode, block, tuple(extra_flags), use_window(program), launch_shape(program), _engine_hash())).encode()).hexdigest()[:20]
+	tag = hashlib.sha256(repr((program.key, n_basic, mode, block, tuple(extra_flags), use_window(program), launch_shape(program), use_group(program), group_shape(program), group_window(program), _engine_hash())).encode()).hexdigest()[:20]
 	return os.path.join(CACHE, f"jdde_{tag}.cubin")
 
 
@@ -149,6 +188,10 @@ def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), fo
 	with open(rhs, "w") as f:
 		f.write(program.body)
 	flags = ["-O3", "-std=c++17", "-lineinfo", *ARCH]
+	group_flags = []
+	if use_group(program):
+		group_block, group_blocks = group_shape(program)
+		group_flags = [f"-DJD_GROUP={use_group(program)}", f"-DJD_GROUP_BLOCK={group_block}", f"-DJD_GROUP_MIN_BLOCKS={group_blocks}", f"-DJD_GROUP_WINDOW={group_window(program)}"]
 	if mode == VERIFY:
 		flags.append("-fmad=false")
 	elif mode == FAST:
@@ -159,6 +202,7 @@ def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), fo
 		f"-DJD_N={program.n}", f"-DJD_NBASIC={n_basic}", f"-DJD_NSITES={program.n_sites}",
 		f"-DJD_NPARAMS={program.n_params}", f'-DJD_RHS_FILE="{rhs}"', f"-DJD_BLOCK={block}",
 		f"-DJD_WINDOW={int(use_window(program))}",
+		*group_flags,
 		*extra_flags,
 		os.path.join(CSRC, "jdde_kernels.cu"), "-o", path + ".tmp"]
 	if verbose:

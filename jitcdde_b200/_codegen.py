@@ -108,6 +108,7 @@ class RHSProgram:
 	uses_past_dy: bool
 	literal_f: list = field(default_factory=list)   # one reference-style `set_dy(i, …)` per component, no CSE, libm pow
 	literal_sites: int = 0
+	group_lanes: int = 0           # blockwise Lyapunov program: 1 + n_lyap lanes can share a member (csrc/jdde_group.cuh); 0: not blockwise
 
 	@property
 	def n_params(self):
@@ -156,10 +157,13 @@ def _to_plain_functions(expr):
 	return expr.xreplace(repl) if repl else expr
 
 
-def generate(f_sym, helpers=(), control_pars=(), simplify=False, do_cse=True):
+def generate(f_sym, helpers=(), control_pars=(), simplify=False, do_cse=True, blocks=None):
 	"""
 	f_sym: list of expressions (component i = dy_i/dt), helpers: list of
 	(symbol, expression) incl. anchor helpers, control_pars: list of symbols.
+	blocks = (n_basic, n_lyap): the system is a basic one followed by n_lyap tangent blocks of the same
+	shape (tangent_vector_f); the statements are then generated block by block (see _generate_blocks), if
+	the blocks turn out to be index-shifted copies of each other.
 	"""
 	control_pars = [sympy.sympify(p) for p in control_pars]
 	exprs = [_to_plain_functions(sympy.sympify(e)) for e in f_sym]
@@ -180,6 +184,21 @@ def generate(f_sym, helpers=(), control_pars=(), simplify=False, do_cse=True):
 	# literal flavour: what the reference would emit (no CSE, libm pow)
 	lit = _LiteralPrinter(par_index)
 	literal_f = [f"set_dy({i}, {lit.doprint(e)});" for i, e in enumerate(exprs)]
+
+	if blocks is not None and blocks[1] > 0:
+		blockwise = _generate_blocks(exprs, blocks[0], blocks[1], par_index, do_cse)
+		if blockwise is not None:
+			body, n_sites = blockwise
+			return RHSProgram(
+				n=n,
+				param_names=[p.name for p in control_pars],
+				n_sites=n_sites,
+				body=body,
+				uses_past_dy=any(e.has(past_dy) for e in exprs),
+				literal_f=literal_f,
+				literal_sites=lit.n_sites,
+				group_lanes=blocks[1]+1,
+			)
 
 	if do_cse:
 		replacements, reduced = sympy.cse(exprs, symbols=sympy.numbered_symbols("x"), order="none")
@@ -258,6 +277,138 @@ def _hoist_anchors(replacements, reduced):
 		out = [(s, e.xreplace(alias)) for s, e in out if s not in alias]
 		new_reduced = [e.xreplace(alias) for e in new_reduced]
 	return out, new_reduced
+
+
+# ---------------------------------------------------------------------------
+# Blockwise programs for Lyapunov systems
+# ---------------------------------------------------------------------------
+
+class _NotBlockwise(Exception):
+	pass
+
+
+class _BlockPrinter(_MacroPrinter):
+	"""Prints the statements of one block: components below n_basic in the usual vocabulary, components of
+	the block itself (offset … offset+n_basic−1) relative to it as JDDE_TY / JDDE_PAST_TY / JDDE_PAST_TDY."""
+
+	def __init__(self, par_index, n_basic, offset):
+		super().__init__(par_index, set())
+		self.n_basic = n_basic
+		self.offset = offset
+
+	def _split(self, index):
+		if not index.is_Integer:
+			raise _NotBlockwise
+		index = int(index)
+		if 0 <= index < self.n_basic:
+			return False, index
+		if self.offset is not None and self.offset <= index < self.offset+self.n_basic:
+			return True, index-self.offset
+		raise _NotBlockwise
+
+	def _print_current_y(self, expr):
+		own, index = self._split(expr.args[0])
+		return f"JDDE_TY({index})" if own else f"JDDE_Y({index})"
+
+	def _print_past_y(self, expr):
+		tm, i, seg = expr.args
+		own, index = self._split(i)
+		return f"JDDE_PAST_{'TY' if own else 'Y'}({self._print(tm)}, {index}, {self._print(seg)})"
+
+	def _print_past_dy(self, expr):
+		tm, i, seg = expr.args
+		own, index = self._split(i)
+		return f"JDDE_PAST_{'TDY' if own else 'DY'}({self._print(tm)}, {index}, {self._print(seg)})"
+
+	def _print_anchors(self, expr):
+		raise _NotBlockwise      # all lookups are made in the prologue
+
+
+def _extract_lookups(exprs):
+	"""Replace every anchors(argument) call by a symbol s_k (inner-most first; calls with the same argument
+	share one). Returns ([(s_k, argument)], expressions); arguments may contain earlier s_j (nested delays)."""
+	seg_of = {}
+	lookups = []
+	out = []
+	for expr in exprs:
+		while True:
+			calls = [c for c in expr.atoms(anchors) if not c.args[0].has(anchors)]
+			if not calls:
+				break
+			for call in sorted(calls, key=sympy.default_sort_key):
+				if call not in seg_of:
+					seg_of[call] = sympy.Symbol(f"s{len(seg_of)}")
+					lookups.append((seg_of[call], call.args[0]))
+			expr = expr.xreplace({c: seg_of[c] for c in calls})
+		out.append(expr)
+	return lookups, out
+
+
+def _generate_blocks(exprs, n_basic, n_lyap, par_index, do_cse):
+	"""
+	Statements for a basic system followed by n_lyap tangent blocks
+	(/root/reference/jitcdde/_jitcdde.py:1046-1089). The tangent blocks are the same expressions with the block's
+	own components shifted by n_basic each; they are printed ONCE, relative to the block, and
+
+	  * the one-thread-per-member engine, the plain-C oracle and the reference's template get them n_lyap times
+	    with JDDE_TOFF = n_basic, 2·n_basic, … (the #ifndef JDDE_GROUP branch), while
+	  * the lane-group engine (csrc/jdde_group.cuh) gives the basic system to one lane and one tangent block
+	    to each further lane of a group (the #ifdef JDDE_GROUP branch).
+
+	All lookups are made first, by everyone. Both branches consist of the same statements, so the arithmetic
+	per component is identical. Returns (body, n_sites), or None if the blocks are not index-shifted copies of
+	each other (then the caller generates the system as a whole).
+	"""
+	if len(exprs) != n_basic*(n_lyap+1):
+		return None
+	lookups, exprs = _extract_lookups(exprs)
+
+	def statements(block_exprs, printer, temp_prefix, setter):
+		if do_cse:
+			replacements, reduced = sympy.cse(block_exprs, symbols=sympy.numbered_symbols(temp_prefix), order="none")
+		else:
+			replacements, reduced = [], list(block_exprs)
+		lines = [f"const double {s.name} = {printer.doprint(e)};" for s, e in replacements]
+		lines += [f"{setter}({i}, {printer.doprint(e)});" for i, e in enumerate(reduced)]
+		return "\n".join(lines) + "\n"
+
+	try:
+		basic_printer = _BlockPrinter(par_index, n_basic, None)
+		prologue = ""
+		for k, (s, argument) in enumerate(lookups):
+			prologue += f"JDDE_SEG {s.name} = JDDE_ANCHORS({k}, {basic_printer.doprint(argument)});\n"
+		basic = statements(exprs[:n_basic], basic_printer, "x", "JDDE_SET_DY")
+		tangent = None
+		for i in range(n_lyap):
+			offset = (i+1)*n_basic
+			text = statements(exprs[offset:offset+n_basic], _BlockPrinter(par_index, n_basic, offset), "w", "JDDE_SET_TDY")
+			if tangent is None:
+				tangent = text
+			elif text != tangent:
+				return None
+	except _NotBlockwise:
+		return None
+
+	body = (
+		"#ifndef JDDE_GROUP\n"
+		"#define JDDE_TY(k) JDDE_Y((k)+JDDE_TOFF)\n"
+		"#define JDDE_PAST_TY(tm, k, s) JDDE_PAST_Y(tm, (k)+JDDE_TOFF, s)\n"
+		"#define JDDE_PAST_TDY(tm, k, s) JDDE_PAST_DY(tm, (k)+JDDE_TOFF, s)\n"
+		"#define JDDE_SET_TDY(c, value) JDDE_SET_DY((c)+JDDE_TOFF, value)\n"
+		"#endif\n"
+		+ prologue +
+		"#ifndef JDDE_GROUP\n"
+		"{\n" + basic + "}\n"
+	)
+	for i in range(n_lyap):
+		body += f"#define JDDE_TOFF {(i+1)*n_basic}\n{{\n{tangent}}}\n#undef JDDE_TOFF\n"
+	body += (
+		"#undef JDDE_TY\n#undef JDDE_PAST_TY\n#undef JDDE_PAST_TDY\n#undef JDDE_SET_TDY\n"
+		"#else\n"
+		"if (JDDE_GROUP_IS_BASIC)\n{\n" + basic + "}\nelse\n{\n" + tangent + "}\n"
+		"#endif\n"
+	)
+	return body, len(lookups)
 
 
 class _LiteralPrinter(C99CodePrinter):

@@ -269,7 +269,8 @@ class jitcdde:
 		# simplify is slow and only reorders arithmetic, so it is opt-in here.
 		simplify = bool(simplify)
 		self.extra_compile_args = tuple(extra_compile_args or ())
-		self._program = _codegen.generate(self.f_sym(), helpers=self.helpers, control_pars=self.control_pars, simplify=simplify, do_cse=do_cse)
+		blocks = (self.n_basic, self.n//self.n_basic-1) if self.n_basic != self.n else None
+		self._program = _codegen.generate(self.f_sym(), helpers=self.helpers, control_pars=self.control_pars, simplify=simplify, do_cse=do_cse, blocks=blocks)
 		if not self._program.n_sites:
 			warn("Differential equation does not include a delay term.", stacklevel=2)
 		mode = _build.VERIFY if self.verification else _build.FAST

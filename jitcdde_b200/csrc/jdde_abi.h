@@ -59,6 +59,7 @@ typedef struct jdde_problem
 typedef struct jdde_image_desc_t
 {
 	int magic, abi, n, n_basic, n_sites, n_params, anchor_stride, block, smem_bytes;
+	int group_lanes, group_block, group_smem_bytes;   /* jdde_k_integrate_group: lanes per member, block size, dynamic shared memory per block (0 lanes: not in this image) */
 } jdde_image_desc_t;
 
 #if defined(__CUDACC__)

@@ -154,6 +154,8 @@ struct Window
 /* everything one trajectory needs while a kernel runs; lives in registers / local memory */
 struct Member
 {
+	static constexpr int NL = JD_N;             /* components this thread owns: all of them */
+	static constexpr bool PREFETCH = true;
 	double * ring;
 	int mask;                                   /* ring capacity - 1 */
 	int first, last, current;
@@ -183,6 +185,19 @@ struct Member
 
 	JD_FN double * slot(int const index) const { return ring + (size_t)(index & mask)*JD_A; }
 
+	/* bring an anchor into L1 ahead of its use (walk) */
+	JD_FN void prefetch(int const index) const
+	{
+#if defined(__CUDA_ARCH__)
+		double const * const a = slot(index);
+		JD_UNROLL
+		for (int k = 0; k < JD_A; k += 16)
+			asm volatile("prefetch.global.L1 [%0];" :: "l"(a+k));
+#else
+		(void)index;
+#endif
+	}
+
 	JD_FN void invalidate_windows()
 	{
 #if JD_WINDOW
@@ -196,6 +211,12 @@ struct Member
 #if JD_WINDOW
 JD_FN void fill_window(Member & M, int const site);
 #endif
+
+/* Past-within-step memory of the controller (cold). One thread per member: the per-member arrays in global memory.
+ * (A group of lanes per member keeps it in registers instead, jdde_group.cuh.) */
+JD_FN double & ctl_last_pws(Member const & M, jdde_problem const & P) { return P.last_pws[M.index]; }
+JD_FN int & ctl_count(Member const & M, jdde_problem const & P) { return P.count[M.index]; }
+JD_FN double & ctl_credit(Member const & M, jdde_problem const & P) { return P.credit[M.index]; }
 
 /* ------------------------------------------------------------------ load / store */
 
@@ -256,7 +277,8 @@ JD_FN void store_member(jdde_problem const & P, long long const m, Member const 
 /* get_past_anchors, jitced_template.c:193-217. One cursor per lookup site; the walk's stopping
  * rules decide which segment is taken when t equals an anchor time.
  * This is the walk through memory; returns the index of the left anchor. */
-JD_FN int walk(Member & M, int const site, double const t, double const * & pa, double const * & pn, double & ta, double & tn)
+template <class MT>
+JD_FN int walk(MT & M, int const site, double const t, double const * & pa, double const * & pn, double & ta, double & tn)
 {
 	int ca = M.cursor[site];
 	pa = M.slot(ca);
@@ -280,6 +302,11 @@ JD_FN int walk(Member & M, int const site, double const t, double const * & pa, 
 	if (t > M.cur_t)
 		M.pws = fmax(M.pws, t-M.cur_t);
 	M.cursor[site] = ca;
+	/* The cursor moves on by about one anchor per step: ask for the anchor after the bracketing pair now (L1
+	 * prefetch, nothing waits for it), so that the lookup that reaches it one or two steps later does not pay
+	 * the DRAM latency. Accepted anchors only: they are immutable. */
+	if (MT::PREFETCH && ca+2 <= M.current)
+		M.prefetch(ca+2);
 	return ca;
 }
 
@@ -553,7 +580,8 @@ JD_FN Seg anchors(Member & M, int const site, double const t)
 	return s;
 }
 #else
-JD_FN Seg anchors(Member & M, int const site, double const t)
+template <class MT>
+JD_FN Seg anchors(MT & M, int const site, double const t)
 {
 	Seg s;
 	walk(M, site, t, s.v, s.w, s.tv, s.tw);
@@ -694,15 +722,39 @@ JD_FN void get_next_step(Member & M, double const delta_t)
 	store_anchor(M.slot(M.last), a);
 }
 
-/* get_p, jitced_template.c:474-498 */
-JD_FN double get_p(Member const & M, double const atol, double const rtol)
+/* get_p, jitced_template.c:474-498: p = max_i |err_i| / (atol + rtol·|y_i|), skipping 0/0; a NaN never wins a
+ * comparison. `local_p` is the part over the components one thread owns.
+ * Production build with several components: the largest ratio is found by cross-multiplication
+ * (e_i/τ_i > e_j/τ_j ⟺ e_i·τ_j > e_j·τ_i for τ >= 0) and only that one is divided out — one FP64 division per
+ * attempt instead of one per component (divisions were 10 % of all instructions of the Lyapunov stepper,
+ * profiles/). Near-ties may pick the other candidate, whose ratio then differs by rounding only. */
+template <int NL>
+JD_FN double local_p(double const (&err)[NL], double const (&new_y)[NL], double const atol, double const rtol)
 {
+#if defined(JD_FAST)
+	if (NL > 1)
+	{
+		double best_e = 0.0, best_tol = 1.0;
+		JD_UNROLL
+		for (int i = 0; i < NL; i++)
+		{
+			double const error = fabs(err[i]);
+			double const tolerance = atol+rtol*fabs(new_y[i]);
+			if ((error != 0.0 || tolerance != 0.0) && error*best_tol > best_e*tolerance)
+			{
+				best_e = error;
+				best_tol = tolerance;
+			}
+		}
+		return best_e/best_tol;
+	}
+#endif
 	double p = 0.0;
 	JD_UNROLL
-	for (int i = 0; i < JD_N; i++)
+	for (int i = 0; i < NL; i++)
 	{
-		double const error = fabs(M.err[i]);
-		double const tolerance = atol+rtol*fabs(M.new_y[i]);
+		double const error = fabs(err[i]);
+		double const tolerance = atol+rtol*fabs(new_y[i]);
 		if (error != 0.0 || tolerance != 0.0)
 		{
 			double const x = error/tolerance;
@@ -711,6 +763,11 @@ JD_FN double get_p(Member const & M, double const atol, double const rtol)
 		}
 	}
 	return p;
+}
+
+JD_FN double get_p(Member const & M, double const atol, double const rtol)
+{
+	return local_p<JD_N>(M.err, M.new_y, atol, rtol);
 }
 
 /* check_new_y_diff, jitced_template.c:502-524. `old_y` = state of the tentative anchor that the last
@@ -744,7 +801,8 @@ JD_FN void accept_step(Member & M)
 /* forget, jitced_template.c:534-561: drop anchors while the next one is still older than the threshold.
  * The anchor times are inspected eight at a time (independent loads in flight together) instead of one
  * after the other; which anchor becomes the first one is unchanged. */
-JD_FN void forget(Member & M, double const delay)
+template <class MT>
+JD_FN void forget(MT & M, double const delay)
 {
 	double const threshold = fmin(M.cur_t - delay, M.last_start);
 	bool moved = false;
@@ -807,7 +865,8 @@ JD_FN void get_recent_state(Member const & M, double const t, double * const out
 JD_FN double sigmoid(double const x) { return (tanh(x)+1)/2; }
 
 /* _jitcdde.py:745-765: UnsuccessfulIntegration becomes a per-member status */
-JD_FN void control_for_min_step(Member & M, jdde_int_params const & P)
+template <class MT>
+JD_FN void control_for_min_step(MT & M, jdde_int_params const & P)
 {
 	if (M.dt < P.min_step)
 		M.status = JDDE_STATUS_MIN_STEP;
@@ -815,27 +874,29 @@ JD_FN void control_for_min_step(Member & M, jdde_int_params const & P)
 
 /* _increase_chance (_jitcdde.py:767-773) and the deterministic do_increase (:733-741); cold: only after a
  * past-within-step event. Operates on the controller memory in the per-member arrays. */
-JD_FN bool pws_allows_increase(Member const & M, jdde_problem const & P, double const new_dt)
+template <class MT>
+JD_FN bool pws_allows_increase(MT & M, jdde_problem const & P, double const new_dt)
 {
 	jdde_int_params const & I = P.P;
-	double const q = new_dt/P.last_pws[M.index];
+	double const q = new_dt/ctl_last_pws(M, P);
 	double const is_explicit = sigmoid(1-q);
 	double const far_from_explicit = sigmoid(q-I.pws_factor);
-	double const few_iterations = sigmoid(1-P.count[M.index]/I.pws_factor);
+	double const few_iterations = sigmoid(1-ctl_count(M, P)/I.pws_factor);
 	double const profile = is_explicit+far_from_explicit*few_iterations;
 	double const chance = profile + I.pws_base_increase_chance*(1-profile);
 
-	double credit = P.credit[M.index] + chance;
+	double credit = ctl_credit(M, P) + chance;
 	bool const increase = credit >= 0.9;
 	if (increase)
 		credit = 0.0;
-	P.credit[M.index] = credit;
+	ctl_credit(M, P) = credit;
 	return increase;
 }
 
 /* _adjust_step_size, _jitcdde.py:775-794 with q = 3 (:726). The two fractional powers use the
  * libm-free roots of jdde_math.h so that CPU oracle and GPU take bit-identical step sizes. */
-JD_FN bool adjust_step_size(Member & M, jdde_problem const & PR)
+template <class MT>
+JD_FN bool adjust_step_size(MT & M, jdde_problem const & PR)
 {
 	jdde_int_params const & P = PR.P;
 	double const p = get_p(M, P.atol, P.rtol);
@@ -854,8 +915,8 @@ JD_FN bool adjust_step_size(Member & M, jdde_problem const & PR)
 			M.dt = new_dt;
 			if (M.pws_pending)
 			{
-				PR.count[M.index] = 0;
-				PR.last_pws[M.index] = 0.0;
+				ctl_count(M, PR) = 0;
+				ctl_last_pws(M, PR) = 0.0;
 				M.pws_pending = false;
 			}
 		}
@@ -866,18 +927,19 @@ JD_FN bool adjust_step_size(Member & M, jdde_problem const & PR)
 /* try_single_step, _jitcdde.py:838-861. Written as one loop so that the step code is instantiated once:
  * pass 0 is the attempt with `length`; if a delayed lookup reached into the step (past within step),
  * passes 1..pws_max_iterations repeat the step with self.dt (sic, :853) until two successive results agree. */
-JD_FN bool try_single_step(Member & M, jdde_problem const & PR, double const length)
+template <class MT>
+JD_FN bool try_single_step(MT & M, jdde_problem const & PR, double const length)
 {
 	jdde_int_params const & P = PR.P;
 	double step = length;
 	int count = 0;
 	for (;;)
 	{
-		double old_y[JD_N];
+		double old_y[MT::NL];
 		if (count)
 		{
 			JD_UNROLL
-			for (int i = 0; i < JD_N; i++)
+			for (int i = 0; i < MT::NL; i++)
 				old_y[i] = M.new_y[i];
 		}
 		get_next_step(M, step);
@@ -885,7 +947,7 @@ JD_FN bool try_single_step(Member & M, jdde_problem const & PR, double const len
 		{
 			if (M.pws == 0.0)
 				break;
-			PR.last_pws[M.index] = M.pws;
+			ctl_last_pws(M, PR) = M.pws;
 			M.pws_pending = true;
 			/* if possible, shrink the step to make the integration explicit */
 			if (M.dt > P.pws_factor*M.pws)
@@ -904,7 +966,7 @@ JD_FN bool try_single_step(Member & M, jdde_problem const & PR, double const len
 			return false;
 		}
 		count++;
-		PR.count[M.index] = count;
+		ctl_count(M, PR) = count;
 		step = M.dt;
 	}
 	return adjust_step_size(M, PR);
@@ -912,7 +974,8 @@ JD_FN bool try_single_step(Member & M, jdde_problem const & PR, double const len
 
 /* Room for one more anchor? The reference's list is unbounded; the ring is not. forget() first
  * (it never removes an anchor a valid lookup can reach), then report overflow. */
-JD_FN bool ensure_room(Member & M, double const max_delay)
+template <class MT>
+JD_FN bool ensure_room(MT & M, double const max_delay)
 {
 	if (M.last+1-M.first <= M.mask)
 		return true;
@@ -925,7 +988,8 @@ JD_FN bool ensure_room(Member & M, double const max_delay)
 
 /* the `while t < target` loops of integrate (_jitcdde.py:830-832) and of
  * step_on_discontinuities (:988-993, steps capped at the target) */
-JD_FN void step_until(Member & M, jdde_problem const & P, double const target, bool const capped, long long const budget)
+template <class MT>
+JD_FN void step_until(MT & M, jdde_problem const & P, double const target, bool const capped, long long const budget)
 {
 	while (M.cur_t < target)
 	{
@@ -1475,7 +1539,7 @@ JD_FN void member_forget(jdde_problem const & P, long long const m)
 
 #if JD_NBASIC != JD_N
 /* orthonormalise and, if old_t is given, the tail of jitcdde_lyap.integrate (_jitcdde.py:1162-1172) */
-JD_FN void member_orthonormalise(jdde_problem const & P, long long const m, int const n_lyap, double const delay, double * const norms, double const * const old_t, double * const lyaps, double * const delta_t)
+JD_FN void member_orthonormalise(jdde_problem const & P, long long const m, int const n_lyap, double const delay, double * const norms, double * const old_t, double * const lyaps, double * const delta_t)
 {
 	Member M;
 	load_member(P, m, M);
@@ -1484,7 +1548,13 @@ JD_FN void member_orthonormalise(jdde_problem const & P, long long const m, int 
 	double nrm[JD_N/JD_NBASIC];
 	if (old_t)
 	{
+		/* A member that reached the target is orthonormalised once: its old_t is then marked (NaN), so that the
+		 * repetition of the call for members that had stopped on the way (full ring, jdde_resume) leaves its
+		 * exponents alone. */
+		if (old_t[m] != old_t[m])
+			return;
 		double const dt = M.cur_t-old_t[m];
+		old_t[m] = NAN;
 		delta_t[m] = dt;
 		if (dt != 0)
 		{
@@ -1508,5 +1578,6 @@ JD_FN void member_orthonormalise(jdde_problem const & P, long long const m, int 
 } // namespace jdde
 
 #include "jdde_team.cuh"
+#include "jdde_group.cuh"
 
 #endif

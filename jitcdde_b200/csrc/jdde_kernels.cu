@@ -23,9 +23,20 @@
 #ifndef JD_MIN_BLOCKS
 #define JD_MIN_BLOCKS 1
 #endif
+#ifndef JD_GROUP_BLOCK
+#define JD_GROUP_BLOCK 64
+#endif
+#ifndef JD_GROUP_MIN_BLOCKS
+#define JD_GROUP_MIN_BLOCKS 1
+#endif
 
 extern "C" __device__ const jdde_image_desc_t jdde_image_desc = {
-	JDDE_IMAGE_MAGIC, JDDE_ABI_VERSION, JD_N, JD_NBASIC, JD_NSITES, JD_NPARAMS, JD_A, JD_BLOCK, JD_WIN_SMEM_BYTES
+	JDDE_IMAGE_MAGIC, JDDE_ABI_VERSION, JD_N, JD_NBASIC, JD_NSITES, JD_NPARAMS, JD_A, JD_BLOCK, JD_WIN_SMEM_BYTES,
+#if defined(JD_GROUP)
+	JD_GROUP, JD_GROUP_BLOCK, JD_GROUP_WINDOW ? (int)((JD_GROUP_BLOCK/32)*JD_GROUPS_PER_WARP*JD_GROUP_WIN_DOUBLES*sizeof(double)) : 0
+#else
+	0, 0, 0
+#endif
 };
 
 #define JD_MEMBER_INDEX() ((long long)blockIdx.x*blockDim.x+threadIdx.x)
@@ -54,6 +65,24 @@ jdde_k_integrate(jdde_problem const P, double const * const targets, int const p
 	if (m < P.n_members)
 		jdde::member_integrate(P, m, targets, per_member, n_steps, resume, out, n_out, budget);
 }
+
+#if defined(JD_GROUP)
+/* the same for Lyapunov systems with a group of JD_GROUP lanes per member (jdde_group.cuh): 32/JD_GROUP members per warp */
+extern "C" __global__ void __launch_bounds__(JD_GROUP_BLOCK, JD_GROUP_MIN_BLOCKS)
+jdde_k_integrate_group(jdde_problem const P, double const * const targets, int const per_member, int const n_steps, int const resume, double * const out, int const n_out, long long const budget)
+{
+	int const lane = threadIdx.x & 31;
+	int const group = lane/JD_GROUP;
+	if (group >= JD_GROUPS_PER_WARP)
+		return;
+	long long const warp = ((long long)blockIdx.x*blockDim.x+threadIdx.x) >> 5;
+	long long const m = warp*JD_GROUPS_PER_WARP+group;
+	extern __shared__ double jd_group_smem[];     /* JD_GROUP_WINDOW: staging area, JD_GROUP_WIN_DOUBLES per member of the block */
+	if (m < P.n_members)
+		jdde::group_integrate(P, m, lane-group*JD_GROUP, group*JD_GROUP, targets, per_member, n_steps, resume, out, n_out, budget,
+			jd_group_smem + (size_t)((threadIdx.x >> 5)*JD_GROUPS_PER_WARP+group)*JD_GROUP_WIN_DOUBLES);
+}
+#endif
 
 extern "C" __global__ void __launch_bounds__(JD_BLOCK)
 jdde_k_integrate_blindly(jdde_problem const P, double const * const targets, int const per_member, double const step, double * const out, int const n_out, double * const lyaps, double * const total_time)
@@ -168,7 +197,7 @@ jdde_k_regrow(jdde_problem const P, double * const new_ring, int const new_cap)
 
 #if JD_NBASIC != JD_N
 extern "C" __global__ void __launch_bounds__(JD_BLOCK)
-jdde_k_orthonormalise(jdde_problem const P, int const n_lyap, double const delay, double * const norms, double const * const old_t, double * const lyaps, double * const delta_t)
+jdde_k_orthonormalise(jdde_problem const P, int const n_lyap, double const delay, double * const norms, double * const old_t, double * const lyaps, double * const delta_t)
 {
 	long long const m = JD_MEMBER_INDEX();
 	if (m < P.n_members)
@@ -177,7 +206,7 @@ jdde_k_orthonormalise(jdde_problem const P, int const n_lyap, double const delay
 
 /* one thread block per member (jdde_team.cuh); dynamic shared memory: blockDim.x + (capacity|1)·(1 + 2·n_basic·n_lyap) doubles */
 extern "C" __global__ void __launch_bounds__(JD_TEAM_BLOCK)
-jdde_k_orthonormalise_team(jdde_problem const P, int const n_lyap, double const delay, double * const norms, double const * const old_t, double * const lyaps, double * const delta_t, int const capacity)
+jdde_k_orthonormalise_team(jdde_problem const P, int const n_lyap, double const delay, double * const norms, double * const old_t, double * const lyaps, double * const delta_t, int const capacity)
 {
 	extern __shared__ double jd_team_smem[];
 	jdde::Team const T = { (int)threadIdx.x, (int)blockDim.x, jd_team_smem };

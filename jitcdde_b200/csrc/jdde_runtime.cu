@@ -29,7 +29,7 @@ struct Kernels
 {
 	cudaKernel_t set_past = nullptr, reset_controller = nullptr, integrate = nullptr, integrate_blindly = nullptr,
 		jump = nullptr, forget = nullptr, get = nullptr, clear_status = nullptr, sum_counters = nullptr, count_failed = nullptr,
-		regrow = nullptr, orthonormalise = nullptr, orthonormalise_team = nullptr;
+		regrow = nullptr, orthonormalise = nullptr, orthonormalise_team = nullptr, integrate_group = nullptr;
 };
 
 } // namespace
@@ -43,6 +43,7 @@ struct jdde_handle
 	Kernels k;
 	int block = 128;
 	int smem_bytes = 0;      /* dynamic shared memory per block (anchor staging window of the image) */
+	int group_lanes = 0, group_block = 0, group_smem_bytes = 0;   /* jdde_k_integrate_group: lanes per member, block size (0: one thread per member) */
 	/* pipelined sampling (jdde_integrate_async): second result buffer, copy stream, events per buffer */
 	cudaStream_t copy_stream = nullptr;
 	double * d_out_alt = nullptr;
@@ -160,13 +161,27 @@ int launch(jdde_handle * h, cudaKernel_t kernel, void ** args)
 	return JDDE_OK;
 }
 
+/* integrate / step_on_discontinuities: Lyapunov images bring a kernel with a group of lanes per member
+ * (csrc/jdde_group.cuh; 32/lanes members per warp), all others one thread per member */
+int launch_integrate(jdde_handle * h, void ** args)
+{
+	if (!h->group_lanes)
+		return launch(h, h->k.integrate, args);
+	long long const N = h->desc.n_members;
+	long long const per_block = (long long)(h->group_block/32)*(32/h->group_lanes);
+	unsigned const grid = (unsigned)((N + per_block - 1)/per_block);
+	JD_CUDA(h, cudaLaunchKernel((const void *)h->k.integrate_group, dim3(grid), dim3(h->group_block), args, (size_t)h->group_smem_bytes, h->stream));
+	h->launches++;
+	return JDDE_OK;
+}
+
 /*
  * Gram–Schmidt over the history with one thread block per member (csrc/jdde_team.cuh). The tangent part of a member's
  * anchors is staged in shared memory: up to the ring capacity if that fits into the opt-in maximum of the device
  * (227 KB on sm_100), else as many anchors as fit (longer histories are streamed through in tiles, pass by pass).
  * JITCDDE_B200_TEAM=0 selects the one-thread-per-member kernel.
  */
-int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * norms, const double * old_t, double * lyaps, double * delta_t)
+int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * norms, double * old_t, double * lyaps, double * delta_t)
 {
 	const char * const choice = getenv("JITCDDE_B200_TEAM");
 	if (!h->k.orthonormalise_team || (choice && choice[0] == '0'))
@@ -398,6 +413,9 @@ int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
 	}
 	h->block = d.block;
 	h->smem_bytes = d.smem_bytes;
+	h->group_lanes = d.group_lanes;
+	h->group_block = d.group_block;
+	h->group_smem_bytes = d.group_smem_bytes;
 	h->team_smem_max = 0;
 
 	struct { const char * name; cudaKernel_t * slot; bool required; } const table[] = {
@@ -414,6 +432,7 @@ int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
 		{"jdde_k_regrow", &h->k.regrow, true},
 		{"jdde_k_orthonormalise", &h->k.orthonormalise, false},
 		{"jdde_k_orthonormalise_team", &h->k.orthonormalise_team, false},
+		{"jdde_k_integrate_group", &h->k.integrate_group, false},
 	};
 	for (auto const & entry : table)
 	{
@@ -426,6 +445,10 @@ int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
 				return fail(h, JDDE_E_IMAGE, std::string("image lacks kernel ") + entry.name);
 		}
 	}
+	if (h->group_lanes && !h->k.integrate_group)
+		return fail(h, JDDE_E_IMAGE, "image announces a lane group per member but lacks jdde_k_integrate_group");
+	if (h->group_lanes && h->group_smem_bytes > 48*1024)
+		JD_CUDA(h, cudaFuncSetAttribute((const void *)h->k.integrate_group, cudaFuncAttributeMaxDynamicSharedMemorySize, h->group_smem_bytes));
 	return JDDE_OK;
 }
 
@@ -563,7 +586,7 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 		int pm = per_member ? 1 : 0;
 		long long budget = h->budget;
 		void * args[] = { &h->P, &d_targets, &pm, &n_steps, &resume, &d_result, &n_out, &budget };
-		if ((rc = launch(h, h->k.integrate, args))) return rc;
+		if ((rc = launch_integrate(h, args))) return rc;
 		JD_CUDA(h, cudaEventRecord(h->kernel_done[slot], h->stream));
 		h->result_direct[slot] = direct != nullptr;
 		h->result_queued[slot] = true;
@@ -586,7 +609,7 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 	long long budget = h->budget;
 	double * d_result = direct ? direct : h->d_out;
 	void * args[] = { &h->P, &d_targets, &pm, &n_steps, &resume, &d_result, &n_out, &budget };
-	if ((rc = launch(h, h->k.integrate, args))) return rc;
+	if ((rc = launch_integrate(h, args))) return rc;
 	if (direct)
 	{
 		/* the states are already on their way into out_state; they have arrived when the kernel has ended */

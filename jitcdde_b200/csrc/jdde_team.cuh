@@ -278,9 +278,11 @@ JD_FN void team_gram_schmidt(Pass && pass, int const n_lyap, double * const norm
  * (the team's scratch lies elsewhere); capacity >= 4 anchors.
  */
 JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, long long const m, int const n_lyap, double const delay,
-	double * const norms, double const * const old_t, double * const lyaps, double * const delta_t, double * const shared, int const capacity)
+	double * const norms, double * const old_t, double * const lyaps, double * const delta_t, double * const shared, int const capacity)
 {
 	if (P.status[m] != JDDE_STATUS_OK)
+		return;
+	if (old_t && old_t[m] != old_t[m])      /* already orthonormalised by the call that is being resumed (member_orthonormalise) */
 		return;
 	constexpr int R = 2*JD_NBASIC;
 	Tangents H;
@@ -355,7 +357,10 @@ JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, lo
 				norms[(size_t)m*n_lyap+i] = nrm[i];
 		}
 		else if (old_t)
+		{
 			delta_t[m] = dt;
+			old_t[m] = NAN;
+		}
 	});
 }
 

@@ -224,7 +224,7 @@ int jdde_adjust_diff(jdde_handle * h, double shift_ratio, double * minima, doubl
 #if JD_NBASIC != JD_N
 /* JITCDDE_TWIN_TEAM = staging capacity in anchors (>= 4; shorter than a history: streamed in tiles) runs the team code of csrc/jdde_team.cuh with a
  * one-thread team instead of member_orthonormalise */
-static void orthonormalise_all(jdde_handle * h, int n_lyap, double delay, double * norms, double const * old_t, double * lyaps, double * delta_t)
+static void orthonormalise_all(jdde_handle * h, int n_lyap, double delay, double * norms, double * old_t, double * lyaps, double * delta_t)
 {
 	const char * const team = getenv("JITCDDE_TWIN_TEAM");
 	if (!team)

@@ -157,7 +157,7 @@ def lyap_program(system, n_lyap, simplify=True):
 	helpers = system.get("helpers", ())
 	delays = _codegen.get_delays(basic, helpers)
 	extended = _codegen.tangent_vector_f(basic, helpers, len(basic), n_lyap, delays, simplify=simplify)
-	return _codegen.generate(extended, control_pars=system.get("control_pars", ())), len(basic)
+	return _codegen.generate(extended, control_pars=system.get("control_pars", ()), blocks=(len(basic), n_lyap)), len(basic)
 
 
 def mg_grid(N, seed_stride=True):

@@ -57,3 +57,27 @@ def test_ensembles_of_other_configurations(twin):
 				np.testing.assert_allclose(ours[key], theirs[key], rtol=4e-16, atol=1e-17)
 			else:
 				assert np.array_equal(ours[key], theirs[key]), (product.__name__, key, np.max(np.abs(ours[key]-theirs[key])))
+
+
+def test_lyapunov_resume_after_partial_ring_overflow(twin):
+	"""Mackey–Glass with per-member delays and 2 exponents: with a ring of 32 anchors the members with long delays
+	fill it during a call, the ring grows and the call is resumed. Members that had already reached the target
+	(and were orthonormalised) must keep their exponents: same results as with a ring that never overflows."""
+	import sympy
+	from jitcdde_b200 import jitcdde_lyap, t, y
+	beta, tau = sympy.symbols("beta tau")
+	f = [beta*y(0, t-tau)/(1+y(0, t-tau)**10) - 0.1*y(0)]
+	pars = np.stack([np.full(12, 0.25), np.linspace(4.0, 26.0, 12)], axis=1)
+	results = []
+	for capacity in (32, 512):
+		DDE = jitcdde_lyap(f, n_lyap=2, control_pars=[beta, tau], max_delay=26.0, delays=[0, tau], n_members=12, verbose=False,
+			verification=True, ring_capacity=capacity)
+		DDE.constant_past([1.0])
+		DDE.set_parameters(pars)
+		DDE.initial_discontinuities_handled = True
+		out = [DDE.integrate(T) for T in (30.0, 60.0, 90.0)]
+		results.append((out, DDE._engine.ring_capacity))
+	assert results[0][1] > 32, "the small ring was meant to overflow"
+	for small, big in zip(results[0][0], results[1][0]):
+		for a, b in zip(small, big):
+			assert np.array_equal(a, b)

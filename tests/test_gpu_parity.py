@@ -212,6 +212,24 @@ def test_lyapunov_ensemble_c3():
 	np.testing.assert_allclose(ours["lyaps"], theirs["lyaps"], rtol=1e-13, atol=1e-15)
 
 
+def test_lane_group_stepper_equals_one_thread_per_member(monkeypatch):
+	"""Lyapunov systems are integrated by 1 + n_lyap lanes per member (csrc/jdde_group.cuh); with
+	JITCDDE_B200_GROUP=0 by one thread per member. Same statements per component → bit-identical in the verification build
+	(N is no multiple of the 6 members a warp holds; step_on_discontinuities and past-within-step included)."""
+	N = 250
+	for verification in (True, False):
+		group = scenarios.product_c3(N, verification=verification)
+		monkeypatch.setenv("JITCDDE_B200_GROUP", "0")
+		solo = scenarios.product_c3(N, verification=verification)
+		monkeypatch.delenv("JITCDDE_B200_GROUP")
+		for key in group:
+			if verification:
+				assert np.array_equal(group[key], solo[key]), key
+			elif key in ("out", "weights"):
+				# FMA contraction is the compiler's choice per kernel; the system is chaotic (λ ≈ 0.08 over 50 time units)
+				np.testing.assert_allclose(group[key], solo[key], rtol=1e-6, atol=1e-8)
+
+
 def test_state_dependent_ensemble_c5a():
 	"""BASELINE.json configs[4], state-dependent delay with per-member pasts (divergent lookups, backward
 	moves of the cursor, max_delay = 1e10 so nothing is ever forgotten and rings grow)."""

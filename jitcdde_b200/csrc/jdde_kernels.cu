@@ -204,16 +204,25 @@ jdde_k_orthonormalise(jdde_problem const P, int const n_lyap, double const delay
 		jdde::member_orthonormalise(P, m, n_lyap, delay, norms, old_t, lyaps, delta_t);
 }
 
-/* one thread block per member (jdde_team.cuh); dynamic shared memory: blockDim.x + (capacity|1)·(1 + 2·n_basic·n_lyap) doubles */
+/* one thread block per member (jdde_team.cuh); dynamic shared memory: blockDim.x + 2 + (capacity|1)·(1 + 2·n_basic·n_lyap) doubles */
 extern "C" __global__ void __launch_bounds__(JD_TEAM_BLOCK)
-jdde_k_orthonormalise_team(jdde_problem const P, int const n_lyap, double const delay, double * const norms, double * const old_t, double * const lyaps, double * const delta_t, int const capacity)
+jdde_k_orthonormalise_team(jdde_problem const P, int const n_lyap, double const delay, double * const norms, double * const old_t, double * const lyaps, double * const delta_t, int const capacity, int const count_from, int const count_to)
 {
-	extern __shared__ double jd_team_smem[];
-	jdde::Team const T = { (int)threadIdx.x, (int)blockDim.x, jd_team_smem };
-	for (long long m = blockIdx.x; m < P.n_members; m += gridDim.x)
+	extern __shared__ double jd_team_smem[];      /* [blockDim.x] scratch, [2] exchange slots of the cluster, then the staged anchors */
+	unsigned crank, csize;
+	asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+	asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+	jdde::Team T = { (int)threadIdx.x, (int)blockDim.x, jd_team_smem };
+	T.crank = (int)crank;
+	T.csize = (int)csize;
+	/* one cluster (csize blocks; 1 without a cluster launch) per member; the blocks of a cluster run the same members */
+	for (long long m = blockIdx.x/csize; m < P.n_members; m += gridDim.x/csize)
 	{
-		jdde::team_member_orthonormalise(T, P, m, n_lyap, delay, norms, old_t, lyaps, delta_t, jd_team_smem+blockDim.x, capacity);
+		jdde::team_member_orthonormalise(T, P, m, n_lyap, delay, norms, old_t, lyaps, delta_t, jd_team_smem+blockDim.x+2, capacity, count_from, count_to);
 		__syncthreads();
+		T.parity = 0;
+		if (csize > 1)
+			jdde::Team::cluster_sync();     /* nobody reads this block's exchange slots any more */
 	}
 }
 #endif

@@ -207,7 +207,7 @@ int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * no
 		if (cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->desc.device) != cudaSuccess)
 			h->sm_count = 148;
 	}
-	long long const room = h->team_smem_max/(long long)sizeof(double) - block;     /* doubles left for the staged anchors */
+	long long const room = h->team_smem_max/(long long)sizeof(double) - 512 - 2;     /* doubles left for the staged anchors */
 	int capacity = cap;
 	if ((long long)(capacity | 1)*per_anchor > room)
 		capacity = (int)(room/per_anchor) - 1;
@@ -216,21 +216,60 @@ int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * no
 		void * targs[] = { &h->P, &n_lyap, &delay, &norms, &old_t, &lyaps, &delta_t };
 		return launch(h, h->k.orthonormalise, targs);
 	}
-	size_t const smem = sizeof(double)*((size_t)block + (size_t)(capacity | 1)*per_anchor);
+	/*
+	 * One launch per history length class. Members whose live anchors fit one block's staging area (`capacity`) are
+	 * handled by a block each. If the ring can hold more, further launches with a cluster of 2, 4, 8 blocks per member
+	 * take the members with up to 2, 4, 8 × (capacity − 1) live anchors — each block keeps its part resident, sums
+	 * are completed through distributed shared memory (csrc/jdde_team.cuh) — and the last launch also streams
+	 * anything longer. A launch skips the members of the other classes at once. JITCDDE_B200_CLUSTER limits the
+	 * cluster size (1: no clusters, longer histories are streamed by one block).
+	 */
+	const char * const cluster_choice = getenv("JITCDDE_B200_CLUSTER");
+	int const cluster_max = cluster_choice ? atoi(cluster_choice) : 8;
 	long long const N = h->desc.n_members;
-	long long const most = (long long)h->sm_count*32;
-	unsigned const grid = (unsigned)(N < most ? N : most);
-	void * args[] = { &h->P, &n_lyap, &delay, &norms, &old_t, &lyaps, &delta_t, &capacity };
-	if (getenv("JITCDDE_B200_DEBUG"))      /* launch shape and kernel attributes on stderr */
+	int count_from = 0;
+	for (int cluster = 1; count_from <= cap; cluster *= 2)
 	{
-		cudaFuncAttributes fa{};
-		cudaError_t const e = cudaFuncGetAttributes(&fa, (const void *)h->k.orthonormalise_team);
-		fprintf(stderr, "[jdde] orthonormalise_team: grid %u block %d smem %zu capacity %d (ring %d) smem_max %d | attributes: %s maxThreads %d regs %d local %zu maxDynamic %d static %zu\n",
-			grid, block, smem, capacity, cap, h->team_smem_max, cudaGetErrorString(e), fa.maxThreadsPerBlock, fa.numRegs, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes);
-		(void)cudaGetLastError();
+		long long const fits = cluster == 1 ? capacity : (long long)cluster*(capacity-1);
+		bool const final_launch = fits >= cap || 2*cluster > cluster_max;
+		int count_to = final_launch ? 0x7fffffff : (int)fits;
+		int const threads = cluster == 1 ? block : 512;
+		size_t const smem = sizeof(double)*((size_t)threads + 2 + (size_t)(capacity | 1)*per_anchor);
+		/* cluster launches: one wave of clusters looping over the members (blocks of 200 KB start slowly) */
+		long long const most = cluster == 1 ? (long long)h->sm_count*32 : (long long)h->sm_count/cluster;
+		unsigned const grid = (unsigned)(N < most ? N : most)*cluster;
+		void * args[] = { &h->P, &n_lyap, &delay, &norms, &old_t, &lyaps, &delta_t, &capacity, &count_from, &count_to };
+		if (getenv("JITCDDE_B200_DEBUG"))      /* launch shape and kernel attributes on stderr */
+		{
+			cudaFuncAttributes fa{};
+			cudaError_t const e = cudaFuncGetAttributes(&fa, (const void *)h->k.orthonormalise_team);
+			fprintf(stderr, "[jdde] orthonormalise_team: grid %u block %d cluster %d smem %zu capacity %d (ring %d) live anchors %d..%d smem_max %d | attributes: %s maxThreads %d regs %d local %zu maxDynamic %d static %zu\n",
+				grid, threads, cluster, smem, capacity, cap, count_from, count_to, h->team_smem_max, cudaGetErrorString(e), fa.maxThreadsPerBlock, fa.numRegs, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes, fa.sharedSizeBytes);
+			(void)cudaGetLastError();
+		}
+		if (cluster > 1)
+		{
+			cudaLaunchConfig_t config{};
+			config.gridDim = dim3(grid);
+			config.blockDim = dim3(threads);
+			config.dynamicSmemBytes = smem;
+			config.stream = h->stream;
+			cudaLaunchAttribute attribute{};
+			attribute.id = cudaLaunchAttributeClusterDimension;
+			attribute.val.clusterDim.x = cluster;
+			attribute.val.clusterDim.y = 1;
+			attribute.val.clusterDim.z = 1;
+			config.attrs = &attribute;
+			config.numAttrs = 1;
+			JD_CUDA(h, cudaLaunchKernelExC(&config, (const void *)h->k.orthonormalise_team, args));
+		}
+		else
+			JD_CUDA(h, cudaLaunchKernel((const void *)h->k.orthonormalise_team, dim3(grid), dim3(threads), args, smem, h->stream));
+		h->launches++;
+		if (final_launch)
+			break;
+		count_from = count_to+1;
 	}
-	JD_CUDA(h, cudaLaunchKernel((const void *)h->k.orthonormalise_team, dim3(grid), dim3(block), args, smem, h->stream));
-	h->launches++;
 	return JDDE_OK;
 }
 

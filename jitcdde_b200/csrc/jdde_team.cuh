@@ -33,7 +33,29 @@ namespace jdde {
 struct Team
 {
 	int rank, size;
-	double * scratch;       /* shared by the team: at least `size` doubles */
+	double * scratch;       /* shared by the team: at least `size` doubles, followed by the two exchange slots of the cluster */
+	/* A thread-block CLUSTER per member (jdde_k_orthonormalise_team launched with a cluster dimension): every block
+	 * of the cluster keeps its own contiguous part of the member's anchors resident in its shared memory; sums over
+	 * segments are completed across the blocks through distributed shared memory (sum() below). 1: no cluster. */
+	int crank = 0, csize = 1;
+	mutable int parity = 0;  /* which of the two exchange slots the next cluster-wide sum uses */
+
+#if defined(__CUDA_ARCH__)
+	__device__ __forceinline__ static void cluster_sync()
+	{
+		asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+	}
+	/* the exchange slot `which` of block `block_rank` of this cluster (distributed shared memory) */
+	__device__ __forceinline__ double remote_slot(int const block_rank, int const which) const
+	{
+		unsigned const local = (unsigned)__cvta_generic_to_shared(scratch+size+which);
+		unsigned remote;
+		asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(block_rank));
+		double value;
+		asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(value) : "r"(remote) : "memory");
+		return value;
+	}
+#endif
 
 	/* body(e) for all e < count, then a barrier */
 	template <class F>
@@ -54,6 +76,71 @@ struct Team
 	JD_FN double sum(double const initial, int const count, F && body) const
 	{
 #if defined(__CUDA_ARCH__)
+		if (csize > 1)
+			return cluster_sum(initial, count, body);
+		return block_sum(initial, count, body);
+#else
+		double total = initial;
+		for (int e = 0; e < count; e++)
+			total += body(e);
+		return total;
+#endif
+	}
+
+#if defined(__CUDA_ARCH__)
+	/*
+	 * Sum over the segments of all blocks of the cluster; every block calls this with its own segments.
+	 * Production build: the blocks reduce their parts concurrently, publish them in their exchange slot, and after
+	 * one cluster barrier everybody adds the csize parts in rank order. Verification build: the reference adds the
+	 * segments in ascending order into one accumulator, so the running total is handed from block to block (block r
+	 * continues from the slot of block r−1); the per-segment products are still formed concurrently.
+	 * The two exchange slots alternate, so a slot is rewritten only after a later cluster barrier has shown that
+	 * everybody has read it.
+	 */
+	template <class F>
+	__device__ __forceinline__ double cluster_sum(double const initial, int const count, F && body) const
+	{
+		int const which = parity;
+		parity ^= 1;
+		double total;
+#if defined(JD_FAST)
+		total = block_sum(0.0, count, body);
+		if (rank == 0)
+			scratch[size+which] = total;
+		cluster_sync();
+		if (rank == 0)
+		{
+			total = initial;
+			for (int r = 0; r < csize; r++)
+				total += remote_slot(r, which);
+			scratch[0] = total;
+		}
+#else
+		for (int r = 0; r < csize; r++)
+		{
+			if (crank == r)
+			{
+				double running = initial;
+				if (r > 0 && rank == 0)
+					running = remote_slot(r-1, which);
+				total = block_sum(running, count, body);      /* only thread 0's `running` enters the sum */
+				if (rank == 0)
+					scratch[size+which] = total;
+			}
+			cluster_sync();
+		}
+		if (rank == 0)
+			scratch[0] = remote_slot(csize-1, which);
+#endif
+		__syncthreads();
+		total = scratch[0];
+		__syncthreads();
+		return total;
+	}
+
+	template <class F>
+	__device__ __forceinline__ double block_sum(double const initial, int const count, F && body) const
+	{
 		double total = 0;
 #if defined(JD_FAST)
 		for (int e = rank; e < count; e += size)
@@ -92,13 +179,8 @@ struct Team
 		total = scratch[0];
 		__syncthreads();
 		return total;
-#else
-		double total = initial;
-		for (int e = 0; e < count; e++)
-			total += body(e);
-		return total;
-#endif
 	}
+#endif
 };
 
 /* anchors [first, first+count) of a member, staged in shared memory: times and the tangent rows
@@ -277,9 +359,11 @@ JD_FN void team_gram_schmidt(Pass && pass, int const n_lyap, double * const norm
  * member_orthonormalise (jdde_engine.cuh) for a team. `shared` = rows[2·n_basic·n_lyap + 1][ks] with ks = capacity | 1
  * (the team's scratch lies elsewhere); capacity >= 4 anchors.
  */
-JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, long long const m, int const n_lyap, double const delay,
-	double * const norms, double * const old_t, double * const lyaps, double * const delta_t, double * const shared, int const capacity)
+JD_FN void team_member_orthonormalise(Team const & T_given, jdde_problem const & P, long long const m, int const n_lyap, double const delay,
+	double * const norms, double * const old_t, double * const lyaps, double * const delta_t, double * const shared, int const capacity,
+	int const count_from = 0, int const count_to = 0x7fffffff)
 {
+	Team T = T_given;
 	if (P.status[m] != JDDE_STATUS_OK)
 		return;
 	if (old_t && old_t[m] != old_t[m])      /* already orthonormalised by the call that is being resumed (member_orthonormalise) */
@@ -292,6 +376,8 @@ JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, lo
 	H.rows = shared;
 	H.times = shared + R*n_lyap*H.ks;
 	int const first = P.first[m], count = P.last[m]-first+1;
+	if (count < count_from || count > count_to)      /* this launch is for histories of another length (jdde_runtime.cu) */
+		return;
 	double const cur_t = H.ring[(size_t)(P.current[m] & H.mask)*JD_A];
 	double const threshold = cur_t-delay;
 
@@ -313,8 +399,29 @@ JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, lo
 	}
 
 	double nrm[JD_N/JD_NBASIC];
-	if (count <= capacity)
+	bool const writer = T.crank == 0;       /* the block of a cluster that reports the results */
+	if (T.csize > 1 && (count + T.csize - 1)/T.csize + 1 <= capacity)
 	{
+		/* resident in the cluster: block r keeps the anchors [lo, hi) plus a copy of anchor lo−1 (for the segment between
+		 * the parts; it receives the same updates, computed from the same operands, and is not written back) */
+		int const chunk = (count + T.csize - 1)/T.csize;
+		int const lo = T.crank*chunk < count ? T.crank*chunk : count;
+		int const hi = lo+chunk < count ? lo+chunk : count;
+		int const halo = (lo > 0 && hi > lo) ? 1 : 0;
+		H.first = first+lo-halo;
+		H.count = hi-lo+halo;
+		stage(T, H, n_lyap, true, 0);
+		team_gram_schmidt([&](int const sub_i, int const sub_j, double const sub_factor, int const scale_i, double const scale_factor, int const acc_1, int const acc_2)
+		{
+			return team_pass(T, H, threshold, sub_i, sub_j, sub_factor, scale_i, scale_factor, acc_1, acc_2, 0, lo == 0, 0.0);
+		}, n_lyap, nrm);
+		stage(T, H, n_lyap, false, halo);
+	}
+	else if (T.csize > 1 && !writer)
+		return;                             /* too long even for the cluster: its first block streams the member alone */
+	else if (count <= capacity)
+	{
+		T.csize = 1;
 		/* resident: one read, all passes on chip, one write */
 		H.first = first;
 		H.count = count;
@@ -327,6 +434,7 @@ JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, lo
 	}
 	else
 	{
+		T.csize = 1;
 		/* streamed: every pass goes through the anchors in tiles [lo, hi); a tile is staged together with anchor lo-1 */
 		team_gram_schmidt([&](int const sub_i, int const sub_j, double const sub_factor, int const scale_i, double const scale_factor, int const acc_1, int const acc_2)
 		{
@@ -347,6 +455,8 @@ JD_FN void team_member_orthonormalise(Team const & T, jdde_problem const & P, lo
 		}, n_lyap, nrm);
 	}
 
+	if (!writer)
+		return;
 	T.for_each(n_lyap+1, [&](int const i)
 	{
 		if (i < n_lyap)

@@ -230,6 +230,21 @@ def test_lane_group_stepper_equals_one_thread_per_member(monkeypatch):
 				np.testing.assert_allclose(group[key], solo[key], rtol=1e-6, atol=1e-8)
 
 
+@pytest.mark.parametrize("ring_capacity", [1024, 2048, 4096])
+def test_cluster_orthonormalisation_is_bitwise_identical(ring_capacity):
+	"""Rings too long for one block's shared memory are orthonormalised by a thread-block cluster per member (2, 4, 8
+	blocks, sums through distributed shared memory; csrc/jdde_team.cuh). The verification build hands the running sums
+	from block to block in the reference's order: bit-identical with the oracle; the production build agrees to rounding."""
+	N = 40
+	theirs = scenarios.oracle_c3(N)
+	ours = scenarios.product_c3(N, verification=True, ring_capacity=ring_capacity)
+	for key in ("out", "weights", "accepted", "rejected"):
+		assert np.array_equal(ours[key], theirs[key]), key
+	np.testing.assert_allclose(ours["lyaps"], theirs["lyaps"], rtol=1e-13, atol=1e-15)
+	fast = scenarios.product_c3(N, verification=False, ring_capacity=ring_capacity)
+	np.testing.assert_allclose(fast["lyaps"][:2], theirs["lyaps"][:2], rtol=1e-6, atol=1e-8)
+
+
 def test_state_dependent_ensemble_c5a():
 	"""BASELINE.json configs[4], state-dependent delay with per-member pasts (divergent lookups, backward
 	moves of the cursor, max_delay = 1e10 so nothing is ever forgotten and rings grow)."""

@@ -69,7 +69,9 @@ namespace jdde {
 #ifndef JD_GROUP_WINDOW
 #define JD_GROUP_WINDOW 0
 #endif
-#define JD_GROUP_WIN_DOUBLES ((JD_NSITES > 0 ? JD_NSITES : 1)*4*JD_A)      /* per member */
+/* per member; + 16 bytes so that the areas of the members of a warp start in different banks (a multiple of 128 bytes
+ * put equal offsets of all members into the same bank: 6-way conflicts on every access, profiles/) */
+#define JD_GROUP_WIN_DOUBLES ((JD_NSITES > 0 ? JD_NSITES : 1)*4*JD_A + 2)
 
 struct GWindow
 {

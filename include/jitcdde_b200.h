@@ -173,6 +173,32 @@ int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t per_memb
  * step; lyaps = average over the steps of log(norms)/dt; total_time [n_members]. */
 int jdde_integrate_blindly_lyap(jdde_handle * h, const double * target, int32_t per_member, double step, double * out_state, double * lyaps, double * total_time, int32_t * status);
 
+/* ---- restricted and transversal Lyapunov exponents ------------------------------------- */
+
+#define JDDE_PROJECT_RESTRICTED 1
+#define JDDE_PROJECT_TRANSVERSAL 2
+
+/* What jitcdde_restricted_lyap / jitcdde_transversal_lyap do to the separation function after integrating
+ * (the image must have been built with -DJD_PROJECT). The arrays are copied.
+ * mode JDDE_PROJECT_RESTRICTED (needs n = n_basic·(2 + 2·n_vectors)): remove_state_component,
+ *   remove_diff_component (jitced_template.c:973-1003) for the listed components, then remove_projections
+ *   (:885-971) for `vectors` [n_vectors][2][n_basic] (state part, derivative part), as
+ *   jitcdde_restricted_lyap.remove_projections calls them (_jitcdde.py:1278-1284);
+ * mode JDDE_PROJECT_TRANSVERSAL: normalise_indices (jitced_template.c:1007-1083) over `indices` (the reference
+ *   compiles them into the module as tangent_indices, _jitcdde.py:571). */
+int jdde_set_projector(jdde_handle * h, int32_t mode, const double * vectors, int32_t n_vectors,
+	const int32_t * state_components, int32_t n_state_components, const int32_t * diff_components, int32_t n_diff_components,
+	const int32_t * indices, int32_t n_indices);
+
+/* apply the projector once with the given delay (the reference passes max_delay); norms [n_members] = norm of the
+ * separation function before its normalisation */
+int jdde_project(jdde_handle * h, double delay, double * norms);
+
+/* integrate_blindly of the two classes (_jitcdde.py:1323-1345, 1484-1507): fixed steps, projector after every step;
+ * out_state [n_members][n] (state of the last anchor; the caller selects n_basic or main_indices),
+ * lyap [n_members] = average over the steps of log(norm)/dt, total_time [n_members]. */
+int jdde_integrate_blindly_projected(jdde_handle * h, const double * target, int32_t per_member, double step, double * out_state, double * lyap, double * total_time, int32_t * status);
+
 /* ---- inspection ----------------------------------------------------------------------- */
 
 int jdde_get_t(jdde_handle * h, double * t);                              /* get_t, jitced_template.c:187-190 */

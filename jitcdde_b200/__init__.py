@@ -22,16 +22,9 @@ from ._dist import gather_members, shard
 from ._network import jitcdde_network
 
 
-def _out_of_scope(name):
-	def stub(*args, **kwargs):
-		raise NotImplementedError(f"{name} is outside the accelerated path of this package (see DESIGN.md, scope).")
-	stub.__name__ = name
-	return stub
-
-jitcdde_restricted_lyap = _out_of_scope("jitcdde_restricted_lyap")
-jitcdde_transversal_lyap = _out_of_scope("jitcdde_transversal_lyap")
+from ._transversal import GroupHandler, jitcdde_restricted_lyap, jitcdde_transversal_lyap
 
 __all__ = [
-	"UnsuccessfulIntegration", "anchors", "current_y", "dy", "input", "jitcdde", "jitcdde_input", "jitcdde_lyap",
+	"UnsuccessfulIntegration", "anchors", "current_y", "dy", "input", "jitcdde", "jitcdde_input", "jitcdde_lyap", "jitcdde_restricted_lyap", "jitcdde_transversal_lyap",
 	"past_dy", "past_y", "quadrature", "t", "y", "jitcdde_network", "shard", "gather_members", "pinned_empty",
 ]

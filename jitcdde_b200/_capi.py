@@ -19,6 +19,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)
 
+PROJECT_RESTRICTED, PROJECT_TRANSVERSAL = 1, 2
 STATUS_OK, STATUS_MIN_STEP, STATUS_OVERFLOW, STATUS_NONFINITE, STATUS_BACKWARDS, STATUS_BUDGET = range(6)
 
 
@@ -60,6 +61,9 @@ SIGNATURES = {
 	"jdde_resume": (ctypes.c_int, [_H, c_double_p, c_double_p, c_double_p, c_int32_p]),
 	"jdde_integrate_blindly": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_int32_p]),
 	"jdde_integrate_blindly_lyap": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_double_p, c_double_p, c_int32_p]),
+	"jdde_set_projector": (ctypes.c_int, [_H, ctypes.c_int32, c_double_p, ctypes.c_int32, c_int32_p, ctypes.c_int32, c_int32_p, ctypes.c_int32, c_int32_p, ctypes.c_int32]),
+	"jdde_project": (ctypes.c_int, [_H, ctypes.c_double, c_double_p]),
+	"jdde_integrate_blindly_projected": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_double_p, c_double_p, c_int32_p]),
 	"jdde_set_max_delay": (ctypes.c_int, [_H, ctypes.c_double]),
 	"jdde_jump": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, ctypes.c_int32, ctypes.c_double, ctypes.c_int32, c_double_p, c_double_p]),
 	"jdde_adjust_diff": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_double_p]),
@@ -325,6 +329,27 @@ class Engine:
 		status = np.empty(self.N, dtype=np.int32)
 		self._check(self.lib.jdde_integrate_blindly_lyap(self._h, _dp(target), pm, float(step or 0.0), _dp(state), _dp(lyaps), _dp(total), status.ctypes.data_as(c_int32_p)))
 		return state, lyaps, total, status
+
+	# restricted / transversal Lyapunov exponents
+	def set_projector(self, mode, vectors=(), state_components=(), diff_components=(), indices=()):
+		"""mode: PROJECT_RESTRICTED (vectors: [(state part, derivative part), …] of length n_basic each, plus components
+		handled by zeroing) or PROJECT_TRANSVERSAL (indices = tangent indices)"""
+		vectors = _f64(np.array([[v[0], v[1]] for v in vectors], dtype=np.float64).reshape(len(vectors), 2, self.n_basic)) if len(vectors) else np.zeros((0, 2, self.n_basic))
+		ints = [np.ascontiguousarray(np.array(x, dtype=np.int32).reshape(-1)) for x in (state_components, diff_components, indices)]
+		ip = lambda a: a.ctypes.data_as(c_int32_p)
+		self._check(self.lib.jdde_set_projector(self._h, int(mode), _dp(vectors), len(vectors), ip(ints[0]), len(ints[0]), ip(ints[1]), len(ints[1]), ip(ints[2]), len(ints[2])))
+
+	def project(self, delay):
+		norms = np.empty(self.N)
+		self._check(self.lib.jdde_project(self._h, float(delay), _dp(norms)))
+		return norms
+
+	def integrate_blindly_projected(self, target, step):
+		target, pm = self._targets(target)
+		state, lyap, total = np.empty((self.N, self.n)), np.empty(self.N), np.empty(self.N)
+		status = np.empty(self.N, dtype=np.int32)
+		self._check(self.lib.jdde_integrate_blindly_projected(self._h, _dp(target), pm, float(step or 0.0), _dp(state), _dp(lyap), _dp(total), status.ctypes.data_as(c_int32_p)))
+		return state, lyap, total, status
 
 	def set_max_delay(self, max_delay):
 		self._check(self.lib.jdde_set_max_delay(self._h, float(max_delay)))

@@ -449,18 +449,10 @@ def get_delays(exprs, helpers=()):
 	return [0, *delays]
 
 
-def tangent_vector_f(f_basic, helpers, n, n_lyap, delays, simplify=True):
-	"""
-	Extended system (main dynamics + n_lyap tangent vectors), following
-	/root/reference/jitcdde/_jitcdde.py:1046-1089: for exponent i and component
-	c the derivative is Σ_delays Σ_k ∂f_c/∂y_k(t−δ) · y_{k+(i+1)n}(t−δ).
-	"""
+def jacobians(f_basic, n, delays, simplify=True):
+	"""jacs[d][c][k] = ∂f_c/∂y_k(t − delays[d]) (/root/reference/jitcdde/_jitcdde.py:1046-1063); helpers already substituted"""
 	from ._symbols import y
-	f_basic = [_to_plain_functions(sympy.sympify(e)) for e in f_basic]
-	helpers = [(sympy.sympify(s), _to_plain_functions(sympy.sympify(e))) for s, e in helpers]
-	f_basic = _substitute_helpers(f_basic, helpers)
-
-	jacs = []   # jacs[d][c][k]
+	jacs = []
 	for delay in delays:
 		rows = []
 		for entry in f_basic:
@@ -474,6 +466,21 @@ def tangent_vector_f(f_basic, helpers, n, n_lyap, delays, simplify=True):
 				row.append(d)
 			rows.append(row)
 		jacs.append(rows)
+	return jacs
+
+
+def tangent_vector_f(f_basic, helpers, n, n_lyap, delays, simplify=True):
+	"""
+	Extended system (main dynamics + n_lyap tangent vectors), following
+	/root/reference/jitcdde/_jitcdde.py:1046-1089: for exponent i and component
+	c the derivative is Σ_delays Σ_k ∂f_c/∂y_k(t−δ) · y_{k+(i+1)n}(t−δ).
+	"""
+	from ._symbols import y
+	f_basic = [_to_plain_functions(sympy.sympify(e)) for e in f_basic]
+	helpers = [(sympy.sympify(s), _to_plain_functions(sympy.sympify(e))) for s, e in helpers]
+	f_basic = _substitute_helpers(f_basic, helpers)
+
+	jacs = jacobians(f_basic, n, delays, simplify=simplify)
 
 	out = list(f_basic)
 	for i in range(n_lyap):

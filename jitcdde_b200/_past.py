@@ -37,15 +37,17 @@ def _hermite(t, a, b):
 
 
 class Past(list):
-	def __init__(self, n, anchors=(), n_basic=None, rng=None):
+	def __init__(self, n, anchors=(), n_basic=None, rng=None, tangent_indices=()):
 		super().__init__()
 		self.n = n
 		self.n_basic = n_basic or n
+		self.tangent_indices = list(tangent_indices)
+		self.main_indices = [i for i in range(n or 0) if i not in self.tangent_indices]
 		self.rng = rng if rng is not None else np.random.default_rng(42)
 		for anchor in anchors:
 			self.add(anchor)
 
-	# past.py:21-50 (tangent_indices belong to the transversal variants, out of scope)
+	# past.py:21-50
 	def prepare_anchor(self, x):
 		time, state, diff = x
 		state = np.array(state, dtype=float)
@@ -53,6 +55,16 @@ class Past(list):
 		time = np.array(time, dtype=float) if np.ndim(time) else float(time)
 		if state.shape != diff.shape:
 			raise ValueError("State and derivative have different shapes.")
+		if self.tangent_indices and state.shape[-1] < self.n:
+			# transversal Lyapunov exponents: one value per group given, the separation function starts in a random direction
+			assert state.shape[-1] == len(self.main_indices)
+			lead = state.shape[:-1]
+			new_state, new_diff = np.empty(lead+(self.n,)), np.empty(lead+(self.n,))
+			new_state[..., self.main_indices] = state
+			new_state[..., self.tangent_indices] = random_direction(len(self.tangent_indices), self.rng)
+			new_diff[..., self.main_indices] = diff
+			new_diff[..., self.tangent_indices] = random_direction(len(self.tangent_indices), self.rng)
+			state, diff = new_state, new_diff
 		if state.shape[-1:] not in [(self.n,), (self.n_basic,)] or state.ndim > 2:
 			raise ValueError("State has wrong shape.")
 		if self.n_basic < self.n and state.shape[-1] == self.n_basic:

@@ -55,6 +55,20 @@ typedef struct jdde_problem
 	jdde_int_params P;
 } jdde_problem;
 
+/* What follows a step of the restricted / transversal Lyapunov classes (jdde_set_projector; all pointers: device memory) */
+typedef struct jdde_projector
+{
+	int mode;                        /* JDDE_PROJECT_RESTRICTED | JDDE_PROJECT_TRANSVERSAL */
+	int n_vectors;                   /* restricted: vectors with more than one non-zero entry … */
+	const double * vectors;          /* … [n_vectors][2][n_basic]: state part, derivative part */
+	int n_state_components;          /* restricted: unit vectors, handled by zeroing the component */
+	const int * state_components;
+	int n_diff_components;
+	const int * diff_components;
+	int n_indices;                   /* transversal: components of the separation function (tangent_indices) */
+	const int * indices;
+} jdde_projector;
+
 /* `jdde_image_desc` global in every kernel image */
 typedef struct jdde_image_desc_t
 {

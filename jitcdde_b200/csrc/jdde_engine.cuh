@@ -1165,7 +1165,7 @@ JD_FN void adjust_diff(Member & M, jdde_problem const & P, double const shift_ra
 }
 
 /* ------------------------------------------------------------------ Lyapunov exponents */
-#if JD_NBASIC != JD_N
+#if JD_NBASIC != JD_N || defined(JD_PROJECT)
 
 /* calculate_sp_matrix, jitced_template.c:657-674 */
 JD_FN void sp_matrix(double const q, double m[4][4])
@@ -1205,6 +1205,8 @@ JD_FN void partial_sp_matrix(double const q, double const z, double m[4][4])
 	m[3][0] = h_5;       m[3][1] = h_2+h_4; m[3][2] = h_8;             m[3][3] = h_2+(h_5+h_6-h_1)*q;
 }
 
+#endif
+#if JD_NBASIC != JD_N
 /* scalar_product, jitced_template.c:773-817 (norm_sq, :740-771, is the case begin_1 == begin_2).
  * Segment matrices (calculate_sp_matrices, :711-733) are recomputed from the anchor times
  * instead of being stored with every anchor: zero before threshold = current.time − delay,
@@ -1351,21 +1353,186 @@ JD_FN void orthonormalise(Member & M, int const n_lyap, double const delay, doub
 }
 #endif
 
+/* ------------------------------------------------------------------ restricted / transversal Lyapunov exponents */
+#if defined(JD_PROJECT)
+
+#if JD_NBASIC != JD_N
+/* subtract_from_past (jitced_template.c:832-844) and scale_past (:819-830) as single passes */
+JD_FN void subtract_from_past(Member & M, int const begin_1, int const begin_2, double const factor)
+{
+	orthonormalise_pass(M, 0.0, begin_1, begin_2, factor, -1, 0.0, -1, -1);
+}
+
+JD_FN void scale_past(Member & M, int const begin, double const factor)
+{
+	orthonormalise_pass(M, 0.0, -1, -1, 0.0, begin, factor, -1, -1);
+}
+
+/* remove_projections, jitced_template.c:885-971 (Python twin: past.py:75-127): for every anchor and every vector a
+ * "dummy" separation function that is the vector at this anchor and zero elsewhere is orthonormalised against the
+ * previous 2·n_vectors−… dummies and its projection removed from the separation function; finally the dummies are
+ * cleared and the separation function is normalised. Returns its norm before normalisation.
+ * `vectors`: [n_vectors][2][n_basic]. Dummy k lives in components (2+k)·n_basic …, the separation function in
+ * n_basic … 2·n_basic−1. The index of a past dummy is formed as the reference forms it (unsigned difference widened
+ * to a signed 64-bit integer before the modulo, :939). */
+JD_FN double remove_projections(Member & M, double const delay, int const n_vectors, double const * const vectors)
+{
+	double const threshold = M.slot(M.current)[0] - delay;
+	int const sep_func = JD_NBASIC;
+	long long const d = 2*(long long)n_vectors;
+	unsigned dummy_num = 0;
+	long long len_dummies = 0;
+	for (int ca = M.first; ca <= M.last; ca++)
+	{
+		for (int vi = 0; vi < n_vectors; vi++)
+		{
+			int const dummy = (2+(int)dummy_num)*JD_NBASIC;
+			for (int j = 0; j < JD_NBASIC; j++)
+			{
+				for (int oa = M.first; oa <= M.last; oa++)
+				{
+					double * const o = M.slot(oa);
+					o[1+dummy+j] = 0.0;
+					o[1+JD_N+dummy+j] = 0.0;
+				}
+				double * const c = M.slot(ca);
+				c[1+dummy+j] = vectors[((size_t)vi*2+0)*JD_NBASIC+j];
+				c[1+JD_N+dummy+j] = vectors[((size_t)vi*2+1)*JD_NBASIC+j];
+			}
+			for (unsigned i = 0; i < len_dummies; i++)
+			{
+				int const past_dummy = (2+(int)((long long)(unsigned)(dummy_num-i-1u) % d))*JD_NBASIC;
+				double const sp = scalar_product(M, threshold, dummy, past_dummy);
+				subtract_from_past(M, dummy, past_dummy, sp);
+			}
+			double const norm = sqrt(scalar_product(M, threshold, dummy, dummy));
+			if (norm > JD_NORM_THRESHOLD)
+			{
+				scale_past(M, dummy, 1./norm);
+				double const sp = scalar_product(M, threshold, sep_func, dummy);
+				subtract_from_past(M, sep_func, dummy, sp);
+			}
+			else
+				scale_past(M, dummy, 0);
+			len_dummies++;
+			dummy_num = (unsigned)((dummy_num+1) % d);
+		}
+		if (len_dummies > n_vectors)
+			len_dummies -= n_vectors;
+	}
+	for (int ca = M.first; ca <= M.last; ca++)
+	{
+		double * const c = M.slot(ca);
+		for (int j = 2*JD_NBASIC; j < JD_N; j++)
+			c[1+j] = c[1+JD_N+j] = 0.0;
+	}
+	double const norm = sqrt(scalar_product(M, threshold, sep_func, sep_func));
+	scale_past(M, sep_func, 1./norm);
+	return norm;
+}
+#endif
+
+/* normalise_indices, jitced_template.c:1007-1083: norm of the components `indices` over the delay window
+ * (norm_sq_tangent: per segment Σ_ij m_ij Σ_index vec_i[index]·vec_j[index]), normalisation if it is not tiny */
+JD_FN double normalise_indices(Member & M, double const delay, int const n_indices, int const * const indices)
+{
+	double const threshold = M.slot(M.current)[0] - delay;
+	double sum = 0;
+	bool partial_done = false;
+	for (int vi = M.first; vi < M.last; vi++)
+	{
+		double const * const v = M.slot(vi);
+		double const * const w = M.slot(vi+1);
+		double const q = w[0] - v[0];
+		double m[4][4];
+		if (!partial_done)
+		{
+			if (w[0] < threshold)
+				continue;
+			partial_sp_matrix(q, (threshold - w[0]) / q, m);
+			partial_done = true;
+		}
+		else
+			sp_matrix(q, m);
+		double const * const vector[4] = { v+1, v+1+JD_N, w+1, w+1+JD_N };
+		double part = 0;
+		for (int i = 0; i < 4; i++)
+			for (int j = 0; j < 4; j++)
+				for (int k = 0; k < n_indices; k++)
+					part += m[i][j] * vector[i][indices[k]] * vector[j][indices[k]];
+		sum += part;
+	}
+	double const norm = sqrt(sum);
+	if (norm > JD_NORM_THRESHOLD)
+	{
+		double const factor = 1./norm;
+		for (int ca = M.first; ca <= M.last; ca++)
+		{
+			double * const c = M.slot(ca);
+			for (int k = 0; k < n_indices; k++)
+			{
+				c[1+indices[k]] *= factor;
+				c[1+JD_N+indices[k]] *= factor;
+			}
+		}
+	}
+	return norm;
+}
+
+/* what jitcdde_restricted_lyap.remove_projections (_jitcdde.py:1278-1284) or
+ * jitcdde_transversal_lyap's DDE.normalise_indices (:1478) do after a step or a call of integrate; returns the norm */
+JD_FN double project(Member & M, jdde_projector const & R, double const delay)
+{
+	M.invalidate_windows();
+#if JD_NBASIC != JD_N
+	if (R.mode == JDDE_PROJECT_RESTRICTED)
+	{
+		/* remove_state_component / remove_diff_component, jitced_template.c:973-1003 */
+		for (int k = 0; k < R.n_state_components; k++)
+			for (int ca = M.first; ca <= M.last; ca++)
+				M.slot(ca)[1+JD_NBASIC+R.state_components[k]] = 0.0;
+		for (int k = 0; k < R.n_diff_components; k++)
+			for (int ca = M.first; ca <= M.last; ca++)
+				M.slot(ca)[1+JD_N+JD_NBASIC+R.diff_components[k]] = 0.0;
+		return remove_projections(M, delay, R.n_vectors, R.vectors);
+	}
+#endif
+	return normalise_indices(M, delay, R.n_indices, R.indices);
+}
+
+JD_FN void member_project(jdde_problem const & P, long long const m, jdde_projector const & R, double const delay, double * const norms)
+{
+	Member M;
+	load_member(P, m, M);
+	if (M.status != JDDE_STATUS_OK)
+		return;
+	norms[m] = project(M, R, delay);
+}
+#endif
+
 /* integrate_blindly, _jitcdde.py:880-933; with `lyaps` the variant of jitcdde_lyap (:1191-1209):
  * orthonormalise after every step and average log(norms)/dt */
-JD_FN void integrate_blindly(Member & M, jdde_problem const & P, double const target, double step, double * const out, int const n_out, double * const lyaps, double * const total_time)
+JD_FN void integrate_blindly(Member & M, jdde_problem const & P, double const target, double step, double * const out, int const n_out, double * const lyaps, double * const total_time, jdde_projector const * const projector = nullptr)
 {
 	if (!(step > 0))
 		step = P.P.max_step;
 	double const total = target-M.cur_t;
 	if (total_time)
 		*total_time = total;
+	/* number of local exponents averaged over the steps: n_lyap (jitcdde_lyap), 1 (restricted / transversal) */
+	int n_exponents = 0;
 #if JD_NBASIC != JD_N
 	int const n_lyap = JD_N/JD_NBASIC-1;
-	double lyap_sum[JD_N/JD_NBASIC];
-	for (int i = 0; i < n_lyap; i++)
-		lyap_sum[i] = 0.0;
+	if (lyaps && !projector)
+		n_exponents = n_lyap;
 #endif
+#if defined(JD_PROJECT)
+	if (lyaps && projector)
+		n_exponents = 1;
+#endif
+	double lyap_sum[JD_N/JD_NBASIC];
+	for (int i = 0; i < n_exponents; i++)
+		lyap_sum[i] = 0.0;
 	if (total > 0)
 	{
 		if (total < step)
@@ -1380,8 +1547,17 @@ JD_FN void integrate_blindly(Member & M, jdde_problem const & P, double const ta
 			accept_step(M);
 			P.accepted[M.index]++;
 			forget(M, P.max_delay);
+#if defined(JD_PROJECT)
+			if (lyaps && projector)
+			{
+				/* _jitcdde.py:1335-1340, :1496-1501 */
+				double const norm = project(M, *projector, P.max_delay);
+				reload_current(M);
+				lyap_sum[0] += log(norm)/dt;
+			}
+#endif
 #if JD_NBASIC != JD_N
-			if (lyaps)
+			if (lyaps && !projector)
 			{
 				double norms[JD_N/JD_NBASIC];
 				orthonormalise(M, n_lyap, P.max_delay, norms);
@@ -1392,21 +1568,15 @@ JD_FN void integrate_blindly(Member & M, jdde_problem const & P, double const ta
 			}
 #endif
 		}
-#if JD_NBASIC != JD_N
-		if (lyaps)
-			for (int i = 0; i < n_lyap; i++)
-				lyaps[i] = lyap_sum[i]/number;
-#endif
+		for (int i = 0; i < n_exponents; i++)
+			lyaps[i] = lyap_sum[i]/number;
 	}
 	else if (total == 0)
 	{
 		double mi[JD_N], ma[JD_N];
 		adjust_diff(M, P, 1e-4, mi, ma);
-#if JD_NBASIC != JD_N
-		if (lyaps)
-			for (int i = 0; i < n_lyap; i++)
-				lyaps[i] = 0.0;
-#endif
+		for (int i = 0; i < n_exponents; i++)
+			lyaps[i] = 0.0;
 	}
 	else
 		M.status = JDDE_STATUS_BACKWARDS;
@@ -1500,7 +1670,7 @@ JD_FN void member_integrate(jdde_problem const & P, long long const m, double co
 	store_member(P, m, M);
 }
 
-JD_FN void member_integrate_blindly(jdde_problem const & P, long long const m, double const * const targets, int const per_member, double const step, double * const out, int const n_out, double * const lyaps, double * const total_time)
+JD_FN void member_integrate_blindly(jdde_problem const & P, long long const m, double const * const targets, int const per_member, double const step, double * const out, int const n_out, double * const lyaps, double * const total_time, jdde_projector const * const projector = nullptr)
 {
 	Member M;
 	load_member(P, m, M);
@@ -1509,13 +1679,14 @@ JD_FN void member_integrate_blindly(jdde_problem const & P, long long const m, d
 	double res[JD_N];
 	double ly[JD_N/JD_NBASIC];
 	double total;
-	integrate_blindly(M, P, per_member ? targets[m] : targets[0], step, res, n_out, lyaps ? ly : nullptr, &total);
+	integrate_blindly(M, P, per_member ? targets[m] : targets[0], step, res, n_out, lyaps ? ly : nullptr, &total, projector);
 	if (out)
 		for (int i = 0; i < n_out; i++)
 			out[(size_t)m*n_out+i] = res[i];
+	int const n_exponents = projector ? 1 : JD_N/JD_NBASIC-1;
 	if (lyaps)
-		for (int i = 0; i < JD_N/JD_NBASIC-1; i++)
-			lyaps[(size_t)m*(JD_N/JD_NBASIC-1)+i] = ly[i];
+		for (int i = 0; i < n_exponents; i++)
+			lyaps[(size_t)m*n_exponents+i] = ly[i];
 	if (total_time)
 		total_time[m] = total;
 	store_member(P, m, M);

@@ -92,6 +92,26 @@ jdde_k_integrate_blindly(jdde_problem const P, double const * const targets, int
 		jdde::member_integrate_blindly(P, m, targets, per_member, step, out, n_out, lyaps, total_time);
 }
 
+#if defined(JD_PROJECT)
+/* restricted / transversal Lyapunov exponents: the projector after a call of integrate, and blind integration with the
+ * projector after every step (one thread per member: cold paths) */
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_project(jdde_problem const P, jdde_projector const R, double const delay, double * const norms)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members)
+		jdde::member_project(P, m, R, delay, norms);
+}
+
+extern "C" __global__ void __launch_bounds__(JD_BLOCK)
+jdde_k_integrate_blindly_projected(jdde_problem const P, jdde_projector const R, double const * const targets, int const per_member, double const step, double * const out, int const n_out, double * const lyaps, double * const total_time)
+{
+	long long const m = JD_MEMBER_INDEX();
+	if (m < P.n_members)
+		jdde::member_integrate_blindly(P, m, targets, per_member, step, out, n_out, lyaps, total_time, &R);
+}
+#endif
+
 extern "C" __global__ void __launch_bounds__(JD_BLOCK)
 jdde_k_jump(jdde_problem const P, int const mode, double const * const amplitude, int const amp_pm, double const * const time, int const time_pm, double const width, int const forward, double * const minima, double * const maxima)
 {

@@ -29,7 +29,7 @@ struct Kernels
 {
 	cudaKernel_t set_past = nullptr, reset_controller = nullptr, integrate = nullptr, integrate_blindly = nullptr,
 		jump = nullptr, forget = nullptr, get = nullptr, clear_status = nullptr, sum_counters = nullptr, count_failed = nullptr,
-		regrow = nullptr, orthonormalise = nullptr, orthonormalise_team = nullptr, integrate_group = nullptr;
+		regrow = nullptr, orthonormalise = nullptr, orthonormalise_team = nullptr, integrate_group = nullptr, project = nullptr, integrate_blindly_projected = nullptr;
 };
 
 } // namespace
@@ -72,6 +72,9 @@ struct jdde_handle
 	int last_per_member = 0, last_n_steps = 0;
 	std::vector<double> last_targets;
 	std::vector<void *> allocations;
+	/* restricted / transversal Lyapunov exponents (jdde_set_projector): device copies of the arrays */
+	jdde_projector projector{};
+	void * projector_memory = nullptr;
 };
 
 namespace {
@@ -408,6 +411,8 @@ int jdde_destroy(jdde_handle * h)
 		cudaFree(p);
 	if (h->d_in)
 		cudaFree(h->d_in);
+	if (h->projector_memory)
+		cudaFree(h->projector_memory);
 	if (h->lib)
 		cudaLibraryUnload(h->lib);
 	if (h->own_stream && h->stream)
@@ -472,6 +477,8 @@ int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
 		{"jdde_k_orthonormalise", &h->k.orthonormalise, false},
 		{"jdde_k_orthonormalise_team", &h->k.orthonormalise_team, false},
 		{"jdde_k_integrate_group", &h->k.integrate_group, false},
+		{"jdde_k_project", &h->k.project, false},
+		{"jdde_k_integrate_blindly_projected", &h->k.integrate_blindly_projected, false},
 	};
 	for (auto const & entry : table)
 	{
@@ -835,6 +842,91 @@ int jdde_integrate_lyap(jdde_handle * h, const double * target, int32_t per_memb
 		return fail(h, JDDE_E_INVALID, "integrate_lyap needs n_basic < n");
 	h->last_kind = 3;
 	return run_lyap(h, target, per_member ? (size_t)h->desc.n_members : 1, per_member, 0, out_state, lyaps, delta_t, status);
+}
+
+int jdde_set_projector(jdde_handle * h, int32_t mode, const double * vectors, int32_t n_vectors,
+	const int32_t * state_components, int32_t n_state, const int32_t * diff_components, int32_t n_diff, const int32_t * indices, int32_t n_indices)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	int const n = h->desc.n, nb = h->desc.n_basic;
+	if (mode == JDDE_PROJECT_RESTRICTED)
+	{
+		if (n_vectors < 0 || n_state < 0 || n_diff < 0 || n != nb*(2+2*n_vectors) || (n_vectors && !vectors) || (n_state && !state_components) || (n_diff && !diff_components))
+			return fail(h, JDDE_E_INVALID, "restricted projector needs n = n_basic·(2 + 2·n_vectors) (_jitcdde.py:1270-1274)");
+		for (int k = 0; k < n_state; k++) if (state_components[k] < 0 || state_components[k] >= nb) return fail(h, JDDE_E_INVALID, "state component out of range");
+		for (int k = 0; k < n_diff; k++) if (diff_components[k] < 0 || diff_components[k] >= nb) return fail(h, JDDE_E_INVALID, "diff component out of range");
+		n_indices = 0;
+	}
+	else if (mode == JDDE_PROJECT_TRANSVERSAL)
+	{
+		if (n_indices < 1 || !indices)
+			return fail(h, JDDE_E_INVALID, "transversal projector needs tangent indices");
+		for (int k = 0; k < n_indices; k++) if (indices[k] < 0 || indices[k] >= n) return fail(h, JDDE_E_INVALID, "tangent index out of range");
+		n_vectors = n_state = n_diff = 0;
+	}
+	else
+		return fail(h, JDDE_E_INVALID, "unknown projector mode");
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	if (h->projector_memory)
+	{
+		cudaFree(h->projector_memory);
+		h->projector_memory = nullptr;
+	}
+	size_t const vector_bytes = (size_t)n_vectors*2*nb*sizeof(double);
+	size_t const int_count = (size_t)n_state+n_diff+n_indices;
+	std::vector<char> host(vector_bytes + int_count*sizeof(int32_t) + 16);
+	if (vector_bytes) memcpy(host.data(), vectors, vector_bytes);
+	int32_t * ints = (int32_t *)(host.data()+vector_bytes);
+	for (int k = 0; k < n_state; k++) ints[k] = state_components[k];
+	for (int k = 0; k < n_diff; k++) ints[n_state+k] = diff_components[k];
+	for (int k = 0; k < n_indices; k++) ints[n_state+n_diff+k] = indices[k];
+	JD_CUDA(h, cudaMalloc(&h->projector_memory, host.size()));
+	JD_CUDA(h, cudaMemcpy(h->projector_memory, host.data(), host.size(), cudaMemcpyHostToDevice));
+	jdde_projector & R = h->projector;
+	R.mode = mode;
+	R.n_vectors = n_vectors;
+	R.vectors = (const double *)h->projector_memory;
+	const int * const device_ints = (const int *)((const char *)h->projector_memory+vector_bytes);
+	R.n_state_components = n_state;
+	R.state_components = device_ints;
+	R.n_diff_components = n_diff;
+	R.diff_components = device_ints+n_state;
+	R.n_indices = n_indices;
+	R.indices = device_ints+n_state+n_diff;
+	return JDDE_OK;
+}
+
+int jdde_project(jdde_handle * h, double delay, double * norms)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (!h->projector.mode) return fail(h, JDDE_E_INVALID, "no projector set (jdde_set_projector)");
+	if (!h->k.project) return fail(h, JDDE_E_IMAGE, "image was built without JD_PROJECT");
+	void * args[] = { &h->P, &h->projector, &delay, &h->d_aux2 };
+	if ((rc = launch(h, h->k.project, args))) return rc;
+	return finish(h, norms, h->d_aux2, (size_t)h->desc.n_members, nullptr);
+}
+
+int jdde_integrate_blindly_projected(jdde_handle * h, const double * target, int32_t per_member, double step, double * out_state, double * lyap, double * total_time, int32_t * status)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (!h->projector.mode) return fail(h, JDDE_E_INVALID, "no projector set (jdde_set_projector)");
+	if (!h->k.integrate_blindly_projected) return fail(h, JDDE_E_IMAGE, "image was built without JD_PROJECT");
+	if (!target) return fail(h, JDDE_E_INVALID, "null argument");
+	size_t const N = (size_t)h->desc.n_members;
+	double * d_targets;
+	if ((rc = stage_in(h, target, per_member ? N : 1, &d_targets))) return rc;
+	int pm = per_member ? 1 : 0;
+	int n_out = h->desc.n;
+	void * args[] = { &h->P, &h->projector, &d_targets, &pm, &step, &h->d_out, &n_out, &h->d_aux, &h->d_aux2 };
+	if ((rc = launch(h, h->k.integrate_blindly_projected, args))) return rc;
+	if (lyap)
+		JD_CUDA(h, cudaMemcpyAsync(lyap, h->d_aux, N*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	if (total_time)
+		JD_CUDA(h, cudaMemcpyAsync(total_time, h->d_aux2, N*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	return finish(h, out_state, h->d_out, N*n_out, status);
 }
 
 int jdde_resume(jdde_handle * h, double * out_state, double * lyaps, double * delta_t, int32_t * status)

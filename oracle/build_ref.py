@@ -46,7 +46,7 @@ def _so_path(name):
 	return os.path.join(REF_DIR, name + sysconfig.get_config_var("EXT_SUFFIX"))
 
 
-def build_ref(program, name, n_basic=None, flavour="chain", flags=VERIFY_FLAGS, force=False):
+def build_ref(program, name, n_basic=None, flavour="chain", flags=VERIFY_FLAGS, force=False, tangent_indices=()):
 	"""Render + compile; returns the path of the extension module."""
 	so = _so_path(name)
 	if os.path.exists(so) and not force:
@@ -91,7 +91,7 @@ def build_ref(program, name, n_basic=None, flavour="chain", flags=VERIFY_FLAGS, 
 		anchor_mem_length=sites,
 		n_basic=n_basic,
 		control_pars=list(program.param_names),
-		tangent_indices=[],
+		tangent_indices=list(tangent_indices),
 		chunk_size=100,
 		callbacks=[],
 		module_name=name,

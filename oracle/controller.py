@@ -233,6 +233,41 @@ class Controller:
 			lyaps = np.zeros(n_lyap)
 		return result, lyaps, delta_t
 
+	# jitcdde_restricted_lyap.remove_projections (_jitcdde.py:1278-1284) / DDE.normalise_indices (:1478)
+	def project(self, projector):
+		if projector["mode"] == "restricted":
+			for component in projector["state_components"]:
+				self.DDE.remove_state_component(component)
+			for component in projector["diff_components"]:
+				self.DDE.remove_diff_component(component)
+			return self.DDE.remove_projections(self.max_delay, [(np.array(v[0], dtype=float), np.array(v[1], dtype=float)) for v in projector["vectors"]])
+		return self.DDE.normalise_indices(self.max_delay)
+
+	# integrate of the restricted / transversal classes, _jitcdde.py:1312-1321, 1471-1480 (the caller selects the components)
+	def integrate_projected(self, target_time, projector):
+		old_t = self.DDE.get_t()
+		result = self.integrate(target_time)
+		delta_t = self.DDE.get_t()-old_t
+		lyap = np.log(self.project(projector))/delta_t if delta_t != 0 else 0.0
+		return result, lyap, delta_t
+
+	# integrate_blindly of the two classes, _jitcdde.py:1323-1345, 1484-1507
+	def integrate_blindly_projected(self, target_time, projector, step=None):
+		step = step or self.max_step
+		total = target_time-self.DDE.get_t()
+		if total < step:
+			step = total
+		number = round(total/step)
+		dt = total/number
+		instantaneous = []
+		for _ in range(number):
+			self.DDE.get_next_step(dt)
+			self.DDE.accept_step()
+			self.accepted += 1
+			self.DDE.forget(self.max_delay)
+			instantaneous.append(np.log(self.project(projector))/dt)
+		return self.DDE.get_current_state().copy(), np.average(instantaneous), total
+
 	def get_state(self):
 		self.DDE.forget(self.max_delay)
 		return [(a[0], np.array(a[1]), np.array(a[2])) for a in self.DDE.get_full_state()]

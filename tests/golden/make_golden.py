@@ -237,9 +237,34 @@ def golden_lyap():
 		accepted=C.accepted, rejected=C.rejected, lyap_controls=np.array([0.0806, 0, -0.0368, -0.1184]))
 
 
+def golden_projected():
+	# restricted and transversal Lyapunov exponents of three synchronised oscillators (tests/test_transversal_lyap.py), short
+	# protocol: 20 blind calls of one step each, then 12 adaptive samples — all from the reference's C core
+	# (remove_state_component / remove_diff_component / remove_projections / normalise_indices)
+	system = systems.synchronised_fhn()
+	for kind in ("restricted", "transversal"):
+		DDE, prog, projector = systems.projected_program(kind)
+		single = np.array([0.3, 0.1])
+		initial = np.array([single[j] for j, group in enumerate(system["groups"]) for _ in group]) if kind == "restricted" else single
+		DDE.constant_past(initial, 0.0)
+		past = [(a.time, a.state, a.diff) for a in DDE.past]
+		roots = roots_from(oracle.build(prog, n_basic=DDE.n_basic))
+		name = "ref_"+kind
+		build_ref.build_ref(prog, name, n_basic=DDE.n_basic, force=True, tangent_indices=projector.get("indices", ()))
+		core = build_ref.load_ref(name).dde_integrator([(float(a[0]), np.array(a[1], dtype=float), np.array(a[2], dtype=float)) for a in past])
+		core.set_parameters(-0.1)
+		C = controller.Controller(core, system["tau"], root_mode=1, roots=roots)
+		blind = [C.integrate_blindly_projected(float(T), projector) for T in range(1, 21)]
+		times = C.t + np.arange(20, 260, 20.0)
+		samples = [C.integrate_projected(T, projector) for T in times]
+		save(kind, **past_arrays(past), k=-0.1, blind_states=np.array([b[0] for b in blind]), blind_lyaps=np.array([b[1] for b in blind]),
+			blind_totals=np.array([b[2] for b in blind]), times=times, states=np.array([s[0] for s in samples]),
+			lyaps=np.array([s[1] for s in samples]), weights=np.array([s[2] for s in samples]), accepted=C.accepted, rejected=C.rejected)
+
+
 if __name__ == "__main__":
 	assert build_ref.reference_available(), "run this where /root/reference exists"
 	makers = dict(roessler=golden_roessler, mg_ensemble=golden_mg_ensemble, neutral=golden_neutral, state_dependent=golden_state_dependent,
-		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input)
+		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected)
 	for name in sys.argv[1:] or makers:      # optional arguments: only these fixtures
 		makers[name]()

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#define JD_PROJECT 1      /* restricted / transversal projections are always part of the twin */
 #include "jdde_engine.cuh"
 
 struct jdde_handle
@@ -29,6 +30,9 @@ struct jdde_handle
 	long long budget = 1ll << 24;
 	long long launches = 0;
 	std::string err;
+	std::vector<double> projector_vectors;
+	std::vector<int> projector_ints;
+	jdde_projector projector{};
 };
 
 static std::string g_err;
@@ -193,6 +197,59 @@ int jdde_integrate_blindly_lyap(jdde_handle * h, const double * target, int32_t 
 	give(h, lyaps, h->out2, (size_t)h->P.n_members*(JD_N/JD_NBASIC-1), nullptr);
 	give(h, total_time, h->aux2, (size_t)h->P.n_members, nullptr);
 	give(h, out, h->out, (size_t)h->P.n_members*JD_NBASIC, status);
+	return JDDE_OK;
+}
+
+int jdde_set_projector(jdde_handle * h, int32_t mode, const double * vectors, int32_t n_vectors,
+	const int32_t * state_components, int32_t n_state, const int32_t * diff_components, int32_t n_diff, const int32_t * indices, int32_t n_indices)
+{
+	if (mode == JDDE_PROJECT_RESTRICTED)
+	{
+		if (JD_N != JD_NBASIC*(2+2*n_vectors)) return fail(h, JDDE_E_INVALID, "restricted projector needs n = n_basic·(2 + 2·n_vectors) (_jitcdde.py:1270-1274)");
+		n_indices = 0;
+	}
+	else if (mode == JDDE_PROJECT_TRANSVERSAL)
+	{
+		if (n_indices < 1 || !indices) return fail(h, JDDE_E_INVALID, "transversal projector needs tangent indices");
+		n_vectors = n_state = n_diff = 0;
+	}
+	else
+		return fail(h, JDDE_E_INVALID, "unknown projector mode");
+	h->projector_vectors.assign(vectors, vectors+(size_t)n_vectors*2*JD_NBASIC);
+	h->projector_ints.clear();
+	h->projector_ints.insert(h->projector_ints.end(), state_components, state_components+n_state);
+	h->projector_ints.insert(h->projector_ints.end(), diff_components, diff_components+n_diff);
+	h->projector_ints.insert(h->projector_ints.end(), indices, indices+n_indices);
+	jdde_projector & R = h->projector;
+	R.mode = mode;
+	R.n_vectors = n_vectors; R.vectors = h->projector_vectors.data();
+	R.n_state_components = n_state; R.state_components = h->projector_ints.data();
+	R.n_diff_components = n_diff; R.diff_components = h->projector_ints.data()+n_state;
+	R.n_indices = n_indices; R.indices = h->projector_ints.data()+n_state+n_diff;
+	return JDDE_OK;
+}
+
+int jdde_project(jdde_handle * h, double delay, double * norms)
+{
+	if (int rc = ready(h)) return rc;
+	if (!h->projector.mode) return fail(h, JDDE_E_INVALID, "no projector set (jdde_set_projector)");
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_project(h->P, m, h->projector, delay, h->aux2.data());
+	h->launches++;
+	give(h, norms, h->aux2, (size_t)h->P.n_members, nullptr);
+	return JDDE_OK;
+}
+
+int jdde_integrate_blindly_projected(jdde_handle * h, const double * target, int32_t pm, double step, double * out, double * lyap, double * total_time, int32_t * status)
+{
+	if (int rc = ready(h)) return rc;
+	if (!h->projector.mode) return fail(h, JDDE_E_INVALID, "no projector set (jdde_set_projector)");
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_integrate_blindly(h->P, m, target, pm, step, h->out.data(), JD_N, h->aux.data(), h->aux2.data(), &h->projector);
+	h->launches++;
+	give(h, lyap, h->aux, (size_t)h->P.n_members, nullptr);
+	give(h, total_time, h->aux2, (size_t)h->P.n_members, nullptr);
+	give(h, out, h->out, (size_t)h->P.n_members*JD_N, status);
 	return JDDE_OK;
 }
 

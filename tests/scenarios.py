@@ -160,6 +160,36 @@ def data_input(g, **kw):
 	return dict(adjust_diff_min=mi, adjust_diff_max=ma, samples=samples, accepted=accepted[0], rejected=rejected[0], max_delay=DDE.max_delay)
 
 
+def _projected(kind, g, **kw):
+	"""jitcdde_restricted_lyap / jitcdde_transversal_lyap on three synchronised oscillators (tests/test_transversal_lyap.py):
+	20 blind calls of one step, then adaptive samples; the past (incl. the random separation function) comes from the fixture"""
+	DDE, _, _ = systems.projected_program(kind, **kw)
+	DDE.add_past_points(past_of(g))
+	DDE.set_parameters(float(g["k"]))
+	select = (lambda s: s[:DDE.n_basic]) if kind == "restricted" else (lambda s: s[DDE.main_indices])
+	blind = [DDE.integrate_blindly(float(T)) for T in range(1, 21)]
+	samples = [DDE.integrate(T) for T in g["times"]]
+	accepted, rejected, _ = DDE.counters()
+	result = dict(blind_states=np.array([b[0] for b in blind]), blind_lyaps=np.array([b[1] for b in blind]), blind_totals=np.array([b[2] for b in blind]),
+		states=np.array([s[0] for s in samples]), lyaps=np.array([s[1] for s in samples]), weights=np.array([s[2] for s in samples]),
+		accepted=accepted[0], rejected=rejected[0])
+	# the fixture holds the whole state of the last anchor; the classes return the basic / main components
+	expected = dict(g)
+	expected["blind_states"] = np.array([select(s) for s in g["blind_states"]])
+	expected["states"] = np.array([select(s) for s in g["states"]])
+	return result, expected
+
+
+def restricted(g, **kw):
+	return _projected("restricted", g, **kw)
+
+
+def transversal(g, **kw):
+	return _projected("transversal", g, **kw)
+
+
+PROJECTED = dict(restricted=restricted, transversal=transversal)
+
 ALL = dict(roessler=roessler, roessler_jump=roessler_jump, mg_ensemble=mg_ensemble, neutral=neutral,
 	state_dependent=state_dependent, ode=ode, kuramoto=kuramoto, mg_lyap=mg_lyap, roessler_lyap=roessler_lyap, data_input=data_input)
 FIXTURE = dict(roessler_jump="roessler")
@@ -170,7 +200,7 @@ def compare(result, g, exact, rtol=1e-10, suffix=""):
 	for key, value in result.items():
 		expected = g[key+suffix] if key+suffix in g else g[key]
 		value = np.asarray(value)
-		if key == "lyaps" and exact:
+		if key in ("lyaps", "blind_lyaps") and exact:
 			# log(norms)/Δt: the reference takes the logarithm with NumPy (_jitcdde.py:1168), whose vectorised log
 			# differs from libm's by an ulp now and then; the norms themselves are compared through the states
 			np.testing.assert_allclose(value, expected, rtol=4e-16, atol=1e-17, err_msg=key)

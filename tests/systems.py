@@ -137,6 +137,42 @@ def data_input_program(system=None):
 	return program, [(a.time, a.state, a.diff) for a in DDE.past], DDE.max_delay
 
 
+def synchronised_fhn():
+	"""tests/test_transversal_lyap.py:22-52, scenario "grouped by variables": three FitzHugh–Nagumo-like oscillators
+	on a ring with a delayed inhibitor, synchronised; coupling k is a control parameter"""
+	a, b, c, tau = -0.025794, 0.01, 0.02, 1.0
+	k = sympy.Symbol("k")
+	f = [
+		y(0)*(a-y(0))*(y(0)-1.0) - y(3) + k*(y(1)-y(0)),
+		y(1)*(a-y(1))*(y(1)-1.0) - y(4) + k*(y(2)-y(1)),
+		y(2)*(a-y(2))*(y(2)-1.0) - y(5) + k*(y(0)-y(2)),
+		b*y(0) - c*y(3, t-tau),
+		b*y(1) - c*y(4, t-tau),
+		b*y(2) - c*y(5, t-tau),
+	]
+	zero = [0.]*6
+	vectors = [([1., 1., 1., 0., 0., 0.], zero), (zero, [1., 1., 1., 0., 0., 0.]), ([0., 0., 0., 1., 1., 1.], zero), (zero, [0., 0., 0., 1., 1., 1.])]
+	return dict(f=f, control_pars=[k], vectors=vectors, groups=([0, 1, 2], [3, 4, 5]), tau=tau)
+
+
+def projected_program(kind, system=None, **kw):
+	"""(DDE object, program, projector description) of jitcdde_restricted_lyap / jitcdde_transversal_lyap for the
+	synchronised oscillators, generated exactly as the class's compile_C does"""
+	from jitcdde_b200 import jitcdde_restricted_lyap, jitcdde_transversal_lyap
+	system = system or synchronised_fhn()
+	if kind == "restricted":
+		DDE = jitcdde_restricted_lyap(system["f"], vectors=system["vectors"], control_pars=system["control_pars"], verbose=False, **kw)
+		simplify = False      # as the reference's test: simplification breaks the symmetry that keeps the dynamics on the manifold
+		projector = dict(mode="restricted", vectors=DDE.vectors, state_components=DDE.state_components, diff_components=DDE.diff_components)
+	else:
+		DDE = jitcdde_transversal_lyap(system["f"], groups=system["groups"], control_pars=system["control_pars"], verbose=False, **kw)
+		simplify = False
+		projector = dict(mode="transversal", indices=DDE.tangent_indices)
+	blocks = (DDE.n_basic, DDE.n//DDE.n_basic-1) if DDE.n_basic != DDE.n else None
+	program = _codegen.generate(list(DDE.f_sym()), helpers=DDE.helpers, control_pars=DDE.control_pars, simplify=simplify, blocks=blocks)
+	return DDE, program, projector
+
+
 def as_list(f):
 	"""f as a list of expressions (dict keyed by y(i) → ordered list)"""
 	if isinstance(f, dict):

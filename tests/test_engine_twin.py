@@ -81,3 +81,47 @@ def test_lyapunov_resume_after_partial_ring_overflow(twin):
 	for small, big in zip(results[0][0], results[1][0]):
 		for a, b in zip(small, big):
 			assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("kind", sorted(scenarios.PROJECTED))
+def test_restricted_and_transversal_lyapunov_bitwise_against_reference_core(twin, kind):
+	"""jitcdde_restricted_lyap (remove_state/diff_component, remove_projections) and jitcdde_transversal_lyap
+	(normalise_indices) against the same calls of the reference's C core (tests/golden/restricted.npz, transversal.npz)"""
+	result, expected = scenarios.PROJECTED[kind](scenarios.golden(kind), verification=True)
+	scenarios.compare(result, expected, exact=True)
+
+
+def test_restricted_and_transversal_lyapunov_agree(twin):
+	"""The reference's own integration test (tests/test_transversal_lyap.py), shortened: both classes give the same largest
+	transversal exponent (within their standard errors) with the sign the coupling dictates, and the restricted run stays on
+	the synchronisation manifold."""
+	from scipy.stats import sem
+	from tests import systems
+	system = systems.synchronised_fhn()
+	results = {}
+	for kind in ("restricted", "transversal"):
+		DDE, _, _ = systems.projected_program(kind, verification=True)
+		rng = np.random.default_rng(42)
+		for k, sign in ((-0.1, 1), (0.1, -1), (0.0, 0)):
+			DDE.purge_past()
+			single = rng.random(2)
+			initial = np.array([single[j] for j, group in enumerate(system["groups"]) for _ in group])
+			DDE.constant_past(initial if kind == "restricted" else single, 0.0)
+			DDE.set_parameters(k)
+			for time in range(1, 100):
+				DDE.integrate_blindly(time)
+			lyaps, weights = [], []
+			for time in DDE.t + np.arange(100, 3100, 100):
+				state, lyap, weight = DDE.integrate(time)
+				lyaps.append(lyap)
+				weights.append(weight)
+			if kind == "restricted":
+				for anchor in DDE.get_state():
+					for group in system["groups"]:
+						assert len({anchor[1][i] for i in group}) == 1 and len({anchor[2][i] for i in group}) == 1
+			results[kind, k] = (np.average(lyaps, weights=weights), sem(lyaps), sign)
+	for k in (-0.1, 0.1, 0.0):
+		(l1, m1, sign), (l2, m2, _) = results["restricted", k], results["transversal", k]
+		assert (np.sign(l1) if abs(l1) > m1 else 0) == sign
+		assert (np.sign(l2) if abs(l2) > m2 else 0) == sign
+		assert abs(l1-l2) < max(m1, m2), (k, l1, m1, l2, m2)

@@ -75,6 +75,26 @@ def test_production_build_matches_reference_core(name):
 	scenarios.compare(result, g, exact=False, rtol=rtol, suffix="_chain" if name == "mg_ensemble" else "")
 
 
+@pytest.mark.parametrize("kind", sorted(scenarios.PROJECTED))
+def test_restricted_and_transversal_lyapunov(kind):
+	"""jitcdde_restricted_lyap / jitcdde_transversal_lyap: the projector kernels against the same calls of
+	the reference's C core — verification build bit for bit, production build to rounding (the system is not chaotic)"""
+	g = scenarios.golden(kind)
+	result, expected = scenarios.PROJECTED[kind](g, verification=True)
+	scenarios.compare(result, expected, exact=True)
+	result, expected = scenarios.PROJECTED[kind](g, verification=False)
+	for key in ("accepted", "rejected"):
+		# FMA contraction may flip an accept/reject decision that sits on the threshold (seen: 304 instead of 305 rejections)
+		assert abs(int(result[key])-int(expected[key])) <= 2+0.01*int(expected[key]), key
+	for key in ("blind_states", "states", "blind_totals"):
+		np.testing.assert_allclose(result[key], expected[key], rtol=1e-6, atol=1e-10, err_msg=key)
+	np.testing.assert_allclose(result["blind_lyaps"], expected["blind_lyaps"], rtol=1e-6, atol=1e-9)
+	# after a flipped decision the steps, hence the overshoot of every sample (the weights), differ: compare the averages
+	np.testing.assert_allclose(np.sum(result["weights"]), np.sum(expected["weights"]), rtol=1e-2)
+	ours, theirs = np.average(result["lyaps"], weights=result["weights"]), np.average(expected["lyaps"], weights=expected["weights"])
+	assert abs(ours-theirs) < 2e-3, (ours, theirs)
+
+
 def test_reference_golden_vector():
 	"""tests/test_jitcdde.py:88-97 with the reference's own tolerance, production build"""
 	g = scenarios.golden("roessler")

@@ -282,6 +282,16 @@ int jdde_net_poll(jdde_net * h, int32_t * done, double * t, int32_t * status);
 /* device addresses of the staged anchor ([n][2] doubles: state, diff per node) and of the error norm (IEEE bits of a
  * non-negative double) of the attempt under way */
 int jdde_net_exchange_pointers(jdde_net * h, uint64_t * stage, uint64_t * p_bits);
+
+/* Fused peer exchange over NVLink (one process per GPU of one node). jdde_net_exchange_handle writes the CUDA IPC
+ * handle (64 bytes) of this rank's exchange buffer; after the ranks have swapped handles (any channel, e.g.
+ * torch.distributed.all_gather_object) jdde_net_connect_peers maps the peers' buffers (handles: [world][handle_bytes],
+ * this rank's own entry is ignored). From then on jdde_net_attempt stores this rank's part of the tentative anchor
+ * directly into every rank's staging buffer from inside the step kernel, merges the error norm with system-scope
+ * atomics and ends with a device-side arrival barrier between the GPUs: no collective call between jdde_net_attempt
+ * and jdde_net_control any more. All ranks must have connected (host barrier) before any of them integrates. */
+int jdde_net_exchange_handle(jdde_net * h, void * handle, size_t handle_bytes);
+int jdde_net_connect_peers(jdde_net * h, int32_t rank, int32_t world, const void * handles, size_t handle_bytes);
 /* whole calls on a single rank: integrate (_jitcdde.py:807-836), integrate_blindly (:880-933), state [n] */
 int jdde_net_integrate(jdde_net * h, double target, double * out_state, int32_t * status);
 int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double * out_state, int32_t * status);

@@ -110,6 +110,8 @@ SIGNATURES.update({
 	"jdde_net_control": (ctypes.c_int, [_H]),
 	"jdde_net_poll": (ctypes.c_int, [_H, c_int32_p, c_double_p, c_int32_p]),
 	"jdde_net_exchange_pointers": (ctypes.c_int, [_H, c_uint64_p, c_uint64_p]),
+	"jdde_net_exchange_handle": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_size_t]),
+	"jdde_net_connect_peers": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_size_t]),
 	"jdde_net_integrate": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_int32_p]),
 	"jdde_net_integrate_blindly": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_double, c_double_p, c_int32_p]),
 	"jdde_net_recent_state": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int32, c_double_p]),
@@ -531,6 +533,18 @@ class NetEngine:
 		status = ctypes.c_int32()
 		self._check(self.lib.jdde_net_integrate_blindly(self._h, float(target), float(step or 0.0), _dp(out), ctypes.byref(status)))
 		return out, status.value
+
+	def exchange_handle(self):
+		"""CUDA IPC handle of this rank's exchange buffer (bytes), to be passed to the peers"""
+		buffer = ctypes.create_string_buffer(64)
+		self._check(self.lib.jdde_net_exchange_handle(self._h, buffer, 64))
+		return buffer.raw
+
+	def connect_peers(self, rank, world, handles):
+		"""handles: list of the `world` handles in rank order; afterwards attempt() exchanges through peer memory"""
+		blob = b"".join(handles)
+		assert len(blob) == 64*world
+		self._check(self.lib.jdde_net_connect_peers(self._h, int(rank), int(world), blob, 64))
 
 	def recent_state(self, t, current_only=False):
 		out = np.empty(self.n)

@@ -32,13 +32,20 @@ class _DeviceArray:
 
 
 class jitcdde_network:
-	def __init__(self, n, local, coupling, edges, node_parameters=(), weight=None, max_delay=None, device=0, ring_capacity=512, verbose=True, poll_every=8):
+	def __init__(self, n, local, coupling, edges, node_parameters=(), weight=None, max_delay=None, device=0, ring_capacity=512, verbose=True, poll_every=8, exchange=None):
 		"""
 		n: number of nodes. local(y, t, *p) and coupling(y_delayed, y): functions returning SymPy expressions.
 		edges: (src, dst, tau[, weight]) arrays, one entry per directed edge src → dst with delay tau > 0.
 		node_parameters: sequence of arrays of length n, passed to `local` in this order.
 		ring_capacity: anchors kept (power of two); must exceed max_delay / smallest step (2·8·n bytes each).
+		exchange (several GPUs, one process each): "peer" (default) — the step kernel stores the new anchor into the
+		peers' memory over NVLink and the GPUs meet in a device-side barrier (csrc/jdn_kernels.cu) — or "nccl": all-gather
+		and all-reduce between the attempt and the control kernel. Environment: JITCDDE_B200_NET_EXCHANGE.
 		"""
+		import os
+		self.exchange = exchange or os.environ.get("JITCDDE_B200_NET_EXCHANGE", "peer")
+		if self.exchange not in ("peer", "nccl"):
+			raise ValueError("exchange must be 'peer' or 'nccl'")
 		self.n = int(n)
 		self.verbose = verbose
 		self.device = device
@@ -136,6 +143,16 @@ class jitcdde_network:
 	# ------------------------------------------------------------------ multi-GPU anchor exchange
 	def _setup_exchange(self):
 		import torch
+		import torch.distributed as dist
+		if self.exchange == "peer":
+			# fused exchange: the step kernel stores into the peers' staging buffers (CUDA IPC over NVLink) and a device-side
+			# arrival barrier completes it; torch.distributed only carries the 64-byte handles, once
+			handles = [None]*self.world
+			dist.all_gather_object(handles, self._engine.exchange_handle())
+			self._engine.connect_peers(self.rank, self.world, handles)
+			dist.barrier()
+			self._exchange = "peer"
+			return
 		stage_ptr, p_ptr = self._engine.exchange_pointers()
 		as_tensor = lambda ptr, count: torch.as_tensor(_DeviceArray(ptr, (count,), "<f8"), device=torch.device("cuda", self.device))
 		self._exchange = (as_tensor(stage_ptr, 2*self.n), as_tensor(p_ptr, 1))
@@ -184,7 +201,8 @@ class jitcdde_network:
 	def integrate(self, target_time):
 		"""as jitcdde.integrate (_jitcdde.py:807-836)"""
 		self._initiate()
-		if self.world == 1:
+		if self.world == 1 or self._exchange == "peer":
+			# (peer exchange: every rank runs the same loop in the runtime library; the GPUs meet on the device)
 			out, status = self._engine.integrate(target_time)
 			self._raise(status)
 			return out
@@ -197,7 +215,7 @@ class jitcdde_network:
 		self._initiate()
 		step = step or self.max_step
 		assert step > 0, "step must be positive"
-		if self.world == 1:
+		if self.world == 1 or self._exchange == "peer":
 			out, status = self._engine.integrate_blindly(target_time, step)
 			self._raise(status)
 			return out

@@ -52,7 +52,30 @@ typedef struct jdn_control
 	int pws;                  /* a lookup reached into the step under way (not supported here) */
 	int commit_slot;          /* >= 0: the staged anchor was accepted and belongs into this ring slot; -1: nothing to commit */
 	jdde_int_params P;
+	/* peer exchange (several GPUs, jdn_exchange below): number of attempts exchanged so far — never reset; its parity
+	 * selects the staging buffer of the attempt under way — and the buffer the last exchange completed */
+	unsigned long long epoch;
+	int exchanged_buffer;
+	int exchange_failed;      /* a peer did not arrive in time */
 } jdn_control;
+
+/*
+ * Peer exchange of the tentative anchor between the GPUs that share one network (one process per GPU). Every rank owns
+ * one jdn_exchange in device memory that its peers map through CUDA IPC. The step kernel of rank r stores the
+ * (state, diff) pairs of the nodes it owns DIRECTLY into stage[b] of every rank (its own included) — 16-byte stores that
+ * travel over NVLink while the kernel still computes other nodes — and merges its part of the error norm into every
+ * rank's p_bits[b] with a system-scope atomicMax; b = parity of the attempt. A one-thread kernel then tells every peer
+ * "my part of attempt k is with you" (release increment of `arrived`) and waits until all peers have told it the same.
+ * No collective call, no host involvement, no second pass over the data. Two buffers: a rank that is one attempt ahead
+ * writes into the other one, and the arrival counters keep it from getting two ahead.
+ */
+#define JDN_PWS_SENTINEL 0xffffffffffffffffull   /* in p_bits: a rank saw a delay shorter than the step */
+typedef struct jdn_exchange
+{
+	unsigned long long p_bits[2];
+	unsigned long long arrived;
+	unsigned long long pad[13];       /* header = 128 bytes; then: double stage[2][n][2] */
+} jdn_exchange;
 
 typedef struct jdn_problem
 {
@@ -71,7 +94,20 @@ typedef struct jdn_problem
 	long long lo, hi;         /* nodes [lo, hi) are integrated by this rank */
 	int cap;
 	int n_node_params;
+	/* peer exchange: world > 1 once jdde_net_connect_peers has mapped the peers' buffers; peers[r] for r = 0…world−1
+	 * (device array; peers[rank] is this rank's own buffer) */
+	int rank, world;
+	jdn_exchange * const * peers;
 } jdn_problem;
+
+#if defined(__CUDACC__)
+static __host__ __device__ inline double * jdn_exchange_stage(jdn_exchange * x, int buffer, long long n)
+#else
+static inline double * jdn_exchange_stage(jdn_exchange * x, int buffer, long long n)
+#endif
+{
+	return (double *)(x+1) + (size_t)buffer*2*(size_t)n;
+}
 
 typedef struct jdn_image_desc_t
 {

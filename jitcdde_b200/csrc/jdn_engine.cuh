@@ -106,7 +106,7 @@ JDN_FN void lookup_edge(jdn_problem const & P, View const & V, double const h, l
  * `scratch`, the node's part of the tentative anchor, and its contribution |err|/(atol+rtol|y_new|) to the error
  * norm (get_p, :474-498; negative if it is to be skipped). Couplings are summed in the order of the edge list.
  */
-JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h, long long const i, double const * const scratch)
+JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h, long long const i, double const * const scratch, pair & staged)
 {
 	long long const row = i-P.lo;
 	long long const e0 = P.row_ptr[row], e1 = P.row_ptr[row+1];
@@ -138,10 +138,8 @@ JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h
 	double const k_4 = acc;
 
 	double const error = fabs((5*k_1-6*k_2-8*k_3+9*k_4) * (h/72.));
-	pair staged;
 	staged.state = y_new;
-	staged.diff = k_4;
-	reinterpret_cast<pair *>(P.stage)[i] = staged;
+	staged.diff = k_4;      /* the caller stores it: into the staging buffer, or straight into every peer's (jdn_kernels.cu) */
 
 	double const tolerance = P.ctrl->P.atol + P.ctrl->P.rtol*fabs(y_new);
 	if (error != 0.0 || tolerance != 0.0)

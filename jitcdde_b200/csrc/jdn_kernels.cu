@@ -49,11 +49,22 @@ jdn_k_attempt(jdn_problem const P, double const * const scratch)
 	jdn::View const V = jdn::view_of(P);
 	long long const i = P.lo + (long long)blockIdx.x*blockDim.x + threadIdx.x;
 	double contribution = -1.0;
+	int const buffer = (int)(C.epoch & 1);
 	if (i < P.hi)
 	{
-		contribution = jdn::attempt_node(P, V, C.h, i, scratch);
+		jdn::pair staged;
+		contribution = jdn::attempt_node(P, V, C.h, i, scratch, staged);
 		if (!(contribution >= 0.0))      /* skipped (0/0) or NaN: ignored by the reference's `x > p` test */
 			contribution = -1.0;
+		if (P.world > 1)
+		{
+			/* fused exchange: the node's part of the tentative anchor goes straight into every rank's staging buffer
+			 * (peer memory over NVLink; consecutive threads write consecutive 16-byte pairs) */
+			for (int r = 0; r < P.world; r++)
+				reinterpret_cast<jdn::pair *>(jdn_exchange_stage(P.peers[r], buffer, P.n))[i] = staged;
+		}
+		else
+			reinterpret_cast<jdn::pair *>(P.stage)[i] = staged;
 	}
 	for (int o = 16; o > 0; o >>= 1)
 		contribution = fmax(contribution, __shfl_down_sync(0xffffffffu, contribution, o));
@@ -66,8 +77,66 @@ jdn_k_attempt(jdn_problem const P, double const * const scratch)
 		for (int w = 1; w < JDN_BLOCK/32; w++)
 			m = fmax(m, s_max[w]);
 		if (m > 0.0)
-			atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(m));
+		{
+			if (P.world > 1)
+				for (int r = 0; r < P.world; r++)
+					atomicMax_system(&P.peers[r]->p_bits[buffer], (unsigned long long)__double_as_longlong(m));
+			else
+				atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(m));
+		}
 	}
+}
+
+/*
+ * Completion of the fused exchange (several GPUs), one thread: tell every peer that this rank's part of the attempt has
+ * been delivered — the step kernel that stored it has ended, so a release increment orders it after the data — and wait
+ * until every peer has said the same. Then hand the merged error norm to the controller. The wait is bounded: a peer that
+ * does not arrive within 20 s ends the integration with an error instead of hanging the device.
+ */
+extern "C" __global__ void jdn_k_exchange(jdn_problem const P)
+{
+	if (blockIdx.x || threadIdx.x || P.world <= 1)
+		return;
+	jdn_control & C = *P.ctrl;
+	if (C.done)
+		return;
+	int const buffer = (int)(C.epoch & 1);
+	if (C.pws)
+		for (int r = 0; r < P.world; r++)
+			atomicMax_system(&P.peers[r]->p_bits[buffer], JDN_PWS_SENTINEL);
+	__threadfence_system();
+	for (int r = 0; r < P.world; r++)
+		if (r != P.rank)
+			asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(&P.peers[r]->arrived), "l"(1ull) : "memory");
+	jdn_exchange * const own = P.peers[P.rank];
+	unsigned long long const expected = (C.epoch+1)*(unsigned long long)(P.world-1);
+	unsigned long long start, now, arrived;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
+	for (;;)
+	{
+		asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(arrived) : "l"(&own->arrived) : "memory");
+		if (arrived >= expected)
+			break;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+		if (now-start > 20000000000ull)
+		{
+			C.exchange_failed = 1;
+			C.status = JDDE_STATUS_NONFINITE;
+			C.done = 1;
+			return;
+		}
+		__nanosleep(200);
+	}
+	unsigned long long const bits = atomicExch_system(&own->p_bits[buffer], 0ull);
+	if (bits == JDN_PWS_SENTINEL)
+	{
+		C.pws = 1;
+		C.p_bits = 0;
+	}
+	else
+		C.p_bits = bits;
+	C.exchanged_buffer = buffer;
+	C.epoch++;
 }
 
 extern "C" __global__ void jdn_k_control(jdn_problem const P)
@@ -84,7 +153,16 @@ jdn_k_commit(jdn_problem const P)
 	if (slot < 0)
 		return;
 	long long const i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-	if (i < P.n)
+	if (i >= P.n)
+		return;
+	if (P.world > 1)
+	{
+		/* written by the peers: read past L1 */
+		double2 const * const staged = reinterpret_cast<double2 const *>(jdn_exchange_stage(P.peers[P.rank], P.ctrl->exchanged_buffer, P.n));
+		double2 const value = __ldcg(staged+i);
+		reinterpret_cast<double2 *>(P.hist)[(size_t)slot*P.n+i] = value;
+	}
+	else
 		reinterpret_cast<jdn::pair *>(P.hist)[(size_t)slot*P.n+i] = reinterpret_cast<jdn::pair const *>(P.stage)[i];
 }
 

@@ -19,7 +19,11 @@ struct jdde_net
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	cudaLibrary_t lib = nullptr;
-	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr;
+	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr;
+	/* peer exchange: this rank's buffer (mapped by the peers through CUDA IPC), the peers' buffers mapped here */
+	jdn_exchange * exchange = nullptr;
+	std::vector<void *> mapped_peers;
+	jdn_exchange ** d_peers = nullptr;
 	int block = 256;
 	jdn_problem P{};
 	double * scratch = nullptr, * d_out = nullptr, * d_par = nullptr;
@@ -128,6 +132,7 @@ int jdde_net_destroy(jdde_net * h)
 	if (!h) return JDDE_OK;
 	cudaSetDevice(h->desc.device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
+	for (void * p : h->mapped_peers) cudaIpcCloseMemHandle(p);
 	for (void * p : h->allocations) cudaFree(p);
 	if (h->lib) cudaLibraryUnload(h->lib);
 	if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -159,6 +164,11 @@ int jdde_net_load_image(jdde_net * h, const void * image, size_t len)
 	for (auto const & entry : table)
 		if (cudaLibraryGetKernel(entry.slot, h->lib, entry.name) != cudaSuccess)
 			return nfail(h, JDDE_E_IMAGE, std::string("image lacks kernel ") + entry.name);
+	if (cudaLibraryGetKernel(&h->k_exchange, h->lib, "jdn_k_exchange") != cudaSuccess)
+	{
+		h->k_exchange = nullptr;
+		(void)cudaGetLastError();
+	}
 	return JDDE_OK;
 }
 
@@ -266,7 +276,14 @@ int jdde_net_attempt(jdde_net * h)
 	void * largs[] = { &h->P, &h->scratch, &E };
 	if (E && (rc = nlaunch(h, h->k_lookup, E, h->block, (size_t)h->P.cap*sizeof(double), largs))) return rc;
 	void * args[] = { &h->P, &h->scratch };
-	return nlaunch(h, h->k_attempt, h->desc.hi-h->desc.lo, h->block, 0, args);
+	if ((rc = nlaunch(h, h->k_attempt, h->desc.hi-h->desc.lo, h->block, 0, args))) return rc;
+	if (h->P.world > 1)
+	{
+		/* the step kernel has stored this rank's part into every rank's staging buffer: complete the exchange */
+		void * xargs[] = { &h->P };
+		return nlaunch(h, h->k_exchange, 1, 1, 0, xargs);
+	}
+	return JDDE_OK;
 }
 
 int jdde_net_control(jdde_net * h)
@@ -379,6 +396,61 @@ int jdde_net_exchange_pointers(jdde_net * h, uint64_t * stage, uint64_t * p_bits
 	if (!h) return JDDE_E_INVALID;
 	if (stage) *stage = (uint64_t)(uintptr_t)h->P.stage;
 	if (p_bits) *p_bits = (uint64_t)(uintptr_t)&h->P.ctrl->p_bits;
+	return JDDE_OK;
+}
+
+int jdde_net_exchange_handle(jdde_net * h, void * handle, size_t handle_bytes)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	if (!handle || handle_bytes < sizeof(cudaIpcMemHandle_t)) return nfail(h, JDDE_E_INVALID, "handle buffer too small (needs 64 bytes)");
+	if (!h->exchange)
+	{
+		size_t const bytes = sizeof(jdn_exchange) + 2*2*(size_t)h->desc.n*sizeof(double);
+		void * q = nullptr;
+		cudaError_t e = cudaMalloc(&q, bytes);
+		if (e != cudaSuccess) return nfail(h, e == cudaErrorMemoryAllocation ? JDDE_E_NOMEM : JDDE_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+		h->allocations.push_back(q);
+		JN_CUDA(h, cudaMemset(q, 0, bytes));
+		h->exchange = static_cast<jdn_exchange *>(q);
+	}
+	cudaIpcMemHandle_t ipc;
+	JN_CUDA(h, cudaIpcGetMemHandle(&ipc, h->exchange));
+	memset(handle, 0, handle_bytes);
+	memcpy(handle, &ipc, sizeof ipc);
+	return JDDE_OK;
+}
+
+int jdde_net_connect_peers(jdde_net * h, int32_t rank, int32_t world, const void * handles, size_t handle_bytes)
+{
+	int rc = nready(h);
+	if (rc) return rc;
+	if (world < 2 || rank < 0 || rank >= world || !handles || handle_bytes < sizeof(cudaIpcMemHandle_t))
+		return nfail(h, JDDE_E_INVALID, "invalid rank, world or handles");
+	if (!h->exchange) return nfail(h, JDDE_E_INVALID, "call jdde_net_exchange_handle first");
+	if (!h->k_exchange) return nfail(h, JDDE_E_IMAGE, "image lacks kernel jdn_k_exchange");
+	if (h->P.world > 1) return nfail(h, JDDE_E_INVALID, "peers already connected");
+	std::vector<jdn_exchange *> peers((size_t)world, nullptr);
+	for (int r = 0; r < world; r++)
+	{
+		if (r == rank)
+		{
+			peers[r] = h->exchange;
+			continue;
+		}
+		cudaIpcMemHandle_t ipc;
+		memcpy(&ipc, (const char *)handles + (size_t)r*handle_bytes, sizeof ipc);
+		void * q = nullptr;
+		JN_CUDA(h, cudaIpcOpenMemHandle(&q, ipc, cudaIpcMemLazyEnablePeerAccess));
+		h->mapped_peers.push_back(q);
+		peers[r] = static_cast<jdn_exchange *>(q);
+	}
+	if ((rc = nalloc(h, &h->d_peers, (size_t)world))) return rc;
+	JN_CUDA(h, cudaMemcpy(h->d_peers, peers.data(), (size_t)world*sizeof(jdn_exchange *), cudaMemcpyHostToDevice));
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	h->P.peers = h->d_peers;
+	h->P.rank = rank;
+	h->P.world = world;
 	return JDDE_OK;
 }
 

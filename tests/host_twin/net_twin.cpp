@@ -134,7 +134,9 @@ int jdde_net_attempt(jdde_net * h)
 	double m = -1.0;
 	for (long long i = h->P.lo; i < h->P.hi; i++)
 	{
-		double c = jdn::attempt_node(h->P, V, C.h, i, h->scratch.data());
+		jdn::pair staged;
+		double c = jdn::attempt_node(h->P, V, C.h, i, h->scratch.data(), staged);
+		reinterpret_cast<jdn::pair *>(h->P.stage)[i] = staged;
 		if (c >= 0.0 && c > m) m = c;
 	}
 	if (m > 0.0)

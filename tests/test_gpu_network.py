@@ -43,3 +43,64 @@ def test_large_network_properties():
 	# phases advance roughly with omega = 1 plus bounded coupling
 	drift = (samples[-1]-g["initial"])/times[-1]
 	assert np.all(np.abs(drift-1.0) < 2.2)
+
+
+def _peer_worker(rank, world, port, queue, n):
+	"""one rank of a two-process run; with a single visible GPU both ranks share it (CUDA IPC works within a device, too)"""
+	import os
+	import warnings
+	warnings.simplefilter("ignore")
+	os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+	import torch
+	import torch.distributed as dist
+	from jitcdde_b200 import jitcdde_network
+	device = rank % torch.cuda.device_count()
+	torch.cuda.set_device(device)
+	dist.init_process_group("gloo", rank=rank, world_size=world)      # rendezvous only: carries the IPC handles
+	g = large_graph(n)
+	net = jitcdde_network(n, local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y), edges=(g["src"], g["dst"], g["edge_tau"]),
+		weight=g["weight"], node_parameters=[g["omega"]], verbose=False, device=device, ring_capacity=512, exchange="peer")
+	net.set_integration_parameters(rtol=0, atol=1e-5)
+	net.constant_past(g["initial"], time=0.0)
+	blind = net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1)
+	out = net.integrate(net.t+2.0)
+	queue.put((rank, blind, out, net.counters()))
+	dist.barrier()
+	dist.destroy_process_group()
+
+
+def test_fused_peer_exchange_equals_one_gpu():
+	"""Two ranks that own half of the nodes each and exchange the tentative anchor through peer memory from inside the step
+	kernel (device-side arrival barrier, csrc/jdn_kernels.cu: jdn_k_exchange) take the same steps and reach bit-identical
+	states as one rank that owns all nodes."""
+	import socket
+	import torch.multiprocessing as mp
+	from jitcdde_b200 import jitcdde_network
+	n = 20_000
+	g = large_graph(n)
+	net = jitcdde_network(n, local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y), edges=(g["src"], g["dst"], g["edge_tau"]),
+		weight=g["weight"], node_parameters=[g["omega"]], verbose=False, ring_capacity=512)
+	net.set_integration_parameters(rtol=0, atol=1e-5)
+	net.constant_past(g["initial"], time=0.0)
+	blind = net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1)
+	out = net.integrate(net.t+2.0)
+	counters = net.counters()
+	del net
+
+	sock = socket.socket()
+	sock.bind(("127.0.0.1", 0))
+	port = sock.getsockname()[1]
+	sock.close()
+	ctx = mp.get_context("spawn")
+	queue = ctx.Queue()
+	procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, queue, n)) for r in range(2)]
+	for p in procs:
+		p.start()
+	results = [queue.get(timeout=600) for _ in procs]
+	for p in procs:
+		p.join(timeout=120)
+		assert p.exitcode == 0
+	for rank, peer_blind, peer_out, peer_counters in results:
+		assert np.array_equal(peer_blind, blind), rank
+		assert np.array_equal(peer_out, out), rank
+		assert tuple(peer_counters) == tuple(counters), rank

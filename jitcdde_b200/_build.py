@@ -94,15 +94,26 @@ def use_window(program):
 	  1  a register-resident window (measured slower: its registers cost resident warps),
 	  2  a per-thread window in shared memory filled by cp.async one move ahead (fastest where it fits:
 	     1.29e10 → 1.77e10 steps/s for the Mackey–Glass ensemble, profiles/variants_r01.md).
+	  3  the same for anchors of more than 8 doubles: contiguous anchors in a per-thread area of shared memory,
+	     lookups hand out pointers into it (n = 6 with one distinct delay: 520 bytes per thread).
 	Mode 2 needs 4 anchors × lookup sites × 8·A bytes of shared memory per thread; it is chosen when that is
-	at most 128 bytes (n = 1 with one distinct delay), so that 32 warps per SM stay resident.
-	JITCDDE_B200_WINDOW overrides (tests exercise all modes).
+	at most 128 bytes (n = 1 with one distinct delay), so that 32 warps per SM stay resident. Mode 3 is chosen up to
+	600 bytes per thread (64-thread blocks, 6 per SM), unless the system is a Lyapunov extension that the lane-group
+	stepper takes (use_group). JITCDDE_B200_WINDOW overrides (tests exercise all modes).
 	"""
+	A = _anchor_doubles(program)
 	override = os.environ.get("JITCDDE_B200_WINDOW")
 	if override is not None:
-		return int(override) if program.n_sites > 0 else 0
-	if program.n_sites > 0 and program.n_sites*4*_anchor_doubles(program)*8 <= 128:
+		mode = int(override) if program.n_sites > 0 else 0
+		if mode == 3 and A <= 8:
+			mode = 2
+		if mode == 2 and A > 8:
+			mode = 3 if program.n_sites*4*A*8+8 <= 600 else 0
+		return mode
+	if program.n_sites > 0 and program.n_sites*4*A*8 <= 128:
 		return 2
+	if program.n_sites > 0 and A > 8 and program.n_sites*4*A*8+8 <= 600 and not getattr(program, "group_lanes", 0):
+		return 3
 	return 0
 
 
@@ -119,6 +130,8 @@ def launch_shape(program):
 	if override:
 		block, blocks = override.split("x")
 		return int(block), int(blocks)
+	if use_window(program) == 3:
+		return 64, 6
 	if program.n <= 2:
 		return (32, 32) if use_window(program) == 2 else (32, 20)
 	if program.n <= 8:

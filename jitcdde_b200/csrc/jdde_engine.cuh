@@ -56,7 +56,7 @@
 #define JD_WINDOW 0
 #endif
 /* Lookups hand anchor pairs around by value (registers) when anchors are small, by pointer otherwise */
-#define JD_SEG_BY_VALUE (JD_WINDOW || JD_A <= 8)
+#define JD_SEG_BY_VALUE (JD_WINDOW == 1 || JD_WINDOW == 2 || JD_A <= 8)
 #define JD_NORM_THRESHOLD (1e-30)     /* jitced_template.c:15 */
 
 #if defined(__CUDACC__)
@@ -117,7 +117,30 @@ JD_FN double seg_tv(Seg const & s) { return s.tv; }
 JD_FN double seg_tw(Seg const & s) { return s.tw; }
 #endif
 
-#if JD_WINDOW == 2
+#if JD_WINDOW == 3
+/* Shared-memory window for anchors too large for registers (device only; 8 < JD_A): as JD_WINDOW == 2 — per thread and
+ * lookup site the anchors cursor−1 … cursor+2 in shared memory, filled by cp.async one cursor move ahead — but the
+ * anchors lie CONTIGUOUSLY in the thread's private area and lookups hand out pointers into it (the by-pointer Seg), so
+ * that the Hermite formulas read the components they need from shared memory instead of making two to three
+ * dependent trips to L2/DRAM per lookup (the neutral ensemble: 20 of 33 cycles per issued instruction on the long
+ * scoreboard, profiles/). The areas of consecutive threads are an odd number of 8-byte words apart: equal offsets of
+ * the 32 lanes fall into different banks. */
+#if JD_A <= 8
+#error "JD_WINDOW == 3 is for anchors of more than 8 doubles"
+#endif
+struct Window
+{
+	bool valid;
+	bool fresh;        /* the copies of (cursor, cursor+1) have been requested but not yet awaited */
+	bool prev_ok;
+	bool next_ok;
+};
+#ifndef JD_BLOCK
+#define JD_BLOCK 128
+#endif
+#define JD_PWIN_DOUBLES ((JD_NSITES > 0 ? JD_NSITES : 1)*4*JD_A + 1)     /* per thread */
+#define JD_WIN_SMEM_BYTES (JD_PWIN_DOUBLES*8*JD_BLOCK)
+#elif JD_WINDOW == 2
 /* Shared-memory window (device only): per thread and lookup site a private 4-anchor circular buffer in shared
  * memory holds the anchors cursor-1 … cursor+2 (slot = index & 3). Anchors are brought in with cp.async
  * (global → shared without passing through registers) one move ahead of their use, so a lookup that stays in
@@ -310,7 +333,118 @@ JD_FN int walk(MT & M, int const site, double const t, double const * & pa, doub
 	return ca;
 }
 
-#if JD_WINDOW == 2
+#if JD_WINDOW == 3
+#if defined(__CUDA_ARCH__)
+extern __shared__ double jd_pwin_smem[];
+
+__device__ __forceinline__ double * pwin_slot(int const site, int const index)
+{
+	return jd_pwin_smem + (size_t)threadIdx.x*JD_PWIN_DOUBLES + (size_t)(site*4 + (index & 3))*JD_A;
+}
+
+__device__ __forceinline__ void pwin_fetch(int const site, int const index, double const * const anchor)
+{
+	double * const dst = pwin_slot(site, index);
+	JD_UNROLL
+	for (int k = 0; k < 1+2*JD_N; k++)
+	{
+		unsigned const d = (unsigned)__cvta_generic_to_shared(dst+k);
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(anchor+k) : "memory");
+	}
+}
+
+__device__ __forceinline__ void pwin_wait()
+{
+	asm volatile("cp.async.wait_all;" ::: "memory");
+}
+#else
+/* host pass of nvcc: never executed */
+inline double * pwin_slot(int, int) { return nullptr; }
+inline void pwin_fetch(int, int, double const *) {}
+inline void pwin_wait() {}
+#endif
+
+JD_FN void fill_window(Member & M, int const site)
+{
+	Window & W = M.win[site];
+	int const ca = M.cursor[site];
+	W.valid = ca+1 <= M.current;
+	if (!W.valid)
+		return;
+	pwin_fetch(site, ca, M.slot(ca));
+	pwin_fetch(site, ca+1, M.slot(ca+1));
+	W.fresh = true;
+	W.next_ok = ca+2 <= M.current;
+	if (W.next_ok)
+		pwin_fetch(site, ca+2, M.slot(ca+2));
+	W.prev_ok = ca-1 >= M.first;
+	if (W.prev_ok)
+		pwin_fetch(site, ca-1, M.slot(ca-1));
+}
+
+/* the same comparisons as walk(), on staged times; invariant as for JD_WINDOW == 2 */
+JD_FN Seg anchors(Member & M, int const site, double const t)
+{
+	Window & W = M.win[site];
+	Seg s;
+	if (W.valid)
+	{
+		if (W.fresh)
+		{
+			pwin_wait();
+			W.fresh = false;
+		}
+		int ca = M.cursor[site];
+		double tv = pwin_slot(site, ca)[0];
+		double tw = pwin_slot(site, ca+1)[0];
+		bool hit = true;
+		while (tv > t && ca > M.first)
+		{
+			if (!W.prev_ok)
+			{
+				hit = false;
+				break;
+			}
+			--ca;
+			W.next_ok = true;
+			W.prev_ok = ca-1 >= M.first;
+			pwin_wait();
+			tw = tv;
+			tv = pwin_slot(site, ca)[0];
+			if (W.prev_ok)
+				pwin_fetch(site, ca-1, M.slot(ca-1));
+		}
+		while (hit && tw < t)
+		{
+			if (!W.next_ok)
+			{
+				hit = false;
+				break;
+			}
+			++ca;
+			W.prev_ok = true;
+			W.next_ok = ca+2 <= M.current;
+			pwin_wait();
+			tv = tw;
+			tw = pwin_slot(site, ca+1)[0];
+			if (W.next_ok)
+				pwin_fetch(site, ca+2, M.slot(ca+2));
+		}
+		M.cursor[site] = ca;
+		if (hit)
+		{
+			s.v = pwin_slot(site, ca);
+			s.w = pwin_slot(site, ca+1);
+			s.tv = tv;
+			s.tw = tw;
+			return s;
+		}
+	}
+	walk(M, site, t, s.v, s.w, s.tv, s.tw);
+	fill_window(M, site);
+	return s;
+}
+#elif JD_WINDOW == 2
 #if defined(__CUDA_ARCH__)
 extern __shared__ d2 jd_win_smem[];
 

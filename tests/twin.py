@@ -20,7 +20,8 @@ _OUT = os.path.join(_HERE, "host_twin", "_build")
 
 def build_twin(program, n_basic=None):
 	n_basic = n_basic or program.n
-	window = int(_build.use_window(program)) % 2      # mode 2 (cp.async into shared memory) exists on the device only
+	window = int(_build.use_window(program))
+	window = window if window < 2 else 0      # modes 2 and 3 (cp.async into shared memory) exist on the device only
 	os.makedirs(_OUT, exist_ok=True)
 	rhs = os.path.join(_OUT, f"rhs_{program.key}.inc")
 	with open(rhs, "w") as f:

@@ -11,9 +11,11 @@
  *
  * HBM layout:
  *   times  [cap]          anchor times (shared by all nodes)
- *   hist   [cap][n][2]    slot-major, (state, diff) of a node interleaved: the n pairs of one anchor are contiguous →
- *                         the node-parallel reads and writes of a step are coalesced, and a delayed lookup gathers ONE
- *                         16-byte pair per history row (two rows per lookup) instead of four scattered doubles
+ *   hist   [cap/2][n][2][2]  (state, diff) of a node interleaved (one 16-byte pair per anchor), and the pairs of ring slots
+ *                         2k and 2k+1 of the same node next to each other (jdn_pair_index): a delayed lookup needs the
+ *                         pairs of two consecutive anchors of ONE node — half of the time they now share a 32-byte sector,
+ *                         and the three stage lookups of an attempt (2–3 consecutive anchors) touch 2 sectors instead of 3.
+ *                         Node-parallel reads and writes of a step stride by 32 bytes (every other pair).
  *   edges  CSR by destination node: row_ptr[n_owned+1], src[E], tau[E], weight[E], cursor[E]
  *          (cursor = the reference's per-call-site search cursor, jitced_template.c:44-45: one lookup site per edge)
  *   stage  [n][2]         the tentative anchor of the attempt under way. It has a FIXED address, so with several
@@ -99,6 +101,20 @@ typedef struct jdn_problem
 	int rank, world;
 	jdn_exchange * const * peers;
 } jdn_problem;
+
+/* ring slots are grouped by 2^JDN_ROW_GROUP_LOG2 consecutive anchors per node (ring capacities are powers of two >= 4) */
+#ifndef JDN_ROW_GROUP_LOG2
+#define JDN_ROW_GROUP_LOG2 2
+#endif
+/* index of the (state, diff) pair of node i in ring slot `slot` (in units of pairs) */
+#if defined(__CUDACC__)
+static __host__ __device__ inline size_t jdn_pair_index(int slot, long long i, long long n)
+#else
+static inline size_t jdn_pair_index(int slot, long long i, long long n)
+#endif
+{
+	return (((size_t)(slot >> JDN_ROW_GROUP_LOG2)*(size_t)n + (size_t)i) << JDN_ROW_GROUP_LOG2) + (size_t)(slot & ((1 << JDN_ROW_GROUP_LOG2)-1));
+}
 
 #if defined(__CUDACC__)
 static __host__ __device__ inline double * jdn_exchange_stage(jdn_exchange * x, int buffer, long long n)

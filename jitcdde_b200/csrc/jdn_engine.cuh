@@ -69,8 +69,8 @@ JDN_FN double past_value(jdn_problem const & P, View const & V, int const ca, lo
 	double const q = anchor_time(V, ca+1)-tv;
 	double const x = (t - tv)/q;
 	pair const * const H = reinterpret_cast<pair const *>(P.hist);
-	pair const v = H[(size_t)(ca & V.mask)*P.n + j];
-	pair const w = H[(size_t)((ca+1) & V.mask)*P.n + j];
+	pair const v = H[jdn_pair_index(ca & V.mask, j, P.n)];
+	pair const w = H[jdn_pair_index((ca+1) & V.mask, j, P.n)];
 	double const a = v.state;
 	double const b = v.diff * q;
 	double const c = w.state;
@@ -110,7 +110,7 @@ JDN_FN double attempt_node(jdn_problem const & P, View const & V, double const h
 {
 	long long const row = i-P.lo;
 	long long const e0 = P.row_ptr[row], e1 = P.row_ptr[row+1];
-	pair const cur = reinterpret_cast<pair const *>(P.hist)[(size_t)(V.current & V.mask)*P.n + i];
+	pair const cur = reinterpret_cast<pair const *>(P.hist)[jdn_pair_index(V.current & V.mask, i, P.n)];
 	double const y = cur.state;
 	double const k_1 = cur.diff;
 	double par[JDN_NPARAMS > 0 ? JDN_NPARAMS : 1];
@@ -267,8 +267,8 @@ JDN_FN double recent_state(jdn_problem const & P, double const t, long long cons
 	jdn_control const & C = *P.ctrl;
 	int const mask = P.cap-1;
 	pair const * const H = reinterpret_cast<pair const *>(P.hist);
-	pair const v = H[(size_t)((C.current-1) & mask)*P.n + i];
-	pair const w = H[(size_t)(C.current & mask)*P.n + i];
+	pair const v = H[jdn_pair_index((C.current-1) & mask, i, P.n)];
+	pair const w = H[jdn_pair_index(C.current & mask, i, P.n)];
 	double const tv = P.times[(C.current-1) & mask];
 	double const q = P.times[C.current & mask]-tv;
 	double const x = (t - tv)/q;

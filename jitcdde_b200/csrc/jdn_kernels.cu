@@ -160,10 +160,10 @@ jdn_k_commit(jdn_problem const P)
 		/* written by the peers: read past L1 */
 		double2 const * const staged = reinterpret_cast<double2 const *>(jdn_exchange_stage(P.peers[P.rank], P.ctrl->exchanged_buffer, P.n));
 		double2 const value = __ldcg(staged+i);
-		reinterpret_cast<double2 *>(P.hist)[(size_t)slot*P.n+i] = value;
+		reinterpret_cast<double2 *>(P.hist)[jdn_pair_index(slot, i, P.n)] = value;
 	}
 	else
-		reinterpret_cast<jdn::pair *>(P.hist)[(size_t)slot*P.n+i] = reinterpret_cast<jdn::pair const *>(P.stage)[i];
+		reinterpret_cast<jdn::pair *>(P.hist)[jdn_pair_index(slot, i, P.n)] = reinterpret_cast<jdn::pair const *>(P.stage)[i];
 }
 
 /* prepare a call: mode, target, step; blind: h and the number of steps are given by the host (_jitcdde.py:880-900) */
@@ -205,7 +205,7 @@ jdn_k_recent_state(jdn_problem const P, double const t, int const current_only, 
 	if (i >= P.n)
 		return;
 	if (current_only)
-		out[i] = P.hist[2*((size_t)(P.ctrl->current & (P.cap-1))*P.n + i)];      /* get_current_state */
+		out[i] = P.hist[2*jdn_pair_index(P.ctrl->current & (P.cap-1), i, P.n)];      /* get_current_state */
 	else
 		out[i] = jdn::recent_state(P, t, i);
 }
@@ -218,8 +218,8 @@ jdn_k_set_past(jdn_problem const P, int const n_anchors, double const * const ti
 	if (i < P.n)
 		for (int k = 0; k < n_anchors; k++)
 		{
-			P.hist[2*((size_t)k*P.n+i)] = states[(size_t)k*P.n+i];
-			P.hist[2*((size_t)k*P.n+i)+1] = diffs[(size_t)k*P.n+i];
+			P.hist[2*jdn_pair_index(k, i, P.n)] = states[(size_t)k*P.n+i];
+			P.hist[2*jdn_pair_index(k, i, P.n)+1] = diffs[(size_t)k*P.n+i];
 		}
 	for (long long e = i; e < n_edges; e += (long long)gridDim.x*blockDim.x)
 		P.cursor[e] = n_anchors-2;      /* all cursors start at last_anchor->previous (:647-648) */

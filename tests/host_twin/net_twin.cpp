@@ -74,11 +74,12 @@ int jdde_net_set_past(jdde_net * h, int32_t k, const double * times, const doubl
 	if (k+1 > h->P.cap) return fail(h, JDDE_E_INVALID, "initial past does not fit into the ring; increase ring_capacity");
 	size_t const n = (size_t)h->desc.n;
 	memcpy(h->times.data(), times, k*sizeof(double));
-	for (size_t r = 0; r < (size_t)k*n; r++)
-	{
-		h->hist[2*r] = states[r];
-		h->hist[2*r+1] = diffs[r];
-	}
+	for (int a = 0; a < k; a++)
+		for (size_t i = 0; i < n; i++)
+		{
+			h->hist[2*jdn_pair_index(a, (long long)i, (long long)n)] = states[(size_t)a*n+i];
+			h->hist[2*jdn_pair_index(a, (long long)i, (long long)n)+1] = diffs[(size_t)a*n+i];
+		}
 	std::fill(h->cursor.begin(), h->cursor.end(), k-2);
 	jdn_control & C = h->ctrl;
 	C.first = 0; C.current = k-1; C.t = times[k-1]; C.last_start = times[0]; C.status = JDDE_STATUS_OK; C.done = 1; C.commit_slot = -1;
@@ -155,7 +156,11 @@ int jdde_net_control(jdde_net * h)
 	if (slot >= 0)
 	{
 		size_t const n = (size_t)h->desc.n;
-		memcpy(&h->hist[2*slot*n], h->stage.data(), 2*n*sizeof(double));
+		for (size_t i = 0; i < n; i++)
+		{
+			h->hist[2*jdn_pair_index(slot, (long long)i, (long long)n)] = h->stage[2*i];
+			h->hist[2*jdn_pair_index(slot, (long long)i, (long long)n)+1] = h->stage[2*i+1];
+		}
 	}
 	h->launches += 2;
 	return JDDE_OK;
@@ -180,7 +185,7 @@ int jdde_net_recent_state(jdde_net * h, double t, int32_t current_only, double *
 {
 	size_t const n = (size_t)h->desc.n;
 	for (size_t i = 0; i < n; i++)
-		out[i] = current_only ? h->hist[2*((size_t)(h->ctrl.current & (h->P.cap-1))*n+i)] : jdn::recent_state(h->P, t, (long long)i);
+		out[i] = current_only ? h->hist[2*jdn_pair_index(h->ctrl.current & (h->P.cap-1), (long long)i, (long long)n)] : jdn::recent_state(h->P, t, (long long)i);
 	return JDDE_OK;
 }
 

@@ -399,7 +399,7 @@ def gpu_arm(args):
 
 
 #: dram__bytes_read.sum + dram__bytes_write.sum of one jdde_k_integrate launch from the ncu capture under profiles/ (null until measured)
-TRAFFIC_PER_LAUNCH = 3648257872   # 2.666 GB read + 0.982 GB written, profiles/ncu_full_r01_final_jdde_k_integrate.csv (launch #14 of the bench)
+TRAFFIC_PER_LAUNCH = 3651599704   # 2.664 GB read + 0.988 GB written, profiles/ncu_full_r01_final_jdde_k_integrate.csv (launch #14 of the bench)
 
 
 def reference_arm(args):

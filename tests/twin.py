@@ -28,7 +28,7 @@ def build_twin(program, n_basic=None):
 		f.write(program.body)
 	so = os.path.join(_OUT, f"twin_{program.key}_{n_basic}_w{window}.so")
 	src = os.path.join(_HERE, "host_twin", "twin.cpp")
-	deps = [src] + [os.path.join(_build.CSRC, x) for x in ("jdde_engine.cuh", "jdde_math.h", "jdde_abi.h")]
+	deps = [src] + [os.path.join(_build.CSRC, x) for x in ("jdde_engine.cuh", "jdde_team.cuh", "jdde_group.cuh", "jdde_math.h", "jdde_abi.h")]
 	if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
 		subprocess.run([
 			"g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",

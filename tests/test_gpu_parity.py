@@ -265,6 +265,18 @@ def test_cluster_orthonormalisation_is_bitwise_identical(ring_capacity):
 	np.testing.assert_allclose(fast["lyaps"][:2], theirs["lyaps"][:2], rtol=1e-6, atol=1e-8)
 
 
+def test_production_build_is_deterministic():
+	"""Lane groups, shared-memory staging by cp.async, cluster sums through distributed shared memory: no result may depend on
+	the timing of warps or blocks — two runs of the production build agree bit for bit (C3 with cluster Gram–Schmidt, C5b with
+	the pointer window)."""
+	a, b = (scenarios.product_c3(100, ring_capacity=1024) for _ in range(2))
+	for key in a:
+		assert np.array_equal(a[key], b[key]), key
+	a, b = (scenarios.product_c5b(512) for _ in range(2))
+	for key in a:
+		assert np.array_equal(a[key], b[key]), key
+
+
 def test_state_dependent_ensemble_c5a():
 	"""BASELINE.json configs[4], state-dependent delay with per-member pasts (divergent lookups, backward
 	moves of the cursor, max_delay = 1e10 so nothing is ever forgotten and rings grow)."""

@@ -13,7 +13,7 @@ The integrator runs as CUDA kernels for sm_100a behind a C ABI
 """
 
 from ._symbols import anchors, current_y, dy, input, past_dy, past_y, quadrature, t, y  # noqa: A004
-from ._jitcdde import UnsuccessfulIntegration, jitcdde, jitcdde_input, jitcdde_lyap, _find_max_delay, _propagate_delays
+from ._jitcdde import UnsuccessfulIntegration, jitcdde, jitcdde_input, jitcdde_lyap, test, _find_max_delay, _propagate_delays
 from ._codegen import get_delays as _get_delays
 from ._capi import pinned_empty
 
@@ -26,5 +26,5 @@ from ._transversal import GroupHandler, jitcdde_restricted_lyap, jitcdde_transve
 
 __all__ = [
 	"UnsuccessfulIntegration", "anchors", "current_y", "dy", "input", "jitcdde", "jitcdde_input", "jitcdde_lyap", "jitcdde_restricted_lyap", "jitcdde_transversal_lyap",
-	"past_dy", "past_y", "quadrature", "t", "y", "jitcdde_network", "shard", "gather_members", "pinned_empty",
+	"past_dy", "past_y", "quadrature", "t", "test", "y", "jitcdde_network", "shard", "gather_members", "pinned_empty",
 ]

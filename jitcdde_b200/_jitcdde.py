@@ -776,3 +776,21 @@ class jitcdde_input(jitcdde):
 		extended_amplitude = np.hstack((amplitude, np.zeros(self.input_past.n)))
 		minima, maxima = super().jump(extended_amplitude, *args, **kwargs)
 		return minima[..., :self.input_base_n], maxima[..., :self.input_base_n]
+
+
+def test(omp=True, sympy=True):
+	"""
+	Quick sanity check of the installation (reference: _jitcdde.py:1661-1677): code generation, nvcc, the runtime
+	library and a CUDA device. Finishes without any message if everything works. `omp` has no meaning here.
+	"""
+	if sympy:
+		import sympy  # noqa: F401
+	from ._symbols import t, y
+	DDE = jitcdde([y(1, t-1), -y(0, t-2)], verbose=False)
+	DDE.compile_C(chunk_size=1, omp=omp)
+	DDE.constant_past([1, 2])
+	DDE.step_on_discontinuities()
+	DDE.integrate(DDE.t+1)
+
+
+test.__test__ = False      # not a pytest test

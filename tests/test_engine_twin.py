@@ -125,3 +125,9 @@ def test_restricted_and_transversal_lyapunov_agree(twin):
 		assert (np.sign(l1) if abs(l1) > m1 else 0) == sign
 		assert (np.sign(l2) if abs(l2) > m2 else 0) == sign
 		assert abs(l1-l2) < max(m1, m2), (k, l1, m1, l2, m2)
+
+
+def test_installation_check(twin):
+	"""jitcdde.test() of the reference (_jitcdde.py:1661-1677): finishes silently"""
+	import jitcdde_b200
+	assert jitcdde_b200.test() is None

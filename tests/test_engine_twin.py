@@ -131,3 +131,52 @@ def test_installation_check(twin):
 	"""jitcdde.test() of the reference (_jitcdde.py:1661-1677): finishes silently"""
 	import jitcdde_b200
 	assert jitcdde_b200.test() is None
+
+
+def test_orthonormalisation_invariants(twin):
+	"""tests/test_past.py:10-27 on the engine's Gram–Schmidt: after orthonormalising, the separation functions have norm 1 and
+	are mutually orthogonal over the delay window — a second pass finds nothing to remove and returns norms of 1."""
+	from jitcdde_b200 import jitcdde_lyap, t, y
+	rng = np.random.default_rng(seed=42)
+	m = 4
+	DDE = jitcdde_lyap([-y(0, t-2)], n_lyap=m-1, verbose=False, verification=True)
+	for time in sorted(rng.uniform(-3, 0, 5)):
+		DDE.add_past_point(time, rng.normal(0, 1, m), rng.normal(0, 1, m))
+	delay = rng.uniform(0.0, 2.0)
+	DDE._initiate()
+	first = DDE._engine.orthonormalise(m-1, delay)
+	assert np.all(first > 0) and not np.allclose(first, 1.0)
+	np.testing.assert_allclose(DDE._engine.orthonormalise(m-1, delay), 1.0, rtol=1e-12)
+
+
+def test_remove_projections_invariants(twin):
+	"""tests/test_past.py:29-86: removing the projections twice changes nothing the second time and leaves a normalised
+	separation function; unit vectors are removed by zeroing the component."""
+	from jitcdde_b200 import jitcdde_restricted_lyap, t, y
+	rng = np.random.default_rng(seed=42)
+	n_basic = 3
+	f = [-y(1, t-1), -y(2, t-1), -y(0, t-1)]
+	random_vector = lambda: rng.random(n_basic)
+	DDE = jitcdde_restricted_lyap(f, vectors=[(random_vector(), random_vector()), (random_vector(), random_vector())], verbose=False, verification=True)
+	assert DDE.n == 6*n_basic
+	time = rng.uniform(-10, 10)
+	for _ in range(rng.integers(3, 10)):
+		DDE.add_past_point(time, rng.random(DDE.n), rng.random(DDE.n))
+		time += 0.1 + rng.random()
+	DDE.remove_projections()
+	before = DDE.get_state()
+	assert abs(DDE.remove_projections()-1.0) < 1e-12
+	for a, b in zip(before, DDE.get_state()):
+		np.testing.assert_allclose(a[1], b[1], rtol=1e-12, atol=1e-14)
+		np.testing.assert_allclose(a[2], b[2], rtol=1e-12, atol=1e-14)
+		assert not a[1][2*n_basic:].any() and not a[2][2*n_basic:].any()      # the dummies are cleared
+
+	unit = np.zeros(n_basic)
+	unit[1] = 1
+	DDE = jitcdde_restricted_lyap(f, vectors=[(unit, np.zeros(n_basic)), (np.zeros(n_basic), unit)], verbose=False, verification=True)
+	assert DDE.n == 2*n_basic and DDE.state_components == [1] and DDE.diff_components == [1]
+	DDE.add_past_point(-1.0, rng.random(DDE.n), rng.random(DDE.n))
+	DDE.add_past_point(0.0, rng.random(DDE.n), rng.random(DDE.n))
+	DDE.remove_projections()
+	for anchor in DDE.get_state():
+		assert anchor[1][n_basic+1] == 0.0 and anchor[2][n_basic+1] == 0.0

@@ -337,3 +337,22 @@ def test_pipelined_sampling(twin):
 @pytest.mark.gpu
 def test_pipelined_sampling_gpu():
 	_pipelined_against_synchronous(N=4096)
+
+
+def test_symbols_from_anywhere_give_the_same_program():
+	"""tests/test_sympy_input.py: symbols imported from the package, from its sympy_symbols module, or defined by hand with
+	SymPy (the reference's users do all three) lead to the same generated statements"""
+	import sympy
+	import jitcdde_b200
+	import jitcdde_b200.sympy_symbols
+	from jitcdde_b200 import _codegen
+	manual_t = sympy.Symbol("t", real=True)
+	manual_current_y, manual_past_y, manual_anchors = (sympy.Function(name, real=True) for name in ("current_y", "past_y", "anchors"))
+	def manual_y(index, time=manual_t):
+		return manual_current_y(index) if time == manual_t else manual_past_y(time, index, manual_anchors(time))
+	bodies = set()
+	for t_, y_ in ((jitcdde_b200.t, jitcdde_b200.y), (jitcdde_b200.sympy_symbols.t, jitcdde_b200.sympy_symbols.y), (manual_t, manual_y),
+			(jitcdde_b200.sympy_symbols.t, manual_y)):
+		f = [sympy.cos(t_)*y_(1, t_-3.5) - y_(0), -y_(0, t_-1.25)*y_(1)]
+		bodies.add(_codegen.generate(f).body)
+	assert len(bodies) == 1

@@ -892,7 +892,8 @@ JD_FN double local_p(double const (&err)[NL], double const (&new_y)[NL], double 
 		{
 			double const error = fabs(err[i]);
 			double const tolerance = atol+rtol*fabs(new_y[i]);
-			if ((error != 0.0 || tolerance != 0.0) && error*best_tol > best_e*tolerance)
+			/* (0/0 needs no test of its own here: 0·best_tol > best_e·0 is false) */
+			if (error*best_tol > best_e*tolerance)
 			{
 				best_e = error;
 				best_tol = tolerance;

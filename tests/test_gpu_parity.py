@@ -265,6 +265,31 @@ def test_cluster_orthonormalisation_is_bitwise_identical(ring_capacity):
 	np.testing.assert_allclose(fast["lyaps"][:2], theirs["lyaps"][:2], rtol=1e-6, atol=1e-8)
 
 
+def _lyap_sweep(n_lyap, N):
+	from jitcdde_b200 import jitcdde_lyap
+	rng = np.random.default_rng(3)
+	system = systems.two_roessler(control=True)
+	DDE = jitcdde_lyap(system["f"], n_lyap=n_lyap, control_pars=system["control_pars"], n_members=N, verbose=False, verification=True, rng=np.random.default_rng(4))
+	DDE.add_past_point(-4.5, rng.random(6), rng.random(6))
+	DDE.add_past_point(0.0, rng.random(6), rng.random(6))
+	DDE.set_integration_parameters(**systems.LYAP_TEST_PARAMETERS)
+	DDE.set_parameters((0.5*np.arange(N)/(N-1)).reshape(N, 1))
+	DDE.step_on_discontinuities()
+	out = [DDE.integrate(DDE.t+5.0) for _ in range(3)]
+	return [np.asarray(x) for sample in out for x in sample] + list(DDE.counters())
+
+
+@pytest.mark.parametrize("n_lyap", [1, 8])
+def test_lane_groups_of_other_sizes(monkeypatch, n_lyap):
+	"""2 lanes per member (16 members per warp) and 9 lanes per member (3 members, 27 of 32 lanes): bit-identical with one
+	thread per member in the verification build"""
+	group = _lyap_sweep(n_lyap, 50)
+	monkeypatch.setenv("JITCDDE_B200_GROUP", "0")
+	solo = _lyap_sweep(n_lyap, 50)
+	for a, b in zip(group, solo):
+		assert np.array_equal(a, b)
+
+
 def test_production_build_is_deterministic():
 	"""Lane groups, shared-memory staging by cp.async, cluster sums through distributed shared memory: no result may depend on
 	the timing of warps or blocks — two runs of the production build agree bit for bit (C3 with cluster Gram–Schmidt, C5b with

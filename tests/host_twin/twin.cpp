@@ -421,6 +421,137 @@ int jdde_get_state(jdde_handle * h, int64_t member, int32_t max_anchors, int32_t
 	return JDDE_OK;
 }
 
+/*
+ * Per-step access to the engine's functions for member 0 — the counterpart of the methods of the reference's dde_integrator
+ * (jitced_template.c:1183-1208), which the product does not export (the boundary is one level higher). Used by
+ * tests/test_random_actions.py, the restatement of the reference's tests/compare_C_and_Python_core.py: random sequences
+ * of core calls on the reference's C core and on this engine must give identical results.
+ */
+static jdde::Member * step_member(jdde_handle * h)
+{
+	static thread_local jdde::Member M;
+	return &M;
+}
+
+static void step_resync(jdde::Member & M)
+{
+	/* anchors were modified in place: refresh the copies of the current and of the last anchor */
+	M.invalidate_windows();
+	double const * const c = M.slot(M.current);
+	double const * const l = M.slot(M.last);
+	M.cur_t = c[0];
+	M.new_t = l[0];
+	for (int i = 0; i < JD_N; i++)
+	{
+		M.cur_y[i] = c[1+i]; M.cur_d[i] = c[1+JD_N+i];
+		M.new_y[i] = l[1+i]; M.new_d[i] = l[1+JD_N+i];
+	}
+}
+
+int twin_step_begin(jdde_handle * h)
+{
+	if (int rc = ready(h)) return rc;
+	jdde::Member & M = *step_member(h);
+	jdde::load_member(h->P, 0, M);
+	step_resync(M);
+	h->aux[0] = 0.0;                                   /* have_old */
+	return JDDE_OK;
+}
+
+void twin_get_next_step(jdde_handle * h, double dt)
+{
+	jdde::Member & M = *step_member(h);
+	if (M.last != M.current)
+	{
+		/* the anchor replaced now is the reference's old_last (jitced_template.c:106-114) */
+		for (int i = 0; i < JD_N; i++) h->out2[i] = M.new_y[i];
+		h->aux[0] = 1.0;
+	}
+	jdde::ensure_room(M, h->P.max_delay);
+	jdde::get_next_step(M, dt);
+}
+
+double twin_get_t(jdde_handle * h) { return step_member(h)->cur_t; }
+double twin_past_within_step(jdde_handle * h) { return step_member(h)->pws; }
+double twin_get_p(jdde_handle * h, double atol, double rtol) { return jdde::get_p(*step_member(h), atol, rtol); }
+
+int twin_check_new_y_diff(jdde_handle * h, double atol, double rtol)
+{
+	if (h->aux[0] == 0.0) return 0;                    /* old_last == NULL, jitced_template.c:513 */
+	return jdde::check_new_y_diff(*step_member(h), h->out2.data(), atol, rtol) ? 1 : 0;
+}
+
+void twin_accept_step(jdde_handle * h)
+{
+	jdde::accept_step(*step_member(h));
+	h->aux[0] = 0.0;
+}
+
+void twin_forget(jdde_handle * h, double delay) { jdde::forget(*step_member(h), delay); }
+
+void twin_get_recent_state(jdde_handle * h, double t, double * out) { jdde::get_recent_state(*step_member(h), t, out, JD_N); }
+
+void twin_get_current_state(jdde_handle * h, double * out)
+{
+	jdde::Member & M = *step_member(h);
+	for (int i = 0; i < JD_N; i++) out[i] = M.slot(M.last)[1+i];
+}
+
+int twin_get_full_state(jdde_handle * h, int max_anchors, double * times, double * states, double * diffs)
+{
+	jdde::Member & M = *step_member(h);
+	int const count = M.last-M.first+1;
+	if (count > max_anchors) return count;
+	for (int k = 0; k < count; k++)
+	{
+		double const * const a = M.slot(M.first+k);
+		times[k] = a[0];
+		memcpy(states+(size_t)k*JD_N, a+1, JD_N*sizeof(double));
+		memcpy(diffs+(size_t)k*JD_N, a+1+JD_N, JD_N*sizeof(double));
+	}
+	return count;
+}
+
+void twin_truncate(jdde_handle * h, double time) { jdde::truncate_past(*step_member(h), time); }
+
+void twin_apply_jump(jdde_handle * h, const double * change, double time, double width, double * minima, double * maxima)
+{
+	jdde::apply_jump(*step_member(h), h->P, change, time, width, minima, maxima);
+}
+
+#if JD_NBASIC != JD_N
+void twin_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * norms)
+{
+	jdde::Member & M = *step_member(h);
+	jdde::orthonormalise(M, n_lyap, delay, norms);
+	step_resync(M);
+}
+
+double twin_remove_projections(jdde_handle * h, double delay, const double * vector)
+{
+	jdde::Member & M = *step_member(h);
+	double const norm = jdde::remove_projections(M, delay, 1, vector);
+	step_resync(M);
+	return norm;
+}
+
+void twin_remove_component(jdde_handle * h, int diff, int index)
+{
+	jdde::Member & M = *step_member(h);
+	for (int ca = M.first; ca <= M.last; ca++)
+		M.slot(ca)[1+(diff ? JD_N : 0)+JD_NBASIC+index] = 0.0;
+	step_resync(M);
+}
+#endif
+
+double twin_normalise_indices(jdde_handle * h, double delay, int n_indices, const int * indices)
+{
+	jdde::Member & M = *step_member(h);
+	double const norm = jdde::normalise_indices(M, delay, n_indices, indices);
+	step_resync(M);
+	return norm;
+}
+
 int jdde_grow_ring(jdde_handle * h, int32_t new_cap)
 {
 	if (new_cap <= h->P.cap || (new_cap & (new_cap-1))) return fail(h, JDDE_E_INVALID, "new capacity must be a larger power of two");

@@ -41,20 +41,21 @@ def system():
 	]
 
 
-def reference_core(program, past):
-	if not build_ref.have_ref(REF_NAME):
+def reference_core(program, past, name=REF_NAME, n_basic=N_BASIC, tangent_indices=TANGENT_INDICES):
+	if not build_ref.have_ref(name):
 		if not build_ref.reference_available():
 			pytest.skip("reference core not built and /root/reference not present")
-		build_ref.build_ref(program, REF_NAME, n_basic=N_BASIC, tangent_indices=TANGENT_INDICES)
-	return build_ref.load_ref(REF_NAME).dde_integrator([(float(a[0]), a[1].copy(), a[2].copy()) for a in past])
+		build_ref.build_ref(program, name, n_basic=n_basic, tangent_indices=tangent_indices)
+	return build_ref.load_ref(name).dde_integrator([(float(a[0]), a[1].copy(), a[2].copy()) for a in past])
 
 
 class EngineCore:
 	"""the engine's functions behind the method names of the reference's dde_integrator"""
 
-	def __init__(self, program, past):
+	def __init__(self, program, past, n=N, n_basic=N_BASIC, max_delay=DELAY):
 		dp = ctypes.POINTER(ctypes.c_double)
-		self.lib = twin_module.build_twin(program, n_basic=N_BASIC)
+		self.n = n
+		self.lib = twin_module.build_twin(program, n_basic=n_basic)
 		for name, restype, argtypes in (
 				("twin_step_begin", ctypes.c_int, [ctypes.c_void_p]),
 				("twin_get_next_step", None, [ctypes.c_void_p, ctypes.c_double]),
@@ -74,17 +75,18 @@ class EngineCore:
 				("twin_remove_component", None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
 				("twin_normalise_indices", ctypes.c_double, [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
 			):
-			function = getattr(self.lib, name)
-			function.restype, function.argtypes = restype, argtypes
+			if hasattr(self.lib, name):      # the Lyapunov entries exist only for n_basic < n
+				function = getattr(self.lib, name)
+				function.restype, function.argtypes = restype, argtypes
 		saved = _capi.load_library, _capi.Engine.load_image
 		_capi.load_library = lambda path=None: self.lib
 		_capi.Engine.load_image = lambda engine, path: None
 		try:
-			self.engine = _capi.Engine(N, N_BASIC, program.n_sites, 0, 1, ring_capacity=256)
+			self.engine = _capi.Engine(n, n_basic, program.n_sites, 0, 1, ring_capacity=256)
 		finally:
 			_capi.load_library, _capi.Engine.load_image = saved
 		self.engine.set_past(np.array([a[0] for a in past]), np.array([a[1] for a in past]), np.array([a[2] for a in past]))
-		self.engine.set_integration_parameters(DELAY, **oracle.DEFAULTS)
+		self.engine.set_integration_parameters(max_delay, **oracle.DEFAULTS)
 		self.h = self.engine._h
 		assert self.lib.twin_step_begin(self.h) == 0
 
@@ -104,23 +106,23 @@ class EngineCore:
 	def past_within_step(self): return self.lib.twin_past_within_step(self.h)
 
 	def get_recent_state(self, time):
-		out = np.empty(N)
+		out = np.empty(self.n)
 		self.lib.twin_get_recent_state(self.h, time, self._p(out))
 		return out
 
 	def get_current_state(self):
-		out = np.empty(N)
+		out = np.empty(self.n)
 		self.lib.twin_get_current_state(self.h, self._p(out))
 		return out
 
 	def get_full_state(self):
-		times, states, diffs = np.empty(256), np.empty((256, N)), np.empty((256, N))
+		times, states, diffs = np.empty(256), np.empty((256, self.n)), np.empty((256, self.n))
 		count = self.lib.twin_get_full_state(self.h, 256, self._p(times), self._p(states), self._p(diffs))
 		return [(times[k], states[k], diffs[k]) for k in range(count)]
 
 	def apply_jump(self, change, time, width):
 		change = np.ascontiguousarray(change, dtype=float)
-		minima, maxima = np.empty(N), np.empty(N)
+		minima, maxima = np.empty(self.n), np.empty(self.n)
 		self.lib.twin_apply_jump(self.h, self._p(change), time, width, self._p(minima), self._p(maxima))
 		return minima, maxima
 
@@ -245,3 +247,71 @@ def test_random_core_actions_match_the_reference_core():
 			raise AssertionError(f"realisation {realisation}, actions {log}: {error}") from error
 		seen.update(log)
 	assert len(seen) == 15      # every kind of action occurred
+
+
+def test_random_core_actions_with_past_within_step():
+	"""the reference's second protocol (tests/compare_C_and_Python_core_2.py): Mackey–Glass with an additional tiny delay, steps of
+	up to 1 — lookups reach into the step under way (past_within_step, extrapolation beyond the tentative anchor)"""
+	tau, tiny = 15, 1e-30
+	program = _codegen.generate([0.25*y(0, t-tau)/(1.0+y(0, t-tau)**10) - 0.1*y(0, t-tiny)])
+	rng = np.random.default_rng(seed=7)
+	pyrng = random.Random(11)
+	seen = set()
+	for realisation in range(150):
+		past = [(time, rng.random(1), rng.random(1)) for time in (0.0, 0.5, 2.0)]
+		R = reference_core(program, past, name="ref_random_actions_2", n_basic=None, tangent_indices=())
+		E = EngineCore(program, past, n=1, n_basic=1, max_delay=tau)
+		log = []
+
+		def both(name, *args):
+			return getattr(R, name)(*args), getattr(E, name)(*args)
+
+		def reduced_interval():
+			full = R.get_full_state()
+			return 0.9*full[0][0]+0.1*full[-1][0], 0.1*full[0][0]+0.9*full[-1][0]
+
+		def truncate_past():
+			both("accept_step")
+			both("truncate", rng.uniform(*reduced_interval()))
+
+		def apply_jump():
+			both("accept_step")
+			A, B = both("apply_jump", np.array([rng.normal(0, 0.1)]), rng.uniform(*reduced_interval()), 0.1)
+			same(A[0], B[0], "apply_jump minima")
+			same(A[1], B[1], "apply_jump maxima")
+
+		def get_full_state():
+			A, B = both("get_full_state")
+			assert len(A) == len(B)
+			for a, b in zip(A, B):
+				for k in range(3):
+					same(a[k], b[k], "get_full_state")
+
+		actions = dict(
+			get_next_step=lambda: both("get_next_step", rng.uniform(1e-5, 1)),
+			get_t=lambda: same(*both("get_t"), "get_t"),
+			get_recent_state=lambda: same(*both("get_recent_state", R.get_t()+rng.uniform(-0.1, 0.1)), "get_recent_state"),
+			get_current_state=lambda: same(*both("get_current_state"), "get_current_state"),
+			get_full_state=get_full_state,
+			get_p=lambda: same(*both("get_p", 10**rng.uniform(-10, -5), 10**rng.uniform(-10, -5)), "get_p"),
+			accept_step=lambda: both("accept_step"),
+			forget=lambda: both("forget", tau),
+			check_new_y_diff=lambda: same(*both("check_new_y_diff", 10**rng.uniform(-10, -5), 10**rng.uniform(-10, -5)), "check_new_y_diff"),
+			past_within_step=lambda: same(R.past_within_step, E.past_within_step, "past_within_step"),
+			truncate_past=truncate_past,
+			apply_jump=apply_jump,
+		)
+		try:
+			actions["get_next_step"]()
+			actions["get_next_step"]()
+			for _ in range(30):
+				name = pyrng.choice(sorted(actions))
+				log.append(name)
+				actions[name]()
+			get_full_state()
+			actions["past_within_step"]()
+		except AssertionError as error:
+			raise AssertionError(f"realisation {realisation}, actions {log}: {error}") from error
+		seen.update(log)
+		E.engine.close()
+	assert len(seen) == len(actions)

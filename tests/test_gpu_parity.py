@@ -322,6 +322,36 @@ def test_lyapunov_spectrum_of_two_roesslers(preparation):
 		assert abs(lyap-control) < 3.5*sem(lyaps[start:, i]), (i, lyap, control, sem(lyaps[start:, i]))
 
 
+def test_full_size_lyapunov_ensemble_c3():
+	"""BASELINE.json configs[2] at its full size — two Rösslers + 4 exponents, 10^5 coupling strengths — on the lane-group stepper
+	and the team Gram–Schmidt (verification build, three samples of 10 time units; ring of 512 anchors: 26 GB): all members
+	finish, the exponents are finite, and a random subsample agrees with the oracle bit for bit."""
+	from jitcdde_b200 import jitcdde_lyap
+	N = 100_000
+	past, k, _ = scenarios.c3_inputs(N)
+	offsets = np.array([10.0, 20.0, 30.0])
+	system = systems.two_roessler(control=True)
+	DDE = jitcdde_lyap(system["f"], n_lyap=4, control_pars=system["control_pars"], n_members=N, verbose=False, verification=True, ring_capacity=512)
+	DDE.add_past_points(past)
+	DDE.set_integration_parameters(**systems.LYAP_TEST_PARAMETERS)
+	DDE.set_parameters(k)
+	DDE.step_on_discontinuities()
+	t0 = DDE.t
+	states, lyaps, weights = zip(*[DDE.integrate(t0+o) for o in offsets])
+	accepted, rejected, _ = DDE.counters()
+	assert DDE._engine.ring_capacity == 512 and np.all(np.isfinite(lyaps)) and accepted.min() > 1000
+
+	pick = np.sort(np.random.default_rng(2).choice(N, 48, replace=False))
+	prog, n_basic = systems.lyap_program(system, 4)
+	lib = oracle.build(prog, n_basic=n_basic)
+	arrays = (np.array([a[0] for a in past]), np.array([a[1] for a in past]), np.array([a[2] for a in past]))
+	ref = oracle.run_ensemble(lib, arrays, k[pick], 4.5, 1, np.array([4.5]), offsets, lyap=True, **systems.LYAP_TEST_PARAMETERS)
+	assert np.array_equal(np.array(states)[:, pick], ref["out"])
+	assert np.array_equal(np.array(weights)[:, pick], ref["weights"])
+	assert np.array_equal(accepted[pick], ref["counters"][:, 0]) and np.array_equal(rejected[pick], ref["counters"][:, 1])
+	np.testing.assert_allclose(np.array(lyaps)[:, pick], ref["lyaps"], rtol=1e-13, atol=1e-15)
+
+
 def test_production_build_is_deterministic():
 	"""Lane groups, shared-memory staging by cp.async, cluster sums through distributed shared memory: no result may depend on
 	the timing of warps or blocks — two runs of the production build agree bit for bit (C3 with cluster Gram–Schmidt, C5b with

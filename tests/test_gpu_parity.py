@@ -352,6 +352,34 @@ def test_full_size_lyapunov_ensemble_c3():
 	np.testing.assert_allclose(np.array(lyaps)[:, pick], ref["lyaps"], rtol=1e-13, atol=1e-15)
 
 
+def test_full_size_state_dependent_and_neutral_ensembles_c5():
+	"""BASELINE.json configs[4] at full size (2^20 members each): state-dependent delay — verification build, random subsample bit for
+	bit against the oracle — and the neutral DDE on the pointer window — production build, the reference's own tolerance."""
+	N = 1 << 20
+	rng = np.random.default_rng(3)
+	ours = scenarios.product_c5a(N, verification=True)
+	pick = np.sort(rng.choice(N, 256, replace=False))
+	times, states, diffs, sample_times = scenarios.c5a_inputs(N)
+	lib = oracle.build(systems.program(systems.state_dependent()))
+	ref = oracle.run_ensemble(lib, (times[pick], states[pick], diffs[pick]), None, 1e10, 3, np.array([0.01, 0.0]), sample_times-0.01, per_member_past=True, n_members=len(pick))
+	assert np.array_equal(ours["out"][:, pick], ref["out"])
+	assert np.array_equal(ours["accepted"][pick], ref["counters"][:, 0]) and np.array_equal(ours["rejected"][pick], ref["counters"][:, 1])
+	assert np.all(np.isfinite(ours["out"]))
+	del ours
+
+	ours = scenarios.product_c5b(N)
+	pick = np.sort(rng.choice(N, 128, replace=False))
+	initial, sample_times = scenarios.c5b_inputs(N)
+	system = systems.neutral()
+	lib = oracle.build(systems.program(system))
+	times = np.broadcast_to(np.array([-1.0, 0.0]), (len(pick), 2)).copy()
+	states = np.stack([initial[pick], initial[pick]], axis=1)
+	ref = oracle.run_ensemble(lib, (times, states, np.zeros_like(states)), None, system["delay"], 2, None, sample_times-0.0, per_member_past=True, n_members=len(pick), rtol=1e-5)
+	np.testing.assert_allclose(ours["out"][:, pick], ref["out"], rtol=1e-4, atol=1e-4)
+	assert np.all(np.isfinite(ours["out"]))
+	assert np.all(np.abs(ours["accepted"][pick]-ref["counters"][:, 0]) <= 0.05*ref["counters"][:, 0]+2)
+
+
 def test_production_build_is_deterministic():
 	"""Lane groups, shared-memory staging by cp.async, cluster sums through distributed shared memory: no result may depend on
 	the timing of warps or blocks — two runs of the production build agree bit for bit (C3 with cluster Gram–Schmidt, C5b with

@@ -32,8 +32,9 @@ def test_network_engine_matches_symbolic_path_on_gpu():
 	assert (nc[0], nc[1]) == sc
 
 
-def test_large_network_properties():
-	g = large_graph(100_000)
+@pytest.mark.parametrize("n", [100_000, 1_000_000])      # 10^6 nodes, 10^7 edges: BASELINE.json configs[3]
+def test_large_network_properties(n):
+	g = large_graph(n)
 	blind_to = float(np.max(g["edge_tau"]))
 	times = blind_to + np.array([1.0, 2.0])
 	runs = [run_network(g, times, blind_to) for _ in range(2)]

@@ -26,11 +26,16 @@
  *   - the history is a power-of-two ring per member in HBM (jdde_abi.h), addressed by logical
  *     indices; the bracket search keeps one cursor per lookup site and reproduces the reference's
  *     walk including its tie-breaks;
- *   - JD_WINDOW (small systems): per lookup site the anchor pair the cursor points at AND the
- *     next anchor are kept in registers across stages, attempts and steps. A lookup that stays
- *     in its segment touches no memory; one that moves on takes the prefetched anchor and issues
- *     the load of the following one, whose latency is hidden behind the rest of the step. Only
- *     accepted anchors (index <= current) are cached: they are immutable while the kernel runs;
+ *   - JD_WINDOW: staging of the anchors a step can reach. Per lookup site the anchors cursor−1 …
+ *     cursor+2 are kept close to the thread and refilled one cursor move ahead of their use, so a
+ *     lookup that stays in its segment or moves by one anchor never waits for L2 or HBM:
+ *       2  in shared memory, filled by cp.async, handed out by value (anchors of up to 8 doubles);
+ *       3  in shared memory, contiguous per thread, handed out as pointers (larger anchors);
+ *       1  in registers (kept for comparison; measured slower);
+ *       0  none: speculative vector loads (small anchors) or the plain walk with an L1 prefetch of
+ *          the next anchor. Lyapunov systems use a group of lanes per member with its own staging
+ *          (jdde_group.cuh). Only accepted anchors (index <= current) are staged: they are
+ *          immutable while the kernel runs;
  *   - arithmetic keeps the reference's association order; with -fmad=false the results are
  *     bit-identical to the CPU oracle (tests/), with FMA contraction they agree to rounding.
  *

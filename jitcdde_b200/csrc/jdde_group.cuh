@@ -27,7 +27,7 @@
  * Arithmetic: per component exactly that of the one-thread-per-member engine (same generated statements,
  * same order), so the verification build is bit-identical to the reference core, too.
  *
- * The generated file (jitcdde_b200/_codegen.py, generate_lyap) has the shape
+ * The generated file (jitcdde_b200/_codegen.py, _generate_blocks) has the shape
  *     <lookups: JDDE_SEG s_k = JDDE_ANCHORS(k, …);>          — executed by every lane
  *     #ifdef JDDE_GROUP   if (JDDE_GROUP_IS_BASIC) { basic statements } else { tangent statements }
  *     #else               { basic } { tangent, JDDE_TOFF = n_basic } { tangent, JDDE_TOFF = 2·n_basic } …

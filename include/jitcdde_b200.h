@@ -296,6 +296,12 @@ int jdde_net_connect_peers(jdde_net * h, int32_t rank, int32_t world, const void
 int jdde_net_integrate(jdde_net * h, double target, double * out_state, int32_t * status);
 int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double * out_state, int32_t * status);
 int jdde_net_recent_state(jdde_net * h, double t, int32_t current_only, double * out_state);
+/* The reference's history is an unbounded list (jitced_template.c:56-73); when the ring is full, a call ends with status
+ * JDDE_STATUS_OVERFLOW. jdde_net_grow_ring moves the live anchors into a larger ring (a power of two) and jdde_net_resume
+ * continues the call exactly where it stopped (with several GPUs: on every rank; jdde_net_begin(h, 2, …) is the
+ * per-attempt form). */
+int jdde_net_grow_ring(jdde_net * h, int32_t new_capacity);
+int jdde_net_resume(jdde_net * h, double * out_state, int32_t * status);
 int jdde_net_get_counters(jdde_net * h, int64_t * accepted, int64_t * rejected, int64_t * attempts);
 int jdde_net_get_dt(jdde_net * h, double * dt);
 int64_t jdde_net_launch_count(const jdde_net * h);

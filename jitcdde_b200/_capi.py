@@ -115,6 +115,8 @@ SIGNATURES.update({
 	"jdde_net_integrate": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_int32_p]),
 	"jdde_net_integrate_blindly": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_double, c_double_p, c_int32_p]),
 	"jdde_net_recent_state": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int32, c_double_p]),
+	"jdde_net_grow_ring": (ctypes.c_int, [_H, ctypes.c_int32]),
+	"jdde_net_resume": (ctypes.c_int, [_H, c_double_p, c_int32_p]),
 	"jdde_net_get_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
 	"jdde_net_get_dt": (ctypes.c_int, [_H, c_double_p]),
 	"jdde_net_launch_count": (ctypes.c_int64, [_H]),
@@ -455,6 +457,7 @@ class NetEngine:
 	def __init__(self, n, lo, hi, n_edges, n_node_params, ring_capacity=128, device=0):
 		self.lib = load_library()
 		self.n, self.lo, self.hi = int(n), int(lo), int(hi)
+		self.ring_capacity = int(ring_capacity)
 		desc = NetDesc(n=n, lo=lo, hi=hi, n_edges=n_edges, n_node_params=n_node_params, ring_capacity=ring_capacity, device=device)
 		self._h = _H()
 		rc = self.lib.jdde_net_create(ctypes.byref(desc), ctypes.byref(self._h))
@@ -532,6 +535,17 @@ class NetEngine:
 		out = np.empty(self.n)
 		status = ctypes.c_int32()
 		self._check(self.lib.jdde_net_integrate_blindly(self._h, float(target), float(step or 0.0), _dp(out), ctypes.byref(status)))
+		return out, status.value
+
+	def grow_ring(self, new_capacity):
+		self._check(self.lib.jdde_net_grow_ring(self._h, int(new_capacity)))
+		self.ring_capacity = int(new_capacity)
+
+	def resume(self):
+		"""continue the call that stopped with STATUS_OVERFLOW (after grow_ring); returns (state, status) like that call"""
+		out = np.empty(self.n)
+		status = ctypes.c_int32()
+		self._check(self.lib.jdde_net_resume(self._h, _dp(out), ctypes.byref(status)))
 		return out, status.value
 
 	def exchange_handle(self):

@@ -22,7 +22,7 @@ import numpy as np
 from . import _build, _capi, _codegen
 from ._jitcdde import UnsuccessfulIntegration, _default_min_step
 
-MODE_ADAPTIVE, MODE_BLIND = 0, 1
+MODE_ADAPTIVE, MODE_BLIND, MODE_CONTINUE = 0, 1, 2
 
 
 class _DeviceArray:
@@ -64,6 +64,7 @@ class jitcdde_network:
 		self._program = _codegen.generate_network(local, coupling, len(self._node_parameters))
 		self._image = _build.build_net_image(self._program)
 		self.ring_capacity = ring_capacity
+		self.max_ring_capacity = 1 << 16
 
 		self.rank, self.world = 0, 1
 		try:
@@ -178,13 +179,22 @@ class jitcdde_network:
 			if done:
 				return status
 
+	def _grow(self, status):
+		"""The reference's history is unbounded: a full ring is doubled (every rank takes the same decision) and the call goes on."""
+		if status != _capi.STATUS_OVERFLOW or self._engine.ring_capacity >= self.max_ring_capacity:
+			return False
+		if self.verbose:
+			print(f"Anchor ring full; growing to {2*self._engine.ring_capacity} anchors.")
+		self._engine.grow_ring(2*self._engine.ring_capacity)
+		return True
+
 	def _raise(self, status):
 		if status == _capi.STATUS_OK:
 			return
 		if status == _capi.STATUS_MIN_STEP:
 			raise UnsuccessfulIntegration("Could not integrate with the given tolerance parameters (step size below min_step).")
 		if status == _capi.STATUS_OVERFLOW:
-			raise MemoryError("Anchor ring full; pass a larger ring_capacity to jitcdde_network.")
+			raise MemoryError("Anchor ring full and it could not be enlarged; pass a larger ring_capacity to jitcdde_network.")
 		raise UnsuccessfulIntegration("A delay became shorter than the step, the step size collapsed or the state is not finite.")
 
 	# ------------------------------------------------------------------ integration
@@ -204,10 +214,16 @@ class jitcdde_network:
 		if self.world == 1 or self._exchange == "peer":
 			# (peer exchange: every rank runs the same loop in the runtime library; the GPUs meet on the device)
 			out, status = self._engine.integrate(target_time)
+			while self._grow(status):
+				out, status = self._engine.resume()
 			self._raise(status)
 			return out
 		self._engine.begin(MODE_ADAPTIVE, target_time)
-		self._raise(self._run())
+		status = self._run()
+		while self._grow(status):
+			self._engine.begin(MODE_CONTINUE, 0.0)
+			status = self._run()
+		self._raise(status)
 		return self._engine.recent_state(target_time)
 
 	def integrate_blindly(self, target_time, step=None):
@@ -217,6 +233,8 @@ class jitcdde_network:
 		assert step > 0, "step must be positive"
 		if self.world == 1 or self._exchange == "peer":
 			out, status = self._engine.integrate_blindly(target_time, step)
+			while self._grow(status):
+				out, status = self._engine.resume()
 			self._raise(status)
 			return out
 		total = target_time-self._engine.poll()[1]
@@ -228,7 +246,11 @@ class jitcdde_network:
 				step = total
 			number = round(total/step)
 			self._engine.begin(MODE_BLIND, target_time, total/number, number)
-			self._raise(self._run())
+			status = self._run()
+			while self._grow(status):
+				self._engine.begin(MODE_CONTINUE, 0.0)
+				status = self._run()
+			self._raise(status)
 		return self._engine.recent_state(target_time, current_only=True)
 
 	def counters(self):

@@ -261,6 +261,35 @@ JDN_FN void control(jdn_problem const & P)
 	C.p_bits = 0;
 }
 
+/* The reference's anchor list is unbounded; the ring is not. A call that stopped with JDDE_STATUS_OVERFLOW goes on after the
+ * ring has grown (regrow_node for every node, then this): the controller continues exactly where control() left off. */
+JDN_FN void continue_call(jdn_control & C)
+{
+	if (C.status == JDDE_STATUS_OVERFLOW)
+		C.status = JDDE_STATUS_OK;
+	C.commit_slot = -1;
+	if (C.status != JDDE_STATUS_OK)
+	{
+		C.done = 1;
+		return;
+	}
+	C.pws = 0;
+	C.p_bits = 0;
+	C.done = 0;
+	if (C.mode == JDN_MODE_ADAPTIVE)
+		C.h = C.dt;
+}
+
+/* copy the live anchors of node i into a ring of another capacity */
+JDN_FN void regrow_node(jdn_problem const & P, double * const new_hist, int const new_cap, long long const i)
+{
+	jdn_control const & C = *P.ctrl;
+	pair const * const from = reinterpret_cast<pair const *>(P.hist);
+	pair * const to = reinterpret_cast<pair *>(new_hist);
+	for (int k = C.first; k <= C.current; k++)
+		to[jdn_pair_index(k & (new_cap-1), i, P.n)] = from[jdn_pair_index(k & (P.cap-1), i, P.n)];
+}
+
 /* get_recent_state, jitced_template.c:287-320: Hermite interpolation on the last segment */
 JDN_FN double recent_state(jdn_problem const & P, double const t, long long const i)
 {

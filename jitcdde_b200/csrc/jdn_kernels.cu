@@ -172,6 +172,11 @@ extern "C" __global__ void jdn_k_begin(jdn_problem const P, int const mode, doub
 	if (blockIdx.x || threadIdx.x)
 		return;
 	jdn_control & C = *P.ctrl;
+	if (mode == JDN_MODE_CONTINUE)
+	{
+		jdn::continue_call(C);
+		return;
+	}
 	if (C.status != JDDE_STATUS_OK)
 	{
 		C.done = 1;
@@ -196,6 +201,18 @@ extern "C" __global__ void jdn_k_begin(jdn_problem const P, int const mode, doub
 			jdn::forget(P, C);
 	}
 	C.last_start = C.t;
+}
+
+/* jdde_net_grow_ring: live anchors into the new ring (node-parallel), anchor times by thread 0 */
+extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
+jdn_k_regrow(jdn_problem const P, double * const new_times, double * const new_hist, int const new_cap)
+{
+	long long const i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i < P.n)
+		jdn::regrow_node(P, new_hist, new_cap, i);
+	if (i == 0)
+		for (int k = P.ctrl->first; k <= P.ctrl->current; k++)
+			new_times[k & (new_cap-1)] = P.times[k & (P.cap-1)];
 }
 
 extern "C" __global__ void __launch_bounds__(JDN_BLOCK)

@@ -20,7 +20,7 @@ struct jdde_net
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	cudaLibrary_t lib = nullptr;
-	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr;
+	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr, k_regrow = nullptr;
 	/* peer exchange: this rank's buffer (mapped by the peers through CUDA IPC), the peers' buffers mapped here */
 	jdn_exchange * exchange = nullptr;
 	std::vector<void *> mapped_peers;
@@ -180,6 +180,8 @@ int jdde_net_load_image(jdde_net * h, const void * image, size_t len)
 	for (auto const & entry : table)
 		if (cudaLibraryGetKernel(entry.slot, h->lib, entry.name) != cudaSuccess)
 			return nfail(h, JDDE_E_IMAGE, std::string("image lacks kernel ") + entry.name);
+	if (cudaLibraryGetKernel(&h->k_regrow, h->lib, "jdn_k_regrow") != cudaSuccess)
+		return nfail(h, JDDE_E_IMAGE, "image lacks kernel jdn_k_regrow");
 	if (cudaLibraryGetKernel(&h->k_exchange, h->lib, "jdn_k_exchange") != cudaSuccess)
 	{
 		h->k_exchange = nullptr;
@@ -426,6 +428,51 @@ int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double 
 	if ((rc = jdde_net_poll(h, nullptr, nullptr, nullptr))) return rc;
 	if (status) *status = h->host_ctrl.status;
 	return jdde_net_recent_state(h, target, 1, out_state);
+}
+
+/* the reference's history is an unbounded list: when the ring is full (status JDDE_STATUS_OVERFLOW) it is enlarged … */
+int jdde_net_grow_ring(jdde_net * h, int32_t new_capacity)
+{
+	int rc = nready_run(h);
+	if (rc) return rc;
+	if (new_capacity <= h->P.cap || (new_capacity & (new_capacity-1)))
+		return nfail(h, JDDE_E_INVALID, "new capacity must be a larger power of two");
+	if ((size_t)new_capacity*sizeof(double) > 48*1024)
+		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double))));
+	double * new_times = nullptr, * new_hist = nullptr;
+	if ((rc = nalloc(h, &new_times, (size_t)new_capacity))) return rc;
+	if ((rc = nalloc(h, &new_hist, 2*(size_t)new_capacity*(size_t)h->desc.n))) return rc;
+	int cap = new_capacity;
+	void * args[] = { &h->P, &new_times, &new_hist, &cap };
+	if ((rc = nlaunch(h, h->k_regrow, h->desc.n, h->block, 0, args))) return rc;
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	for (double * old : { h->P.times, h->P.hist })
+	{
+		cudaFree(old);
+		for (auto it = h->allocations.begin(); it != h->allocations.end(); ++it)
+			if (*it == old) { h->allocations.erase(it); break; }
+	}
+	h->P.times = new_times;
+	h->P.hist = new_hist;
+	h->P.cap = new_capacity;
+	h->desc.ring_capacity = new_capacity;
+	JN_CUDA(h, cudaMemcpy(&h->P.ctrl->cap, &cap, sizeof cap, cudaMemcpyHostToDevice));
+	drop_batch(h);
+	return JDDE_OK;
+}
+
+/* … and the call goes on where it stopped (same target, same remaining steps) */
+int jdde_net_resume(jdde_net * h, double * out_state, int32_t * status)
+{
+	int rc = jdde_net_begin(h, JDN_MODE_CONTINUE, 0.0, 0.0, 0);
+	if (rc) return rc;
+	if ((rc = run_until_done(h))) return rc;
+	if (status) *status = h->host_ctrl.status;
+	if (h->host_ctrl.mode == JDN_MODE_BLIND)
+		return jdde_net_recent_state(h, h->host_ctrl.target, 1, out_state);
+	if (h->host_ctrl.status == JDDE_STATUS_OK)
+		return jdde_net_recent_state(h, h->host_ctrl.target, 0, out_state);
+	return JDDE_OK;
 }
 
 int jdde_net_get_counters(jdde_net * h, int64_t * accepted, int64_t * rejected, int64_t * attempts)

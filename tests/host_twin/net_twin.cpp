@@ -110,6 +110,7 @@ int jdde_net_begin(jdde_net * h, int32_t mode, double target, double step, int64
 {
 	if (int rc = ready(h)) return rc;
 	jdn_control & C = h->ctrl;
+	if (mode == JDN_MODE_CONTINUE) { jdn::continue_call(C); h->launches++; return JDDE_OK; }
 	if (C.status != JDDE_STATUS_OK) { C.done = 1; return JDDE_OK; }
 	C.mode = mode; C.target = target; C.commit_slot = -1; C.pws = 0; C.p_bits = 0;
 	if (mode == JDN_MODE_BLIND) { C.h = step; C.remaining = steps; C.done = steps <= 0; }
@@ -220,6 +221,31 @@ int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double 
 	if (int rc = run(h)) return rc;
 	if (status) *status = h->ctrl.status;
 	return jdde_net_recent_state(h, target, 1, out);
+}
+
+int jdde_net_grow_ring(jdde_net * h, int32_t new_cap)
+{
+	if (new_cap <= h->P.cap || (new_cap & (new_cap-1))) return fail(h, JDDE_E_INVALID, "new capacity must be a larger power of two");
+	size_t const n = (size_t)h->desc.n;
+	std::vector<double> new_times((size_t)new_cap, 0.0), new_hist(2*(size_t)new_cap*n, 0.0);
+	for (size_t i = 0; i < n; i++)
+		jdn::regrow_node(h->P, new_hist.data(), new_cap, (long long)i);
+	for (int k = h->ctrl.first; k <= h->ctrl.current; k++)
+		new_times[(size_t)(k & (new_cap-1))] = h->times[(size_t)(k & (h->P.cap-1))];
+	h->times.swap(new_times); h->hist.swap(new_hist);
+	h->P.times = h->times.data(); h->P.hist = h->hist.data();
+	h->P.cap = new_cap; h->ctrl.cap = new_cap; h->desc.ring_capacity = new_cap;
+	return JDDE_OK;
+}
+
+int jdde_net_resume(jdde_net * h, double * out, int32_t * status)
+{
+	if (int rc = jdde_net_begin(h, JDN_MODE_CONTINUE, 0.0, 0.0, 0)) return rc;
+	if (int rc = run(h)) return rc;
+	if (status) *status = h->ctrl.status;
+	if (h->ctrl.mode == JDN_MODE_BLIND) return jdde_net_recent_state(h, h->ctrl.target, 1, out);
+	if (h->ctrl.status == JDDE_STATUS_OK) return jdde_net_recent_state(h, h->ctrl.target, 0, out);
+	return JDDE_OK;
 }
 
 int jdde_net_get_counters(jdde_net * h, int64_t * a, int64_t * r, int64_t * k)

@@ -112,3 +112,14 @@ def test_fused_peer_exchange_equals_one_gpu():
 		assert np.array_equal(peer_blind, blind), rank
 		assert np.array_equal(peer_out, out), rank
 		assert tuple(peer_counters) == tuple(counters), rank
+
+
+def test_ring_growth_on_gpu():
+	"""a ring of 16 anchors for a delay window of 63 steps: filled, doubled (twice over 48 KB of shared memory for the anchor times
+	is not reached here), continued — identical to a ring that is large enough; the CUDA graph of the attempt batch is rebuilt"""
+	g = large_graph(20_000)
+	blind_to = float(np.max(g["edge_tau"]))
+	times = blind_to + np.array([1.0, 2.0])
+	small = run_network(g, times, blind_to, ring_capacity=16)
+	large = run_network(g, times, blind_to, ring_capacity=512)
+	assert np.array_equal(small[0], large[0]) and np.array_equal(small[1], large[1]) and small[2] == large[2]

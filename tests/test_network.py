@@ -134,3 +134,15 @@ def test_node_partition_exchange_protocol(twin):
 		assert np.array_equal(samples[-1], engines[1][0].recent_state(T))
 	assert np.array_equal(np.array(samples), reference)
 	assert engines[0][0].counters() == counters
+
+
+def test_ring_growth_gives_the_same_trajectory(twin):
+	"""The reference keeps every anchor in an unbounded list; a ring that is too small for the delay window fills up, is doubled
+	and the call goes on where it stopped (blind and adaptive): same states and step counts as with a ring that is large enough."""
+	g = kuramoto_graph(12)
+	blind_to = float(np.max(g["edge_tau"]))
+	times = blind_to + np.arange(0.5, 3.5, 0.5)
+	small = run_network(g, times, blind_to, ring_capacity=8)
+	large = run_network(g, times, blind_to, ring_capacity=512)
+	assert np.array_equal(small[0], large[0]) and np.array_equal(small[1], large[1])
+	assert small[2] == large[2] and small[3] == large[3]

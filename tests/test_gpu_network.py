@@ -46,7 +46,7 @@ def test_large_network_properties(n):
 	assert np.all(np.abs(drift-1.0) < 2.2)
 
 
-def _peer_worker(rank, world, port, queue, n):
+def _peer_worker(rank, world, port, queue, n, ring_capacity):
 	"""one rank of a two-process run; with a single visible GPU both ranks share it (CUDA IPC works within a device, too)"""
 	import os
 	import warnings
@@ -60,7 +60,7 @@ def _peer_worker(rank, world, port, queue, n):
 	dist.init_process_group("gloo", rank=rank, world_size=world)      # rendezvous only: carries the IPC handles
 	g = large_graph(n)
 	net = jitcdde_network(n, local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y), edges=(g["src"], g["dst"], g["edge_tau"]),
-		weight=g["weight"], node_parameters=[g["omega"]], verbose=False, device=device, ring_capacity=512, exchange="peer")
+		weight=g["weight"], node_parameters=[g["omega"]], verbose=False, device=device, ring_capacity=ring_capacity, exchange="peer")
 	net.set_integration_parameters(rtol=0, atol=1e-5)
 	net.constant_past(g["initial"], time=0.0)
 	blind = net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1)
@@ -70,7 +70,8 @@ def _peer_worker(rank, world, port, queue, n):
 	dist.destroy_process_group()
 
 
-def test_fused_peer_exchange_equals_one_gpu():
+@pytest.mark.parametrize("ring_capacity", [512, 16])      # 16: the ring fills up and is doubled on both ranks while they integrate
+def test_fused_peer_exchange_equals_one_gpu(ring_capacity):
 	"""Two ranks that own half of the nodes each and exchange the tentative anchor through peer memory from inside the step
 	kernel (device-side arrival barrier, csrc/jdn_kernels.cu: jdn_k_exchange) take the same steps and reach bit-identical
 	states as one rank that owns all nodes."""
@@ -101,7 +102,7 @@ def test_fused_peer_exchange_equals_one_gpu():
 	sock.close()
 	ctx = mp.get_context("spawn")
 	queue = ctx.Queue()
-	procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, queue, n)) for r in range(2)]
+	procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, queue, n, ring_capacity)) for r in range(2)]
 	for p in procs:
 		p.start()
 	results = [queue.get(timeout=600) for _ in procs]

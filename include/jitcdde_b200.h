@@ -137,6 +137,17 @@ int jdde_integrate_async(jdde_handle * h, const double * target, int32_t per_mem
  * arrived, without waiting for younger work. */
 int jdde_wait_result(jdde_handle * h, int32_t age);
 
+/* A series of jitcdde.integrate calls in ONE launch — the user's sampling loop `for T in times: DDE.integrate(T)`
+ * (/root/reference/examples/mackey_glass.py:76-78; per call _jitcdde.py:807-836): every member integrates to
+ * targets[0], interpolates its state there, forgets, goes on to targets[1], … exactly as n_samples separate calls of
+ * jdde_integrate would make it do (same steps, same states, bit for bit), but without waiting for the other members
+ * in between and with its controller state loaded and stored once. targets: [n_samples] or, with per_member,
+ * [n_members][n_samples] (ascending); out_states: [n_samples][n_members][n]; status: [n_members]. Not available for
+ * kernel images that integrate with a group of lanes per member (Lyapunov systems): JDDE_E_INVALID. */
+int jdde_integrate_samples(jdde_handle * h, const double * targets, int32_t n_samples, int32_t per_member, double * out_states, int32_t * status);
+/* ... queued like jdde_integrate_async (out_states page-locked; jdde_wait_result / jdde_synchronize as there). */
+int jdde_integrate_samples_async(jdde_handle * h, const double * targets, int32_t n_samples, int32_t per_member, double * out_states);
+
 /* step_on_discontinuities (_jitcdde.py:985-997): for each of the n_steps sorted step lengths,
  * adaptive steps capped so that one lands on t + step; steps [n_steps] or [n_members][n_steps]
  * (the host side computes them with _propagate_delays, :75-86). */

@@ -96,6 +96,9 @@ def use_window(program):
 	     1.29e10 → 1.77e10 steps/s for the Mackey–Glass ensemble, profiles/variants_r01.md).
 	  3  the same for anchors of more than 8 doubles: contiguous anchors in a per-thread area of shared memory,
 	     lookups hand out pointers into it (n = 6 with one distinct delay: 520 bytes per thread).
+	  4  an 8-anchor window (cursor−3 … cursor+4, 24 bytes per anchor for n = 1) with one cp.async group per anchor and
+	     wait_group: no lookup waits for a copy any more, but more instructions per move; measured equal to mode 2
+	     within 2 % (profiles/variants_r02.md), kept as a variant (JITCDDE_B200_WINDOW=4).
 	Mode 2 needs 4 anchors × lookup sites × 8·A bytes of shared memory per thread; it is chosen when that is
 	at most 128 bytes (n = 1 with one distinct delay), so that 32 warps per SM stay resident. Mode 3 is chosen up to
 	600 bytes per thread (64-thread blocks, 6 per SM), unless the system is a Lyapunov extension that the lane-group
@@ -107,7 +110,7 @@ def use_window(program):
 		mode = int(override) if program.n_sites > 0 else 0
 		if mode == 3 and A <= 8:
 			mode = 2
-		if mode == 2 and A > 8:
+		if mode in (2, 4) and A > 8:
 			mode = 3 if program.n_sites*4*A*8+8 <= 600 else 0
 		return mode
 	if program.n_sites > 0 and program.n_sites*4*A*8 <= 128:
@@ -122,9 +125,9 @@ def launch_shape(program):
 	(block size, resident blocks per SM) the kernels are compiled for. The integrate kernel is bound by
 	latency (dependent FP64 chains and scattered anchor loads), not by issue slots or bandwidth, so resident
 	warps matter more than spill-free code: small systems are compiled for one-warp blocks (a finished warp
-	frees its slot at once) — 32 per SM (64 registers per thread) with the shared-memory window, 20 per SM
-	(<= 96 registers) without — the measured optima on B200 (profiles/variants_r01.md). Larger systems keep
-	all registers.
+	frees its slot at once) — 28 per SM (72 registers per thread) with the shared-memory window, 20 per SM
+	(<= 96 registers) without — the measured optima on B200 (profiles/variants_r01.md, variants_r02.md). Larger
+	systems keep all registers.
 	"""
 	override = os.environ.get("JITCDDE_B200_LAUNCH")
 	if override:
@@ -133,7 +136,7 @@ def launch_shape(program):
 	if use_window(program) == 3:
 		return 64, 6
 	if program.n <= 2:
-		return (32, 32) if use_window(program) == 2 else (32, 20)
+		return (32, 28) if use_window(program) in (2, 4) else (32, 20)
 	if program.n <= 8:
 		return 128, 4
 	return 128, 1
@@ -227,21 +230,28 @@ def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), fo
 	return path
 
 
-def build_net_image(program, block=256, force=False, verbose=False):
-	"""Kernel image of the network engine for one (local, coupling) pair (`program` = _codegen.NetProgram)."""
+def build_net_image(program, block=256, mode=FAST, force=False, verbose=False):
+	"""Kernel image of the network engine for one (local, coupling) pair (`program` = _codegen.NetProgram); `mode` as
+	for build_image: VERIFY compiles without FMA contraction and with the bit-reproducible elementary functions."""
 	os.makedirs(CACHE, exist_ok=True)
 	h = hashlib.sha256()
 	for name in ("jdn_engine.cuh", "jdn_kernels.cu", "jdn_abi.h", "jdde_abi.h", "jdde_math.h"):
 		with open(os.path.join(CSRC, name), "rb") as f:
 			h.update(f.read())
-	tag = hashlib.sha256(repr((program.key, block, h.hexdigest())).encode()).hexdigest()[:20]
+	tag = hashlib.sha256(repr((program.key, block, mode, h.hexdigest())).encode()).hexdigest()[:20]
 	path = os.path.join(CACHE, f"jdn_{tag}.cubin")
 	if os.path.exists(path) and not force:
 		return path
 	rhs = os.path.join(CACHE, f"net_{program.key}.inc")
 	with open(rhs, "w") as f:
 		f.write(program.body)
-	cmd = [nvcc(), "-cubin", "-O3", "-std=c++17", "-lineinfo", *ARCH, f'-DJDN_RHS_FILE="{rhs}"', f"-DJDN_BLOCK={block}",
+	if mode == VERIFY:
+		mode_flags = ["-fmad=false"]
+	elif mode == FAST:
+		mode_flags = ["-DJD_FAST=1"]
+	else:
+		raise ValueError(mode)
+	cmd = [nvcc(), "-cubin", "-O3", "-std=c++17", "-lineinfo", *ARCH, *mode_flags, f'-DJDN_RHS_FILE="{rhs}"', f"-DJDN_BLOCK={block}",
 		os.path.join(CSRC, "jdn_kernels.cu"), "-o", path + ".tmp"]
 	if verbose:
 		print(" ".join(cmd))

@@ -57,6 +57,8 @@ SIGNATURES = {
 	"jdde_integrate": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, c_int32_p]),
 	"jdde_integrate_async": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p]),
 	"jdde_wait_result": (ctypes.c_int, [_H, ctypes.c_int32]),
+	"jdde_integrate_samples": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_int32_p]),
+	"jdde_integrate_samples_async": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p]),
 	"jdde_step_on_discontinuities": (ctypes.c_int, [_H, ctypes.c_int32, c_double_p, ctypes.c_int32, c_double_p, c_int32_p]),
 	"jdde_resume": (ctypes.c_int, [_H, c_double_p, c_double_p, c_double_p, c_int32_p]),
 	"jdde_integrate_blindly": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_double, c_double_p, c_int32_p]),
@@ -268,8 +270,8 @@ class Engine:
 		"""fetch=False: leave everything on the device, do not synchronise. fetch_status=False: copy the
 		states back but not the per-member status (use count_failed / get_status afterwards)."""
 		target, pm = self._targets(target)
-		if fetch and out is None:
-			out = np.empty((self.N, self.n))
+		if fetch:
+			out = np.empty((self.N, self.n)) if out is None else self._checked_out(out, (self.N, self.n))
 		if fetch and fetch_status and status is None:
 			status = self._pinned_status()
 		if not (fetch and fetch_status):
@@ -281,13 +283,48 @@ class Engine:
 	def integrate_async(self, target, out):
 		"""queue an integrate() whose result lands in `out` (page-locked, (N, n) float64) by the next synchronize()"""
 		target, pm = self._targets(target)
-		if out.shape != (self.N, self.n) or out.dtype != np.float64 or not out.flags.c_contiguous:
-			raise ValueError("out must be a C-contiguous float64 array of shape (n_members, n)")
+		self._checked_out(out, (self.N, self.n))
 		self._check(self.lib.jdde_integrate_async(self._h, _dp(target), pm, _dp(out)))
 		return out
 
 	def wait_result(self, age=0):
 		self._check(self.lib.jdde_wait_result(self._h, int(age)))
+
+	def _sample_targets(self, targets):
+		targets = _f64(targets)
+		if targets.ndim == 1:
+			return targets, 0
+		if targets.ndim != 2 or targets.shape[0] != self.N:
+			raise ValueError(f"sample times must have shape (n_samples,) or ({self.N}, n_samples)")
+		return targets, 1
+
+	def integrate_samples(self, targets, out=None, status=None, fetch=True, fetch_status=True):
+		"""a series of integrate() calls in one launch; out: (n_samples, N, n). fetch / fetch_status as for integrate()."""
+		targets, pm = self._sample_targets(targets)
+		K = targets.shape[-1]
+		if fetch:
+			out = np.empty((K, self.N, self.n)) if out is None else self._checked_out(out, (K, self.N, self.n))
+		if fetch and fetch_status and status is None:
+			status = self._pinned_status()
+		if not (fetch and fetch_status):
+			status = None
+		self._check(self.lib.jdde_integrate_samples(self._h, _dp(targets), K, pm, _dp(out) if fetch else None,
+			status.ctypes.data_as(c_int32_p) if status is not None else None))
+		return out, status
+
+	def integrate_samples_async(self, targets, out):
+		targets, pm = self._sample_targets(targets)
+		K = targets.shape[-1]
+		self._checked_out(out, (K, self.N, self.n))
+		self._check(self.lib.jdde_integrate_samples_async(self._h, _dp(targets), K, pm, _dp(out)))
+		return out
+
+	@staticmethod
+	def _checked_out(out, shape):
+		"""the runtime writes prod(shape)·8 bytes through this pointer (the kernel itself, if the memory is page-locked)"""
+		if not isinstance(out, np.ndarray) or out.shape != tuple(shape) or out.dtype != np.float64 or not out.flags.c_contiguous or not out.flags.writeable:
+			raise ValueError(f"out must be a writeable C-contiguous float64 array of shape {tuple(shape)}")
+		return out
 
 	def _pinned_status(self):
 		"""per-member status lands in page-locked memory (full-bandwidth D2H); callers get a fresh copy only if they keep it"""
@@ -300,20 +337,21 @@ class Engine:
 		pm = int(steps.ndim == 2)
 		if pm and steps.shape[0] != self.N:
 			raise ValueError("steps have wrong shape")
-		out = np.empty((self.N, self.n)) if out is None else out
+		out = np.empty((self.N, self.n)) if out is None else self._checked_out(out, (self.N, self.n))
 		status = np.empty(self.N, dtype=np.int32) if status is None else status
 		self._check(self.lib.jdde_step_on_discontinuities(self._h, steps.shape[-1], _dp(steps), pm, _dp(out), status.ctypes.data_as(c_int32_p)))
 		return out, status
 
-	def resume(self, lyap=False):
-		"""repeat the last integrate / step_on_discontinuities / integrate_lyap call for members that stopped"""
+	def resume(self, lyap=False, samples=None):
+		"""repeat the last integrate / step_on_discontinuities / integrate_lyap / integrate_samples call for members that
+		stopped (samples: the (n_samples, N, n) result array of the integrate_samples call that is resumed)"""
 		status = np.empty(self.N, dtype=np.int32)
 		if lyap:
 			n_lyap = self.n//self.n_basic-1
 			state, lyaps, delta_t = np.empty((self.N, self.n_basic)), np.empty((self.N, n_lyap)), np.empty(self.N)
 			self._check(self.lib.jdde_resume(self._h, _dp(state), _dp(lyaps), _dp(delta_t), status.ctypes.data_as(c_int32_p)))
 			return state, lyaps, delta_t, status
-		out = np.empty((self.N, self.n))
+		out = np.empty((self.N, self.n)) if samples is None else samples
 		self._check(self.lib.jdde_resume(self._h, _dp(out), None, None, status.ctypes.data_as(c_int32_p)))
 		return out, status
 

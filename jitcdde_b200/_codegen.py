@@ -29,6 +29,8 @@ Vocabulary (all macros):
   JDDE_PAST_DY(time, i, s)  cubic Hermite derivative           (reference: past_dy → get_past_diff)
   JDDE_SET_DY(i, value)     store derivative component         (reference: set_dy)
   JDDE_IPOW(x, e)           x**e for a literal integer e as a fixed multiplication chain
+  JDDE_SIN/COS/EXP/TANH/LOG elementary functions: libm in the production build, the bit-reproducible ones of
+                            csrc/jdde_math.h in the verification build, oracle and "chain" reference core
 
 Lookup sites: the reference gives every textual `anchors(…)` call its own
 search cursor (`anchor_mem`, jitced_template.c:44-45, 193-217;
@@ -50,12 +52,16 @@ from ._symbols import anchors, current_y, past_dy, past_y, t
 
 _MAX_IPOW = 64
 
+#: elementary functions that csrc/jdde_math.h implements with the same bits on CPU and GPU for the verification build
+#: (the production build and the "literal" reference flavour call libm)
+_ELEMENTARY = {"sin": "JDDE_SIN", "cos": "JDDE_COS", "exp": "JDDE_EXP", "tanh": "JDDE_TANH", "log": "JDDE_LOG"}
+
 
 class _MacroPrinter(C99CodePrinter):
 	"""Prints SymPy expressions in the JDDE_* macro vocabulary."""
 
 	def __init__(self, par_index, seg_symbols, literal_pow=False):
-		super().__init__({"allow_unknown_functions": True})
+		super().__init__({"allow_unknown_functions": True, "user_functions": dict(_ELEMENTARY)})
 		self.par_index = par_index
 		self.seg_symbols = seg_symbols
 		self.literal_pow = literal_pow

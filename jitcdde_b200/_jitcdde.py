@@ -484,6 +484,34 @@ class jitcdde:
 				result = out
 		return self._shape_state(result)
 
+	def integrate_samples(self, times, out=None, wait=True):
+		"""
+		Extension: the sampling loop `[DDE.integrate(T) for T in times]` (examples/mackey_glass.py:76-78) as ONE kernel
+		launch — the same steps and the same states as the separate calls, bit for bit, but a trajectory does not wait
+		for the others at every sample and the host is not in the loop. `times`: ascending, shape (n_samples,) or
+		(n_members, n_samples). Returns an array of shape (n_samples, n) — (n_samples, n_members, n) for ensembles —,
+		`out` if given (page-locked memory from `pinned_empty` is written by the kernel itself). `wait=False` queues the
+		work like `integrate(..., wait=False)`.
+		"""
+		self._initiate()
+		times = np.asarray(times, dtype=float)
+		if times.ndim not in (1, 2) or times.shape[-1] < 1 or np.any(np.diff(times, axis=-1) < 0):
+			raise ValueError("times must be a non-empty ascending sequence")
+		if not self.initial_discontinuities_handled:
+			warn("You did not explicitly handle initial discontinuities. Proceed only if you know what you are doing. See https://jitcdde.rtfd.io/#discontinuities for details.", stacklevel=2)
+		if not wait:
+			if out is None:
+				raise ValueError("wait=False needs a preallocated `out` (jitcdde_b200.pinned_empty)")
+			self._queued = True
+			return self._engine.integrate_samples_async(times, out)
+		if getattr(self, "_queued", False):
+			self.synchronize()
+		result, status = self._engine.integrate_samples(times, out=out, fetch_status=False)
+		status = self._engine.get_status() if self._engine.count_failed() else None
+		while self._check_status(status, retry=True):
+			result, status = self._engine.resume(samples=result)
+		return result[:, 0].copy() if self.n_members == 1 and out is None else result
+
 	def wait_result(self, age=0):
 		"""wait for the `out` of the `integrate(..., wait=False)` call `age` calls ago (0: the latest, 1: the one before)
 		without waiting for younger work; member failures are only reported by `synchronize()`"""

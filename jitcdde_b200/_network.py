@@ -32,7 +32,7 @@ class _DeviceArray:
 
 
 class jitcdde_network:
-	def __init__(self, n, local, coupling, edges, node_parameters=(), weight=None, max_delay=None, device=0, ring_capacity=512, verbose=True, poll_every=8, exchange=None):
+	def __init__(self, n, local, coupling, edges, node_parameters=(), weight=None, max_delay=None, device=0, ring_capacity=512, verbose=True, poll_every=8, exchange=None, verification=False):
 		"""
 		n: number of nodes. local(y, t, *p) and coupling(y_delayed, y): functions returning SymPy expressions.
 		edges: (src, dst, tau[, weight]) arrays, one entry per directed edge src → dst with delay tau > 0.
@@ -62,7 +62,8 @@ class jitcdde_network:
 		self.max_delay = float(max_delay if max_delay is not None else (self._tau.max() if len(tau) else 0.0))
 		self._node_parameters = [np.asarray(p, dtype=float) for p in node_parameters]
 		self._program = _codegen.generate_network(local, coupling, len(self._node_parameters))
-		self._image = _build.build_net_image(self._program)
+		self.verification = verification      # kernels without FMA contraction, bit-reproducible elementary functions (as for jitcdde)
+		self._image = _build.build_net_image(self._program, mode=_build.VERIFY if verification else _build.FAST)
 		self.ring_capacity = ring_capacity
 		self.max_ring_capacity = 1 << 16
 

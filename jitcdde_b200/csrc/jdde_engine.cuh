@@ -61,7 +61,7 @@
 #define JD_WINDOW 0
 #endif
 /* Lookups hand anchor pairs around by value (registers) when anchors are small, by pointer otherwise */
-#define JD_SEG_BY_VALUE (JD_WINDOW == 1 || JD_WINDOW == 2 || JD_A <= 8)
+#define JD_SEG_BY_VALUE (JD_WINDOW == 1 || JD_WINDOW == 2 || JD_WINDOW == 4 || JD_A <= 8)
 #define JD_NORM_THRESHOLD (1e-30)     /* jitced_template.c:15 */
 
 #if defined(__CUDACC__)
@@ -163,6 +163,35 @@ struct Window
 #define JD_BLOCK 128
 #endif
 #define JD_WIN_SMEM_BYTES ((JD_NSITES > 0 ? JD_NSITES : 1)*4*JD_A*8*JD_BLOCK)
+#elif JD_WINDOW == 4
+/* Shared-memory window (device only): per thread and lookup site a private circular buffer of JD_WSLOTS = 8 anchors in
+ * shared memory (slot = index & 7) holds the ACCEPTED anchors hi−7 … hi around the cursor; in the steady state
+ * hi = cursor + JD_WAHEAD, i.e. cursor−3 … cursor+4. Anchors are brought in with cp.async (global → shared without
+ * passing through registers), one commit group per anchor, always in increasing index order: a forward move of the
+ * cursor asks for ONE new anchor, four moves ahead of its use, and waits (cp.async.wait_group 3) only for the anchor it
+ * steps onto — whose copy was requested three moves earlier; the three younger copies stay in flight. Moving back (the
+ * retry after a rejected step looks up earlier times) finds the three anchors behind the cursor still in place and
+ * never waits. (The first version kept cursor−1 … cursor+2 and waited for ALL copies at every move: two moves within
+ * one attempt, or one move back, paid a full memory round trip — 10 % of all stall samples, profiles/.)
+ * Only accepted anchors (index <= current) are staged: they are immutable while the kernel runs.
+ * Layout: an anchor's 1+2n doubles are (1+2n)/2 pairs of 16 bytes plus one single. Rows of 16-byte elements, one per
+ * lane ([row][JD_BLOCK]: consecutive lanes at consecutive elements, conflict-free LDS.128): first the pair rows of all
+ * slots, then rows that hold the singles of two neighbouring slots each — every address is the thread's base address
+ * plus a function of the slot, nothing else to keep in registers. 24 bytes per anchor for n = 1 instead of the padded
+ * 32, 192 bytes per thread. This is the staging of `north_star`. */
+#define JD_WSLOTS 8
+#define JD_WAHEAD 4
+#define JD_WPAIRS ((1+2*JD_N)/2)
+struct Window
+{
+	int hi;            /* highest staged index; all of hi−7 … hi are staged (requested in this order) */
+	int sync;          /* highest index whose copy is known to have landed */
+};
+#ifndef JD_BLOCK
+#define JD_BLOCK 128
+#endif
+#define JD_WIN_PAIR_ROWS ((JD_NSITES > 0 ? JD_NSITES : 1)*JD_WSLOTS*JD_WPAIRS)
+#define JD_WIN_SMEM_BYTES ((JD_WIN_PAIR_ROWS + (JD_NSITES > 0 ? JD_NSITES : 1)*JD_WSLOTS/2)*16*JD_BLOCK)
 #elif JD_WINDOW
 /* register-resident window of one lookup site: the anchor pair (cursor, cursor+1) plus the prefetched
  * neighbours cursor-1 and cursor+2, so that the cursor can move one anchor in either direction (forward:
@@ -191,6 +220,9 @@ struct Member
 #if JD_WINDOW
 	Window win[JD_NSITES > 0 ? JD_NSITES : 1];
 #endif
+#if JD_WINDOW == 4
+	unsigned wbase;                             /* index of this thread's element in every row of the window (shared memory) */
+#endif
 	double par[JD_NPARAMS > 0 ? JD_NPARAMS : 1];
 
 	double cur_t, cur_y[JD_N], cur_d[JD_N];     /* last accepted anchor (`current`) */
@@ -204,7 +236,7 @@ struct Member
 	 * touched when a delay is shorter than a step. It stays in the per-member arrays in global memory and is
 	 * accessed by the cold paths directly; the hot loop only carries this flag (last_pws != False). */
 	bool pws_pending;
-	long long index;                            /* this member's index in the per-member arrays */
+	int index;                                  /* this member's index in the per-member arrays (jdde_create: n_members < 2^31) */
 
 	/* Counters since load_member, added to the 64-bit totals by store_member. Only `attempts` is touched in
 	 * the hot path; accepted steps are recovered from the advance of `current`. */
@@ -231,13 +263,24 @@ struct Member
 #if JD_WINDOW
 		JD_UNROLL
 		for (int s = 0; s < JD_NSITES; s++)
+#if JD_WINDOW == 4
+			win[s].hi = -0x40000000;
+#else
 			win[s].valid = false;
+#endif
 #endif
 	}
 };
 
 #if JD_WINDOW
 JD_FN void fill_window(Member & M, int const site);
+#endif
+#if JD_WINDOW == 4
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void win_init(Member & M);
+#else
+inline void win_init(Member &) {}
+#endif
 #endif
 
 /* Past-within-step memory of the controller (cold). One thread per member: the per-member arrays in global memory.
@@ -251,7 +294,7 @@ JD_FN double & ctl_credit(Member const & M, jdde_problem const & P) { return P.c
 JD_FN void load_member(jdde_problem const & P, long long const m, Member & M)
 {
 	M.mask = P.cap-1;
-	M.index = m;
+	M.index = (int)m;
 	M.ring = P.ring + (size_t)m*P.ring_stride;
 	M.first = P.first[m];
 	M.last = P.last[m];
@@ -271,6 +314,9 @@ JD_FN void load_member(jdde_problem const & P, long long const m, Member & M)
 		M.cur_y[i] = c[1+i];
 		M.cur_d[i] = c[1+JD_N+i];
 	}
+#if JD_WINDOW == 4
+	win_init(M);
+#endif
 #if JD_WINDOW
 	JD_UNROLL
 	for (int s = 0; s < JD_NSITES; s++)
@@ -573,6 +619,179 @@ JD_FN Seg anchors(Member & M, int const site, double const t)
 			/* t <= time of an accepted anchor <= current.time: no past-within-step contribution */
 			win_read(site, ca, s.v);
 			win_read(site, ca+1, s.w);
+			return s;
+		}
+	}
+	double const * pa; double const * pn; double ta, tn;
+	walk(M, site, t, pa, pn, ta, tn);
+	load_anchor(pa, s.v);
+	load_anchor(pn, s.w);
+	fill_window(M, site);
+	return s;
+}
+#elif JD_WINDOW == 4
+#if defined(__CUDA_ARCH__)
+extern __shared__ d2 jd_win_smem[];
+
+__device__ __forceinline__ void win_init(Member & M)
+{
+	/* (through an opaque move: otherwise the compiler re-reads the thread index from its special register — a slow
+	 * read — at every lookup instead of keeping this value in a register) */
+	asm volatile("mov.u32 %0, %1;" : "=r"(M.wbase) : "r"(threadIdx.x));
+}
+
+/* this thread's element of pair row `row` of the slot of anchor `index` */
+__device__ __forceinline__ d2 * win_pair_pointer(Member const & M, int const site, int const index, int const row)
+{
+	return jd_win_smem + (M.wbase + (unsigned)(((site*JD_WSLOTS + (index & (JD_WSLOTS-1)))*JD_WPAIRS + row)*JD_BLOCK));
+}
+
+/* … and the single, which shares a 16-byte element with the single of the neighbouring slot */
+__device__ __forceinline__ double * win_single_pointer(Member const & M, int const site, int const index)
+{
+	int const slot = index & (JD_WSLOTS-1);
+	return reinterpret_cast<double *>(jd_win_smem + (M.wbase + (unsigned)((JD_WIN_PAIR_ROWS + site*(JD_WSLOTS/2) + (slot >> 1))*JD_BLOCK))) + (slot & 1);
+}
+
+/* address of the window in the shared state space, as cp.async wants it: the symbol itself (an immediate), not a
+ * conversion of a generic pointer (which reads a special register every time) */
+__device__ __forceinline__ unsigned win_shared_base()
+{
+	unsigned base;
+	asm("mov.u32 %0, _ZN4jdde11jd_win_smemE;" : "=r"(base));
+	return base;
+}
+
+/* request the copy of one anchor: one commit group */
+__device__ __forceinline__ void win_fetch(Member const & M, int const site, int const index)
+{
+	double const * const anchor = M.slot(index);
+	int const slot = index & (JD_WSLOTS-1);
+	unsigned const base = win_shared_base() + M.wbase*16u;
+	JD_UNROLL
+	for (int r = 0; r < JD_WPAIRS; r++)
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(base + (unsigned)(((site*JD_WSLOTS + slot)*JD_WPAIRS + r)*(JD_BLOCK*16))), "l"(anchor+2*r) : "memory");
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(base + (unsigned)((JD_WIN_PAIR_ROWS + site*(JD_WSLOTS/2) + (slot >> 1))*(JD_BLOCK*16) + (slot & 1)*8)), "l"(anchor+2*JD_WPAIRS) : "memory");
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+/* Make sure that the copy of anchor `need` has landed. Copies are requested in increasing index order and complete in
+ * that order as far as wait_group is concerned: with hi − need >= 3 younger groups of this site (other sites only add
+ * younger ones), "at most 3 groups pending" implies that the group of `need` is complete. (The "memory" clobbers keep
+ * the compiler from moving reads of the window across the wait; the reads themselves are ordinary loads, free to be
+ * scheduled ahead of their use.) */
+__device__ __forceinline__ void win_sync(Window & W, int const need)
+{
+	if (W.sync < need)
+	{
+		if (W.hi-need >= JD_WAHEAD-1)
+		{
+			asm volatile("cp.async.wait_group 3;" ::: "memory");
+			W.sync = W.hi-(JD_WAHEAD-1);
+		}
+		else
+		{
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+			W.sync = W.hi;
+		}
+	}
+}
+
+__device__ __forceinline__ d2 win_pair(Member const & M, int const site, int const index, int const row)
+{
+	return *win_pair_pointer(M, site, index, row);
+}
+
+/* the rest of an anchor whose first pair (time, first component) has been read already */
+__device__ __forceinline__ void win_read_rest(Member const & M, int const site, int const index, d2 const first, double (&a)[JD_A])
+{
+	a[0] = first.x;
+	a[1] = first.y;
+	JD_UNROLL
+	for (int r = 1; r < JD_WPAIRS; r++)
+	{
+		d2 const v = win_pair(M, site, index, r);
+		a[2*r] = v.x;
+		a[2*r+1] = v.y;
+	}
+	a[2*JD_WPAIRS] = *win_single_pointer(M, site, index);
+	JD_UNROLL
+	for (int k = 2*JD_WPAIRS+1; k < JD_A; k++)
+		a[k] = 0.0;
+}
+#else
+/* host pass of nvcc: never executed */
+inline void win_fetch(Member const &, int, int) {}
+inline void win_sync(Window &, int) {}
+inline d2 win_pair(Member const &, int, int, int) { return d2(); }
+inline void win_read_rest(Member const &, int, int, d2, double (&)[JD_A]) {}
+#endif
+
+/* stage the anchors around the cursor of a site: hi−7 … hi with hi = min(cursor + JD_WAHEAD, current) */
+JD_FN void fill_window(Member & M, int const site)
+{
+	Window & W = M.win[site];
+	int const ca = M.cursor[site];
+	int const hi = ca+JD_WAHEAD <= M.current ? ca+JD_WAHEAD : M.current;
+	if (hi <= ca)
+	{
+		W.hi = -0x40000000;      /* nothing to stage: the segment of the cursor ends at a tentative anchor */
+		return;
+	}
+	JD_UNROLL
+	for (int k = JD_WSLOTS-1; k >= 0; k--)
+		win_fetch(M, site, hi-k);       /* (indices below `first` are never looked at; their slots of the ring are this member's own memory) */
+	W.hi = hi;
+	W.sync = hi-JD_WSLOTS;
+}
+
+/* the same comparisons as walk(), on staged anchors */
+JD_FN Seg anchors(Member & M, int const site, double const t)
+{
+	Window & W = M.win[site];
+	Seg s;
+	int ca = M.cursor[site];
+	if (W.hi > ca && ca > W.hi-JD_WSLOTS)
+	{
+		if (W.hi < ca+JD_WAHEAD && W.hi < M.current)
+			win_fetch(M, site, ++W.hi);      /* `current` has moved on since the window was filled */
+		win_sync(W, ca+1);
+		d2 v = win_pair(M, site, ca, 0);
+		d2 w = win_pair(M, site, ca+1, 0);
+		bool hit = true;
+		/* while (ca->time > t && ca->previous) ca = ca->previous; */
+		while (v.x > t && ca > M.first)
+		{
+			if (ca-1 <= W.hi-JD_WSLOTS)
+			{
+				hit = false;
+				break;
+			}
+			--ca;
+			w = v;
+			v = win_pair(M, site, ca, 0);
+		}
+		/* while (ca->next->time < t && ca->next->next) ca = ca->next; */
+		while (hit && w.x < t)
+		{
+			if (ca+2 > W.hi)
+			{
+				hit = false;      /* next anchor is tentative or missing: let walk() decide */
+				break;
+			}
+			++ca;
+			if (W.hi < ca+JD_WAHEAD && W.hi < M.current)
+				win_fetch(M, site, ++W.hi);      /* overwrites the slot of anchor hi−8 <= cursor−4 */
+			win_sync(W, ca+1);
+			v = w;
+			w = win_pair(M, site, ca+1, 0);
+		}
+		M.cursor[site] = ca;
+		if (hit)
+		{
+			/* t <= time of an accepted anchor <= current.time: no past-within-step contribution */
+			win_read_rest(M, site, ca, v, s.v);
+			win_read_rest(M, site, ca+1, w, s.w);
 			return s;
 		}
 	}
@@ -1020,7 +1239,7 @@ JD_FN void get_recent_state(Member const & M, double const t, double * const out
 /* ------------------------------------------------------------------ controller (_jitcdde.py) */
 
 /* _jitcdde.py:21 */
-JD_FN double sigmoid(double const x) { return (tanh(x)+1)/2; }
+JD_FN double sigmoid(double const x) { return (JDDE_TANH(x)+1)/2; }
 
 /* _jitcdde.py:745-765: UnsuccessfulIntegration becomes a per-member status */
 template <class MT>
@@ -1051,22 +1270,26 @@ JD_FN bool pws_allows_increase(MT & M, jdde_problem const & P, double const new_
 	return increase;
 }
 
-/* _adjust_step_size, _jitcdde.py:775-794 with q = 3 (:726). The two fractional powers use the
- * libm-free roots of jdde_math.h so that CPU oracle and GPU take bit-identical step sizes. */
+/* _adjust_step_size, _jitcdde.py:775-794 with q = 3 (:726). The two fractional powers use the libm-free root of
+ * jdde_math.h so that CPU oracle and GPU take bit-identical step sizes. Decrease (p**(-1/3)) and increase (p**(-1/4))
+ * share ONE instance of the root code, selected by a flag: in a warp of 32 trajectories some lane decreases and some
+ * lane increases in nearly every attempt, so two branches cost the warp both of them one after the other. */
 template <class MT>
 JD_FN bool adjust_step_size(MT & M, jdde_problem const & PR)
 {
 	jdde_int_params const & P = PR.P;
 	double const p = get_p(M, P.atol, P.rtol);
-	if (p > P.decrease_threshold)
+	bool const decrease = p > P.decrease_threshold;
+	if (decrease || p <= P.increase_threshold)
 	{
-		M.dt *= fmax(P.safety_factor*jdde_inv_root3(p), P.min_factor);
-		control_for_min_step(M, P);
-		return false;
-	}
-	if (p <= P.increase_threshold)
-	{
-		double const factor = (p != 0.0) ? P.safety_factor*jdde_inv_root4(p) : P.max_factor;
+		double const root = jdde_inv_root(p, !decrease);
+		if (decrease)
+		{
+			M.dt *= fmax(P.safety_factor*root, P.min_factor);
+			control_for_min_step(M, P);
+			return false;
+		}
+		double const factor = (p != 0.0) ? P.safety_factor*root : P.max_factor;
 		double const new_dt = fmin(M.dt*fmin(factor, P.max_factor), P.max_step);
 		if (!M.pws_pending || pws_allows_increase(M, PR, new_dt))
 		{
@@ -1146,20 +1369,56 @@ JD_FN bool ensure_room(MT & M, double const max_delay)
 
 /* the `while t < target` loops of integrate (_jitcdde.py:830-832) and of
  * step_on_discontinuities (:988-993, steps capped at the target) */
+/* One more rejected attempt. On the device the per-member total in global memory is incremented by a reduction that
+ * returns nothing (RED: no register, nothing to wait for) instead of a counter carried through the hot loop. */
+template <class MT>
+JD_FN void count_rejection(MT & M, jdde_problem const &)
+{
+	M.rejected++;      /* (a group of lanes per member: every lane keeps the count, one of them stores it) */
+}
+
+JD_FN void count_rejection(Member & M, jdde_problem const & P)
+{
+#if defined(__CUDA_ARCH__)
+	atomicAdd(reinterpret_cast<unsigned long long *>(P.rejected+M.index), 1ull);
+#else
+	P.rejected[M.index]++;
+#endif
+}
+
+/* last_actual_step_start (jitced_template.c:48, set by get_next_step :424) after a series of attempts of the stepping
+ * loop: the time of `current` if the last attempt left a tentative anchor behind (it was rejected), else the time of the
+ * anchor before `current` (the accepted step started there). Recomputing it after the loop instead of carrying it
+ * through the loop frees two registers of the hot loop (the assignments in get_next_step become dead stores there).
+ * Valid where nothing but the stepper touches the history between load_member and store_member: the integrate kernels. */
+template <class MT>
+JD_FN void settle_last_start(MT & M, jdde_problem const & P)
+{
+	/* (attempts: calls of get_next_step since the member was loaded; none: the stored value stands) */
+	M.last_start = M.attempts == 0 ? P.last_start[M.index] : M.last != M.current ? M.cur_t : M.slot(M.current-1)[0];
+}
+
+/* the `while t < target` loops of integrate (_jitcdde.py:830-832) and of
+ * step_on_discontinuities (:988-993, steps capped at the target) */
 template <class MT>
 JD_FN void step_until(MT & M, jdde_problem const & P, double const target, bool const capped, long long const budget)
 {
+	int const attempt_budget = budget > 0x7fffffff ? 0x7fffffff : (int)budget;
 	while (M.cur_t < target)
 	{
-		if (!ensure_room(M, P.max_delay))
-			break;
+		if (M.last+1-M.first > M.mask)
+		{
+			settle_last_start(M, P);
+			if (!ensure_room(M, P.max_delay))
+				break;
+		}
 		if (!(M.dt > 0.0))
 		{
 			/* a step size of zero/NaN would never reach the target: the reference would spin forever */
 			M.status = JDDE_STATUS_NONFINITE;
 			break;
 		}
-		if (M.attempts >= budget)
+		if (M.attempts >= attempt_budget)
 		{
 			/* watchdog: a kernel must end; the caller clears the status and calls again to go on */
 			M.status = JDDE_STATUS_BUDGET;
@@ -1170,11 +1429,12 @@ JD_FN void step_until(MT & M, jdde_problem const & P, double const target, bool 
 			accept_step(M);
 		else
 		{
-			M.rejected++;
+			count_rejection(M, P);
 			if (M.status != JDDE_STATUS_OK)
 				break;
 		}
 	}
+	settle_last_start(M, P);
 }
 
 /* ------------------------------------------------------------------ jumps */
@@ -1768,42 +2028,122 @@ JD_FN void member_reset_controller(jdde_problem const & P, long long const m)
 	P.credit[m] = 0.0;
 }
 
-/* integrate (n_steps == 0: `targets` are absolute times) or step_on_discontinuities
- * (n_steps > 0: `targets` are step lengths, applied cumulatively, _jitcdde.py:986-987).
+/* get_recent_state (jitced_template.c:287-320) at the moment a step is accepted: the segment (current, tentative anchor)
+ * is in registers — same anchors, same formula as get_recent_state reads from the ring after accept_step */
+JD_FN void recent_state_of_step(Member const & M, double const t, double * const out, int const n_out)
+{
+	double const q = M.new_t-M.cur_t;
+	double const x = (t - M.cur_t)/q;
+	JD_UNROLL
+	for (int index = 0; index < JD_N; index++)
+	{
+		double const a = M.cur_y[index];
+		double const b = M.cur_d[index] * q;
+		double const c = M.new_y[index];
+		double const d = M.new_d[index] * q;
+		if (index < n_out)
+			out[index] = (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
+	}
+}
+
+/* integrate (n_steps == 0: `targets` are absolute times), step_on_discontinuities
+ * (n_steps > 0: `targets` are step lengths, applied cumulatively, _jitcdde.py:986-987) or a series of
+ * integrate calls (n_steps < 0: `targets` are −n_steps absolute sample times, the user's sampling loop of
+ * examples/mackey_glass.py:76-78 in one launch; results out[sample][member][component]).
  * `resume`: the call repeats an earlier one that stopped for some members (ring overflow, attempt
- * budget); members continue in the step and towards the target they had reached. */
+ * budget); members continue in the step and towards the target they had reached.
+ *
+ * ONE stepping loop serves all three (the stepper is instantiated once) and a member never leaves it before its last
+ * target: the call is a sequence of stretches — integrate: one uncapped stretch to an absolute time; sampling: one
+ * per sample time; step_on_discontinuities: capped stretches of given lengths. The step that reaches the end of a
+ * stretch interpolates the output there from the two anchors it has in registers (what get_recent_state would read
+ * back from the ring), moves on to the next stretch and is accepted; the lanes of a warp stay together in the loop
+ * instead of taking turns with an epilogue per sample. forget() runs once, at the end: its threshold only grows, so
+ * one call with the final threshold drops exactly the anchors that one call per sample would have dropped (and when
+ * the ring runs full on the way, ensure_room forgets at once). */
 JD_FN void member_integrate(jdde_problem const & P, long long const m, double const * const targets, int const per_member, int const n_steps, int const resume, double * const out, int const n_out, long long const budget)
 {
 	Member M;
 	load_member(P, m, M);
 	if (M.status != JDDE_STATUS_OK)
 		return;
-	double target;
-	if (n_steps == 0)
+	bool const capped = n_steps > 0;
+	int const n_stretches = capped ? n_steps : n_steps < 0 ? -n_steps : 1;
+	double const * const steps = per_member ? targets+(size_t)m*n_stretches : targets;
+	double * const result = out ? out+(size_t)m*n_out : nullptr;
+	size_t const result_stride = (size_t)P.n_members*n_out;                 /* between the samples of one member */
+	int s = n_steps != 0 && resume ? P.resume_index[m] : 0;
+	double target = 0.0;
+	if (s < n_stretches)
+		target = capped ? (resume ? P.resume_target[m] : M.cur_t + steps[s]) : steps[s];
+	/* sample times that need no step (the reference extrapolates or interpolates on the last segment, _jitcdde.py:833-834) */
+	while (!capped && s < n_stretches && !(M.cur_t < target))
 	{
-		target = per_member ? targets[m] : targets[0];
-		step_until(M, P, target, false, budget);
+		if (result)
+			get_recent_state(M, target, result+(size_t)s*result_stride, n_out);
+		if (++s < n_stretches)
+			target = steps[s];
 	}
-	else
+	while (s < n_stretches)
 	{
-		target = resume ? P.resume_target[m] : M.cur_t;
-		double const * const steps = per_member ? targets+(size_t)m*n_steps : targets;
-		int s = resume ? P.resume_index[m] : 0;
-		for (; s < n_steps; s++)
+		/* here: cur_t < target */
+		if ((M.attempts & 31) == 31 || M.last+1-M.first > M.mask)
 		{
-			if (!(resume && s == P.resume_index[m]))
-				target = M.cur_t + steps[s];
-			step_until(M, P, target, true, budget);
+			/* Drop what no lookup can reach any more, every 32 attempts — the lanes of a warp count their attempts
+			 * alike, so they do it together — instead of each lane on its own when its ring is full (one lane in ten
+			 * at every attempt, with the whole warp waiting: 17 % of the stall samples, profiles/). The reference forgets
+			 * at the end of integrate; forgetting earlier with a smaller threshold drops a subset of the same anchors. */
+			settle_last_start(M, P);
+			forget(M, P.max_delay);
+			if (M.last+1-M.first > M.mask)
+			{
+				M.status = JDDE_STATUS_OVERFLOW;
+				break;
+			}
+		}
+		if (!(M.dt > 0.0))
+		{
+			/* a step size of zero/NaN would never reach the target: the reference would spin forever */
+			M.status = JDDE_STATUS_NONFINITE;
+			break;
+		}
+		if (M.attempts >= (int)budget)      /* (the caller passes at most INT_MAX) */
+		{
+			/* watchdog: a kernel must end; the caller clears the status and calls again to go on */
+			M.status = JDDE_STATUS_BUDGET;
+			break;
+		}
+		double const length = capped ? fmin(M.dt, target-M.cur_t) : M.dt;
+		if (try_single_step(M, P, length))
+		{
+			/* the `while t < target` of integrate (_jitcdde.py:830-832) / of step_on_discontinuities (:988-993) ends with this step? */
+			while (!(M.new_t < target))
+			{
+				if (!capped && result)
+					recent_state_of_step(M, target, result+(size_t)s*result_stride, n_out);
+				if (++s == n_stretches)
+					break;
+				target = capped ? M.new_t + steps[s] : steps[s];
+			}
+			accept_step(M);
+		}
+		else
+		{
+			count_rejection(M, P);
 			if (M.status != JDDE_STATUS_OK)
 				break;
 		}
+	}
+	settle_last_start(M, P);
+	if (n_steps != 0)
+	{
 		P.resume_index[m] = s;
 		P.resume_target[m] = target;
 	}
 	if (M.status == JDDE_STATUS_OK)
 	{
-		if (out)
-			get_recent_state(M, target, out+(size_t)m*n_out, n_out);
+		if (capped && result)
+			get_recent_state(M, target, result, n_out);
 		forget(M, P.max_delay);
 	}
 	P.accepted[m] += M.current - P.current[m];      /* every accepted step appends exactly one anchor */

@@ -47,6 +47,7 @@ struct jdde_handle
 	/* pipelined sampling (jdde_integrate_async): second result buffer, copy stream, events per buffer */
 	cudaStream_t copy_stream = nullptr;
 	double * d_out_alt = nullptr;
+	double * d_samples[2] = { nullptr, nullptr };  size_t samples_count[2] = { 0, 0 };   /* results of jdde_integrate_samples that cannot go straight to the host */
 	cudaEvent_t kernel_done[2] = { nullptr, nullptr }, copy_done[2] = { nullptr, nullptr };
 	bool copy_pending[2] = { false, false };
 	bool result_direct[2] = { false, false }, result_queued[2] = { false, false };
@@ -68,7 +69,7 @@ struct jdde_handle
 	double * d_aux2 = nullptr;                           /* [N] */
 	unsigned long long * d_sums = nullptr;               /* [3] */
 	/* last integration call, for jdde_resume */
-	int last_kind = 0;                                   /* 0 none, 1 integrate, 2 step_on_discontinuities, 3 integrate_lyap */
+	int last_kind = 0;                                   /* 0 none, 1 integrate, 2 step_on_discontinuities, 3 integrate_lyap, 4 integrate_samples */
 	int last_per_member = 0, last_n_steps = 0;
 	std::vector<double> last_targets;
 	std::vector<void *> allocations;
@@ -411,6 +412,9 @@ int jdde_destroy(jdde_handle * h)
 		cudaFree(p);
 	if (h->d_in)
 		cudaFree(h->d_in);
+	for (double * p : h->d_samples)
+		if (p)
+			cudaFree(p);
 	if (h->projector_memory)
 		cudaFree(h->projector_memory);
 	if (h->lib)
@@ -490,6 +494,15 @@ int jdde_load_rhs(jdde_handle * h, const void * image, size_t len)
 			if (entry.required)
 				return fail(h, JDDE_E_IMAGE, std::string("image lacks kernel ") + entry.name);
 		}
+	}
+	if (h->smem_bytes > 48*1024)
+		JD_CUDA(h, cudaFuncSetAttribute((const void *)h->k.integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+	/* (no preferred carve-out: the driver sizes shared memory for the resident blocks and leaves the rest to L1, which
+	 * the register spills of the stepper live in — forcing the maximum carve-out cost 25 % of the throughput, profiles/) */
+	if (getenv("JITCDDE_B200_CARVEOUT") && h->smem_bytes > 0)
+	{
+		if (cudaFuncSetAttribute((const void *)h->k.integrate, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("JITCDDE_B200_CARVEOUT"))) != cudaSuccess)
+			(void)cudaGetLastError();
 	}
 	if (h->group_lanes && !h->k.integrate_group)
 		return fail(h, JDDE_E_IMAGE, "image announces a lane group per member but lacks jdde_k_integrate_group");
@@ -599,13 +612,41 @@ int jdde_set_integration_parameters(jdde_handle * h, const jdde_int_params * p, 
 	return JDDE_OK;
 }
 
+/* device buffer for the results of a sampling call: [n_samples][N][n] */
+static int samples_buffer(jdde_handle * h, int slot, size_t count, double ** out)
+{
+	if (h->samples_count[slot] < count)
+	{
+		if (h->d_samples[slot])
+		{
+			JD_CUDA(h, cudaStreamSynchronize(h->stream));
+			if (h->copy_stream)
+				JD_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+			JD_CUDA(h, cudaFree(h->d_samples[slot]));
+			h->d_samples[slot] = nullptr;
+			h->samples_count[slot] = 0;
+		}
+		cudaError_t e = cudaMalloc((void **)&h->d_samples[slot], count*sizeof(double));
+		if (e != cudaSuccess)
+			return fail(h, e == cudaErrorMemoryAllocation ? JDDE_E_NOMEM : JDDE_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+		h->samples_count[slot] = count;
+	}
+	*out = h->d_samples[slot];
+	return JDDE_OK;
+}
+
+/* n_steps == 0: integrate; > 0: step_on_discontinuities; < 0: −n_steps samples (results [samples][N][n_out]) */
 static int run_integrate(jdde_handle * h, const double * targets, size_t count, int per_member, int n_steps, int resume, double * out_state, int n_out, int32_t * status, bool pipelined = false)
 {
 	int rc;
 	double * d_targets;
 	if (!targets)
 		return fail(h, JDDE_E_INVALID, "null argument");
-	double * const direct = n_steps == 0 ? direct_alias(out_state) : nullptr;
+	if (n_steps < 0 && h->group_lanes)
+		return fail(h, JDDE_E_INVALID, "sampling in one launch is not available for images with a group of lanes per member");
+	size_t const n_results = n_steps < 0 ? (size_t)-n_steps : 1;
+	size_t const result_count = n_results*(size_t)h->desc.n_members*(size_t)n_out;
+	double * const direct = n_steps <= 0 ? direct_alias(out_state) : nullptr;
 	if (pipelined)
 	{
 		if (!out_state)
@@ -622,9 +663,10 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 			if ((rc = dev_alloc(h, &h->d_out_alt, (size_t)h->desc.n_members*h->desc.n))) return rc;
 		}
 		int const slot = h->out_slot ^= 1;
-		double * d_result = direct ? direct : slot ? h->d_out_alt : h->d_out;
 		if (!direct && h->copy_pending[slot])       /* the copy that still reads this buffer (two calls ago) */
 			JD_CUDA(h, cudaStreamWaitEvent(h->stream, h->copy_done[slot], 0));
+		double * d_result = direct ? direct : slot ? h->d_out_alt : h->d_out;
+		if (!direct && n_results > 1 && (rc = samples_buffer(h, slot, result_count, &d_result))) return rc;
 		h->last_targets.assign(targets, targets+count);
 		h->last_per_member = per_member;
 		h->last_n_steps = n_steps;
@@ -639,7 +681,7 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 		if (direct)
 			return JDDE_OK;
 		JD_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->kernel_done[slot], 0));
-		JD_CUDA(h, cudaMemcpyAsync(out_state, d_result, (size_t)h->desc.n_members*n_out*sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+		JD_CUDA(h, cudaMemcpyAsync(out_state, d_result, result_count*sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
 		JD_CUDA(h, cudaEventRecord(h->copy_done[slot], h->copy_stream));
 		h->copy_pending[slot] = true;
 		return JDDE_OK;
@@ -654,6 +696,7 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 	int pm = per_member ? 1 : 0;
 	long long budget = h->budget;
 	double * d_result = direct ? direct : h->d_out;
+	if (!direct && n_results > 1 && (rc = samples_buffer(h, 0, result_count, &d_result))) return rc;
 	void * args[] = { &h->P, &d_targets, &pm, &n_steps, &resume, &d_result, &n_out, &budget };
 	if ((rc = launch_integrate(h, args))) return rc;
 	if (direct)
@@ -664,7 +707,7 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 			JD_CUDA(h, cudaStreamSynchronize(h->stream));
 		return JDDE_OK;
 	}
-	return finish(h, out_state, h->d_out, (size_t)h->desc.n_members*n_out, status);
+	return finish(h, out_state, d_result, result_count, status);
 }
 
 int jdde_integrate(jdde_handle * h, const double * target, int32_t per_member, double * out_state, int32_t * status)
@@ -701,6 +744,30 @@ int jdde_wait_result(jdde_handle * h, int32_t age)
 	else if (h->copy_pending[slot])
 		JD_CUDA(h, cudaEventSynchronize(h->copy_done[slot]));
 	return JDDE_OK;
+}
+
+int jdde_integrate_samples(jdde_handle * h, const double * targets, int32_t n_samples, int32_t per_member, double * out_states, int32_t * status)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (n_samples < 1)
+		return fail(h, JDDE_E_INVALID, "n_samples must be positive");
+	h->last_kind = 4;
+	return run_integrate(h, targets, (per_member ? (size_t)h->desc.n_members : 1)*(size_t)n_samples, per_member, -n_samples, 0, out_states, h->desc.n, status);
+}
+
+int jdde_integrate_samples_async(jdde_handle * h, const double * targets, int32_t n_samples, int32_t per_member, double * out_states)
+{
+	if (!h)
+		return JDDE_E_INVALID;
+	h->queueing = true;
+	int rc = ready_to_integrate(h);
+	h->queueing = false;
+	if (rc) return rc;
+	if (n_samples < 1)
+		return fail(h, JDDE_E_INVALID, "n_samples must be positive");
+	h->last_kind = 0;      /* nothing to resume */
+	return run_integrate(h, targets, (per_member ? (size_t)h->desc.n_members : 1)*(size_t)n_samples, per_member, -n_samples, 0, out_states, h->desc.n, nullptr, true);
 }
 
 int jdde_step_on_discontinuities(jdde_handle * h, int32_t n_steps, const double * steps, int32_t per_member, double * out_state, int32_t * status)
@@ -938,6 +1005,7 @@ int jdde_resume(jdde_handle * h, double * out_state, double * lyaps, double * de
 	{
 		case 1:
 		case 2:
+		case 4:      /* sampling: out_state is [samples][N][n]; samples written before the stop are written again only for members that had not reached them */
 			return run_integrate(h, targets.data(), targets.size(), h->last_per_member, h->last_n_steps, 1, out_state, h->desc.n, status);
 		case 3:
 			return run_lyap(h, targets.data(), targets.size(), h->last_per_member, 1, out_state, lyaps, delta_t, status);
@@ -1099,7 +1167,7 @@ int jdde_set_attempt_budget(jdde_handle * h, int64_t attempts)
 {
 	if (!h || attempts < 1)
 		return fail(h, JDDE_E_INVALID, "budget must be positive");
-	h->budget = attempts;
+	h->budget = attempts > 0x7fffffff ? 0x7fffffff : attempts;      /* the kernels count attempts per call in 32 bits */
 	return JDDE_OK;
 }
 

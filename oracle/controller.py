@@ -49,13 +49,14 @@ def discontinuity_steps(delays, propagations=1, min_distance=1e-5):
 	return steps
 
 
-def _sigmoid(x):
-	return (np.tanh(x)+1)/2
+def _sigmoid(x, tanh=np.tanh):
+	return (tanh(x)+1)/2
 
 
 class Controller:
-	def __init__(self, core, max_delay, root_mode=0, roots=None, **kwargs):
+	def __init__(self, core, max_delay, root_mode=0, roots=None, tanh=None, **kwargs):
 		self.DDE = core
+		self.tanh = tanh or getattr(roots, "tanh", None) or np.tanh      # jdde_tanh of the compiled oracle for runs the GPU is to reproduce bit for bit
 		self.max_delay = max_delay
 		self.root_mode = root_mode
 		self.roots = roots
@@ -102,9 +103,9 @@ class Controller:
 	# _jitcdde.py:767-773
 	def _increase_chance(self, new_dt):
 		q = new_dt/self.last_pws
-		is_explicit = _sigmoid(1-q)
-		far_from_explicit = _sigmoid(q-self.pws_factor)
-		few_iterations = _sigmoid(1-self.count/self.pws_factor)
+		is_explicit = _sigmoid(1-q, self.tanh)
+		far_from_explicit = _sigmoid(q-self.pws_factor, self.tanh)
+		few_iterations = _sigmoid(1-self.count/self.pws_factor, self.tanh)
 		profile = is_explicit+far_from_explicit*few_iterations
 		return profile + self.pws_base_increase_chance*(1-profile)
 

@@ -24,7 +24,7 @@ _CSRC = os.path.join(os.path.dirname(_HERE), "jitcdde_b200", "csrc")
 #: verification flags: no fast-math, no FMA contraction (hard part 1)
 VERIFY_FLAGS = ["-O2", "-ffp-contract=off"]
 #: timing flags for the CPU-baseline leg
-FAST_FLAGS = ["-O3"]   # no -march=native: the prebuilt .so must also run on the GPU box's host CPU
+FAST_FLAGS = ["-O3", "-DJDDE_LIBM"]   # no -march=native: the prebuilt .so must also run on the GPU box's host CPU
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 

@@ -38,7 +38,11 @@ REF_TESTS = "/root/reference/tests"
 def roots_from(lib):
 	lib.jo_inv_root.restype = ctypes.c_double
 	lib.jo_inv_root.argtypes = [ctypes.c_double, ctypes.c_int]
-	return lambda p, order: lib.jo_inv_root(p, int(order))
+	lib.jo_tanh.restype = ctypes.c_double
+	lib.jo_tanh.argtypes = [ctypes.c_double]
+	roots = lambda p, order: lib.jo_inv_root(p, int(order))
+	roots.tanh = lambda x: lib.jo_tanh(float(x))      # the controller's sigmoids (oracle/controller.py) with the same bits as on the GPU
+	return roots
 
 
 def make_core(prog, name, past, n_basic=None, flavour="chain", parameters=None):

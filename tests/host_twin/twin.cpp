@@ -21,7 +21,7 @@ struct jdde_handle
 {
 	jdde_desc desc{};
 	jdde_problem P{};
-	std::vector<double> ring, par, dt, last_pws, credit, last_start, out, out2, aux, aux2;
+	std::vector<double> ring, par, dt, last_pws, credit, last_start, out, out2, aux, aux2, samples;
 	std::vector<int> first, last, current, count, status, cursor, resume_index;
 	std::vector<double> resume_target, last_targets;
 	int last_kind = 0, last_pm = 0, last_n_steps = 0;
@@ -156,6 +156,28 @@ int jdde_integrate_async(jdde_handle * h, const double * target, int32_t pm, dou
 {
 	if (!out) return fail(h, JDDE_E_INVALID, "null argument");
 	int const rc = jdde_integrate(h, target, pm, out, nullptr);
+	h->last_kind = 0;
+	return rc;
+}
+
+int jdde_integrate_samples(jdde_handle * h, const double * targets, int32_t n_samples, int32_t pm, double * out, int32_t * status)
+{
+	if (int rc = ready(h)) return rc;
+	if (n_samples < 1) return fail(h, JDDE_E_INVALID, "n_samples must be positive");
+	remember(h, 4, targets, (pm ? (size_t)h->P.n_members : 1)*(size_t)n_samples, pm, -n_samples);
+	if (h->samples.size() < (size_t)n_samples*h->P.n_members*JD_N)
+		h->samples.resize((size_t)n_samples*h->P.n_members*JD_N);
+	for (long long m = 0; m < h->P.n_members; m++)
+		jdde::member_integrate(h->P, m, targets, pm, -n_samples, 0, h->samples.data(), JD_N, h->budget);
+	h->launches++;
+	give(h, out, h->samples, (size_t)n_samples*h->P.n_members*JD_N, status);
+	return JDDE_OK;
+}
+
+int jdde_integrate_samples_async(jdde_handle * h, const double * targets, int32_t n_samples, int32_t pm, double * out)
+{
+	if (!out) return fail(h, JDDE_E_INVALID, "null argument");
+	int const rc = jdde_integrate_samples(h, targets, n_samples, pm, out, nullptr);
 	h->last_kind = 0;
 	return rc;
 }
@@ -351,6 +373,15 @@ int jdde_resume(jdde_handle * h, double * out_state, double * lyaps, double * de
 	}
 	if (h->last_kind == 3)
 		return run_lyap(h, targets.data(), h->last_pm, 1, out_state, lyaps, delta_t, status);
+	if (h->last_kind == 4)
+	{
+		int const n_samples = -h->last_n_steps;
+		for (long long m = 0; m < h->P.n_members; m++)
+			jdde::member_integrate(h->P, m, targets.data(), h->last_pm, h->last_n_steps, 1, h->samples.data(), JD_N, h->budget);
+		h->launches++;
+		give(h, out_state, h->samples, (size_t)n_samples*h->P.n_members*JD_N, status);
+		return JDDE_OK;
+	}
 	return fail(h, JDDE_E_INVALID, "nothing to resume");
 }
 

@@ -180,3 +180,46 @@ def test_remove_projections_invariants(twin):
 	DDE.remove_projections()
 	for anchor in DDE.get_state():
 		assert anchor[1][n_basic+1] == 0.0 and anchor[2][n_basic+1] == 0.0
+
+
+@pytest.mark.parametrize("capacity", [16, 256])
+def test_sampling_in_one_launch_equals_separate_calls(twin, capacity):
+	"""integrate_samples(times) is the loop `[integrate(T) for T in times]` inside one launch: the same steps and the same
+	states, bit for bit — also when the ring (16 anchors here) fills up on the way, grows and the call is resumed, and with
+	per-member sample times."""
+	import sympy
+	from jitcdde_b200 import jitcdde, t, y
+	beta, tau = sympy.symbols("beta tau")
+	f = [beta*y(0, t-tau)/(1+y(0, t-tau)**10) - 0.1*y(0)]
+	N = 7
+	pars = np.stack([np.linspace(0.2, 0.3, N), np.linspace(8.0, 20.0, N)], axis=1)
+	times = 25.0 + 7.5*np.arange(1, 9)
+	per_member = times[None, :] + 0.1*np.arange(N)[:, None]
+
+	def fresh():
+		DDE = jitcdde(f, control_pars=[beta, tau], max_delay=20.0, n_members=N, verbose=False, verification=True, ring_capacity=capacity)
+		DDE.constant_past([1.0])
+		DDE.set_parameters(pars)
+		DDE.delays = pars[:, 1:2]
+		DDE.max_delay = 20.0
+		DDE.step_on_discontinuities()
+		return DDE
+
+	for sample_times, separate in ((times, lambda k: times[k]), (per_member, lambda k: per_member[:, k])):
+		one = fresh()
+		series = one.integrate_samples(sample_times)
+		many = fresh()
+		loop = np.stack([many.integrate(separate(k)) for k in range(len(times))])
+		assert series.shape == (len(times), N, 1)
+		assert np.array_equal(series, loop)
+		for a, b in zip(one.counters(), many.counters()):
+			assert np.array_equal(a, b)
+		assert np.array_equal(one.t, many.t) and np.array_equal(one.dt, many.dt)
+		if capacity == 16:
+			assert one._engine.ring_capacity > 16, "the small ring was meant to overflow"
+
+	single = jitcdde([0.25*y(0, t-15)/(1+y(0, t-15)**10) - 0.1*y(0)], verbose=False, verification=True)
+	single.constant_past([1.0])
+	single.step_on_discontinuities()
+	series = single.integrate_samples(single.t + np.arange(1, 6)*10.0)
+	assert series.shape == (5, 1)

@@ -12,11 +12,19 @@ deterministic grid β_i = 0.15+0.20·i/2499, τ_j = 10+15·j/3999 (10^7 members 
 members per GPU, weak scaling: contiguous member ranges per rank, no collective in the data path),
 past = constant 1, default integration parameters of the reference, per-member
 step_on_discontinuities (target τ_j), then the sampling loop `integrate(30 + 10·k)`.
-One bench STEP = one `integrate` call advancing every member by 10 time units (≈ 23 accepted
-steps per member). `value` = accepted steps of all members and ranks ÷ device time (CUDA events on the
-launching stream, max over ranks) with all inputs resident in HBM; `e2e` = the same loop through the
-public Python API with host buffers: per step the target time goes host→device and the states and
-per-member status come back device→host into pinned memory.
+One bench STEP = one sample: every member advances by 10 time units (≈ 23 accepted steps per member) and
+delivers its state at the sample time — what one `integrate(T)` call of the reference's sampling loop
+(examples/mackey_glass.py:76-78) does. Samples are issued `--samples-per-launch` at a time
+(`integrate_samples`: the same steps and states as separate calls, bit for bit, tests/). `value` =
+accepted steps of all members and ranks ÷ device time (CUDA events on the launching stream, max over
+ranks) with all inputs resident in HBM; `e2e` = the same loop through the public Python API with host
+buffers: per launch the sample times go host→device and the states of every sample come back
+device→host into pinned memory, the failed-member count at the end.
+
+The line also carries: `parity_check` (a random subsample of THIS production run against the CPU oracle),
+`configs` (the other BASELINE.json configurations at their named shapes, each with its own roofline
+object) and `network` (configs[3]: one delay-coupled system, node-partitioned over the N GPUs with the
+fused NVLink peer exchange).
 """
 
 import argparse
@@ -33,6 +41,7 @@ if ROOT not in sys.path:
 	sys.path.insert(0, ROOT)
 
 MEMBERS_PER_GPU = 1_250_000
+SAMPLES_PER_LAUNCH = 10
 ADVANCE = 10.0
 MAX_DELAY = 25.0
 BYTES_PER_STEP = 266      # algorithmic bytes per accepted step, SURVEY.md §8d / DESIGN.md
@@ -47,7 +56,8 @@ def config(members_per_gpu, world):
 		"members_per_gpu": members_per_gpu,
 		"members_total": members_per_gpu*world,
 		"sharding": "members dealt round-robin to the ranks, no data-path collective",
-		"step": f"integrate(): advance every member by {ADVANCE:g} time units",
+		"step": f"one sample: advance every member by {ADVANCE:g} time units and deliver its state (integrate(T) of the reference's sampling loop)",
+		"samples_per_launch": SAMPLES_PER_LAUNCH,
 		"integration_parameters": "reference defaults (atol 1e-10, rtol 1e-5)",
 		"discontinuities": "step_on_discontinuities, target tau_j per member",
 		"ring_capacity": 128,
@@ -81,6 +91,8 @@ class ClockSampler:
 			self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
 			self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
 			self.thread = threading.Thread(target=self._run, daemon=True)
+			if os.environ.get("BENCH_NO_CLOCK_THREAD"):
+				self._stop.set()
 			self.thread.start()
 		except Exception:
 			self.nv = None
@@ -188,15 +200,21 @@ def cpu_reference(steps, warmup, members_per_core, cores=None):
 	The reference's own C core (oracle/_ref/ref_mg_bench, the unmodified jitced_template.c rendered for
 	this system, reference-like flags) driven by the reference's Python control loop
 	(oracle/controller.py), one process per core, members dealt evenly. Returns
-	(steps/s, ms per step, cores, description). Falls back to the plain-C port of the oracle if the
-	reference module was not prebuilt.
+	(steps/s, ms per step, cores, description, kind). If the reference module was not prebuilt, the plain-C port
+	of the oracle is timed instead — announced on stderr and in `kind`.
 	"""
 	import multiprocessing as mp
 	from oracle import build_ref
 	from tests import systems
 	cores = cores or os.cpu_count()
 	if not build_ref.have_ref("ref_mg_bench"):
+		# never silently: the line then says kind "port" and why
+		print("bench.py: oracle/_ref/ref_mg_bench*.so is missing (built by __graft_entry__.build() where /root/reference exists); "
+			"timing the plain-C port of the oracle instead", file=sys.stderr, flush=True)
 		return cpu_port(steps, warmup, members_per_core*cores, cores) + ("port",)
+	# the parent loads the reference module too (the workers are forked from it): the process that prints the line is
+	# one that has the reference's compiled core mapped
+	build_ref.load_ref("ref_mg_bench")
 	pars = systems.mg_grid(members_per_core*cores)
 	chunks = [pars[c::cores] for c in range(cores)]
 	ctx = mp.get_context("fork")
@@ -218,7 +236,9 @@ def cpu_reference(steps, warmup, members_per_core, cores=None):
 		elapsed = time.perf_counter()-t0
 	finally:
 		for pool in pools:
-			pool.terminate()
+			pool.close()
+		for pool in pools:
+			pool.join()
 	sample = f"{members_per_core*cores} members of the same grid ({members_per_core} per core), {steps} steps of {ADVANCE:g} time units after {warmup} warm-up steps"
 	return total/elapsed, 1e3*elapsed/steps, cores, sample, "reference"
 
@@ -245,6 +265,47 @@ def cpu_port(steps, warmup, members, cores):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+def ncu_traffic():
+	"""DRAM bytes per launch of the dominant kernel from the committed ncu capture of this round (one launch of
+	SAMPLES_PER_LAUNCH samples of the bench workload), or None: it is a measurement made under ncu, not by this run."""
+	path = os.path.join(ROOT, "profiles", "ncu_full_r02_jdde_k_integrate.csv")
+	try:
+		values = {}
+		with open(path) as f:
+			for line in f:
+				name, unit, value = (line.rstrip("\n").split(",") + ["", ""])[:3]
+				if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+					values[name] = float(value)*{"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+		return int(values["dram__bytes_read.sum"]+values["dram__bytes_write.sum"]), os.path.relpath(path, ROOT)
+	except (OSError, KeyError, ValueError):
+		return None, None
+
+
+def parity_check(engine, pars, sample_times, last_states, picks=512, seed=7):
+	"""A random subsample of the members of THIS run (production build, FMA contraction) against the CPU oracle
+	(verification arithmetic) over the whole history of the run: accepted-step counts and the states at the last sample."""
+	from oracle import oracle
+	from tests import systems
+	rng = np.random.default_rng(seed)
+	N = len(pars)
+	pick = np.sort(rng.choice(N, min(picks, N), replace=False))
+	accepted = engine.get_counters()[0][pick]
+	lib = oracle.build(systems.program(systems.mackey_glass()))
+	past = (np.array([-1.0, 0.0]), np.ones((2, 1)), np.zeros((2, 1)))
+	ref = oracle.run_ensemble(lib, past, pars[pick], MAX_DELAY, 1, pars[pick, 1:2].copy(), np.asarray(sample_times, dtype=float), absolute_samples=True)
+	ours, theirs = last_states[pick, 0], ref["out"][-1, :, 0]
+	different = int(np.sum(accepted != ref["counters"][:, 0]))
+	same = accepted == ref["counters"][:, 0]
+	rel = np.abs(ours-theirs)/np.maximum(np.abs(theirs), 1e-300)
+	return {
+		"members": int(len(pick)), "samples": int(len(sample_times)), "horizon": float(sample_times[-1]),
+		"counts_identical": different == 0, "members_with_different_counts": different,
+		"accepted_steps_checked": int(ref["counters"][:, 0].sum()),
+		"max_rel": float(rel.max()), "max_rel_members_with_identical_counts": float(rel[same].max()) if same.any() else None,
+		"oracle": "oracle/dde_oracle.c (verification arithmetic, pinned to the reference core in tests/test_oracle.py); members with larger delays and gains are chaotic: rounding differences grow along the horizon",
+	}
+
+
 def gpu_arm(args):
 	import torch
 	import torch.distributed as dist
@@ -264,6 +325,7 @@ def gpu_arm(args):
 		dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
 	members = args.members
+	S = max(1, args.samples_per_launch)
 	# Weak scaling: every rank integrates `members` members. Members are dealt to the ranks round-robin
 	# (rank r takes r, r+world, … of the global grid), so every GPU sees the same mix of (β, τ) and hence of
 	# step sizes; contiguous blocks would give the ranks with larger β systematically more steps.
@@ -303,8 +365,8 @@ def gpu_arm(args):
 	# ---------------- device-resident loop: `value`
 	# After the discontinuity stepping member j stands at t = tau_j (10…25). All members are then sampled
 	# on the common time grid T_k = 30 + 10 k, as a user of the reference samples a trajectory
-	# (examples/mackey_glass.py:76-78). The only per-step input is the scalar T_k (8 bytes); the ensemble
-	# state (anchor rings, controller state) is resident in HBM.
+	# (examples/mackey_glass.py:76-78), S samples per launch. The only per-launch input are the S sample times; the
+	# ensemble state (anchor rings, controller state) and the sampled states (device buffer) are resident in HBM.
 	setup_start = time.perf_counter()
 	DDE = fresh()
 	torch.cuda.synchronize()
@@ -313,20 +375,35 @@ def gpu_arm(args):
 	stream = torch.cuda.current_stream()
 	engine.set_stream(stream.cuda_stream)
 	T0 = 30.0
-	k = 0
+	sample_times = []
+
+	def times_of(count):
+		k0 = len(sample_times)
+		times = T0+ADVANCE*np.arange(k0+1, k0+count+1)
+		sample_times.extend(times)
+		return times
+
+	def device_samples(count):
+		done = 0
+		while done < count:
+			n = min(S, count-done)
+			w = time.perf_counter()
+			engine.integrate_samples(times_of(n), fetch=False)
+			if os.environ.get("BENCH_DEBUG"):
+				w1 = time.perf_counter()
+				torch.cuda.synchronize()
+				print(f"[debug] launch of {n} samples: call {1e3*(w1-w):.2f} ms, done {1e3*(time.perf_counter()-w):.2f} ms", file=sys.stderr, flush=True)
+			done += n
+
 	clocks = ClockSampler(local_rank)      # started before the warm-up: NVML's first queries are slow
-	for _ in range(args.warmup):
-		k += 1
-		engine.integrate(T0+ADVANCE*k, fetch=False)
+	device_samples(args.warmup)
 	accepted_before = engine.sum_counters()[0]
 	launches_before = engine.launch_count
 	ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 	barrier()
 	clocks.mark_start()
 	ev0.record(stream)
-	for _ in range(args.steps):
-		k += 1
-		engine.integrate(T0+ADVANCE*k, fetch=False)
+	device_samples(args.steps)
 	ev1.record(stream)
 	clocks.sample_now()      # the host is ahead of the GPU here: the launches above are still running
 	barrier()
@@ -342,28 +419,33 @@ def gpu_arm(args):
 	value = total_accepted/(ms*1e-3)
 
 	# ---------------- end to end through the public API with host buffers: `e2e`
-	# per step: the target time goes host→device, the kernel runs, the states (N×8 B) come back device→host
-	# into pinned memory; the number of failed members (8 B) is read once at the end (the status array follows only
-	# if it is non-zero); all inside the timed region
-	# Sampling is pipelined as the public API offers it (integrate(..., wait=False) / wait_result / synchronize):
-	# while the kernel of sample k runs, the states of sample k-1 travel to the host and are read there.
-	outs = [pinned_empty((members, 1)), pinned_empty((members, 1))]
+	# per launch: the S sample times go host→device, the kernel runs and writes the states of every sample (S×N×8 B)
+	# into page-locked host memory; the number of failed members (8 B) is read once at the end (the status array follows
+	# only if it is non-zero); all inside the timed region. Sampling is pipelined as the public API offers it
+	# (integrate_samples(..., wait=False) / wait_result / synchronize): while the kernel of one launch runs, the states
+	# of the previous one are read on the host.
+	outs = [pinned_empty((S, members, 1)), pinned_empty((S, members, 1))]
 	for i in range(2):
-		k += 1
-		DDE.integrate(T0+ADVANCE*k, out=outs[i])
+		DDE.integrate_samples(times_of(S), out=outs[i])
 	accepted_before = engine.sum_counters()[0]
+	e2e_launches = []
+	left = args.steps
+	while left > 0:
+		e2e_launches.append(min(S, left))
+		left -= e2e_launches[-1]
 	barrier()
 	w0 = time.perf_counter()
 	ev0.record(stream)
 	checksum = 0.0
-	for i in range(args.steps):
-		k += 1
-		DDE.integrate(T0+ADVANCE*k, out=outs[i & 1], wait=False)   # queue: H2D target, kernel, D2H states
+	for i, n in enumerate(e2e_launches):
+		DDE.integrate_samples(times_of(n), out=outs[i & 1][:n], wait=False)   # queue: H2D sample times, kernel, states to the host
 		if i:
-			DDE.wait_result(1)                                       # the previous sample has arrived …
-			checksum += float(outs[(i-1) & 1][0, 0])                 # … and is read on the host
-	DDE.synchronize()                                                # last sample + failed-member count (8 B) + status check
-	checksum += float(outs[(args.steps-1) & 1][0, 0])
+			DDE.wait_result(1)                                                  # the previous launch has arrived …
+			checksum += float(outs[(i-1) & 1][e2e_launches[i-1]-1, 0, 0])       # … and is read on the host
+	DDE.synchronize()                                                           # last launch + failed-member count (8 B) + status check
+	last = len(e2e_launches)-1
+	last_states = outs[last & 1][e2e_launches[last]-1]
+	checksum += float(last_states[0, 0])
 	ev1.record(stream)
 	barrier()
 	e2e_ms = reduce_max(max(ev0.elapsed_time(ev1), 1e3*(time.perf_counter()-w0)))
@@ -373,23 +455,35 @@ def gpu_arm(args):
 	peak, peak_source = measured_peaks()
 	from jitcdde_b200._capi import measure_fp64_peak
 	fp64_peak = measure_fp64_peak(local_rank)      # FLOP/s, DFMA microbenchmark on this GPU (not in MEASURED_PEAKS.json)
-	# dominant kernel = jdde_k_integrate, one launch per step: algorithmic bytes of this rank's launches ÷ their duration
+	# dominant kernel = jdde_k_integrate, one launch per S samples: algorithmic bytes of this rank's launches ÷ their duration
 	achieved = (total_accepted/world*BYTES_PER_STEP)/(ms*1e-3)/1e9
+	traffic, traffic_source = ncu_traffic()
 	line = {
 		"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
 		"ms_per_step": ms/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-		"dtype": "f64", "data": "synthetic", "config": config(members, world),
+		"dtype": "f64", "data": "synthetic", "config": dict(config(members, world), samples_per_launch=S),
 		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(members*8),
-			"ms_per_step": e2e_ms/args.steps, "api": "DDE.integrate(T, out=pinned, wait=False) + wait_result(1) per step, synchronize() at the end"},
+			"ms_per_step": e2e_ms/args.steps, "api": "DDE.integrate_samples(times, out=pinned, wait=False) + wait_result(1) per launch, synchronize() at the end"},
 		"gpu_launches": int(launches),
 		"clocks": clocks.summary(),
-		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": TRAFFIC_PER_LAUNCH,
+		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": traffic,
+			"traffic_source": traffic_source and f"{traffic_source} (ncu capture of one launch of this workload, {SAMPLES_PER_LAUNCH} samples; not measured by this run)",
 			"kernel": "jdde_k_integrate", "algorithmic_bytes_per_accepted_step": BYTES_PER_STEP, "peak_source": peak_source,
 			"fp64_tflops_algorithmic": value/world*FLOPS_PER_STEP/1e12, "fp64_peak_tflops_measured": fp64_peak/1e12,
-			"fp64_frac": value/world*FLOPS_PER_STEP/fp64_peak},
+			"fp64_frac": value/world*FLOPS_PER_STEP/fp64_peak,
+			"limiter": "instruction issue and latency, not DRAM: the staged anchors cut real DRAM traffic to about half of the algorithmic bytes (see traffic), so `frac` is a fraction of the HBM ceiling of the ALGORITHM, which the kernel approaches from the latency side (ncu: profiles/README.md)"},
 		"accepted_steps_per_member_per_step": total_accepted/(members*world*args.steps),
 		"setup": {"seconds": setup_seconds, "what": "code generation, kernel image (cache hit or nvcc), engine creation, upload of past and parameters, step_on_discontinuities; not part of any timed region"},
 	}
+	if rank == 0 and not args.no_parity:
+		line["parity_check"] = parity_check(engine, pars, sample_times, np.array(last_states), picks=args.parity_members)
+	del outs
+	DDE._drop_engine()
+	if not args.no_extras:
+		import bench_configs
+		if world == 1:
+			line["configs"] = bench_configs.ensemble_legs(peak, quick=args.quick_extras)
+		line["network"] = bench_configs.network_leg(peak, local_rank, rank, world, nodes=args.network_nodes)
 	if rank == 0 and world == 1 and not args.no_cpu:
 		v, ms_cpu, cores, sample, kind = cpu_reference(args.cpu_steps, 1, args.cpu_members_per_core)
 		line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
@@ -400,10 +494,6 @@ def gpu_arm(args):
 		print(json.dumps(line), flush=True)
 	if world > 1:
 		dist.destroy_process_group()
-
-
-#: dram__bytes_read.sum + dram__bytes_write.sum of one jdde_k_integrate launch from the ncu capture under profiles/ (null until measured)
-TRAFFIC_PER_LAUNCH = 3651599704   # 2.664 GB read + 0.988 GB written, profiles/ncu_full_r01_final_jdde_k_integrate.csv (launch #14 of the bench)
 
 
 def reference_arm(args):
@@ -432,6 +522,12 @@ def main():
 	parser.add_argument("--cpu-members-per-core", type=int, default=512)
 	parser.add_argument("--cpu-steps", type=int, default=10)
 	parser.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+	parser.add_argument("--samples-per-launch", type=int, default=SAMPLES_PER_LAUNCH, help="samples issued per kernel launch (integrate_samples)")
+	parser.add_argument("--no-parity", action="store_true", help="skip the comparison of a subsample of the run with the CPU oracle")
+	parser.add_argument("--parity-members", type=int, default=512)
+	parser.add_argument("--no-extras", action="store_true", help="skip the legs of the other BASELINE.json configurations and of the network")
+	parser.add_argument("--quick-extras", action="store_true", help="the other configurations at a tenth of their size (smoke runs)")
+	parser.add_argument("--network-nodes", type=int, default=1_000_000)
 	args = parser.parse_args()
 	if args.warmup < 3:
 		args.warmup = 3

@@ -2073,9 +2073,9 @@ JD_FN void member_integrate(jdde_problem const & P, long long const m, double co
 	double * const result = out ? out+(size_t)m*n_out : nullptr;
 	size_t const result_stride = (size_t)P.n_members*n_out;                 /* between the samples of one member */
 	int s = n_steps != 0 && resume ? P.resume_index[m] : 0;
-	double target = 0.0;
-	if (s < n_stretches)
-		target = capped ? (resume ? P.resume_target[m] : M.cur_t + steps[s]) : steps[s];
+	double target = capped && resume ? P.resume_target[m] : 0.0;      /* (a member that had finished keeps its last target: it is the time of the output) */
+	if (s < n_stretches && !(capped && resume))
+		target = capped ? M.cur_t + steps[s] : steps[s];
 	/* sample times that need no step (the reference extrapolates or interpolates on the last segment, _jitcdde.py:833-834) */
 	while (!capped && s < n_stretches && !(M.cur_t < target))
 	{

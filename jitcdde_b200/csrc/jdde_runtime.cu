@@ -646,7 +646,10 @@ static int run_integrate(jdde_handle * h, const double * targets, size_t count, 
 		return fail(h, JDDE_E_INVALID, "sampling in one launch is not available for images with a group of lanes per member");
 	size_t const n_results = n_steps < 0 ? (size_t)-n_steps : 1;
 	size_t const result_count = n_results*(size_t)h->desc.n_members*(size_t)n_out;
-	double * const direct = n_steps <= 0 ? direct_alias(out_state) : nullptr;
+	/* A single sample per launch is written by the kernel straight into page-locked host memory. Several samples per launch
+	 * are not: lanes reach their samples at different times, so the 8-byte results would cross PCIe one by one; they go to
+	 * a device buffer and the copy engine brings them over while the next launch runs. */
+	double * const direct = n_steps == 0 ? direct_alias(out_state) : nullptr;
 	if (pipelined)
 	{
 		if (!out_state)

@@ -46,7 +46,7 @@ def _so_path(name):
 	return os.path.join(REF_DIR, name + sysconfig.get_config_var("EXT_SUFFIX"))
 
 
-def build_ref(program, name, n_basic=None, flavour="chain", flags=VERIFY_FLAGS, force=False, tangent_indices=()):
+def build_ref(program, name, n_basic=None, flavour="chain", flags=VERIFY_FLAGS, force=False, tangent_indices=(), definitions=""):
 	"""Render + compile; returns the path of the extension module."""
 	so = _so_path(name)
 	if os.path.exists(so) and not force:
@@ -77,7 +77,7 @@ def build_ref(program, name, n_basic=None, flavour="chain", flags=VERIFY_FLAGS, 
 	elif flavour == "literal":
 		sites = program.literal_sites
 		f_c = "\n".join(program.literal_f) + "\n"
-		defs = ""
+		defs = definitions      # e.g. an #include of csrc/jdde_math.h for right-hand sides written with its functions
 	else:
 		raise ValueError(flavour)
 

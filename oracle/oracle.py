@@ -259,12 +259,13 @@ class Trajectory:
 		self.lib.jo_raw_truncate(self._h, ctypes.c_double(time))
 
 
-def run_ensemble(lib, past, parameters, max_delay, disc_mode, disc_steps, sample_offsets, root_mode=1, per_member_past=False, keep_output=True, lyap=False, n_members=None, **integration_parameters):
+def run_ensemble(lib, past, parameters, max_delay, disc_mode, disc_steps, sample_offsets, root_mode=1, per_member_past=False, keep_output=True, lyap=False, n_members=None, absolute_samples=False, **integration_parameters):
 	"""
 	Run N independent members through past → discontinuity handling → sampling loop (jo_run_ensemble).
 	`past` = (times[k], states[k][n], diffs[k][n]) shared by all members, or with a leading member axis if
 	`per_member_past`. disc_mode: 0 none, 1 step_on_discontinuities(disc_steps[m]), 2 adjust_diff,
-	3 integrate_blindly(t + disc_steps[m][0], step = disc_steps[m][1]). With `lyap`, samples are taken with
+	3 integrate_blindly(t + disc_steps[m][0], step = disc_steps[m][1]). Samples are taken at t_after_disc + offset, or at
+	the given times themselves with `absolute_samples`. With `lyap`, samples are taken with
 	integrate_lyap. Returns dict(out, counters[N][3], status[N], t[N] [, lyaps, weights]).
 	"""
 	n, n_basic = lib.jo_n(), lib.jo_n_basic()
@@ -297,7 +298,7 @@ def run_ensemble(lib, past, parameters, max_delay, disc_mode, disc_steps, sample
 		ctypes.c_long(N), ctypes.c_int(k), _p(times), _p(states), _p(diffs), ctypes.c_int(int(per_member_past)),
 		_p(parameters) if parameters.size else None, ctypes.byref(P), ctypes.c_double(max_delay),
 		ctypes.c_int(disc_mode), ctypes.c_int(n_disc), _p(disc),
-		ctypes.c_int(len(offs)), _p(offs),
+		ctypes.c_int(-len(offs) if absolute_samples else len(offs)), _p(offs),
 		_p(out) if keep_output else None,
 		_p(lyaps) if lyap else None, _p(weights) if lyap else None,
 		counters.ctypes.data_as(ctypes.POINTER(ctypes.c_long)),

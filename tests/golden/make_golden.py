@@ -185,6 +185,55 @@ def golden_kuramoto():
 	save("kuramoto", **past_arrays(past), blind=blind, offsets=offsets, samples=samples, accepted=C.accepted, rejected=C.rejected)
 
 
+def network_graph(n=128, k=10, seed=11):
+	"""fixed in-degree random graph of BASELINE.json configs[3] at a size the reference core can take (one search cursor per
+	edge: 1280 call sites): tau ~ U(pi/5, 2pi), natural frequencies ~ U(0.8, 1.2), coupling c·q/k per edge"""
+	rng = np.random.default_rng(seed)
+	dst = np.repeat(np.arange(n, dtype=np.int64), k)
+	src = rng.integers(0, n, size=n*k)
+	tau = rng.uniform(np.pi/5, 2*np.pi, size=n*k)
+	return dict(n=n, src=src, dst=dst, edge_tau=tau, weight=42*0.05/k, omega=rng.uniform(0.8, 1.2, n), initial=rng.uniform(0, 2*np.pi, n))
+
+
+def golden_network():
+	"""
+	The structured network engine (jitcdde_network) against the REFERENCE'S C core: the same 128-node delay-coupled Kuramoto
+	network written out for the reference as it wants it — one `set_dy(i, …)` per node, one `anchors()` call per in-edge
+	(/root/reference/examples/kuramoto_network.py:50-62) — with the terms of a node in the order and association of the
+	engine (local term first, then the in-edges in input order, each `weight*coupling` added to the running sum), the
+	coupling function printed by the same code generator, sin from csrc/jdde_math.h. Driven by the reference's controller
+	restated in oracle/controller.py with the network engine's step limit (max_step = smallest delay).
+	"""
+	import types
+	import sympy
+	from jitcdde_b200 import _codegen
+	g = network_graph()
+	n, E = g["n"], len(g["src"])
+	net_program = _codegen.generate_network(lambda y, t, w: w, lambda yd, y: sympy.sin(yd-y), 1)
+	lines = []
+	for i in range(n):
+		edges = np.nonzero(g["dst"] == i)[0]      # input order within a node: what the CSR build of jitcdde_network keeps
+		terms = f"JDN_LOCAL(current_y({i}), t, par)"
+		for e in edges:
+			tau = repr(float(g["edge_tau"][e]))
+			terms += f" + {float(g['weight'])!r}*JDN_COUPLING(past_y(t-{tau}, {int(g['src'][e])}, anchors(t-{tau})), current_y({i}))"
+		lines.append(f"{{ double const par[1] = {{ {float(g['omega'][i])!r} }}; set_dy({i}, {terms}); }}")
+	program = types.SimpleNamespace(n=n, n_sites=E, param_names=[], literal_f=lines, literal_sites=E, body="")
+	definitions = f'#include "{os.path.join(ROOT, "jitcdde_b200", "csrc", "jdde_math.h")}"\n' + net_program.body
+	build_ref.build_ref(program, "ref_network", flavour="literal", definitions=definitions, force=True)
+	module = build_ref.load_ref("ref_network")
+	past = [(-1.0, g["initial"], np.zeros(n)), (0.0, g["initial"], np.zeros(n))]
+	core = module.dde_integrator([(a[0], np.array(a[1], dtype=float), np.array(a[2], dtype=float)) for a in past])
+	roots = roots_from(oracle.build(systems.program(systems.mackey_glass())))
+	max_delay, min_delay = float(np.max(g["edge_tau"])), float(np.min(g["edge_tau"]))
+	C = controller.Controller(core, max_delay, root_mode=1, roots=roots, rtol=0, atol=1e-5, max_step=min_delay, first_step=min(1.0, min_delay))
+	blind = C.integrate_blindly(max_delay, 0.1)
+	times = max_delay + np.arange(0.5, 8.5, 0.5)
+	samples = np.array([C.integrate(T) for T in times])
+	save("network", src=g["src"], dst=g["dst"], edge_tau=g["edge_tau"], weight=g["weight"], omega=g["omega"], initial=g["initial"],
+		blind_to=max_delay, blind=blind, times=times, samples=samples, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
+
+
 def golden_data_input():
 	"""the extended system and joined past that jitcdde_input hands to the core (reference: _jitcdde.py:1519-1659)"""
 	prog, past, max_delay = systems.data_input_program()
@@ -269,6 +318,6 @@ def golden_projected():
 if __name__ == "__main__":
 	assert build_ref.reference_available(), "run this where /root/reference exists"
 	makers = dict(roessler=golden_roessler, mg_ensemble=golden_mg_ensemble, neutral=golden_neutral, state_dependent=golden_state_dependent,
-		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected)
+		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected, network=golden_network)
 	for name in sys.argv[1:] or makers:      # optional arguments: only these fixtures
 		makers[name]()

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import sympy
 
-from tests.test_network import kuramoto_graph, run_network, run_symbolic
+from tests.test_network import kuramoto_graph, run_network, run_network_golden, run_symbolic
 
 pytestmark = pytest.mark.gpu
 
@@ -30,6 +30,28 @@ def test_network_engine_matches_symbolic_path_on_gpu():
 	np.testing.assert_allclose(nb, sb, rtol=1e-9)
 	np.testing.assert_allclose(ns, ss, rtol=1e-8)
 	assert (nc[0], nc[1]) == sc
+
+
+def test_network_engine_against_reference_core_on_gpu():
+	"""BASELINE.json configs[3] at the size the reference core can take (128 nodes, in-degree 10): the CUDA verification build of
+	the network engine reproduces the reference's C core bit for bit — identical step counts, identical states (golden:
+	tests/golden/network.npz, written by the reference core itself)."""
+	g, blind, samples, counters, t_end = run_network_golden()
+	assert np.array_equal(blind, g["blind"])
+	assert np.array_equal(samples, g["samples"])
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert t_end == float(g["final_t"])
+	# the production build (FMA contraction, CUDA's sin): identical counts, states to rounding (north_star: 1e-10)
+	from jitcdde_b200 import jitcdde_network
+	import sympy
+	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False)
+	net.set_integration_parameters(rtol=0, atol=1e-5)
+	net.constant_past(g["initial"], time=0.0)
+	net.integrate_blindly(float(g["blind_to"]), 0.1)
+	fast = np.array([net.integrate(T) for T in g["times"]])
+	np.testing.assert_allclose(fast, g["samples"], rtol=1e-10)
+	assert net.counters()[:2] == (int(g["accepted"]), int(g["rejected"]))
 
 
 @pytest.mark.parametrize("n", [100_000, 1_000_000])      # 10^6 nodes, 10^7 edges: BASELINE.json configs[3]

@@ -7,6 +7,8 @@ core (golden "kuramoto"). The two paths add the coupling terms in a different or
 agree to rounding, not bit for bit: states within 1e-9, identical step counts.
 """
 
+import os
+
 import numpy as np
 import pytest
 import sympy
@@ -72,6 +74,30 @@ def test_network_engine_matches_symbolic_path(twin):
 	np.testing.assert_allclose(ns, ss, rtol=1e-9)
 	assert (nc[0], nc[1]) == sc
 	assert abs(nt-st) < 1e-9
+
+
+def run_network_golden(**kw):
+	"""the 128-node network of tests/golden/network.npz (outputs of the REFERENCE'S C core, tests/golden/make_golden.py::golden_network)
+	on the network engine, verification build"""
+	from jitcdde_b200 import jitcdde_network
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "network.npz"))
+	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False, verification=True, **kw)
+	net.set_integration_parameters(rtol=0, atol=1e-5)
+	net.constant_past(g["initial"], time=0.0)
+	blind = net.integrate_blindly(float(g["blind_to"]), 0.1)
+	samples = np.array([net.integrate(T) for T in g["times"]])
+	return g, blind, samples, net.counters(), net.t
+
+
+def test_network_engine_against_reference_core(twin):
+	"""The reference's C core has integrated this network itself (one expression per node, one anchors() call per edge, as
+	examples/kuramoto_network.py:50-62 builds it): identical accepted and rejected step counts, identical bits of every state."""
+	g, blind, samples, counters, t_end = run_network_golden()
+	assert np.array_equal(blind, g["blind"])
+	assert np.array_equal(samples, g["samples"])
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert t_end == float(g["final_t"])
 
 
 def test_node_partition_exchange_protocol(twin):

@@ -65,7 +65,7 @@ class jitcdde_network:
 		self.verification = verification      # kernels without FMA contraction, bit-reproducible elementary functions (as for jitcdde)
 		self._image = _build.build_net_image(self._program, mode=_build.VERIFY if verification else _build.FAST)
 		self.ring_capacity = ring_capacity
-		self.max_ring_capacity = 1 << 16
+		self.max_ring_capacity = 1 << 14      # the anchor times of the ring are staged in shared memory (128 KB)
 
 		self.rank, self.world = 0, 1
 		try:
@@ -187,6 +187,13 @@ class jitcdde_network:
 		if self.verbose:
 			print(f"Anchor ring full; growing to {2*self._engine.ring_capacity} anchors.")
 		self._engine.grow_ring(2*self._engine.ring_capacity)
+		if self.world > 1 and self._exchange == "peer":
+			# every rank has grown at the same attempt: the new history replicas are mapped anew
+			import torch.distributed as dist
+			handles = [None]*self.world
+			dist.all_gather_object(handles, self._engine.exchange_handle())
+			self._engine.connect_peers(self.rank, self.world, handles)
+			dist.barrier()
 		return True
 
 	def _raise(self, status):

@@ -90,7 +90,11 @@ JDN_FN void lookup_edge(jdn_problem const & P, View const & V, double const h, l
 	long long const j = P.src[e];
 	double const tau = P.tau[e];
 	double const d1 = (V.t_cur+0.5*h)-tau, d2 = (V.t_cur+0.75*h)-tau, d3 = (V.t_cur+h)-tau;
-	if (d3 > V.t_cur)
+	/* A lookup reaches into the step under way iff the step is longer than the delay. Tested on h and tau themselves:
+	 * with h == tau (a step size that has saturated at max_step = smallest delay, or a blind step of that length)
+	 * (t+h)−tau lands one ulp above t in a few percent of the attempts, and the walk below then simply ends at the last
+	 * accepted anchor — an extrapolation by one ulp, not a lookup into the tentative anchor. */
+	if (h > tau)
 		pws = 1;
 	int ca = walk(V, P.cursor[e], d1);
 	scratch[3*e] = past_value(P, V, ca, j, d1);

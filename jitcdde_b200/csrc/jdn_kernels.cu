@@ -7,6 +7,7 @@
  * nodes: 26 blocks per SM, several waves); the per-node error contributions are max-reduced per block (warp
  * shuffles, then shared memory) and merged with one atomicMax per block.
  */
+#include <cooperative_groups.h>
 #include "jdn_engine.cuh"
 
 #ifndef JDN_BLOCK
@@ -137,6 +138,143 @@ extern "C" __global__ void jdn_k_exchange(jdn_problem const P)
 		C.p_bits = bits;
 	C.exchanged_buffer = buffer;
 	C.epoch++;
+}
+
+/*
+ * The persistent stepper: ONE cooperative launch runs up to `max_attempts` attempted steps — lookup phase (grid-stride
+ * over the in-edges), grid barrier, step phase (grid-stride over the owned nodes), grid barrier, controller (one
+ * thread), grid barrier — instead of five launches per attempt. A node's new (state, diff) pair goes straight into
+ * ring slot current+1 (the tentative anchor: no lookup can reach it, every delay being at least a step), so an accepted
+ * step only moves `current`: no staging buffer, no commit pass. With several GPUs the pair is stored into the same slot
+ * of every rank's history replica over NVLink while the rank still computes other nodes, block maxima of the error
+ * norm go to every rank's exchange header (system-scope atomicMax), and between step phase and controller thread 0 of
+ * block 0 tells every peer that this rank's part has been delivered (release increment) and waits until all peers have
+ * said the same — the only inter-GPU synchronisation of an attempt, 8 bytes per peer on the critical path.
+ * Grid barriers order the phases on this GPU (cooperative groups: release/acquire at GPU scope, cumulative with the
+ * system-scope release/acquire of the arrival counters). The controller state is read afresh after every barrier.
+ */
+extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
+jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, int const max_attempts)
+{
+	extern __shared__ double s_times[];      /* cap doubles */
+	__shared__ double s_max[JDN_BLOCK/32];
+	namespace cg = cooperative_groups;
+	cg::grid_group grid = cg::this_grid();
+	jdn_control & C = *P.ctrl;
+	long long const tid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	long long const stride = (long long)gridDim.x*blockDim.x;
+	jdn::pair * const own_hist = reinterpret_cast<jdn::pair *>(P.hist);
+	for (int attempt = 0; attempt < max_attempts; attempt++)
+	{
+		if (C.done)
+			break;      /* (every thread of every block sees the same value: written before the last grid barrier) */
+		jdn::View V = jdn::view_of(P);
+		double const h = C.h;
+		int const slot = (V.current+1) & V.mask;
+		int const buffer = (int)(C.epoch & 1);
+
+		/* lookup phase */
+		for (int k = threadIdx.x; k < P.cap; k += blockDim.x)
+			s_times[k] = P.times[k];
+		__syncthreads();
+		V.times = s_times;
+		int pws = 0;
+		for (long long e = tid; e < n_edges; e += stride)
+			jdn::lookup_edge(P, V, h, e, scratch, pws);
+		if (pws)
+			C.pws = 1;
+		grid.sync();
+
+		/* step phase */
+		double contribution = -1.0;
+		for (long long i = P.lo + tid; i < P.hi; i += stride)
+		{
+			jdn::pair staged;
+			double c = jdn::attempt_node(P, V, h, i, scratch, staged);
+			if (c >= 0.0)      /* skipped (0/0) or NaN: ignored by the reference's `x > p` test */
+				contribution = fmax(contribution, c);
+			size_t const where = jdn_pair_index(slot, i, P.n);
+			if (P.world > 1)
+				for (int r = 0; r < P.world; r++)
+					reinterpret_cast<jdn::pair *>(P.peer_hist[r])[where] = staged;
+			else
+				own_hist[where] = staged;
+		}
+		for (int o = 16; o > 0; o >>= 1)
+			contribution = fmax(contribution, __shfl_down_sync(0xffffffffu, contribution, o));
+		if ((threadIdx.x & 31) == 0)
+			s_max[threadIdx.x >> 5] = contribution;
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			double m = s_max[0];
+			for (int w = 1; w < JDN_BLOCK/32; w++)
+				m = fmax(m, s_max[w]);
+			if (m > 0.0)
+			{
+				if (P.world > 1)
+					for (int r = 0; r < P.world; r++)
+						atomicMax_system(&P.peers[r]->p_bits[buffer], (unsigned long long)__double_as_longlong(m));
+				else
+					atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(m));
+			}
+		}
+		__syncthreads();      /* s_max is reused in the next attempt */
+		grid.sync();
+
+		/* exchange barrier between the GPUs, then the controller */
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+		{
+			bool arrived_all = true;
+			if (P.world > 1)
+			{
+				if (C.pws)
+					for (int r = 0; r < P.world; r++)
+						atomicMax_system(&P.peers[r]->p_bits[buffer], JDN_PWS_SENTINEL);
+				__threadfence_system();
+				for (int r = 0; r < P.world; r++)
+					if (r != P.rank)
+						asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(&P.peers[r]->arrived), "l"(1ull) : "memory");
+				jdn_exchange * const own = P.peers[P.rank];
+				unsigned long long const expected = (C.epoch+1)*(unsigned long long)(P.world-1);
+				unsigned long long start, now, arrived;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
+				for (;;)
+				{
+					asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(arrived) : "l"(&own->arrived) : "memory");
+					if (arrived >= expected)
+						break;
+					asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+					if (now-start > 20000000000ull)      /* a peer that does not arrive within 20 s ends the integration instead of hanging the device */
+					{
+						C.exchange_failed = 1;
+						C.status = JDDE_STATUS_NONFINITE;
+						C.done = 1;
+						arrived_all = false;
+						break;
+					}
+					__nanosleep(100);
+				}
+				if (arrived_all)
+				{
+					unsigned long long const bits = atomicExch_system(&own->p_bits[buffer], 0ull);
+					if (bits == JDN_PWS_SENTINEL)
+					{
+						C.pws = 1;
+						C.p_bits = 0;
+					}
+					else
+						C.p_bits = bits;
+					C.exchanged_buffer = buffer;
+					C.epoch++;
+				}
+			}
+			if (arrived_all)
+				jdn::control(P);
+			__threadfence();
+		}
+		grid.sync();
+	}
 }
 
 extern "C" __global__ void jdn_k_control(jdn_problem const P)

@@ -1,8 +1,10 @@
 /*
  * jdn_runtime.cu — host side of the network engine (jdde_net_* in include/jitcdde_b200.h); part of
- * libjitcdde_b200.so. Owns the device memory of one system (layout: jdn_abi.h), loads the kernel image and
- * launches  attempt → [anchor exchange between ranks, done by the caller] → control → commit  per attempted
- * step; the controller runs on the device, the host polls a flag every few attempts. No numerical code here.
+ * libjitcdde_b200.so. Owns the device memory of one system (layout: jdn_abi.h), loads the kernel image and runs the
+ * integration calls: by default as cooperative launches of the persistent stepper jdn_k_run (hundreds of attempted steps
+ * per launch, exchange between the GPUs included); the per-attempt kernels  lookup → attempt → [exchange] → control →
+ * commit  remain for callers that exchange the anchors themselves (NCCL) and for comparison (JITCDDE_B200_NET_PERSISTENT=0).
+ * The controller runs on the device, the host polls a flag per launch. No numerical code here.
  */
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -14,17 +16,23 @@
 
 #include "jdn_abi.h"
 
+#define JDN_MAX_RING_CAPACITY 16384
+
 struct jdde_net
 {
 	jdde_net_desc desc{};
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	cudaLibrary_t lib = nullptr;
-	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr, k_regrow = nullptr;
+	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr, k_regrow = nullptr, k_run = nullptr;
 	/* peer exchange: this rank's buffer (mapped by the peers through CUDA IPC), the peers' buffers mapped here */
 	jdn_exchange * exchange = nullptr;
-	std::vector<void *> mapped_peers;
+	std::vector<void *> mapped_peers, mapped_hist;
 	jdn_exchange ** d_peers = nullptr;
+	double ** d_peer_hist = nullptr;          /* persistent stepper: the ranks' history replicas (own entry: P.hist) */
+	int peer_rank = 0, peer_world = 1;
+	bool persistent = true;                   /* jdn_k_run (one cooperative launch per batch of attempts) instead of five kernels per attempt */
+	int run_grid = 0;                         /* co-resident blocks of jdn_k_run */
 	/* `poll_every` attempts (lookup, step, [exchange], control, commit: 4–5 launches each) captured once as a CUDA graph and
 	 * replayed: small networks are bound by launch gaps, not by the kernels (10^5 nodes: 45 µs of kernels per 70 µs attempt) */
 	cudaGraphExec_t batch = nullptr;
@@ -107,6 +115,8 @@ int jdde_net_create(const jdde_net_desc * d, jdde_net ** out)
 		return nfail(nullptr, JDDE_E_INVALID, "invalid descriptor");
 	if (d->ring_capacity < 4 || (d->ring_capacity & (d->ring_capacity-1)))
 		return nfail(nullptr, JDDE_E_INVALID, "ring_capacity must be a power of two >= 4");
+	if (d->ring_capacity > JDN_MAX_RING_CAPACITY)
+		return nfail(nullptr, JDDE_E_INVALID, "ring_capacity above 16384 (the anchor times of the ring are staged in shared memory: 128 KB)");
 	int count = 0;
 	cudaError_t e = cudaGetDeviceCount(&count);
 	if (e != cudaSuccess || count < 1)
@@ -148,6 +158,7 @@ int jdde_net_destroy(jdde_net * h)
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->batch) cudaGraphExecDestroy(h->batch);
 	for (void * p : h->mapped_peers) cudaIpcCloseMemHandle(p);
+	for (void * p : h->mapped_hist) cudaIpcCloseMemHandle(p);
 	for (void * p : h->allocations) cudaFree(p);
 	if (h->lib) cudaLibraryUnload(h->lib);
 	if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -186,6 +197,21 @@ int jdde_net_load_image(jdde_net * h, const void * image, size_t len)
 	{
 		h->k_exchange = nullptr;
 		(void)cudaGetLastError();
+	}
+	if (cudaLibraryGetKernel(&h->k_run, h->lib, "jdn_k_run") != cudaSuccess)
+	{
+		h->k_run = nullptr;
+		(void)cudaGetLastError();
+	}
+	h->run_grid = 0;
+	const char * const choice = getenv("JITCDDE_B200_NET_PERSISTENT");
+	h->persistent = h->k_run && !(choice && choice[0] == '0');
+	/* the bracket search keeps the anchor times in shared memory: 8 bytes per ring slot */
+	if ((size_t)h->P.cap*sizeof(double) > 48*1024)
+	{
+		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->P.cap*sizeof(double))));
+		if (h->k_run)
+			JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->P.cap*sizeof(double))));
 	}
 	return JDDE_OK;
 }
@@ -383,12 +409,50 @@ static int launch_batch(jdde_net * h)
 	return JDDE_OK;
 }
 
+/* one cooperative launch of the persistent stepper: up to `attempts` attempted steps on the device */
+static int launch_run(jdde_net * h, int attempts)
+{
+	int rc;
+	if ((rc = nready_run(h))) return rc;
+	size_t const smem = (size_t)h->P.cap*sizeof(double);
+	if (!h->run_grid)
+	{
+		int per_sm = 0, sms = 0;
+		JN_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)h->k_run, h->block, smem));
+		JN_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->desc.device));
+		if (per_sm < 1) return nfail(h, JDDE_E_CUDA, "jdn_k_run does not fit an SM");
+		long long const work = h->desc.n_edges > h->desc.hi-h->desc.lo ? h->desc.n_edges : h->desc.hi-h->desc.lo;
+		long long const needed = (work + h->block - 1)/h->block;
+		long long const resident = (long long)per_sm*sms;
+		h->run_grid = (int)(needed < resident ? (needed ? needed : 1) : resident);
+	}
+	long long E = h->desc.n_edges;
+	void * args[] = { &h->P, &h->scratch, &E, &attempts };
+	cudaLaunchConfig_t config{};
+	config.gridDim = dim3((unsigned)h->run_grid);
+	config.blockDim = dim3((unsigned)h->block);
+	config.dynamicSmemBytes = smem;
+	config.stream = h->stream;
+	cudaLaunchAttribute attribute{};
+	attribute.id = cudaLaunchAttributeCooperative;
+	attribute.val.cooperative = 1;
+	config.attrs = &attribute;
+	config.numAttrs = 1;
+	JN_CUDA(h, cudaLaunchKernelExC(&config, (const void *)h->k_run, args));
+	h->launches++;
+	return JDDE_OK;
+}
+
 static int run_until_done(jdde_net * h)
 {
 	for (;;)
 	{
 		int rc;
-		if ((rc = launch_batch(h))) return rc;
+		if (h->persistent && (h->P.world <= 1 || h->P.peer_hist))
+		{
+			if ((rc = launch_run(h, h->poll_every*32))) return rc;
+		}
+		else if ((rc = launch_batch(h))) return rc;
 		int32_t done = 0;
 		if ((rc = jdde_net_poll(h, &done, nullptr, nullptr))) return rc;
 		if (done) return JDDE_OK;
@@ -437,8 +501,16 @@ int jdde_net_grow_ring(jdde_net * h, int32_t new_capacity)
 	if (rc) return rc;
 	if (new_capacity <= h->P.cap || (new_capacity & (new_capacity-1)))
 		return nfail(h, JDDE_E_INVALID, "new capacity must be a larger power of two");
+	if (new_capacity > JDN_MAX_RING_CAPACITY)
+		return nfail(h, JDDE_E_NOMEM, "ring capacity above 16384 (the anchor times of the ring are staged in shared memory)");
 	if ((size_t)new_capacity*sizeof(double) > 48*1024)
+	{
 		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double))));
+		if (h->k_run)
+			JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double))));
+	}
+	h->run_grid = 0;
+	h->P.peer_hist = nullptr;      /* the peers' mappings of the old history are void: jdde_net_connect_peers again (every rank grows at the same attempt) */
 	double * new_times = nullptr, * new_hist = nullptr;
 	if ((rc = nalloc(h, &new_times, (size_t)new_capacity))) return rc;
 	if ((rc = nalloc(h, &new_hist, 2*(size_t)new_capacity*(size_t)h->desc.n))) return rc;
@@ -505,7 +577,7 @@ int jdde_net_exchange_handle(jdde_net * h, void * handle, size_t handle_bytes)
 {
 	int rc = nready(h);
 	if (rc) return rc;
-	if (!handle || handle_bytes < sizeof(cudaIpcMemHandle_t)) return nfail(h, JDDE_E_INVALID, "handle buffer too small (needs 64 bytes)");
+	if (!handle || handle_bytes < sizeof(cudaIpcMemHandle_t)) return nfail(h, JDDE_E_INVALID, "handle buffer too small (needs 64 bytes, 128 with the history replica)");
 	if (!h->exchange)
 	{
 		size_t const bytes = sizeof(jdn_exchange) + 2*2*(size_t)h->desc.n*sizeof(double);
@@ -520,9 +592,18 @@ int jdde_net_exchange_handle(jdde_net * h, void * handle, size_t handle_bytes)
 	JN_CUDA(h, cudaIpcGetMemHandle(&ipc, h->exchange));
 	memset(handle, 0, handle_bytes);
 	memcpy(handle, &ipc, sizeof ipc);
+	if (handle_bytes >= 2*sizeof(cudaIpcMemHandle_t))
+	{
+		/* second handle: this rank's history replica, into which the peers' persistent steppers store their nodes' anchors */
+		JN_CUDA(h, cudaStreamSynchronize(h->stream));
+		JN_CUDA(h, cudaIpcGetMemHandle(&ipc, h->P.hist));
+		memcpy((char *)handle + sizeof ipc, &ipc, sizeof ipc);
+	}
 	return JDDE_OK;
 }
 
+/* May be called again (after jdde_net_grow_ring, whose new history the peers have to map anew): the exchange buffers stay
+ * mapped, the history replicas are mapped afresh. */
 int jdde_net_connect_peers(jdde_net * h, int32_t rank, int32_t world, const void * handles, size_t handle_bytes)
 {
 	int rc = nready(h);
@@ -531,25 +612,53 @@ int jdde_net_connect_peers(jdde_net * h, int32_t rank, int32_t world, const void
 		return nfail(h, JDDE_E_INVALID, "invalid rank, world or handles");
 	if (!h->exchange) return nfail(h, JDDE_E_INVALID, "call jdde_net_exchange_handle first");
 	if (!h->k_exchange) return nfail(h, JDDE_E_IMAGE, "image lacks kernel jdn_k_exchange");
-	if (h->P.world > 1) return nfail(h, JDDE_E_INVALID, "peers already connected");
-	std::vector<jdn_exchange *> peers((size_t)world, nullptr);
-	for (int r = 0; r < world; r++)
-	{
-		if (r == rank)
-		{
-			peers[r] = h->exchange;
-			continue;
-		}
-		cudaIpcMemHandle_t ipc;
-		memcpy(&ipc, (const char *)handles + (size_t)r*handle_bytes, sizeof ipc);
-		void * q = nullptr;
-		JN_CUDA(h, cudaIpcOpenMemHandle(&q, ipc, cudaIpcMemLazyEnablePeerAccess));
-		h->mapped_peers.push_back(q);
-		peers[r] = static_cast<jdn_exchange *>(q);
-	}
-	if ((rc = nalloc(h, &h->d_peers, (size_t)world))) return rc;
-	JN_CUDA(h, cudaMemcpy(h->d_peers, peers.data(), (size_t)world*sizeof(jdn_exchange *), cudaMemcpyHostToDevice));
+	if (h->P.world > 1 && (h->P.world != world || h->P.rank != rank)) return nfail(h, JDDE_E_INVALID, "peers already connected with another rank or world size");
 	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	bool const first_time = h->P.world <= 1;
+	if (first_time)
+	{
+		std::vector<jdn_exchange *> peers((size_t)world, nullptr);
+		for (int r = 0; r < world; r++)
+		{
+			if (r == rank)
+			{
+				peers[r] = h->exchange;
+				continue;
+			}
+			cudaIpcMemHandle_t ipc;
+			memcpy(&ipc, (const char *)handles + (size_t)r*handle_bytes, sizeof ipc);
+			void * q = nullptr;
+			JN_CUDA(h, cudaIpcOpenMemHandle(&q, ipc, cudaIpcMemLazyEnablePeerAccess));
+			h->mapped_peers.push_back(q);
+			peers[r] = static_cast<jdn_exchange *>(q);
+		}
+		if ((rc = nalloc(h, &h->d_peers, (size_t)world))) return rc;
+		JN_CUDA(h, cudaMemcpy(h->d_peers, peers.data(), (size_t)world*sizeof(jdn_exchange *), cudaMemcpyHostToDevice));
+	}
+	h->P.peer_hist = nullptr;
+	for (void * q : h->mapped_hist) cudaIpcCloseMemHandle(q);
+	h->mapped_hist.clear();
+	if (handle_bytes >= 2*sizeof(cudaIpcMemHandle_t) && h->persistent)
+	{
+		std::vector<double *> replicas((size_t)world, nullptr);
+		for (int r = 0; r < world; r++)
+		{
+			if (r == rank)
+			{
+				replicas[r] = h->P.hist;
+				continue;
+			}
+			cudaIpcMemHandle_t ipc;
+			memcpy(&ipc, (const char *)handles + (size_t)r*handle_bytes + sizeof ipc, sizeof ipc);
+			void * q = nullptr;
+			JN_CUDA(h, cudaIpcOpenMemHandle(&q, ipc, cudaIpcMemLazyEnablePeerAccess));
+			h->mapped_hist.push_back(q);
+			replicas[r] = static_cast<double *>(q);
+		}
+		if (!h->d_peer_hist && (rc = nalloc(h, &h->d_peer_hist, (size_t)world))) return rc;
+		JN_CUDA(h, cudaMemcpy(h->d_peer_hist, replicas.data(), (size_t)world*sizeof(double *), cudaMemcpyHostToDevice));
+		h->P.peer_hist = h->d_peer_hist;
+	}
 	drop_batch(h);
 	h->P.peers = h->d_peers;
 	h->P.rank = rank;

@@ -69,7 +69,8 @@ def test_large_network_properties(n):
 
 
 def _peer_worker(rank, world, port, queue, n, ring_capacity):
-	"""one rank of a two-process run; with a single visible GPU both ranks share it (CUDA IPC works within a device, too)"""
+	"""one rank of a two-process run: rank r on device r when the box has two GPUs (stores and arrival counters then cross
+	NVLink); with a single visible GPU both ranks share it (CUDA IPC works within a device, too)"""
 	import os
 	import warnings
 	warnings.simplefilter("ignore")
@@ -87,7 +88,7 @@ def _peer_worker(rank, world, port, queue, n, ring_capacity):
 	net.constant_past(g["initial"], time=0.0)
 	blind = net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1)
 	out = net.integrate(net.t+2.0)
-	queue.put((rank, blind, out, net.counters()))
+	queue.put((rank, blind, out, net.counters(), device, str(getattr(torch.cuda.get_device_properties(device), "uuid", device))))
 	dist.barrier()
 	dist.destroy_process_group()
 
@@ -131,10 +132,16 @@ def test_fused_peer_exchange_equals_one_gpu(ring_capacity):
 	for p in procs:
 		p.join(timeout=120)
 		assert p.exitcode == 0
-	for rank, peer_blind, peer_out, peer_counters in results:
+	for rank, peer_blind, peer_out, peer_counters, device, uuid in results:
 		assert np.array_equal(peer_blind, blind), rank
 		assert np.array_equal(peer_out, out), rank
 		assert tuple(peer_counters) == tuple(counters), rank
+	import torch
+	devices = sorted({(r[4], r[5]) for r in results})
+	print(f"fused peer exchange ran on device(s) {[d[0] for d in devices]} of {torch.cuda.device_count()} visible")
+	if torch.cuda.device_count() >= 2:
+		# two GPUs on the box: the two ranks MUST have been on different devices (peer stores over NVLink, system-scope atomics)
+		assert len(devices) == 2, devices
 
 
 def test_ring_growth_on_gpu():

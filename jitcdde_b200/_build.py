@@ -238,7 +238,8 @@ def build_net_image(program, block=256, mode=FAST, force=False, verbose=False):
 	for name in ("jdn_engine.cuh", "jdn_kernels.cu", "jdn_abi.h", "jdde_abi.h", "jdde_math.h"):
 		with open(os.path.join(CSRC, name), "rb") as f:
 			h.update(f.read())
-	tag = hashlib.sha256(repr((program.key, block, mode, h.hexdigest())).encode()).hexdigest()[:20]
+	extra = tuple(os.environ.get("JITCDDE_B200_NET_FLAGS", "").split())      # experiments: e.g. -DJDN_RUN_MIN_BLOCKS=6
+	tag = hashlib.sha256(repr((program.key, block, mode, extra, h.hexdigest())).encode()).hexdigest()[:20]
 	path = os.path.join(CACHE, f"jdn_{tag}.cubin")
 	if os.path.exists(path) and not force:
 		return path
@@ -251,7 +252,7 @@ def build_net_image(program, block=256, mode=FAST, force=False, verbose=False):
 		mode_flags = ["-DJD_FAST=1"]
 	else:
 		raise ValueError(mode)
-	cmd = [nvcc(), "-cubin", "-O3", "-std=c++17", "-lineinfo", *ARCH, *mode_flags, f'-DJDN_RHS_FILE="{rhs}"', f"-DJDN_BLOCK={block}",
+	cmd = [nvcc(), "-cubin", "-O3", "-std=c++17", "-lineinfo", *ARCH, *mode_flags, *extra, f'-DJDN_RHS_FILE="{rhs}"', f"-DJDN_BLOCK={block}",
 		os.path.join(CSRC, "jdn_kernels.cu"), "-o", path + ".tmp"]
 	if verbose:
 		print(" ".join(cmd))

@@ -133,6 +133,7 @@ static inline double * jdn_exchange_stage(jdn_exchange * x, int buffer, long lon
 typedef struct jdn_image_desc_t
 {
 	int magic, abi, n_node_params, block;
+	int run_smem_bytes;      /* jdn_k_run: dynamic shared memory per block in addition to the 8·capacity bytes of anchor times */
 } jdn_image_desc_t;
 
 #endif

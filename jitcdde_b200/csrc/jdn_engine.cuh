@@ -85,7 +85,7 @@ JDN_FN double past_value(jdn_problem const & P, View const & V, int const ca, lo
  * history rows, so they share their gathers. Results go to scratch[3e…3e+2]; the edge's cursor is updated.
  * Edge-parallel: 10^7 independent threads for a 10^6-node network of in-degree 10.
  */
-JDN_FN void lookup_edge(jdn_problem const & P, View const & V, double const h, long long const e, double * const scratch, int & pws)
+JDN_FN void lookup_edge_values(jdn_problem const & P, View const & V, double const h, long long const e, double & v1, double & v2, double & v3, int & pws)
 {
 	long long const j = P.src[e];
 	double const tau = P.tau[e];
@@ -97,12 +97,17 @@ JDN_FN void lookup_edge(jdn_problem const & P, View const & V, double const h, l
 	if (h > tau)
 		pws = 1;
 	int ca = walk(V, P.cursor[e], d1);
-	scratch[3*e] = past_value(P, V, ca, j, d1);
+	v1 = past_value(P, V, ca, j, d1);
 	ca = walk(V, ca, d2);
-	scratch[3*e+1] = past_value(P, V, ca, j, d2);
+	v2 = past_value(P, V, ca, j, d2);
 	ca = walk(V, ca, d3);
-	scratch[3*e+2] = past_value(P, V, ca, j, d3);
+	v3 = past_value(P, V, ca, j, d3);
 	P.cursor[e] = ca;
+}
+
+JDN_FN void lookup_edge(jdn_problem const & P, View const & V, double const h, long long const e, double * const scratch, int & pws)
+{
+	lookup_edge_values(P, V, h, e, scratch[3*e], scratch[3*e+1], scratch[3*e+2], pws);
 }
 
 /*

@@ -14,7 +14,16 @@
 #define JDN_BLOCK 256
 #endif
 
-extern "C" __device__ const jdn_image_desc_t jdn_image_desc = { JDN_IMAGE_MAGIC, JDDE_ABI_VERSION, JDN_NPARAMS, JDN_BLOCK };
+#ifndef JDN_TILE_NODES
+#define JDN_TILE_NODES 64
+#endif
+#ifndef JDN_TILE_EDGES
+#define JDN_TILE_EDGES 1024
+#endif
+/* dynamic shared memory of jdn_k_run after the anchor times: values [3][JDN_TILE_EDGES], row offsets, stage states, block maxima, node of each edge */
+#define JDN_RUN_SMEM_BYTES (3*JDN_TILE_EDGES*8 + (JDN_TILE_NODES+1)*8 + JDN_TILE_NODES*8 + 32*8 + JDN_TILE_EDGES)
+
+extern "C" __device__ const jdn_image_desc_t jdn_image_desc = { JDN_IMAGE_MAGIC, JDDE_ABI_VERSION, JDN_NPARAMS, JDN_BLOCK, JDN_RUN_SMEM_BYTES };
 
 /* lookup phase: one thread per edge of the owned nodes */
 extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
@@ -141,85 +150,198 @@ extern "C" __global__ void jdn_k_exchange(jdn_problem const P)
 }
 
 /*
- * The persistent stepper: ONE cooperative launch runs up to `max_attempts` attempted steps — lookup phase (grid-stride
- * over the in-edges), grid barrier, step phase (grid-stride over the owned nodes), grid barrier, controller (one
- * thread), grid barrier — instead of five launches per attempt. A node's new (state, diff) pair goes straight into
- * ring slot current+1 (the tentative anchor: no lookup can reach it, every delay being at least a step), so an accepted
- * step only moves `current`: no staging buffer, no commit pass. With several GPUs the pair is stored into the same slot
- * of every rank's history replica over NVLink while the rank still computes other nodes, block maxima of the error
- * norm go to every rank's exchange header (system-scope atomicMax), and between step phase and controller thread 0 of
- * block 0 tells every peer that this rank's part has been delivered (release increment) and waits until all peers have
- * said the same — the only inter-GPU synchronisation of an attempt, 8 bytes per peer on the critical path.
- * Grid barriers order the phases on this GPU (cooperative groups: release/acquire at GPU scope, cumulative with the
- * system-scope release/acquire of the arrival counters). The controller state is read afresh after every barrier.
+ * The persistent stepper: ONE cooperative launch runs up to `max_attempts` attempted steps instead of five launches
+ * per attempt, and an attempted step is ONE pass over the network.
+ *
+ * A block takes tiles of JDN_TILE_NODES consecutive nodes. For a tile all threads first interpolate the delayed source
+ * states of the tile's in-edges at the three stage times (one thread per edge: the scattered reads of the history, the
+ * part that HBM bounds) — into SHARED memory, not into a scratch array in global memory; then, stage by stage, every
+ * edge thread turns its value into its term weight·coupling(·, y_stage of its node) and one thread per node adds the
+ * terms of its node in the order of the edge list (the reference's order) and forms the next stage state. Seven block
+ * barriers per tile, no grid barrier between lookup and step phase, 48 bytes per edge less traffic and one pass less
+ * over the edge arrays than the two-kernel version. (A tile with more than JDN_TILE_EDGES in-edges keeps its values in
+ * the global scratch array.)
+ *
+ * A node's new (state, diff) pair goes straight into ring slot current+1 (the tentative anchor: no lookup can reach it,
+ * every delay being at least a step), so an accepted step only moves `current`: no staging buffer, no commit pass. With
+ * several GPUs the pair is stored into the same slot of every rank's history replica over NVLink while the rank still
+ * computes other tiles, block maxima of the error norm go to every rank's exchange header (system-scope atomicMax),
+ * and after a grid barrier thread 0 of block 0 tells every peer that this rank's part has been delivered (release
+ * increment) and waits until all peers have said the same — the only inter-GPU synchronisation of an attempt, 8 bytes
+ * per peer on the critical path — and runs the controller. A second grid barrier publishes its decision.
+ * Grid barriers (cooperative groups: release/acquire at GPU scope) are cumulative with the system-scope release/acquire
+ * of the arrival counters. The controller state is read afresh after every barrier.
  */
-extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
+#if JDN_TILE_NODES > JDN_BLOCK-1 || JDN_TILE_NODES > 256
+#error "a tile needs one thread per node (and one more for the row offsets) and its node indices fit a byte"
+#endif
+
+#ifndef JDN_RUN_MIN_BLOCKS
+#define JDN_RUN_MIN_BLOCKS 4
+#endif
+
+extern "C" __global__ void __launch_bounds__(JDN_BLOCK, JDN_RUN_MIN_BLOCKS)
 jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, int const max_attempts)
 {
-	extern __shared__ double s_times[];      /* cap doubles */
-	__shared__ double s_max[JDN_BLOCK/32];
+	extern __shared__ double s_times[];                /* cap doubles, then: */
+	double * const s_value = s_times+P.cap;            /* per edge of the tile: delayed value, then term, of stage 0, 1, 2 */
+	long long * const s_row = reinterpret_cast<long long *>(s_value+3*JDN_TILE_EDGES);     /* [JDN_TILE_NODES+1] */
+	double * const s_y = reinterpret_cast<double *>(s_row+JDN_TILE_NODES+1);               /* stage state of the tile's nodes */
+	double * const s_max = s_y+JDN_TILE_NODES;         /* [32] block reduction of the error norm */
+	unsigned char * const s_node = reinterpret_cast<unsigned char *>(s_max+32);            /* node of the edge within the tile */
 	namespace cg = cooperative_groups;
 	cg::grid_group grid = cg::this_grid();
 	jdn_control & C = *P.ctrl;
-	long long const tid = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-	long long const stride = (long long)gridDim.x*blockDim.x;
 	jdn::pair * const own_hist = reinterpret_cast<jdn::pair *>(P.hist);
+	long long const owned = P.hi-P.lo;
+	long long const n_tiles = (owned + JDN_TILE_NODES-1)/JDN_TILE_NODES;
 	for (int attempt = 0; attempt < max_attempts; attempt++)
 	{
 		if (C.done)
 			break;      /* (every thread of every block sees the same value: written before the last grid barrier) */
 		jdn::View V = jdn::view_of(P);
 		double const h = C.h;
+		double const atol = C.P.atol, rtol = C.P.rtol;
 		int const slot = (V.current+1) & V.mask;
 		int const buffer = (int)(C.epoch & 1);
-
-		/* lookup phase */
 		for (int k = threadIdx.x; k < P.cap; k += blockDim.x)
 			s_times[k] = P.times[k];
 		__syncthreads();
 		V.times = s_times;
+		double const t1 = V.t_cur+0.5*h, t2 = V.t_cur+0.75*h, t3 = V.t_cur+h;
 		int pws = 0;
-		for (long long e = tid; e < n_edges; e += stride)
-			jdn::lookup_edge(P, V, h, e, scratch, pws);
+		double block_contribution = -1.0;      /* (threads 0 … JDN_TILE_NODES−1: their nodes) */
+
+		for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+		{
+			long long const row0 = tile*JDN_TILE_NODES;
+			int const nn = (int)(owned-row0 < JDN_TILE_NODES ? owned-row0 : JDN_TILE_NODES);
+			if (threadIdx.x <= nn)
+				s_row[threadIdx.x] = P.row_ptr[row0+threadIdx.x];
+			__syncthreads();
+			long long const e0 = s_row[0];
+			int const ne = (int)(s_row[nn]-e0);
+			bool const in_shared = ne <= JDN_TILE_EDGES;
+			double * const value = in_shared ? s_value : scratch+3*e0;      /* [3][ne] in shared memory, [ne][3] in the scratch array */
+			int const edge_stride = in_shared ? 1 : 3, stage_stride = in_shared ? JDN_TILE_EDGES : 1;
+
+			/* lookups: one thread per in-edge of the tile */
+			for (int k = threadIdx.x; k < ne; k += blockDim.x)
+			{
+				double v1, v2, v3;
+				jdn::lookup_edge_values(P, V, h, e0+k, v1, v2, v3, pws);
+				value[k*edge_stride] = v1;
+				value[k*edge_stride+stage_stride] = v2;
+				value[k*edge_stride+2*stage_stride] = v3;
+				if (in_shared)
+				{
+					/* the node this edge leads to: the last row of the tile that starts at or before it */
+					int lo = 0, hi = nn-1;
+					while (lo < hi)
+					{
+						int const mid = (lo+hi+1) >> 1;
+						if (s_row[mid]-e0 <= k)
+							lo = mid;
+						else
+							hi = mid-1;
+					}
+					s_node[k] = (unsigned char)lo;
+				}
+			}
+			/* one thread per node of the tile: current anchor, parameters, first stage state */
+			long long const i = P.lo+row0+threadIdx.x;
+			double y = 0.0, k_1 = 0.0, k_2 = 0.0, k_3 = 0.0, y_stage = 0.0;
+			double par[JDN_NPARAMS > 0 ? JDN_NPARAMS : 1];
+			if (threadIdx.x < nn)
+			{
+				jdn::pair const cur = own_hist[jdn_pair_index(V.current & V.mask, i, P.n)];
+				y = cur.state;
+				k_1 = cur.diff;
+				for (int q = 0; q < JDN_NPARAMS; q++)
+					par[q] = P.node_par[(size_t)q*P.n+i];
+				y_stage = y + 0.5*h*k_1;
+				s_y[threadIdx.x] = y_stage;
+			}
+			__syncthreads();
+			for (int stage = 0; stage < 3; stage++)
+			{
+				/* every edge: its term of this stage (get_next_step's three evaluations of f, jitced_template.c:441-463) */
+				if (in_shared)
+					for (int k = threadIdx.x; k < ne; k += blockDim.x)
+					{
+						double const yd = value[k+stage*JDN_TILE_EDGES];
+						value[k+stage*JDN_TILE_EDGES] = P.weight[e0+k]*JDN_COUPLING(yd, s_y[s_node[k]]);
+					}
+				__syncthreads();
+				if (threadIdx.x < nn)
+				{
+					double const t_stage = stage == 0 ? t1 : stage == 1 ? t2 : t3;
+					double acc = JDN_LOCAL(y_stage, t_stage, par);
+					long long const r0 = s_row[threadIdx.x]-e0, r1 = s_row[threadIdx.x+1]-e0;
+					if (in_shared)
+						for (long long k = r0; k < r1; k++)
+							acc += value[k+stage*JDN_TILE_EDGES];
+					else
+						for (long long k = r0; k < r1; k++)
+							acc += P.weight[e0+k]*JDN_COUPLING(value[3*k+stage], y_stage);
+					if (stage == 0)
+					{
+						k_2 = acc;
+						y_stage = y + 0.75*h*k_2;
+					}
+					else if (stage == 1)
+					{
+						k_3 = acc;
+						y_stage = y + (h/9.) * (2*k_1+3*k_2+4*k_3);
+					}
+					else
+					{
+						double const k_4 = acc;
+						double const error = fabs((5*k_1-6*k_2-8*k_3+9*k_4) * (h/72.));
+						jdn::pair staged;
+						staged.state = y_stage;
+						staged.diff = k_4;
+						size_t const where = jdn_pair_index(slot, i, P.n);
+						if (P.world > 1)
+							for (int r = 0; r < P.world; r++)
+								reinterpret_cast<jdn::pair *>(P.peer_hist[r])[where] = staged;
+						else
+							own_hist[where] = staged;
+						/* get_p, jitced_template.c:474-498: 0/0 is skipped, a NaN never wins the comparison */
+						double const tolerance = atol + rtol*fabs(y_stage);
+						if (error != 0.0 || tolerance != 0.0)
+						{
+							double const c = error/tolerance;
+							if (c >= 0.0)
+								block_contribution = fmax(block_contribution, c);
+						}
+					}
+					s_y[threadIdx.x] = y_stage;
+				}
+				__syncthreads();
+			}
+		}
 		if (pws)
 			C.pws = 1;
-		grid.sync();
-
-		/* step phase */
-		double contribution = -1.0;
-		for (long long i = P.lo + tid; i < P.hi; i += stride)
-		{
-			jdn::pair staged;
-			double c = jdn::attempt_node(P, V, h, i, scratch, staged);
-			if (c >= 0.0)      /* skipped (0/0) or NaN: ignored by the reference's `x > p` test */
-				contribution = fmax(contribution, c);
-			size_t const where = jdn_pair_index(slot, i, P.n);
-			if (P.world > 1)
-				for (int r = 0; r < P.world; r++)
-					reinterpret_cast<jdn::pair *>(P.peer_hist[r])[where] = staged;
-			else
-				own_hist[where] = staged;
-		}
+		/* error norm of this block's nodes (threads 0 … JDN_TILE_NODES−1 hold them) */
 		for (int o = 16; o > 0; o >>= 1)
-			contribution = fmax(contribution, __shfl_down_sync(0xffffffffu, contribution, o));
+			block_contribution = fmax(block_contribution, __shfl_down_sync(0xffffffffu, block_contribution, o));
 		if ((threadIdx.x & 31) == 0)
-			s_max[threadIdx.x >> 5] = contribution;
+			s_max[threadIdx.x >> 5] = block_contribution;
 		__syncthreads();
 		if (threadIdx.x == 0)
 		{
-			double m = s_max[0];
-			for (int w = 1; w < JDN_BLOCK/32; w++)
-				m = fmax(m, s_max[w]);
-			if (m > 0.0)
+			for (int w = 1; w < (JDN_TILE_NODES+31)/32; w++)
+				block_contribution = fmax(block_contribution, s_max[w]);
+			if (block_contribution > 0.0)
 			{
 				if (P.world > 1)
 					for (int r = 0; r < P.world; r++)
-						atomicMax_system(&P.peers[r]->p_bits[buffer], (unsigned long long)__double_as_longlong(m));
+						atomicMax_system(&P.peers[r]->p_bits[buffer], (unsigned long long)__double_as_longlong(block_contribution));
 				else
-					atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(m));
+					atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(block_contribution));
 			}
 		}
-		__syncthreads();      /* s_max is reused in the next attempt */
 		grid.sync();
 
 		/* exchange barrier between the GPUs, then the controller */

@@ -33,6 +33,7 @@ struct jdde_net
 	int peer_rank = 0, peer_world = 1;
 	bool persistent = true;                   /* jdn_k_run (one cooperative launch per batch of attempts) instead of five kernels per attempt */
 	int run_grid = 0;                         /* co-resident blocks of jdn_k_run */
+	int run_smem_bytes = 0;                   /* its dynamic shared memory beyond the anchor times (image descriptor) */
 	/* `poll_every` attempts (lookup, step, [exchange], control, commit: 4–5 launches each) captured once as a CUDA graph and
 	 * replayed: small networks are bound by launch gaps, not by the kernels (10^5 nodes: 45 µs of kernels per 70 µs attempt) */
 	cudaGraphExec_t batch = nullptr;
@@ -184,6 +185,7 @@ int jdde_net_load_image(jdde_net * h, const void * image, size_t len)
 	if (d.magic != JDN_IMAGE_MAGIC || d.abi != JDDE_ABI_VERSION) return nfail(h, JDDE_E_IMAGE, "image built for another ABI version");
 	if (d.n_node_params != h->desc.n_node_params) return nfail(h, JDDE_E_IMAGE, "image does not match the descriptor (node parameters)");
 	h->block = d.block;
+	h->run_smem_bytes = d.run_smem_bytes;
 	struct { const char * name; cudaKernel_t * slot; } const table[] = {
 		{"jdn_k_lookup", &h->k_lookup}, {"jdn_k_attempt", &h->k_attempt}, {"jdn_k_control", &h->k_control}, {"jdn_k_commit", &h->k_commit},
 		{"jdn_k_begin", &h->k_begin}, {"jdn_k_recent_state", &h->k_recent}, {"jdn_k_set_past", &h->k_set_past},
@@ -208,11 +210,9 @@ int jdde_net_load_image(jdde_net * h, const void * image, size_t len)
 	h->persistent = h->k_run && !(choice && choice[0] == '0');
 	/* the bracket search keeps the anchor times in shared memory: 8 bytes per ring slot */
 	if ((size_t)h->P.cap*sizeof(double) > 48*1024)
-	{
 		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->P.cap*sizeof(double))));
-		if (h->k_run)
-			JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->P.cap*sizeof(double))));
-	}
+	if (h->k_run && (size_t)h->P.cap*sizeof(double)+h->run_smem_bytes > 48*1024)
+		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->P.cap*sizeof(double)+h->run_smem_bytes)));
 	return JDDE_OK;
 }
 
@@ -414,7 +414,7 @@ static int launch_run(jdde_net * h, int attempts)
 {
 	int rc;
 	if ((rc = nready_run(h))) return rc;
-	size_t const smem = (size_t)h->P.cap*sizeof(double);
+	size_t const smem = (size_t)h->P.cap*sizeof(double)+(size_t)h->run_smem_bytes;
 	if (!h->run_grid)
 	{
 		int per_sm = 0, sms = 0;
@@ -504,11 +504,9 @@ int jdde_net_grow_ring(jdde_net * h, int32_t new_capacity)
 	if (new_capacity > JDN_MAX_RING_CAPACITY)
 		return nfail(h, JDDE_E_NOMEM, "ring capacity above 16384 (the anchor times of the ring are staged in shared memory)");
 	if ((size_t)new_capacity*sizeof(double) > 48*1024)
-	{
 		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double))));
-		if (h->k_run)
-			JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double))));
-	}
+	if (h->k_run && (size_t)new_capacity*sizeof(double)+h->run_smem_bytes > 48*1024)
+		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double)+h->run_smem_bytes)));
 	h->run_grid = 0;
 	h->P.peer_hist = nullptr;      /* the peers' mappings of the old history are void: jdde_net_connect_peers again (every rank grows at the same attempt) */
 	double * new_times = nullptr, * new_hist = nullptr;

@@ -71,15 +71,17 @@ typedef struct jdde_desc
 } jdde_desc;
 
 /* set_integration_parameters, _jitcdde.py:621-638 (same names, same defaults on the Python side).
- * pws_fuzzy_increase (RNG-driven step-size increase) is not supported; the deterministic
- * credit rule (_jitcdde.py:733-741) is always used. */
+ * pws_fuzzy_seed: 0 = pws_fuzzy_increase=False, the deterministic credit rule (_jitcdde.py:733-741); otherwise
+ * pws_fuzzy_increase=True (:730-731): after a past-within-step event the step size is increased with the probability
+ * the reference computes, drawn from a counter-based generator keyed by this seed, the member index and the member's
+ * number of right-hand-side evaluations (csrc/jdde_math.h: jdde_uniform) — reproducible, independent of scheduling. */
 typedef struct jdde_int_params
 {
 	double atol, rtol, first_step, min_step, max_step;
 	double decrease_threshold, increase_threshold, safety_factor, max_factor, min_factor;
 	double pws_factor, pws_atol, pws_rtol, pws_base_increase_chance;
 	int32_t pws_max_iterations;
-	int32_t reserved;
+	int32_t pws_fuzzy_seed;
 } jdde_int_params;
 
 /* ---- life cycle ------------------------------------------------------------------- */
@@ -227,6 +229,11 @@ int jdde_sum_counters(jdde_handle * h, int64_t * accepted, int64_t * rejected, i
  * times[max_anchors], states/diffs[max_anchors][n]; *n_anchors receives the number written
  * (or needed, if larger than max_anchors). get_full_state, jitced_template.c:336-352. */
 int jdde_get_state(jdde_handle * h, int64_t member, int32_t max_anchors, int32_t * n_anchors, double * times, double * states, double * diffs);
+
+/* Largest number of anchors any member holds at the moment (last − first + 1): lets the caller size the ring BEFORE calls that
+ * cannot be resumed after an overflow — integrate_blindly, jump, adjust_diff (the reference's list just grows,
+ * jitced_template.c:56-73). */
+int jdde_max_live_anchors(jdde_handle * h, int32_t * count);
 
 /* Double (or more) the ring of every member, keeping all anchors, and clear JDDE_STATUS_OVERFLOW.
  * The reference's list is unbounded (malloc per anchor, jitced_template.c:434). */

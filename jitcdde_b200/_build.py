@@ -19,7 +19,18 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_PKG), "include")
-CACHE = os.path.join(_PKG, "_cache")
+PREBUILT = os.path.join(_PKG, "_cache")      # images that travel with the tree (read-mostly)
+
+
+def _user_cache():
+	explicit = os.environ.get("JITCDDE_B200_CACHE")
+	if explicit:
+		return explicit
+	base = os.environ.get("XDG_CACHE_HOME") or os.path.join(os.path.expanduser("~"), ".cache")
+	return os.path.join(base, "jitcdde_b200")
+
+
+CACHE = _user_cache()
 RUNTIME_LIB = os.path.join(_PKG, "libjitcdde_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -43,6 +54,45 @@ def _sources_hash(sources, extra=""):
 		with open(path, "rb") as f:
 			h.update(f.read())
 	return h.hexdigest()
+
+
+def cache_dir():
+	"""where new images are written (created on demand)"""
+	path = _user_cache()
+	os.makedirs(path, exist_ok=True)
+	return path
+
+
+def _cached(name):
+	"""path of a cached file if it exists (prebuilt directory first), marking it as recently used"""
+	for root in (PREBUILT, _user_cache()):
+		path = os.path.join(root, name)
+		if os.path.exists(path):
+			try:
+				os.utime(path)
+			except OSError:
+				pass
+			return path
+	return None
+
+
+def _evict(limit_mb=None):
+	"""keep the user cache below the limit: least recently used images first"""
+	limit = float(os.environ.get("JITCDDE_B200_CACHE_MB", limit_mb or 2048))*1e6
+	root = _user_cache()
+	try:
+		entries = [(e.stat().st_mtime, e.stat().st_size, e.path) for e in os.scandir(root) if e.is_file()]
+	except OSError:
+		return
+	total = sum(size for _, size, _ in entries)
+	for _, size, path in sorted(entries):
+		if total <= limit:
+			break
+		try:
+			os.remove(path)
+			total -= size
+		except OSError:
+			pass
 
 
 def _stale(target, stamp_value):
@@ -183,7 +233,7 @@ def group_window(program):
 
 def image_path(program, n_basic, mode, block, extra_flags=()):
 	tag = hashlib.sha256(repr((program.key, n_basic, mode, block, tuple(extra_flags), use_window(program), launch_shape(program), use_group(program), group_shape(program), group_window(program), _engine_hash())).encode()).hexdigest()[:20]
-	return os.path.join(CACHE, f"jdde_{tag}.cubin")
+	return os.path.join(cache_dir(), f"jdde_{tag}.cubin")
 
 
 def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), force=False, verbose=False):
@@ -192,15 +242,15 @@ def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), fo
 	(`program` = _codegen.RHSProgram). Returns the path of the cubin.
 	"""
 	n_basic = n_basic or program.n
-	os.makedirs(CACHE, exist_ok=True)
 	default_block, default_blocks = launch_shape(program)
 	block = block or default_block
 	if not any(f.startswith("-DJD_MIN_BLOCKS") for f in extra_flags):
 		extra_flags = (*extra_flags, f"-DJD_MIN_BLOCKS={default_blocks}")
 	path = image_path(program, n_basic, mode, block, extra_flags)
-	if os.path.exists(path) and not force:
-		return path
-	rhs = os.path.join(CACHE, f"rhs_{program.key}.inc")
+	hit = None if force else _cached(os.path.basename(path))
+	if hit:
+		return hit
+	rhs = os.path.join(cache_dir(), f"rhs_{program.key}.inc")
 	with open(rhs, "w") as f:
 		f.write(program.body)
 	flags = ["-O3", "-std=c++17", "-lineinfo", *ARCH]
@@ -227,23 +277,24 @@ def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), fo
 	if result.returncode:
 		raise RuntimeError(f"nvcc failed:\n{result.stderr}\ncommand: {' '.join(cmd)}")
 	os.replace(path + ".tmp", path)
+	_evict()
 	return path
 
 
 def build_net_image(program, block=256, mode=FAST, force=False, verbose=False):
 	"""Kernel image of the network engine for one (local, coupling) pair (`program` = _codegen.NetProgram); `mode` as
 	for build_image: VERIFY compiles without FMA contraction and with the bit-reproducible elementary functions."""
-	os.makedirs(CACHE, exist_ok=True)
 	h = hashlib.sha256()
 	for name in ("jdn_engine.cuh", "jdn_kernels.cu", "jdn_abi.h", "jdde_abi.h", "jdde_math.h"):
 		with open(os.path.join(CSRC, name), "rb") as f:
 			h.update(f.read())
 	extra = tuple(os.environ.get("JITCDDE_B200_NET_FLAGS", "").split())      # experiments: e.g. -DJDN_RUN_MIN_BLOCKS=6
 	tag = hashlib.sha256(repr((program.key, block, mode, extra, h.hexdigest())).encode()).hexdigest()[:20]
-	path = os.path.join(CACHE, f"jdn_{tag}.cubin")
-	if os.path.exists(path) and not force:
-		return path
-	rhs = os.path.join(CACHE, f"net_{program.key}.inc")
+	path = os.path.join(cache_dir(), f"jdn_{tag}.cubin")
+	hit = None if force else _cached(os.path.basename(path))
+	if hit:
+		return hit
+	rhs = os.path.join(cache_dir(), f"net_{program.key}.inc")
 	with open(rhs, "w") as f:
 		f.write(program.body)
 	if mode == VERIFY:
@@ -265,10 +316,54 @@ def build_net_image(program, block=256, mode=FAST, force=False, verbose=False):
 
 def build_peak_image(force=False):
 	"""cubin of the FP64 throughput microbenchmark (csrc/jdde_peak.cu)"""
-	os.makedirs(CACHE, exist_ok=True)
 	src = os.path.join(CSRC, "jdde_peak.cu")
-	path = os.path.join(CACHE, f"jdde_peak_{_sources_hash([src])[:16]}.cubin")
-	if not os.path.exists(path) or force:
+	name = f"jdde_peak_{_sources_hash([src])[:16]}.cubin"
+	hit = None if force else _cached(name)
+	if hit:
+		return hit
+	path = os.path.join(cache_dir(), name)
+	if True:
 		subprocess.run([nvcc(), "-cubin", "-O3", "-lineinfo", *ARCH, src, "-o", path + ".tmp"], check=True)
 		os.replace(path + ".tmp", path)
 	return path
+
+
+# ---------------------------------------------------------------------------
+# save_compiled / module_location (reference: jitcxde_common's save_compiled, _jitcdde.py:178-179, tests/test_jitcdde.py:138-147)
+
+_CONTAINER_MAGIC = b"JDDEIMG1"
+
+
+def save_image(path, image, meta, overwrite=False):
+	"""one file: magic, length of the JSON header, header (what the engine needs to know about the system), kernel image"""
+	import json
+	if os.path.exists(path) and not overwrite:
+		raise OSError(f"Target File {path} already exists and overwriting is disabled")
+	header = json.dumps(meta).encode()
+	with open(image, "rb") as f:
+		blob = f.read()
+	with open(path, "wb") as f:
+		f.write(_CONTAINER_MAGIC + len(header).to_bytes(4, "little") + header + blob)
+	return path
+
+
+def load_image_file(path):
+	"""(meta, path of the kernel image extracted into the cache) of a file written by save_image"""
+	import json
+	with open(path, "rb") as f:
+		data = f.read()
+	if data[:8] != _CONTAINER_MAGIC:
+		raise ValueError(f"{path} is not a module file written by save_compiled")
+	n = int.from_bytes(data[8:12], "little")
+	meta = json.loads(data[12:12+n].decode())
+	blob = data[12+n:]
+	name = "loaded_" + hashlib.sha256(blob).hexdigest()[:20] + ".cubin"
+	hit = _cached(name)
+	if hit:
+		return meta, hit
+	target = os.path.join(cache_dir(), name)
+	with open(target + ".tmp", "wb") as f:
+		f.write(blob)
+	os.replace(target + ".tmp", target)
+	_evict()
+	return meta, target

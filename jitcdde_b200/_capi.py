@@ -38,7 +38,7 @@ class IntParams(ctypes.Structure):
 		("safety_factor", ctypes.c_double), ("max_factor", ctypes.c_double), ("min_factor", ctypes.c_double),
 		("pws_factor", ctypes.c_double), ("pws_atol", ctypes.c_double), ("pws_rtol", ctypes.c_double),
 		("pws_base_increase_chance", ctypes.c_double),
-		("pws_max_iterations", ctypes.c_int32), ("reserved", ctypes.c_int32),
+		("pws_max_iterations", ctypes.c_int32), ("pws_fuzzy_seed", ctypes.c_int32),
 	]
 
 
@@ -79,6 +79,7 @@ SIGNATURES = {
 	"jdde_get_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
 	"jdde_sum_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
 	"jdde_get_state": (ctypes.c_int, [_H, ctypes.c_int64, ctypes.c_int32, c_int32_p, c_double_p, c_double_p, c_double_p]),
+	"jdde_max_live_anchors": (ctypes.c_int, [_H, c_int32_p]),
 	"jdde_grow_ring": (ctypes.c_int, [_H, ctypes.c_int32]),
 	"jdde_clear_status": (ctypes.c_int, [_H, ctypes.c_int32]),
 	"jdde_set_attempt_budget": (ctypes.c_int, [_H, ctypes.c_int64]),
@@ -473,6 +474,19 @@ class Engine:
 	def grow_ring(self, new_capacity):
 		self._check(self.lib.jdde_grow_ring(self._h, int(new_capacity)))
 		self.ring_capacity = int(new_capacity)
+
+	def max_live_anchors(self):
+		count = ctypes.c_int32()
+		self._check(self.lib.jdde_max_live_anchors(self._h, ctypes.byref(count)))
+		return count.value
+
+	def ensure_capacity(self, anchors):
+		"""grow the ring so that every member can hold `anchors` anchors (for calls that cannot be resumed after an overflow)"""
+		capacity = self.ring_capacity
+		while capacity < anchors+1:
+			capacity *= 2
+		if capacity > self.ring_capacity:
+			self.grow_ring(capacity)
 
 	def clear_status(self, code):
 		self._check(self.lib.jdde_clear_status(self._h, int(code)))

@@ -12,6 +12,7 @@ leading member axis. With the default `n_members=1` all shapes are the
 reference's.
 """
 
+import os
 from warnings import warn
 
 import numpy as np
@@ -66,7 +67,8 @@ class jitcdde:
 	control_pars, verbose, rng.
 
 	Not supported (out of the accelerated path): callback_functions (a host
-	callback per right-hand-side evaluation cannot run on the device), module_location.
+	callback per right-hand-side evaluation cannot run on the device). module_location takes a
+	file written by save_compiled (kernel image + dimensions).
 
 	Extensions: n_members (ensemble size), device (CUDA ordinal), ring_capacity (anchors
 	kept per member; grows automatically), verification (build kernels without FMA
@@ -93,14 +95,26 @@ class jitcdde:
 		):
 		if callback_functions:
 			raise NotImplementedError("callback_functions are not supported: a Python callback per right-hand-side evaluation cannot run on the GPU.")
-		if module_location is not None:
-			raise NotImplementedError("module_location is not supported; compiled kernel images are cached automatically (jitcdde_b200/_cache).")
 		if rng is None:
 			rng = np.random.default_rng(seed=42)
 
 		self.verbose = verbose
+		self._loaded = None
+		if module_location is not None:
+			# a module file written by save_compiled: kernel image + what the engine needs to know about the system; no
+			# symbolic input needed (reference: _jitcdde.py:178-179, 585-592). `n`, if given, must match.
+			meta, image = _build.load_image_file(module_location)
+			if n is not None and n != meta["n"]:
+				raise ValueError(f"n = {n} does not match the module file (n = {meta['n']}).")
+			if len(control_pars) != meta["n_params"]:
+				raise ValueError(f"The module file was compiled with {meta['n_params']} control parameters; provide them again (control_pars).")
+			self._loaded = (meta, image)
+			f_sym, n = (), meta["n"]
+			if not hasattr(self, "n_basic") or self.n_basic is None:
+				self.n_basic = meta["n_basic"]
+			verification = meta["mode"] == _build.VERIFY
 		self.f_sym = self._handle_input(f_sym, n)
-		if not hasattr(self, "n_basic"):
+		if not hasattr(self, "n_basic") or self.n_basic is None:
 			self.n_basic = self.n
 		self.helpers = [(sympy.sympify(h[0]), sympy.sympify(h[1])) for h in (helpers or [])]
 		self.control_pars = list(control_pars)
@@ -124,6 +138,13 @@ class jitcdde:
 		self.extra_compile_args = ()
 		self._int_params_dirty = True
 		self._pushed_max_delay = None
+		if self._loaded:
+			from types import SimpleNamespace
+			meta, image = self._loaded
+			self._program = SimpleNamespace(n=meta["n"], n_sites=meta["n_sites"], n_params=meta["n_params"], key=meta["key"])
+			self._image = image
+			if delays is None and max_delay is None:
+				raise ValueError("With module_location you must give delays or max_delay (the module file holds no symbolic input).")
 
 	# jitcxde._handle_input: iterable / generator function / dict keyed by y(i)
 	def _handle_input(self, f_sym, n=None):
@@ -259,12 +280,31 @@ class jitcdde:
 	def generate_lambdas(self, simplify=None):
 		raise NotImplementedError("There is no Python/CPU core in this package: the integrator only runs as CUDA kernels on a B200.")
 
+	def save_compiled(self, destination="", overwrite=False):
+		"""
+		Saves the compiled kernel image together with what the engine needs to know about the system (dimensions, lookup
+		sites, control parameters, build mode) to one file that `module_location` accepts, so that a later session — or
+		another machine with a B200 — skips code generation and nvcc (reference: jitcxde_common's save_compiled, used at
+		tests/test_jitcdde.py:138-147). `destination`: a file name, or a directory (or "": the working directory) in which
+		the file is named after the system. Returns the path.
+		"""
+		if self._program is None:
+			self.compile_C()
+		name = f"jitced_{self._program.key}.jdde"
+		if destination == "" or os.path.isdir(destination):
+			destination = os.path.join(destination or ".", name)
+		meta = dict(n=self.n, n_basic=self.n_basic, n_sites=self._program.n_sites, n_params=self._program.n_params, key=self._program.key,
+			mode=_build.VERIFY if self.verification else _build.FAST, format=1)
+		return _build.save_image(destination, self._image, meta, overwrite=overwrite)
+
 	def compile_C(self, simplify=None, do_cse=True, chunk_size=100, extra_compile_args=None, extra_link_args=None, verbose=False, modulename=None, omp=False):
 		"""
 		Translate the derivative to CUDA and compile it for sm_100a (replaces the C translation
 		of _jitcdde.py:420-575). `chunk_size`, `extra_link_args`, `modulename` and `omp` have no
 		meaning here and are ignored; `extra_compile_args` are passed to nvcc.
 		"""
+		if self._loaded:
+			raise RuntimeError("This integrator was loaded from a module file (module_location); there is nothing to compile.")
 		# The reference simplifies by default for n <= 10 (SymEngine's cheap simplify). SymPy's
 		# simplify is slow and only reorders arithmetic, so it is opt-in here.
 		simplify = bool(simplify)
@@ -358,8 +398,6 @@ class jitcdde:
 			pws_base_increase_chance=0.1,
 			pws_fuzzy_increase=False,
 			):
-		if pws_fuzzy_increase:
-			raise NotImplementedError("pws_fuzzy_increase (random step-size increases) is not supported; the deterministic rule is used.")
 		if first_step > max_step:
 			first_step = max_step
 			warn("Decreasing first_step to match max_step", stacklevel=2)
@@ -388,6 +426,8 @@ class jitcdde:
 			safety_factor=safety_factor, max_factor=max_factor, min_factor=min_factor,
 			pws_factor=pws_factor, pws_atol=pws_atol, pws_rtol=pws_rtol,
 			pws_max_iterations=pws_max_iterations, pws_base_increase_chance=pws_base_increase_chance,
+			# pws_fuzzy_increase (_jitcdde.py:730-731): the draws come from a counter-based generator on the device, seeded from self.rng
+			pws_fuzzy_seed=int(self.rng.integers(1, 2**31-1)) if pws_fuzzy_increase else 0,
 		)
 		self.atol, self.rtol, self.min_step, self.max_step = atol, rtol, min_step, max_step
 		self.integration_parameters_set = True
@@ -531,6 +571,7 @@ class jitcdde:
 	def adjust_diff(self, shift_ratio=1e-4):
 		self._initiate()
 		self.initial_discontinuities_handled = True
+		self._engine.ensure_capacity(self._engine.max_live_anchors()+3)      # two new anchors; not resumable after an overflow
 		minima, maxima = self._engine.adjust_diff(shift_ratio)
 		self._check_status(self._engine.get_status())
 		return self._shape_state(minima), self._shape_state(maxima)
@@ -540,9 +581,21 @@ class jitcdde:
 		self.initial_discontinuities_handled = True
 		step = step or self.max_step
 		assert step > 0, "step must be positive"
+		self._room_for_blind_steps(target_time, step)
 		result, status = self._engine.integrate_blindly(target_time, step)
-		self._check_status(status)   # a full ring cannot be resumed here: pass a larger ring_capacity
+		self._check_status(status)
 		return self._shape_state(result)
+
+	def _room_for_blind_steps(self, target_time, step):
+		"""A blind call cannot be resumed after a ring overflow (the reference's anchor list is unbounded): make the ring large
+		enough beforehand — what the members hold now plus the steps of the call that forget() cannot drop, i.e. those within
+		max_delay of the end, plus a margin."""
+		total = float(np.max(np.asarray(target_time, dtype=float)-self._engine.get_t()))
+		if not total > 0:
+			return self._engine.ensure_capacity(self._engine.max_live_anchors()+3)
+		number = max(1, round(total/min(step, total)))
+		kept = int(np.ceil(min(total, self.max_delay)/(total/number)))+2 if np.isfinite(self.max_delay) else number
+		self._engine.ensure_capacity(self._engine.max_live_anchors()+min(number, kept)+4)
 
 	def step_on_discontinuities(self, *, propagations=1, min_distance=1e-5, max_step=None):
 		self._initiate()
@@ -595,6 +648,7 @@ class jitcdde:
 			amplitude = np.full(self.n, amplitude, dtype=float)
 		amplitude = np.array(amplitude, dtype=float)
 		assert amplitude.shape in [(self.n,), (self.n_members, self.n)]
+		self._engine.ensure_capacity(self._engine.max_live_anchors()+3)      # two new anchors; not resumable after an overflow
 		minima, maxima = self._engine.jump(amplitude, time, width, forward)
 		self._check_status(self._engine.get_status())
 		return self._shape_state(minima), self._shape_state(maxima)
@@ -619,6 +673,19 @@ class jitcdde_lyap(jitcdde):
 	"""
 
 	def __init__(self, f_sym=(), n_lyap=1, simplify=None, **kwargs):
+		if kwargs.get("module_location") is not None:
+			# a saved module holds the extended system already (save_compiled of a jitcdde_lyap)
+			meta, _ = _build.load_image_file(kwargs["module_location"])
+			n_basic = kwargs.pop("n", None) or meta["n_basic"]
+			if n_basic != meta["n_basic"] or meta["n"] != n_basic*(n_lyap+1):
+				raise ValueError(f"The module file holds a system with n_basic = {meta['n_basic']} and {meta['n']//meta['n_basic']-1} Lyapunov exponents.")
+			self.n_basic = n_basic
+			self._n_lyap = n_lyap
+			super().__init__((), n=meta["n"], **kwargs)
+			self.n_basic = n_basic
+			self.initiate_past()
+			assert self.max_delay > 0, "Maximum delay must be positive for calculating Lyapunov exponents."
+			return
 		self.n_basic = kwargs.pop("n", None)
 		helpers = [(sympy.sympify(h[0]), sympy.sympify(h[1])) for h in (kwargs.pop("helpers", None) or [])]
 		if any(_is_anchor_helper(helper) for helper in helpers):
@@ -674,6 +741,7 @@ class jitcdde_lyap(jitcdde):
 		self.initial_discontinuities_handled = True
 		step = step or self.max_step
 		assert step > 0, "step must be positive"
+		self._room_for_blind_steps(target_time, step)
 		state, lyaps, total, status = self._engine.integrate_blindly_lyap(target_time, step)
 		self._check_status(status)
 		if self.n_members == 1:
@@ -782,9 +850,16 @@ class jitcdde_input(jitcdde):
 		self.reset_integrator(idc_unhandled=True)
 
 	def integrate(self, target_time, out=None):
+		"""`out`, if given, receives the state of the system proper (without the dummy variables of the input) and is returned"""
 		if np.any(np.asarray(target_time) > self.input_duration):
 			warn("Integrating beyond duration of input. From now on, the input will be extrapolated. You very likely do not want this. Instead define a longer input or stop integrating.", stacklevel=2)
-		return super().integrate(target_time)[..., :self.input_base_n]
+		result = super().integrate(target_time)[..., :self.input_base_n]
+		if out is not None:
+			if np.shape(out) != np.shape(result):
+				raise ValueError(f"out must have shape {np.shape(result)}")
+			out[...] = result
+			return out
+		return result
 
 	def integrate_blindly(self, *args, **kwargs):
 		return super().integrate_blindly(*args, **kwargs)[..., :self.input_base_n]

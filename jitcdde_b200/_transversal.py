@@ -124,6 +124,7 @@ class _ProjectedLyap(jitcdde):
 		self.initial_discontinuities_handled = True
 		step = step or self.max_step
 		assert step > 0, "step must be positive"
+		self._room_for_blind_steps(target_time, step)
 		state, lyap, total, status = self._engine.integrate_blindly_projected(target_time, step)
 		self._check_status(status)
 		return _shape(self._select(state), self.n_members), _shape(lyap, self.n_members), _shape(total, self.n_members)

@@ -1249,8 +1249,8 @@ JD_FN void control_for_min_step(MT & M, jdde_int_params const & P)
 		M.status = JDDE_STATUS_MIN_STEP;
 }
 
-/* _increase_chance (_jitcdde.py:767-773) and the deterministic do_increase (:733-741); cold: only after a
- * past-within-step event. Operates on the controller memory in the per-member arrays. */
+/* _increase_chance (_jitcdde.py:767-773) and do_increase (:730-741: drawn, or the deterministic credit rule); cold: only
+ * after a past-within-step event. Operates on the controller memory in the per-member arrays. */
 template <class MT>
 JD_FN bool pws_allows_increase(MT & M, jdde_problem const & P, double const new_dt)
 {
@@ -1261,6 +1261,14 @@ JD_FN bool pws_allows_increase(MT & M, jdde_problem const & P, double const new_
 	double const few_iterations = sigmoid(1-ctl_count(M, P)/I.pws_factor);
 	double const profile = is_explicit+far_from_explicit*few_iterations;
 	double const chance = profile + I.pws_base_increase_chance*(1-profile);
+
+	if (I.pws_fuzzy_seed)
+	{
+		/* pws_fuzzy_increase (_jitcdde.py:730-731): `rng.random() < chance`; the draw is a function of the seed, the member and
+		 * the number of right-hand-side evaluations the member has made (3 per attempted step + those of jumps) */
+		long long const evaluations = 3*(P.attempts[M.index]+M.attempts) + P.extra_rhs[M.index]+M.extra_rhs;
+		return jdde_uniform((unsigned)I.pws_fuzzy_seed, (unsigned long long)M.index, (unsigned long long)evaluations) < chance;
+	}
 
 	double credit = ctl_credit(M, P) + chance;
 	bool const increase = credit >= 0.9;
@@ -1973,8 +1981,13 @@ JD_FN void integrate_blindly(Member & M, jdde_problem const & P, double const ta
 	}
 	else if (total == 0)
 	{
-		double mi[JD_N], ma[JD_N];
-		adjust_diff(M, P, 1e-4, mi, ma);
+		/* jitcdde.integrate_blindly calls adjust_diff here (_jitcdde.py:925-926); the variants of jitcdde_lyap (:1191-1209) and of
+		 * the restricted / transversal classes just make no step */
+		if (!lyaps)
+		{
+			double mi[JD_N], ma[JD_N];
+			adjust_diff(M, P, 1e-4, mi, ma);
+		}
 		for (int i = 0; i < n_exponents; i++)
 			lyaps[i] = 0.0;
 	}

@@ -317,6 +317,24 @@ JDDE_HD double jdde_log(double x)
 	return dk*6.93147180369123816490e-01 - ((hfsq - (s*(hfsq + R) + dk*1.90821492927058770002e-10)) - f);
 }
 
+/* A uniform number in [0, 1) that is a pure function of (seed, stream, counter): what pws_fuzzy_increase draws
+ * (/root/reference/jitcdde/_jitcdde.py:730-731, `self.rng.random() < p`). The reference consumes a NumPy generator
+ * sequentially; an ensemble needs a draw that does not depend on which trajectory asks first, so every trajectory
+ * (stream) indexes its own sequence by the number of right-hand-side evaluations it has made (counter). Two rounds of the
+ * SplitMix64 finaliser over the combined words; the same bits on CPU and GPU. */
+JDDE_HD double jdde_uniform(unsigned seed, unsigned long long stream, unsigned long long counter)
+{
+	unsigned long long z = (unsigned long long)seed*0x9E3779B97F4A7C15ull ^ stream*0xD1B54A32D192ED03ull ^ counter*0x8CB92BA72F3D8DD7ull;
+	for (int round = 0; round < 2; round++)
+	{
+		z += 0x9E3779B97F4A7C15ull;
+		z = (z ^ (z >> 30))*0xBF58476D1CE4E5B9ull;
+		z = (z ^ (z >> 27))*0x94D049BB133111EBull;
+		z ^= z >> 31;
+	}
+	return (double)(z >> 11)*0x1.0p-53;
+}
+
 /* what the generated right-hand sides call (jitcdde_b200/_codegen.py) */
 #if defined(JD_FAST) || defined(JDDE_LIBM)
 #  define JDDE_SIN(x) sin(x)

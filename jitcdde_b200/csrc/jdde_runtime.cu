@@ -1127,6 +1127,25 @@ int jdde_get_state(jdde_handle * h, int64_t member, int32_t max_anchors, int32_t
 	return JDDE_OK;
 }
 
+int jdde_max_live_anchors(jdde_handle * h, int32_t * count)
+{
+	int rc = ready(h);
+	if (rc) return rc;
+	if (!h->have_past) return fail(h, JDDE_E_INVALID, "no past set (jdde_set_past)");
+	if (!count) return fail(h, JDDE_E_INVALID, "null argument");
+	size_t const N = (size_t)h->desc.n_members;
+	std::vector<int> first(N), last(N);
+	JD_CUDA(h, cudaStreamSynchronize(h->stream));
+	JD_CUDA(h, cudaMemcpy(first.data(), h->P.first, N*sizeof(int), cudaMemcpyDeviceToHost));
+	JD_CUDA(h, cudaMemcpy(last.data(), h->P.last, N*sizeof(int), cudaMemcpyDeviceToHost));
+	int most = 0;
+	for (size_t m = 0; m < N; m++)
+		if (last[m]-first[m]+1 > most)
+			most = last[m]-first[m]+1;
+	*count = most;
+	return JDDE_OK;
+}
+
 int jdde_grow_ring(jdde_handle * h, int32_t new_capacity)
 {
 	int rc = ready(h);

@@ -39,6 +39,7 @@ class Params(ctypes.Structure):
 		("pws_factor", ctypes.c_double), ("pws_atol", ctypes.c_double), ("pws_rtol", ctypes.c_double),
 		("pws_base_increase_chance", ctypes.c_double),
 		("pws_max_iterations", ctypes.c_int32), ("root_mode", ctypes.c_int32),
+		("fuzzy_seed", ctypes.c_int32), ("pad_", ctypes.c_int32),
 	]
 
 DEFAULTS = dict(
@@ -48,7 +49,7 @@ DEFAULTS = dict(
 )
 
 
-def make_params(root_mode=1, **kwargs):
+def make_params(root_mode=1, fuzzy_seed=0, **kwargs):
 	values = dict(DEFAULTS)
 	values.update(kwargs)
 	# same clipping as the reference, _jitcdde.py:688-693
@@ -56,7 +57,7 @@ def make_params(root_mode=1, **kwargs):
 		values["first_step"] = values["max_step"]
 	if values["min_step"] > values["first_step"]:
 		values["min_step"] = values["first_step"]
-	return Params(root_mode=root_mode, **values)
+	return Params(root_mode=root_mode, fuzzy_seed=int(fuzzy_seed), **values)
 
 
 def _arr(x, shape=None):

@@ -31,7 +31,7 @@ def srcline(key):
     if not key: return ""
     f, ln = key
     if f not in lines:
-        try: lines[f] = open("/root/repo/jitcdde_b200/csrc/" + f).read().split("\n")
+        try: lines[f] = open(f if f.startswith("/") else "/root/repo/jitcdde_b200/csrc/" + f).read().split("\n")
         except Exception: lines[f] = []
     L = lines[f]
     return L[ln-1].strip()[:80] if 0 < ln <= len(L) else ""

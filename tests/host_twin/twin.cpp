@@ -607,6 +607,16 @@ int jdde_clear_status(jdde_handle * h, int32_t code)
 	for (auto & s : h->status) if (s == code) s = JDDE_STATUS_OK;
 	return JDDE_OK;
 }
+int jdde_max_live_anchors(jdde_handle * h, int32_t * count)
+{
+	int most = 0;
+	for (long long m = 0; m < h->P.n_members; m++)
+		if (h->last[m]-h->first[m]+1 > most)
+			most = h->last[m]-h->first[m]+1;
+	*count = most;
+	return JDDE_OK;
+}
+
 int jdde_set_attempt_budget(jdde_handle * h, int64_t attempts) { if (attempts < 1) return fail(h, JDDE_E_INVALID, "budget must be positive"); h->budget = attempts; return JDDE_OK; }
 int jdde_host_alloc(size_t bytes, void ** out) { *out = malloc(bytes ? bytes : 1); return *out ? JDDE_OK : JDDE_E_NOMEM; }
 int jdde_host_free(void * p) { free(p); return JDDE_OK; }

@@ -7,12 +7,14 @@ past-within-step iteration — must reproduce the reference's golden vector y(T=
 annihilating jumps, many tiny samples). Runs on the host twin here and on the GPU with -m gpu.
 """
 
+import os
+
 import numpy as np
 import pytest
 import sympy
 
 from jitcdde_b200 import UnsuccessfulIntegration, _find_max_delay, _get_delays, jitcdde, quadrature, t, y
-from tests import scenarios
+from tests import scenarios, systems
 
 omega = np.array([0.88167179, 0.87768425])
 delay = 4.5
@@ -356,3 +358,35 @@ def test_symbols_from_anywhere_give_the_same_program():
 		f = [sympy.cos(t_)*y_(1, t_-3.5) - y_(0), -y_(0, t_-1.25)*y_(1)]
 		bodies.add(_codegen.generate(f).body)
 	assert len(bodies) == 1
+
+
+def test_save_compiled_and_module_location():
+	"""tests/test_jitcdde.py:138-147 of the reference: save_compiled() writes a module file, jitcdde(n=…, module_location=…,
+	delays=…) loads it without any symbolic input. Host side only here (file format, metadata, refusals); the GPU test
+	integrates with the loaded image."""
+	import tempfile
+	from jitcdde_b200 import _build, jitcdde
+	system = systems.two_roessler()
+	DDE = jitcdde(system["f"], verbose=False)
+	with tempfile.TemporaryDirectory() as directory:
+		path = DDE.save_compiled(directory)
+		assert os.path.dirname(path) == directory and os.path.getsize(path) > 1000
+		with pytest.raises(OSError):
+			DDE.save_compiled(path)
+		assert DDE.save_compiled(path, overwrite=True) == path
+		meta, image = _build.load_image_file(path)
+		assert (meta["n"], meta["n_basic"], meta["n_sites"], meta["n_params"], meta["mode"]) == (6, 6, 1, 0, "fast")
+		with open(image, "rb") as f, open(DDE._image, "rb") as g:
+			assert f.read() == g.read()
+		loaded = jitcdde(n=6, module_location=path, delays=[system["delay"]], verbose=False)
+		assert loaded.n == 6 and loaded.max_delay == system["delay"] and loaded._program.n_sites == 1
+		with pytest.raises(RuntimeError):
+			loaded.compile_C()
+		with pytest.raises(ValueError):
+			jitcdde(n=5, module_location=path, delays=[system["delay"]])
+		with pytest.raises(ValueError):
+			jitcdde(module_location=path)
+		with open(os.path.join(directory, "garbage"), "wb") as f:
+			f.write(b"not a module")
+		with pytest.raises(ValueError):
+			jitcdde(module_location=os.path.join(directory, "garbage"), delays=[1.0])

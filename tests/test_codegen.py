@@ -40,7 +40,7 @@ def test_blockwise_generation_falls_back_when_blocks_differ():
 
 def test_build_policy_access_paths():
 	mg = systems.program(systems.mackey_glass())
-	assert _build.use_window(mg) == 2 and _build.launch_shape(mg) == (32, 32)          # one 32-byte anchor per sector: per-thread window, by value
+	assert _build.use_window(mg) == 2 and _build.launch_shape(mg) == (32, 28)          # one 32-byte anchor per sector: per-thread window, by value; 72 registers
 	neutral = systems.program(systems.neutral())
 	assert _build.use_window(neutral) == 3 and _build.launch_shape(neutral) == (64, 6)  # 13 doubles per anchor: pointer window in shared memory
 	kuramoto = systems.program(systems.kuramoto())

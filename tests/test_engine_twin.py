@@ -223,3 +223,67 @@ def test_sampling_in_one_launch_equals_separate_calls(twin, capacity):
 	single.step_on_discontinuities()
 	series = single.integrate_samples(single.t + np.arange(1, 6)*10.0)
 	assert series.shape == (5, 1)
+
+
+def test_pws_fuzzy_increase(twin):
+	"""pws_fuzzy_increase=True (/root/reference/jitcdde/_jitcdde.py:730-731; reference test: tests/test_jitcdde.py:182-186): after
+	a past-within-step event (first_step 30 > delay 4.5) the step size is increased with the reference's probability, drawn per
+	member from a counter-based generator. The engine and the oracle draw the same numbers: bit-identical; the draws matter
+	(other seeds, other steps); two runs agree; and the result meets the reference's golden vector within its tolerance."""
+	from oracle import oracle
+	from tests import systems
+	g = scenarios.golden("roessler")
+	past = scenarios.past_of(g)
+	N = 8
+	k = np.linspace(0.2, 0.3, N)[:, None]
+	k[0, 0] = 0.25      # the coupling of tests/test_jitcdde.py:30-41
+	times = np.linspace(0, 10, 10, endpoint=True)
+	system = systems.two_roessler(control=True)
+
+	def run(seed):
+		DDE = scenarios.make(system, n_members=N, verification=True, rng=np.random.default_rng(seed))
+		DDE.add_past_points(past)
+		DDE.set_integration_parameters(pws_fuzzy_increase=True, **systems.ROESSLER_TEST_PARAMETERS)
+		DDE.set_parameters(k)
+		DDE.initial_discontinuities_handled = True
+		out = np.array([DDE.integrate(T) for T in times])
+		return out, DDE.counters(), DDE._int_params["pws_fuzzy_seed"]
+
+	out, counters, seed = run(1)
+	again, counters_again, _ = run(1)
+	assert seed != 0 and np.array_equal(out, again) and all(np.array_equal(a, b) for a, b in zip(counters, counters_again))
+	other, counters_other, other_seed = run(2)
+	assert other_seed != seed and not np.array_equal(counters[0], counters_other[0])
+	deterministic = scenarios.make(system, n_members=N, verification=True)
+	deterministic.add_past_points(past)
+	deterministic.set_integration_parameters(**systems.ROESSLER_TEST_PARAMETERS)
+	deterministic.set_parameters(k)
+	deterministic.initial_discontinuities_handled = True
+	deterministic.integrate(10.0)
+	assert not np.array_equal(counters[0], deterministic.counters()[0])
+
+	lib = oracle.build(systems.program(system))
+	arrays = (np.array([a[0] for a in past]), np.array([a[1] for a in past]), np.array([a[2] for a in past]))
+	ref = oracle.run_ensemble(lib, arrays, k, 4.5, 0, None, times, absolute_samples=True, fuzzy_seed=seed, n_members=N, **systems.ROESSLER_TEST_PARAMETERS)
+	assert np.array_equal(out, ref["out"])
+	assert np.array_equal(counters[0], ref["counters"][:, 0]) and np.array_equal(counters[1], ref["counters"][:, 1])
+	# member 0 is the reference's own test case: tests/test_jitcdde.py:61-64, 88-97
+	np.testing.assert_allclose(out[-1, 0], g["y10_reference"], rtol=1e-3, atol=1e-6)
+
+
+def test_blind_integration_grows_the_ring_beforehand(twin):
+	"""The reference-style call integrate_blindly(max_delay, small step) needs more anchors than the default ring of 64 holds; a
+	blind call cannot be resumed after an overflow, so the ring is sized before it. Same result as with a ring that
+	is large enough from the start; jump and adjust_diff on a full ring likewise."""
+	from jitcdde_b200 import jitcdde, t, y
+	f = [0.25*y(0, t-15)/(1+y(0, t-15)**10) - 0.1*y(0)]
+	results = []
+	for capacity in (None, 1024):
+		DDE = jitcdde(f, verbose=False, verification=True, ring_capacity=capacity)
+		DDE.constant_past([1.0])
+		blind = DDE.integrate_blindly(30.0, 0.1)
+		mi, ma = DDE.jump(0.1, DDE.t)
+		after = DDE.integrate_blindly(DDE.t+10.0, 0.05)
+		mi2, ma2 = DDE.adjust_diff()
+		results.append((blind, mi, ma, after, mi2, ma2, DDE.t, len(DDE.get_state())))
+	assert all(np.array_equal(a, b) for a, b in zip(*results))

@@ -453,3 +453,85 @@ def test_neutral_ensemble_c5b():
 	# components oscillate through zero: tolerance relative to the amplitude (~1) as well
 	np.testing.assert_allclose(ours["out"], theirs["out"], rtol=1e-4, atol=1e-4)
 	assert np.all(np.abs(ours["accepted"]-theirs["accepted"]) <= 0.05*theirs["accepted"]+2)
+
+
+def test_pws_fuzzy_increase_on_gpu():
+	"""pws_fuzzy_increase=True (_jitcdde.py:730-731; reference test tests/test_jitcdde.py:182-186): the draws come from the
+	counter-based generator shared with the oracle — verification build bit for bit, reference's golden vector within its tolerance."""
+	g = scenarios.golden("roessler")
+	past = scenarios.past_of(g)
+	N = 64
+	k = np.linspace(0.2, 0.3, N)[:, None]
+	k[0, 0] = 0.25
+	times = np.linspace(0, 10, 10, endpoint=True)
+	system = systems.two_roessler(control=True)
+	DDE = scenarios.make(system, n_members=N, verification=True, rng=np.random.default_rng(5))
+	DDE.add_past_points(past)
+	DDE.set_integration_parameters(pws_fuzzy_increase=True, **systems.ROESSLER_TEST_PARAMETERS)
+	DDE.set_parameters(k)
+	DDE.initial_discontinuities_handled = True
+	out = np.array([DDE.integrate(T) for T in times])
+	accepted, rejected, _ = DDE.counters()
+	lib = oracle.build(systems.program(system))
+	arrays = (np.array([a[0] for a in past]), np.array([a[1] for a in past]), np.array([a[2] for a in past]))
+	ref = oracle.run_ensemble(lib, arrays, k, 4.5, 0, None, times, absolute_samples=True, fuzzy_seed=DDE._int_params["pws_fuzzy_seed"], n_members=N, **systems.ROESSLER_TEST_PARAMETERS)
+	assert np.array_equal(out, ref["out"])
+	assert np.array_equal(accepted, ref["counters"][:, 0]) and np.array_equal(rejected, ref["counters"][:, 1])
+	np.testing.assert_allclose(out[-1, 0], g["y10_reference"], rtol=1e-3, atol=1e-6)
+
+
+def test_integration_with_saved_module(tmp_path):
+	"""tests/test_jitcdde.py:138-147 (TestIntegrationSaveAndLoad): save_compiled(), then an integrator built from the module file
+	alone — no symbolic input — reproduces the reference core's vectors bit for bit (the file carries the verification image)."""
+	g = scenarios.golden("roessler")
+	original = scenarios.make(systems.two_roessler(), verification=True)
+	path = original.save_compiled(str(tmp_path), overwrite=True)
+	DDE = jitcdde(n=6, module_location=path, delays=[systems.two_roessler()["delay"]], verbose=False)
+	DDE.set_integration_parameters(**systems.ROESSLER_TEST_PARAMETERS)
+	DDE.add_past_points(scenarios.past_of(g))
+	DDE.initial_discontinuities_handled = True
+	samples = np.array([DDE.integrate(T) for T in g["times"]])
+	assert np.array_equal(samples, g["samples"])
+	accepted, rejected, _ = DDE.counters()
+	assert (accepted[0], rejected[0]) == (int(g["accepted"]), int(g["rejected"]))
+
+
+def test_blind_integration_grows_the_ring_beforehand_on_gpu():
+	"""integrate_blindly(max_delay, small step) with the default ring of 64 anchors, jump and adjust_diff on a full ring"""
+	from jitcdde_b200 import t, y
+	f = [0.25*y(0, t-15)/(1+y(0, t-15)**10) - 0.1*y(0)]
+	results = []
+	for capacity in (None, 1024):
+		DDE = jitcdde(f, verbose=False, verification=True, ring_capacity=capacity)
+		DDE.constant_past([1.0])
+		blind = DDE.integrate_blindly(30.0, 0.1)
+		mi, ma = DDE.jump(0.1, DDE.t)
+		after = DDE.integrate_blindly(DDE.t+10.0, 0.05)
+		mi2, ma2 = DDE.adjust_diff()
+		results.append((blind, mi, ma, after, mi2, ma2, DDE.t, len(DDE.get_state())))
+	assert all(np.array_equal(a, b) for a, b in zip(*results))
+
+
+def test_past_from_function_and_state_round_trip_on_gpu():
+	"""past_from_function (anchor placement is this package's own heuristic: the reference's lives in chspy and
+	has no golden vector — parity-unpinned) and the round trip get_state() → add_past_points() of
+	examples/mackey_glass_parameter_jump.py:55-57: the second integrator continues bit for bit where the first one stands."""
+	from jitcdde_b200 import t, y
+	f = [0.25*y(0, t-15)/(1+y(0, t-15)**10) - 0.1*y(0)]
+	DDE = jitcdde(f, verbose=False, verification=True)
+	DDE.past_from_function(lambda time: [1.0+0.1*np.sin(0.3*time)])
+	DDE.step_on_discontinuities()
+	a = DDE.integrate(DDE.t+50.0)
+	state = DDE.get_state()
+	assert len(state) > 10 and all(np.isfinite(anchor[1]).all() for anchor in state)
+	direct = DDE.integrate(DDE.t+25.0)
+	second = jitcdde(f, verbose=False, verification=True)
+	second.add_past_points(state)
+	second.initial_discontinuities_handled = True
+	second.set_integration_parameters(first_step=float(DDE.dt))
+	continued = second.integrate(second.t+25.0)
+	assert second.t > 0 and np.all(np.isfinite(continued))
+	# the anchors round-trip exactly; the second integrator starts with its own first step, so the states agree to the tolerance
+	np.testing.assert_allclose(continued, direct, rtol=1e-4)
+	again = second.get_state()
+	assert np.array_equal(np.array([anchor[0] for anchor in again])[:3] >= state[0][0], [True]*3)

@@ -289,6 +289,7 @@ def build_net_image(program, block=256, mode=FAST, force=False, verbose=False):
 		with open(os.path.join(CSRC, name), "rb") as f:
 			h.update(f.read())
 	extra = tuple(os.environ.get("JITCDDE_B200_NET_FLAGS", "").split())      # experiments: e.g. -DJDN_RUN_MIN_BLOCKS=6
+	block = int(os.environ.get("JITCDDE_B200_NET_BLOCK", block))
 	tag = hashlib.sha256(repr((program.key, block, mode, extra, h.hexdigest())).encode()).hexdigest()[:20]
 	path = os.path.join(cache_dir(), f"jdn_{tag}.cubin")
 	hit = None if force else _cached(os.path.basename(path))

@@ -602,15 +602,15 @@ class NetEngine:
 
 	def exchange_handle(self):
 		"""CUDA IPC handle of this rank's exchange buffer (bytes), to be passed to the peers"""
-		buffer = ctypes.create_string_buffer(128)      # exchange buffer + history replica
-		self._check(self.lib.jdde_net_exchange_handle(self._h, buffer, 128))
+		buffer = ctypes.create_string_buffer(64)
+		self._check(self.lib.jdde_net_exchange_handle(self._h, buffer, 64))
 		return buffer.raw
 
 	def connect_peers(self, rank, world, handles):
 		"""handles: list of the `world` handles in rank order; afterwards attempt() exchanges through peer memory"""
 		blob = b"".join(handles)
-		assert len(blob) == 128*world
-		self._check(self.lib.jdde_net_connect_peers(self._h, int(rank), int(world), blob, 128))
+		assert len(blob) == 64*world
+		self._check(self.lib.jdde_net_connect_peers(self._h, int(rank), int(world), blob, 64))
 
 	def recent_state(self, t, current_only=False):
 		out = np.empty(self.n)

@@ -187,13 +187,6 @@ class jitcdde_network:
 		if self.verbose:
 			print(f"Anchor ring full; growing to {2*self._engine.ring_capacity} anchors.")
 		self._engine.grow_ring(2*self._engine.ring_capacity)
-		if self.world > 1 and self._exchange == "peer":
-			# every rank has grown at the same attempt: the new history replicas are mapped anew
-			import torch.distributed as dist
-			handles = [None]*self.world
-			dist.all_gather_object(handles, self._engine.exchange_handle())
-			self._engine.connect_peers(self.rank, self.world, handles)
-			dist.barrier()
 		return True
 
 	def _raise(self, status):

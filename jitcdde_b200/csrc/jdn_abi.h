@@ -101,10 +101,6 @@ typedef struct jdn_problem
 	 * (device array; peers[rank] is this rank's own buffer) */
 	int rank, world;
 	jdn_exchange * const * peers;
-	/* persistent stepper (jdn_k_run): the ranks' history replicas, mapped through CUDA IPC like the exchange buffers — the
-	 * step phase stores a node's new (state, diff) pair straight into ring slot current+1 of EVERY replica; no staging
-	 * buffer, no commit pass (peer_hist[rank] is this rank's own `hist`; NULL: not connected) */
-	double * const * peer_hist;
 } jdn_problem;
 
 /* ring slots are grouped by 2^JDN_ROW_GROUP_LOG2 consecutive anchors per node (ring capacities are powers of two >= 4) */

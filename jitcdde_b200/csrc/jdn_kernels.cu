@@ -163,12 +163,13 @@ extern "C" __global__ void jdn_k_exchange(jdn_problem const P)
  * the global scratch array.)
  *
  * A node's new (state, diff) pair goes straight into ring slot current+1 (the tentative anchor: no lookup can reach it,
- * every delay being at least a step), so an accepted step only moves `current`: no staging buffer, no commit pass. With
- * several GPUs the pair is stored into the same slot of every rank's history replica over NVLink while the rank still
- * computes other tiles, block maxima of the error norm go to every rank's exchange header (system-scope atomicMax),
- * and after a grid barrier thread 0 of block 0 tells every peer that this rank's part has been delivered (release
- * increment) and waits until all peers have said the same — the only inter-GPU synchronisation of an attempt, 8 bytes
- * per peer on the critical path — and runs the controller. A second grid barrier publishes its decision.
+ * every delay being at least a step), so an accepted step only moves `current`: no staging buffer, no commit pass on
+ * one GPU. With several GPUs the pair is also stored into every other rank's staging buffer over NVLink — consecutive
+ * nodes, full-width packets — while the rank still computes other tiles; the error norm is merged on the GPU first and
+ * after a grid barrier thread 0 of block 0 passes the rank's maximum to every peer (one system-scope atomicMax each),
+ * tells every peer that this rank's part has been delivered (release increment) and waits until all peers have said
+ * the same — the only inter-GPU synchronisation of an attempt — and runs the controller. A second grid barrier
+ * publishes its decision; after an accepted step the ranks copy the other ranks' nodes from staging into the ring.
  * Grid barriers (cooperative groups: release/acquire at GPU scope) are cumulative with the system-scope release/acquire
  * of the arrival counters. The controller state is read afresh after every barrier.
  */
@@ -301,12 +302,14 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 						jdn::pair staged;
 						staged.state = y_stage;
 						staged.diff = k_4;
-						size_t const where = jdn_pair_index(slot, i, P.n);
-						if (P.world > 1)
-							for (int r = 0; r < P.world; r++)
-								reinterpret_cast<jdn::pair *>(P.peer_hist[r])[where] = staged;
-						else
-							own_hist[where] = staged;
+						/* into the tentative slot of this rank's ring, and — several GPUs — into the staging buffer of every
+						 * other rank: consecutive nodes at consecutive 16-byte pairs, i.e. full-width NVLink packets (the ring
+						 * keeps the pairs of four slots of a node together, 64 bytes from node to node: stores of single
+						 * pairs into the peers' rings measured 0.40 efficiency on 8 GPUs, profiles/) */
+						own_hist[jdn_pair_index(slot, i, P.n)] = staged;
+						for (int r = 0; r < P.world; r++)
+							if (r != P.rank)
+								reinterpret_cast<jdn::pair *>(jdn_exchange_stage(P.peers[r], buffer, P.n))[i] = staged;
 						/* get_p, jitced_template.c:474-498: 0/0 is skipped, a NaN never wins the comparison */
 						double const tolerance = atol + rtol*fabs(y_stage);
 						if (error != 0.0 || tolerance != 0.0)
@@ -333,14 +336,10 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 		{
 			for (int w = 1; w < (JDN_TILE_NODES+31)/32; w++)
 				block_contribution = fmax(block_contribution, s_max[w]);
+			/* merged on this GPU first (one atomic per block on a local word); thread 0 of block 0 passes the maximum of the
+			 * rank on to the peers after the grid barrier — one remote atomic per peer instead of one per block and peer */
 			if (block_contribution > 0.0)
-			{
-				if (P.world > 1)
-					for (int r = 0; r < P.world; r++)
-						atomicMax_system(&P.peers[r]->p_bits[buffer], (unsigned long long)__double_as_longlong(block_contribution));
-				else
-					atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(block_contribution));
-			}
+				atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(block_contribution));
 		}
 		grid.sync();
 
@@ -350,9 +349,10 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 			bool arrived_all = true;
 			if (P.world > 1)
 			{
-				if (C.pws)
+				unsigned long long const mine = C.pws ? JDN_PWS_SENTINEL : C.p_bits;
+				if (mine)
 					for (int r = 0; r < P.world; r++)
-						atomicMax_system(&P.peers[r]->p_bits[buffer], JDN_PWS_SENTINEL);
+						atomicMax_system(&P.peers[r]->p_bits[buffer], mine);
 				__threadfence_system();
 				for (int r = 0; r < P.world; r++)
 					if (r != P.rank)
@@ -396,6 +396,20 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 			__threadfence();
 		}
 		grid.sync();
+		if (P.world > 1 && C.commit_slot >= 0)
+		{
+			/* the step was accepted: the other ranks' nodes go from the staging buffer (written by the peers: read past L1)
+			 * into the ring slot that has just become `current` */
+			int const committed = C.commit_slot;
+			double2 const * const staged = reinterpret_cast<double2 const *>(jdn_exchange_stage(P.peers[P.rank], C.exchanged_buffer, P.n));
+			long long const others = P.n-owned;
+			for (long long k = (long long)blockIdx.x*blockDim.x+threadIdx.x; k < others; k += (long long)gridDim.x*blockDim.x)
+			{
+				long long const i = k < P.lo ? k : k+owned;
+				reinterpret_cast<double2 *>(P.hist)[jdn_pair_index(committed, i, P.n)] = __ldcg(staged+i);
+			}
+			grid.sync();
+		}
 	}
 }
 

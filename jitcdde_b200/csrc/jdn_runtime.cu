@@ -27,9 +27,8 @@ struct jdde_net
 	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr, k_regrow = nullptr, k_run = nullptr;
 	/* peer exchange: this rank's buffer (mapped by the peers through CUDA IPC), the peers' buffers mapped here */
 	jdn_exchange * exchange = nullptr;
-	std::vector<void *> mapped_peers, mapped_hist;
+	std::vector<void *> mapped_peers;
 	jdn_exchange ** d_peers = nullptr;
-	double ** d_peer_hist = nullptr;          /* persistent stepper: the ranks' history replicas (own entry: P.hist) */
 	int peer_rank = 0, peer_world = 1;
 	bool persistent = true;                   /* jdn_k_run (one cooperative launch per batch of attempts) instead of five kernels per attempt */
 	int run_grid = 0;                         /* co-resident blocks of jdn_k_run */
@@ -159,7 +158,6 @@ int jdde_net_destroy(jdde_net * h)
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	if (h->batch) cudaGraphExecDestroy(h->batch);
 	for (void * p : h->mapped_peers) cudaIpcCloseMemHandle(p);
-	for (void * p : h->mapped_hist) cudaIpcCloseMemHandle(p);
 	for (void * p : h->allocations) cudaFree(p);
 	if (h->lib) cudaLibraryUnload(h->lib);
 	if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -425,6 +423,9 @@ static int launch_run(jdde_net * h, int attempts)
 		long long const needed = (work + h->block - 1)/h->block;
 		long long const resident = (long long)per_sm*sms;
 		h->run_grid = (int)(needed < resident ? (needed ? needed : 1) : resident);
+		const char * const cap = getenv("JITCDDE_B200_NET_GRID");      /* experiments: fewer blocks make the grid barriers cheaper */
+		if (cap && atoi(cap) > 0 && atoi(cap) < h->run_grid)
+			h->run_grid = atoi(cap);
 	}
 	long long E = h->desc.n_edges;
 	void * args[] = { &h->P, &h->scratch, &E, &attempts };
@@ -448,7 +449,7 @@ static int run_until_done(jdde_net * h)
 	for (;;)
 	{
 		int rc;
-		if (h->persistent && (h->P.world <= 1 || h->P.peer_hist))
+		if (h->persistent)
 		{
 			if ((rc = launch_run(h, h->poll_every*32))) return rc;
 		}
@@ -508,7 +509,6 @@ int jdde_net_grow_ring(jdde_net * h, int32_t new_capacity)
 	if (h->k_run && (size_t)new_capacity*sizeof(double)+h->run_smem_bytes > 48*1024)
 		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double)+h->run_smem_bytes)));
 	h->run_grid = 0;
-	h->P.peer_hist = nullptr;      /* the peers' mappings of the old history are void: jdde_net_connect_peers again (every rank grows at the same attempt) */
 	double * new_times = nullptr, * new_hist = nullptr;
 	if ((rc = nalloc(h, &new_times, (size_t)new_capacity))) return rc;
 	if ((rc = nalloc(h, &new_hist, 2*(size_t)new_capacity*(size_t)h->desc.n))) return rc;
@@ -590,18 +590,9 @@ int jdde_net_exchange_handle(jdde_net * h, void * handle, size_t handle_bytes)
 	JN_CUDA(h, cudaIpcGetMemHandle(&ipc, h->exchange));
 	memset(handle, 0, handle_bytes);
 	memcpy(handle, &ipc, sizeof ipc);
-	if (handle_bytes >= 2*sizeof(cudaIpcMemHandle_t))
-	{
-		/* second handle: this rank's history replica, into which the peers' persistent steppers store their nodes' anchors */
-		JN_CUDA(h, cudaStreamSynchronize(h->stream));
-		JN_CUDA(h, cudaIpcGetMemHandle(&ipc, h->P.hist));
-		memcpy((char *)handle + sizeof ipc, &ipc, sizeof ipc);
-	}
 	return JDDE_OK;
 }
 
-/* May be called again (after jdde_net_grow_ring, whose new history the peers have to map anew): the exchange buffers stay
- * mapped, the history replicas are mapped afresh. */
 int jdde_net_connect_peers(jdde_net * h, int32_t rank, int32_t world, const void * handles, size_t handle_bytes)
 {
 	int rc = nready(h);
@@ -610,10 +601,8 @@ int jdde_net_connect_peers(jdde_net * h, int32_t rank, int32_t world, const void
 		return nfail(h, JDDE_E_INVALID, "invalid rank, world or handles");
 	if (!h->exchange) return nfail(h, JDDE_E_INVALID, "call jdde_net_exchange_handle first");
 	if (!h->k_exchange) return nfail(h, JDDE_E_IMAGE, "image lacks kernel jdn_k_exchange");
-	if (h->P.world > 1 && (h->P.world != world || h->P.rank != rank)) return nfail(h, JDDE_E_INVALID, "peers already connected with another rank or world size");
+	if (h->P.world > 1) return nfail(h, JDDE_E_INVALID, "peers already connected");
 	JN_CUDA(h, cudaStreamSynchronize(h->stream));
-	bool const first_time = h->P.world <= 1;
-	if (first_time)
 	{
 		std::vector<jdn_exchange *> peers((size_t)world, nullptr);
 		for (int r = 0; r < world; r++)
@@ -632,30 +621,6 @@ int jdde_net_connect_peers(jdde_net * h, int32_t rank, int32_t world, const void
 		}
 		if ((rc = nalloc(h, &h->d_peers, (size_t)world))) return rc;
 		JN_CUDA(h, cudaMemcpy(h->d_peers, peers.data(), (size_t)world*sizeof(jdn_exchange *), cudaMemcpyHostToDevice));
-	}
-	h->P.peer_hist = nullptr;
-	for (void * q : h->mapped_hist) cudaIpcCloseMemHandle(q);
-	h->mapped_hist.clear();
-	if (handle_bytes >= 2*sizeof(cudaIpcMemHandle_t) && h->persistent)
-	{
-		std::vector<double *> replicas((size_t)world, nullptr);
-		for (int r = 0; r < world; r++)
-		{
-			if (r == rank)
-			{
-				replicas[r] = h->P.hist;
-				continue;
-			}
-			cudaIpcMemHandle_t ipc;
-			memcpy(&ipc, (const char *)handles + (size_t)r*handle_bytes + sizeof ipc, sizeof ipc);
-			void * q = nullptr;
-			JN_CUDA(h, cudaIpcOpenMemHandle(&q, ipc, cudaIpcMemLazyEnablePeerAccess));
-			h->mapped_hist.push_back(q);
-			replicas[r] = static_cast<double *>(q);
-		}
-		if (!h->d_peer_hist && (rc = nalloc(h, &h->d_peer_hist, (size_t)world))) return rc;
-		JN_CUDA(h, cudaMemcpy(h->d_peer_hist, replicas.data(), (size_t)world*sizeof(double *), cudaMemcpyHostToDevice));
-		h->P.peer_hist = h->d_peer_hist;
 	}
 	drop_batch(h);
 	h->P.peers = h->d_peers;

@@ -128,6 +128,11 @@ int jdde_set_max_delay(jdde_handle * h, double max_delay);
  * (_jitcdde.py:775-861). target: 1 value or [n_members]; out_state [n_members][n]; status [n_members]. */
 int jdde_integrate(jdde_handle * h, const double * target, int32_t per_member, double * out_state, int32_t * status);
 
+/* jdde_integrate that also reports where every member stands afterwards (get_t, jitced_template.c:187, which the reference's
+ * integrate consults before every call, _jitcdde.py:824): t_after[n_members], fetched with the states in the same
+ * synchronisation — a sampling loop over single calls then costs one host↔device round trip per call, not three. */
+int jdde_integrate_t(jdde_handle * h, const double * target, int32_t per_member, double * out_state, int32_t * status, double * t_after);
+
 /* Pipelined sampling: as jdde_integrate, but returns as soon as the work is queued. If out_state is page-locked
  * memory the GPU can address (jdde_host_alloc, cudaHostAlloc, registered memory), the kernel writes the states
  * straight into it (also in jdde_integrate); otherwise they are copied on a second stream while the next call's

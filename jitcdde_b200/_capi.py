@@ -55,6 +55,7 @@ SIGNATURES = {
 	"jdde_set_parameters": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32]),
 	"jdde_set_integration_parameters": (ctypes.c_int, [_H, ctypes.POINTER(IntParams), ctypes.c_double]),
 	"jdde_integrate": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, c_int32_p]),
+	"jdde_integrate_t": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p, c_int32_p, c_double_p]),
 	"jdde_integrate_async": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, c_double_p]),
 	"jdde_wait_result": (ctypes.c_int, [_H, ctypes.c_int32]),
 	"jdde_integrate_samples": (ctypes.c_int, [_H, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_int32_p]),
@@ -280,6 +281,15 @@ class Engine:
 		self._check(self.lib.jdde_integrate(self._h, _dp(target), pm, _dp(out) if fetch else None,
 			status.ctypes.data_as(c_int32_p) if status is not None else None))
 		return out, status
+
+	def integrate_t(self, target, out=None):
+		"""integrate() that returns (states, status, times of the members afterwards) after ONE synchronisation"""
+		target, pm = self._targets(target)
+		out = np.empty((self.N, self.n)) if out is None else self._checked_out(out, (self.N, self.n))
+		status = np.empty(self.N, dtype=np.int32)
+		t_after = np.empty(self.N)
+		self._check(self.lib.jdde_integrate_t(self._h, _dp(target), pm, _dp(out), status.ctypes.data_as(c_int32_p), _dp(t_after)))
+		return out, status, t_after
 
 	def integrate_async(self, target, out):
 		"""queue an integrate() whose result lands in `out` (page-locked, (N, n) float64) by the next synchronize()"""

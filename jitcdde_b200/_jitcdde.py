@@ -503,7 +503,7 @@ class jitcdde:
 		`ring_capacity` large enough or sample synchronously).
 		"""
 		self._initiate()
-		if self.n_members == 1 and wait and self._engine.get_t()[0] > target_time:
+		if self.n_members == 1 and wait and self._current_t() > target_time:
 			warn("The target time is smaller than the current time. No integration step will happen. The returned state will be extrapolated from the interpolating Hermite polynomial for the last integration step. You may see this because you try to integrate backwards in time, in which case you did something wrong. You may see this just because your sampling step is small, in which case there is no need to worry (though you should think about increasing your sampling time).", stacklevel=2)
 		if not self.initial_discontinuities_handled:
 			warn("You did not explicitly handle initial discontinuities. Proceed only if you know what you are doing. This is only fine if you somehow chose your initial past such that the derivative of the last anchor complies with the DDE. In this case, you can set the attribute `initial_discontinuities_handled` to `True` to suppress this warning. See https://jitcdde.rtfd.io/#discontinuities for details.", stacklevel=2)
@@ -514,9 +514,17 @@ class jitcdde:
 			return self._engine.integrate_async(target_time, out)
 		if getattr(self, "_queued", False):
 			self.synchronize()
-		# the per-member status stays on the device unless a member failed (8 bytes back instead of 4·N)
-		result, status = self._engine.integrate(target_time, out=out, fetch_status=False)
-		status = self._engine.get_status() if self._engine.count_failed() else None
+		if self.n_members == 1:
+			# one trajectory (the reference's use): state, status and the time reached come back in one round trip; the time
+			# serves the check above at the next call (the reference asks get_t before every call, _jitcdde.py:824)
+			result, status, t_after = self._engine.integrate_t(target_time, out=out)
+			self._t_known = (self._engine, float(t_after[0])) if not status.any() else None
+			self._t_known_launches = self._engine.launch_count      # any later launch (jump, new past, …) voids the cached time
+			status = status if status.any() else None
+		else:
+			# the per-member status stays on the device unless a member failed (8 bytes back instead of 4·N)
+			result, status = self._engine.integrate(target_time, out=out, fetch_status=False)
+			status = self._engine.get_status() if self._engine.count_failed() else None
 		while self._check_status(status, retry=True):
 			result, status = self._engine.resume()
 			if out is not None:
@@ -551,6 +559,13 @@ class jitcdde:
 		while self._check_status(status, retry=True):
 			result, status = self._engine.resume(samples=result)
 		return result[:, 0].copy() if self.n_members == 1 and out is None else result
+
+	def _current_t(self):
+		"""time of a single trajectory: as reported by the last integrate() if nothing else has touched the engine since"""
+		known = getattr(self, "_t_known", None)
+		if known is not None and known[0] is self._engine and self._engine.launch_count == getattr(self, "_t_known_launches", -1):
+			return known[1]
+		return float(self._engine.get_t()[0])
 
 	def wait_result(self, age=0):
 		"""wait for the `out` of the `integrate(..., wait=False)` call `age` calls ago (0: the latest, 1: the one before)

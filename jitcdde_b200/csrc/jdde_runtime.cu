@@ -721,6 +721,22 @@ int jdde_integrate(jdde_handle * h, const double * target, int32_t per_member, d
 	return run_integrate(h, target, per_member ? (size_t)h->desc.n_members : 1, per_member, 0, 0, out_state, h->desc.n, status);
 }
 
+int jdde_integrate_t(jdde_handle * h, const double * target, int32_t per_member, double * out_state, int32_t * status, double * t_after)
+{
+	int rc = ready_to_integrate(h);
+	if (rc) return rc;
+	if (!t_after)
+		return fail(h, JDDE_E_INVALID, "null argument");
+	h->last_kind = 1;
+	/* the kernel, the times of the members (jdde_k_get) and the copies are queued; one synchronisation at the end */
+	if ((rc = run_integrate(h, target, per_member ? (size_t)h->desc.n_members : 1, per_member, 0, 0, nullptr, h->desc.n, nullptr))) return rc;
+	int what = 0;
+	void * gargs[] = { &h->P, &what, &h->d_aux };
+	if ((rc = launch(h, h->k.get, gargs))) return rc;
+	JD_CUDA(h, cudaMemcpyAsync(t_after, h->d_aux, (size_t)h->desc.n_members*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	return finish(h, out_state, h->d_out, (size_t)h->desc.n_members*h->desc.n, status);
+}
+
 int jdde_integrate_async(jdde_handle * h, const double * target, int32_t per_member, double * out_state)
 {
 	if (!h)

@@ -136,6 +136,8 @@ static void remember(jdde_handle * h, int kind, const double * targets, size_t c
 	h->last_targets.assign(targets, targets+count);
 }
 
+extern "C" int jdde_get_t(jdde_handle * h, double * t);
+
 static void run_integrate(jdde_handle * h, const double * targets, int pm, int n_steps, int resume, int n_out)
 {
 	for (long long m = 0; m < h->P.n_members; m++)
@@ -150,6 +152,12 @@ int jdde_integrate(jdde_handle * h, const double * target, int32_t pm, double * 
 	run_integrate(h, target, pm, 0, 0, JD_N);
 	give(h, out, h->out, (size_t)h->P.n_members*JD_N, status);
 	return JDDE_OK;
+}
+
+int jdde_integrate_t(jdde_handle * h, const double * target, int32_t pm, double * out, int32_t * status, double * t_after)
+{
+	if (int rc = jdde_integrate(h, target, pm, out, status)) return rc;
+	return jdde_get_t(h, t_after);
 }
 
 int jdde_integrate_async(jdde_handle * h, const double * target, int32_t pm, double * out)

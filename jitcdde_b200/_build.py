@@ -95,6 +95,20 @@ def _evict(limit_mb=None):
 			pass
 
 
+def _write_atomically(path, text):
+	"""generated include files: written under a process-private name and renamed (several ranks generate the same file)"""
+	try:
+		with open(path) as f:
+			if f.read() == text:
+				return
+	except OSError:
+		pass
+	tmp = f"{path}.{os.getpid()}.tmp"
+	with open(tmp, "w") as f:
+		f.write(text)
+	os.replace(tmp, path)
+
+
 def _stale(target, stamp_value):
 	"""A built file is current if its stamp file holds the hash of the sources it was built from (content, not
 	mtimes: the tree is copied to other machines, and several ranks may import the package at once)."""
@@ -251,8 +265,7 @@ def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), fo
 	if hit:
 		return hit
 	rhs = os.path.join(cache_dir(), f"rhs_{program.key}.inc")
-	with open(rhs, "w") as f:
-		f.write(program.body)
+	_write_atomically(rhs, program.body)
 	flags = ["-O3", "-std=c++17", "-lineinfo", *ARCH]
 	group_flags = []
 	if use_group(program):
@@ -264,19 +277,20 @@ def build_image(program, n_basic=None, mode=FAST, block=None, extra_flags=(), fo
 		flags.append("-DJD_FAST=1")
 	else:
 		raise ValueError(mode)
+	tmp = f"{path}.{os.getpid()}.tmp"      # several ranks may build the same image at once: every process its own temporary, the rename is atomic
 	cmd = [nvcc(), "-cubin", *flags,
 		f"-DJD_N={program.n}", f"-DJD_NBASIC={n_basic}", f"-DJD_NSITES={program.n_sites}",
 		f"-DJD_NPARAMS={program.n_params}", f'-DJD_RHS_FILE="{rhs}"', f"-DJD_BLOCK={block}",
 		f"-DJD_WINDOW={int(use_window(program))}",
 		*group_flags,
 		*extra_flags,
-		os.path.join(CSRC, "jdde_kernels.cu"), "-o", path + ".tmp"]
+		os.path.join(CSRC, "jdde_kernels.cu"), "-o", tmp]
 	if verbose:
 		print(" ".join(cmd))
 	result = subprocess.run(cmd, capture_output=True, text=True)
 	if result.returncode:
 		raise RuntimeError(f"nvcc failed:\n{result.stderr}\ncommand: {' '.join(cmd)}")
-	os.replace(path + ".tmp", path)
+	os.replace(tmp, path)
 	_evict()
 	return path
 
@@ -296,22 +310,23 @@ def build_net_image(program, block=256, mode=FAST, force=False, verbose=False):
 	if hit:
 		return hit
 	rhs = os.path.join(cache_dir(), f"net_{program.key}.inc")
-	with open(rhs, "w") as f:
-		f.write(program.body)
+	_write_atomically(rhs, program.body)
 	if mode == VERIFY:
 		mode_flags = ["-fmad=false"]
 	elif mode == FAST:
 		mode_flags = ["-DJD_FAST=1"]
 	else:
 		raise ValueError(mode)
+	tmp = f"{path}.{os.getpid()}.tmp"
 	cmd = [nvcc(), "-cubin", "-O3", "-std=c++17", "-lineinfo", *ARCH, *mode_flags, *extra, f'-DJDN_RHS_FILE="{rhs}"', f"-DJDN_BLOCK={block}",
-		os.path.join(CSRC, "jdn_kernels.cu"), "-o", path + ".tmp"]
+		os.path.join(CSRC, "jdn_kernels.cu"), "-o", tmp]
 	if verbose:
 		print(" ".join(cmd))
 	result = subprocess.run(cmd, capture_output=True, text=True)
 	if result.returncode:
 		raise RuntimeError(f"nvcc failed:\n{result.stderr}\ncommand: {' '.join(cmd)}")
-	os.replace(path + ".tmp", path)
+	os.replace(tmp, path)
+	_evict()
 	return path
 
 
@@ -323,9 +338,9 @@ def build_peak_image(force=False):
 	if hit:
 		return hit
 	path = os.path.join(cache_dir(), name)
-	if True:
-		subprocess.run([nvcc(), "-cubin", "-O3", "-lineinfo", *ARCH, src, "-o", path + ".tmp"], check=True)
-		os.replace(path + ".tmp", path)
+	tmp = f"{path}.{os.getpid()}.tmp"
+	subprocess.run([nvcc(), "-cubin", "-O3", "-lineinfo", *ARCH, src, "-o", tmp], check=True)
+	os.replace(tmp, path)
 	return path
 
 
@@ -363,8 +378,8 @@ def load_image_file(path):
 	if hit:
 		return meta, hit
 	target = os.path.join(cache_dir(), name)
-	with open(target + ".tmp", "wb") as f:
+	with open(f"{target}.{os.getpid()}.tmp", "wb") as f:
 		f.write(blob)
-	os.replace(target + ".tmp", target)
+	os.replace(f"{target}.{os.getpid()}.tmp", target)
 	_evict()
 	return meta, target

@@ -428,10 +428,13 @@ def gpu_arm(args):
 	for i in range(2):
 		DDE.integrate_samples(times_of(S), out=outs[i])
 	accepted_before = engine.sum_counters()[0]
+	# launch sizes: S samples per launch, tapering off towards the end (…, S, S/2, S/4, …) — the copy of one launch's states to the
+	# host overlaps the kernel of the next, so only the LAST launch's copy is exposed, and a small last launch keeps it short
 	e2e_launches = []
 	left = args.steps
 	while left > 0:
-		e2e_launches.append(min(S, left))
+		n = S if left >= 2*S else max(1, (left+1)//2) if left > 2 else left
+		e2e_launches.append(min(n, left))
 		left -= e2e_launches[-1]
 	barrier()
 	w0 = time.perf_counter()
@@ -463,7 +466,7 @@ def gpu_arm(args):
 		"ms_per_step": ms/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
 		"dtype": "f64", "data": "synthetic", "config": dict(config(members, world), samples_per_launch=S),
 		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(members*8),
-			"ms_per_step": e2e_ms/args.steps, "api": "DDE.integrate_samples(times, out=pinned, wait=False) + wait_result(1) per launch, synchronize() at the end"},
+			"ms_per_step": e2e_ms/args.steps, "api": "DDE.integrate_samples(times, out=pinned, wait=False) + wait_result(1) per launch, synchronize() at the end", "samples_per_launch": e2e_launches},
 		"gpu_launches": int(launches),
 		"clocks": clocks.summary(),
 		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": traffic,

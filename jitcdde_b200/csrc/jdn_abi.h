@@ -101,6 +101,11 @@ typedef struct jdn_problem
 	 * (device array; peers[rank] is this rank's own buffer) */
 	int rank, world;
 	jdn_exchange * const * peers;
+	/* warp tiles of the persistent stepper: consecutive owned nodes (rows tile_start[k] … tile_start[k+1]−1 of row_ptr) with at
+	 * most 32 nodes and at most 32 in-edges together — one lane per edge, one lane per node — or a single node with more
+	 * in-edges (handled in rounds); built by jdde_net_set_graph */
+	int const * tile_start;
+	long long n_warp_tiles;
 } jdn_problem;
 
 /* ring slots are grouped by 2^JDN_ROW_GROUP_LOG2 consecutive anchors per node (ring capacities are powers of two >= 4) */

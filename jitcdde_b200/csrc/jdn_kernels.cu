@@ -173,6 +173,77 @@ extern "C" __global__ void jdn_k_exchange(jdn_problem const P)
  * Grid barriers (cooperative groups: release/acquire at GPU scope) are cumulative with the system-scope release/acquire
  * of the arrival counters. The controller state is read afresh after every barrier.
  */
+/* end of an attempt in the persistent steppers, thread 0 of block 0: exchange barrier between the GPUs, then the controller */
+__device__ __forceinline__ void jdn_run_exchange_and_control(jdn_problem const & P, jdn_control & C, int const buffer)
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0)
+		return;
+	bool arrived_all = true;
+	if (P.world > 1)
+	{
+		unsigned long long const mine = C.pws ? JDN_PWS_SENTINEL : C.p_bits;
+		if (mine)
+			for (int r = 0; r < P.world; r++)
+				atomicMax_system(&P.peers[r]->p_bits[buffer], mine);
+		__threadfence_system();
+		for (int r = 0; r < P.world; r++)
+			if (r != P.rank)
+				asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(&P.peers[r]->arrived), "l"(1ull) : "memory");
+		jdn_exchange * const own = P.peers[P.rank];
+		unsigned long long const expected = (C.epoch+1)*(unsigned long long)(P.world-1);
+		unsigned long long start, now, arrived;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
+		for (;;)
+		{
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(arrived) : "l"(&own->arrived) : "memory");
+			if (arrived >= expected)
+				break;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			if (now-start > 20000000000ull)      /* a peer that does not arrive within 20 s ends the integration instead of hanging the device */
+			{
+				C.exchange_failed = 1;
+				C.status = JDDE_STATUS_NONFINITE;
+				C.done = 1;
+				arrived_all = false;
+				break;
+			}
+			__nanosleep(100);
+		}
+		if (arrived_all)
+		{
+			unsigned long long const bits = atomicExch_system(&own->p_bits[buffer], 0ull);
+			if (bits == JDN_PWS_SENTINEL)
+			{
+				C.pws = 1;
+				C.p_bits = 0;
+			}
+			else
+				C.p_bits = bits;
+			C.exchanged_buffer = buffer;
+			C.epoch++;
+		}
+	}
+	if (arrived_all)
+		jdn::control(P);
+	__threadfence();
+}
+
+/* after an accepted step, several GPUs: the other ranks' nodes go from the staging buffer (written by the peers: read past L1)
+ * into the ring slot that has just become `current` (all threads of the grid; a grid barrier follows) */
+__device__ __forceinline__ void jdn_run_commit(jdn_problem const & P, jdn_control const & C, long long const owned)
+{
+	if (P.world <= 1 || C.commit_slot < 0)
+		return;
+	int const committed = C.commit_slot;
+	double2 const * const staged = reinterpret_cast<double2 const *>(jdn_exchange_stage(P.peers[P.rank], C.exchanged_buffer, P.n));
+	long long const others = P.n-owned;
+	for (long long k = (long long)blockIdx.x*blockDim.x+threadIdx.x; k < others; k += (long long)gridDim.x*blockDim.x)
+	{
+		long long const i = k < P.lo ? k : k+owned;
+		reinterpret_cast<double2 *>(P.hist)[jdn_pair_index(committed, i, P.n)] = __ldcg(staged+i);
+	}
+}
+
 #if JDN_TILE_NODES > JDN_BLOCK-1 || JDN_TILE_NODES > 256
 #error "a tile needs one thread per node (and one more for the row offsets) and its node indices fit a byte"
 #endif
@@ -343,73 +414,191 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 		}
 		grid.sync();
 
-		/* exchange barrier between the GPUs, then the controller */
-		if (blockIdx.x == 0 && threadIdx.x == 0)
+		jdn_run_exchange_and_control(P, C, buffer);
+		grid.sync();
+		jdn_run_commit(P, C, owned);
+		if (P.world > 1 && C.commit_slot >= 0)
+			grid.sync();
+	}
+}
+
+/*
+ * The persistent stepper, warp tiles (a variant, JITCDDE_B200_NET_TILES=warp; jdn_k_run above takes a thread block per tile
+ * of 64 nodes and needs seven block barriers per tile — 6.8 warps stalled at a barrier per issued instruction,
+ * profiles/ — but this one needs more registers than it gets and measured 0.77 against 0.65 ms per attempt): a WARP takes a
+ * tile of consecutive nodes with at most 32 in-edges together — lane k does the lookups of edge k (the three delayed
+ * values stay in its registers) and, stage by stage, its term weight·coupling(·, y_stage of its node); lane j < nn is
+ * also the thread of node j: it collects the terms of its node by shuffles in the order of the edge list (the
+ * reference's order, bit-identical) and forms the next stage state, which the edge lanes fetch by shuffle. No block
+ * barrier, no shared memory but the anchor times; the warps of an SM are at different points of their tiles and hide
+ * each other's latencies. A node with more than 32 in-edges is a tile of its own: its lanes take the edges in rounds,
+ * the delayed values go through the scratch array. Exchange between the GPUs, controller and grid barriers as above.
+ */
+#ifndef JDN_WARP_MIN_BLOCKS
+#define JDN_WARP_MIN_BLOCKS 3
+#endif
+
+extern "C" __global__ void __launch_bounds__(JDN_BLOCK, JDN_WARP_MIN_BLOCKS)
+jdn_k_run_warp(jdn_problem const P, double * const scratch, long long const n_edges, int const max_attempts)
+{
+	extern __shared__ double s_times[];                /* cap doubles */
+	__shared__ double s_max[JDN_BLOCK/32];
+	namespace cg = cooperative_groups;
+	cg::grid_group grid = cg::this_grid();
+	jdn_control & C = *P.ctrl;
+	jdn::pair * const own_hist = reinterpret_cast<jdn::pair *>(P.hist);
+	long long const owned = P.hi-P.lo;
+	int const lane = threadIdx.x & 31;
+	long long const warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+	long long const n_warps = ((long long)gridDim.x*blockDim.x) >> 5;
+	unsigned const full = 0xffffffffu;
+	for (int attempt = 0; attempt < max_attempts; attempt++)
+	{
+		if (C.done)
+			break;      /* (every thread of every block sees the same value: written before the last grid barrier) */
+		jdn::View V = jdn::view_of(P);
+		double const h = C.h;
+		double const atol = C.P.atol, rtol = C.P.rtol;
+		int const slot = (V.current+1) & V.mask;
+		int const buffer = (int)(C.epoch & 1);
+		for (int k = threadIdx.x; k < P.cap; k += blockDim.x)
+			s_times[k] = P.times[k];
+		__syncthreads();
+		V.times = s_times;
+		double const t1 = V.t_cur+0.5*h, t2 = V.t_cur+0.75*h, t3 = V.t_cur+h;
+		int pws = 0;
+		double contribution = -1.0;      /* (node lanes) */
+
+		for (long long tile = warp; tile < P.n_warp_tiles; tile += n_warps)
 		{
-			bool arrived_all = true;
-			if (P.world > 1)
+			int const row0 = P.tile_start[tile];
+			int const nn = P.tile_start[tile+1]-row0;
+			/* row offsets of the tile: lane j holds the first edge of node j (lane nn: the end) */
+			long long const my_row = lane <= nn ? P.row_ptr[row0+lane] : 0;
+			long long const e0 = __shfl_sync(full, my_row, 0);
+			int const ne = (int)(__shfl_sync(full, my_row, nn)-e0);
+			int const first = (int)(my_row-e0);                                   /* node lane: first edge of my node within the tile */
+			int const degree = (int)(__shfl_down_sync(full, my_row, 1)-my_row);    /* node lane: in-degree of my node */
+			long long const i = P.lo+row0+lane;                                    /* node lane: my node */
+			bool const is_node = lane < nn;
+			double y = 0.0, k_1 = 0.0, k_2 = 0.0, k_3 = 0.0, y_stage = 0.0;
+			double par[JDN_NPARAMS > 0 ? JDN_NPARAMS : 1];
+			if (is_node)
 			{
-				unsigned long long const mine = C.pws ? JDN_PWS_SENTINEL : C.p_bits;
-				if (mine)
-					for (int r = 0; r < P.world; r++)
-						atomicMax_system(&P.peers[r]->p_bits[buffer], mine);
-				__threadfence_system();
-				for (int r = 0; r < P.world; r++)
-					if (r != P.rank)
-						asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(&P.peers[r]->arrived), "l"(1ull) : "memory");
-				jdn_exchange * const own = P.peers[P.rank];
-				unsigned long long const expected = (C.epoch+1)*(unsigned long long)(P.world-1);
-				unsigned long long start, now, arrived;
-				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
-				for (;;)
+				jdn::pair const cur = own_hist[jdn_pair_index(V.current & V.mask, i, P.n)];
+				y = cur.state;
+				k_1 = cur.diff;
+				for (int q = 0; q < JDN_NPARAMS; q++)
+					par[q] = P.node_par[(size_t)q*P.n+i];
+				y_stage = y + 0.5*h*k_1;
+			}
+			bool const small = ne <= 32;
+			double v1 = 0.0, v2 = 0.0, v3 = 0.0, weight = 0.0;
+			int node = 0;
+			int most = 0;       /* largest in-degree of the tile's nodes: how many terms the node lanes collect */
+			if (small)
+			{
+				if (lane < ne)
 				{
-					asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(arrived) : "l"(&own->arrived) : "memory");
-					if (arrived >= expected)
-						break;
-					asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-					if (now-start > 20000000000ull)      /* a peer that does not arrive within 20 s ends the integration instead of hanging the device */
-					{
-						C.exchange_failed = 1;
-						C.status = JDDE_STATUS_NONFINITE;
-						C.done = 1;
-						arrived_all = false;
-						break;
-					}
-					__nanosleep(100);
+					jdn::lookup_edge_values(P, V, h, e0+lane, v1, v2, v3, pws);
+					weight = P.weight[e0+lane];
 				}
-				if (arrived_all)
+				/* the node this lane's edge leads to: the last node whose first edge is at or before it */
+				for (int j = 1; j < nn; j++)
+					node += __shfl_sync(full, first, j) <= lane;
+				most = is_node ? degree : 0;
+				for (int o = 16; o > 0; o >>= 1)
+					most = max(most, __shfl_xor_sync(full, most, o));
+			}
+			else
+			{
+				/* one node with many in-edges: lookups in rounds of 32, values through the scratch array */
+				for (long long e = e0+lane; e < e0+ne; e += 32)
+					jdn::lookup_edge(P, V, h, e, scratch, pws);
+				__syncwarp();
+			}
+			for (int stage = 0; stage < 3; stage++)
+			{
+				double const t_stage = stage == 0 ? t1 : stage == 1 ? t2 : t3;
+				double acc = 0.0;
+				if (small)
 				{
-					unsigned long long const bits = atomicExch_system(&own->p_bits[buffer], 0ull);
-					if (bits == JDN_PWS_SENTINEL)
+					/* every edge lane: its term of this stage with the stage state of its node … */
+					double const ys = __shfl_sync(full, y_stage, node);
+					double const yd = stage == 0 ? v1 : stage == 1 ? v2 : v3;
+					double const term = lane < ne ? weight*JDN_COUPLING(yd, ys) : 0.0;
+					/* … every node lane: local part + the terms of its node in the order of the edge list */
+					if (is_node)
+						acc = JDN_LOCAL(y_stage, t_stage, par);
+					for (int q = 0; q < most; q++)
 					{
-						C.pws = 1;
-						C.p_bits = 0;
+						double const tq = __shfl_sync(full, term, (first+q) & 31);
+						if (is_node && q < degree)
+							acc += tq;
+					}
+				}
+				else if (lane == 0)
+				{
+					acc = JDN_LOCAL(y_stage, t_stage, par);
+					for (long long e = e0; e < e0+ne; e++)
+						acc += P.weight[e]*JDN_COUPLING(scratch[3*e+stage], y_stage);
+				}
+				if (is_node)
+				{
+					if (stage == 0)
+					{
+						k_2 = acc;
+						y_stage = y + 0.75*h*k_2;
+					}
+					else if (stage == 1)
+					{
+						k_3 = acc;
+						y_stage = y + (h/9.) * (2*k_1+3*k_2+4*k_3);
 					}
 					else
-						C.p_bits = bits;
-					C.exchanged_buffer = buffer;
-					C.epoch++;
+					{
+						double const k_4 = acc;
+						double const error = fabs((5*k_1-6*k_2-8*k_3+9*k_4) * (h/72.));
+						jdn::pair staged;
+						staged.state = y_stage;
+						staged.diff = k_4;
+						own_hist[jdn_pair_index(slot, i, P.n)] = staged;
+						for (int r = 0; r < P.world; r++)
+							if (r != P.rank)
+								reinterpret_cast<jdn::pair *>(jdn_exchange_stage(P.peers[r], buffer, P.n))[i] = staged;
+						/* get_p, jitced_template.c:474-498: 0/0 is skipped, a NaN never wins the comparison */
+						double const tolerance = atol + rtol*fabs(y_stage);
+						if (error != 0.0 || tolerance != 0.0)
+						{
+							double const c = error/tolerance;
+							if (c >= 0.0)
+								contribution = fmax(contribution, c);
+						}
+					}
 				}
 			}
-			if (arrived_all)
-				jdn::control(P);
-			__threadfence();
+		}
+		if (pws)
+			C.pws = 1;
+		/* error norm of this block's nodes, merged on this GPU */
+		for (int o = 16; o > 0; o >>= 1)
+			contribution = fmax(contribution, __shfl_down_sync(full, contribution, o));
+		if (lane == 0)
+			s_max[threadIdx.x >> 5] = contribution;
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			for (int w = 1; w < JDN_BLOCK/32; w++)
+				contribution = fmax(contribution, s_max[w]);
+			if (contribution > 0.0)
+				atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(contribution));
 		}
 		grid.sync();
+		jdn_run_exchange_and_control(P, C, buffer);
+		grid.sync();
+		jdn_run_commit(P, C, owned);
 		if (P.world > 1 && C.commit_slot >= 0)
-		{
-			/* the step was accepted: the other ranks' nodes go from the staging buffer (written by the peers: read past L1)
-			 * into the ring slot that has just become `current` */
-			int const committed = C.commit_slot;
-			double2 const * const staged = reinterpret_cast<double2 const *>(jdn_exchange_stage(P.peers[P.rank], C.exchanged_buffer, P.n));
-			long long const others = P.n-owned;
-			for (long long k = (long long)blockIdx.x*blockDim.x+threadIdx.x; k < others; k += (long long)gridDim.x*blockDim.x)
-			{
-				long long const i = k < P.lo ? k : k+owned;
-				reinterpret_cast<double2 *>(P.hist)[jdn_pair_index(committed, i, P.n)] = __ldcg(staged+i);
-			}
 			grid.sync();
-		}
 	}
 }
 

@@ -24,7 +24,7 @@ struct jdde_net
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	cudaLibrary_t lib = nullptr;
-	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr, k_regrow = nullptr, k_run = nullptr;
+	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr, k_regrow = nullptr, k_run = nullptr, k_run_warp = nullptr;
 	/* peer exchange: this rank's buffer (mapped by the peers through CUDA IPC), the peers' buffers mapped here */
 	jdn_exchange * exchange = nullptr;
 	std::vector<void *> mapped_peers;
@@ -33,6 +33,8 @@ struct jdde_net
 	bool persistent = true;                   /* jdn_k_run (one cooperative launch per batch of attempts) instead of five kernels per attempt */
 	int run_grid = 0;                         /* co-resident blocks of jdn_k_run */
 	int run_smem_bytes = 0;                   /* its dynamic shared memory beyond the anchor times (image descriptor) */
+	bool warp_tiles = false;                  /* jdn_k_run_warp (a warp per tile of <= 32 in-edges) instead of jdn_k_run (a block per tile of 64 nodes) */
+	int * d_tile_start = nullptr;
 	/* `poll_every` attempts (lookup, step, [exchange], control, commit: 4–5 launches each) captured once as a CUDA graph and
 	 * replayed: small networks are bound by launch gaps, not by the kernels (10^5 nodes: 45 µs of kernels per 70 µs attempt) */
 	cudaGraphExec_t batch = nullptr;
@@ -203,9 +205,18 @@ int jdde_net_load_image(jdde_net * h, const void * image, size_t len)
 		h->k_run = nullptr;
 		(void)cudaGetLastError();
 	}
+	if (cudaLibraryGetKernel(&h->k_run_warp, h->lib, "jdn_k_run_warp") != cudaSuccess)
+	{
+		h->k_run_warp = nullptr;
+		(void)cudaGetLastError();
+	}
 	h->run_grid = 0;
 	const char * const choice = getenv("JITCDDE_B200_NET_PERSISTENT");
 	h->persistent = h->k_run && !(choice && choice[0] == '0');
+	const char * const tiles = getenv("JITCDDE_B200_NET_TILES");
+	h->warp_tiles = h->k_run_warp && tiles && tiles[0] == 'w';      /* "warp": the warp-per-tile variant (measured slower: its registers spill, profiles/configs_r02.md) */
+	if (h->k_run_warp && (size_t)h->P.cap*sizeof(double) > 48*1024)
+		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->P.cap*sizeof(double))));
 	/* the bracket search keeps the anchor times in shared memory: 8 bytes per ring slot */
 	if ((size_t)h->P.cap*sizeof(double) > 48*1024)
 		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->P.cap*sizeof(double))));
@@ -240,6 +251,38 @@ int jdde_net_set_graph(jdde_net * h, const int64_t * row_ptr, const int32_t * sr
 	JN_CUDA(h, cudaMemcpyAsync(h->d_tau, tau, E*sizeof(double), cudaMemcpyHostToDevice, h->stream));
 	JN_CUDA(h, cudaMemcpyAsync(h->d_weight, weight, E*sizeof(double), cudaMemcpyHostToDevice, h->stream));
 	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	/* warp tiles of the persistent stepper: consecutive nodes while they are at most 32 and have at most 32 in-edges together;
+	 * a node with more in-edges is a tile of its own */
+	{
+		std::vector<int> tiles;
+		tiles.push_back(0);
+		size_t row = 0;
+		while (row < owned)
+		{
+			size_t end = row+1;
+			int64_t edges = row_ptr[row+1]-row_ptr[row];
+			while (end < owned && end-row < 32 && edges+(row_ptr[end+1]-row_ptr[end]) <= 32)
+			{
+				edges += row_ptr[end+1]-row_ptr[end];
+				end++;
+			}
+			tiles.push_back((int)end);
+			row = end;
+		}
+		if (h->d_tile_start)
+		{
+			for (auto it = h->allocations.begin(); it != h->allocations.end(); ++it)
+				if (*it == h->d_tile_start) { h->allocations.erase(it); break; }
+			cudaFree(h->d_tile_start);
+			h->d_tile_start = nullptr;
+		}
+		int rc2 = nalloc(h, &h->d_tile_start, tiles.size());
+		if (rc2) return rc2;
+		JN_CUDA(h, cudaMemcpy(h->d_tile_start, tiles.data(), tiles.size()*sizeof(int), cudaMemcpyHostToDevice));
+		h->P.tile_start = h->d_tile_start;
+		h->P.n_warp_tiles = (long long)tiles.size()-1;
+		h->run_grid = 0;
+	}
 	h->have_graph = true;
 	return JDDE_OK;
 }
@@ -412,15 +455,22 @@ static int launch_run(jdde_net * h, int attempts)
 {
 	int rc;
 	if ((rc = nready_run(h))) return rc;
-	size_t const smem = (size_t)h->P.cap*sizeof(double)+(size_t)h->run_smem_bytes;
+	cudaKernel_t const kernel = h->warp_tiles ? h->k_run_warp : h->k_run;
+	size_t const smem = (size_t)h->P.cap*sizeof(double)+(h->warp_tiles ? 0 : (size_t)h->run_smem_bytes);
 	if (!h->run_grid)
 	{
 		int per_sm = 0, sms = 0;
-		JN_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)h->k_run, h->block, smem));
+		JN_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kernel, h->block, smem));
 		JN_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->desc.device));
-		if (per_sm < 1) return nfail(h, JDDE_E_CUDA, "jdn_k_run does not fit an SM");
-		long long const work = h->desc.n_edges > h->desc.hi-h->desc.lo ? h->desc.n_edges : h->desc.hi-h->desc.lo;
-		long long const needed = (work + h->block - 1)/h->block;
+		if (per_sm < 1) return nfail(h, JDDE_E_CUDA, "the persistent stepper does not fit an SM");
+		long long needed;
+		if (h->warp_tiles)
+			needed = (h->P.n_warp_tiles*32 + h->block - 1)/h->block;
+		else
+		{
+			long long const work = h->desc.n_edges > h->desc.hi-h->desc.lo ? h->desc.n_edges : h->desc.hi-h->desc.lo;
+			needed = (work + h->block - 1)/h->block;
+		}
 		long long const resident = (long long)per_sm*sms;
 		h->run_grid = (int)(needed < resident ? (needed ? needed : 1) : resident);
 		const char * const cap = getenv("JITCDDE_B200_NET_GRID");      /* experiments: fewer blocks make the grid barriers cheaper */
@@ -439,7 +489,7 @@ static int launch_run(jdde_net * h, int attempts)
 	attribute.val.cooperative = 1;
 	config.attrs = &attribute;
 	config.numAttrs = 1;
-	JN_CUDA(h, cudaLaunchKernelExC(&config, (const void *)h->k_run, args));
+	JN_CUDA(h, cudaLaunchKernelExC(&config, (const void *)kernel, args));
 	h->launches++;
 	return JDDE_OK;
 }
@@ -508,6 +558,8 @@ int jdde_net_grow_ring(jdde_net * h, int32_t new_capacity)
 		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double))));
 	if (h->k_run && (size_t)new_capacity*sizeof(double)+h->run_smem_bytes > 48*1024)
 		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double)+h->run_smem_bytes)));
+	if (h->k_run_warp && (size_t)new_capacity*sizeof(double) > 48*1024)
+		JN_CUDA(h, cudaFuncSetAttribute((const void *)h->k_run_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)new_capacity*sizeof(double))));
 	h->run_grid = 0;
 	double * new_times = nullptr, * new_hist = nullptr;
 	if ((rc = nalloc(h, &new_times, (size_t)new_capacity))) return rc;

@@ -25,6 +25,7 @@
 #include "../../include/jitcdde_b200.h"
 
 #define JDDE_IMAGE_MAGIC 0x4a444445   /* "JDDE" */
+#define JDDE_TEAM_FLAG_DOUBLES 64       /* shared memory of jdde_k_orthonormalise_team between the exchange slots and the staged anchors (one flag byte per thread of a block of up to 512) */
 
 typedef struct jdde_problem
 {

@@ -224,25 +224,40 @@ jdde_k_orthonormalise(jdde_problem const P, int const n_lyap, double const delay
 		jdde::member_orthonormalise(P, m, n_lyap, delay, norms, old_t, lyaps, delta_t);
 }
 
-/* one thread block per member (jdde_team.cuh); dynamic shared memory: blockDim.x + 2 + (capacity|1)·(1 + 2·n_basic·n_lyap) doubles */
+/* one thread block (or cluster) per member (jdde_team.cuh); dynamic shared memory: blockDim.x + 2 + JD_TEAM_FLAG_DOUBLES +
+ * (capacity|1)·(1 + 2·n_basic·n_lyap) doubles. A launch handles the members whose history length lies in [count_from, count_to]
+ * (jdde_runtime.cu: launch_orthonormalise); the others are sorted out blockDim.x members at a time — one thread looks at one
+ * member — so that a launch that has little to do costs microseconds, not a barrier per skipped member. */
 extern "C" __global__ void __launch_bounds__(JD_TEAM_BLOCK)
 jdde_k_orthonormalise_team(jdde_problem const P, int const n_lyap, double const delay, double * const norms, double * const old_t, double * const lyaps, double * const delta_t, int const capacity, int const count_from, int const count_to)
 {
-	extern __shared__ double jd_team_smem[];      /* [blockDim.x] scratch, [2] exchange slots of the cluster, then the staged anchors */
+	extern __shared__ double jd_team_smem[];      /* [blockDim.x] scratch, [2] exchange slots of the cluster, the flags, then the staged anchors */
 	unsigned crank, csize;
 	asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
 	asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
 	jdde::Team T = { (int)threadIdx.x, (int)blockDim.x, jd_team_smem };
 	T.crank = (int)crank;
 	T.csize = (int)csize;
-	/* one cluster (csize blocks; 1 without a cluster launch) per member; the blocks of a cluster run the same members */
-	for (long long m = blockIdx.x/csize; m < P.n_members; m += gridDim.x/csize)
+	unsigned char * const wanted = reinterpret_cast<unsigned char *>(jd_team_smem+blockDim.x+2);
+	double * const staged = jd_team_smem+blockDim.x+2+JD_TEAM_FLAG_DOUBLES;
+	/* the blocks of a cluster run the same members (and come to the same flags) */
+	long long const n_teams = gridDim.x/csize, team = blockIdx.x/csize;
+	for (long long base = team; base < P.n_members; base += n_teams*blockDim.x)
 	{
-		jdde::team_member_orthonormalise(T, P, m, n_lyap, delay, norms, old_t, lyaps, delta_t, jd_team_smem+blockDim.x+2, capacity, count_from, count_to);
+		long long const candidate = base + (long long)threadIdx.x*n_teams;
+		wanted[threadIdx.x] = candidate < P.n_members && jdde::team_has_work(P, candidate, old_t, count_from, count_to);
 		__syncthreads();
-		T.parity = 0;
-		if (csize > 1)
-			jdde::Team::cluster_sync();     /* nobody reads this block's exchange slots any more */
+		for (int k = 0; k < (int)blockDim.x; k++)
+		{
+			if (!wanted[k])
+				continue;
+			jdde::team_member_orthonormalise(T, P, base + (long long)k*n_teams, n_lyap, delay, norms, old_t, lyaps, delta_t, staged, capacity, count_from, count_to);
+			__syncthreads();
+			T.parity = 0;
+			if (csize > 1)
+				jdde::Team::cluster_sync();     /* nobody reads this block's exchange slots any more */
+		}
+		__syncthreads();
 	}
 }
 #endif

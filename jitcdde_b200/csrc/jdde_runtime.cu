@@ -211,7 +211,7 @@ int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * no
 		if (cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->desc.device) != cudaSuccess)
 			h->sm_count = 148;
 	}
-	long long const room = h->team_smem_max/(long long)sizeof(double) - 512 - 2;     /* doubles left for the staged anchors */
+	long long const room = h->team_smem_max/(long long)sizeof(double) - 512 - 2 - JDDE_TEAM_FLAG_DOUBLES;     /* doubles left for the staged anchors */
 	int capacity = cap;
 	if ((long long)(capacity | 1)*per_anchor > room)
 		capacity = (int)(room/per_anchor) - 1;
@@ -238,7 +238,7 @@ int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * no
 		bool const final_launch = fits >= cap || 2*cluster > cluster_max;
 		int count_to = final_launch ? 0x7fffffff : (int)fits;
 		int const threads = cluster == 1 ? block : 512;
-		size_t const smem = sizeof(double)*((size_t)threads + 2 + (size_t)(capacity | 1)*per_anchor);
+		size_t const smem = sizeof(double)*((size_t)threads + 2 + JDDE_TEAM_FLAG_DOUBLES + (size_t)(capacity | 1)*per_anchor);
 		/* cluster launches: one wave of clusters looping over the members (blocks of 200 KB start slowly) */
 		long long const most = cluster == 1 ? (long long)h->sm_count*32 : (long long)h->sm_count/cluster;
 		unsigned const grid = (unsigned)(N < most ? N : most)*cluster;

@@ -29,6 +29,8 @@ namespace jdde {
 #ifndef JD_TEAM_BLOCK
 #define JD_TEAM_BLOCK 512
 #endif
+#define JD_TEAM_FLAG_DOUBLES JDDE_TEAM_FLAG_DOUBLES      /* one byte per thread of the largest block: "this member is for this launch" */
+static_assert(JD_TEAM_BLOCK <= 8*JDDE_TEAM_FLAG_DOUBLES, "flag area of jdde_k_orthonormalise_team");
 
 struct Team
 {
@@ -39,6 +41,7 @@ struct Team
 	 * segments are completed across the blocks through distributed shared memory (sum() below). 1: no cluster. */
 	int crank = 0, csize = 1;
 	mutable int parity = 0;  /* which of the two exchange slots the next cluster-wide sum uses */
+	mutable int flip = 0;    /* which half of the scratch area the next block-wide sum uses (production build) */
 
 #if defined(__CUDA_ARCH__)
 	__device__ __forceinline__ static void cluster_sync()
@@ -104,17 +107,15 @@ struct Team
 		parity ^= 1;
 		double total;
 #if defined(JD_FAST)
+		/* every thread adds the blocks' parts itself, in rank order: one cluster barrier per sum, nothing to broadcast */
 		total = block_sum(0.0, count, body);
 		if (rank == 0)
 			scratch[size+which] = total;
 		cluster_sync();
-		if (rank == 0)
-		{
-			total = initial;
-			for (int r = 0; r < csize; r++)
-				total += remote_slot(r, which);
-			scratch[0] = total;
-		}
+		total = initial;
+		for (int r = 0; r < csize; r++)
+			total += remote_slot(r, which);
+		return total;
 #else
 		for (int r = 0; r < csize; r++)
 		{
@@ -131,11 +132,11 @@ struct Team
 		}
 		if (rank == 0)
 			scratch[0] = remote_slot(csize-1, which);
-#endif
 		__syncthreads();
 		total = scratch[0];
 		__syncthreads();
 		return total;
+#endif
 	}
 
 	template <class F>
@@ -143,19 +144,22 @@ struct Team
 	{
 		double total = 0;
 #if defined(JD_FAST)
+		/* tree within a warp, then every thread adds the warps' parts in warp order (the same value everywhere); the
+		 * parts alternate between two halves of the scratch area, so one barrier per sum is enough */
 		for (int e = rank; e < count; e += size)
 			total += body(e);
 		for (int offset = 16; offset > 0; offset >>= 1)
 			total += __shfl_down_sync(0xffffffffu, total, offset);
+		int const n_warps = (size+31) >> 5;
+		double * const parts = scratch + (flip ? n_warps : 0);
+		flip ^= 1;
 		if ((rank & 31) == 0)
-			scratch[rank >> 5] = total;
+			parts[rank >> 5] = total;
 		__syncthreads();
-		if (rank == 0)
-		{
-			for (int w = 1; w < (size+31)/32; w++)
-				total += scratch[w];
-			scratch[0] = initial+total;
-		}
+		total = initial;
+		for (int w = 0; w < n_warps; w++)
+			total += parts[w];
+		return total;
 #else
 		/* the reference's order: ascending e, one accumulator */
 		total = initial;
@@ -174,11 +178,11 @@ struct Team
 		}
 		if (rank == 0)
 			scratch[0] = total;
-#endif
 		__syncthreads();
 		total = scratch[0];
 		__syncthreads();
 		return total;
+#endif
 	}
 #endif
 };
@@ -205,9 +209,12 @@ struct Tangents
 	JD_FN void sweep(Team const & T, int const from, F && body) const
 	{
 #if defined(__CUDA_ARCH__)
-		for (int r = 0; r < R; r++)
-			for (int a = from+T.rank; a < count; a += T.size)
-				body(a, r);
+		int const span = count-from;      /* all threads busy also when there are fewer anchors than threads */
+		for (int e = T.rank; e < R*span; e += T.size)
+		{
+			int const r = e/span;
+			body(from+e-r*span, r);
+		}
 		__syncthreads();
 #else
 		(void)T;
@@ -353,6 +360,18 @@ JD_FN void team_gram_schmidt(Pass && pass, int const n_lyap, double * const norm
 	}
 	if (pending_scale >= 0)
 		pass(-1, -1, 0.0, pending_scale, pending_factor, -1, -1);
+}
+
+/* is member m for the launch that takes the histories of count_from … count_to anchors? (the conditions under which
+ * team_member_orthonormalise returns at once) */
+JD_FN bool team_has_work(jdde_problem const & P, long long const m, double const * const old_t, int const count_from, int const count_to)
+{
+	if (P.status[m] != JDDE_STATUS_OK)
+		return false;
+	if (old_t && old_t[m] != old_t[m])
+		return false;
+	int const count = P.last[m]-P.first[m]+1;
+	return count >= count_from && count <= count_to;
 }
 
 /*

@@ -209,11 +209,27 @@ struct Tangents
 	JD_FN void sweep(Team const & T, int const from, F && body) const
 	{
 #if defined(__CUDA_ARCH__)
-		int const span = count-from;      /* all threads busy also when there are fewer anchors than threads */
-		for (int e = T.rank; e < R*span; e += T.size)
+		/* element e = r·span + a of the R × span block, e = rank, rank + size, …: all threads are busy also when there are
+		 * fewer anchors than threads; (r, a) are carried along instead of divided out */
+		int const span = count-from;
+		if (span > 0)
 		{
-			int const r = e/span;
-			body(from+e-r*span, r);
+			int r = 0, a = T.rank;
+			while (a >= span)
+			{
+				a -= span;
+				r++;
+			}
+			while (r < R)
+			{
+				body(from+a, r);
+				a += T.size;
+				while (a >= span)
+				{
+					a -= span;
+					r++;
+				}
+			}
 		}
 		__syncthreads();
 #else
@@ -228,9 +244,13 @@ struct Tangents
 /*
  * Ring → shared memory (in = true: the tangent part of every anchor and its time) and back (in = false: the tangent
  * part of the anchors a >= from). One warp per anchor, lanes along the anchor's doubles: global accesses are contiguous
- * runs (the state part, then the diff part of the separation functions). The way in uses cp.async: the copies of all
- * anchors are in flight at once and do not occupy registers.
+ * runs (the state part, then the diff part of the separation functions). Several anchors per lane are in flight
+ * (round 2, profiles/ncu_r02_gram_schmidt.md: the cp.async loop of round 1 waited for each copy before it could reuse
+ * the address registers of the next — 19 % of the kernel's stall samples).
  */
+#ifndef JD_STAGE_DEPTH
+#define JD_STAGE_DEPTH 8
+#endif
 JD_FN void stage(Team const & T, Tangents const & H, int const n_lyap, bool const in, int const from)
 {
 	constexpr int R = 2*JD_NBASIC;
@@ -252,23 +272,32 @@ JD_FN void stage(Team const & T, Tangents const & H, int const n_lyap, bool cons
 			source = 1+part*JD_N+JD_NBASIC+rem;
 		}
 		double * const on_chip = H.rows + row*H.ks;
-		for (int a = from+warp; a < H.count; a += n_warps)
+		/* JD_STAGE_DEPTH anchors per lane in flight: the loads of a batch are issued before the first store waits for its value */
+		for (int a0 = from+warp; a0 < H.count; a0 += JD_STAGE_DEPTH*n_warps)
 		{
-			if (!in)
-				H.slot(a)[source] = on_chip[a];
-			else
+			double value[JD_STAGE_DEPTH] = {};
+			JD_UNROLL
+			for (int u = 0; u < JD_STAGE_DEPTH; u++)
 			{
-#if defined(__CUDA_ARCH__)
-				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(on_chip+a)), "l"(H.slot(a)+source) : "memory");
-#else
-				on_chip[a] = H.slot(a)[source];
-#endif
+				int const a = a0+u*n_warps;
+				if (a < H.count)
+					value[u] = in ? H.slot(a)[source] : on_chip[a];
+			}
+			JD_UNROLL
+			for (int u = 0; u < JD_STAGE_DEPTH; u++)
+			{
+				int const a = a0+u*n_warps;
+				if (a < H.count)
+				{
+					if (in)
+						on_chip[a] = value[u];
+					else
+						H.slot(a)[source] = value[u];
+				}
 			}
 		}
 	}
 #if defined(__CUDA_ARCH__)
-	if (in)
-		asm volatile("cp.async.wait_all;" ::: "memory");
 	__syncthreads();
 #endif
 }

@@ -211,7 +211,20 @@ int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * no
 		if (cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->desc.device) != cudaSuccess)
 			h->sm_count = 148;
 	}
-	long long const room = h->team_smem_max/(long long)sizeof(double) - 512 - 2 - JDDE_TEAM_FLAG_DOUBLES;     /* doubles left for the staged anchors */
+	/* JITCDDE_B200_TEAM_SMEM (bytes per block) and JITCDDE_B200_TEAM_THREADS trade the size of a block for the number of
+	 * blocks per SM: smaller blocks let one member's barriers and staging overlap another member's arithmetic, and the
+	 * anchors of a member then span more blocks of a cluster (profiles/ncu_r02_gram_schmidt.md) */
+	const char * const smem_choice = getenv("JITCDDE_B200_TEAM_SMEM");
+	const char * const threads_choice = getenv("JITCDDE_B200_TEAM_THREADS");
+	int smem_limit = h->team_smem_max;
+	if (smem_choice && atoi(smem_choice) >= 16*1024 && atoi(smem_choice) < smem_limit)
+		smem_limit = atoi(smem_choice);
+	int team_threads = 512;
+	if (threads_choice && atoi(threads_choice) >= 64 && atoi(threads_choice) <= 512)
+		team_threads = (atoi(threads_choice)/32)*32;
+	if (block > team_threads)
+		block = team_threads;
+	long long const room = smem_limit/(long long)sizeof(double) - 512 - 2 - JDDE_TEAM_FLAG_DOUBLES;     /* doubles left for the staged anchors */
 	int capacity = cap;
 	if ((long long)(capacity | 1)*per_anchor > room)
 		capacity = (int)(room/per_anchor) - 1;
@@ -237,10 +250,15 @@ int launch_orthonormalise(jdde_handle * h, int n_lyap, double delay, double * no
 		long long const fits = cluster == 1 ? capacity : (long long)cluster*(capacity-1);
 		bool const final_launch = fits >= cap || 2*cluster > cluster_max;
 		int count_to = final_launch ? 0x7fffffff : (int)fits;
-		int const threads = cluster == 1 ? block : 512;
+		int const threads = cluster == 1 ? block : team_threads;
 		size_t const smem = sizeof(double)*((size_t)threads + 2 + JDDE_TEAM_FLAG_DOUBLES + (size_t)(capacity | 1)*per_anchor);
 		/* cluster launches: one wave of clusters looping over the members (blocks of 200 KB start slowly) */
-		long long const most = cluster == 1 ? (long long)h->sm_count*32 : (long long)h->sm_count/cluster;
+		long long per_sm = h->team_smem_max/(long long)(smem+1024);      /* resident blocks per SM: shared memory, 128 registers per thread */
+		if (per_sm > 65536/(128*threads))
+			per_sm = 65536/(128*threads);
+		if (per_sm < 1)
+			per_sm = 1;
+		long long const most = cluster == 1 ? (long long)h->sm_count*32 : (long long)h->sm_count*per_sm/cluster;
 		unsigned const grid = (unsigned)(N < most ? N : most)*cluster;
 		void * args[] = { &h->P, &n_lyap, &delay, &norms, &old_t, &lyaps, &delta_t, &capacity, &count_from, &count_to };
 		if (getenv("JITCDDE_B200_DEBUG"))      /* launch shape and kernel attributes on stderr */

@@ -60,6 +60,9 @@ typedef struct jdn_control
 	unsigned long long epoch;
 	int exchanged_buffer;
 	int exchange_failed;      /* a peer did not arrive in time */
+	/* persistent stepper: tiles beyond a block's first one are handed out in the order in which the blocks ask (blocks on a
+	 * slower path to memory take fewer); zero between attempts */
+	int next_tile;
 } jdn_control;
 
 /*
@@ -106,6 +109,9 @@ typedef struct jdn_problem
 	 * in-edges (handled in rounds); built by jdde_net_set_graph */
 	int const * tile_start;
 	long long n_warp_tiles;
+	/* block tiles of the persistent stepper: consecutive owned nodes per tile (<= JDN_TILE_NODES of the image; 0: that
+	 * maximum), chosen by the runtime for the size of the rank's part (jdn_runtime.cu: launch_run) */
+	int tile_nodes;
 } jdn_problem;
 
 /* ring slots are grouped by 2^JDN_ROW_GROUP_LOG2 consecutive anchors per node (ring capacities are powers of two >= 4) */

@@ -173,8 +173,24 @@ extern "C" __global__ void jdn_k_exchange(jdn_problem const P)
  * Grid barriers (cooperative groups: release/acquire at GPU scope) are cumulative with the system-scope release/acquire
  * of the arrival counters. The controller state is read afresh after every barrier.
  */
+/* -DJDN_PROFILE (JITCDDE_B200_NET_FLAGS): thread 0 of block 0 adds up the time it spends in each phase of an attempt and
+ * prints the sums at the end of the launch (scripts/gpu_net_phases.py) — a measuring aid, not compiled otherwise */
+#if defined(JDN_PROFILE)
+#define JDN_PHASE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long now_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)); jdn_phase_ns[k] += now_-jdn_phase_last; jdn_phase_last = now_; } } while (0)
+#define JDN_PHASE_STATE unsigned long long jdn_phase_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0}, jdn_phase_last = 0; int jdn_phase_attempts = 0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(jdn_phase_last))
+#define JDN_PHASE_ARGS , jdn_phase_ns, jdn_phase_last
+#define JDN_PHASE_PARAMS , unsigned long long * const jdn_phase_ns, unsigned long long & jdn_phase_last
+#define JDN_PHASE_REPORT do { if (blockIdx.x == 0 && threadIdx.x == 0 && jdn_phase_attempts) printf("[jdn phases] rank %d attempts %d | tiles(own block) %.1f | grid barrier %.1f | push norm + arrival signals %.1f | wait for peers %.1f | controller %.1f | grid barrier %.1f | commit + grid barrier %.1f  (us per attempt)\n", P.rank, jdn_phase_attempts, jdn_phase_ns[0]*1e-3/jdn_phase_attempts, jdn_phase_ns[1]*1e-3/jdn_phase_attempts, jdn_phase_ns[2]*1e-3/jdn_phase_attempts, jdn_phase_ns[3]*1e-3/jdn_phase_attempts, jdn_phase_ns[4]*1e-3/jdn_phase_attempts, jdn_phase_ns[5]*1e-3/jdn_phase_attempts, jdn_phase_ns[6]*1e-3/jdn_phase_attempts); } while (0)
+#else
+#define JDN_PHASE(k) do { } while (0)
+#define JDN_PHASE_STATE do { } while (0)
+#define JDN_PHASE_ARGS
+#define JDN_PHASE_PARAMS
+#define JDN_PHASE_REPORT do { } while (0)
+#endif
+
 /* end of an attempt in the persistent steppers, thread 0 of block 0: exchange barrier between the GPUs, then the controller */
-__device__ __forceinline__ void jdn_run_exchange_and_control(jdn_problem const & P, jdn_control & C, int const buffer)
+__device__ __forceinline__ void jdn_run_exchange_and_control(jdn_problem const & P, jdn_control & C, int const buffer JDN_PHASE_PARAMS)
 {
 	if (blockIdx.x != 0 || threadIdx.x != 0)
 		return;
@@ -223,9 +239,12 @@ __device__ __forceinline__ void jdn_run_exchange_and_control(jdn_problem const &
 			C.epoch++;
 		}
 	}
+	JDN_PHASE(3);
+	C.next_tile = 0;      /* (all blocks are past their tiles: first grid barrier) */
 	if (arrived_all)
 		jdn::control(P);
 	__threadfence();
+	JDN_PHASE(4);
 }
 
 /* after an accepted step, several GPUs: the other ranks' nodes go from the staging buffer (written by the peers: read past L1)
@@ -266,7 +285,10 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 	jdn_control & C = *P.ctrl;
 	jdn::pair * const own_hist = reinterpret_cast<jdn::pair *>(P.hist);
 	long long const owned = P.hi-P.lo;
-	long long const n_tiles = (owned + JDN_TILE_NODES-1)/JDN_TILE_NODES;
+	int const tile_nodes = P.tile_nodes > 0 && P.tile_nodes < JDN_TILE_NODES ? P.tile_nodes : JDN_TILE_NODES;
+	long long const n_tiles = (owned + tile_nodes-1)/tile_nodes;
+	__shared__ long long s_next_tile[2];      /* the tile after the one under way (two slots: written while the other is still read) */
+	JDN_PHASE_STATE;
 	for (int attempt = 0; attempt < max_attempts; attempt++)
 	{
 		if (C.done)
@@ -284,12 +306,18 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 		int pws = 0;
 		double block_contribution = -1.0;      /* (threads 0 … JDN_TILE_NODES−1: their nodes) */
 
-		for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+		/* a block starts with tile blockIdx.x; the tiles beyond the first gridDim.x are taken in the order in which the blocks
+		 * get there (one atomic per tile, asked for while the tile before is computed): the blocks do not run at the same
+		 * speed — 13 % of an attempt was waiting for the slowest one with a fixed assignment, profiles/configs_r02.md */
+		int turn = 0;
+		for (long long tile = blockIdx.x; tile < n_tiles; turn ^= 1)
 		{
-			long long const row0 = tile*JDN_TILE_NODES;
-			int const nn = (int)(owned-row0 < JDN_TILE_NODES ? owned-row0 : JDN_TILE_NODES);
+			long long const row0 = tile*tile_nodes;
+			int const nn = (int)(owned-row0 < tile_nodes ? owned-row0 : tile_nodes);
 			if (threadIdx.x <= nn)
 				s_row[threadIdx.x] = P.row_ptr[row0+threadIdx.x];
+			if (threadIdx.x == blockDim.x-1)
+				s_next_tile[turn] = (long long)gridDim.x + atomicAdd(&P.ctrl->next_tile, 1);
 			__syncthreads();
 			long long const e0 = s_row[0];
 			int const ne = (int)(s_row[nn]-e0);
@@ -394,6 +422,7 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 				}
 				__syncthreads();
 			}
+			tile = s_next_tile[turn];
 		}
 		if (pws)
 			C.pws = 1;
@@ -412,14 +441,22 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 			if (block_contribution > 0.0)
 				atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(block_contribution));
 		}
+		JDN_PHASE(0);
 		grid.sync();
+		JDN_PHASE(1);
 
-		jdn_run_exchange_and_control(P, C, buffer);
+		jdn_run_exchange_and_control(P, C, buffer JDN_PHASE_ARGS);
 		grid.sync();
+		JDN_PHASE(5);
 		jdn_run_commit(P, C, owned);
 		if (P.world > 1 && C.commit_slot >= 0)
 			grid.sync();
+		JDN_PHASE(6);
+#if defined(JDN_PROFILE)
+		jdn_phase_attempts++;
+#endif
 	}
+	JDN_PHASE_REPORT;
 }
 
 /*
@@ -452,6 +489,7 @@ jdn_k_run_warp(jdn_problem const P, double * const scratch, long long const n_ed
 	long long const warp = ((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
 	long long const n_warps = ((long long)gridDim.x*blockDim.x) >> 5;
 	unsigned const full = 0xffffffffu;
+	JDN_PHASE_STATE;
 	for (int attempt = 0; attempt < max_attempts; attempt++)
 	{
 		if (C.done)
@@ -593,13 +631,21 @@ jdn_k_run_warp(jdn_problem const P, double * const scratch, long long const n_ed
 			if (contribution > 0.0)
 				atomicMax(&P.ctrl->p_bits, (unsigned long long)__double_as_longlong(contribution));
 		}
+		JDN_PHASE(0);
 		grid.sync();
-		jdn_run_exchange_and_control(P, C, buffer);
+		JDN_PHASE(1);
+		jdn_run_exchange_and_control(P, C, buffer JDN_PHASE_ARGS);
 		grid.sync();
+		JDN_PHASE(5);
 		jdn_run_commit(P, C, owned);
 		if (P.world > 1 && C.commit_slot >= 0)
 			grid.sync();
+		JDN_PHASE(6);
+#if defined(JDN_PROFILE)
+		jdn_phase_attempts++;
+#endif
 	}
+	JDN_PHASE_REPORT;
 }
 
 extern "C" __global__ void jdn_k_control(jdn_problem const P)

@@ -193,7 +193,7 @@ def network_leg(peak, device, rank, world, nodes=1_000_000, in_degree=10, span=1
 		g = network_graph(nodes, in_degree)
 		net = jitcdde_network(nodes, local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y), edges=(g["src"], g["dst"], g["edge_tau"]),
 			weight=g["weight"], node_parameters=[g["omega"]], verbose=False, device=device, ring_capacity=512)
-		net.set_integration_parameters(rtol=0, atol=1e-5)
+		net.set_integration_parameters(rtol=0, atol=1e-5, max_step=float(np.min(g["edge_tau"])))      # steps up to the smallest delay (the workload of round 1; beyond it the engine iterates on the past within the step)
 		net.constant_past(g["initial"], time=0.0)
 		net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1)
 		net.integrate(net.t+0.2)      # warm-up: step size settles, graphs are captured

@@ -102,19 +102,26 @@ class jitcdde_network:
 
 	# ------------------------------------------------------------------ parameters
 	def set_integration_parameters(self, atol=1e-10, rtol=1e-5, first_step=1.0, min_step=_default_min_step, max_step=10.0,
-			decrease_threshold=1.1, increase_threshold=0.5, safety_factor=0.9, max_factor=5.0, min_factor=0.2):
-		if max_step > self.min_delay:
+			decrease_threshold=1.1, increase_threshold=0.5, safety_factor=0.9, max_factor=5.0, min_factor=0.2,
+			pws_factor=3, pws_atol=0.0, pws_rtol=1e-5, pws_max_iterations=10, pws_base_increase_chance=0.1, pws_fuzzy_increase=False):
+		"""as jitcdde.set_integration_parameters (_jitcdde.py:621-743). A delay shorter than the step (past within step) is
+		handled as by the reference — the step is repeated until two successive results agree, or shrunk — on one GPU and with
+		the fused peer exchange; the all-gather exchange (exchange="nccl") does not iterate and limits max_step to the
+		smallest delay instead. pws_fuzzy_increase (a random draw per step-size increase) is not available for networks."""
+		if pws_fuzzy_increase:
+			raise NotImplementedError("pws_fuzzy_increase is not available for jitcdde_network; the deterministic credit rule (the reference's default) is used.")
+		if self.world > 1 and self.exchange == "nccl" and max_step > self.min_delay:
 			max_step = self.min_delay
 			if self.verbose:
-				print(f"max_step limited to the smallest delay ({self.min_delay:g}): the network engine needs delay >= step.")
+				print(f"max_step limited to the smallest delay ({self.min_delay:g}): the all-gather exchange needs delay >= step.")
 		if first_step > max_step:
 			first_step = max_step
 		if min_step > first_step:
 			min_step = first_step
 		self._int_params = dict(atol=atol, rtol=rtol, first_step=first_step, min_step=min_step, max_step=max_step,
 			decrease_threshold=decrease_threshold, increase_threshold=increase_threshold, safety_factor=safety_factor,
-			max_factor=max_factor, min_factor=min_factor, pws_factor=3, pws_atol=0.0, pws_rtol=1e-5,
-			pws_max_iterations=10, pws_base_increase_chance=0.1)
+			max_factor=max_factor, min_factor=min_factor, pws_factor=pws_factor, pws_atol=pws_atol, pws_rtol=pws_rtol,
+			pws_max_iterations=pws_max_iterations, pws_base_increase_chance=pws_base_increase_chance)
 		self.max_step = max_step
 		self.integration_parameters_set = True
 		if self._engine is not None:

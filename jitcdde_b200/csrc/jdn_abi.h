@@ -52,7 +52,7 @@ typedef struct jdn_control
 	int mode;
 	int done;                 /* 1: target reached or failure; attempt kernels return at once */
 	int status;               /* JDDE_STATUS_* */
-	int pws;                  /* a lookup reached into the step under way (not supported here) */
+	int pws;                  /* a lookup reached into the step under way on a path that does not iterate (the two-kernel attempt, warp tiles): the integration stops */
 	int commit_slot;          /* >= 0: the staged anchor was accepted and belongs into this ring slot; -1: nothing to commit */
 	jdde_int_params P;
 	/* peer exchange (several GPUs, jdn_exchange below): number of attempts exchanged so far — never reset; its parity
@@ -63,6 +63,24 @@ typedef struct jdn_control
 	/* persistent stepper: tiles beyond a block's first one are handed out in the order in which the blocks ask (blocks on a
 	 * slower path to memory take fewer); zero between attempts */
 	int next_tile;
+	/*
+	 * Past within step (a delay shorter than the step: /root/reference/jitcdde/_jitcdde.py:838-861, jitced_template.c:193-217).
+	 * `tentative`: an anchor after `current` exists — the result of an attempt that was not accepted (rejected, or one pass of
+	 * the iteration below); it is what the reference's list holds as last_anchor != current: lookups beyond `current`
+	 * interpolate towards it, the next attempt replaces it. It lives in tentative buffer (epoch & 1) ^ 1, its time in
+	 * times[current+1]. `pws_pass` = 0: the attempt under way is the first pass of try_single_step; k > 0: the k-th repetition
+	 * with the overlapping lookups (two successive results must agree). pws_bits = max over the lookups of the attempt of
+	 * t − t_current as IEEE bits; diff_bits != 0: check_new_y_diff failed for some node. last_pws, count, credit: the
+	 * controller's memory (last_pws, count, increase_credit of the reference).
+	 */
+	int tentative;
+	int pws_pass;
+	unsigned long long pws_bits;
+	unsigned long long diff_bits;
+	double last_pws;
+	double credit;
+	int count;
+	int pad_;
 } jdn_control;
 
 /*
@@ -80,7 +98,9 @@ typedef struct jdn_exchange
 {
 	unsigned long long p_bits[2];
 	unsigned long long arrived;
-	unsigned long long pad[13];       /* header = 128 bytes; then: double stage[2][n][2] */
+	unsigned long long pws_bits[2];   /* past within step: largest overlap of a lookup with the step, and "two successive results differ" */
+	unsigned long long diff_bits[2];
+	unsigned long long pad[9];        /* header = 128 bytes; then: double stage[2][n][2] */
 } jdn_exchange;
 
 typedef struct jdn_problem
@@ -112,6 +132,13 @@ typedef struct jdn_problem
 	/* block tiles of the persistent stepper: consecutive owned nodes per tile (<= JDN_TILE_NODES of the image; 0: that
 	 * maximum), chosen by the runtime for the size of the rank's part (jdn_runtime.cu: launch_run) */
 	int tile_nodes;
+	/* the two tentative buffers [n][2] of ONE GPU (several GPUs: the staging buffers of the exchange serve as such): attempt k
+	 * writes the (state, diff) pairs of its result into tentative[k & 1] (k = ctrl->epoch) — and into ring slot current+1 —
+	 * and reads the result of attempt k−1, if that is still the last anchor, from the other one. Null: no iteration (the
+	 * integration stops when a delay is shorter than the step). */
+	double * tentative[2];
+	int iterate;              /* 1: this path handles a past within the step as the reference does (persistent stepper with block tiles, host twin) */
+	int keep_tentative;       /* 1: a step may be longer than a delay of this rank's in-edges: results are also stored in the tentative buffers */
 } jdn_problem;
 
 /* ring slots are grouped by 2^JDN_ROW_GROUP_LOG2 consecutive anchors per node (ring capacities are powers of two >= 4) */

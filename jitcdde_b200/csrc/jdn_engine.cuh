@@ -50,27 +50,48 @@ struct View
 	double t_cur;
 };
 
+#if defined(__GNUC__) || defined(__CUDACC__)
+#  define JDN_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#  define JDN_UNLIKELY(x) (x)
+#endif
+
 JDN_FN double anchor_time(View const & V, int const index) { return V.times[index & V.mask]; }
 
-/* get_past_anchors (jitced_template.c:193-217) for one edge; the tentative anchor is never reachable here */
-JDN_FN int walk(View const & V, int ca, double const t)
+/* tentative buffer b of this rank: the staging buffer of the exchange with several GPUs, else the rank's own pair of buffers */
+JDN_FN pair * tentative_buffer(jdn_problem const & P, int const b)
+{
+	if (P.world > 1)
+		return reinterpret_cast<pair *>(jdn_exchange_stage(P.peers[P.rank], b, P.n));
+	return reinterpret_cast<pair *>(P.tentative[b]);
+}
+
+/* the (state, diff) pairs of the anchor after `current`, if there is one: the result of the attempt before, in the buffer
+ * that attempt wrote */
+JDN_FN pair const * last_tentative(jdn_problem const & P)
+{
+	return tentative_buffer(P, (int)((P.ctrl->epoch & 1) ^ 1));
+}
+
+/* get_past_anchors (jitced_template.c:193-217) for one edge: back while the anchor is later than t, forward while the
+ * next one is earlier and not the last of the list (`last`: the current anchor, or the tentative one after it) */
+JDN_FN int walk(View const & V, int ca, double const t, int const last)
 {
 	while (anchor_time(V, ca) > t && ca > V.first)
 		--ca;
-	while (anchor_time(V, ca+1) < t && ca+2 <= V.current)
+	while (anchor_time(V, ca+1) < t && ca+2 <= last)
 		++ca;
 	return ca;
 }
 
-/* get_past_value (jitced_template.c:221-235) of node j on the segment starting at anchor ca */
-JDN_FN double past_value(jdn_problem const & P, View const & V, int const ca, long long const j, double const t)
+JDN_FN int walk(View const & V, int const ca, double const t) { return walk(V, ca, t, V.current); }
+
+/* get_past_value (jitced_template.c:221-235) of node j on the segment from anchor ca (pair v) to the next one (pair w) */
+JDN_FN double hermite(View const & V, int const ca, double const t, pair const v, pair const w)
 {
 	double const tv = anchor_time(V, ca);
 	double const q = anchor_time(V, ca+1)-tv;
 	double const x = (t - tv)/q;
-	pair const * const H = reinterpret_cast<pair const *>(P.hist);
-	pair const v = H[jdn_pair_index(ca & V.mask, j, P.n)];
-	pair const w = H[jdn_pair_index((ca+1) & V.mask, j, P.n)];
 	double const a = v.state;
 	double const b = v.diff * q;
 	double const c = w.state;
@@ -78,24 +99,62 @@ JDN_FN double past_value(jdn_problem const & P, View const & V, int const ca, lo
 	return (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
 }
 
+JDN_FN double past_value(jdn_problem const & P, View const & V, int const ca, long long const j, double const t)
+{
+	pair const * const H = reinterpret_cast<pair const *>(P.hist);
+	return hermite(V, ca, t, H[jdn_pair_index(ca & V.mask, j, P.n)], H[jdn_pair_index((ca+1) & V.mask, j, P.n)]);
+}
+
+/*
+ * Past within step: the lookups of an edge whose delay is shorter than the step (jitced_template.c:193-235 with
+ * t > current->time). The last anchor of the list is then either `current` — the lookup extrapolates the last segment —
+ * or the result of an attempt that was not accepted (jdn_control::tentative), towards which it interpolates. All three
+ * stages see the anchors as they were before the attempt: get_next_step replaces the last anchor only after its last
+ * evaluation of f (:465-468), so the lookups of an attempt still do not depend on its stages. Rare, kept out of line.
+ */
+JDN_FN void lookup_edge_beyond(jdn_problem const & P, View const & V, double const d1, double const d2, double const d3, long long const e, double & v1, double & v2, double & v3)
+{
+	long long const j = P.src[e];
+	bool const tentative = P.ctrl->tentative && P.iterate;
+	int const last = tentative ? V.current+1 : V.current;
+	pair const * const H = reinterpret_cast<pair const *>(P.hist);
+	double const d[3] = { d1, d2, d3 };
+	double v[3];
+	int ca = P.cursor[e];
+	for (int k = 0; k < 3; k++)
+	{
+		ca = walk(V, ca, d[k], last);
+		pair const w = ca+1 > V.current ? last_tentative(P)[j] : H[jdn_pair_index((ca+1) & V.mask, j, P.n)];
+		v[k] = hermite(V, ca, d[k], H[jdn_pair_index(ca & V.mask, j, P.n)], w);
+	}
+	P.cursor[e] = ca;
+	v1 = v[0];
+	v2 = v[1];
+	v3 = v[2];
+}
+
 /*
  * Lookup phase of one attempted step, ONE EDGE: the delayed state of the source node at the three stage times
  * t + h/2, t + 3h/4, t + h (get_past_anchors + get_past_value, jitced_template.c:193-235, three times for this
  * edge's call site, in the order the reference evaluates them). The three lookups fall on the same or neighbouring
- * history rows, so they share their gathers. Results go to scratch[3e…3e+2]; the edge's cursor is updated.
+ * history rows, so they share their gathers. The edge's cursor is updated.
  * Edge-parallel: 10^7 independent threads for a 10^6-node network of in-degree 10.
+ *
+ * `overlap` grows to the largest t − t_current of a lookup beyond the current anchor (past_within_step,
+ * jitced_template.c:211-213); such an edge takes the path above. (A lookup at or before the current anchor never walks
+ * onto the segment after it, so the anchors up to `current` are all the common path has to know.)
  */
-JDN_FN void lookup_edge_values(jdn_problem const & P, View const & V, double const h, long long const e, double & v1, double & v2, double & v3, int & pws)
+JDN_FN void lookup_edge_values(jdn_problem const & P, View const & V, double const h, long long const e, double & v1, double & v2, double & v3, double & overlap)
 {
-	long long const j = P.src[e];
 	double const tau = P.tau[e];
 	double const d1 = (V.t_cur+0.5*h)-tau, d2 = (V.t_cur+0.75*h)-tau, d3 = (V.t_cur+h)-tau;
-	/* A lookup reaches into the step under way iff the step is longer than the delay. Tested on h and tau themselves:
-	 * with h == tau (a step size that has saturated at max_step = smallest delay, or a blind step of that length)
-	 * (t+h)−tau lands one ulp above t in a few percent of the attempts, and the walk below then simply ends at the last
-	 * accepted anchor — an extrapolation by one ulp, not a lookup into the tentative anchor. */
-	if (h > tau)
-		pws = 1;
+	if (JDN_UNLIKELY(d3 > V.t_cur))      /* (d1 < d2 < d3) */
+	{
+		overlap = fmax(overlap, d3-V.t_cur);
+		lookup_edge_beyond(P, V, d1, d2, d3, e, v1, v2, v3);
+		return;
+	}
+	long long const j = P.src[e];
 	int ca = walk(V, P.cursor[e], d1);
 	v1 = past_value(P, V, ca, j, d1);
 	ca = walk(V, ca, d2);
@@ -103,6 +162,17 @@ JDN_FN void lookup_edge_values(jdn_problem const & P, View const & V, double con
 	ca = walk(V, ca, d3);
 	v3 = past_value(P, V, ca, j, d3);
 	P.cursor[e] = ca;
+}
+
+/* the same where nothing iterates: the flag `pws` stops the integration. Tested on h and tau themselves there: with h == tau,
+ * (t+h)−tau lands one ulp above t in a few percent of the attempts, and flagging that would stop an integration whose step
+ * size has saturated at max_step = smallest delay. */
+JDN_FN void lookup_edge_values(jdn_problem const & P, View const & V, double const h, long long const e, double & v1, double & v2, double & v3, int & pws)
+{
+	double overlap = 0.0;
+	if (h > P.tau[e])
+		pws = 1;
+	lookup_edge_values(P, V, h, e, v1, v2, v3, overlap);
 }
 
 JDN_FN void lookup_edge(jdn_problem const & P, View const & V, double const h, long long const e, double * const scratch, int & pws)
@@ -177,9 +247,40 @@ JDN_FN void forget(jdn_problem const & P, jdn_control & C)
 		C.first++;
 }
 
-/* what follows an attempt on the Python side of the reference: _adjust_step_size (_jitcdde.py:775-794), accept_step,
- * the loop test of integrate (:830) or the step count of integrate_blindly (:928-931), forget, and the preparation
- * of the next attempt. Run by ONE thread. */
+/* _jitcdde.py:21 */
+JDN_FN double sigmoid(double const x) { return (JDDE_TANH(x)+1)/2; }
+
+/* _increase_chance and _do_increase (the credit rule), _jitcdde.py:733-773: after a past-within-step event the step size
+ * only grows when enough credit has gathered */
+JDN_FN bool pws_allows_increase(jdn_control & C, double const new_dt)
+{
+	jdde_int_params const & I = C.P;
+	double const q = new_dt/C.last_pws;
+	double const is_explicit = sigmoid(1-q);
+	double const far_from_explicit = sigmoid(q-I.pws_factor);
+	double const few_iterations = sigmoid(1-C.count/I.pws_factor);
+	double const profile = is_explicit+far_from_explicit*few_iterations;
+	double const chance = profile + I.pws_base_increase_chance*(1-profile);
+	C.credit += chance;
+	if (C.credit >= 0.9)
+	{
+		C.credit = 0.0;
+		return true;
+	}
+	return false;
+}
+
+/* the time of the anchor after `current` becomes that of the attempt just made (it stays the last anchor) */
+JDN_FN void keep_tentative(jdn_problem const & P, jdn_control & C)
+{
+	C.tentative = 1;
+	P.times[(C.current+1) & (P.cap-1)] = C.t + C.h;
+}
+
+/* what follows an attempt on the Python side of the reference: try_single_step (_jitcdde.py:838-861) — written as a state
+ * machine, one call per get_next_step: C.pws_pass says which pass of it the attempt was —, _adjust_step_size (:775-794),
+ * accept_step, the loop test of integrate (:830) or the step count of integrate_blindly (:928-931), forget, and the
+ * preparation of the next attempt. Run by ONE thread. */
 JDN_FN void control(jdn_problem const & P)
 {
 	jdn_control & C = *P.ctrl;
@@ -191,11 +292,17 @@ JDN_FN void control(jdn_problem const & P)
 	union { unsigned long long u; double d; } bits;
 	bits.u = C.p_bits;
 	double const p = bits.d;
+	bits.u = C.pws_bits;
+	double const overlap = bits.d;
+	bool const differs = C.diff_bits != 0;
 	C.attempts++;
+	C.p_bits = 0;
+	C.pws_bits = 0;
+	C.diff_bits = 0;
 
 	if (C.pws)
 	{
-		/* a delay shorter than the step: the single-kernel stage evaluation does not cover this */
+		/* a delay shorter than the step on a path that does not iterate */
 		C.status = JDDE_STATUS_NONFINITE;
 		C.done = 1;
 		return;
@@ -204,10 +311,62 @@ JDN_FN void control(jdn_problem const & P)
 	bool accept = true;
 	if (C.mode == JDN_MODE_ADAPTIVE)
 	{
-		if (p > I.decrease_threshold)
+		bool shrink = false;      /* dt /= pws_factor and a rejected attempt */
+		if (C.pws_pass == 0)
+		{
+			if (overlap != 0.0)
+			{
+				C.last_pws = overlap;
+				if (C.dt > I.pws_factor*overlap || I.pws_max_iterations < 1)
+					shrink = true;      /* if possible, shrink the step to make the integration explicit */
+				else
+				{
+					/* repeat the step (with self.dt, :853) until two successive results agree */
+					C.pws_pass = C.count = 1;
+					C.last_start = C.t;
+					keep_tentative(P, C);
+					C.h = C.dt;
+					return;
+				}
+			}
+		}
+		else if (!differs)
+			C.pws_pass = 0;      /* converged: on to the error control */
+		else if (C.pws_pass >= I.pws_max_iterations)
+			shrink = true;
+		else
+		{
+			C.pws_pass = C.count = C.pws_pass+1;
+			C.last_start = C.t;
+			keep_tentative(P, C);
+			C.h = C.dt;
+			return;
+		}
+
+		if (shrink)
+		{
+			C.pws_pass = 0;
+			C.dt /= I.pws_factor;
+			accept = false;
+		}
+		else if (p > I.decrease_threshold)
 		{
 			C.dt *= fmax(I.safety_factor*jdde_inv_root3(p), I.min_factor);
 			accept = false;
+		}
+		else if (p <= I.increase_threshold)
+		{
+			double const factor = (p != 0.0) ? I.safety_factor*jdde_inv_root4(p) : I.max_factor;
+			double const new_dt = fmin(C.dt*fmin(factor, I.max_factor), I.max_step);
+			if (C.last_pws == 0.0 || pws_allows_increase(C, new_dt))
+			{
+				C.dt = new_dt;
+				C.count = 0;
+				C.last_pws = 0.0;
+			}
+		}
+		if (!accept)
+		{
 			C.rejected++;
 			if (C.dt < I.min_step)
 			{
@@ -215,11 +374,6 @@ JDN_FN void control(jdn_problem const & P)
 				C.done = 1;
 				return;
 			}
-		}
-		else if (p <= I.increase_threshold)
-		{
-			double const factor = (p != 0.0) ? I.safety_factor*jdde_inv_root4(p) : I.max_factor;
-			C.dt = fmin(C.dt*fmin(factor, I.max_factor), I.max_step);
 		}
 	}
 
@@ -231,6 +385,7 @@ JDN_FN void control(jdn_problem const & P)
 		C.current++;
 		P.times[C.current & mask] = C.t;
 		C.commit_slot = C.current & mask;
+		C.tentative = 0;
 		C.accepted++;
 		if (C.mode == JDN_MODE_BLIND)
 		{
@@ -245,7 +400,10 @@ JDN_FN void control(jdn_problem const & P)
 		}
 	}
 	else
+	{
 		C.last_start = C.t;
+		keep_tentative(P, C);
+	}
 
 	if (C.done)
 		return;
@@ -267,7 +425,6 @@ JDN_FN void control(jdn_problem const & P)
 	}
 	if (C.mode == JDN_MODE_ADAPTIVE)
 		C.h = C.dt;
-	C.p_bits = 0;
 }
 
 /* The reference's anchor list is unbounded; the ring is not. A call that stopped with JDDE_STATUS_OVERFLOW goes on after the
@@ -284,6 +441,8 @@ JDN_FN void continue_call(jdn_control & C)
 	}
 	C.pws = 0;
 	C.p_bits = 0;
+	C.pws_bits = 0;
+	C.diff_bits = 0;
 	C.done = 0;
 	if (C.mode == JDN_MODE_ADAPTIVE)
 		C.h = C.dt;

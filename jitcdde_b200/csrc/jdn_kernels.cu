@@ -201,6 +201,12 @@ __device__ __forceinline__ void jdn_run_exchange_and_control(jdn_problem const &
 		if (mine)
 			for (int r = 0; r < P.world; r++)
 				atomicMax_system(&P.peers[r]->p_bits[buffer], mine);
+		if (C.pws_bits)      /* rare: a delay shorter than the step */
+			for (int r = 0; r < P.world; r++)
+				atomicMax_system(&P.peers[r]->pws_bits[buffer], C.pws_bits);
+		if (C.diff_bits)
+			for (int r = 0; r < P.world; r++)
+				atomicMax_system(&P.peers[r]->diff_bits[buffer], C.diff_bits);
 		__threadfence_system();
 		for (int r = 0; r < P.world; r++)
 			if (r != P.rank)
@@ -235,10 +241,14 @@ __device__ __forceinline__ void jdn_run_exchange_and_control(jdn_problem const &
 			}
 			else
 				C.p_bits = bits;
+			C.pws_bits = atomicExch_system(&own->pws_bits[buffer], 0ull);
+			C.diff_bits = atomicExch_system(&own->diff_bits[buffer], 0ull);
 			C.exchanged_buffer = buffer;
 			C.epoch++;
 		}
 	}
+	else
+		C.epoch++;      /* (one GPU: the parity of the attempts selects the tentative buffer) */
 	JDN_PHASE(3);
 	C.next_tile = 0;      /* (all blocks are past their tiles: first grid barrier) */
 	if (arrived_all)
@@ -288,6 +298,7 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 	int const tile_nodes = P.tile_nodes > 0 && P.tile_nodes < JDN_TILE_NODES ? P.tile_nodes : JDN_TILE_NODES;
 	long long const n_tiles = (owned + tile_nodes-1)/tile_nodes;
 	__shared__ long long s_next_tile[2];      /* the tile after the one under way (two slots: written while the other is still read) */
+	__shared__ double s_tolerance[2];         /* atol, rtol */
 	JDN_PHASE_STATE;
 	for (int attempt = 0; attempt < max_attempts; attempt++)
 	{
@@ -295,16 +306,25 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 			break;      /* (every thread of every block sees the same value: written before the last grid barrier) */
 		jdn::View V = jdn::view_of(P);
 		double const h = C.h;
-		double const atol = C.P.atol, rtol = C.P.rtol;
 		int const slot = (V.current+1) & V.mask;
 		int const buffer = (int)(C.epoch & 1);
+		/* past within step (jdn_abi.h): the result also goes into tentative buffer `buffer` — with several GPUs that is this
+		 * rank's own staging buffer —, where the next attempt finds it if this one is not accepted; in a repetition
+		 * (pws_pass > 0) it is compared with the result before (check_new_y_diff, jitced_template.c:502-524) */
+		bool const repetition = C.pws_pass > 0;
 		for (int k = threadIdx.x; k < P.cap; k += blockDim.x)
 			s_times[k] = P.times[k];
+		if (threadIdx.x == 0)
+		{
+			s_tolerance[0] = C.P.atol;
+			s_tolerance[1] = C.P.rtol;
+		}
 		__syncthreads();
 		V.times = s_times;
-		double const t1 = V.t_cur+0.5*h, t2 = V.t_cur+0.75*h, t3 = V.t_cur+h;
-		int pws = 0;
 		double block_contribution = -1.0;      /* (threads 0 … JDN_TILE_NODES−1: their nodes) */
+		/* (what only the last stage or the rare past-within-step path needs — tolerances, stage times, the tentative buffer — is
+		 * fetched where it is used, the tolerances from shared memory: at 64 registers per thread everything carried through
+		 * the tile loop is a spill, and a load from global memory there would sit on the critical path of every tile) */
 
 		/* a block starts with tile blockIdx.x; the tiles beyond the first gridDim.x are taken in the order in which the blocks
 		 * get there (one atomic per tile, asked for while the tile before is computed): the blocks do not run at the same
@@ -329,7 +349,10 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 			for (int k = threadIdx.x; k < ne; k += blockDim.x)
 			{
 				double v1, v2, v3;
-				jdn::lookup_edge_values(P, V, h, e0+k, v1, v2, v3, pws);
+				double overlap = 0.0;
+				jdn::lookup_edge_values(P, V, h, e0+k, v1, v2, v3, overlap);
+				if (overlap > 0.0)      /* rare: a delay shorter than the step */
+					atomicMax(&P.ctrl->pws_bits, (unsigned long long)__double_as_longlong(overlap));
 				value[k*edge_stride] = v1;
 				value[k*edge_stride+stage_stride] = v2;
 				value[k*edge_stride+2*stage_stride] = v3;
@@ -375,7 +398,7 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 				__syncthreads();
 				if (threadIdx.x < nn)
 				{
-					double const t_stage = stage == 0 ? t1 : stage == 1 ? t2 : t3;
+					double const t_stage = V.t_cur + (stage == 0 ? 0.5*h : stage == 1 ? 0.75*h : h);
 					double acc = JDN_LOCAL(y_stage, t_stage, par);
 					long long const r0 = s_row[threadIdx.x]-e0, r1 = s_row[threadIdx.x+1]-e0;
 					if (in_shared)
@@ -406,11 +429,20 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 						 * keeps the pairs of four slots of a node together, 64 bytes from node to node: stores of single
 						 * pairs into the peers' rings measured 0.40 efficiency on 8 GPUs, profiles/) */
 						own_hist[jdn_pair_index(slot, i, P.n)] = staged;
+						if (repetition)
+						{
+							double const difference = fabs(y_stage - jdn::last_tentative(P)[i].state);
+							double const tolerance = C.P.pws_atol + fabs(C.P.pws_rtol*y_stage);
+							if (!(tolerance >= difference))
+								P.ctrl->diff_bits = 1;
+						}
+						if (P.keep_tentative)
+							jdn::tentative_buffer(P, buffer)[i] = staged;
 						for (int r = 0; r < P.world; r++)
 							if (r != P.rank)
 								reinterpret_cast<jdn::pair *>(jdn_exchange_stage(P.peers[r], buffer, P.n))[i] = staged;
 						/* get_p, jitced_template.c:474-498: 0/0 is skipped, a NaN never wins the comparison */
-						double const tolerance = atol + rtol*fabs(y_stage);
+						double const tolerance = s_tolerance[0] + s_tolerance[1]*fabs(y_stage);
 						if (error != 0.0 || tolerance != 0.0)
 						{
 							double const c = error/tolerance;
@@ -424,8 +456,6 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 			}
 			tile = s_next_tile[turn];
 		}
-		if (pws)
-			C.pws = 1;
 		/* error norm of this block's nodes (threads 0 … JDN_TILE_NODES−1 hold them) */
 		for (int o = 16; o > 0; o >>= 1)
 			block_contribution = fmax(block_contribution, __shfl_down_sync(0xffffffffu, block_contribution, o));
@@ -696,6 +726,8 @@ extern "C" __global__ void jdn_k_begin(jdn_problem const P, int const mode, doub
 	C.commit_slot = -1;
 	C.pws = 0;
 	C.p_bits = 0;
+	C.pws_bits = C.diff_bits = 0;
+	C.pws_pass = 0;
 	if (mode == JDN_MODE_BLIND)
 	{
 		C.h = h;
@@ -762,5 +794,8 @@ jdn_k_set_past(jdn_problem const P, int const n_anchors, double const * const ti
 		C.done = 1;
 		C.commit_slot = -1;
 		C.accepted = C.rejected = C.attempts = 0;
+		C.tentative = 0;
+		C.pws_pass = 0;
+		C.pws_bits = C.diff_bits = 0;
 	}
 }

@@ -32,6 +32,7 @@ struct jdde_net
 	int peer_rank = 0, peer_world = 1;
 	bool persistent = true;                   /* jdn_k_run (one cooperative launch per batch of attempts) instead of five kernels per attempt */
 	int run_grid = 0;                         /* co-resident blocks of jdn_k_run */
+	double min_tau = 0.0, max_step = 1e300;   /* smallest delay of this rank's in-edges; max_step of the integration parameters */
 	int run_smem_bytes = 0;                   /* its dynamic shared memory beyond the anchor times (image descriptor) */
 	bool warp_tiles = false;                  /* jdn_k_run_warp (a warp per tile of <= 32 in-edges) instead of jdn_k_run (a block per tile of 64 nodes) */
 	int * d_tile_start = nullptr;
@@ -139,6 +140,9 @@ int jdde_net_create(const jdde_net_desc * d, jdde_net ** out)
 	if ((rc = nalloc(h, &P.times, cap))) return bail(rc);
 	if ((rc = nalloc(h, &P.hist, 2*cap*n))) return bail(rc);
 	if ((rc = nalloc(h, &P.stage, 2*n))) return bail(rc);
+	/* the two tentative buffers of the past-within-step iteration (jdn_abi.h); several GPUs use the staging buffers of the exchange */
+	if ((rc = nalloc(h, &P.tentative[0], 2*n))) return bail(rc);
+	if ((rc = nalloc(h, &P.tentative[1], 2*n))) return bail(rc);
 	if ((rc = nalloc(h, &h->d_par, n*(size_t)(d->n_node_params ? d->n_node_params : 1)))) return bail(rc);
 	if ((rc = nalloc(h, &h->d_row_ptr, owned+1))) return bail(rc);
 	if ((rc = nalloc(h, &h->d_src, E))) return bail(rc);
@@ -244,6 +248,9 @@ int jdde_net_set_graph(jdde_net * h, const int64_t * row_ptr, const int32_t * sr
 	if (!row_ptr || (h->desc.n_edges && (!src || !tau || !weight))) return nfail(h, JDDE_E_INVALID, "null argument");
 	size_t const owned = (size_t)(h->desc.hi-h->desc.lo), E = (size_t)h->desc.n_edges;
 	if (row_ptr[0] != 0 || (size_t)row_ptr[owned] != E) return nfail(h, JDDE_E_INVALID, "row_ptr does not match n_edges");
+	h->min_tau = E ? tau[0] : 1e300;
+	for (size_t e = 0; e < E; e++)
+		if (tau[e] < h->min_tau) h->min_tau = tau[e];
 	for (size_t e = 0; e < E; e++)
 		if (src[e] < 0 || src[e] >= h->desc.n || !(tau[e] > 0.0))
 			return nfail(h, JDDE_E_INVALID, "edge with source out of range or non-positive delay");
@@ -342,6 +349,8 @@ int jdde_net_set_integration_parameters(jdde_net * h, const jdde_int_params * p,
 	jdn_control c;
 	JN_CUDA(h, cudaMemcpy(&c, h->P.ctrl, sizeof c, cudaMemcpyDeviceToHost));
 	c.P = q; c.dt = q.first_step; c.max_delay = max_delay; c.cap = h->P.cap;
+	h->max_step = q.max_step;
+	c.last_pws = 0.0; c.count = 0; c.credit = 0.0;      /* _jitcdde.py:727-729 */
 	JN_CUDA(h, cudaMemcpy(h->P.ctrl, &c, sizeof c, cudaMemcpyHostToDevice));
 	h->have_int = true;
 	return JDDE_OK;
@@ -360,6 +369,7 @@ int jdde_net_attempt(jdde_net * h)
 {
 	int rc = nready_run(h);
 	if (rc) return rc;
+	h->P.iterate = 0;      /* the two-kernel attempt does not iterate on a past within the step: it stops the integration */
 	long long E = h->desc.n_edges;
 	void * largs[] = { &h->P, &h->scratch, &E };
 	if (E && (rc = nlaunch(h, h->k_lookup, E, h->block, (size_t)h->P.cap*sizeof(double), largs))) return rc;
@@ -504,6 +514,11 @@ static int launch_run(jdde_net * h, int attempts)
 			nodes = atoi(choice);
 		h->P.tile_nodes = (int)nodes;
 	}
+	h->P.iterate = h->warp_tiles ? 0 : 1;      /* block tiles handle a past within the step; warp tiles stop the integration */
+	/* an adaptive step can only reach into a delay if max_step exceeds the smallest delay of this rank's in-edges (blind steps
+	 * are all accepted: no tentative anchor outlives them); otherwise no lookup ever reads a tentative anchor and the
+	 * stepper does not store it */
+	h->P.keep_tentative = h->P.iterate && h->max_step > h->min_tau;
 	long long E = h->desc.n_edges;
 	void * args[] = { &h->P, &h->scratch, &E, &attempts };
 	cudaLaunchConfig_t config{};

@@ -195,19 +195,14 @@ def network_graph(n=128, k=10, seed=11):
 	return dict(n=n, src=src, dst=dst, edge_tau=tau, weight=42*0.05/k, omega=rng.uniform(0.8, 1.2, n), initial=rng.uniform(0, 2*np.pi, n))
 
 
-def golden_network():
-	"""
-	The structured network engine (jitcdde_network) against the REFERENCE'S C core: the same 128-node delay-coupled Kuramoto
-	network written out for the reference as it wants it — one `set_dy(i, …)` per node, one `anchors()` call per in-edge
+def _reference_network_core(g, name):
+	"""the reference's C core for the network g: one `set_dy(i, …)` per node, one `anchors()` call per in-edge
 	(/root/reference/examples/kuramoto_network.py:50-62) — with the terms of a node in the order and association of the
 	engine (local term first, then the in-edges in input order, each `weight*coupling` added to the running sum), the
-	coupling function printed by the same code generator, sin from csrc/jdde_math.h. Driven by the reference's controller
-	restated in oracle/controller.py with the network engine's step limit (max_step = smallest delay).
-	"""
+	coupling function printed by the same code generator, sin from csrc/jdde_math.h"""
 	import types
 	import sympy
 	from jitcdde_b200 import _codegen
-	g = network_graph()
 	n, E = g["n"], len(g["src"])
 	net_program = _codegen.generate_network(lambda y, t, w: w, lambda yd, y: sympy.sin(yd-y), 1)
 	lines = []
@@ -220,10 +215,21 @@ def golden_network():
 		lines.append(f"{{ double const par[1] = {{ {float(g['omega'][i])!r} }}; set_dy({i}, {terms}); }}")
 	program = types.SimpleNamespace(n=n, n_sites=E, param_names=[], literal_f=lines, literal_sites=E, body="")
 	definitions = f'#include "{os.path.join(ROOT, "jitcdde_b200", "csrc", "jdde_math.h")}"\n' + net_program.body
-	build_ref.build_ref(program, "ref_network", flavour="literal", definitions=definitions, force=True)
-	module = build_ref.load_ref("ref_network")
+	build_ref.build_ref(program, name, flavour="literal", definitions=definitions, force=True)
+	module = build_ref.load_ref(name)
 	past = [(-1.0, g["initial"], np.zeros(n)), (0.0, g["initial"], np.zeros(n))]
-	core = module.dde_integrator([(a[0], np.array(a[1], dtype=float), np.array(a[2], dtype=float)) for a in past])
+	return module.dde_integrator([(a[0], np.array(a[1], dtype=float), np.array(a[2], dtype=float)) for a in past])
+
+
+def golden_network():
+	"""
+	The structured network engine (jitcdde_network) against the REFERENCE'S C core on a 128-node delay-coupled Kuramoto
+	network, driven by the reference's controller restated in oracle/controller.py with max_step = smallest delay (the
+	step limit the network engine had before it could iterate on a past within the step; it is never reached here).
+	"""
+	g = network_graph()
+	n = g["n"]
+	core = _reference_network_core(g, "ref_network")
 	roots = roots_from(oracle.build(systems.program(systems.mackey_glass())))
 	max_delay, min_delay = float(np.max(g["edge_tau"])), float(np.min(g["edge_tau"]))
 	C = controller.Controller(core, max_delay, root_mode=1, roots=roots, rtol=0, atol=1e-5, max_step=min_delay, first_step=min(1.0, min_delay))
@@ -232,6 +238,33 @@ def golden_network():
 	samples = np.array([C.integrate(T) for T in times])
 	save("network", src=g["src"], dst=g["dst"], edge_tau=g["edge_tau"], weight=g["weight"], omega=g["omega"], initial=g["initial"],
 		blind_to=max_delay, blind=blind, times=times, samples=samples, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
+
+
+def golden_network_pws():
+	"""
+	The same with delays SHORTER than the steps (past within step, _jitcdde.py:838-861): every tenth edge has a delay of
+	0.002–0.03 while the tolerance allows steps of ≈ 0.05–0.3, so lookups reach into the step under way, the step is
+	repeated until two successive results agree, shrunk when it is far from explicit, and the step size grows by the
+	credit rule afterwards. Default max_step (10), default pws parameters, no blind start: the integration starts at the
+	end of the constant past with first_step = 1 and has to find its step size through rejections with a tentative
+	anchor in place. Written by the reference's C core under the controller of oracle/controller.py.
+	"""
+	g = network_graph(n=96, k=6, seed=23)
+	rng = np.random.default_rng(5)
+	short = rng.random(len(g["edge_tau"])) < 0.1
+	g["edge_tau"] = np.where(short, rng.uniform(0.002, 0.03, len(short)), g["edge_tau"])
+	core = _reference_network_core(g, "ref_network_pws")
+	roots = roots_from(oracle.build(systems.program(systems.mackey_glass())))
+	max_delay = float(np.max(g["edge_tau"]))
+	C = controller.Controller(core, max_delay, root_mode=1, roots=roots, rtol=0, atol=1e-4)
+	times = np.arange(0.5, 12.5, 0.5)
+	samples, dts = [], []
+	for T in times:
+		samples.append(C.integrate(T))
+		dts.append(C.dt)
+	print(f"network_pws: accepted {C.accepted}, rejected {C.rejected}, short delays {int(short.sum())}, dt {min(dts):.4f}..{max(dts):.4f}")
+	save("network_pws", src=g["src"], dst=g["dst"], edge_tau=g["edge_tau"], weight=g["weight"], omega=g["omega"], initial=g["initial"],
+		times=times, samples=np.array(samples), dts=np.array(dts), accepted=C.accepted, rejected=C.rejected, final_t=C.t)
 
 
 def golden_data_input():
@@ -318,6 +351,6 @@ def golden_projected():
 if __name__ == "__main__":
 	assert build_ref.reference_available(), "run this where /root/reference exists"
 	makers = dict(roessler=golden_roessler, mg_ensemble=golden_mg_ensemble, neutral=golden_neutral, state_dependent=golden_state_dependent,
-		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected, network=golden_network)
+		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected, network=golden_network, network_pws=golden_network_pws)
 	for name in sys.argv[1:] or makers:      # optional arguments: only these fixtures
 		makers[name]()

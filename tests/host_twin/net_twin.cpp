@@ -15,7 +15,7 @@ struct jdde_net
 	jdde_net_desc desc{};
 	jdn_problem P{};
 	jdn_control ctrl{};
-	std::vector<double> times, hist, stage, par, tau, weight, scratch;
+	std::vector<double> times, hist, stage, tent[2], par, tau, weight, scratch;
 	std::vector<long long> row_ptr;
 	std::vector<int> src, cursor;
 	bool have_graph = false, have_past = false, have_int = false;
@@ -37,12 +37,16 @@ int jdde_net_create(const jdde_net_desc * d, jdde_net ** out)
 	size_t const n = (size_t)d->n, cap = (size_t)d->ring_capacity, E = (size_t)d->n_edges;
 	h->times.assign(cap, 0.0); h->hist.assign(2*cap*n, 0.0);
 	h->stage.assign(2*n, 0.0);
+	h->tent[0].assign(2*n, 0.0); h->tent[1].assign(2*n, 0.0);
 	h->par.assign(n*(JDN_NPARAMS ? JDN_NPARAMS : 1), 0.0);
 	h->row_ptr.assign((size_t)(d->hi-d->lo)+1, 0); h->src.assign(E, 0); h->tau.assign(E, 0.0); h->weight.assign(E, 0.0);
 	h->cursor.assign(E, 0); h->scratch.assign(3*E, 0.0);
 	jdn_problem & P = h->P;
 	P.ctrl = &h->ctrl; P.times = h->times.data(); P.hist = h->hist.data();
 	P.stage = h->stage.data(); P.node_par = h->par.data();
+	P.tentative[0] = h->tent[0].data(); P.tentative[1] = h->tent[1].data();
+	P.world = 1;
+	P.iterate = d->lo == 0 && d->hi == d->n;      /* (a rank of a partitioned network, exchange driven from Python: no iteration) */
 	P.row_ptr = h->row_ptr.data(); P.src = h->src.data(); P.tau = h->tau.data(); P.weight = h->weight.data(); P.cursor = h->cursor.data();
 	P.n = d->n; P.lo = d->lo; P.hi = d->hi; P.cap = d->ring_capacity; P.n_node_params = d->n_node_params;
 	*out = h;
@@ -84,6 +88,7 @@ int jdde_net_set_past(jdde_net * h, int32_t k, const double * times, const doubl
 	jdn_control & C = h->ctrl;
 	C.first = 0; C.current = k-1; C.t = times[k-1]; C.last_start = times[0]; C.status = JDDE_STATUS_OK; C.done = 1; C.commit_slot = -1;
 	C.accepted = C.rejected = C.attempts = 0;
+	C.tentative = 0; C.pws_pass = 0; C.pws_bits = C.diff_bits = 0;
 	h->have_past = true;
 	return JDDE_OK;
 }
@@ -94,6 +99,7 @@ int jdde_net_set_integration_parameters(jdde_net * h, const jdde_int_params * p,
 	if (q.first_step > q.max_step) q.first_step = q.max_step;
 	if (q.min_step > q.first_step) q.min_step = q.first_step;
 	h->ctrl.P = q; h->ctrl.dt = q.first_step; h->ctrl.max_delay = max_delay; h->ctrl.cap = h->P.cap;
+	h->ctrl.last_pws = 0.0; h->ctrl.count = 0; h->ctrl.credit = 0.0;
 	h->have_int = true;
 	return JDDE_OK;
 }
@@ -112,7 +118,7 @@ int jdde_net_begin(jdde_net * h, int32_t mode, double target, double step, int64
 	jdn_control & C = h->ctrl;
 	if (mode == JDN_MODE_CONTINUE) { jdn::continue_call(C); h->launches++; return JDDE_OK; }
 	if (C.status != JDDE_STATUS_OK) { C.done = 1; return JDDE_OK; }
-	C.mode = mode; C.target = target; C.commit_slot = -1; C.pws = 0; C.p_bits = 0;
+	C.mode = mode; C.target = target; C.commit_slot = -1; C.pws = 0; C.p_bits = 0; C.pws_bits = C.diff_bits = 0; C.pws_pass = 0;
 	if (mode == JDN_MODE_BLIND) { C.h = step; C.remaining = steps; C.done = steps <= 0; }
 	else { C.h = C.dt; C.done = !(C.t < target); if (C.done) jdn::forget(h->P, C); }
 	C.last_start = C.t;
@@ -127,11 +133,24 @@ int jdde_net_attempt(jdde_net * h)
 	h->launches++;
 	if (C.done) return JDDE_OK;
 	jdn::View V = jdn::view_of(h->P);
+	bool const iterate = h->P.iterate;
+	jdn::pair * const fresh = jdn::tentative_buffer(h->P, (int)(C.epoch & 1));
+	double overlap = 0.0;
 	for (long long e = 0; e < h->desc.n_edges; e++)
 	{
-		int pws = 0;
-		jdn::lookup_edge(h->P, V, C.h, e, h->scratch.data(), pws);
-		if (pws) C.pws = 1;
+		if (iterate)
+			jdn::lookup_edge_values(h->P, V, C.h, e, h->scratch[3*e], h->scratch[3*e+1], h->scratch[3*e+2], overlap);
+		else
+		{
+			int pws = 0;
+			jdn::lookup_edge(h->P, V, C.h, e, h->scratch.data(), pws);
+			if (pws) C.pws = 1;
+		}
+	}
+	if (overlap > 0.0)
+	{
+		union { unsigned long long u; double d; } bits; bits.d = overlap;
+		C.pws_bits = bits.u;
 	}
 	double m = -1.0;
 	for (long long i = h->P.lo; i < h->P.hi; i++)
@@ -139,6 +158,17 @@ int jdde_net_attempt(jdde_net * h)
 		jdn::pair staged;
 		double c = jdn::attempt_node(h->P, V, C.h, i, h->scratch.data(), staged);
 		reinterpret_cast<jdn::pair *>(h->P.stage)[i] = staged;
+		if (iterate)
+		{
+			if (C.pws_pass > 0)      /* check_new_y_diff against the result of the pass before */
+			{
+				double const difference = fabs(staged.state - jdn::last_tentative(h->P)[i].state);
+				double const tolerance = C.P.pws_atol + fabs(C.P.pws_rtol*staged.state);
+				if (!(tolerance >= difference))
+					C.diff_bits = 1;
+			}
+			fresh[i] = staged;
+		}
 		if (c >= 0.0 && c > m) m = c;
 	}
 	if (m > 0.0)
@@ -152,6 +182,7 @@ int jdde_net_attempt(jdde_net * h)
 int jdde_net_control(jdde_net * h)
 {
 	if (int rc = ready(h)) return rc;
+	h->ctrl.epoch++;      /* (the parity of the attempts selects the tentative buffer) */
 	jdn::control(h->P);
 	int const slot = h->ctrl.commit_slot;
 	if (slot >= 0)

@@ -6,18 +6,21 @@ import numpy as np
 import pytest
 import sympy
 
-from tests.test_network import kuramoto_graph, run_network, run_network_golden, run_symbolic
+from tests.test_network import kuramoto_graph, run_network, run_network_golden, run_network_pws_golden, run_symbolic
 
 pytestmark = pytest.mark.gpu
 
 
-def large_graph(n, k=10, seed=42):
+def large_graph(n, k=10, seed=42, short_delays=False):
 	"""BASELINE.json configs[3] shape: fixed in-degree k random graph, tau ~ U(pi/5, 2pi), omega = 1,
-	coupling strength of examples/kuramoto_network.py (c·q = 2.1) spread over the k inputs."""
+	coupling strength of examples/kuramoto_network.py (c·q = 2.1) spread over the k inputs. short_delays: every tenth delay
+	is shorter than the steps the tolerance allows (past within step)."""
 	rng = np.random.default_rng(seed)
 	dst = np.repeat(np.arange(n, dtype=np.int64), k)
 	src = rng.integers(0, n, size=n*k)
 	tau = rng.uniform(np.pi/5, 2*np.pi, size=n*k)
+	if short_delays:
+		tau = np.where(rng.random(n*k) < 0.1, rng.uniform(0.002, 0.03, n*k), tau)
 	return dict(n=n, src=src, dst=dst, edge_tau=tau, weight=42*0.05/k, omega=np.ones(n), initial=rng.uniform(0, 2*np.pi, n))
 
 
@@ -46,11 +49,32 @@ def test_network_engine_against_reference_core_on_gpu():
 	import sympy
 	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
 		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False)
-	net.set_integration_parameters(rtol=0, atol=1e-5)
+	net.set_integration_parameters(rtol=0, atol=1e-5, max_step=float(np.min(g["edge_tau"])))
 	net.constant_past(g["initial"], time=0.0)
 	net.integrate_blindly(float(g["blind_to"]), 0.1)
 	fast = np.array([net.integrate(T) for T in g["times"]])
 	np.testing.assert_allclose(fast, g["samples"], rtol=1e-10)
+	assert net.counters()[:2] == (int(g["accepted"]), int(g["rejected"]))
+
+
+def test_network_past_within_step_on_gpu():
+	"""delays shorter than the step (tests/golden/network_pws.npz, written by the reference's C core under the reference's
+	controller): the persistent stepper repeats a step until two successive results agree, as _jitcdde.py:838-861 —
+	identical step counts, step sizes and states, bit for bit"""
+	g, samples, dts, counters, t_end = run_network_pws_golden()
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert counters[2] > counters[0]+counters[1]
+	assert np.array_equal(dts, g["dts"])
+	assert np.array_equal(samples, g["samples"])
+	assert t_end == float(g["final_t"])
+	# production build: the same decisions, states to rounding
+	from jitcdde_b200 import jitcdde_network
+	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False)
+	net.set_integration_parameters(rtol=0, atol=1e-4)
+	net.constant_past(g["initial"], time=0.0)
+	fast = np.array([net.integrate(T) for T in g["times"]])
+	np.testing.assert_allclose(fast, g["samples"], rtol=1e-9)
 	assert net.counters()[:2] == (int(g["accepted"]), int(g["rejected"]))
 
 
@@ -68,7 +92,7 @@ def test_large_network_properties(n):
 	assert np.all(np.abs(drift-1.0) < 2.2)
 
 
-def _peer_worker(rank, world, port, queue, n, ring_capacity):
+def _peer_worker(rank, world, port, queue, n, ring_capacity, short_delays=False):
 	"""one rank of a two-process run: rank r on device r when the box has two GPUs (stores and arrival counters then cross
 	NVLink); with a single visible GPU both ranks share it (CUDA IPC works within a device, too)"""
 	import os
@@ -81,7 +105,7 @@ def _peer_worker(rank, world, port, queue, n, ring_capacity):
 	device = rank % torch.cuda.device_count()
 	torch.cuda.set_device(device)
 	dist.init_process_group("gloo", rank=rank, world_size=world)      # rendezvous only: carries the IPC handles
-	g = large_graph(n)
+	g = large_graph(n, short_delays=short_delays)
 	net = jitcdde_network(n, local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y), edges=(g["src"], g["dst"], g["edge_tau"]),
 		weight=g["weight"], node_parameters=[g["omega"]], verbose=False, device=device, ring_capacity=ring_capacity, exchange="peer")
 	net.set_integration_parameters(rtol=0, atol=1e-5)
@@ -93,8 +117,8 @@ def _peer_worker(rank, world, port, queue, n, ring_capacity):
 	dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ring_capacity", [512, 16])      # 16: the ring fills up and is doubled on both ranks while they integrate
-def test_fused_peer_exchange_equals_one_gpu(ring_capacity):
+@pytest.mark.parametrize("ring_capacity,short_delays", [(512, False), (16, False), (512, True)])      # 16: the ring fills up and is doubled on both ranks while they integrate; short delays: past within step, the overlap and "results differ" are merged between the ranks
+def test_fused_peer_exchange_equals_one_gpu(ring_capacity, short_delays):
 	"""Two ranks that own half of the nodes each and exchange the tentative anchor through peer memory from inside the step
 	kernel (device-side arrival barrier, csrc/jdn_kernels.cu: jdn_k_exchange) take the same steps and reach bit-identical
 	states as one rank that owns all nodes."""
@@ -109,7 +133,7 @@ def test_fused_peer_exchange_equals_one_gpu(ring_capacity):
 	except ImportError:
 		pass
 	n = 20_000
-	g = large_graph(n)
+	g = large_graph(n, short_delays=short_delays)
 	net = jitcdde_network(n, local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y), edges=(g["src"], g["dst"], g["edge_tau"]),
 		weight=g["weight"], node_parameters=[g["omega"]], verbose=False, ring_capacity=512)
 	net.set_integration_parameters(rtol=0, atol=1e-5)
@@ -117,6 +141,8 @@ def test_fused_peer_exchange_equals_one_gpu(ring_capacity):
 	blind = net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1)
 	out = net.integrate(net.t+2.0)
 	counters = net.counters()
+	if short_delays:
+		assert counters[2] > counters[0]+counters[1]      # steps were repeated
 	del net
 
 	sock = socket.socket()
@@ -125,7 +151,7 @@ def test_fused_peer_exchange_equals_one_gpu(ring_capacity):
 	sock.close()
 	ctx = mp.get_context("spawn")
 	queue = ctx.Queue()
-	procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, queue, n, ring_capacity)) for r in range(2)]
+	procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, queue, n, ring_capacity, short_delays)) for r in range(2)]
 	for p in procs:
 		p.start()
 	results = [queue.get(timeout=600) for _ in procs]

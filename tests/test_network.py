@@ -31,7 +31,7 @@ def run_network(g, sample_times, blind_to, **kw):
 	from jitcdde_b200 import jitcdde_network
 	net = jitcdde_network(g["n"], local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
 		edges=(g["src"], g["dst"], g["edge_tau"]), weight=g["weight"], node_parameters=[g["omega"]], verbose=False, **kw)
-	net.set_integration_parameters(rtol=0, atol=1e-6)
+	net.set_integration_parameters(rtol=0, atol=1e-6, max_step=float(np.min(g["edge_tau"])))      # (as run_symbolic)
 	net.constant_past(g["initial"], time=0.0)
 	blind = net.integrate_blindly(blind_to, 0.1)
 	samples = np.array([net.integrate(T) for T in sample_times])
@@ -49,7 +49,8 @@ def prebuild_images():
 	engine need (the symbolic path has one lookup site per edge; its image takes minutes to compile)"""
 	from jitcdde_b200 import _build, _codegen
 	_build.build_image(_codegen.generate(symbolic_f(kuramoto_graph(12))), mode=_build.VERIFY)
-	_build.build_net_image(_codegen.generate_network(lambda y, t, w: w, lambda yd, y: sympy.sin(yd-y), 1))
+	for mode in (_build.FAST, _build.VERIFY):
+		_build.build_net_image(_codegen.generate_network(lambda y, t, w: w, lambda yd, y: sympy.sin(yd-y), 1), mode=mode)
 
 
 def run_symbolic(g, sample_times, blind_to, **kw):
@@ -83,7 +84,7 @@ def run_network_golden(**kw):
 	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "network.npz"))
 	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
 		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False, verification=True, **kw)
-	net.set_integration_parameters(rtol=0, atol=1e-5)
+	net.set_integration_parameters(rtol=0, atol=1e-5, max_step=float(np.min(g["edge_tau"])))      # (as make_golden.py::golden_network)
 	net.constant_past(g["initial"], time=0.0)
 	blind = net.integrate_blindly(float(g["blind_to"]), 0.1)
 	samples = np.array([net.integrate(T) for T in g["times"]])
@@ -97,6 +98,35 @@ def test_network_engine_against_reference_core(twin):
 	assert np.array_equal(blind, g["blind"])
 	assert np.array_equal(samples, g["samples"])
 	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert t_end == float(g["final_t"])
+
+
+def run_network_pws_golden(**kw):
+	"""the 96-node network of tests/golden/network_pws.npz — every tenth delay shorter than the steps — on the network engine,
+	verification build, default integration parameters but the tolerance (as the reference core was driven: make_golden.py::golden_network_pws)"""
+	from jitcdde_b200 import jitcdde_network
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "network_pws.npz"))
+	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False, verification=True, **kw)
+	net.set_integration_parameters(rtol=0, atol=1e-4)
+	net.constant_past(g["initial"], time=0.0)
+	samples, dts = [], []
+	for T in g["times"]:
+		samples.append(net.integrate(T))
+		dts.append(net.dt)
+	return g, np.array(samples), np.array(dts), net.counters(), net.t
+
+
+def test_network_past_within_step_against_reference_core(twin):
+	"""Delays shorter than the step (_jitcdde.py:838-861): lookups reach into the step under way and interpolate towards the
+	result of the attempt before; the step is repeated until two successive results agree or shrunk, the step size then
+	grows by the credit rule. Same accepted and rejected counts, same step sizes, same bits as the reference's C core under
+	the reference's controller."""
+	g, samples, dts, counters, t_end = run_network_pws_golden()
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert counters[2] > counters[0]+counters[1]      # repetitions: more calls of get_next_step than steps
+	assert np.array_equal(dts, g["dts"])
+	assert np.array_equal(samples, g["samples"])
 	assert t_end == float(g["final_t"])
 
 

@@ -325,6 +325,14 @@ int jdde_net_recent_state(jdde_net * h, double t, int32_t current_only, double *
  * per-attempt form). */
 int jdde_net_grow_ring(jdde_net * h, int32_t new_capacity);
 int jdde_net_resume(jdde_net * h, double * out_state, int32_t * status);
+
+/* adjust_diff (_jitcdde.py:863-878: a zero-amplitude jump of width shift_ratio·(distance of the last two anchors) at the last
+ * anchor, jitced_template.c:1122-1174): the last anchor is replaced by two, the second with the derivative the differential
+ * equation gives there. minima/maxima [n] (may be null): extrema of every node over the jump interval. Several ranks: _begin
+ * on every rank, then a barrier of the ranks (phase 1 stores into the peers' buffers), then _end on every rank. */
+int jdde_net_adjust_diff(jdde_net * h, double shift_ratio, double * minima, double * maxima);
+int jdde_net_adjust_diff_begin(jdde_net * h, double shift_ratio);
+int jdde_net_adjust_diff_end(jdde_net * h, double * minima, double * maxima);
 int jdde_net_get_counters(jdde_net * h, int64_t * accepted, int64_t * rejected, int64_t * attempts);
 int jdde_net_get_dt(jdde_net * h, double * dt);
 int64_t jdde_net_launch_count(const jdde_net * h);

@@ -121,6 +121,9 @@ SIGNATURES.update({
 	"jdde_net_recent_state": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int32, c_double_p]),
 	"jdde_net_grow_ring": (ctypes.c_int, [_H, ctypes.c_int32]),
 	"jdde_net_resume": (ctypes.c_int, [_H, c_double_p, c_int32_p]),
+	"jdde_net_adjust_diff": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_double_p]),
+	"jdde_net_adjust_diff_begin": (ctypes.c_int, [_H, ctypes.c_double]),
+	"jdde_net_adjust_diff_end": (ctypes.c_int, [_H, c_double_p, c_double_p]),
 	"jdde_net_get_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
 	"jdde_net_get_dt": (ctypes.c_int, [_H, c_double_p]),
 	"jdde_net_launch_count": (ctypes.c_int64, [_H]),
@@ -609,6 +612,17 @@ class NetEngine:
 		status = ctypes.c_int32()
 		self._check(self.lib.jdde_net_resume(self._h, _dp(out), ctypes.byref(status)))
 		return out, status.value
+
+	def adjust_diff(self, shift_ratio=1e-4, barrier=None):
+		"""adjust_diff of the reference; returns (minima, maxima). Several ranks: `barrier` is called between the two halves."""
+		minima, maxima = np.empty(self.n), np.empty(self.n)
+		if barrier is None:
+			self._check(self.lib.jdde_net_adjust_diff(self._h, float(shift_ratio), _dp(minima), _dp(maxima)))
+		else:
+			self._check(self.lib.jdde_net_adjust_diff_begin(self._h, float(shift_ratio)))
+			barrier()
+			self._check(self.lib.jdde_net_adjust_diff_end(self._h, _dp(minima), _dp(maxima)))
+		return minima, maxima
 
 	def exchange_handle(self):
 		"""CUDA IPC handle of this rank's exchange buffer (bytes), to be passed to the peers"""

@@ -234,11 +234,27 @@ class jitcdde_network:
 		self._raise(status)
 		return self._engine.recent_state(target_time)
 
+	def adjust_diff(self, shift_ratio=1e-4):
+		"""as jitcdde.adjust_diff (_jitcdde.py:863-878): a zero-amplitude jump at the last anchor, so that the integration starts
+		with the derivative the differential equation gives there. Returns (minima, maxima) of every node over the jump interval."""
+		self._initiate()
+		if self.world > 1:
+			if self._exchange != "peer":
+				raise NotImplementedError("adjust_diff with several ranks needs the peer exchange (exchange='peer').")
+			import torch.distributed as dist
+			result = self._engine.adjust_diff(shift_ratio, barrier=dist.barrier)
+			dist.barrier()      # nobody goes on (and overwrites the buffers) before everybody has read them
+			return result
+		return self._engine.adjust_diff(shift_ratio)
+
 	def integrate_blindly(self, target_time, step=None):
-		"""as jitcdde.integrate_blindly (_jitcdde.py:880-933); target == t (adjust_diff) is not supported"""
+		"""as jitcdde.integrate_blindly (_jitcdde.py:880-933); with target_time == t it is adjust_diff, as there"""
 		self._initiate()
 		step = step or self.max_step
 		assert step > 0, "step must be positive"
+		if target_time == self._engine.poll()[1]:
+			self.adjust_diff()
+			return self._engine.recent_state(target_time, current_only=True)
 		if self.world == 1 or self._exchange == "peer":
 			out, status = self._engine.integrate_blindly(target_time, step)
 			while self._grow(status):

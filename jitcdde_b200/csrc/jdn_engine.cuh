@@ -458,6 +458,92 @@ JDN_FN void regrow_node(jdn_problem const & P, double * const new_hist, int cons
 		to[jdn_pair_index(k & (new_cap-1), i, P.n)] = from[jdn_pair_index(k & (P.cap-1), i, P.n)];
 }
 
+/*
+ * adjust_diff (_jitcdde.py:863-878): a jump of amplitude zero at the last anchor, i.e. apply_jump(0, time, width) with
+ * time = t_last − width, width = shift_ratio·(t_last − t_before) (jitced_template.c:1122-1174). It replaces the last
+ * anchor (t_last) by two: one at `time` with the interpolated state and derivative of the last segment (truncate_past,
+ * :1089-1108) and one at new_t = time + width with the interpolated state and the derivative that f gives there — so
+ * that the derivative at the start of the integration is the one of the differential equation instead of that of the
+ * initial past. Phase 1, ONE NODE: both anchors from the history as it is (f's lookups use the untouched list, its
+ * call sites keep their cursors); phase 2 writes them (adjust_diff_commit_node), so that no lookup of phase 1 sees them.
+ */
+JDN_FN void adjust_diff_node(jdn_problem const & P, View const & V, long long const i, double const time, double const new_t, pair & truncated, pair & fresh)
+{
+	pair const * const H = reinterpret_cast<pair const *>(P.hist);
+	int const left = V.current-1;      /* (the last anchor before new_t: time < new_t <= t_last + an ulp) */
+	pair const v = H[jdn_pair_index(left & V.mask, i, P.n)];
+	pair const w = H[jdn_pair_index(V.current & V.mask, i, P.n)];
+	fresh.state = hermite(V, left, new_t, v, w);
+	double par[JDN_NPARAMS > 0 ? JDN_NPARAMS : 1];
+	for (int k = 0; k < JDN_NPARAMS; k++)
+		par[k] = P.node_par[(size_t)k*P.n+i];
+	double acc = JDN_LOCAL(fresh.state, new_t, par);
+	long long const row = i-P.lo;
+	for (long long e = P.row_ptr[row]; e < P.row_ptr[row+1]; e++)
+	{
+		double const d = new_t-P.tau[e];
+		int const ca = walk(V, P.cursor[e], d);
+		P.cursor[e] = ca;
+		acc += P.weight[e]*JDN_COUPLING(past_value(P, V, ca, P.src[e], d), fresh.state);
+	}
+	fresh.diff = acc;
+	/* truncate_past: get_past_value and get_past_diff (jitced_template.c:237-251) at `time` */
+	truncated.state = hermite(V, left, time, v, w);
+	double const tv = anchor_time(V, left);
+	double const q = anchor_time(V, left+1)-tv;
+	double const x = (time - tv)/q;
+	double const a = v.state;
+	double const b = v.diff * q;
+	double const c = w.state;
+	double const d = w.diff * q;
+	truncated.diff = ( (1-x)*(b-x*3*(2*(a-c)+b+d)) + d*x ) / q;
+}
+
+/* phase 2, one node of the WHOLE network (every rank keeps the whole history): the two anchors go into ring slots current and
+ * current+1; minimum and maximum of the node on the segment between them (extrema, jitced_template.c:253-285) */
+JDN_FN void adjust_diff_commit_node(jdn_problem const & P, long long const i, double const q, pair const truncated, pair const fresh, double & minimum, double & maximum)
+{
+	jdn_control const & C = *P.ctrl;
+	pair * const H = reinterpret_cast<pair *>(P.hist);
+	H[jdn_pair_index(C.current & (P.cap-1), i, P.n)] = truncated;
+	H[jdn_pair_index((C.current+1) & (P.cap-1), i, P.n)] = fresh;
+	double const a = truncated.state;
+	double const b = truncated.diff * q;
+	double const c = fresh.state;
+	double const d = fresh.diff * q;
+	minimum = fmin(a, c);
+	maximum = fmax(a, c);
+	double const radicant = b*b + b*d + d*d + 3*(a-c)*(3*(a-c) + 2*(b+d));
+	if (radicant >= 0)
+	{
+		double const A = 1/(2*a + b - 2*c + d);
+		double const B = a + 2*b/3 - c + d/3;
+		for (int sign = -1; sign <= 1; sign += 2)
+		{
+			double const x = (B+sign*sqrt(radicant)/3) * A;
+			if (0 < x && x < 1)
+			{
+				double const value = (1-x) * ( (1-x) * (b*x + (a-c)*(2*x+1)) - d*x*x) + c;
+				minimum = fmin(minimum, value);
+				maximum = fmax(maximum, value);
+			}
+		}
+	}
+}
+
+/* after phase 2, one thread: the list now ends with the two new anchors, the second one is current (accept_step) */
+JDN_FN void adjust_diff_control(jdn_problem const & P, double const time, double const new_t)
+{
+	jdn_control & C = *P.ctrl;
+	int const mask = P.cap-1;
+	P.times[C.current & mask] = time;
+	C.current++;
+	P.times[C.current & mask] = new_t;
+	C.t = new_t;
+	C.tentative = 0;
+	C.commit_slot = -1;
+}
+
 /* get_recent_state, jitced_template.c:287-320: Hermite interpolation on the last segment */
 JDN_FN double recent_state(jdn_problem const & P, double const t, long long const i)
 {

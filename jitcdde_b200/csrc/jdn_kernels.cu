@@ -768,6 +768,53 @@ jdn_k_recent_state(jdn_problem const P, double const t, int const current_only, 
 		out[i] = jdn::recent_state(P, t, i);
 }
 
+/* adjust_diff, phase 1 (jdn_engine.cuh): node-parallel over the owned nodes; the two anchors go into tentative buffers 0 and 1
+ * of EVERY rank (several GPUs: the peers' staging buffers — the integration is at rest, nobody else uses them) */
+extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
+jdn_k_adjust_diff(jdn_problem const P, double const time, double const new_t)
+{
+	long long const k = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if (k >= P.hi-P.lo)
+		return;
+	long long const i = P.lo+k;
+	jdn::View const V = jdn::view_of(P);
+	jdn::pair truncated, fresh;
+	jdn::adjust_diff_node(P, V, i, time, new_t, truncated, fresh);
+	if (P.world > 1)
+		for (int r = 0; r < P.world; r++)
+		{
+			reinterpret_cast<jdn::pair *>(jdn_exchange_stage(P.peers[r], 0, P.n))[i] = truncated;
+			reinterpret_cast<jdn::pair *>(jdn_exchange_stage(P.peers[r], 1, P.n))[i] = fresh;
+		}
+	else
+	{
+		jdn::tentative_buffer(P, 0)[i] = truncated;
+		jdn::tentative_buffer(P, 1)[i] = fresh;
+	}
+}
+
+/* phase 2: all nodes (every rank keeps the whole history), after the ranks have met; extrema to out[0…n) and out[n…2n) */
+extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
+jdn_k_adjust_diff_commit(jdn_problem const P, double const time, double const new_t, double * const out)
+{
+	long long const i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if (i >= P.n)
+		return;
+	/* (written by the peers: read past L1) */
+	double2 const a = __ldcg(reinterpret_cast<double2 const *>(jdn::tentative_buffer(P, 0))+i);
+	double2 const b = __ldcg(reinterpret_cast<double2 const *>(jdn::tentative_buffer(P, 1))+i);
+	jdn::pair truncated, fresh;
+	truncated.state = a.x; truncated.diff = a.y;
+	fresh.state = b.x; fresh.diff = b.y;
+	jdn::adjust_diff_commit_node(P, i, new_t-time, truncated, fresh, out[i], out[P.n+i]);
+}
+
+extern "C" __global__ void jdn_k_adjust_diff_control(jdn_problem const P, double const time, double const new_t)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		jdn::adjust_diff_control(P, time, new_t);
+}
+
 /* initial past (initiate_past_from_list, jitced_template.c:575-606): anchors [k][n] → rows of the ring */
 extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
 jdn_k_set_past(jdn_problem const P, int const n_anchors, double const * const times, double const * const states, double const * const diffs, long long const n_edges)

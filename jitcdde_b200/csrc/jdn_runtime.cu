@@ -24,7 +24,7 @@ struct jdde_net
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	cudaLibrary_t lib = nullptr;
-	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr, k_regrow = nullptr, k_run = nullptr, k_run_warp = nullptr;
+	cudaKernel_t k_lookup = nullptr, k_attempt = nullptr, k_control = nullptr, k_commit = nullptr, k_begin = nullptr, k_recent = nullptr, k_set_past = nullptr, k_exchange = nullptr, k_regrow = nullptr, k_run = nullptr, k_run_warp = nullptr, k_adjust = nullptr, k_adjust_commit = nullptr, k_adjust_control = nullptr;
 	/* peer exchange: this rank's buffer (mapped by the peers through CUDA IPC), the peers' buffers mapped here */
 	jdn_exchange * exchange = nullptr;
 	std::vector<void *> mapped_peers;
@@ -32,7 +32,9 @@ struct jdde_net
 	int peer_rank = 0, peer_world = 1;
 	bool persistent = true;                   /* jdn_k_run (one cooperative launch per batch of attempts) instead of five kernels per attempt */
 	int run_grid = 0;                         /* co-resident blocks of jdn_k_run */
-	double min_tau = 0.0, max_step = 1e300;   /* smallest delay of this rank's in-edges; max_step of the integration parameters */
+	double min_tau = 0.0, max_step = 1e300;
+	double adjust_time = 0.0, adjust_new_t = 0.0;      /* between jdde_net_adjust_diff_begin and _end */
+	bool adjusting = false;   /* smallest delay of this rank's in-edges; max_step of the integration parameters */
 	int run_smem_bytes = 0;                   /* its dynamic shared memory beyond the anchor times (image descriptor) */
 	bool warp_tiles = false;                  /* jdn_k_run_warp (a warp per tile of <= 32 in-edges) instead of jdn_k_run (a block per tile of 64 nodes) */
 	int * d_tile_start = nullptr;
@@ -150,7 +152,7 @@ int jdde_net_create(const jdde_net_desc * d, jdde_net ** out)
 	if ((rc = nalloc(h, &h->d_weight, E))) return bail(rc);
 	if ((rc = nalloc(h, &P.cursor, E))) return bail(rc);
 	if ((rc = nalloc(h, &h->scratch, 3*E))) return bail(rc);
-	if ((rc = nalloc(h, &h->d_out, n))) return bail(rc);
+	if ((rc = nalloc(h, &h->d_out, 2*n))) return bail(rc);      /* states of all nodes; minima and maxima of adjust_diff */
 	P.node_par = h->d_par; P.row_ptr = h->d_row_ptr; P.src = h->d_src; P.tau = h->d_tau; P.weight = h->d_weight;
 	if (cudaMemsetAsync(P.ctrl, 0, sizeof(jdn_control), h->stream) != cudaSuccess) return bail(nfail(h, JDDE_E_CUDA, "cudaMemset failed"));
 	*out = h;
@@ -214,6 +216,10 @@ int jdde_net_load_image(jdde_net * h, const void * image, size_t len)
 		h->k_run_warp = nullptr;
 		(void)cudaGetLastError();
 	}
+	if (cudaLibraryGetKernel(&h->k_adjust, h->lib, "jdn_k_adjust_diff") != cudaSuccess
+		|| cudaLibraryGetKernel(&h->k_adjust_commit, h->lib, "jdn_k_adjust_diff_commit") != cudaSuccess
+		|| cudaLibraryGetKernel(&h->k_adjust_control, h->lib, "jdn_k_adjust_diff_control") != cudaSuccess)
+		return nfail(h, JDDE_E_IMAGE, "image lacks the adjust_diff kernels");
 	h->run_grid = 0;
 	h->P.tile_nodes = 0;
 	const char * const choice = getenv("JITCDDE_B200_NET_PERSISTENT");
@@ -624,6 +630,56 @@ int jdde_net_grow_ring(jdde_net * h, int32_t new_capacity)
 	JN_CUDA(h, cudaMemcpy(&h->P.ctrl->cap, &cap, sizeof cap, cudaMemcpyHostToDevice));
 	drop_batch(h);
 	return JDDE_OK;
+}
+
+/*
+ * adjust_diff (_jitcdde.py:863-878) in two halves, so that several ranks can meet in between (phase 1 stores this rank's
+ * nodes into every rank's buffers, phase 2 reads all nodes): begin → [barrier of the ranks] → end. One rank: jdde_net_adjust_diff.
+ */
+int jdde_net_adjust_diff_begin(jdde_net * h, double shift_ratio)
+{
+	int rc = nready_run(h);
+	if (rc) return rc;
+	if ((rc = jdde_net_poll(h, nullptr, nullptr, nullptr))) return rc;
+	jdn_control const & c = h->host_ctrl;
+	if (c.status != JDDE_STATUS_OK) return nfail(h, JDDE_E_INVALID, "the integration has failed; set a new past first");
+	if (c.current+2-c.first > h->P.cap) return nfail(h, JDDE_E_NOMEM, "anchor ring full; increase ring_capacity");
+	double before = 0.0;
+	JN_CUDA(h, cudaMemcpyAsync(&before, h->P.times+((c.current-1) & (h->P.cap-1)), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	double const width = shift_ratio*(c.t-before);      /* _jitcdde.py:875-878 and jump(…, forward=False), :958-960 */
+	h->adjust_time = c.t-width;
+	h->adjust_new_t = h->adjust_time+width;                 /* apply_jump: new->time = time+width, jitced_template.c:1141 */
+	void * args[] = { &h->P, &h->adjust_time, &h->adjust_new_t };
+	if ((rc = nlaunch(h, h->k_adjust, h->desc.hi-h->desc.lo, h->block, 0, args))) return rc;
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));          /* (the peers may read what this rank stored once the ranks have met) */
+	h->adjusting = true;
+	return JDDE_OK;
+}
+
+int jdde_net_adjust_diff_end(jdde_net * h, double * minima, double * maxima)
+{
+	int rc = nready_run(h);
+	if (rc) return rc;
+	if (!h->adjusting) return nfail(h, JDDE_E_INVALID, "jdde_net_adjust_diff_end without jdde_net_adjust_diff_begin");
+	h->adjusting = false;
+	void * args[] = { &h->P, &h->adjust_time, &h->adjust_new_t, &h->d_out };
+	if ((rc = nlaunch(h, h->k_adjust_commit, h->desc.n, h->block, 0, args))) return rc;
+	void * cargs[] = { &h->P, &h->adjust_time, &h->adjust_new_t };
+	if ((rc = nlaunch(h, h->k_adjust_control, 1, 1, 0, cargs))) return rc;
+	size_t const bytes = (size_t)h->desc.n*sizeof(double);
+	if (minima) JN_CUDA(h, cudaMemcpyAsync(minima, h->d_out, bytes, cudaMemcpyDeviceToHost, h->stream));
+	if (maxima) JN_CUDA(h, cudaMemcpyAsync(maxima, h->d_out+h->desc.n, bytes, cudaMemcpyDeviceToHost, h->stream));
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	return JDDE_OK;
+}
+
+int jdde_net_adjust_diff(jdde_net * h, double shift_ratio, double * minima, double * maxima)
+{
+	if (h && h->P.world > 1) return nfail(h, JDDE_E_INVALID, "several ranks: jdde_net_adjust_diff_begin, a barrier of the ranks, jdde_net_adjust_diff_end");
+	int rc = jdde_net_adjust_diff_begin(h, shift_ratio);
+	if (rc) return rc;
+	return jdde_net_adjust_diff_end(h, minima, maxima);
 }
 
 /* … and the call goes on where it stopped (same target, same remaining steps) */

@@ -267,6 +267,23 @@ def golden_network_pws():
 		times=times, samples=np.array(samples), dts=np.array(dts), accepted=C.accepted, rejected=C.rejected, final_t=C.t)
 
 
+def golden_network_adjust_diff():
+	"""adjust_diff at the end of a constant past (the alternative to the blind start of examples/kuramoto_network.py), then an
+	adaptive integration — by the reference's C core under the controller of oracle/controller.py"""
+	g = network_graph(n=64, k=5, seed=3)
+	core = _reference_network_core(g, "ref_network_adjust")
+	roots = roots_from(oracle.build(systems.program(systems.mackey_glass())))
+	max_delay = float(np.max(g["edge_tau"]))
+	C = controller.Controller(core, max_delay, root_mode=1, roots=roots, rtol=0, atol=1e-5)
+	minima, maxima = C.adjust_diff()
+	t_after = C.t
+	times = np.arange(0.5, 6.5, 0.5)
+	samples = np.array([C.integrate(T) for T in times])
+	print(f"network_adjust_diff: accepted {C.accepted}, rejected {C.rejected}")
+	save("network_adjust_diff", src=g["src"], dst=g["dst"], edge_tau=g["edge_tau"], weight=g["weight"], omega=g["omega"], initial=g["initial"],
+		minima=minima, maxima=maxima, t_after=t_after, times=times, samples=samples, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
+
+
 def golden_data_input():
 	"""the extended system and joined past that jitcdde_input hands to the core (reference: _jitcdde.py:1519-1659)"""
 	prog, past, max_delay = systems.data_input_program()
@@ -351,6 +368,7 @@ def golden_projected():
 if __name__ == "__main__":
 	assert build_ref.reference_available(), "run this where /root/reference exists"
 	makers = dict(roessler=golden_roessler, mg_ensemble=golden_mg_ensemble, neutral=golden_neutral, state_dependent=golden_state_dependent,
-		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected, network=golden_network, network_pws=golden_network_pws)
+		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected, network=golden_network, network_pws=golden_network_pws,
+		network_adjust_diff=golden_network_adjust_diff)
 	for name in sys.argv[1:] or makers:      # optional arguments: only these fixtures
 		makers[name]()

@@ -269,6 +269,33 @@ int jdde_net_grow_ring(jdde_net * h, int32_t new_cap)
 	return JDDE_OK;
 }
 
+int jdde_net_adjust_diff(jdde_net * h, double shift_ratio, double * minima, double * maxima)
+{
+	if (int rc = ready(h)) return rc;
+	jdn_control & C = h->ctrl;
+	int const mask = h->P.cap-1;
+	if (C.current+2-C.first > h->P.cap) return fail(h, JDDE_E_NOMEM, "anchor ring full; increase ring_capacity");
+	double const width = shift_ratio*(C.t-h->times[(C.current-1) & mask]);
+	double const time = C.t-width, new_t = time+width;
+	jdn::View const V = jdn::view_of(h->P);
+	size_t const n = (size_t)h->desc.n;
+	std::vector<jdn::pair> truncated(n), fresh(n);
+	for (long long i = h->P.lo; i < h->P.hi; i++)
+		jdn::adjust_diff_node(h->P, V, i, time, new_t, truncated[i], fresh[i]);
+	for (long long i = h->P.lo; i < h->P.hi; i++)
+	{
+		double lo, hi;
+		jdn::adjust_diff_commit_node(h->P, i, new_t-time, truncated[i], fresh[i], lo, hi);
+		if (minima) minima[i] = lo;
+		if (maxima) maxima[i] = hi;
+	}
+	jdn::adjust_diff_control(h->P, time, new_t);
+	h->launches += 3;
+	return JDDE_OK;
+}
+int jdde_net_adjust_diff_begin(jdde_net * h, double) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
+int jdde_net_adjust_diff_end(jdde_net * h, double *, double *) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
+
 int jdde_net_resume(jdde_net * h, double * out, int32_t * status)
 {
 	if (int rc = jdde_net_begin(h, JDN_MODE_CONTINUE, 0.0, 0.0, 0)) return rc;

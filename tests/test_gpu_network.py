@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import sympy
 
-from tests.test_network import kuramoto_graph, run_network, run_network_golden, run_network_pws_golden, run_symbolic
+from tests.test_network import kuramoto_graph, run_network, run_network_adjust_diff_golden, run_network_golden, run_network_pws_golden, run_symbolic
 
 pytestmark = pytest.mark.gpu
 
@@ -78,6 +78,17 @@ def test_network_past_within_step_on_gpu():
 	assert net.counters()[:2] == (int(g["accepted"]), int(g["rejected"]))
 
 
+def test_network_adjust_diff_on_gpu():
+	"""adjust_diff for a network (tests/golden/network_adjust_diff.npz, reference core): same extrema, same anchors — the
+	integration that follows takes the same steps to the same bits"""
+	g, minima, maxima, t_after, samples, counters, t_end = run_network_adjust_diff_golden()
+	assert np.array_equal(minima, g["minima"]) and np.array_equal(maxima, g["maxima"])
+	assert t_after == float(g["t_after"])
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert np.array_equal(samples, g["samples"])
+	assert t_end == float(g["final_t"])
+
+
 @pytest.mark.parametrize("n", [100_000, 1_000_000])      # 10^6 nodes, 10^7 edges: BASELINE.json configs[3]
 def test_large_network_properties(n):
 	g = large_graph(n)
@@ -90,6 +101,15 @@ def test_large_network_properties(n):
 	# phases advance roughly with omega = 1 plus bounded coupling
 	drift = (samples[-1]-g["initial"])/times[-1]
 	assert np.all(np.abs(drift-1.0) < 2.2)
+
+
+def _start(net, g, short_delays):
+	"""the blind start of examples/kuramoto_network.py — or, in the run with short delays, adjust_diff (both halves of it meet
+	between the ranks) — and what the network looks like afterwards"""
+	if short_delays:
+		minima, maxima = net.adjust_diff()
+		return np.concatenate([minima, maxima])
+	return net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1)
 
 
 def _peer_worker(rank, world, port, queue, n, ring_capacity, short_delays=False):
@@ -110,7 +130,7 @@ def _peer_worker(rank, world, port, queue, n, ring_capacity, short_delays=False)
 		weight=g["weight"], node_parameters=[g["omega"]], verbose=False, device=device, ring_capacity=ring_capacity, exchange="peer")
 	net.set_integration_parameters(rtol=0, atol=1e-5)
 	net.constant_past(g["initial"], time=0.0)
-	blind = net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1)
+	blind = _start(net, g, short_delays)
 	out = net.integrate(net.t+2.0)
 	queue.put((rank, blind, out, net.counters(), device, str(getattr(torch.cuda.get_device_properties(device), "uuid", device))))
 	dist.barrier()
@@ -138,7 +158,7 @@ def test_fused_peer_exchange_equals_one_gpu(ring_capacity, short_delays):
 		weight=g["weight"], node_parameters=[g["omega"]], verbose=False, ring_capacity=512)
 	net.set_integration_parameters(rtol=0, atol=1e-5)
 	net.constant_past(g["initial"], time=0.0)
-	blind = net.integrate_blindly(float(np.max(g["edge_tau"])), 0.1)
+	blind = _start(net, g, short_delays)
 	out = net.integrate(net.t+2.0)
 	counters = net.counters()
 	if short_delays:

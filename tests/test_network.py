@@ -130,6 +130,31 @@ def test_network_past_within_step_against_reference_core(twin):
 	assert t_end == float(g["final_t"])
 
 
+def run_network_adjust_diff_golden(**kw):
+	"""tests/golden/network_adjust_diff.npz (reference core: adjust_diff after a constant past, then integrate) on the network engine"""
+	from jitcdde_b200 import jitcdde_network
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "network_adjust_diff.npz"))
+	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False, verification=True, **kw)
+	net.set_integration_parameters(rtol=0, atol=1e-5)
+	net.constant_past(g["initial"], time=0.0)
+	minima, maxima = net.adjust_diff()
+	t_after = net.t
+	samples = np.array([net.integrate(T) for T in g["times"]])
+	return g, minima, maxima, t_after, samples, net.counters(), net.t
+
+
+def test_network_adjust_diff_against_reference_core(twin):
+	"""adjust_diff (_jitcdde.py:863-878, apply_jump + truncate_past of the C core) for a network: same extrema over the jump
+	interval, same anchors (the integration that follows takes the same steps to the same bits)"""
+	g, minima, maxima, t_after, samples, counters, t_end = run_network_adjust_diff_golden()
+	assert np.array_equal(minima, g["minima"]) and np.array_equal(maxima, g["maxima"])
+	assert t_after == float(g["t_after"])
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert np.array_equal(samples, g["samples"])
+	assert t_end == float(g["final_t"])
+
+
 def test_node_partition_exchange_protocol(twin):
 	"""Two engine instances, each owning half of the nodes (what two ranks hold), driven through the per-attempt
 	protocol attempt → exchange staged slices + max of the error norm → control: same trajectory as one instance."""

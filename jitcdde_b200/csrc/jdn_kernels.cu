@@ -280,6 +280,13 @@ __device__ __forceinline__ void jdn_run_commit(jdn_problem const & P, jdn_contro
 #ifndef JDN_RUN_MIN_BLOCKS
 #define JDN_RUN_MIN_BLOCKS 4
 #endif
+/* Several GPUs: how a tile's new pairs reach the peers' staging buffers. 1: ONE bulk copy (cp.async.bulk shared → global, up to
+ * 1 KB) per tile and peer, issued by one thread and completed asynchronously — the copy engine of the SM forms full NVLink
+ * packets, the threads go on with the next tile. 0: every node thread stores its 16-byte pair to every peer (round 2 before
+ * this: the overhead of the exchange grew in proportion to the bytes stored, ≈ 125 GB/s per GPU, profiles/configs_r02.md). */
+#ifndef JDN_BULK_PUSH
+#define JDN_BULK_PUSH 1
+#endif
 
 extern "C" __global__ void __launch_bounds__(JDN_BLOCK, JDN_RUN_MIN_BLOCKS)
 jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, int const max_attempts)
@@ -299,6 +306,9 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 	long long const n_tiles = (owned + tile_nodes-1)/tile_nodes;
 	__shared__ long long s_next_tile[2];      /* the tile after the one under way (two slots: written while the other is still read) */
 	__shared__ double s_tolerance[2];         /* atol, rtol */
+#if JDN_BULK_PUSH
+	__shared__ __align__(16) double2 s_out[JDN_TILE_NODES];      /* the tile's new (state, diff) pairs on their way to the peers */
+#endif
 	JDN_PHASE_STATE;
 	for (int attempt = 0; attempt < max_attempts; attempt++)
 	{
@@ -338,6 +348,10 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 				s_row[threadIdx.x] = P.row_ptr[row0+threadIdx.x];
 			if (threadIdx.x == blockDim.x-1)
 				s_next_tile[turn] = (long long)gridDim.x + atomicAdd(&P.ctrl->next_tile, 1);
+#if JDN_BULK_PUSH
+			if (P.world > 1 && threadIdx.x == 0)      /* the bulk copies of the tile before have read s_out */
+				asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
 			__syncthreads();
 			long long const e0 = s_row[0];
 			int const ne = (int)(s_row[nn]-e0);
@@ -438,9 +452,17 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 						}
 						if (P.keep_tentative)
 							jdn::tentative_buffer(P, buffer)[i] = staged;
+#if JDN_BULK_PUSH
+						if (P.world > 1)
+						{
+							s_out[threadIdx.x] = make_double2(staged.state, staged.diff);
+							asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      /* visible to the bulk copy below */
+						}
+#else
 						for (int r = 0; r < P.world; r++)
 							if (r != P.rank)
 								reinterpret_cast<jdn::pair *>(jdn_exchange_stage(P.peers[r], buffer, P.n))[i] = staged;
+#endif
 						/* get_p, jitced_template.c:474-498: 0/0 is skipped, a NaN never wins the comparison */
 						double const tolerance = s_tolerance[0] + s_tolerance[1]*fabs(y_stage);
 						if (error != 0.0 || tolerance != 0.0)
@@ -454,8 +476,28 @@ jdn_k_run(jdn_problem const P, double * const scratch, long long const n_edges, 
 				}
 				__syncthreads();
 			}
+#if JDN_BULK_PUSH
+			if (P.world > 1 && threadIdx.x == 0)
+			{
+				/* consecutive nodes at consecutive 16-byte pairs of every other rank's staging buffer */
+				unsigned const source = (unsigned)__cvta_generic_to_shared(s_out);
+				unsigned const bytes = (unsigned)nn*16u;
+				for (int r = 0; r < P.world; r++)
+					if (r != P.rank)
+					{
+						unsigned long long const target = (unsigned long long)__cvta_generic_to_global(
+							reinterpret_cast<jdn::pair *>(jdn_exchange_stage(P.peers[r], buffer, P.n)) + (P.lo+row0));
+						asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(target), "r"(source), "r"(bytes) : "memory");
+					}
+				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			}
+#endif
 			tile = s_next_tile[turn];
 		}
+#if JDN_BULK_PUSH
+		if (P.world > 1 && threadIdx.x == 0)      /* all of this block's pairs have been written at the peers */
+			asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
 		/* error norm of this block's nodes (threads 0 … JDN_TILE_NODES−1 hold them) */
 		for (int o = 16; o > 0; o >>= 1)
 			block_contribution = fmax(block_contribution, __shfl_down_sync(0xffffffffu, block_contribution, o));

@@ -199,27 +199,34 @@ __device__ __forceinline__ void jdn_run_exchange_and_control(jdn_problem const &
 	{
 		unsigned long long const mine = C.pws ? JDN_PWS_SENTINEL : C.p_bits;
 		if (mine)
-			for (int r = 0; r < P.world; r++)
-				atomicMax_system(&P.peers[r]->p_bits[buffer], mine);
+			for (int r = 0; r < P.world; r++)      /* (reductions that return nothing: posted, not waited for one by one) */
+				asm volatile("red.relaxed.sys.global.max.u64 [%0], %1;" :: "l"(&P.peers[r]->p_bits[buffer]), "l"(mine) : "memory");
 		if (C.pws_bits)      /* rare: a delay shorter than the step */
 			for (int r = 0; r < P.world; r++)
 				atomicMax_system(&P.peers[r]->pws_bits[buffer], C.pws_bits);
 		if (C.diff_bits)
 			for (int r = 0; r < P.world; r++)
 				atomicMax_system(&P.peers[r]->diff_bits[buffer], C.diff_bits);
+		/* ONE system-scope fence orders everything this rank has stored (the grid barrier has made the other blocks' stores
+		 * this thread's business) before the arrival increments, which can then be relaxed — a release increment per peer
+		 * is a fence per peer, one after the other; the poll is relaxed, too, with one fence once all have arrived */
 		__threadfence_system();
 		for (int r = 0; r < P.world; r++)
 			if (r != P.rank)
-				asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(&P.peers[r]->arrived), "l"(1ull) : "memory");
+				asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(&P.peers[r]->arrived), "l"(1ull) : "memory");
+		JDN_PHASE(2);
 		jdn_exchange * const own = P.peers[P.rank];
 		unsigned long long const expected = (C.epoch+1)*(unsigned long long)(P.world-1);
 		unsigned long long start, now, arrived;
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
 		for (;;)
 		{
-			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(arrived) : "l"(&own->arrived) : "memory");
+			asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(arrived) : "l"(&own->arrived) : "memory");
 			if (arrived >= expected)
+			{
+				__threadfence_system();
 				break;
+			}
 			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
 			if (now-start > 20000000000ull)      /* a peer that does not arrive within 20 s ends the integration instead of hanging the device */
 			{
@@ -229,7 +236,7 @@ __device__ __forceinline__ void jdn_run_exchange_and_control(jdn_problem const &
 				arrived_all = false;
 				break;
 			}
-			__nanosleep(100);
+			__nanosleep(20);
 		}
 		if (arrived_all)
 		{

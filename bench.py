@@ -281,15 +281,17 @@ def ncu_traffic():
 		return None, None
 
 
-def parity_check(engine, pars, sample_times, last_states, picks=512, seed=7):
+def parity_check(counters, pars, sample_times, last_states, picks=512, seed=7):
 	"""A random subsample of the members of THIS run (production build, FMA contraction) against the CPU oracle
-	(verification arithmetic) over the whole history of the run: accepted-step counts and the states at the last sample."""
+	(verification arithmetic) over the first samples of the run (snapshot taken before the settle phase; the members with
+	larger delays and gains are chaotic, so the comparison has a horizon): accepted-step counts and the states at the last
+	sample of the snapshot."""
 	from oracle import oracle
 	from tests import systems
 	rng = np.random.default_rng(seed)
 	N = len(pars)
 	pick = np.sort(rng.choice(N, min(picks, N), replace=False))
-	accepted = engine.get_counters()[0][pick]
+	accepted = counters[pick]
 	lib = oracle.build(systems.program(systems.mackey_glass()))
 	past = (np.array([-1.0, 0.0]), np.ones((2, 1)), np.zeros((2, 1)))
 	ref = oracle.run_ensemble(lib, past, pars[pick], MAX_DELAY, 1, pars[pick, 1:2].copy(), np.asarray(sample_times, dtype=float), absolute_samples=True)
@@ -396,27 +398,91 @@ def gpu_arm(args):
 			done += n
 
 	clocks = ClockSampler(local_rank)      # started before the warm-up: NVML's first queries are slow
+
+	# the first 63 samples of the run (to t = 660), and a snapshot of counters and states after them for `parity_check`
+	parity_snapshot = None
+	device_samples(60)
+	snapshot_states, _ = engine.integrate_samples(times_of(3))
+	if rank == 0 and not args.no_parity:
+		parity_snapshot = (engine.get_counters()[0].copy(), list(sample_times), np.array(snapshot_states[-1]))
+
+	# Untimed, before the W warm-up steps: wait until the device is quiet. A process that has just released a lot of device
+	# memory (the GPU test-suite allocates 100 GB for the full-size Lyapunov ensemble) leaves the driver clearing it for tens of
+	# seconds, during which this kernel was measured 4 % to 28× slower (profiles/README.md), recovering gradually. Launches of S
+	# samples are repeated in windows of 0.4 s until the median of a window is no longer more than 0.5 % faster than that of the
+	# window before (a quiet device: two windows), at most 120 s.
+	settle = {"launches": 0, "first_ms_per_step": None, "last_ms_per_step": None, "windows": 0}
+	settle_start = time.perf_counter()
+	# first of all: the memory of an earlier process is back (free memory no longer grows), at most 60 s
+	free_before = torch.cuda.mem_get_info(local_rank)[0]
+	while time.perf_counter()-settle_start < 60.0:
+		time.sleep(0.25)
+		free_now = torch.cuda.mem_get_info(local_rank)[0]
+		if free_now <= free_before + (64 << 20):
+			break
+		free_before = free_now
+	settle["waited_for_memory_seconds"] = time.perf_counter()-settle_start
+	s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	previous = None
+	while time.perf_counter()-settle_start < 120.0:
+		window, window_start = [], time.perf_counter()
+		while time.perf_counter()-window_start < 0.4:
+			s0.record(stream)
+			device_samples(S)
+			s1.record(stream)
+			torch.cuda.synchronize()
+			window.append(s0.elapsed_time(s1)/S)
+		median = float(np.median(window))
+		settle["launches"] += len(window)
+		settle["windows"] += 1
+		if settle["first_ms_per_step"] is None:
+			settle["first_ms_per_step"] = window[0]
+		settle["last_ms_per_step"] = median
+		if previous is not None and median > 0.995*previous:
+			break
+		previous = median
+	settle["seconds"] = time.perf_counter()-settle_start
+
 	device_samples(args.warmup)
-	accepted_before = engine.sum_counters()[0]
-	launches_before = engine.launch_count
 	ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-	barrier()
+
+	def timed_steps():
+		"""exactly K steps, device-timed between barriers; (ms as max over ranks, accepted steps of all ranks, launches of this rank)"""
+		accepted_before = engine.sum_counters()[0]
+		launches_before = engine.launch_count
+		barrier()
+		ev0.record(stream)
+		device_samples(args.steps)
+		ev1.record(stream)
+		clocks.sample_now()      # the host is ahead of the GPU here: the launches above are still running
+		barrier()
+		launches = engine.launch_count-launches_before      # (launches of jdde_k_integrate inside the timed region)
+		return reduce_max(ev0.elapsed_time(ev1)), reduce_sum(engine.sum_counters()[0]-accepted_before), launches
+
+	def repeated(measure):
+		"""The timed region is repeated until the two fastest repeats agree within 2 % (a quiet machine: two repeats), at most 8
+		times or 60 s: another process's leftovers (see the settle phase above) come in bursts and only ever slow a repeat
+		down. Reported: the SECOND fastest repeat; all repeats are listed in the line."""
+		results, start = [], time.perf_counter()
+		while True:
+			results.append(measure())
+			times = sorted(r[0] for r in results)
+			if len(times) >= 2 and times[1] < 1.02*times[0]:
+				break
+			if len(times) >= 8 or time.perf_counter()-start > 60.0:
+				break
+		chosen = sorted(results, key=lambda r: r[0])[min(1, len(results)-1)]
+		return chosen, [r[0]/args.steps for r in results]
+
 	clocks.mark_start()
-	ev0.record(stream)
-	device_samples(args.steps)
-	ev1.record(stream)
-	clocks.sample_now()      # the host is ahead of the GPU here: the launches above are still running
-	barrier()
+	(ms, total_accepted, launches), value_repeats = repeated(timed_steps)
 	clocks.mark_end()
 	clocks.stop()
-	ms = reduce_max(ev0.elapsed_time(ev1))
-	launches = engine.launch_count-launches_before
-	accepted = engine.sum_counters()[0]-accepted_before
-	total_accepted = reduce_sum(accepted)
 	status = engine.get_status()
 	if status.any():
 		raise SystemExit(f"members failed: {np.unique(status)}")
 	value = total_accepted/(ms*1e-3)
+	accepted = total_accepted/world      # (weak scaling: every rank takes the same mix of members)
 
 	# ---------------- end to end through the public API with host buffers: `e2e`
 	# per launch: the S sample times go host→device, the kernel runs and writes the states of every sample (S×N×8 B)
@@ -425,9 +491,27 @@ def gpu_arm(args):
 	# (integrate_samples(..., wait=False) / wait_result / synchronize): while the kernel of one launch runs, the states
 	# of the previous one are read on the host.
 	outs = [pinned_empty((S, members, 1)), pinned_empty((S, members, 1))]
-	for i in range(2):
-		DDE.integrate_samples(times_of(S), out=outs[i])
-	accepted_before = engine.sum_counters()[0]
+	# untimed, as before the device-resident loop: the same path (kernel + copy of the states to page-locked memory) in windows
+	# of 0.4 s until a window is no longer faster than the one before, at most 60 s (a quiet machine: two windows)
+	e2e_settle = {"launches": 0, "windows": 0, "first_ms_per_step": None, "last_ms_per_step": None}
+	e2e_settle_start = time.perf_counter()
+	previous = None
+	while time.perf_counter()-e2e_settle_start < 60.0:
+		window, window_start = [], time.perf_counter()
+		while time.perf_counter()-window_start < 0.4 or len(window) < 2:
+			w = time.perf_counter()
+			DDE.integrate_samples(times_of(S), out=outs[len(window) & 1])
+			window.append(1e3*(time.perf_counter()-w)/S)
+		median = float(np.median(window))
+		e2e_settle["launches"] += len(window)
+		e2e_settle["windows"] += 1
+		if e2e_settle["first_ms_per_step"] is None:
+			e2e_settle["first_ms_per_step"] = window[0]
+		e2e_settle["last_ms_per_step"] = median
+		if previous is not None and median > 0.995*previous:
+			break
+		previous = median
+	e2e_settle["seconds"] = time.perf_counter()-e2e_settle_start
 	# launch sizes: S samples per launch, tapering off towards the end (…, S, S/2, S/4, …) — the copy of one launch's states to the
 	# host overlaps the kernel of the next, so only the LAST launch's copy is exposed, and a small last launch keeps it short
 	e2e_launches = []
@@ -436,23 +520,30 @@ def gpu_arm(args):
 		n = S if left >= 2*S else max(1, (left+1)//2) if left > 2 else left
 		e2e_launches.append(min(n, left))
 		left -= e2e_launches[-1]
-	barrier()
-	w0 = time.perf_counter()
-	ev0.record(stream)
-	checksum = 0.0
-	for i, n in enumerate(e2e_launches):
-		DDE.integrate_samples(times_of(n), out=outs[i & 1][:n], wait=False)   # queue: H2D sample times, kernel, states to the host
-		if i:
-			DDE.wait_result(1)                                                  # the previous launch has arrived …
-			checksum += float(outs[(i-1) & 1][e2e_launches[i-1]-1, 0, 0])       # … and is read on the host
-	DDE.synchronize()                                                           # last launch + failed-member count (8 B) + status check
-	last = len(e2e_launches)-1
-	last_states = outs[last & 1][e2e_launches[last]-1]
-	checksum += float(last_states[0, 0])
-	ev1.record(stream)
-	barrier()
-	e2e_ms = reduce_max(max(ev0.elapsed_time(ev1), 1e3*(time.perf_counter()-w0)))
-	e2e_accepted = reduce_sum(engine.sum_counters()[0]-accepted_before)
+	checksums = []
+
+	def timed_e2e():
+		accepted_before = engine.sum_counters()[0]
+		barrier()
+		w0 = time.perf_counter()
+		ev0.record(stream)
+		checksum = 0.0
+		for i, n in enumerate(e2e_launches):
+			DDE.integrate_samples(times_of(n), out=outs[i & 1][:n], wait=False)   # queue: H2D sample times, kernel, states to the host
+			if i:
+				DDE.wait_result(1)                                                  # the previous launch has arrived …
+				checksum += float(outs[(i-1) & 1][e2e_launches[i-1]-1, 0, 0])       # … and is read on the host
+		DDE.synchronize()                                                           # last launch + failed-member count (8 B) + status check
+		last = len(e2e_launches)-1
+		checksum += float(outs[last & 1][e2e_launches[last]-1][0, 0])
+		ev1.record(stream)
+		barrier()
+		checksums.append(checksum)
+		ms_e2e = reduce_max(max(ev0.elapsed_time(ev1), 1e3*(time.perf_counter()-w0)))
+		return ms_e2e, reduce_sum(engine.sum_counters()[0]-accepted_before), len(e2e_launches)
+
+	(e2e_ms, e2e_accepted, _), e2e_repeats = repeated(timed_e2e)
+	checksum = checksums[-1]
 	e2e_value = e2e_accepted/(e2e_ms*1e-3)
 
 	peak, peak_source = measured_peaks()
@@ -468,6 +559,9 @@ def gpu_arm(args):
 		"e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(members*8),
 			"ms_per_step": e2e_ms/args.steps, "api": "DDE.integrate_samples(times, out=pinned, wait=False) + wait_result(1) per launch, synchronize() at the end", "samples_per_launch": e2e_launches},
 		"gpu_launches": int(launches),
+		"e2e_settle": e2e_settle,
+		"repeats_ms_per_step": {"value": value_repeats, "e2e": e2e_repeats, "rule": "each repeat times exactly K steps; repeated until the two fastest agree within 2 % (at most 8 repeats or 60 s); the second fastest is reported"},
+		"settle": dict(settle, what="untimed launches before the warm-up, in windows of 0.4 s, until a window's median is no longer faster than the one before (the device may still be clearing memory released by an earlier process)"),
 		"clocks": clocks.summary(),
 		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": traffic,
 			"traffic_source": traffic_source and f"{traffic_source} (ncu capture of one launch of this workload, {SAMPLES_PER_LAUNCH} samples; not measured by this run)",
@@ -479,7 +573,7 @@ def gpu_arm(args):
 		"setup": {"seconds": setup_seconds, "what": "code generation, kernel image (cache hit or nvcc), engine creation, upload of past and parameters, step_on_discontinuities; not part of any timed region"},
 	}
 	if rank == 0 and not args.no_parity:
-		line["parity_check"] = parity_check(engine, pars, sample_times, np.array(last_states), picks=args.parity_members)
+		line["parity_check"] = parity_check(parity_snapshot[0], pars, parity_snapshot[1], parity_snapshot[2], picks=args.parity_members)
 	del outs
 	DDE._drop_engine()
 	if not args.no_extras:

@@ -469,7 +469,7 @@ def gpu_arm(args):
 			times = sorted(r[0] for r in results)
 			if len(times) >= 2 and times[1] < 1.02*times[0]:
 				break
-			if len(times) >= 8 or time.perf_counter()-start > 60.0:
+			if len(times) >= 8 or reduce_max(time.perf_counter()-start) > 60.0:      # (the same decision on every rank)
 				break
 		chosen = sorted(results, key=lambda r: r[0])[min(1, len(results)-1)]
 		return chosen, [r[0]/args.steps for r in results]

@@ -267,6 +267,32 @@ def golden_network_pws():
 		times=times, samples=np.array(samples), dts=np.array(dts), accepted=C.accepted, rejected=C.rejected, final_t=C.t)
 
 
+def saturated_ring(n=8, tau=0.1):
+	"""a ring of n nearly uncoupled phase oscillators, every delay equal to tau: with a loose tolerance the step size saturates at
+	max_step = tau, and (t+h)−tau then lands one ulp above t in a few percent of the attempts"""
+	rng = np.random.default_rng(2)
+	dst = np.arange(n, dtype=np.int64)
+	return dict(n=n, src=(dst-1) % n, dst=dst, edge_tau=np.full(n, tau), weight=0.05, omega=rng.uniform(0.9, 1.1, n), initial=rng.uniform(0, 2*np.pi, n))
+
+
+def golden_network_saturated():
+	"""step size saturated at max_step = the (only) delay, then blind steps of exactly that length — by the reference's C core:
+	the one-ulp overlaps are past-within-step events there, too (the step is shrunk by pws_factor and the attempt rejected)"""
+	g = saturated_ring()
+	core = _reference_network_core(g, "ref_network_saturated")
+	roots = roots_from(oracle.build(systems.program(systems.mackey_glass())))
+	C = controller.Controller(core, 0.1, root_mode=1, roots=roots, rtol=0, atol=1e-3, max_step=0.1, first_step=0.1)
+	times = np.arange(2.0, 42.0, 2.0)
+	samples, dts = [], []
+	for T in times:
+		samples.append(C.integrate(T))
+		dts.append(C.dt)
+	blind = C.integrate_blindly(C.t+5.0, 0.1)
+	print(f"network_saturated: accepted {C.accepted}, rejected {C.rejected}, dt {min(dts)}..{max(dts)}")
+	save("network_saturated", src=g["src"], dst=g["dst"], edge_tau=g["edge_tau"], weight=g["weight"], omega=g["omega"], initial=g["initial"],
+		times=times, samples=np.array(samples), dts=np.array(dts), blind=blind, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
+
+
 def golden_network_adjust_diff():
 	"""adjust_diff at the end of a constant past (the alternative to the blind start of examples/kuramoto_network.py), then an
 	adaptive integration — by the reference's C core under the controller of oracle/controller.py"""
@@ -369,6 +395,6 @@ if __name__ == "__main__":
 	assert build_ref.reference_available(), "run this where /root/reference exists"
 	makers = dict(roessler=golden_roessler, mg_ensemble=golden_mg_ensemble, neutral=golden_neutral, state_dependent=golden_state_dependent,
 		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected, network=golden_network, network_pws=golden_network_pws,
-		network_adjust_diff=golden_network_adjust_diff)
+		network_adjust_diff=golden_network_adjust_diff, network_saturated=golden_network_saturated)
 	for name in sys.argv[1:] or makers:      # optional arguments: only these fixtures
 		makers[name]()

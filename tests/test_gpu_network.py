@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import sympy
 
-from tests.test_network import kuramoto_graph, run_network, run_network_adjust_diff_golden, run_network_golden, run_network_pws_golden, run_symbolic
+from tests.test_network import kuramoto_graph, run_network, run_network_adjust_diff_golden, run_network_golden, run_network_pws_golden, run_network_saturated_golden, run_symbolic
 
 pytestmark = pytest.mark.gpu
 
@@ -76,6 +76,17 @@ def test_network_past_within_step_on_gpu():
 	fast = np.array([net.integrate(T) for T in g["times"]])
 	np.testing.assert_allclose(fast, g["samples"], rtol=1e-9)
 	assert net.counters()[:2] == (int(g["accepted"]), int(g["rejected"]))
+
+
+def test_step_size_saturated_at_the_smallest_delay_on_gpu():
+	"""the step size saturates at max_step = the delay: one-ulp overlaps are handled as by the reference (tests/golden/network_saturated.npz,
+	reference core), blind steps of exactly the delay included"""
+	g, samples, dts, blind, counters, t_end = run_network_saturated_golden()
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert np.array_equal(dts, g["dts"])
+	assert np.array_equal(samples, g["samples"])
+	assert np.array_equal(blind, g["blind"])
+	assert t_end == float(g["final_t"])
 
 
 def test_network_adjust_diff_on_gpu():

@@ -155,6 +155,35 @@ def test_network_adjust_diff_against_reference_core(twin):
 	assert t_end == float(g["final_t"])
 
 
+def run_network_saturated_golden(**kw):
+	"""tests/golden/network_saturated.npz: a ring whose step size saturates at max_step = the delay, then blind steps of that length"""
+	from jitcdde_b200 import jitcdde_network
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "network_saturated.npz"))
+	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False, verification=True, **kw)
+	net.set_integration_parameters(rtol=0, atol=1e-3, max_step=0.1, first_step=0.1)
+	net.constant_past(g["initial"], time=0.0)
+	samples, dts = [], []
+	for T in g["times"]:
+		samples.append(net.integrate(T))
+		dts.append(net.dt)
+	blind = net.integrate_blindly(net.t+5.0, 0.1)
+	return g, np.array(samples), np.array(dts), blind, net.counters(), net.t
+
+
+def test_step_size_saturated_at_the_smallest_delay(twin):
+	"""ADVICE.md (round 1): once dt has saturated at max_step = smallest delay, (t+h)−tau rounds one ulp above t in a few percent of
+	the attempts. That is a past-within-step event of one ulp — in the reference, too, which shrinks the step by pws_factor and
+	rejects the attempt (12 of 474 here) — not a reason to stop; blind steps of exactly the delay extrapolate the last segment by
+	that ulp. Same counts, step sizes and bits as the reference's C core."""
+	g, samples, dts, blind, counters, t_end = run_network_saturated_golden()
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert np.array_equal(dts, g["dts"]) and dts.max() == 0.1 and dts.min() < 0.1
+	assert np.array_equal(samples, g["samples"])
+	assert np.array_equal(blind, g["blind"])
+	assert t_end == float(g["final_t"])
+
+
 def test_node_partition_exchange_protocol(twin):
 	"""Two engine instances, each owning half of the nodes (what two ranks hold), driven through the per-attempt
 	protocol attempt → exchange staged slices + max of the error norm → control: same trajectory as one instance."""

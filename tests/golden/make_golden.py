@@ -293,6 +293,35 @@ def golden_network_saturated():
 		times=times, samples=np.array(samples), dts=np.array(dts), blind=blind, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
 
 
+def hub_graph(n=200, hub=57, hub_degree=1100, seed=9):
+	"""a hub with more in-edges than a tile of the persistent stepper keeps in shared memory (1024: that tile goes through the
+	scratch array), nodes without in-edges, in-degree 0–4 elsewhere"""
+	rng = np.random.default_rng(seed)
+	degree = rng.integers(0, 5, n)
+	degree[hub] = hub_degree
+	degree[[3, 120]] = 0
+	dst = np.repeat(np.arange(n, dtype=np.int64), degree)
+	src = rng.integers(0, n, len(dst))
+	tau = rng.uniform(0.5, 3.0, len(dst))
+	return dict(n=n, src=src, dst=dst, edge_tau=tau, weight=0.002, omega=rng.uniform(0.8, 1.2, n), initial=rng.uniform(0, 2*np.pi, n))
+
+
+def golden_network_hub():
+	"""a network with a hub of 1100 in-edges (the tile with the hub does not fit the shared-memory staging of jdn_k_run) and
+	nodes without in-edges — by the reference's C core"""
+	g = hub_graph()
+	core = _reference_network_core(g, "ref_network_hub")
+	roots = roots_from(oracle.build(systems.program(systems.mackey_glass())))
+	max_delay, min_delay = float(np.max(g["edge_tau"])), float(np.min(g["edge_tau"]))
+	C = controller.Controller(core, max_delay, root_mode=1, roots=roots, rtol=0, atol=1e-5, max_step=min_delay, first_step=min(1.0, min_delay))
+	blind = C.integrate_blindly(max_delay, 0.1)
+	times = max_delay + np.arange(0.5, 4.5, 0.5)
+	samples = np.array([C.integrate(T) for T in times])
+	print(f"network_hub: {len(g['src'])} edges, accepted {C.accepted}, rejected {C.rejected}")
+	save("network_hub", src=g["src"], dst=g["dst"], edge_tau=g["edge_tau"], weight=g["weight"], omega=g["omega"], initial=g["initial"],
+		blind_to=max_delay, blind=blind, times=times, samples=samples, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
+
+
 def golden_network_adjust_diff():
 	"""adjust_diff at the end of a constant past (the alternative to the blind start of examples/kuramoto_network.py), then an
 	adaptive integration — by the reference's C core under the controller of oracle/controller.py"""
@@ -395,6 +424,7 @@ if __name__ == "__main__":
 	assert build_ref.reference_available(), "run this where /root/reference exists"
 	makers = dict(roessler=golden_roessler, mg_ensemble=golden_mg_ensemble, neutral=golden_neutral, state_dependent=golden_state_dependent,
 		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected, network=golden_network, network_pws=golden_network_pws,
-		network_adjust_diff=golden_network_adjust_diff, network_saturated=golden_network_saturated)
+		network_adjust_diff=golden_network_adjust_diff, network_saturated=golden_network_saturated,
+		network_hub=golden_network_hub)
 	for name in sys.argv[1:] or makers:      # optional arguments: only these fixtures
 		makers[name]()

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import sympy
 
-from tests.test_network import kuramoto_graph, run_network, run_network_adjust_diff_golden, run_network_golden, run_network_pws_golden, run_network_saturated_golden, run_symbolic
+from tests.test_network import kuramoto_graph, run_network, run_network_adjust_diff_golden, run_network_golden, run_network_hub_golden, run_network_pws_golden, run_network_saturated_golden, run_symbolic
 
 pytestmark = pytest.mark.gpu
 
@@ -76,6 +76,16 @@ def test_network_past_within_step_on_gpu():
 	fast = np.array([net.integrate(T) for T in g["times"]])
 	np.testing.assert_allclose(fast, g["samples"], rtol=1e-9)
 	assert net.counters()[:2] == (int(g["accepted"]), int(g["rejected"]))
+
+
+def test_network_with_a_hub_on_gpu():
+	"""a hub with 1100 in-edges — its tile exceeds the 1024 edges jdn_k_run stages in shared memory and goes through the scratch
+	array — and nodes without in-edges: bit-identical with the reference core (tests/golden/network_hub.npz)"""
+	g, blind, samples, counters, t_end = run_network_hub_golden()
+	assert np.array_equal(blind, g["blind"])
+	assert np.array_equal(samples, g["samples"])
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert t_end == float(g["final_t"])
 
 
 def test_step_size_saturated_at_the_smallest_delay_on_gpu():

@@ -77,6 +77,19 @@ def test_network_engine_matches_symbolic_path(twin):
 	assert abs(nt-st) < 1e-9
 
 
+def run_network_hub_golden(**kw):
+	"""tests/golden/network_hub.npz: a hub with 1100 in-edges, nodes without in-edges (reference core)"""
+	from jitcdde_b200 import jitcdde_network
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "network_hub.npz"))
+	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False, verification=True, **kw)
+	net.set_integration_parameters(rtol=0, atol=1e-5, max_step=float(np.min(g["edge_tau"])))
+	net.constant_past(g["initial"], time=0.0)
+	blind = net.integrate_blindly(float(g["blind_to"]), 0.1)
+	samples = np.array([net.integrate(T) for T in g["times"]])
+	return g, blind, samples, net.counters(), net.t
+
+
 def run_network_golden(**kw):
 	"""the 128-node network of tests/golden/network.npz (outputs of the REFERENCE'S C core, tests/golden/make_golden.py::golden_network)
 	on the network engine, verification build"""
@@ -181,6 +194,15 @@ def test_step_size_saturated_at_the_smallest_delay(twin):
 	assert np.array_equal(dts, g["dts"]) and dts.max() == 0.1 and dts.min() < 0.1
 	assert np.array_equal(samples, g["samples"])
 	assert np.array_equal(blind, g["blind"])
+	assert t_end == float(g["final_t"])
+
+
+def test_network_with_a_hub_against_reference_core(twin):
+	"""in-degrees from 0 to 1100: the sums of a node run over its in-edges in input order, however many"""
+	g, blind, samples, counters, t_end = run_network_hub_golden()
+	assert np.array_equal(blind, g["blind"])
+	assert np.array_equal(samples, g["samples"])
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
 	assert t_end == float(g["final_t"])
 
 

@@ -333,6 +333,12 @@ int jdde_net_resume(jdde_net * h, double * out_state, int32_t * status);
 int jdde_net_adjust_diff(jdde_net * h, double shift_ratio, double * minima, double * maxima);
 int jdde_net_adjust_diff_begin(jdde_net * h, double shift_ratio);
 int jdde_net_adjust_diff_end(jdde_net * h, double * minima, double * maxima);
+
+/* jump (_jitcdde.py:935-974, apply_jump of the C core): amplitude [n] is added to the state over the interval (time, time+width)
+ * (forward != 0) or (time−width, time); the time must lie on the last segment of the history — usually it is the time the
+ * integration has reached. Several ranks: jdde_net_jump_begin, a barrier of the ranks, jdde_net_adjust_diff_end. */
+int jdde_net_jump(jdde_net * h, const double * amplitude, double time, double width, int32_t forward, double * minima, double * maxima);
+int jdde_net_jump_begin(jdde_net * h, const double * amplitude, double time, double width, int32_t forward);
 int jdde_net_get_counters(jdde_net * h, int64_t * accepted, int64_t * rejected, int64_t * attempts);
 int jdde_net_get_dt(jdde_net * h, double * dt);
 int64_t jdde_net_launch_count(const jdde_net * h);

@@ -123,6 +123,8 @@ SIGNATURES.update({
 	"jdde_net_resume": (ctypes.c_int, [_H, c_double_p, c_int32_p]),
 	"jdde_net_adjust_diff": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_double_p]),
 	"jdde_net_adjust_diff_begin": (ctypes.c_int, [_H, ctypes.c_double]),
+	"jdde_net_jump": (ctypes.c_int, [_H, c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_double_p, c_double_p]),
+	"jdde_net_jump_begin": (ctypes.c_int, [_H, c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_int32]),
 	"jdde_net_adjust_diff_end": (ctypes.c_int, [_H, c_double_p, c_double_p]),
 	"jdde_net_get_counters": (ctypes.c_int, [_H, c_int64_p, c_int64_p, c_int64_p]),
 	"jdde_net_get_dt": (ctypes.c_int, [_H, c_double_p]),
@@ -620,6 +622,18 @@ class NetEngine:
 			self._check(self.lib.jdde_net_adjust_diff(self._h, float(shift_ratio), _dp(minima), _dp(maxima)))
 		else:
 			self._check(self.lib.jdde_net_adjust_diff_begin(self._h, float(shift_ratio)))
+			barrier()
+			self._check(self.lib.jdde_net_adjust_diff_end(self._h, _dp(minima), _dp(maxima)))
+		return minima, maxima
+
+	def jump(self, amplitude, time, width=1e-5, forward=True, barrier=None):
+		"""jump of the reference; amplitude: [n]; returns (minima, maxima). Several ranks: `barrier` is called between the two halves."""
+		amplitude = np.ascontiguousarray(np.broadcast_to(np.asarray(amplitude, dtype=np.float64), (self.n,)))
+		minima, maxima = np.empty(self.n), np.empty(self.n)
+		if barrier is None:
+			self._check(self.lib.jdde_net_jump(self._h, _dp(amplitude), float(time), float(width), int(bool(forward)), _dp(minima), _dp(maxima)))
+		else:
+			self._check(self.lib.jdde_net_jump_begin(self._h, _dp(amplitude), float(time), float(width), int(bool(forward))))
 			barrier()
 			self._check(self.lib.jdde_net_adjust_diff_end(self._h, _dp(minima), _dp(maxima)))
 		return minima, maxima

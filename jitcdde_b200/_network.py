@@ -247,6 +247,20 @@ class jitcdde_network:
 			return result
 		return self._engine.adjust_diff(shift_ratio)
 
+	def jump(self, amplitude, time, width=1e-5, forward=True):
+		"""as jitcdde.jump (_jitcdde.py:935-974): adds `amplitude` (a number or one per node) to the state over the interval
+		(time, time+width) — or (time−width, time) with forward=False —, for a time on the last segment of the history (usually
+		the time the integration has reached). Returns (minima, maxima) of every node over the jump interval."""
+		self._initiate()
+		if self.world > 1:
+			if self._exchange != "peer":
+				raise NotImplementedError("jump with several ranks needs the peer exchange (exchange='peer').")
+			import torch.distributed as dist
+			result = self._engine.jump(amplitude, time, width, forward, barrier=dist.barrier)
+			dist.barrier()
+			return result
+		return self._engine.jump(amplitude, time, width, forward)
+
 	def integrate_blindly(self, target_time, step=None):
 		"""as jitcdde.integrate_blindly (_jitcdde.py:880-933); with target_time == t it is adjust_diff, as there"""
 		self._initiate()

@@ -464,16 +464,17 @@ JDN_FN void regrow_node(jdn_problem const & P, double * const new_hist, int cons
  * anchor (t_last) by two: one at `time` with the interpolated state and derivative of the last segment (truncate_past,
  * :1089-1108) and one at new_t = time + width with the interpolated state and the derivative that f gives there — so
  * that the derivative at the start of the integration is the one of the differential equation instead of that of the
- * initial past. Phase 1, ONE NODE: both anchors from the history as it is (f's lookups use the untouched list, its
+ * initial past. `jump` (_jitcdde.py:935-974) is the same with an amplitude added to the state of the second anchor, at
+ * time (forward) or time − width, here for a time on the last segment of the history. Phase 1, ONE NODE: both anchors from the history as it is (f's lookups use the untouched list, its
  * call sites keep their cursors); phase 2 writes them (adjust_diff_commit_node), so that no lookup of phase 1 sees them.
  */
-JDN_FN void adjust_diff_node(jdn_problem const & P, View const & V, long long const i, double const time, double const new_t, pair & truncated, pair & fresh)
+JDN_FN void adjust_diff_node(jdn_problem const & P, View const & V, long long const i, double const time, double const new_t, double const change, pair & truncated, pair & fresh)
 {
 	pair const * const H = reinterpret_cast<pair const *>(P.hist);
 	int const left = V.current-1;      /* (the last anchor before new_t: time < new_t <= t_last + an ulp) */
 	pair const v = H[jdn_pair_index(left & V.mask, i, P.n)];
 	pair const w = H[jdn_pair_index(V.current & V.mask, i, P.n)];
-	fresh.state = hermite(V, left, new_t, v, w);
+	fresh.state = hermite(V, left, new_t, v, w) + change;      /* (jump: the amplitude of this node; adjust_diff: zero) */
 	double par[JDN_NPARAMS > 0 ? JDN_NPARAMS : 1];
 	for (int k = 0; k < JDN_NPARAMS; k++)
 		par[k] = P.node_par[(size_t)k*P.n+i];

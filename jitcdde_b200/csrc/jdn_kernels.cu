@@ -820,7 +820,7 @@ jdn_k_recent_state(jdn_problem const P, double const t, int const current_only, 
 /* adjust_diff, phase 1 (jdn_engine.cuh): node-parallel over the owned nodes; the two anchors go into tentative buffers 0 and 1
  * of EVERY rank (several GPUs: the peers' staging buffers — the integration is at rest, nobody else uses them) */
 extern "C" __global__ void __launch_bounds__(JDN_BLOCK)
-jdn_k_adjust_diff(jdn_problem const P, double const time, double const new_t)
+jdn_k_adjust_diff(jdn_problem const P, double const time, double const new_t, double const * const amplitude)
 {
 	long long const k = (long long)blockIdx.x*blockDim.x + threadIdx.x;
 	if (k >= P.hi-P.lo)
@@ -828,7 +828,7 @@ jdn_k_adjust_diff(jdn_problem const P, double const time, double const new_t)
 	long long const i = P.lo+k;
 	jdn::View const V = jdn::view_of(P);
 	jdn::pair truncated, fresh;
-	jdn::adjust_diff_node(P, V, i, time, new_t, truncated, fresh);
+	jdn::adjust_diff_node(P, V, i, time, new_t, amplitude ? amplitude[i] : 0.0, truncated, fresh);
 	if (P.world > 1)
 		for (int r = 0; r < P.world; r++)
 		{

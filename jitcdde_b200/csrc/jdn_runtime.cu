@@ -636,7 +636,28 @@ int jdde_net_grow_ring(jdde_net * h, int32_t new_capacity)
  * adjust_diff (_jitcdde.py:863-878) in two halves, so that several ranks can meet in between (phase 1 stores this rank's
  * nodes into every rank's buffers, phase 2 reads all nodes): begin → [barrier of the ranks] → end. One rank: jdde_net_adjust_diff.
  */
-int jdde_net_adjust_diff_begin(jdde_net * h, double shift_ratio)
+/* apply_jump(amplitude, time, width) (jitced_template.c:1122-1174) for a `time` on the last segment of the history; phase 1 */
+static int jump_begin(jdde_net * h, const double * amplitude, double time, double width, double t_last, double t_before)
+{
+	int rc;
+	if (!(time > t_before) || !(time <= t_last) || !(width > 0))
+		return nfail(h, JDDE_E_INVALID, "jump: the time must lie on the last segment of the history (after the last anchor but one, not after the last) and the width must be positive");
+	h->adjust_time = time;
+	h->adjust_new_t = time+width;                           /* apply_jump: new->time = time+width, jitced_template.c:1141 */
+	double * d_amplitude = nullptr;
+	if (amplitude)
+	{
+		d_amplitude = h->d_out;                             /* (free until phase 2 writes the extrema) */
+		JN_CUDA(h, cudaMemcpyAsync(d_amplitude, amplitude, (size_t)h->desc.n*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+	}
+	void * args[] = { &h->P, &h->adjust_time, &h->adjust_new_t, &d_amplitude };
+	if ((rc = nlaunch(h, h->k_adjust, h->desc.hi-h->desc.lo, h->block, 0, args))) return rc;
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));          /* (the peers may read what this rank stored once the ranks have met) */
+	h->adjusting = true;
+	return JDDE_OK;
+}
+
+static int last_two_times(jdde_net * h, double * t_last, double * t_before)
 {
 	int rc = nready_run(h);
 	if (rc) return rc;
@@ -644,17 +665,29 @@ int jdde_net_adjust_diff_begin(jdde_net * h, double shift_ratio)
 	jdn_control const & c = h->host_ctrl;
 	if (c.status != JDDE_STATUS_OK) return nfail(h, JDDE_E_INVALID, "the integration has failed; set a new past first");
 	if (c.current+2-c.first > h->P.cap) return nfail(h, JDDE_E_NOMEM, "anchor ring full; increase ring_capacity");
-	double before = 0.0;
-	JN_CUDA(h, cudaMemcpyAsync(&before, h->P.times+((c.current-1) & (h->P.cap-1)), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	JN_CUDA(h, cudaMemcpyAsync(t_before, h->P.times+((c.current-1) & (h->P.cap-1)), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
 	JN_CUDA(h, cudaStreamSynchronize(h->stream));
-	double const width = shift_ratio*(c.t-before);      /* _jitcdde.py:875-878 and jump(…, forward=False), :958-960 */
-	h->adjust_time = c.t-width;
-	h->adjust_new_t = h->adjust_time+width;                 /* apply_jump: new->time = time+width, jitced_template.c:1141 */
-	void * args[] = { &h->P, &h->adjust_time, &h->adjust_new_t };
-	if ((rc = nlaunch(h, h->k_adjust, h->desc.hi-h->desc.lo, h->block, 0, args))) return rc;
-	JN_CUDA(h, cudaStreamSynchronize(h->stream));          /* (the peers may read what this rank stored once the ranks have met) */
-	h->adjusting = true;
+	*t_last = c.t;
 	return JDDE_OK;
+}
+
+int jdde_net_adjust_diff_begin(jdde_net * h, double shift_ratio)
+{
+	double t_last = 0.0, t_before = 0.0;
+	int rc = last_two_times(h, &t_last, &t_before);
+	if (rc) return rc;
+	double const width = shift_ratio*(t_last-t_before);      /* _jitcdde.py:875-878 and jump(…, forward=False), :958-960 */
+	return jump_begin(h, nullptr, t_last-width, width, t_last, t_before);
+}
+
+/* jump (_jitcdde.py:935-974): amplitude [n]; forward != 0: the jump interval is (time, time+width), else (time−width, time) */
+int jdde_net_jump_begin(jdde_net * h, const double * amplitude, double time, double width, int32_t forward)
+{
+	if (!amplitude) return nfail(h, JDDE_E_INVALID, "null argument");
+	double t_last = 0.0, t_before = 0.0;
+	int rc = last_two_times(h, &t_last, &t_before);
+	if (rc) return rc;
+	return jump_begin(h, amplitude, forward ? time : time-width, width, t_last, t_before);
 }
 
 int jdde_net_adjust_diff_end(jdde_net * h, double * minima, double * maxima)
@@ -672,6 +705,14 @@ int jdde_net_adjust_diff_end(jdde_net * h, double * minima, double * maxima)
 	if (maxima) JN_CUDA(h, cudaMemcpyAsync(maxima, h->d_out+h->desc.n, bytes, cudaMemcpyDeviceToHost, h->stream));
 	JN_CUDA(h, cudaStreamSynchronize(h->stream));
 	return JDDE_OK;
+}
+
+int jdde_net_jump(jdde_net * h, const double * amplitude, double time, double width, int32_t forward, double * minima, double * maxima)
+{
+	if (h && h->P.world > 1) return nfail(h, JDDE_E_INVALID, "several ranks: jdde_net_jump_begin, a barrier of the ranks, jdde_net_adjust_diff_end");
+	int rc = jdde_net_jump_begin(h, amplitude, time, width, forward);
+	if (rc) return rc;
+	return jdde_net_adjust_diff_end(h, minima, maxima);
 }
 
 int jdde_net_adjust_diff(jdde_net * h, double shift_ratio, double * minima, double * maxima)

@@ -339,6 +339,29 @@ def golden_network_adjust_diff():
 		minima=minima, maxima=maxima, t_after=t_after, times=times, samples=samples, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
 
 
+def golden_network_jump():
+	"""jumps during the integration of a network (forward with one amplitude per node, backward with a common one) — by the
+	reference's C core under the controller of oracle/controller.py"""
+	g = network_graph(n=64, k=5, seed=3)
+	core = _reference_network_core(g, "ref_network_jump")
+	roots = roots_from(oracle.build(systems.program(systems.mackey_glass())))
+	max_delay, min_delay = float(np.max(g["edge_tau"])), float(np.min(g["edge_tau"]))
+	C = controller.Controller(core, max_delay, root_mode=1, roots=roots, rtol=0, atol=1e-5, max_step=min_delay, first_step=min(1.0, min_delay))
+	C.integrate_blindly(max_delay, 0.1)
+	first = C.integrate(max_delay+2.0)
+	amplitude = np.random.default_rng(4).uniform(-0.5, 0.5, g["n"])
+	extrema_1 = C.jump(amplitude, C.t, 1e-5, forward=True)
+	t_1 = C.t
+	second = np.array([C.integrate(T) for T in max_delay+np.array([2.5, 3.0, 4.0])])
+	extrema_2 = C.jump(0.3, C.t, 1e-4, forward=False)
+	t_2 = C.t
+	third = np.array([C.integrate(T) for T in max_delay+np.array([4.5, 5.0, 6.0])])
+	print(f"network_jump: accepted {C.accepted}, rejected {C.rejected}")
+	save("network_jump", src=g["src"], dst=g["dst"], edge_tau=g["edge_tau"], weight=g["weight"], omega=g["omega"], initial=g["initial"],
+		blind_to=max_delay, first=first, amplitude=amplitude, minima_1=extrema_1[0], maxima_1=extrema_1[1], t_1=t_1, second=second,
+		minima_2=extrema_2[0], maxima_2=extrema_2[1], t_2=t_2, third=third, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
+
+
 def golden_data_input():
 	"""the extended system and joined past that jitcdde_input hands to the core (reference: _jitcdde.py:1519-1659)"""
 	prog, past, max_delay = systems.data_input_program()
@@ -425,6 +448,6 @@ if __name__ == "__main__":
 	makers = dict(roessler=golden_roessler, mg_ensemble=golden_mg_ensemble, neutral=golden_neutral, state_dependent=golden_state_dependent,
 		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected, network=golden_network, network_pws=golden_network_pws,
 		network_adjust_diff=golden_network_adjust_diff, network_saturated=golden_network_saturated,
-		network_hub=golden_network_hub)
+		network_hub=golden_network_hub, network_jump=golden_network_jump)
 	for name in sys.argv[1:] or makers:      # optional arguments: only these fixtures
 		makers[name]()

@@ -269,19 +269,18 @@ int jdde_net_grow_ring(jdde_net * h, int32_t new_cap)
 	return JDDE_OK;
 }
 
-int jdde_net_adjust_diff(jdde_net * h, double shift_ratio, double * minima, double * maxima)
+static int twin_jump(jdde_net * h, const double * amplitude, double time, double width, double * minima, double * maxima)
 {
-	if (int rc = ready(h)) return rc;
 	jdn_control & C = h->ctrl;
 	int const mask = h->P.cap-1;
 	if (C.current+2-C.first > h->P.cap) return fail(h, JDDE_E_NOMEM, "anchor ring full; increase ring_capacity");
-	double const width = shift_ratio*(C.t-h->times[(C.current-1) & mask]);
-	double const time = C.t-width, new_t = time+width;
+	if (!(time > h->times[(C.current-1) & mask]) || !(time <= C.t) || !(width > 0)) return fail(h, JDDE_E_INVALID, "jump: the time must lie on the last segment of the history");
+	double const new_t = time+width;
 	jdn::View const V = jdn::view_of(h->P);
 	size_t const n = (size_t)h->desc.n;
 	std::vector<jdn::pair> truncated(n), fresh(n);
 	for (long long i = h->P.lo; i < h->P.hi; i++)
-		jdn::adjust_diff_node(h->P, V, i, time, new_t, truncated[i], fresh[i]);
+		jdn::adjust_diff_node(h->P, V, i, time, new_t, amplitude ? amplitude[i] : 0.0, truncated[i], fresh[i]);
 	for (long long i = h->P.lo; i < h->P.hi; i++)
 	{
 		double lo, hi;
@@ -293,6 +292,18 @@ int jdde_net_adjust_diff(jdde_net * h, double shift_ratio, double * minima, doub
 	h->launches += 3;
 	return JDDE_OK;
 }
+int jdde_net_adjust_diff(jdde_net * h, double shift_ratio, double * minima, double * maxima)
+{
+	if (int rc = ready(h)) return rc;
+	double const width = shift_ratio*(h->ctrl.t-h->times[(h->ctrl.current-1) & (h->P.cap-1)]);
+	return twin_jump(h, nullptr, h->ctrl.t-width, width, minima, maxima);
+}
+int jdde_net_jump(jdde_net * h, const double * amplitude, double time, double width, int32_t forward, double * minima, double * maxima)
+{
+	if (int rc = ready(h)) return rc;
+	return twin_jump(h, amplitude, forward ? time : time-width, width, minima, maxima);
+}
+int jdde_net_jump_begin(jdde_net * h, const double *, double, double, int32_t) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
 int jdde_net_adjust_diff_begin(jdde_net * h, double) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
 int jdde_net_adjust_diff_end(jdde_net * h, double *, double *) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
 

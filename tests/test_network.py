@@ -206,6 +206,40 @@ def test_network_with_a_hub_against_reference_core(twin):
 	assert t_end == float(g["final_t"])
 
 
+def run_network_jump_golden(**kw):
+	"""tests/golden/network_jump.npz (reference core): a forward jump with one amplitude per node, a backward jump with a common one"""
+	from jitcdde_b200 import jitcdde_network
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "network_jump.npz"))
+	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False, verification=True, **kw)
+	net.set_integration_parameters(rtol=0, atol=1e-5, max_step=float(np.min(g["edge_tau"])))
+	net.constant_past(g["initial"], time=0.0)
+	b = float(g["blind_to"])
+	net.integrate_blindly(b, 0.1)
+	out = {"first": net.integrate(b+2.0)}
+	out["minima_1"], out["maxima_1"] = net.jump(g["amplitude"], net.t, 1e-5, forward=True)
+	out["t_1"] = net.t
+	out["second"] = np.array([net.integrate(T) for T in b+np.array([2.5, 3.0, 4.0])])
+	out["minima_2"], out["maxima_2"] = net.jump(0.3, net.t, 1e-4, forward=False)
+	out["t_2"] = net.t
+	out["third"] = np.array([net.integrate(T) for T in b+np.array([4.5, 5.0, 6.0])])
+	return g, out, net.counters(), net.t
+
+
+def check_network_jump(g, out, counters, t_end):
+	for key in ("first", "minima_1", "maxima_1", "second", "minima_2", "maxima_2", "third"):
+		assert np.array_equal(out[key], g[key]), key
+	assert out["t_1"] == float(g["t_1"]) and out["t_2"] == float(g["t_2"])
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert t_end == float(g["final_t"])
+
+
+def test_network_jump_against_reference_core(twin):
+	"""jump (_jitcdde.py:935-974, apply_jump of the C core) for a network, forward and backward: same extrema, same anchors, the
+	integration goes on with the same steps to the same bits"""
+	check_network_jump(*run_network_jump_golden())
+
+
 def test_node_partition_exchange_protocol(twin):
 	"""Two engine instances, each owning half of the nodes (what two ranks hold), driven through the per-attempt
 	protocol attempt → exchange staged slices + max of the error norm → control: same trajectory as one instance."""

@@ -318,6 +318,9 @@ int jdde_net_connect_peers(jdde_net * h, int32_t rank, int32_t world, const void
 /* whole calls on a single rank: integrate (_jitcdde.py:807-836), integrate_blindly (:880-933), state [n] */
 int jdde_net_integrate(jdde_net * h, double target, double * out_state, int32_t * status);
 int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double * out_state, int32_t * status);
+/* one entry of the step list of step_on_discontinuities (_jitcdde.py:985-997): adaptive steps to `target`, each attempt capped at
+ * the distance to it; otherwise as jdde_net_integrate (status, ring growth and jdde_net_resume included) */
+int jdde_net_step_to(jdde_net * h, double target, double * out_state, int32_t * status);
 int jdde_net_recent_state(jdde_net * h, double t, int32_t current_only, double * out_state);
 /* The reference's history is an unbounded list (jitced_template.c:56-73); when the ring is full, a call ends with status
  * JDDE_STATUS_OVERFLOW. jdde_net_grow_ring moves the live anchors into a larger ring (a power of two) and jdde_net_resume

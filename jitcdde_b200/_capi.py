@@ -121,6 +121,7 @@ SIGNATURES.update({
 	"jdde_net_recent_state": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_int32, c_double_p]),
 	"jdde_net_grow_ring": (ctypes.c_int, [_H, ctypes.c_int32]),
 	"jdde_net_resume": (ctypes.c_int, [_H, c_double_p, c_int32_p]),
+	"jdde_net_step_to": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_int32_p]),
 	"jdde_net_adjust_diff": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_double_p]),
 	"jdde_net_adjust_diff_begin": (ctypes.c_int, [_H, ctypes.c_double]),
 	"jdde_net_jump": (ctypes.c_int, [_H, c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_double_p, c_double_p]),
@@ -602,6 +603,13 @@ class NetEngine:
 		out = np.empty(self.n)
 		status = ctypes.c_int32()
 		self._check(self.lib.jdde_net_integrate_blindly(self._h, float(target), float(step or 0.0), _dp(out), ctypes.byref(status)))
+		return out, status.value
+
+	def step_to(self, target):
+		"""adaptive steps capped at the target (one entry of the step list of step_on_discontinuities); returns (state, status)"""
+		out = np.empty(self.n)
+		status = ctypes.c_int32()
+		self._check(self.lib.jdde_net_step_to(self._h, float(target), _dp(out), ctypes.byref(status)))
 		return out, status.value
 
 	def grow_ring(self, new_capacity):

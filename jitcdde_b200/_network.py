@@ -247,6 +247,35 @@ class jitcdde_network:
 			return result
 		return self._engine.adjust_diff(shift_ratio)
 
+	def step_on_discontinuities(self, *, propagations=1, min_distance=1e-5, max_distinct_delays=64):
+		"""as jitcdde.step_on_discontinuities (_jitcdde.py:935-999): adaptive steps that end exactly where the initial discontinuity
+		arrives through the delays (and their sums, `propagations` times). Sensible for networks with FEW distinct delays (the
+		number of steps grows like their number to the power of `propagations`); for heterogeneous delays use integrate_blindly or
+		adjust_diff, as examples/kuramoto_network.py does."""
+		from ._jitcdde import _propagate_delays
+		self._initiate()
+		if self.world > 1 and self._exchange != "peer":
+			raise NotImplementedError("step_on_discontinuities with several ranks needs the peer exchange (exchange='peer').")
+		assert min_distance > 0, "min_distance must be positive."
+		assert isinstance(propagations, int), "Non-integer number of propagations."
+		delays = [float(d) for d in np.unique(self._tau)]
+		if len(delays) > max_distinct_delays:
+			raise ValueError(f"{len(delays)} distinct delays: stepping on all discontinuities is not sensible; use integrate_blindly or adjust_diff.")
+		delays.append(0.0)
+		steps = _propagate_delays(delays, propagations, min_distance)
+		steps.sort()
+		steps.remove(0)
+		if not steps:
+			self.adjust_diff()
+			return self._engine.recent_state(self.t, current_only=True)
+		out = None
+		for step in steps:
+			out, status = self._engine.step_to(self._engine.poll()[1]+step)
+			while self._grow(status):
+				out, status = self._engine.resume()
+			self._raise(status)
+		return out
+
 	def jump(self, amplitude, time, width=1e-5, forward=True):
 		"""as jitcdde.jump (_jitcdde.py:935-974): adds `amplitude` (a number or one per node) to the state over the interval
 		(time, time+width) — or (time−width, time) with forward=False —, for a time on the last segment of the history (usually

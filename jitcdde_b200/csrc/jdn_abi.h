@@ -34,6 +34,7 @@
 
 #define JDN_MODE_ADAPTIVE 0   /* integrate: adaptive steps until t >= target */
 #define JDN_MODE_BLIND    1   /* integrate_blindly: `remaining` fixed steps of length h */
+#define JDN_MODE_CAPPED   3   /* step_on_discontinuities (_jitcdde.py:985-997): adaptive steps, each capped at the distance to the target */
 #define JDN_MODE_CONTINUE 2   /* jdde_net_begin only: go on with the call that stopped because the ring was full (after jdde_net_grow_ring) */
 
 typedef struct jdn_control

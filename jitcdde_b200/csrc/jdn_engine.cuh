@@ -270,6 +270,17 @@ JDN_FN bool pws_allows_increase(jdn_control & C, double const new_dt)
 	return false;
 }
 
+/* length of the next first pass of try_single_step: dt (integrate, _jitcdde.py:831), min(dt, target − t) (step_on_discontinuities,
+ * :993), the fixed step (integrate_blindly) */
+JDN_FN double next_length(jdn_control const & C)
+{
+	if (C.mode == JDN_MODE_BLIND)
+		return C.h;
+	if (C.mode == JDN_MODE_CAPPED)
+		return fmin(C.dt, C.target-C.t);
+	return C.dt;
+}
+
 /* the time of the anchor after `current` becomes that of the attempt just made (it stays the last anchor) */
 JDN_FN void keep_tentative(jdn_problem const & P, jdn_control & C)
 {
@@ -309,7 +320,7 @@ JDN_FN void control(jdn_problem const & P)
 	}
 
 	bool accept = true;
-	if (C.mode == JDN_MODE_ADAPTIVE)
+	if (C.mode != JDN_MODE_BLIND)
 	{
 		bool shrink = false;      /* dt /= pws_factor and a rejected attempt */
 		if (C.pws_pass == 0)
@@ -423,8 +434,7 @@ JDN_FN void control(jdn_problem const & P)
 			return;
 		}
 	}
-	if (C.mode == JDN_MODE_ADAPTIVE)
-		C.h = C.dt;
+	C.h = next_length(C);
 }
 
 /* The reference's anchor list is unbounded; the ring is not. A call that stopped with JDDE_STATUS_OVERFLOW goes on after the
@@ -444,8 +454,7 @@ JDN_FN void continue_call(jdn_control & C)
 	C.pws_bits = 0;
 	C.diff_bits = 0;
 	C.done = 0;
-	if (C.mode == JDN_MODE_ADAPTIVE)
-		C.h = C.dt;
+	C.h = next_length(C);
 }
 
 /* copy the live anchors of node i into a ring of another capacity */

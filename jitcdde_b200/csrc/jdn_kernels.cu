@@ -785,7 +785,7 @@ extern "C" __global__ void jdn_k_begin(jdn_problem const P, int const mode, doub
 	}
 	else
 	{
-		C.h = C.dt;
+		C.h = jdn::next_length(C);      /* dt, or min(dt, target − t) for step_on_discontinuities */
 		C.done = !(C.t < target);
 		if (C.done)
 			jdn::forget(P, C);

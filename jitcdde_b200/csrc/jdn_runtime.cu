@@ -570,6 +570,18 @@ int jdde_net_integrate(jdde_net * h, double target, double * out_state, int32_t 
 	return JDDE_OK;
 }
 
+/* one step of step_on_discontinuities (_jitcdde.py:985-997): adaptive steps, each capped at the distance to the target */
+int jdde_net_step_to(jdde_net * h, double target, double * out_state, int32_t * status)
+{
+	int rc = jdde_net_begin(h, JDN_MODE_CAPPED, target, 0.0, 0);
+	if (rc) return rc;
+	if ((rc = run_until_done(h))) return rc;
+	if (status) *status = h->host_ctrl.status;
+	if (h->host_ctrl.status == JDDE_STATUS_OK)
+		return jdde_net_recent_state(h, target, 0, out_state);
+	return JDDE_OK;
+}
+
 /* integrate_blindly (_jitcdde.py:880-933); step <= 0 means max_step */
 int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double * out_state, int32_t * status)
 {

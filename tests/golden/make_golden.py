@@ -362,6 +362,32 @@ def golden_network_jump():
 		minima_2=extrema_2[0], maxima_2=extrema_2[1], t_2=t_2, third=third, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
 
 
+def two_delay_graph(n=24, seed=6):
+	"""in-degree 2, delays drawn from {0.7, 1.3}: few distinct delays, the case step_on_discontinuities is meant for"""
+	rng = np.random.default_rng(seed)
+	dst = np.repeat(np.arange(n, dtype=np.int64), 2)
+	src = rng.integers(0, n, 2*n)
+	tau = rng.choice([0.7, 1.3], 2*n)
+	return dict(n=n, src=src, dst=dst, edge_tau=tau, weight=0.4, omega=rng.uniform(0.8, 1.2, n), initial=rng.uniform(0, 2*np.pi, n))
+
+
+def golden_network_discontinuities():
+	"""step_on_discontinuities (two propagations) for a network with two distinct delays, then an adaptive integration — by the
+	reference's C core under the controller of oracle/controller.py"""
+	g = two_delay_graph()
+	core = _reference_network_core(g, "ref_network_disc")
+	roots = roots_from(oracle.build(systems.program(systems.mackey_glass())))
+	C = controller.Controller(core, 1.3, root_mode=1, roots=roots, rtol=0, atol=1e-6)
+	steps = controller.discontinuity_steps([0.7, 1.3], propagations=2)
+	after = C.step_on_discontinuities(steps)
+	t_after = C.t
+	times = t_after + np.arange(0.5, 4.5, 0.5)
+	samples = np.array([C.integrate(T) for T in times])
+	print(f"network_discontinuities: steps {steps}, accepted {C.accepted}, rejected {C.rejected}")
+	save("network_discontinuities", src=g["src"], dst=g["dst"], edge_tau=g["edge_tau"], weight=g["weight"], omega=g["omega"], initial=g["initial"],
+		steps=np.array(steps), after=after, t_after=t_after, times=times, samples=samples, accepted=C.accepted, rejected=C.rejected, final_t=C.t)
+
+
 def golden_data_input():
 	"""the extended system and joined past that jitcdde_input hands to the core (reference: _jitcdde.py:1519-1659)"""
 	prog, past, max_delay = systems.data_input_program()
@@ -448,6 +474,7 @@ if __name__ == "__main__":
 	makers = dict(roessler=golden_roessler, mg_ensemble=golden_mg_ensemble, neutral=golden_neutral, state_dependent=golden_state_dependent,
 		ode=golden_ode, kuramoto=golden_kuramoto, lyap=golden_lyap, data_input=golden_data_input, projected=golden_projected, network=golden_network, network_pws=golden_network_pws,
 		network_adjust_diff=golden_network_adjust_diff, network_saturated=golden_network_saturated,
-		network_hub=golden_network_hub, network_jump=golden_network_jump)
+		network_hub=golden_network_hub, network_jump=golden_network_jump,
+		network_discontinuities=golden_network_discontinuities)
 	for name in sys.argv[1:] or makers:      # optional arguments: only these fixtures
 		makers[name]()

@@ -120,7 +120,7 @@ int jdde_net_begin(jdde_net * h, int32_t mode, double target, double step, int64
 	if (C.status != JDDE_STATUS_OK) { C.done = 1; return JDDE_OK; }
 	C.mode = mode; C.target = target; C.commit_slot = -1; C.pws = 0; C.p_bits = 0; C.pws_bits = C.diff_bits = 0; C.pws_pass = 0;
 	if (mode == JDN_MODE_BLIND) { C.h = step; C.remaining = steps; C.done = steps <= 0; }
-	else { C.h = C.dt; C.done = !(C.t < target); if (C.done) jdn::forget(h->P, C); }
+	else { C.h = jdn::next_length(C); C.done = !(C.t < target); if (C.done) jdn::forget(h->P, C); }
 	C.last_start = C.t;
 	h->launches++;
 	return JDDE_OK;
@@ -306,6 +306,15 @@ int jdde_net_jump(jdde_net * h, const double * amplitude, double time, double wi
 int jdde_net_jump_begin(jdde_net * h, const double *, double, double, int32_t) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
 int jdde_net_adjust_diff_begin(jdde_net * h, double) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
 int jdde_net_adjust_diff_end(jdde_net * h, double *, double *) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
+
+int jdde_net_step_to(jdde_net * h, double target, double * out, int32_t * status)
+{
+	if (int rc = jdde_net_begin(h, JDN_MODE_CAPPED, target, 0.0, 0)) return rc;
+	if (int rc = run(h)) return rc;
+	if (status) *status = h->ctrl.status;
+	if (h->ctrl.status == JDDE_STATUS_OK) return jdde_net_recent_state(h, target, 0, out);
+	return JDDE_OK;
+}
 
 int jdde_net_resume(jdde_net * h, double * out, int32_t * status)
 {

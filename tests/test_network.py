@@ -240,6 +240,33 @@ def test_network_jump_against_reference_core(twin):
 	check_network_jump(*run_network_jump_golden())
 
 
+def run_network_discontinuities_golden(**kw):
+	"""tests/golden/network_discontinuities.npz (reference core): step_on_discontinuities with two propagations, then integrate"""
+	from jitcdde_b200 import jitcdde_network
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "network_discontinuities.npz"))
+	net = jitcdde_network(len(g["omega"]), local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=float(g["weight"]), node_parameters=[g["omega"]], verbose=False, verification=True, **kw)
+	net.set_integration_parameters(rtol=0, atol=1e-6)
+	net.constant_past(g["initial"], time=0.0)
+	after = net.step_on_discontinuities(propagations=2)
+	t_after = net.t
+	samples = np.array([net.integrate(T) for T in g["times"]])
+	return g, after, t_after, samples, net.counters(), net.t
+
+
+def check_network_discontinuities(g, after, t_after, samples, counters, t_end):
+	assert np.array_equal(after, g["after"]) and t_after == float(g["t_after"])
+	assert np.array_equal(samples, g["samples"])
+	assert (counters[0], counters[1]) == (int(g["accepted"]), int(g["rejected"]))
+	assert t_end == float(g["final_t"])
+
+
+def test_network_step_on_discontinuities_against_reference_core(twin):
+	"""step_on_discontinuities (_jitcdde.py:935-999) for a network with two distinct delays: adaptive steps capped at the times at
+	which the initial discontinuity arrives (two propagations: 0.7, 1.3, 1.4, 2.0, 2.6 after each other, as the reference adds them up)"""
+	check_network_discontinuities(*run_network_discontinuities_golden())
+
+
 def test_node_partition_exchange_protocol(twin):
 	"""Two engine instances, each owning half of the nodes (what two ranks hold), driven through the per-attempt
 	protocol attempt → exchange staged slices + max of the error norm → control: same trajectory as one instance."""

@@ -322,6 +322,11 @@ int jdde_net_integrate_blindly(jdde_net * h, double target, double step, double 
  * the distance to it; otherwise as jdde_net_integrate (status, ring growth and jdde_net_resume included) */
 int jdde_net_step_to(jdde_net * h, double target, double * out_state, int32_t * status);
 int jdde_net_recent_state(jdde_net * h, double t, int32_t current_only, double * out_state);
+
+/* get_state (_jitcdde.py:357-371): the live anchors in order, for a checkpoint or for switching integrators (they are what
+ * jdde_net_set_past takes). *count = their number; with times == NULL nothing else happens; otherwise times [count],
+ * states and diffs [count][n] are filled (capacity = anchors the arrays have room for). */
+int jdde_net_get_history(jdde_net * h, int32_t * count, double * times, double * states, double * diffs, int32_t capacity);
 /* The reference's history is an unbounded list (jitced_template.c:56-73); when the ring is full, a call ends with status
  * JDDE_STATUS_OVERFLOW. jdde_net_grow_ring moves the live anchors into a larger ring (a power of two) and jdde_net_resume
  * continues the call exactly where it stopped (with several GPUs: on every rank; jdde_net_begin(h, 2, …) is the

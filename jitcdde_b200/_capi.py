@@ -122,6 +122,7 @@ SIGNATURES.update({
 	"jdde_net_grow_ring": (ctypes.c_int, [_H, ctypes.c_int32]),
 	"jdde_net_resume": (ctypes.c_int, [_H, c_double_p, c_int32_p]),
 	"jdde_net_step_to": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_int32_p]),
+	"jdde_net_get_history": (ctypes.c_int, [_H, c_int32_p, c_double_p, c_double_p, c_double_p, ctypes.c_int32]),
 	"jdde_net_adjust_diff": (ctypes.c_int, [_H, ctypes.c_double, c_double_p, c_double_p]),
 	"jdde_net_adjust_diff_begin": (ctypes.c_int, [_H, ctypes.c_double]),
 	"jdde_net_jump": (ctypes.c_int, [_H, c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_int32, c_double_p, c_double_p]),
@@ -604,6 +605,15 @@ class NetEngine:
 		status = ctypes.c_int32()
 		self._check(self.lib.jdde_net_integrate_blindly(self._h, float(target), float(step or 0.0), _dp(out), ctypes.byref(status)))
 		return out, status.value
+
+	def get_history(self):
+		"""the live anchors in order: (times [k], states [k, n], diffs [k, n])"""
+		count = ctypes.c_int32()
+		self._check(self.lib.jdde_net_get_history(self._h, ctypes.byref(count), None, None, None, 0))
+		k = count.value
+		times, states, diffs = np.empty(k), np.empty((k, self.n)), np.empty((k, self.n))
+		self._check(self.lib.jdde_net_get_history(self._h, ctypes.byref(count), _dp(times), _dp(states), _dp(diffs), k))
+		return times, states, diffs
 
 	def step_to(self, target):
 		"""adaptive steps capped at the target (one entry of the step list of step_on_discontinuities); returns (state, status)"""

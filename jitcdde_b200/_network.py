@@ -95,6 +95,20 @@ class jitcdde_network:
 		self._past = [(time-1.0, state, np.zeros_like(state)), (float(time), state, np.zeros_like(state))]
 		self._drop()
 
+	def add_past_points(self, anchors):
+		"""anchors: (time, state, derivative) triples, e.g. what get_state returned (reference: _jitcdde.py:298-309)"""
+		for time, state, derivative in anchors:
+			self._past.append((float(time), np.array(state, dtype=float), np.array(derivative, dtype=float)))
+		self._past.sort(key=lambda a: a[0])
+		self._drop()
+
+	def get_state(self):
+		"""as jitcdde.get_state (_jitcdde.py:357-371): all anchors the integration still needs, as (time, state, derivative)
+		triples — a checkpoint: hand them to add_past_points of a new jitcdde_network (and its step size, `dt`, to first_step)."""
+		self._initiate()
+		times, states, diffs = self._engine.get_history()
+		return [(float(times[k]), states[k].copy(), diffs[k].copy()) for k in range(len(times))]
+
 	def _drop(self):
 		if self._engine is not None:
 			self._engine.close()

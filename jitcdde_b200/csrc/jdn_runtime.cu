@@ -767,6 +767,49 @@ int jdde_net_get_dt(jdde_net * h, double * dt)
 	return JDDE_OK;
 }
 
+/*
+ * get_state (_jitcdde.py:357-371; the reference forgets first, then hands out all anchors): the live anchors first … current in
+ * order — checkpoint / resume, switching integrators. A first call with times == nullptr only reports their number. No kernel:
+ * the groups of four ring slots that hold live anchors are copied to the host one at a time and unpacked there.
+ */
+int jdde_net_get_history(jdde_net * h, int32_t * count, double * times, double * states, double * diffs, int32_t capacity)
+{
+	int rc = nready_run(h);
+	if (rc) return rc;
+	if ((rc = jdde_net_poll(h, nullptr, nullptr, nullptr))) return rc;
+	jdn_control const & c = h->host_ctrl;
+	int const live = c.current-c.first+1;
+	if (count) *count = live;
+	if (!times) return JDDE_OK;
+	if (!states || !diffs) return nfail(h, JDDE_E_INVALID, "null argument");
+	if (capacity < live) return nfail(h, JDDE_E_INVALID, "room for fewer anchors than there are (ask for their number first)");
+	size_t const n = (size_t)h->desc.n;
+	int const mask = h->P.cap-1;
+	int const group_slots = 1 << JDN_ROW_GROUP_LOG2;
+	std::vector<double> ring_times((size_t)h->P.cap), group(2*n*(size_t)group_slots);
+	JN_CUDA(h, cudaMemcpyAsync(ring_times.data(), h->P.times, ring_times.size()*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	JN_CUDA(h, cudaStreamSynchronize(h->stream));
+	int loaded = -1;
+	for (int k = 0; k < live; k++)
+	{
+		int const slot = (c.first+k) & mask;
+		times[k] = ring_times[(size_t)slot];
+		if ((slot >> JDN_ROW_GROUP_LOG2) != loaded)
+		{
+			loaded = slot >> JDN_ROW_GROUP_LOG2;
+			JN_CUDA(h, cudaMemcpyAsync(group.data(), h->P.hist + 2*jdn_pair_index(loaded << JDN_ROW_GROUP_LOG2, 0, (long long)n), group.size()*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+			JN_CUDA(h, cudaStreamSynchronize(h->stream));
+		}
+		size_t const within = (size_t)(slot & (group_slots-1));
+		for (size_t i = 0; i < n; i++)
+		{
+			states[(size_t)k*n+i] = group[2*(i*group_slots+within)];
+			diffs[(size_t)k*n+i] = group[2*(i*group_slots+within)+1];
+		}
+	}
+	return JDDE_OK;
+}
+
 int jdde_net_exchange_pointers(jdde_net * h, uint64_t * stage, uint64_t * p_bits)
 {
 	if (!h) return JDDE_E_INVALID;

@@ -307,6 +307,27 @@ int jdde_net_jump_begin(jdde_net * h, const double *, double, double, int32_t) {
 int jdde_net_adjust_diff_begin(jdde_net * h, double) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
 int jdde_net_adjust_diff_end(jdde_net * h, double *, double *) { return fail(h, JDDE_E_INVALID, "host twin: one rank only"); }
 
+int jdde_net_get_history(jdde_net * h, int32_t * count, double * times, double * states, double * diffs, int32_t capacity)
+{
+	jdn_control const & C = h->ctrl;
+	int const live = C.current-C.first+1;
+	if (count) *count = live;
+	if (!times) return JDDE_OK;
+	if (capacity < live) return fail(h, JDDE_E_INVALID, "room for fewer anchors than there are");
+	size_t const n = (size_t)h->desc.n;
+	for (int k = 0; k < live; k++)
+	{
+		int const slot = (C.first+k) & (h->P.cap-1);
+		times[k] = h->times[(size_t)slot];
+		for (size_t i = 0; i < n; i++)
+		{
+			states[(size_t)k*n+i] = h->hist[2*jdn_pair_index(slot, (long long)i, (long long)n)];
+			diffs[(size_t)k*n+i] = h->hist[2*jdn_pair_index(slot, (long long)i, (long long)n)+1];
+		}
+	}
+	return JDDE_OK;
+}
+
 int jdde_net_step_to(jdde_net * h, double target, double * out, int32_t * status)
 {
 	if (int rc = jdde_net_begin(h, JDN_MODE_CAPPED, target, 0.0, 0)) return rc;

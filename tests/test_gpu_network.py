@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import sympy
 
-from tests.test_network import check_network_discontinuities, check_network_jump, kuramoto_graph, run_network, run_network_adjust_diff_golden, run_network_discontinuities_golden, run_network_golden, run_network_hub_golden, run_network_jump_golden, run_network_pws_golden, run_network_saturated_golden, run_symbolic
+from tests.test_network import check_network_discontinuities, check_network_jump, checkpoint_round_trip, kuramoto_graph, run_network, run_network_adjust_diff_golden, run_network_discontinuities_golden, run_network_golden, run_network_hub_golden, run_network_jump_golden, run_network_pws_golden, run_network_saturated_golden, run_symbolic
 
 pytestmark = pytest.mark.gpu
 
@@ -81,6 +81,11 @@ def test_network_past_within_step_on_gpu():
 def test_network_step_on_discontinuities_on_gpu():
 	"""step_on_discontinuities for a network with two distinct delays (tests/golden/network_discontinuities.npz, reference core)"""
 	check_network_discontinuities(*run_network_discontinuities_golden())
+
+
+def test_network_checkpoint_and_resume_on_gpu():
+	"""get_state (the live anchors, unpacked from the ring on the host) → add_past_points of a new network → the same trajectory"""
+	checkpoint_round_trip()
 
 
 def test_network_jump_on_gpu():

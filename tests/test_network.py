@@ -267,6 +267,35 @@ def test_network_step_on_discontinuities_against_reference_core(twin):
 	check_network_discontinuities(*run_network_discontinuities_golden())
 
 
+def checkpoint_round_trip(**kw):
+	"""integrate, take the state (get_state), start a NEW network from it with the step size the first one had reached, go on with
+	both: the same trajectory, bit for bit (reference: get_state / add_past_points, _jitcdde.py:298-309, 357-371;
+	examples/mackey_glass_parameter_jump.py:55-57 switches integrators this way)"""
+	from jitcdde_b200 import jitcdde_network
+	g = kuramoto_graph(12)
+	make = lambda: jitcdde_network(g["n"], local=lambda y, t, w: w, coupling=lambda yd, y: sympy.sin(yd-y),
+		edges=(g["src"], g["dst"], g["edge_tau"]), weight=g["weight"], node_parameters=[g["omega"]], verbose=False, **kw)
+	blind_to = float(np.max(g["edge_tau"]))
+	net = make()
+	net.set_integration_parameters(rtol=0, atol=1e-6)
+	net.constant_past(g["initial"], time=0.0)
+	net.integrate_blindly(blind_to, 0.1)
+	net.integrate(blind_to+2.0)
+	anchors, dt = net.get_state(), net.dt
+	assert anchors[-1][0] == net.t and anchors[-1][0]-anchors[0][0] >= blind_to      # the whole delay window is there
+	assert all(a[0] < b[0] for a, b in zip(anchors, anchors[1:]))
+	resumed = make()
+	resumed.set_integration_parameters(rtol=0, atol=1e-6, first_step=dt)
+	resumed.add_past_points(anchors)
+	targets = blind_to+np.array([2.5, 3.0, 4.0])
+	assert np.array_equal(np.array([resumed.integrate(T) for T in targets]), np.array([net.integrate(T) for T in targets]))
+	assert resumed.t == net.t
+
+
+def test_network_checkpoint_and_resume(twin):
+	checkpoint_round_trip()
+
+
 def test_node_partition_exchange_protocol(twin):
 	"""Two engine instances, each owning half of the nodes (what two ranks hold), driven through the per-attempt
 	protocol attempt → exchange staged slices + max of the error norm → control: same trajectory as one instance."""

@@ -174,7 +174,7 @@ extern "C" __global__ void jdn_k_exchange(jdn_problem const P)
  * of the arrival counters. The controller state is read afresh after every barrier.
  */
 /* -DJDN_PROFILE (JITCDDE_B200_NET_FLAGS): thread 0 of block 0 adds up the time it spends in each phase of an attempt and
- * prints the sums at the end of the launch (scripts/gpu_net_phases.py) — a measuring aid, not compiled otherwise */
+ * prints the sums at the end of the launch (scripts/gpu_net_phases.sh) — a measuring aid, not compiled otherwise */
 #if defined(JDN_PROFILE)
 #define JDN_PHASE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long now_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)); jdn_phase_ns[k] += now_-jdn_phase_last; jdn_phase_last = now_; } } while (0)
 #define JDN_PHASE_STATE unsigned long long jdn_phase_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0}, jdn_phase_last = 0; int jdn_phase_attempts = 0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(jdn_phase_last))

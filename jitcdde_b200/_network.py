@@ -6,13 +6,17 @@
 The reference expresses such systems through its symbolic API, one expression per node with literal delays
 (/root/reference/examples/kuramoto_network.py:42-63); that path exists here too (`jitcdde`) and is what this
 class is tested against on small networks, but it cannot be code-generated for 10^6 nodes (hard
-part 7). Method names and semantics follow `jitcdde`: constant_past / add_past_point, set_integration_parameters,
-integrate_blindly, integrate, t.
+part 7). Method names and semantics follow `jitcdde`: constant_past / add_past_point(s) / get_state,
+set_integration_parameters, step_on_discontinuities / adjust_diff / integrate_blindly, integrate, jump, t, dt. Delays shorter
+than the step are handled as by the reference (past-within-step repetitions, _jitcdde.py:838-861).
 
-Multi-GPU: launched with one process per GPU (torch.distributed initialised, NCCL), the nodes are partitioned
-into contiguous blocks; every rank keeps the whole history, integrates its block and, after every attempted step,
-the ranks all-gather the staged anchor slices over NVLink and max-reduce the error norm, so that all take the
-same accept/reject decision. Without torch.distributed the whole network runs on one GPU.
+On one GPU an integrate call is a handful of launches of a persistent cooperative kernel (csrc/jdn_kernels.cu: jdn_k_run).
+Multi-GPU: launched with one process per GPU (torch.distributed initialised), the nodes are partitioned into contiguous
+blocks; every rank keeps the whole history, integrates its block and, in every attempted step, pushes its part of the new
+anchor into the peers' memory over NVLink from inside the step kernel; the ranks merge the error norm and meet in a
+device-side barrier, so that all take the same accept/reject decision (exchange="peer", the default; SURVEY.md §8e,
+DESIGN.md §5). exchange="nccl" instead all-gathers the staged anchor slices and max-reduces the error norm between an
+attempt kernel and a control kernel. Without torch.distributed the whole network runs on one GPU.
 """
 
 from warnings import warn
